@@ -1,0 +1,232 @@
+/*
+ * jlama_b200.h -- C ABI of libjlama_b200.so, the Blackwell (sm_100a) back-end for
+ * tjake/Jlama's quantized forward pass.
+ *
+ * This is the drop-in boundary: plain C types only (pointers, ints, sizes), the
+ * conventions jextract/Panama-FFI binds (the reference's existing natives:
+ * jlama-native/src/main/c/simd/vector_simd.h:22-39 and
+ * jlama-native/src/main/c/gpu/vector_gpu.h:7-19).  Each entry point cites the
+ * reference interface it replaces.  Reference paths are relative to
+ * /root/reference; "core/" = jlama-core/src/main/java/com/github/tjake/jlama/,
+ * "native/java/" = jlama-native/src/main/java/com/github/tjake/jlama/tensor/operations/.
+ *
+ * Conventions
+ *  - every function returns int status (JL_OK or a negative JL_ERR_*) or an
+ *    int64 handle with -1 = failure (vector_gpu.h:10-15 convention).  Nothing
+ *    aborts the process (the reference GPU natives call exit(),
+ *    vector_gpu.c:96,116 -- deliberately not reproduced).
+ *  - there is no CPU fallback: with no usable sm_100 device jl_init fails.
+ *  - thread-safe: calls on one jl_ctx are serialised internally; model calls
+ *    run on the model's own stream.
+ *  - dtype codes: Jlama DType (core/safetensors/DType.java) subset.
+ */
+#ifndef JLAMA_B200_H
+#define JLAMA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JL_OK 0
+#define JL_ERR_INVALID (-1)     /* IllegalArgumentException analogue (Guava Preconditions in the reference) */
+#define JL_ERR_CUDA (-2)        /* CUDA runtime error; see jl_last_error */
+#define JL_ERR_OOM (-3)         /* device memory exhausted (NativeGPUTensorOperations.java:145-150 "limitReached") */
+#define JL_ERR_UNSUPPORTED (-4) /* UnsupportedOperationException analogue (TestOperations.java:140 relies on it) */
+#define JL_ERR_NCCL (-5)
+
+/* dtypes */
+#define JL_F32 0
+#define JL_BF16 1
+#define JL_Q4 2 /* core/tensor/Q4ByteBufferTensor.java:34-259: 32-element blocks, byte j = q[j] | q[j+16]<<4, separate f32 scales [rows, cols/32] */
+#define JL_I8 3 /* core/tensor/Q8ByteBufferTensor.java:37-223: int8 + f32 scale per 32 */
+
+typedef struct jl_ctx jl_ctx;
+typedef struct jl_model jl_model;
+
+/* ---- lifecycle: replaces init_gpu (vector_gpu.h:7, vector_gpu.c:227-239) -------------- */
+/* info[0]=free bytes, [1]=total bytes, [2]=SM count, [3]=compute capability*10 (100 for B200). */
+int jl_init(int device, jl_ctx **out, int64_t *info /* nullable, int64[4] */);
+int jl_shutdown(jl_ctx *ctx);
+const char *jl_last_error(jl_ctx *ctx); /* never NULL */
+const char *jl_version(void);
+int jl_sync(jl_ctx *ctx);
+/* number of kernels this library launched since jl_init (bench.py's gpu_launches claim) */
+int64_t jl_kernel_launches(jl_ctx *ctx);
+
+/* ---- TensorOperations.registerModelTensor (core/tensor/operations/TensorOperations.java:39;
+ *      NativeGPUTensorOperations.java:104-151 -> register_tensor, vector_gpu.h:10) ------------
+ * Copies a weight (and its Q4/I8 block scales) to HBM once; returns a tensor id, -1 on failure.
+ * `rows` x `cols` is the logical shape; Q4 data is rows*cols/2 bytes, scales rows*cols/32 floats.
+ * Unlike the reference (int size => < 2 GiB) sizes are 64-bit. */
+int64_t jl_register_tensor(jl_ctx *ctx, int dtype, int64_t rows, int64_t cols, const void *data, const float *scales);
+int jl_unregister_tensor(jl_ctx *ctx, int64_t id);
+
+/* ---- TensorOperations.batchDotProduct (TensorOperations.java:62-72) with a registered B ----
+ * Drop-in for gpu_gemm (vector_gpu.h:17) / gemm_q8_q4, gemm_f32_q4, gemm_f32, gemm_f32_bf16
+ * (vector_simd.h:22-39).  A and R are HOST buffers (the Java MemorySegments):
+ *   r[ldc*i + j - roffset] = sum_{t<k} A[i, a_col_off+t] * B[j, b_col_off+t],  i in [0,m), j in [n0,n0+n)
+ * a_dtype in {JL_F32, JL_BF16, JL_I8}; for JL_I8 `a_scales` are the Q8 block scales [m, lda/32]
+ * (produced by jl_quantize_q8 or by Jlama itself).  lda/ldc in elements.
+ * Offsets follow NativeSimdTensorOperations.java:96-107 (roffset is subtracted from the output index,
+ * vector_simd.c:344). */
+int jl_gemm(jl_ctx *ctx, int a_dtype, const void *a, const float *a_scales, int a_col_off, int lda, int64_t b_id,
+            int b_col_off, float *r, int roffset, int m, int n0, int n, int k, int ldc);
+/* dotProductBatchChunk (TensorOperations.java:86-99; gemm_*_batch, vector_simd.h:24-39): one A, several B/R. */
+int jl_gemm_batch(jl_ctx *ctx, int batch_num, int a_dtype, const void *a, const float *a_scales, int a_col_off, int lda,
+                  const int64_t *b_ids, int b_col_off, float *const *r, int roffset, int m, int n0, int n, int k,
+                  int ldc);
+/* batchDotProduct where B is a HOST tensor too (attention scores against a KV page held by Java,
+ * CausalSelfAttention.java:324-330).  b_dtype in {JL_F32, JL_BF16}. */
+int jl_gemm_host(jl_ctx *ctx, int a_dtype, const void *a, int a_col_off, int lda, int b_dtype, const void *b,
+                 int b_col_off, int ldb, float *r, int roffset, int m, int n0, int n, int k, int ldc);
+
+/* ---- remaining TensorOperations methods on HOST f32 buffers (TensorOperations.java:101-149) ----
+ * All run as CUDA kernels (upload, kernel, read back); there is no CPU path. */
+/* a[r, off:off+len] += b[(r or 0), off:off+len]; b_dtype in {JL_F32, JL_BF16, JL_Q4 (+b_scales)}
+ * (PanamaTensorOperations.java:2151-2325) */
+int jl_accumulate(jl_ctx *ctx, float *a, int a_rows, int lda, int b_dtype, const void *b, const float *b_scales,
+                  int b_rows, int ldb, int offset, int length);
+/* a *= b (PanamaTensorOperations.java:2062-2097) */
+int jl_maccumulate(jl_ctx *ctx, float *a, int a_rows, int lda, const float *b, int b_rows, int ldb, int offset,
+                   int length);
+/* x[r, off:off+len] *= factor (PanamaTensorOperations.java:2474-2514) */
+int jl_scale(jl_ctx *ctx, float factor, float *x, int rows, int ldx, int offset, int length);
+/* y[yoff+i] += alpha * x[xoff+i] (PanamaTensorOperations.java:2567-2611) */
+int jl_saxpy(jl_ctx *ctx, float alpha, const float *x, float *y, int xoffset, int yoffset, int limit);
+/* y[0, yoff+i] += sum_r alpha[aoff+r] * x[xrow+r, xoff+i]  (TensorOperations.java:122-137,
+ * PanamaTensorOperations.java:2614-2698) */
+int jl_saxpy_batch(jl_ctx *ctx, const float *alpha, const float *x, int ldx, float *y, int xoffset, int yoffset,
+                   int limit, int a_offset, int x_row_offset, int batch);
+/* quantize(t, I8, offset, length) (TensorOperations.java:145-149; PanamaTensorOperations.java:1684-1774):
+ * d = max/127, q = (byte)(x*(127/max) + 0.5f) truncating; writes q[rows, ldx] (only [offset, offset+length))
+ * and scales[rows, ldx/32]. */
+int jl_quantize_q8(jl_ctx *ctx, const float *x, int rows, int ldx, int offset, int length, int8_t *q, float *scales);
+/* quantize(t, BF16, ...) : FloatConversions.float32ToBFloat16 RNE (core/math/FloatConversions.java:35-61) */
+int jl_quantize_bf16(jl_ctx *ctx, const float *x, int rows, int ldx, int offset, int length, uint16_t *out);
+/* AbstractTensor.quantize(Q4) weight quantiser on the GPU (Q4ByteBufferTensor.java:66-120);
+ * byte-identical to the reference's files. */
+int jl_quantize_q4_weights(jl_ctx *ctx, const float *x, int64_t rows, int64_t cols, uint8_t *q, float *scales);
+
+/* ---- layer-level fused entry points on HOST buffers --------------------------------------
+ * The reference does these as scalar Java loops outside TensorOperations (SURVEY 7 "hard parts");
+ * a device-resident layer subclass calls them instead. */
+/* RMSNorm.forward (core/model/RMSNorm.java:34-56) */
+int jl_rmsnorm(jl_ctx *ctx, const float *x, int rows, int ldx, int w_dtype, const void *w, float weight_adjustment,
+               float eps, int embedding_length, int offset, int length, float *out);
+/* VectorMath.softMax (core/math/VectorMath.java:69-90) */
+int jl_softmax(jl_ctx *ctx, float *x, int offset, int length);
+/* MLPBlock activation loop + maccumulate (core/model/MLPBlock.java:132-141): gate = silu(gate) * up */
+int jl_silu_mul(jl_ctx *ctx, float *gate, const float *up, int rows, int ld, int offset, int length);
+/* VectorMath.precomputeFreqsCis (core/math/VectorMath.java:148-165): out[end*dim/2][2] (cos,sin).
+ * Host-side double libm, identical recipe to the reference. */
+int jl_precompute_freqs_cis(int dim, int end, double theta, double scaling_factor, float *out);
+
+/* ---- DistributedContext / KvBufferCache host logic (pure functions) -----------------------
+ * core/model/DistributedContext.java:60-98 */
+typedef struct {
+    int embeddingSegmentStart, embeddingSegmentLength;
+    int attentionSegmentStart, attentionSegmentLength;
+    int hiddenSegmentStart, hiddenSegmentLength;
+    int kvSegmentStart, kvSegmentLength;
+    int headStart, headEnd, groupHeadStart, groupHeadEnd;
+    int numberOfLayers, layerStart, layerEnd;
+} jl_dctx;
+int jl_dctx_build(int embedding_length, int attention_length, int hidden_length, int head_size, int head_group_size,
+                  int num_layers, int model_shard, int num_model_shards, int layer_shard, int num_layer_shards,
+                  jl_dctx *out);
+/* KvBufferCache.computePageSize (core/tensor/KvBufferCache.java:224-280) */
+int jl_kv_page_geometry(int num_layers, int context_length, int kv_segment_length, int dtype_size,
+                        int64_t max_page_bytes, int *layers_per_page, int *ctx_per_page);
+
+/* ---- device-resident model: AbstractModel / LlamaModel mirror -----------------------------
+ * core/model/AbstractModel.java:100-183,295-329,443-491,516-646; core/model/llama/LlamaModel.java:68-184.
+ * The host driver (C++) replays generate()'s exact call sequence with every layer op as a CUDA
+ * kernel on device-resident activations, paged KV in HBM, CUDA-graphed decode. */
+typedef struct {
+    int context_length, embedding_length, hidden_length;
+    int num_heads, num_kv_heads, num_layers, vocab_size, head_size;
+    float layer_norm_eps;
+    double rope_theta;   /* LlamaConfig.java:27-57 */
+    double rope_scaling; /* only rope_type "linear" is honoured by the reference (:55-56) */
+    int working_qtype;   /* JL_I8 (default, Q8 activations), JL_F32, JL_BF16 (AbstractModel.java:119-176) */
+    int kv_dtype;        /* JL_F32 (reference default workingDType) or JL_BF16 */
+    int max_batch;       /* jlama.max_batch_size, 256 (AbstractModel.java:57,304) */
+    int max_sessions;    /* concurrent KvBuffers (KvBufferCache.java:58-60) */
+    int max_context;     /* positions to reserve pages for (<= context_length); 0 = context_length */
+    int tp_rank, tp_size; /* jlama-net model shard (DistributedContext modelShard/numModelShards) */
+    int prefill_tensor_core; /* 1: M>=64 GEMMs use the tcgen05 BF16 path; 0: exact-integer SIMT path */
+    int flags;           /* JL_MODEL_* */
+} jl_model_config;
+
+#define JL_MODEL_NO_GRAPH 1 /* launch decode kernels eagerly instead of through a CUDA graph */
+#define JL_MODEL_NO_PDL 2   /* disable programmatic dependent launch between decode kernels */
+
+/* tensor slots */
+#define JL_T_EMBED 0
+#define JL_T_OUT_NORM 1
+#define JL_T_LM_HEAD 2
+#define JL_L_ATTN_NORM 0
+#define JL_L_Q 1
+#define JL_L_K 2
+#define JL_L_V 3
+#define JL_L_O 4
+#define JL_L_FFN_NORM 5
+#define JL_L_GATE 6
+#define JL_L_DOWN 7
+#define JL_L_UP 8
+
+int jl_model_create(jl_ctx *ctx, const jl_model_config *cfg, jl_model **out);
+/* layer < 0: global slot (JL_T_*); else per-layer slot (JL_L_*).  The tensor must already hold this
+ * rank's shard (rows for q/k/v/gate/up, columns for o/down: LlamaModel.java:120-133,
+ * Weights.getLoadOffsets core/safetensors/Weights.java:99-117). */
+int jl_model_set_tensor(jl_model *m, int layer, int slot, int64_t tensor_id);
+/* allocate scratch + KV page pool, build RoPE table, capture graphs */
+int jl_model_finalize(jl_model *m);
+int jl_model_free(jl_model *m);
+/* KvBuffer lifecycle (KvBufferCache.getKvBuffer / close) */
+int jl_model_reset_session(jl_model *m, int session);
+/* AbstractModel.batchForward (:295-312): prompt tokens (HOST int32) in chunks of max_batch. */
+int jl_model_batch_forward(jl_model *m, int session, const int32_t *tokens, int n, int start_pos);
+/* AbstractModel.sample (:443-491) on the last forwarded row of `session`: final norm, lm_head, argmax
+ * (temperature 0) or softmax sampling with `uniform`.  logits_out (HOST, [vocab]) may be NULL. */
+int jl_model_sample(jl_model *m, int session, float temperature, float uniform, int32_t *token_out, float *logits_out);
+/* One decode step for `n` sessions at once (the reference's "batch" = concurrent sessions):
+ * forward(token_i, position_i) + sample at temperature 0, one CUDA-graph launch.
+ * tokens/positions/next_tokens are HOST int32[n]; logits_out HOST [n, vocab] or NULL. */
+int jl_model_decode(jl_model *m, int n, const int32_t *sessions, const int32_t *tokens, const int32_t *positions,
+                    int32_t *next_tokens, float *logits_out);
+/* AbstractModel.generate (:516-646) at temperature 0 over token ids: returns n_new tokens (the first is
+ * sampled from the prompt's last row).  timings_ms (nullable double[2]) = {prompt, generate} wall ms like
+ * Generator.Response.  logits_out HOST [n_new, vocab] or NULL. */
+int jl_model_generate(jl_model *m, int session, const int32_t *prompt, int n_prompt, int n_new, int32_t *out_tokens,
+                      float *logits_out, double *timings_ms);
+/* device-side decode loop without per-token host round trips: feeds each step's argmax into the next
+ * step on the GPU (tokens stay in HBM); copies the n_new tokens back at the end.  Used for `value`
+ * in bench.py (inputs resident in HBM). */
+int jl_model_decode_resident(jl_model *m, int session, int32_t first_token, int start_pos, int n_new,
+                             int32_t *out_tokens);
+/* test hooks: copy a K/V row (f32) or the hidden rows of the last batch_forward chunk to HOST */
+int jl_model_read_kv(jl_model *m, int session, int layer, int position, int which /*0=K,1=V*/, float *out);
+int jl_model_read_hidden(jl_model *m, int session, float *out /* [embedding_length] last row */);
+/* per-token algorithmic bytes of the decode weight stream on this rank (roofline numerator) */
+int64_t jl_model_weight_bytes(jl_model *m);
+/* event-timed duration (ms) of the last jl_model_decode / decode_resident GPU work, and of its
+ * dominant kernel class (the quantised GEMV), measured with CUDA events on the model stream */
+int jl_model_last_timing(jl_model *m, double *total_ms, double *gemv_ms);
+
+/* ---- jlama-net replacement: NCCL over NVLink instead of gRPC -------------------------------
+ * JlamaService.combine (jlama-net/src/main/java/com/github/tjake/jlama/net/grpc/JlamaService.java:300-359)
+ * == all-reduce SUM of [M,E] f32.  One process per GPU; rank 0 creates the id, the launcher
+ * (torch.distributed / any store) broadcasts it. */
+int jl_comm_unique_id(jl_ctx *ctx, uint8_t *id128 /* 128 bytes */);
+int jl_comm_init(jl_ctx *ctx, const uint8_t *id128, int rank, int world);
+/* HOST-buffer all-reduce for tests of the collective itself */
+int jl_comm_allreduce_f32(jl_ctx *ctx, float *host_buf, int64_t count);
+int jl_comm_destroy(jl_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JLAMA_B200_H */

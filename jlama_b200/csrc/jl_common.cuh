@@ -1,0 +1,232 @@
+// Internal declarations shared by the translation units of libjlama_b200.so.
+// sm_100a only.  No torch types anywhere in this library.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/jlama_b200.h"
+
+#define QBLOCK 32
+
+struct DevTensor {
+    int dtype = 0;
+    int64_t rows = 0, cols = 0;
+    void *data = nullptr;    // f32 / bf16 / packed nibbles / int8
+    float *scales = nullptr; // [rows, cols/32] for Q4 / I8
+    size_t bytes = 0;
+};
+
+struct jl_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr; // op-level API stream
+    std::mutex mu;
+    std::string last_error;
+    std::unordered_map<int64_t, DevTensor> tensors;
+    int64_t next_id = 1;
+    long long launches = 0;
+    // op-level scratch (grown on demand)
+    void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_bytes[4] = {0, 0, 0, 0};
+    // comm
+    void *nccl_comm = nullptr;
+    int rank = 0, world = 1;
+};
+
+int jl_set_error(jl_ctx *ctx, int code, const char *fmt, ...);
+#define JL_CUDA_CHECK(ctx, expr)                                                                      \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess)                                                                        \
+            return jl_set_error(ctx, _e == cudaErrorMemoryAllocation ? JL_ERR_OOM : JL_ERR_CUDA,      \
+                                "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+void *jl_scratch(jl_ctx *ctx, int slot, size_t bytes); // nullptr on OOM
+
+// ---------------------------------------------------------------------------------------------
+// Quantised GEMV / small-M GEMM (jl_gemv.cu)
+// ---------------------------------------------------------------------------------------------
+enum GemvPrologue {
+    PRO_Q8_GLOBAL = 0,  // activations already int8 + scales in global memory
+    PRO_F32_QUANT,      // f32 activations -> Q8 (PanamaTensorOperations.quantizeQ8 semantics) in the prologue
+    PRO_RMSNORM_QUANT,  // f32 hidden row -> RMSNorm (RMSNorm.java:34-56) -> Q8
+    PRO_F32,            // f32 activations used as-is (F32 x W path)
+    PRO_RMSNORM_F32,    // RMSNorm then f32 activations
+    PRO_BF16_GLOBAL,    // bf16 activations in global -> f32
+};
+enum GemvEpilogue {
+    EPI_STORE = 0,    // out[m, out_off + row] = acc
+    EPI_ADD_RESIDUAL, // out[m, row] = acc + residual[m, row]
+    EPI_SILU_MUL,     // seg0 = gate, seg1 = up: out[m,row] = silu(g) * u   (MLPBlock.java:132-141)
+};
+
+struct GemvSeg {
+    const void *w;       // weight rows, leading dim = ldw elements
+    const float *ws;     // block scales (Q4/I8) with leading dim ldw/32
+    float *out;          // f32 output [M, out_ld]
+    int rows;            // rows in this segment
+    int out_ld;
+    int out_off;         // added to the row index on store (already includes -roffset)
+};
+
+struct GemvParams {
+    GemvSeg seg[3];
+    int nseg;
+    int w_dtype;             // JL_Q4 / JL_I8 / JL_BF16 / JL_F32
+    int ldw;                 // weight leading dimension in elements
+    int w_col_off;           // first weight column (elements, multiple of 32 for quantised)
+    int K;                   // reduction length
+    int M;                   // activation rows (1..GEMV_MAX_M)
+    // activations
+    const void *a;           // f32 / int8 / bf16 [M, lda]
+    const float *a_scales;   // for PRO_Q8_GLOBAL: [M, lda/32]
+    int lda;
+    int a_col_off;
+    // norm prologue
+    const void *norm_w;      // f32 or bf16 [E]
+    int norm_w_dtype;
+    float norm_adj, norm_eps;
+    int norm_E;
+    // epilogue
+    const float *residual;   // [M, res_ld]
+    int res_ld;
+    int row0;                // first global row handled by this launch (n0)
+    int total_rows;          // rows handled by this launch
+};
+
+#define GEMV_MAX_M 8
+
+// Launch on `stream`.  use_pdl: launch with the programmatic-stream-serialization attribute.
+int jl_launch_gemv(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int prologue, int epilogue, bool use_pdl);
+
+// ---------------------------------------------------------------------------------------------
+// Element-wise / normalisation / sampling kernels (jl_elementwise.cu)
+// ---------------------------------------------------------------------------------------------
+int jl_launch_accumulate(jl_ctx *ctx, cudaStream_t s, float *a, int a_rows, int lda, int b_dtype, const void *b,
+                         const float *b_scales, int b_rows, int ldb, int offset, int length);
+int jl_launch_maccumulate(jl_ctx *ctx, cudaStream_t s, float *a, int a_rows, int lda, const float *b, int b_rows, int ldb,
+                          int offset, int length);
+int jl_launch_scale(jl_ctx *ctx, cudaStream_t s, float f, float *x, int rows, int ldx, int offset, int length);
+int jl_launch_saxpy_batch(jl_ctx *ctx, cudaStream_t s, const float *alpha, const float *x, int ldx, float *y, int xoffset,
+                          int yoffset, int limit, int a_offset, int x_row_offset, int batch);
+int jl_launch_quantize_q8(jl_ctx *ctx, cudaStream_t s, const float *x, int rows, int ldx, int offset, int length,
+                          int8_t *q, float *scales);
+int jl_launch_quantize_bf16(jl_ctx *ctx, cudaStream_t s, const float *x, int rows, int ldx, int offset, int length,
+                            uint16_t *out);
+int jl_launch_quantize_q4w(jl_ctx *ctx, cudaStream_t s, const float *x, int64_t rows, int64_t cols, uint8_t *q,
+                           float *scales);
+int jl_launch_rmsnorm(jl_ctx *ctx, cudaStream_t s, const float *x, int rows, int ldx, int w_dtype, const void *w, float adj,
+                      float eps, int E, int offset, int length, float *out);
+int jl_launch_softmax(jl_ctx *ctx, cudaStream_t s, float *x, int offset, int length);
+int jl_launch_silu_mul(jl_ctx *ctx, cudaStream_t s, float *gate, const float *up, int rows, int ld, int offset, int length);
+// embedding rows -> f32 hidden (LlamaModel.java:68-100); tokens on device
+int jl_launch_embed(jl_ctx *ctx, cudaStream_t s, const DevTensor &wte, const int32_t *tokens, int n, float *out, int E);
+// argmax with strict '>' (lowest index wins; AbstractModel.java:455-469): two-stage
+int jl_launch_argmax(jl_ctx *ctx, cudaStream_t s, const float *logits, int rows, int vocab, int ld, int32_t *out_tokens,
+                     void *scratch);
+size_t jl_argmax_scratch_bytes(int rows);
+
+// ---------------------------------------------------------------------------------------------
+// Attention over the paged KV cache (jl_attention.cu)
+// ---------------------------------------------------------------------------------------------
+struct KvLayout {
+    // Page = [layers_per_page, 2, ctx_per_page, kv_len] (KvBufferCache.java:102); page table per session.
+    int layers_per_page, ctx_per_page, kv_len; // kv_len = this rank's kvSegmentLength
+    int n_ctx_pages;                            // page-table stride per (session, layer_page)
+    int n_layer_pages;
+    int kv_dtype;                               // JL_F32 or JL_BF16
+    void *const *page_table;                    // device: [sessions][n_layer_pages][n_ctx_pages] -> page base
+};
+
+struct AttnParams {
+    KvLayout kv;
+    int layer;
+    int heads, kv_heads, head_size; // this rank's heads
+    int head0_global;               // first global head on this rank (for the RoPE table quirk)
+    int kv_head0_global;
+    const float *q;  // [rows, q_ld]  raw projections (pre-RoPE)
+    const float *k;  // [rows, kv_ld]
+    const float *v;  // [rows, kv_ld]
+    int q_ld, kv_ld;
+    float *out;      // [rows, q_ld] attention output (this rank's heads)
+    const float *rope; // [(positions) * hs/2][2]
+    int rows;                  // query rows in this launch
+    const int32_t *sessions;   // device [rows] session of each row
+    const int32_t *positions;  // device [rows] absolute position of each row
+    float scale;
+    // split-K workspace
+    float *ws;       // [rows, heads, splits, hs + 2]
+    int splits;
+};
+
+// Writes rotated K and V of every row into the pages and rotates q in place (CausalSelfAttention.java:199-311).
+int jl_launch_rope_kv_append(jl_ctx *ctx, cudaStream_t s, const AttnParams &p, float *q_inplace, bool use_pdl);
+// Causal attention of each row against positions [0, pos] of its session (CausalSelfAttention.java:314-356).
+int jl_launch_paged_attention(jl_ctx *ctx, cudaStream_t s, const AttnParams &p, int max_pos, bool use_pdl);
+
+// ---------------------------------------------------------------------------------------------
+// Larger-M GEMM paths for prefill (jl_gemm.cu)
+// ---------------------------------------------------------------------------------------------
+// C[M,N] (+epilogue) = A[M,K] * W[N,K]^T for M > GEMV_MAX_M.  exact integer (dp4a) SIMT path for
+// Q8-activation x Q4, FMA path for f32 activations.
+int jl_launch_gemm_simt(jl_ctx *ctx, cudaStream_t s, const GemvParams &p, int prologue_kind, int epilogue);
+
+// ---------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ uint4 ldg_nc_u4(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ldg_nc_f32(const float *p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+__device__ __forceinline__ float bf16_bits_to_f32(uint16_t b) { return __uint_as_float(((uint32_t)b) << 16); }
+
+// jafama-equivalent activation in double, cast to float (ActivationFunction.java:29-37)
+__device__ __forceinline__ float silu_ref(float x) { return (float)((double)x * (1.0 / (1.0 + exp(-(double)x)))); }
+
+template <typename K, typename... Args>
+static inline cudaError_t jl_launch_kernel(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                                           Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}

@@ -1,0 +1,530 @@
+// Block-quantised GEMV / small-M GEMM for decode:  out[m, n] = sum_k A[m,k] * W[n,k]
+//
+// Replaces, for M <= 8, the reference's batchDotProduct back-ends
+//   I8 x Q4  : PanamaTensorOperations.java:768-1044 (GemmerI8Q4_512), vector_simd.c:261-437
+//   F32 x Q4 : PanamaTensorOperations.java:289-548, vector_simd.c:770-964
+// and the WebGPU GEMV native/res/gemm_i8q4_v5.wgsl:57-137, and fuses the scalar Java loops that
+// surround them in the decode step: RMSNorm (RMSNorm.java:34-56), the Q8 activation quantiser
+// (PanamaTensorOperations.java:1684-1723), the residual add (TransformerBlock.java:185,203) and
+// SiLU*up (MLPBlock.java:132-141).
+//
+// HBM-bound by design: every weight byte is read exactly once with 128-bit coalesced
+// ld.global.nc loads straight into registers (one 16-byte Q4 block per lane, 512 B per warp
+// request), activations are staged once per CTA in shared memory in a bank-conflict-free
+// [half][block][16B] layout, integer dot products use dp4a, the reduction is a warp shuffle.
+// The first weight chunk of every warp is requested BEFORE griddepcontrol.wait, so with
+// programmatic dependent launch the weight stream of kernel N+1 is already in flight while
+// kernel N drains (the activations are the only true dependency).
+#include "jl_common.cuh"
+
+#define GEMV_THREADS 256
+#define GEMV_WARPS 8
+#define CH 4 // 32-element blocks per lane per chunk
+
+struct GemvSmem {
+    // offsets into dynamic shared memory, computed identically on host and device
+    int nblk;  // K/32
+    int M;
+};
+
+template <int WDT>
+struct WBuf {
+    uint4 q[CH * (WDT == JL_I8 ? 2 : 1)];
+    float s[CH];
+};
+
+// Which weight row does item-row `row` (index within the launch) map to?
+__device__ __forceinline__ void seg_lookup(const GemvParams &p, int row, int &seg, int &local) {
+    seg = 0;
+    local = row;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        if (seg == i && i + 1 < p.nseg && local >= p.seg[i].rows) {
+            local -= p.seg[i].rows;
+            seg = i + 1;
+        }
+    }
+}
+
+template <int WDT>
+__device__ __forceinline__ void load_chunk(WBuf<WDT> &b, const uint8_t *wrow, const float *srow, int blk0, int nblk,
+                                           int lane) {
+#pragma unroll
+    for (int j = 0; j < CH; j++) {
+        int bi = blk0 + j * 32 + lane;
+        if (bi < nblk) {
+            if (WDT == JL_Q4) {
+                b.q[j] = ldg_nc_u4(wrow + (size_t)bi * 16);
+            } else {
+                b.q[2 * j] = ldg_nc_u4(wrow + (size_t)bi * 32);
+                b.q[2 * j + 1] = ldg_nc_u4(wrow + (size_t)bi * 32 + 16);
+            }
+            b.s[j] = ldg_nc_f32(srow + bi);
+        }
+    }
+}
+
+// ---- activation staging -------------------------------------------------------------------------
+// Q8 layout in smem:  q[m][half][blk][16] int8, then sc[m][blk] f32, then sum[m][blk] int32
+// F32 layout in smem: f[m][c4(8)][blk][4] floats
+__device__ __forceinline__ size_t q8_bytes_per_row(int nblk) { return (size_t)nblk * 32 + (size_t)nblk * 8; }
+
+template <bool ACTQ8, int MM>
+__device__ void stage_activations(const GemvParams &p, int prologue, unsigned char *smem, int nblk) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ double red[GEMV_WARPS];
+    __shared__ float rs_sh;
+    int8_t *aq = (int8_t *)smem;
+    float *asc = (float *)(smem + (size_t)MM * nblk * 32);
+    int *asum = (int *)(smem + (size_t)MM * nblk * 32 + (size_t)MM * nblk * 4);
+    float *af = (float *)smem;
+    const int K = p.K;
+
+    for (int m = 0; m < MM; m++) {
+        const bool live = m < p.M;
+        float rsf = 1.0f;
+        const bool norm = (prologue == PRO_RMSNORM_QUANT || prologue == PRO_RMSNORM_F32);
+        const float *x = (const float *)p.a + (size_t)m * p.lda + p.a_col_off;
+        if (norm && live) {
+            // RMSNorm.java:41-52: float products summed in double over [0, E)
+            double ss = 0.0;
+            for (int i = tid; i < K; i += GEMV_THREADS) {
+                float v = x[i];
+                ss += (double)__fmul_rn(v, v);
+            }
+            ss = warp_sum_d(ss);
+            if (lane == 0) red[warp] = ss;
+            __syncthreads();
+            if (tid == 0) {
+                double t = 0;
+                for (int w = 0; w < GEMV_WARPS; w++) t += red[w];
+                t /= (double)p.norm_E;
+                t += (double)p.norm_eps;
+                rs_sh = (float)(1.0 / sqrt(t));
+            }
+            __syncthreads();
+            rsf = rs_sh;
+        }
+        // one warp per 32-element block
+        for (int b = warp; b < nblk; b += GEMV_WARPS) {
+            float v = 0.0f;
+            if (live) {
+                if (prologue == PRO_Q8_GLOBAL) {
+                    int8_t qv = ((const int8_t *)p.a)[(size_t)m * p.lda + p.a_col_off + b * 32 + lane];
+                    int s = __reduce_add_sync(0xffffffffu, (int)qv);
+                    aq[(((size_t)m * 2 + (lane >> 4)) * nblk + b) * 16 + (lane & 15)] = qv;
+                    if (lane == 0) {
+                        asc[m * nblk + b] = p.a_scales[(size_t)m * (p.lda / 32) + p.a_col_off / 32 + b];
+                        asum[m * nblk + b] = s;
+                    }
+                    continue;
+                }
+                if (prologue == PRO_BF16_GLOBAL)
+                    v = bf16_bits_to_f32(((const uint16_t *)p.a)[(size_t)m * p.lda + p.a_col_off + b * 32 + lane]);
+                else
+                    v = x[b * 32 + lane];
+                if (norm) {
+                    int col = b * 32 + lane;
+                    float w = p.norm_w_dtype == JL_BF16 ? bf16_bits_to_f32(((const uint16_t *)p.norm_w)[col])
+                                                        : ((const float *)p.norm_w)[col];
+                    v = __fmul_rn(__fadd_rn(p.norm_adj, w), __fmul_rn(rsf, v));
+                }
+            }
+            if (ACTQ8) {
+                // PanamaTensorOperations.java:1696-1710
+                float mx = warp_max(fabsf(v));
+                float d = __fdiv_rn(mx, 127.0f);
+                float id = mx != 0.0f ? __fdiv_rn(127.0f, mx) : 0.0f;
+                int qi = (int)__fadd_rn(__fmul_rn(v, id), 0.5f); // F2B truncation toward zero
+                int8_t qv = (int8_t)qi;
+                int s = __reduce_add_sync(0xffffffffu, (int)qv);
+                aq[(((size_t)m * 2 + (lane >> 4)) * nblk + b) * 16 + (lane & 15)] = qv;
+                if (lane == 0) {
+                    asc[m * nblk + b] = d;
+                    asum[m * nblk + b] = s;
+                }
+            } else {
+                af[(((size_t)m * 8 + (lane >> 2)) * nblk + b) * 4 + (lane & 3)] = v;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// ---- per-chunk math -------------------------------------------------------------------------------
+template <int WDT, bool ACTQ8, int MM>
+__device__ __forceinline__ void compute_chunk(const WBuf<WDT> &w, float (&acc)[MM], const unsigned char *smem, int blk0,
+                                              int nblk, int lane) {
+    const int8_t *aq = (const int8_t *)smem;
+    const float *asc = (const float *)(smem + (size_t)MM * nblk * 32);
+    const int *asum = (const int *)(smem + (size_t)MM * nblk * 32 + (size_t)MM * nblk * 4);
+    const float *af = (const float *)smem;
+#pragma unroll
+    for (int j = 0; j < CH; j++) {
+        int bi = blk0 + j * 32 + lane;
+        if (bi >= nblk) continue;
+        const float sb = w.s[j];
+        if (ACTQ8) {
+#pragma unroll
+            for (int m = 0; m < MM; m++) {
+                const uint4 alo = *(const uint4 *)(aq + (((size_t)m * 2 + 0) * nblk + bi) * 16);
+                const uint4 ahi = *(const uint4 *)(aq + (((size_t)m * 2 + 1) * nblk + bi) * 16);
+                int s = 0;
+                if (WDT == JL_Q4) {
+                    const uint4 q = w.q[j];
+                    s = __dp4a((int)(q.x & 0x0F0F0F0Fu), (int)alo.x, s);
+                    s = __dp4a((int)((q.x >> 4) & 0x0F0F0F0Fu), (int)ahi.x, s);
+                    s = __dp4a((int)(q.y & 0x0F0F0F0Fu), (int)alo.y, s);
+                    s = __dp4a((int)((q.y >> 4) & 0x0F0F0F0Fu), (int)ahi.y, s);
+                    s = __dp4a((int)(q.z & 0x0F0F0F0Fu), (int)alo.z, s);
+                    s = __dp4a((int)((q.z >> 4) & 0x0F0F0F0Fu), (int)ahi.z, s);
+                    s = __dp4a((int)(q.w & 0x0F0F0F0Fu), (int)alo.w, s);
+                    s = __dp4a((int)((q.w >> 4) & 0x0F0F0F0Fu), (int)ahi.w, s);
+                    s -= 8 * asum[m * nblk + bi]; // sum a*(nib-8) = sum a*nib - 8*sum a   (exact)
+                } else {
+                    const uint4 q0 = w.q[2 * j], q1 = w.q[2 * j + 1];
+                    s = __dp4a((int)q0.x, (int)alo.x, s);
+                    s = __dp4a((int)q0.y, (int)alo.y, s);
+                    s = __dp4a((int)q0.z, (int)alo.z, s);
+                    s = __dp4a((int)q0.w, (int)alo.w, s);
+                    s = __dp4a((int)q1.x, (int)ahi.x, s);
+                    s = __dp4a((int)q1.y, (int)ahi.y, s);
+                    s = __dp4a((int)q1.z, (int)ahi.z, s);
+                    s = __dp4a((int)q1.w, (int)ahi.w, s);
+                }
+                // acc += (sa*sb) * isum   (vector_simd.c:384-420)
+                acc[m] = fmaf(__fmul_rn(asc[m * nblk + bi], sb), (float)s, acc[m]);
+            }
+        } else {
+            // F32 activations: acc += sb * sum_j a_j * (w_j)   with w_j = nib-8 (Q4) or int8 (I8)
+            float wf[32];
+            if (WDT == JL_Q4) {
+                const uint4 q = w.q[j];
+                const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t lo = qw[i] & 0x0F0F0F0Fu, hi = (qw[i] >> 4) & 0x0F0F0F0Fu;
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        // byte t -> float(2^23 + nib) via PRMT, minus (2^23 + 8)
+                        wf[i * 4 + t] = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7540 | t)) - 8388616.0f;
+                        wf[16 + i * 4 + t] = __uint_as_float(__byte_perm(hi, 0x4B000000u, 0x7540 | t)) - 8388616.0f;
+                    }
+                }
+            } else {
+                const uint4 q0 = w.q[2 * j], q1 = w.q[2 * j + 1];
+                const uint32_t qw[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+#pragma unroll
+                    for (int t = 0; t < 4; t++) wf[i * 4 + t] = (float)(int)(int8_t)((qw[i] >> (8 * t)) & 0xFF);
+            }
+#pragma unroll
+            for (int m = 0; m < MM; m++) {
+                float part = 0.0f;
+#pragma unroll
+                for (int c4 = 0; c4 < 8; c4++) {
+                    const float4 a4 = *(const float4 *)(af + (((size_t)m * 8 + c4) * nblk + bi) * 4);
+                    part = fmaf(a4.x, wf[c4 * 4 + 0], part);
+                    part = fmaf(a4.y, wf[c4 * 4 + 1], part);
+                    part = fmaf(a4.z, wf[c4 * 4 + 2], part);
+                    part = fmaf(a4.w, wf[c4 * 4 + 3], part);
+                }
+                acc[m] = fmaf(sb, part, acc[m]);
+            }
+        }
+    }
+}
+
+template <int WDT, bool ACTQ8, int EPI, int MM>
+__global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvParams p, const int prologue) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nblk = p.K / 32;
+    const int nchunks = (nblk + 32 * CH - 1) / (32 * CH);
+    constexpr int NW = (EPI == EPI_SILU_MUL) ? 2 : 1; // weight rows per output row
+    const int wbytes_per_blk = (WDT == JL_Q4) ? 16 : 32;
+
+    // balanced static partition of output rows over all warps of the grid
+    const long long gw = (long long)blockIdx.x * GEMV_WARPS + warp;
+    const long long tw = (long long)gridDim.x * GEMV_WARPS;
+    const int r0 = (int)(((long long)p.total_rows * gw) / tw);
+    const int r1 = (int)(((long long)p.total_rows * (gw + 1)) / tw);
+
+    // item iterator: (row r, weight-row wr, chunk c)
+    int r = r0, wr = 0, c = 0;
+    auto row_ptrs = [&](int rr, int wrr, const uint8_t *&wrow, const float *&srow) {
+        int seg, local;
+        if (EPI == EPI_SILU_MUL) {
+            seg = wrr;
+            local = rr;
+        } else {
+            seg_lookup(p, rr, seg, local);
+        }
+        const GemvSeg &sg = p.seg[seg];
+        const size_t grow = (size_t)(p.row0 + local);
+        wrow = (const uint8_t *)sg.w + (grow * (size_t)(p.ldw / 32) + (size_t)(p.w_col_off / 32)) * wbytes_per_blk;
+        srow = sg.ws + grow * (size_t)(p.ldw / 32) + (size_t)(p.w_col_off / 32);
+    };
+    auto advance = [&](int &rr, int &wrr, int &cc) {
+        if (++cc == nchunks) {
+            cc = 0;
+            if (++wrr == NW) {
+                wrr = 0;
+                ++rr;
+            }
+        }
+    };
+
+    WBuf<WDT> buf0, buf1;
+    const uint8_t *wrow;
+    const float *srow;
+    if (r < r1) {
+        row_ptrs(r, wr, wrow, srow);
+        load_chunk<WDT>(buf0, wrow, srow, c * 32 * CH, nblk, lane);
+    }
+    // weights are in flight; let the next kernel in the stream start its own prefetch
+    pdl_launch_dependents();
+    // activations are produced by the previous kernel
+    pdl_wait();
+    stage_activations<ACTQ8, MM>(p, prologue, smem, nblk);
+
+    float acc[MM];
+    float gate[MM];
+#pragma unroll
+    for (int m = 0; m < MM; m++) acc[m] = 0.0f, gate[m] = 0.0f;
+
+    auto finish_row = [&](int rr, int wrr) {
+#pragma unroll
+        for (int m = 0; m < MM; m++) acc[m] = warp_sum(acc[m]);
+        if (EPI == EPI_SILU_MUL && wrr == 0) {
+#pragma unroll
+            for (int m = 0; m < MM; m++) gate[m] = acc[m], acc[m] = 0.0f;
+            return;
+        }
+        if (lane == 0) {
+            int seg = 0, local = rr;
+            if (EPI != EPI_SILU_MUL) seg_lookup(p, rr, seg, local);
+            const GemvSeg &sg = p.seg[seg];
+            const int col = p.row0 + local + sg.out_off;
+#pragma unroll
+            for (int m = 0; m < MM; m++) {
+                if (m < p.M) {
+                    float v = acc[m];
+                    if (EPI == EPI_ADD_RESIDUAL) v = __fadd_rn(v, p.residual[(size_t)m * p.res_ld + (p.row0 + local)]);
+                    if (EPI == EPI_SILU_MUL) v = __fmul_rn(silu_ref(gate[m]), v);
+                    sg.out[(size_t)m * sg.out_ld + col] = v;
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < MM; m++) acc[m] = 0.0f;
+    };
+
+    while (r < r1) {
+        int nr = r, nwr = wr, nc = c;
+        advance(nr, nwr, nc);
+        if (nr < r1) {
+            row_ptrs(nr, nwr, wrow, srow);
+            load_chunk<WDT>(buf1, wrow, srow, nc * 32 * CH, nblk, lane);
+        }
+        compute_chunk<WDT, ACTQ8, MM>(buf0, acc, smem, c * 32 * CH, nblk, lane);
+        if (c == nchunks - 1) finish_row(r, wr);
+        r = nr, wr = nwr, c = nc;
+        if (r >= r1) break;
+        advance(nr, nwr, nc);
+        if (nr < r1) {
+            row_ptrs(nr, nwr, wrow, srow);
+            load_chunk<WDT>(buf0, wrow, srow, nc * 32 * CH, nblk, lane);
+        }
+        compute_chunk<WDT, ACTQ8, MM>(buf1, acc, smem, c * 32 * CH, nblk, lane);
+        if (c == nchunks - 1) finish_row(r, wr);
+        r = nr, wr = nwr, c = nc;
+    }
+}
+
+// ---- dense (F32 / BF16 weights) GEMV: GemmerF32 / GemmerF32BF16 (PanamaTensorOperations.java:1046-1231,1466-1539)
+template <int WDT, int EPI, int MM>
+__global__ void __launch_bounds__(GEMV_THREADS) gemv_dense_kernel(const GemvParams p, const int prologue) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float *af = (float *)smem; // [MM][K]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ double red[GEMV_WARPS];
+    __shared__ float rs_sh;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int K = p.K;
+    for (int m = 0; m < MM; m++) {
+        const bool live = m < p.M;
+        float rsf = 1.0f;
+        const bool norm = (prologue == PRO_RMSNORM_F32);
+        const float *x = (const float *)p.a + (size_t)m * p.lda + p.a_col_off;
+        if (norm && live) {
+            double ss = 0.0;
+            for (int i = tid; i < K; i += GEMV_THREADS) {
+                float v = x[i];
+                ss += (double)__fmul_rn(v, v);
+            }
+            ss = warp_sum_d(ss);
+            if (lane == 0) red[warp] = ss;
+            __syncthreads();
+            if (tid == 0) {
+                double t = 0;
+                for (int w = 0; w < GEMV_WARPS; w++) t += red[w];
+                t /= (double)p.norm_E;
+                t += (double)p.norm_eps;
+                rs_sh = (float)(1.0 / sqrt(t));
+            }
+            __syncthreads();
+            rsf = rs_sh;
+        }
+        for (int i = tid; i < K; i += GEMV_THREADS) {
+            float v = 0.0f;
+            if (live) {
+                if (prologue == PRO_BF16_GLOBAL)
+                    v = bf16_bits_to_f32(((const uint16_t *)p.a)[(size_t)m * p.lda + p.a_col_off + i]);
+                else
+                    v = x[i];
+                if (norm) {
+                    float w = p.norm_w_dtype == JL_BF16 ? bf16_bits_to_f32(((const uint16_t *)p.norm_w)[i])
+                                                        : ((const float *)p.norm_w)[i];
+                    v = __fmul_rn(__fadd_rn(p.norm_adj, w), __fmul_rn(rsf, v));
+                }
+            }
+            af[(size_t)m * K + i] = v;
+        }
+    }
+    __syncthreads();
+    const long long gw = (long long)blockIdx.x * GEMV_WARPS + warp;
+    const long long tw = (long long)gridDim.x * GEMV_WARPS;
+    const int r0 = (int)(((long long)p.total_rows * gw) / tw);
+    const int r1 = (int)(((long long)p.total_rows * (gw + 1)) / tw);
+    for (int r = r0; r < r1; r++) {
+        int seg, local;
+        seg_lookup(p, r, seg, local);
+        const GemvSeg &sg = p.seg[seg];
+        const size_t grow = (size_t)(p.row0 + local);
+        float acc[MM];
+#pragma unroll
+        for (int m = 0; m < MM; m++) acc[m] = 0.0f;
+        if (WDT == JL_F32) {
+            const float *wrow = (const float *)sg.w + grow * (size_t)p.ldw + p.w_col_off;
+            for (int i = lane; i < K; i += 32) {
+                float w = ldg_nc_f32(wrow + i);
+#pragma unroll
+                for (int m = 0; m < MM; m++) acc[m] = fmaf(af[(size_t)m * K + i], w, acc[m]);
+            }
+        } else {
+            const uint16_t *wrow = (const uint16_t *)sg.w + grow * (size_t)p.ldw + p.w_col_off;
+            for (int i = lane; i < K; i += 32) {
+                float w = bf16_bits_to_f32(wrow[i]);
+#pragma unroll
+                for (int m = 0; m < MM; m++) acc[m] = fmaf(af[(size_t)m * K + i], w, acc[m]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < MM; m++) acc[m] = warp_sum(acc[m]);
+        if (lane == 0) {
+            const int col = p.row0 + local + sg.out_off;
+#pragma unroll
+            for (int m = 0; m < MM; m++)
+                if (m < p.M) {
+                    float v = acc[m];
+                    if (EPI == EPI_ADD_RESIDUAL) v = __fadd_rn(v, p.residual[(size_t)m * p.res_ld + (p.row0 + local)]);
+                    sg.out[(size_t)m * sg.out_ld + col] = v;
+                }
+        }
+    }
+}
+
+// ---- host launcher ---------------------------------------------------------------------------------
+template <int WDT, bool ACTQ8, int EPI, int MM>
+static int launch_q(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int prologue, bool pdl, int grid, size_t smem) {
+    auto kern = gemv_kernel<WDT, ACTQ8, EPI, MM>;
+    if (smem > 48 * 1024) {
+        static thread_local size_t configured = 0; // per-instantiation high-water mark
+        if (smem > configured) {
+            JL_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+    }
+    JL_CUDA_CHECK(ctx, jl_launch_kernel(kern, dim3(grid), dim3(GEMV_THREADS), smem, stream, pdl, p, prologue));
+    ctx->launches++;
+    return JL_OK;
+}
+
+template <int WDT, bool ACTQ8, int EPI>
+static int launch_m(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int prologue, bool pdl, int grid, size_t smem1) {
+    if (p.M <= 1) return launch_q<WDT, ACTQ8, EPI, 1>(ctx, stream, p, prologue, pdl, grid, smem1);
+    if (p.M <= 2) return launch_q<WDT, ACTQ8, EPI, 2>(ctx, stream, p, prologue, pdl, grid, smem1 * 2);
+    if (p.M <= 4) return launch_q<WDT, ACTQ8, EPI, 4>(ctx, stream, p, prologue, pdl, grid, smem1 * 4);
+    return launch_q<WDT, ACTQ8, EPI, 8>(ctx, stream, p, prologue, pdl, grid, smem1 * 8);
+}
+
+template <int WDT, bool ACTQ8>
+static int launch_e(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int prologue, int epi, bool pdl, int grid,
+                    size_t smem1) {
+    switch (epi) {
+        case EPI_STORE: return launch_m<WDT, ACTQ8, EPI_STORE>(ctx, stream, p, prologue, pdl, grid, smem1);
+        case EPI_ADD_RESIDUAL: return launch_m<WDT, ACTQ8, EPI_ADD_RESIDUAL>(ctx, stream, p, prologue, pdl, grid, smem1);
+        case EPI_SILU_MUL: return launch_m<WDT, ACTQ8, EPI_SILU_MUL>(ctx, stream, p, prologue, pdl, grid, smem1);
+    }
+    return jl_set_error(ctx, JL_ERR_INVALID, "bad epilogue %d", epi);
+}
+
+template <int WDT, int EPI, int MM>
+static int launch_dense(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int prologue, bool pdl, int grid) {
+    auto kern = gemv_dense_kernel<WDT, EPI, MM>;
+    size_t smem = (size_t)MM * p.K * 4;
+    if (smem > 200 * 1024) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "dense gemv: M*K too large for shared memory");
+    if (smem > 48 * 1024)
+        JL_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    JL_CUDA_CHECK(ctx, jl_launch_kernel(kern, dim3(grid), dim3(GEMV_THREADS), smem, stream, pdl, p, prologue));
+    ctx->launches++;
+    return JL_OK;
+}
+
+template <int WDT, int EPI>
+static int launch_dense_m(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int prologue, bool pdl, int grid) {
+    if (p.M <= 1) return launch_dense<WDT, EPI, 1>(ctx, stream, p, prologue, pdl, grid);
+    if (p.M <= 2) return launch_dense<WDT, EPI, 2>(ctx, stream, p, prologue, pdl, grid);
+    if (p.M <= 4) return launch_dense<WDT, EPI, 4>(ctx, stream, p, prologue, pdl, grid);
+    return launch_dense<WDT, EPI, 8>(ctx, stream, p, prologue, pdl, grid);
+}
+
+int jl_launch_gemv(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int prologue, int epilogue, bool use_pdl) {
+    if (p.M < 1 || p.M > GEMV_MAX_M) return jl_set_error(ctx, JL_ERR_INVALID, "gemv: M=%d out of range", p.M);
+    if (p.K <= 0 || p.total_rows <= 0) return jl_set_error(ctx, JL_ERR_INVALID, "gemv: empty problem");
+    const bool quant_w = (p.w_dtype == JL_Q4 || p.w_dtype == JL_I8);
+    const int rows = p.total_rows;
+    // grid: a multiple of the SM count; every warp gets >= 1 row when possible
+    int per_sm = rows >= ctx->sm_count * GEMV_WARPS * 4 ? 3 : (rows >= ctx->sm_count * GEMV_WARPS * 2 ? 2 : 1);
+    int grid = ctx->sm_count * per_sm;
+    int max_grid = (rows + GEMV_WARPS - 1) / GEMV_WARPS;
+    if (grid > max_grid) grid = max_grid;
+    if (grid < 1) grid = 1;
+
+    if (!quant_w) {
+        if (prologue != PRO_F32 && prologue != PRO_RMSNORM_F32 && prologue != PRO_BF16_GLOBAL)
+            return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "dense weights need f32/bf16 activations");
+        if (epilogue == EPI_SILU_MUL) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "dense silu epilogue");
+        if (p.w_dtype == JL_F32)
+            return epilogue == EPI_STORE ? launch_dense_m<JL_F32, EPI_STORE>(ctx, stream, p, prologue, use_pdl, grid)
+                                         : launch_dense_m<JL_F32, EPI_ADD_RESIDUAL>(ctx, stream, p, prologue, use_pdl, grid);
+        return epilogue == EPI_STORE ? launch_dense_m<JL_BF16, EPI_STORE>(ctx, stream, p, prologue, use_pdl, grid)
+                                     : launch_dense_m<JL_BF16, EPI_ADD_RESIDUAL>(ctx, stream, p, prologue, use_pdl, grid);
+    }
+    if ((p.K % 32) || (p.w_col_off % 32) || (p.ldw % 32))
+        return jl_set_error(ctx, JL_ERR_INVALID, "quantised gemv needs K, offsets and ld multiples of 32");
+    const bool actq8 = (prologue == PRO_Q8_GLOBAL || prologue == PRO_F32_QUANT || prologue == PRO_RMSNORM_QUANT);
+    const int nblk = p.K / 32;
+    const size_t smem1 = actq8 ? (size_t)nblk * 40 : (size_t)p.K * 4;
+    const int mm = p.M <= 1 ? 1 : (p.M <= 2 ? 2 : (p.M <= 4 ? 4 : 8));
+    if (smem1 * mm > 200 * 1024)
+        return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "gemv: activations (M=%d,K=%d) exceed shared memory", p.M, p.K);
+    if (p.w_dtype == JL_Q4)
+        return actq8 ? launch_e<JL_Q4, true>(ctx, stream, p, prologue, epilogue, use_pdl, grid, smem1)
+                     : launch_e<JL_Q4, false>(ctx, stream, p, prologue, epilogue, use_pdl, grid, smem1);
+    return actq8 ? launch_e<JL_I8, true>(ctx, stream, p, prologue, epilogue, use_pdl, grid, smem1)
+                 : launch_e<JL_I8, false>(ctx, stream, p, prologue, epilogue, use_pdl, grid, smem1);
+}

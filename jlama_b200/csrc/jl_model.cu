@@ -1,0 +1,808 @@
+// Device-resident host driver: the C++ mirror of AbstractModel / LlamaModel / TransformerBlock /
+// CausalSelfAttention / MLPBlock (core/model/AbstractModel.java:295-329,443-491,516-646;
+// core/model/llama/LlamaModel.java:68-184; core/model/TransformerBlock.java:158-215;
+// core/model/CausalSelfAttention.java:145-385; core/model/MLPBlock.java:106-166).
+// It replays generate()'s exact call sequence; every layer op is a CUDA kernel on activations that
+// never leave HBM, KV lives in device pages shaped like KvBufferCache's, and the per-token decode
+// step is captured once into a CUDA graph with programmatic dependent launch between kernels.
+#include "jl_common.cuh"
+
+#include <chrono>
+#include <map>
+#include <math.h>
+#include <string.h>
+
+int jl_comm_allreduce_dev(jl_ctx *ctx, cudaStream_t stream, float *buf, size_t count);
+
+struct jl_model {
+    jl_ctx *ctx = nullptr;
+    jl_model_config cfg;
+    jl_dctx d;
+    cudaStream_t stream = nullptr;
+    bool finalized = false;
+    DevTensor g[3];
+    bool g_set[3] = {false, false, false};
+    std::vector<DevTensor> l; // [layers][9]
+    std::vector<char> l_set;
+    int group = 1, attn_seg = 0, kv_seg = 0, h_seg = 0, heads_local = 0, kv_heads_local = 0;
+    // rope
+    float *rope = nullptr;
+    // KV pages
+    KvLayout kv;
+    void **page_table_dev = nullptr;
+    std::vector<void *> page_table_host;
+    size_t page_bytes = 0;
+    int max_context = 0;
+    // scratch
+    int maxB = 0;
+    float *x = nullptr, *xb = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *att = nullptr, *hbuf = nullptr,
+          *partial = nullptr, *logits = nullptr, *attn_ws = nullptr, *last_hidden = nullptr;
+    int max_splits = 32;
+    int32_t *d_tokens = nullptr, *d_positions = nullptr, *d_sessions = nullptr, *d_next = nullptr, *d_hist = nullptr,
+            *d_counter = nullptr;
+    void *argmax_scratch = nullptr;
+    int32_t *h_pinned = nullptr; // pinned staging: tokens | positions | sessions | next
+    int hist_cap = 0;
+    // graphs keyed by (n, splits, resident)
+    std::map<long long, cudaGraphExec_t> graphs;
+    // eager-mode event timing of the GEMV launches
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    double last_total_ms = 0, last_gemv_ms = 0;
+    bool timing_valid = false;
+    int64_t weight_bytes = 0;
+};
+
+#define M_CHECK(expr)                 \
+    do {                              \
+        int _rc = (expr);             \
+        if (_rc != JL_OK) return _rc; \
+    } while (0)
+
+static bool use_pdl(const jl_model *m) { return !(m->cfg.flags & JL_MODEL_NO_PDL); }
+static bool use_graph(const jl_model *m) { return !(m->cfg.flags & JL_MODEL_NO_GRAPH); }
+
+extern "C" int jl_model_create(jl_ctx *ctx, const jl_model_config *cfg, jl_model **out) {
+    if (!ctx || !cfg || !out) return JL_ERR_INVALID;
+    *out = nullptr;
+    const jl_model_config &c = *cfg;
+    if (c.embedding_length <= 0 || c.num_heads <= 0 || c.num_kv_heads <= 0 || c.num_layers <= 0 || c.vocab_size <= 0 ||
+        c.hidden_length <= 0 || c.context_length <= 0 || c.num_heads % c.num_kv_heads)
+        return jl_set_error(ctx, JL_ERR_INVALID, "model_create: bad config");
+    jl_model *m = new jl_model();
+    m->ctx = ctx;
+    m->cfg = c;
+    if (m->cfg.head_size <= 0) m->cfg.head_size = c.embedding_length / c.num_heads; // Config.java:254
+    if (m->cfg.max_batch <= 0) m->cfg.max_batch = 256;
+    if (m->cfg.max_sessions <= 0) m->cfg.max_sessions = 1;
+    if (m->cfg.tp_size <= 0) m->cfg.tp_size = 1;
+    if (m->cfg.rope_scaling == 0.0) m->cfg.rope_scaling = 1.0;
+    if (m->cfg.working_qtype != JL_I8 && m->cfg.working_qtype != JL_F32)
+        return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "model_create: working_qtype must be JL_I8 or JL_F32"), delete m, JL_ERR_UNSUPPORTED;
+    if (m->cfg.kv_dtype != JL_F32 && m->cfg.kv_dtype != JL_BF16)
+        return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "model_create: kv_dtype must be JL_F32 or JL_BF16"), delete m, JL_ERR_UNSUPPORTED;
+    const int hs = m->cfg.head_size;
+    m->group = c.num_heads / c.num_kv_heads;
+    // jlama-net limits model shards to the number of KV heads (JlamaService.java:65-68)
+    if (m->cfg.tp_size > c.num_kv_heads || c.num_kv_heads % m->cfg.tp_size)
+        return jl_set_error(ctx, JL_ERR_INVALID, "model_create: tp_size must divide num_kv_heads"), delete m, JL_ERR_INVALID;
+    int rc = jl_dctx_build(c.embedding_length, c.num_heads * hs, c.hidden_length, hs, m->group, c.num_layers, m->cfg.tp_rank,
+                           m->cfg.tp_size, 0, 1, &m->d);
+    if (rc) return delete m, jl_set_error(ctx, rc, "model_create: bad shard config");
+    m->attn_seg = m->d.attentionSegmentLength;
+    m->kv_seg = m->d.kvSegmentLength;
+    m->h_seg = m->d.hiddenSegmentLength;
+    m->heads_local = m->attn_seg / hs;
+    m->kv_heads_local = m->kv_seg / hs;
+    m->l.resize((size_t)c.num_layers * 9);
+    m->l_set.assign((size_t)c.num_layers * 9, 0);
+    m->max_context = c.max_context > 0 && c.max_context < c.context_length ? c.max_context : c.context_length;
+    *out = m;
+    return JL_OK;
+}
+
+extern "C" int jl_model_set_tensor(jl_model *m, int layer, int slot, int64_t tensor_id) {
+    if (!m) return JL_ERR_INVALID;
+    jl_ctx *ctx = m->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    auto it = ctx->tensors.find(tensor_id);
+    if (it == ctx->tensors.end()) return jl_set_error(ctx, JL_ERR_INVALID, "model_set_tensor: unknown tensor id");
+    const DevTensor &t = it->second;
+    const jl_model_config &c = m->cfg;
+    const int E = c.embedding_length;
+    auto expect = [&](int64_t rows, int64_t cols) {
+        return (t.rows == rows && t.cols == cols)
+                   ? JL_OK
+                   : jl_set_error(ctx, JL_ERR_INVALID, "model_set_tensor: layer %d slot %d expects [%lld,%lld], got [%lld,%lld]",
+                                  layer, slot, (long long)rows, (long long)cols, (long long)t.rows, (long long)t.cols);
+    };
+    if (layer < 0) {
+        if (slot < 0 || slot > 2) return jl_set_error(ctx, JL_ERR_INVALID, "bad global slot");
+        if (slot == JL_T_OUT_NORM) {
+            M_CHECK(expect(1, E));
+            if (t.dtype != JL_F32 && t.dtype != JL_BF16) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "norm weights must be F32/BF16");
+        } else
+            M_CHECK(expect(c.vocab_size, E));
+        m->g[slot] = t;
+        m->g_set[slot] = true;
+        return JL_OK;
+    }
+    if (layer >= c.num_layers || slot < 0 || slot > 8) return jl_set_error(ctx, JL_ERR_INVALID, "bad layer slot");
+    switch (slot) {
+        case JL_L_ATTN_NORM:
+        case JL_L_FFN_NORM:
+            M_CHECK(expect(1, E));
+            if (t.dtype != JL_F32 && t.dtype != JL_BF16) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "norm weights must be F32/BF16");
+            break;
+        case JL_L_Q: M_CHECK(expect(m->attn_seg, E)); break;
+        case JL_L_K:
+        case JL_L_V: M_CHECK(expect(m->kv_seg, E)); break;
+        case JL_L_O: M_CHECK(expect(E, m->attn_seg)); break;
+        case JL_L_GATE:
+        case JL_L_UP: M_CHECK(expect(m->h_seg, E)); break;
+        case JL_L_DOWN: M_CHECK(expect(E, m->h_seg)); break;
+    }
+    m->l[(size_t)layer * 9 + slot] = t;
+    m->l_set[(size_t)layer * 9 + slot] = 1;
+    return JL_OK;
+}
+
+static int dev_alloc(jl_ctx *ctx, void **p, size_t bytes) {
+    if (cudaMalloc(p, bytes ? bytes : 16) != cudaSuccess) {
+        cudaGetLastError();
+        return jl_set_error(ctx, JL_ERR_OOM, "out of device memory (%zu bytes)", bytes);
+    }
+    return JL_OK;
+}
+
+extern "C" int jl_model_finalize(jl_model *m) {
+    if (!m) return JL_ERR_INVALID;
+    jl_ctx *ctx = m->ctx;
+    if (m->finalized) return JL_OK;
+    const jl_model_config &c = m->cfg;
+    JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < 2; i++)
+        if (!m->g_set[i]) return jl_set_error(ctx, JL_ERR_INVALID, "model_finalize: global tensor %d missing", i);
+    for (size_t i = 0; i < m->l_set.size(); i++)
+        if (!m->l_set[i]) return jl_set_error(ctx, JL_ERR_INVALID, "model_finalize: layer %zu slot %zu missing", i / 9, i % 9);
+    const int E = c.embedding_length, hs = c.head_size;
+    JL_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    // RoPE table (Config.java:271-276) padded by 2*kv_heads positions: head h reads position pos+2*kvh
+    // (CausalSelfAttention.java:260-268); the reference would throw past the end of its table.
+    {
+        const int positions = c.context_length + 2 * c.num_kv_heads;
+        std::vector<float> tbl((size_t)positions * (hs / 2) * 2);
+        jl_precompute_freqs_cis(hs, positions, c.rope_theta, c.rope_scaling, tbl.data());
+        M_CHECK(dev_alloc(ctx, (void **)&m->rope, tbl.size() * 4));
+        JL_CUDA_CHECK(ctx, cudaMemcpy(m->rope, tbl.data(), tbl.size() * 4, cudaMemcpyHostToDevice));
+    }
+    // KV geometry (KvBufferCache.java:99-112,224-280)
+    const int kv_esz = c.kv_dtype == JL_F32 ? 4 : 2;
+    int lpp, cpp;
+    if (jl_kv_page_geometry(c.num_layers, c.context_length, m->kv_seg, kv_esz, 1 << 23, &lpp, &cpp))
+        return jl_set_error(ctx, JL_ERR_INVALID, "kv page geometry");
+    m->kv.layers_per_page = lpp;
+    m->kv.ctx_per_page = cpp;
+    m->kv.kv_len = m->kv_seg;
+    m->kv.n_layer_pages = (c.num_layers + lpp - 1) / lpp;
+    m->kv.n_ctx_pages = (m->max_context + cpp - 1) / cpp;
+    m->kv.kv_dtype = c.kv_dtype;
+    m->page_bytes = (size_t)lpp * 2 * cpp * m->kv_seg * kv_esz;
+    const size_t nent = (size_t)c.max_sessions * m->kv.n_layer_pages * m->kv.n_ctx_pages;
+    m->page_table_host.assign(nent, nullptr);
+    M_CHECK(dev_alloc(ctx, (void **)&m->page_table_dev, nent * sizeof(void *)));
+    JL_CUDA_CHECK(ctx, cudaMemset(m->page_table_dev, 0, nent * sizeof(void *)));
+    m->kv.page_table = m->page_table_dev;
+    // scratch
+    m->maxB = c.max_batch > c.max_sessions ? c.max_batch : c.max_sessions;
+    const size_t B = m->maxB;
+    M_CHECK(dev_alloc(ctx, (void **)&m->x, B * E * 4));
+    M_CHECK(dev_alloc(ctx, (void **)&m->xb, B * E * 4));
+    M_CHECK(dev_alloc(ctx, (void **)&m->q, B * m->attn_seg * 4));
+    M_CHECK(dev_alloc(ctx, (void **)&m->k, B * m->kv_seg * 4));
+    M_CHECK(dev_alloc(ctx, (void **)&m->v, B * m->kv_seg * 4));
+    M_CHECK(dev_alloc(ctx, (void **)&m->att, B * m->attn_seg * 4));
+    M_CHECK(dev_alloc(ctx, (void **)&m->hbuf, B * m->h_seg * 4));
+    M_CHECK(dev_alloc(ctx, (void **)&m->partial, B * E * 4));
+    M_CHECK(dev_alloc(ctx, (void **)&m->logits, (size_t)c.max_sessions * c.vocab_size * 4));
+    M_CHECK(dev_alloc(ctx, (void **)&m->last_hidden, (size_t)c.max_sessions * E * 4));
+    M_CHECK(dev_alloc(ctx, (void **)&m->attn_ws, B * m->heads_local * m->max_splits * (hs + 2) * 4));
+    M_CHECK(dev_alloc(ctx, (void **)&m->d_tokens, B * 4));
+    M_CHECK(dev_alloc(ctx, (void **)&m->d_positions, B * 4));
+    M_CHECK(dev_alloc(ctx, (void **)&m->d_sessions, B * 4));
+    M_CHECK(dev_alloc(ctx, (void **)&m->d_next, B * 4));
+    m->hist_cap = 1 << 16;
+    M_CHECK(dev_alloc(ctx, (void **)&m->d_hist, (size_t)m->hist_cap * 4));
+    M_CHECK(dev_alloc(ctx, (void **)&m->d_counter, 4));
+    M_CHECK(dev_alloc(ctx, &m->argmax_scratch, jl_argmax_scratch_bytes(c.max_sessions)));
+    JL_CUDA_CHECK(ctx, cudaMallocHost((void **)&m->h_pinned, B * 4 * 4));
+    JL_CUDA_CHECK(ctx, cudaEventCreate(&m->ev_begin));
+    JL_CUDA_CHECK(ctx, cudaEventCreate(&m->ev_end));
+    // algorithmic decode bytes per token on this rank: every linear weight once + lm_head
+    auto tb = [](const DevTensor &t) { return (int64_t)t.bytes; };
+    int64_t wb = 0;
+    for (int L = 0; L < c.num_layers; L++)
+        for (int s : {JL_L_Q, JL_L_K, JL_L_V, JL_L_O, JL_L_GATE, JL_L_DOWN, JL_L_UP}) wb += tb(m->l[(size_t)L * 9 + s]);
+    wb += tb(m->g_set[JL_T_LM_HEAD] ? m->g[JL_T_LM_HEAD] : m->g[JL_T_EMBED]);
+    m->weight_bytes = wb;
+    m->finalized = true;
+    return JL_OK;
+}
+
+extern "C" int64_t jl_model_weight_bytes(jl_model *m) { return m ? m->weight_bytes : -1; }
+
+extern "C" int jl_model_free(jl_model *m) {
+    if (!m) return JL_ERR_INVALID;
+    jl_ctx *ctx = m->ctx;
+    cudaSetDevice(ctx->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    for (auto &kv : m->graphs) cudaGraphExecDestroy(kv.second);
+    for (void *p : m->page_table_host)
+        if (p) cudaFree(p);
+    void *bufs[] = {m->rope, m->page_table_dev, m->x, m->xb, m->q, m->k, m->v, m->att, m->hbuf, m->partial, m->logits,
+                    m->last_hidden, m->attn_ws, m->d_tokens, m->d_positions, m->d_sessions, m->d_next, m->d_hist, m->d_counter,
+                    m->argmax_scratch};
+    for (void *p : bufs)
+        if (p) cudaFree(p);
+    if (m->h_pinned) cudaFreeHost(m->h_pinned);
+    for (auto e : m->ev_pool) cudaEventDestroy(e);
+    if (m->ev_begin) cudaEventDestroy(m->ev_begin);
+    if (m->ev_end) cudaEventDestroy(m->ev_end);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+    return JL_OK;
+}
+
+extern "C" int jl_model_reset_session(jl_model *m, int session) {
+    if (!m || !m->finalized || session < 0 || session >= m->cfg.max_sessions) return JL_ERR_INVALID;
+    jl_ctx *ctx = m->ctx;
+    JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    JL_CUDA_CHECK(ctx, cudaStreamSynchronize(m->stream));
+    // pages stay allocated (a KvBuffer keeps its pages until close); contents are dead once positions restart.
+    // Zero them so a fresh session starts from the reference's zero-initialised page (TensorCache.java:105).
+    const size_t per = (size_t)m->kv.n_layer_pages * m->kv.n_ctx_pages;
+    for (size_t i = 0; i < per; i++) {
+        void *p = m->page_table_host[(size_t)session * per + i];
+        if (p) JL_CUDA_CHECK(ctx, cudaMemsetAsync(p, 0, m->page_bytes, m->stream));
+    }
+    JL_CUDA_CHECK(ctx, cudaStreamSynchronize(m->stream));
+    return JL_OK;
+}
+
+// make sure pages for positions [p0, p1] of `session` exist (KvBufferCache.java:307-318 lazy pages)
+static int ensure_pages(jl_model *m, int session, int p0, int p1) {
+    jl_ctx *ctx = m->ctx;
+    if (p1 >= m->max_context)
+        return jl_set_error(ctx, JL_ERR_INVALID, "position %d exceeds reserved context %d", p1, m->max_context);
+    bool changed = false;
+    for (int cp = p0 / m->kv.ctx_per_page; cp <= p1 / m->kv.ctx_per_page; cp++)
+        for (int lp = 0; lp < m->kv.n_layer_pages; lp++) {
+            size_t idx = ((size_t)session * m->kv.n_layer_pages + lp) * m->kv.n_ctx_pages + cp;
+            if (!m->page_table_host[idx]) {
+                void *p = nullptr;
+                M_CHECK(dev_alloc(ctx, &p, m->page_bytes));
+                JL_CUDA_CHECK(ctx, cudaMemsetAsync(p, 0, m->page_bytes, m->stream));
+                m->page_table_host[idx] = p;
+                JL_CUDA_CHECK(ctx, cudaMemcpyAsync(&m->page_table_dev[idx], &m->page_table_host[idx], sizeof(void *),
+                                                   cudaMemcpyHostToDevice, m->stream));
+                changed = true;
+            }
+        }
+    if (changed) JL_CUDA_CHECK(ctx, cudaStreamSynchronize(m->stream)); // host staging of the pointer must outlive the copy
+    return JL_OK;
+}
+
+static cudaEvent_t next_event(jl_model *m) {
+    if (m->ev_used == m->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        m->ev_pool.push_back(e);
+    }
+    return m->ev_pool[m->ev_used++];
+}
+
+// one quantised/dense GEMM call site; M rows of `a` against W; splits M into GEMV_MAX_M chunks.
+// `timed`: bracket with events (eager mode only) for the roofline numerator.
+static int run_gemm(jl_model *m, GemvParams p, int prologue, int epilogue, int M, size_t a_row_bytes, bool timed) {
+    jl_ctx *ctx = m->ctx;
+    if (timed) cudaEventRecord(next_event(m), m->stream);
+    for (int m0 = 0; m0 < M; m0 += GEMV_MAX_M) {
+        GemvParams c = p;
+        c.M = M - m0 < GEMV_MAX_M ? M - m0 : GEMV_MAX_M;
+        c.a = (const char *)p.a + (size_t)m0 * a_row_bytes;
+        for (int s = 0; s < c.nseg; s++) c.seg[s].out = p.seg[s].out + (size_t)m0 * p.seg[s].out_ld;
+        if (c.residual) c.residual = p.residual + (size_t)m0 * p.res_ld;
+        M_CHECK(jl_launch_gemv(ctx, m->stream, c, prologue, epilogue, use_pdl(m)));
+    }
+    if (timed) cudaEventRecord(next_event(m), m->stream);
+    return JL_OK;
+}
+
+static void set_w(GemvParams &p, int seg, const DevTensor &t, float *out, int out_ld) {
+    p.seg[seg].w = t.data;
+    p.seg[seg].ws = t.scales;
+    p.seg[seg].out = out;
+    p.seg[seg].rows = (int)t.rows;
+    p.seg[seg].out_ld = out_ld;
+    p.seg[seg].out_off = 0;
+}
+
+// AbstractModel.forward (:314-329) over M rows whose tokens/positions/sessions are already on the device.
+static int forward_rows(jl_model *m, int M, int max_pos, int splits, bool timed) {
+    jl_ctx *ctx = m->ctx;
+    const jl_model_config &c = m->cfg;
+    const int E = c.embedding_length, hs = c.head_size;
+    const bool q8 = c.working_qtype == JL_I8;
+    const bool pdl = use_pdl(m);
+    M_CHECK(jl_launch_embed(ctx, m->stream, m->g[JL_T_EMBED], m->d_tokens, M, m->x, E));
+    for (int L = 0; L < c.num_layers; L++) {
+        const DevTensor *lw = &m->l[(size_t)L * 9];
+        // Q8 activations only pair with Q4/I8 weights (AbstractModel.java:119-176)
+        auto act_q = [&](const DevTensor &w) { return q8 && (w.dtype == JL_Q4 || w.dtype == JL_I8); };
+        // ---- pre-norm + quantise + QKV (TransformerBlock.java:170-175, CausalSelfAttention.java:161-171) ----
+        {
+            GemvParams p = {};
+            p.nseg = 3;
+            set_w(p, 0, lw[JL_L_Q], m->q, m->attn_seg);
+            set_w(p, 1, lw[JL_L_K], m->k, m->kv_seg);
+            set_w(p, 2, lw[JL_L_V], m->v, m->kv_seg);
+            // k and v outputs are indexed by their own local row: out col = local
+            p.w_dtype = lw[JL_L_Q].dtype;
+            p.ldw = E;
+            p.K = E;
+            p.a = m->x;
+            p.lda = E;
+            p.norm_w = lw[JL_L_ATTN_NORM].data;
+            p.norm_w_dtype = lw[JL_L_ATTN_NORM].dtype;
+            p.norm_adj = 0.0f;
+            p.norm_eps = c.layer_norm_eps;
+            p.norm_E = E;
+            p.total_rows = m->attn_seg + 2 * m->kv_seg;
+            M_CHECK(run_gemm(m, p, act_q(lw[JL_L_Q]) ? PRO_RMSNORM_QUANT : PRO_RMSNORM_F32, EPI_STORE, M, (size_t)E * 4, timed));
+        }
+        // ---- KV append + RoPE, attention (CausalSelfAttention.java:199-356) ----
+        AttnParams ap = {};
+        ap.kv = m->kv;
+        ap.layer = L;
+        ap.heads = m->heads_local;
+        ap.kv_heads = m->kv_heads_local;
+        ap.head_size = hs;
+        ap.head0_global = m->d.headStart;
+        ap.kv_head0_global = m->d.groupHeadStart;
+        ap.q = m->q;
+        ap.k = m->k;
+        ap.v = m->v;
+        ap.q_ld = m->attn_seg;
+        ap.kv_ld = m->kv_seg;
+        ap.out = m->att;
+        ap.rope = m->rope;
+        ap.rows = M;
+        ap.sessions = m->d_sessions;
+        ap.positions = m->d_positions;
+        ap.scale = (float)(1.0 / sqrt((double)hs)); // CausalSelfAttention.java:134
+        ap.ws = m->attn_ws;
+        ap.splits = splits;
+        M_CHECK(jl_launch_rope_kv_append(ctx, m->stream, ap, m->q, pdl));
+        M_CHECK(jl_launch_paged_attention(ctx, m->stream, ap, max_pos, pdl));
+        // ---- o_proj (+ reducer) + residual (CausalSelfAttention.java:363-378, TransformerBlock.java:185) ----
+        {
+            GemvParams p = {};
+            p.nseg = 1;
+            const bool tp = c.tp_size > 1;
+            set_w(p, 0, lw[JL_L_O], tp ? m->partial : m->xb, E);
+            p.w_dtype = lw[JL_L_O].dtype;
+            p.ldw = m->attn_seg;
+            p.K = m->attn_seg;
+            p.a = m->att;
+            p.lda = m->attn_seg;
+            p.residual = m->x;
+            p.res_ld = E;
+            p.total_rows = E;
+            M_CHECK(run_gemm(m, p, act_q(lw[JL_L_O]) ? PRO_F32_QUANT : PRO_F32, tp ? EPI_STORE : EPI_ADD_RESIDUAL, M,
+                             (size_t)m->attn_seg * 4, timed));
+            if (tp) {
+                M_CHECK(jl_comm_allreduce_dev(ctx, m->stream, m->partial, (size_t)M * E));
+                // xb = reduced + x
+                JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->xb, m->partial, (size_t)M * E * 4, cudaMemcpyDeviceToDevice, m->stream));
+                M_CHECK(jl_launch_accumulate(ctx, m->stream, m->xb, M, E, JL_F32, m->x, nullptr, M, E, 0, E));
+            }
+        }
+        // ---- pre-FF norm + quantise + gate/up + SiLU*up (TransformerBlock.java:187-196, MLPBlock.java:117-141) ----
+        {
+            GemvParams p = {};
+            p.nseg = 2;
+            set_w(p, 0, lw[JL_L_GATE], m->hbuf, m->h_seg);
+            set_w(p, 1, lw[JL_L_UP], m->hbuf, m->h_seg);
+            p.w_dtype = lw[JL_L_GATE].dtype;
+            p.ldw = E;
+            p.K = E;
+            p.a = m->xb;
+            p.lda = E;
+            p.norm_w = lw[JL_L_FFN_NORM].data;
+            p.norm_w_dtype = lw[JL_L_FFN_NORM].dtype;
+            p.norm_eps = c.layer_norm_eps;
+            p.norm_E = E;
+            p.total_rows = m->h_seg;
+            M_CHECK(run_gemm(m, p, act_q(lw[JL_L_GATE]) ? PRO_RMSNORM_QUANT : PRO_RMSNORM_F32, EPI_SILU_MUL, M, (size_t)E * 4, timed));
+        }
+        // ---- down_proj (+ reducer) + residual (MLPBlock.java:144-160, TransformerBlock.java:203) ----
+        {
+            GemvParams p = {};
+            p.nseg = 1;
+            const bool tp = c.tp_size > 1;
+            set_w(p, 0, lw[JL_L_DOWN], tp ? m->partial : m->x, E);
+            p.w_dtype = lw[JL_L_DOWN].dtype;
+            p.ldw = m->h_seg;
+            p.K = m->h_seg;
+            p.a = m->hbuf;
+            p.lda = m->h_seg;
+            p.residual = m->xb;
+            p.res_ld = E;
+            p.total_rows = E;
+            M_CHECK(run_gemm(m, p, act_q(lw[JL_L_DOWN]) ? PRO_F32_QUANT : PRO_F32, tp ? EPI_STORE : EPI_ADD_RESIDUAL, M,
+                             (size_t)m->h_seg * 4, timed));
+            if (tp) {
+                M_CHECK(jl_comm_allreduce_dev(ctx, m->stream, m->partial, (size_t)M * E));
+                JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->x, m->partial, (size_t)M * E * 4, cudaMemcpyDeviceToDevice, m->stream));
+                M_CHECK(jl_launch_accumulate(ctx, m->stream, m->x, M, E, JL_F32, m->xb, nullptr, M, E, 0, E));
+            }
+        }
+    }
+    return JL_OK;
+}
+
+// AbstractModel.sample (:443-473) for `n` hidden rows [n, E] -> logits [n, vocab] -> argmax tokens
+static int sample_rows(jl_model *m, const float *hidden, int n, bool timed) {
+    jl_ctx *ctx = m->ctx;
+    const jl_model_config &c = m->cfg;
+    const int E = c.embedding_length;
+    const DevTensor &w = m->g_set[JL_T_LM_HEAD] ? m->g[JL_T_LM_HEAD] : m->g[JL_T_EMBED];
+    GemvParams p = {};
+    p.nseg = 1;
+    set_w(p, 0, w, m->logits, c.vocab_size);
+    p.w_dtype = w.dtype;
+    p.ldw = E;
+    p.K = E;
+    p.a = hidden;
+    p.lda = E;
+    p.norm_w = m->g[JL_T_OUT_NORM].data;
+    p.norm_w_dtype = m->g[JL_T_OUT_NORM].dtype;
+    p.norm_eps = c.layer_norm_eps;
+    p.norm_E = E;
+    p.total_rows = c.vocab_size;
+    // lm_head uses un-quantised F32 activations (AbstractModel.java:444-449)
+    M_CHECK(run_gemm(m, p, PRO_RMSNORM_F32, EPI_STORE, n, (size_t)E * 4, timed));
+    M_CHECK(jl_launch_argmax(ctx, m->stream, m->logits, n, c.vocab_size, c.vocab_size, m->d_next, m->argmax_scratch));
+    return JL_OK;
+}
+
+static int pick_splits(const jl_model *m, int max_pos, int rows) {
+    // enough CTAs to cover the SMs, at most one split per 128 positions
+    int want = (max_pos + 1 + 127) / 128;
+    int fill = (m->ctx->sm_count * 2) / (m->kv_heads_local * rows > 0 ? m->kv_heads_local * rows : 1);
+    if (fill < 1) fill = 1;
+    int s = want < fill ? want : fill;
+    if (s > m->max_splits) s = m->max_splits;
+    if (s < 1) s = 1;
+    // bucket to powers of two so few graphs are needed
+    int b = 1;
+    while (b < s) b <<= 1;
+    return b > m->max_splits ? m->max_splits : b;
+}
+
+extern "C" int jl_model_batch_forward(jl_model *m, int session, const int32_t *tokens, int n, int start_pos) {
+    if (!m || !m->finalized || !tokens || n <= 0 || session < 0 || session >= m->cfg.max_sessions || start_pos < 0)
+        return JL_ERR_INVALID;
+    jl_ctx *ctx = m->ctx;
+    JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    const int E = m->cfg.embedding_length;
+    M_CHECK(ensure_pages(m, session, start_pos, start_pos + n - 1));
+    for (int i = 0; i < n; i += m->cfg.max_batch) { // AbstractModel.java:304
+        const int cnt = n - i < m->cfg.max_batch ? n - i : m->cfg.max_batch;
+        int32_t *hp = m->h_pinned;
+        for (int j = 0; j < cnt; j++) {
+            hp[j] = tokens[i + j];
+            hp[m->maxB + j] = start_pos + i + j;
+            hp[2 * m->maxB + j] = session;
+        }
+        JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_tokens, hp, (size_t)cnt * 4, cudaMemcpyHostToDevice, m->stream));
+        JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_positions, hp + m->maxB, (size_t)cnt * 4, cudaMemcpyHostToDevice, m->stream));
+        JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_sessions, hp + 2 * m->maxB, (size_t)cnt * 4, cudaMemcpyHostToDevice, m->stream));
+        const int max_pos = start_pos + i + cnt - 1;
+        M_CHECK(forward_rows(m, cnt, max_pos, pick_splits(m, max_pos, cnt), false));
+        // keep the last row for sample()
+        JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->last_hidden + (size_t)session * E, m->x + (size_t)(cnt - 1) * E, (size_t)E * 4,
+                                           cudaMemcpyDeviceToDevice, m->stream));
+        JL_CUDA_CHECK(ctx, cudaStreamSynchronize(m->stream)); // pinned staging is reused by the next chunk
+    }
+    return JL_OK;
+}
+
+__global__ void softmax_sample_kernel(float *logits, int vocab, float temperature, float uniform, int32_t *out);
+
+extern "C" int jl_model_sample(jl_model *m, int session, float temperature, float uniform, int32_t *token_out,
+                               float *logits_out) {
+    if (!m || !m->finalized || !token_out || session < 0 || session >= m->cfg.max_sessions) return JL_ERR_INVALID;
+    jl_ctx *ctx = m->ctx;
+    JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    const int E = m->cfg.embedding_length, V = m->cfg.vocab_size;
+    M_CHECK(sample_rows(m, m->last_hidden + (size_t)session * E, 1, false));
+    if (temperature != 0.0f) {
+        // AbstractModel.java:475-487: exp((l - max)/T), float prefix sum against the uniform sample
+        softmax_sample_kernel<<<1, 1024, 0, m->stream>>>(m->logits, V, temperature, uniform, m->d_next);
+        ctx->launches++;
+        JL_CUDA_CHECK(ctx, cudaGetLastError());
+    }
+    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->h_pinned + 3 * m->maxB, m->d_next, 4, cudaMemcpyDeviceToHost, m->stream));
+    if (logits_out && temperature == 0.0f)
+        JL_CUDA_CHECK(ctx, cudaMemcpyAsync(logits_out, m->logits, (size_t)V * 4, cudaMemcpyDeviceToHost, m->stream));
+    JL_CUDA_CHECK(ctx, cudaStreamSynchronize(m->stream));
+    *token_out = m->h_pinned[3 * m->maxB];
+    return JL_OK;
+}
+
+// exp((l-max)/T) then the first index whose running sum reaches `uniform` (AbstractModel.java:475-489).
+// Sequential prefix order is part of the semantics, so one thread walks the normalised values.
+__global__ void softmax_sample_kernel(float *logits, int vocab, float temperature, float uniform, int32_t *out) {
+    __shared__ float red[32];
+    __shared__ float bc;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float mx = -INFINITY;
+    for (int i = tid; i < vocab; i += blockDim.x) mx = fmaxf(mx, logits[i]);
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        float t = red[0];
+        for (int i = 1; i < 32; i++) t = fmaxf(t, red[i]);
+        bc = t;
+    }
+    __syncthreads();
+    mx = bc;
+    float sum = 0.0f;
+    for (int i = tid; i < vocab; i += blockDim.x) {
+        const float e = (float)exp(((double)logits[i] - (double)mx) / (double)temperature);
+        logits[i] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    __syncthreads();
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.0f;
+        for (int i = 0; i < 32; i++) t += red[i];
+        float acc = 0.0f;
+        int pick = vocab - 1;
+        for (int i = 0; i < vocab; i++) {
+            acc += logits[i] / t;
+            if (acc >= uniform) {
+                pick = i;
+                break;
+            }
+        }
+        *out = pick;
+    }
+}
+
+// device-side bookkeeping at the end of a resident decode step: feed the sampled token back, advance
+// the position, append to the history ring.
+__global__ void advance_kernel(int32_t *tokens, int32_t *positions, const int32_t *next, int32_t *hist, int32_t *counter,
+                               int n, int cap) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int i = threadIdx.x;
+    const int cnt = *counter;
+    if (i < n) {
+        tokens[i] = next[i];
+        positions[i] += 1;
+        if (cnt * n + i < cap) hist[cnt * n + i] = next[i];
+    }
+    __syncthreads();
+    if (i == 0) *counter = cnt + 1;
+}
+
+static int decode_body(jl_model *m, int n, int max_pos, int splits, bool resident, bool timed) {
+    jl_ctx *ctx = m->ctx;
+    M_CHECK(forward_rows(m, n, max_pos, splits, timed));
+    M_CHECK(sample_rows(m, m->x, n, timed));
+    if (resident) {
+        JL_CUDA_CHECK(ctx, jl_launch_kernel(advance_kernel, dim3(1), dim3(256), 0, m->stream, false, m->d_tokens, m->d_positions,
+                                            (const int32_t *)m->d_next, m->d_hist, m->d_counter, n, m->hist_cap));
+        ctx->launches++;
+    }
+    return JL_OK;
+}
+
+// run the decode body through a cached CUDA graph (or eagerly)
+static int run_decode(jl_model *m, int n, int max_pos, bool resident) {
+    jl_ctx *ctx = m->ctx;
+    const int splits = pick_splits(m, max_pos, n);
+    if (!use_graph(m)) {
+        m->ev_used = 0;
+        int rc = decode_body(m, n, max_pos, splits, resident, true);
+        m->timing_valid = rc == JL_OK;
+        return rc;
+    }
+    const long long key = ((long long)n << 32) | ((long long)splits << 1) | (resident ? 1 : 0);
+    auto it = m->graphs.find(key);
+    if (it == m->graphs.end()) {
+        cudaGraph_t graph = nullptr;
+        const long long before = ctx->launches;
+        JL_CUDA_CHECK(ctx, cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = decode_body(m, n, max_pos, splits, resident, false);
+        cudaError_t ce = cudaStreamEndCapture(m->stream, &graph);
+        const long long per_graph = ctx->launches - before;
+        ctx->launches = before;
+        if (rc != JL_OK) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        if (ce != cudaSuccess) return jl_set_error(ctx, JL_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+        cudaGraphExec_t exec = nullptr;
+        ce = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) return jl_set_error(ctx, JL_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+        m->graphs[key] = exec;
+        m->graphs[-key - 1] = (cudaGraphExec_t)(intptr_t)per_graph; // launch count of this graph (not a real exec)
+        it = m->graphs.find(key);
+    }
+    JL_CUDA_CHECK(ctx, cudaGraphLaunch(it->second, m->stream));
+    ctx->launches += (long long)(intptr_t)m->graphs[-key - 1];
+    return JL_OK;
+}
+
+extern "C" int jl_model_decode(jl_model *m, int n, const int32_t *sessions, const int32_t *tokens, const int32_t *positions,
+                               int32_t *next_tokens, float *logits_out) {
+    if (!m || !m->finalized || n <= 0 || n > m->cfg.max_sessions || n > GEMV_MAX_M || !sessions || !tokens || !positions ||
+        !next_tokens)
+        return m ? jl_set_error(m->ctx, JL_ERR_INVALID, "decode: bad arguments (n=%d, max %d)", n, GEMV_MAX_M) : JL_ERR_INVALID;
+    jl_ctx *ctx = m->ctx;
+    JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    int max_pos = 0;
+    int32_t *hp = m->h_pinned;
+    for (int i = 0; i < n; i++) {
+        if (sessions[i] < 0 || sessions[i] >= m->cfg.max_sessions || positions[i] < 0)
+            return jl_set_error(ctx, JL_ERR_INVALID, "decode: bad session/position");
+        M_CHECK(ensure_pages(m, sessions[i], positions[i], positions[i]));
+        if (positions[i] > max_pos) max_pos = positions[i];
+        hp[i] = tokens[i];
+        hp[m->maxB + i] = positions[i];
+        hp[2 * m->maxB + i] = sessions[i];
+    }
+    JL_CUDA_CHECK(ctx, cudaEventRecord(m->ev_begin, m->stream));
+    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_tokens, hp, (size_t)n * 4, cudaMemcpyHostToDevice, m->stream));
+    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_positions, hp + m->maxB, (size_t)n * 4, cudaMemcpyHostToDevice, m->stream));
+    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_sessions, hp + 2 * m->maxB, (size_t)n * 4, cudaMemcpyHostToDevice, m->stream));
+    M_CHECK(run_decode(m, n, max_pos, false));
+    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(hp + 3 * m->maxB, m->d_next, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+    if (logits_out)
+        JL_CUDA_CHECK(ctx, cudaMemcpyAsync(logits_out, m->logits, (size_t)n * m->cfg.vocab_size * 4, cudaMemcpyDeviceToHost, m->stream));
+    JL_CUDA_CHECK(ctx, cudaEventRecord(m->ev_end, m->stream));
+    JL_CUDA_CHECK(ctx, cudaStreamSynchronize(m->stream));
+    for (int i = 0; i < n; i++) next_tokens[i] = hp[3 * m->maxB + i];
+    float ms = 0;
+    cudaEventElapsedTime(&ms, m->ev_begin, m->ev_end);
+    m->last_total_ms = ms;
+    if (!use_graph(m) && m->timing_valid) {
+        double g = 0;
+        for (size_t i = 0; i + 1 < m->ev_used; i += 2) {
+            float t = 0;
+            cudaEventElapsedTime(&t, m->ev_pool[i], m->ev_pool[i + 1]);
+            g += t;
+        }
+        m->last_gemv_ms = g;
+    }
+    return JL_OK;
+}
+
+extern "C" int jl_model_decode_resident(jl_model *m, int session, int32_t first_token, int start_pos, int n_new,
+                                        int32_t *out_tokens) {
+    if (!m || !m->finalized || session < 0 || session >= m->cfg.max_sessions || n_new <= 0 || !out_tokens || start_pos < 0)
+        return JL_ERR_INVALID;
+    jl_ctx *ctx = m->ctx;
+    if (n_new > m->hist_cap) return jl_set_error(ctx, JL_ERR_INVALID, "decode_resident: n_new too large");
+    JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    M_CHECK(ensure_pages(m, session, start_pos, start_pos + n_new - 1));
+    int32_t *hp = m->h_pinned;
+    hp[0] = first_token;
+    hp[m->maxB] = start_pos;
+    hp[2 * m->maxB] = session;
+    hp[3 * m->maxB] = 0;
+    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_tokens, hp, 4, cudaMemcpyHostToDevice, m->stream));
+    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_positions, hp + m->maxB, 4, cudaMemcpyHostToDevice, m->stream));
+    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_sessions, hp + 2 * m->maxB, 4, cudaMemcpyHostToDevice, m->stream));
+    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_counter, hp + 3 * m->maxB, 4, cudaMemcpyHostToDevice, m->stream));
+    JL_CUDA_CHECK(ctx, cudaEventRecord(m->ev_begin, m->stream));
+    double gemv = 0;
+    for (int i = 0; i < n_new; i++) {
+        M_CHECK(run_decode(m, 1, start_pos + i, true));
+        if (!use_graph(m)) {
+            // eager profiling mode: collect the per-GEMV event pairs of this step
+            JL_CUDA_CHECK(ctx, cudaStreamSynchronize(m->stream));
+            for (size_t e = 0; e + 1 < m->ev_used; e += 2) {
+                float t = 0;
+                cudaEventElapsedTime(&t, m->ev_pool[e], m->ev_pool[e + 1]);
+                gemv += t;
+            }
+        }
+    }
+    JL_CUDA_CHECK(ctx, cudaEventRecord(m->ev_end, m->stream));
+    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(out_tokens, m->d_hist, (size_t)n_new * 4, cudaMemcpyDeviceToHost, m->stream));
+    JL_CUDA_CHECK(ctx, cudaStreamSynchronize(m->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, m->ev_begin, m->ev_end);
+    m->last_total_ms = ms;
+    m->last_gemv_ms = gemv;
+    return JL_OK;
+}
+
+extern "C" int jl_model_last_timing(jl_model *m, double *total_ms, double *gemv_ms) {
+    if (!m) return JL_ERR_INVALID;
+    if (total_ms) *total_ms = m->last_total_ms;
+    if (gemv_ms) *gemv_ms = m->last_gemv_ms;
+    return JL_OK;
+}
+
+extern "C" int jl_model_generate(jl_model *m, int session, const int32_t *prompt, int n_prompt, int n_new, int32_t *out_tokens,
+                                 float *logits_out, double *timings_ms) {
+    if (!m || !m->finalized || !prompt || n_prompt <= 0 || n_new <= 0 || !out_tokens) return JL_ERR_INVALID;
+    const int V = m->cfg.vocab_size;
+    auto t0 = std::chrono::steady_clock::now();
+    M_CHECK(jl_model_reset_session(m, session));
+    M_CHECK(jl_model_batch_forward(m, session, prompt, n_prompt, 0));
+    int32_t next = 0;
+    M_CHECK(jl_model_sample(m, session, 0.0f, 0.0f, &next, logits_out));
+    auto t1 = std::chrono::steady_clock::now();
+    out_tokens[0] = next;
+    for (int i = 1; i < n_new; i++) {
+        const int32_t pos = n_prompt + i - 1;
+        int32_t nx = 0;
+        M_CHECK(jl_model_decode(m, 1, &session, &next, &pos, &nx, logits_out ? logits_out + (size_t)i * V : nullptr));
+        next = nx;
+        out_tokens[i] = next;
+    }
+    auto t2 = std::chrono::steady_clock::now();
+    if (timings_ms) {
+        timings_ms[0] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        timings_ms[1] = std::chrono::duration<double, std::milli>(t2 - t1).count();
+    }
+    return JL_OK;
+}
+
+extern "C" int jl_model_read_kv(jl_model *m, int session, int layer, int position, int which, float *out) {
+    if (!m || !m->finalized || !out || session < 0 || session >= m->cfg.max_sessions || layer < 0 ||
+        layer >= m->cfg.num_layers || position < 0 || position >= m->max_context || (which != 0 && which != 1))
+        return JL_ERR_INVALID;
+    jl_ctx *ctx = m->ctx;
+    JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    const KvLayout &kv = m->kv;
+    const int lp = layer / kv.layers_per_page, rl = layer % kv.layers_per_page;
+    const int cp = position / kv.ctx_per_page, rc = position % kv.ctx_per_page;
+    const char *base = (const char *)m->page_table_host[((size_t)session * kv.n_layer_pages + lp) * kv.n_ctx_pages + cp];
+    if (!base) return jl_set_error(ctx, JL_ERR_INVALID, "read_kv: page not allocated");
+    const size_t elem = (((size_t)rl * 2 + which) * kv.ctx_per_page + rc) * kv.kv_len;
+    JL_CUDA_CHECK(ctx, cudaStreamSynchronize(m->stream));
+    if (kv.kv_dtype == JL_F32) {
+        JL_CUDA_CHECK(ctx, cudaMemcpy(out, base + elem * 4, (size_t)kv.kv_len * 4, cudaMemcpyDeviceToHost));
+    } else {
+        std::vector<uint16_t> tmp(kv.kv_len);
+        JL_CUDA_CHECK(ctx, cudaMemcpy(tmp.data(), base + elem * 2, (size_t)kv.kv_len * 2, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < kv.kv_len; i++) {
+            uint32_t u = ((uint32_t)tmp[i]) << 16;
+            memcpy(&out[i], &u, 4);
+        }
+    }
+    return JL_OK;
+}
+
+extern "C" int jl_model_read_hidden(jl_model *m, int session, float *out) {
+    if (!m || !m->finalized || !out || session < 0 || session >= m->cfg.max_sessions) return JL_ERR_INVALID;
+    jl_ctx *ctx = m->ctx;
+    JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    JL_CUDA_CHECK(ctx, cudaStreamSynchronize(m->stream));
+    JL_CUDA_CHECK(ctx, cudaMemcpy(out, m->last_hidden + (size_t)session * m->cfg.embedding_length,
+                                  (size_t)m->cfg.embedding_length * 4, cudaMemcpyDeviceToHost));
+    return JL_OK;
+}

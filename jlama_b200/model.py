@@ -1,0 +1,180 @@
+"""Host-side mirror of AbstractModel / LlamaModel (core/model/AbstractModel.java, core/model/llama/LlamaModel.java)
+on top of the device-resident C++ driver (csrc/jl_model.cu, C ABI jl_model_*).
+
+    model = LlamaModel(ctx, cfg, weights)            # ModelSupport.loadModel + registerModelTensor
+    tokens = model.generate(prompt_ids, n_new)       # AbstractModel.generate at temperature 0
+
+Sharding follows jlama-net: DistributedContext (model/DistributedContext.java:60-98) decides the row
+slices of q/k/v/gate/up and the column slices of o/down (LlamaModel.java:120-133; Weights.getLoadOffsets,
+safetensors/Weights.java:99-117); the slices are cut on the host and only this rank's part is uploaded.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import native
+from .native import BF16, F32, I8, Q4, ptr
+
+
+class DistributedContext:
+    """model/DistributedContext.java:60-98 via the library's pure host function jl_dctx_build."""
+
+    def __init__(self, cfg, model_shard=0, num_model_shards=1, layer_shard=0, num_layer_shards=1):
+        hs = cfg["E"] // cfg["heads"]
+        d = native.Dctx()
+        rc = native.load().jl_dctx_build(cfg["E"], cfg["heads"] * hs, cfg["H"], hs, cfg["heads"] // cfg["kv_heads"],
+                                         cfg["layers"], model_shard, num_model_shards, layer_shard, num_layer_shards,
+                                         C.byref(d))
+        if rc != 0:
+            raise ValueError("bad shard configuration")
+        for name, _ in native.Dctx._fields_:
+            setattr(self, name, getattr(d, name))
+        self.model_shard, self.num_model_shards = model_shard, num_model_shards
+
+
+def _slice_rows(t, start, length):
+    dt, data, scales = t
+    return (dt, np.ascontiguousarray(data[start:start + length]),
+            None if scales is None else np.ascontiguousarray(scales[start:start + length]))
+
+
+def _slice_cols(t, start, length):
+    """AbstractTensor.sparsify columns (core/tensor/AbstractTensor.java:151-172): copy of a column range."""
+    dt, data, scales = t
+    if dt == Q4:
+        assert start % 32 == 0 and length % 32 == 0
+        return (dt, np.ascontiguousarray(data[:, start // 2:(start + length) // 2]),
+                np.ascontiguousarray(scales[:, start // 32:(start + length) // 32]))
+    if dt == I8:
+        return (dt, np.ascontiguousarray(data[:, start:start + length]),
+                np.ascontiguousarray(scales[:, start // 32:(start + length) // 32]))
+    return (dt, np.ascontiguousarray(data[:, start:start + length]), None)
+
+
+class LlamaModel:
+    def __init__(self, ctx, cfg, weights, working_qtype=I8, kv_dtype=F32, max_batch=256, max_sessions=1, max_context=0,
+                 tp_rank=0, tp_size=1, flags=0):
+        self.ctx, self.cfg, self.lib = ctx, cfg, ctx.lib
+        self.dctx = DistributedContext(cfg, tp_rank, tp_size)
+        mc = native.ModelConfig(
+            context_length=cfg["ctx"], embedding_length=cfg["E"], hidden_length=cfg["H"], num_heads=cfg["heads"],
+            num_kv_heads=cfg["kv_heads"], num_layers=cfg["layers"], vocab_size=cfg["vocab"], head_size=cfg["E"] // cfg["heads"],
+            layer_norm_eps=cfg["eps"], rope_theta=cfg["rope_theta"], rope_scaling=cfg.get("rope_scale", 1.0),
+            working_qtype=working_qtype, kv_dtype=kv_dtype, max_batch=max_batch, max_sessions=max_sessions,
+            max_context=max_context, tp_rank=tp_rank, tp_size=tp_size, prefill_tensor_core=0, flags=flags)
+        h = C.c_void_p()
+        ctx.check(self.lib.jl_model_create(ctx.h, C.byref(mc), C.byref(h)))
+        self.h = h
+        self._ids = []
+        self.max_sessions = max_sessions
+        if callable(weights):
+            get = weights
+        else:
+            get = weights.get
+        d = self.dctx
+
+        def put(layer, slot, name, shard=None):
+            t = get(name)
+            if t is None:
+                return False
+            if shard == "rows_attn":
+                t = _slice_rows(t, d.attentionSegmentStart, d.attentionSegmentLength)
+            elif shard == "rows_kv":
+                t = _slice_rows(t, d.kvSegmentStart, d.kvSegmentLength)
+            elif shard == "rows_hidden":
+                t = _slice_rows(t, d.hiddenSegmentStart, d.hiddenSegmentLength)
+            elif shard == "cols_attn":
+                t = _slice_cols(t, d.attentionSegmentStart, d.attentionSegmentLength)
+            elif shard == "cols_hidden":
+                t = _slice_cols(t, d.hiddenSegmentStart, d.hiddenSegmentLength)
+            dt, data, scales = t
+            rows = data.shape[0]
+            cols = data.shape[1] * (2 if dt == Q4 else 1)
+            tid = self.lib.jl_register_tensor(ctx.h, dt, rows, cols, ptr(data), ptr(scales))
+            if tid < 0:
+                raise native.JlamaNativeError(-1, self.lib.jl_last_error(ctx.h).decode())
+            self._ids.append(tid)
+            ctx.check(self.lib.jl_model_set_tensor(self.h, layer, slot, tid))
+            return True
+
+        sharded = tp_size > 1
+        put(-1, native.T_EMBED, "model.embed_tokens.weight")
+        put(-1, native.T_OUT_NORM, "model.norm.weight")
+        put(-1, native.T_LM_HEAD, "lm_head.weight")
+        for i in range(cfg["layers"]):
+            b = "model.layers.%d." % i
+            put(i, native.L_ATTN_NORM, b + "input_layernorm.weight")
+            put(i, native.L_Q, b + "self_attn.q_proj.weight", "rows_attn" if sharded else None)
+            put(i, native.L_K, b + "self_attn.k_proj.weight", "rows_kv" if sharded else None)
+            put(i, native.L_V, b + "self_attn.v_proj.weight", "rows_kv" if sharded else None)
+            put(i, native.L_O, b + "self_attn.o_proj.weight", "cols_attn" if sharded else None)
+            put(i, native.L_FFN_NORM, b + "post_attention_layernorm.weight")
+            put(i, native.L_GATE, b + "mlp.gate_proj.weight", "rows_hidden" if sharded else None)
+            put(i, native.L_DOWN, b + "mlp.down_proj.weight", "cols_hidden" if sharded else None)
+            put(i, native.L_UP, b + "mlp.up_proj.weight", "rows_hidden" if sharded else None)
+        ctx.check(self.lib.jl_model_finalize(self.h))
+
+    # -- AbstractModel API ---------------------------------------------------------------------------
+    def reset_session(self, session=0):
+        self.ctx.check(self.lib.jl_model_reset_session(self.h, session))
+
+    def batch_forward(self, tokens, start_pos=0, session=0):
+        tokens = np.ascontiguousarray(tokens, dtype=np.int32)
+        self.ctx.check(self.lib.jl_model_batch_forward(self.h, session, ptr(tokens), len(tokens), start_pos))
+
+    def sample(self, session=0, temperature=0.0, uniform=0.0, want_logits=True):
+        tok = C.c_int32()
+        logits = np.empty(self.cfg["vocab"], dtype=np.float32) if want_logits else None
+        self.ctx.check(self.lib.jl_model_sample(self.h, session, C.c_float(temperature), C.c_float(uniform), C.byref(tok),
+                                                ptr(logits)))
+        return tok.value, logits
+
+    def decode(self, tokens, positions, sessions=None, want_logits=False):
+        tokens = np.ascontiguousarray(tokens, dtype=np.int32)
+        positions = np.ascontiguousarray(positions, dtype=np.int32)
+        n = len(tokens)
+        sessions = np.arange(n, dtype=np.int32) if sessions is None else np.ascontiguousarray(sessions, dtype=np.int32)
+        nxt = np.empty(n, dtype=np.int32)
+        logits = np.empty((n, self.cfg["vocab"]), dtype=np.float32) if want_logits else None
+        self.ctx.check(self.lib.jl_model_decode(self.h, n, ptr(sessions), ptr(tokens), ptr(positions), ptr(nxt), ptr(logits)))
+        return nxt, logits
+
+    def decode_resident(self, first_token, start_pos, n_new, session=0):
+        out = np.empty(n_new, dtype=np.int32)
+        self.ctx.check(self.lib.jl_model_decode_resident(self.h, session, int(first_token), start_pos, n_new, ptr(out)))
+        return out
+
+    def generate(self, prompt, n_new, session=0, want_logits=False):
+        prompt = np.ascontiguousarray(prompt, dtype=np.int32)
+        out = np.empty(n_new, dtype=np.int32)
+        logits = np.empty((n_new, self.cfg["vocab"]), dtype=np.float32) if want_logits else None
+        tm = (C.c_double * 2)()
+        self.ctx.check(self.lib.jl_model_generate(self.h, session, ptr(prompt), len(prompt), n_new, ptr(out), ptr(logits), tm))
+        self.last_timings_ms = (tm[0], tm[1])
+        return out, logits
+
+    def read_kv(self, layer, position, which, session=0):
+        out = np.empty(self.dctx.kvSegmentLength, dtype=np.float32)
+        self.ctx.check(self.lib.jl_model_read_kv(self.h, session, layer, position, which, ptr(out)))
+        return out
+
+    def read_hidden(self, session=0):
+        out = np.empty(self.cfg["E"], dtype=np.float32)
+        self.ctx.check(self.lib.jl_model_read_hidden(self.h, session, ptr(out)))
+        return out
+
+    def weight_bytes(self):
+        return int(self.lib.jl_model_weight_bytes(self.h))
+
+    def last_timing(self):
+        a, b = C.c_double(), C.c_double()
+        self.lib.jl_model_last_timing(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def close(self):
+        if self.h:
+            self.lib.jl_model_free(self.h)
+            self.h = None
+            for tid in self._ids:
+                self.lib.jl_unregister_tensor(self.ctx.h, tid)
+            self._ids = []

@@ -1,0 +1,166 @@
+"""ctypes binding of libjlama_b200.so (the C ABI in include/jlama_b200.h).
+
+This is the Python stand-in for the Panama-FFI binding a Jlama maintainer would generate with
+jextract.  There is no fallback: if the shared library is missing or the device is
+not an sm_100 GPU, loading / jl_init fails loudly.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libjlama_b200.so")
+
+JL_OK, JL_ERR_INVALID, JL_ERR_CUDA, JL_ERR_OOM, JL_ERR_UNSUPPORTED, JL_ERR_NCCL = 0, -1, -2, -3, -4, -5
+F32, BF16, Q4, I8 = 0, 1, 2, 3
+MODEL_NO_GRAPH, MODEL_NO_PDL = 1, 2
+
+T_EMBED, T_OUT_NORM, T_LM_HEAD = 0, 1, 2
+L_ATTN_NORM, L_Q, L_K, L_V, L_O, L_FFN_NORM, L_GATE, L_DOWN, L_UP = range(9)
+
+
+class JlamaNativeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("jlama_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class UnsupportedOperation(JlamaNativeError):
+    """UnsupportedOperationException analogue (TestOperations.java:140 relies on it)."""
+
+
+class ModelConfig(C.Structure):
+    _fields_ = [
+        ("context_length", C.c_int), ("embedding_length", C.c_int), ("hidden_length", C.c_int),
+        ("num_heads", C.c_int), ("num_kv_heads", C.c_int), ("num_layers", C.c_int), ("vocab_size", C.c_int),
+        ("head_size", C.c_int), ("layer_norm_eps", C.c_float), ("rope_theta", C.c_double), ("rope_scaling", C.c_double),
+        ("working_qtype", C.c_int), ("kv_dtype", C.c_int), ("max_batch", C.c_int), ("max_sessions", C.c_int),
+        ("max_context", C.c_int), ("tp_rank", C.c_int), ("tp_size", C.c_int), ("prefill_tensor_core", C.c_int),
+        ("flags", C.c_int),
+    ]
+
+
+class Dctx(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "embeddingSegmentStart", "embeddingSegmentLength", "attentionSegmentStart", "attentionSegmentLength",
+        "hiddenSegmentStart", "hiddenSegmentLength", "kvSegmentStart", "kvSegmentLength", "headStart", "headEnd",
+        "groupHeadStart", "groupHeadEnd", "numberOfLayers", "layerStart", "layerEnd")]
+
+
+# every symbol include/jlama_b200.h declares: (restype, argtypes)
+_vp, _i, _i64, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
+SIGNATURES = {
+    "jl_init": (_i, [_i, C.POINTER(_vp), _vp]),
+    "jl_shutdown": (_i, [_vp]),
+    "jl_last_error": (C.c_char_p, [_vp]),
+    "jl_version": (C.c_char_p, []),
+    "jl_sync": (_i, [_vp]),
+    "jl_kernel_launches": (_i64, [_vp]),
+    "jl_register_tensor": (_i64, [_vp, _i, _i64, _i64, _vp, _vp]),
+    "jl_unregister_tensor": (_i, [_vp, _i64]),
+    "jl_gemm": (_i, [_vp, _i, _vp, _vp, _i, _i, _i64, _i, _vp, _i, _i, _i, _i, _i, _i]),
+    "jl_gemm_batch": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i]),
+    "jl_gemm_host": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i]),
+    "jl_accumulate": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i]),
+    "jl_maccumulate": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i]),
+    "jl_scale": (_i, [_vp, _f, _vp, _i, _i, _i, _i]),
+    "jl_saxpy": (_i, [_vp, _f, _vp, _vp, _i, _i, _i]),
+    "jl_saxpy_batch": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i]),
+    "jl_quantize_q8": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "jl_quantize_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "jl_quantize_q4_weights": (_i, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "jl_rmsnorm": (_i, [_vp, _vp, _i, _i, _i, _vp, _f, _f, _i, _i, _i, _vp]),
+    "jl_softmax": (_i, [_vp, _vp, _i, _i]),
+    "jl_silu_mul": (_i, [_vp, _vp, _vp, _i, _i, _i, _i]),
+    "jl_precompute_freqs_cis": (_i, [_i, _i, _d, _d, _vp]),
+    "jl_dctx_build": (_i, [_i] * 10 + [C.POINTER(Dctx)]),
+    "jl_kv_page_geometry": (_i, [_i, _i, _i, _i, _i64, C.POINTER(_i), C.POINTER(_i)]),
+    "jl_model_create": (_i, [_vp, C.POINTER(ModelConfig), C.POINTER(_vp)]),
+    "jl_model_set_tensor": (_i, [_vp, _i, _i, _i64]),
+    "jl_model_finalize": (_i, [_vp]),
+    "jl_model_free": (_i, [_vp]),
+    "jl_model_reset_session": (_i, [_vp, _i]),
+    "jl_model_batch_forward": (_i, [_vp, _i, _vp, _i, _i]),
+    "jl_model_sample": (_i, [_vp, _i, _f, _f, _vp, _vp]),
+    "jl_model_decode": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "jl_model_generate": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
+    "jl_model_decode_resident": (_i, [_vp, _i, C.c_int32, _i, _i, _vp]),
+    "jl_model_read_kv": (_i, [_vp, _i, _i, _i, _i, _vp]),
+    "jl_model_read_hidden": (_i, [_vp, _i, _vp]),
+    "jl_model_weight_bytes": (_i64, [_vp]),
+    "jl_model_last_timing": (_i, [_vp, C.POINTER(_d), C.POINTER(_d)]),
+    "jl_comm_unique_id": (_i, [_vp, _vp]),
+    "jl_comm_init": (_i, [_vp, _vp, _i, _i]),
+    "jl_comm_allreduce_f32": (_i, [_vp, _vp, _i64]),
+    "jl_comm_destroy": (_i, [_vp]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the C-ABI library.  Raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s is missing: run `python -m jlama_b200.build` (or __graft_entry__.build())" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def ptr(a):
+    """numpy array (or None) -> void*"""
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def check(ctx_handle, rc):
+    if rc == JL_OK:
+        return
+    msg = load().jl_last_error(ctx_handle)
+    msg = msg.decode() if msg else ""
+    if rc == JL_ERR_UNSUPPORTED:
+        raise UnsupportedOperation(rc, msg)
+    raise JlamaNativeError(rc, msg)
+
+
+class Context:
+    """jl_ctx owner.  One per process per GPU."""
+
+    def __init__(self, device=0):
+        lib = load()
+        h = C.c_void_p()
+        info = (C.c_int64 * 4)()
+        rc = lib.jl_init(device, C.byref(h), info)
+        if rc != JL_OK:
+            msg = lib.jl_last_error(None)
+            raise JlamaNativeError(rc, (msg.decode() if msg else "") + " -- no CPU fallback exists")
+        self.h = h
+        self.lib = lib
+        self.free_bytes, self.total_bytes, self.sm_count, self.cc = list(info)
+        self.device = device
+
+    def check(self, rc):
+        check(self.h, rc)
+
+    def sync(self):
+        self.check(self.lib.jl_sync(self.h))
+
+    def kernel_launches(self):
+        return int(self.lib.jl_kernel_launches(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.jl_shutdown(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

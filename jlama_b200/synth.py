@@ -1,0 +1,137 @@
+"""Model configs (public HF config.json values) and seeded synthetic checkpoints.
+
+There are no checkpoints or network here, so benchmarks and parity tests run on synthetic weights of
+the real architecture:
+
+  mode "quantize": W ~ N(0, 0.02^2) f32, norm weights 1 + N(0, 0.1^2), then quantised with the
+                   reference quantiser semantics (tensor.quantize_q4 / quantize_q8_weights).
+  mode "direct"  : the packed Q4 bytes and the f32 block scales are drawn directly (uniform nibbles,
+                   scales of magnitude ~0.02/4.6 with random sign) -- every byte pattern is a valid JQ4
+                   tensor, and an 8B model is generated in seconds instead of minutes.
+
+Weights are returned as  name -> (dtype_code, data, scales)  with Jlama's tensor names
+(LlamaModel.java:72,115-141,152-156).
+"""
+import numpy as np
+
+from .native import BF16, F32, I8, Q4
+from .tensor import quantize_q4, quantize_q8_weights
+
+CONFIGS = {
+    # tiny configs for parity tests (the oracle finishes in seconds)
+    "tiny": dict(ctx=256, E=256, H=512, heads=8, kv_heads=4, layers=2, vocab=512, eps=1e-5, rope_theta=10000.0),
+    "tiny-mha": dict(ctx=128, E=128, H=256, heads=4, kv_heads=4, layers=2, vocab=320, eps=1e-5, rope_theta=10000.0),
+    "small": dict(ctx=512, E=512, H=1536, heads=8, kv_heads=2, layers=4, vocab=2048, eps=1e-5, rope_theta=500000.0),
+    "small-hs128": dict(ctx=512, E=1024, H=2048, heads=8, kv_heads=2, layers=2, vocab=1024, eps=1e-5, rope_theta=500000.0),
+    # BASELINE.json configs (public HF config.json dims)
+    "llama-3.2-1b": dict(ctx=131072, E=2048, H=8192, heads=32, kv_heads=8, layers=16, vocab=128256, eps=1e-5,
+                         rope_theta=500000.0, tied=True),
+    "llama-3-8b": dict(ctx=8192, E=4096, H=14336, heads=32, kv_heads=8, layers=32, vocab=128256, eps=1e-5,
+                       rope_theta=500000.0),
+}
+
+SEED0 = 0x4A4C414D41  # "JLAMA"
+
+
+def get_config(name, **over):
+    cfg = dict(CONFIGS[name])
+    cfg.setdefault("tied", False)
+    cfg["name"] = name
+    cfg.update(over)
+    return cfg
+
+
+def _direct_q4(rng, rows, cols, std):
+    q = rng.integers(0, 256, size=(rows, cols // 2), dtype=np.uint8)
+    # uniform nibbles in [-8, 7] have std ~4.61 -> |scale| ~ std/4.61, jittered, random sign
+    mag = (std / 4.61) * (0.5 + rng.random((rows, cols // 32), dtype=np.float32))
+    sign = np.where(rng.random((rows, cols // 32), dtype=np.float32) < 0.5, np.float32(-1), np.float32(1))
+    return q, (mag * sign).astype(np.float32)
+
+
+def _direct_q8(rng, rows, cols, std):
+    q = rng.integers(-127, 128, size=(rows, cols), dtype=np.int8)
+    mag = (std / 73.3) * (0.5 + rng.random((rows, cols // 32), dtype=np.float32))
+    return q, mag.astype(np.float32)
+
+
+def make_tensor(seed, rows, cols, wdtype, mode, std=0.02):
+    rng = np.random.default_rng(seed)
+    if wdtype == Q4:
+        if mode == "direct":
+            q, s = _direct_q4(rng, rows, cols, std)
+        else:
+            q, s = quantize_q4(rng.standard_normal((rows, cols), dtype=np.float32) * np.float32(std))
+        return (Q4, q, s)
+    if wdtype == I8:
+        if mode == "direct":
+            q, s = _direct_q8(rng, rows, cols, std)
+        else:
+            q, s = quantize_q8_weights(rng.standard_normal((rows, cols), dtype=np.float32) * np.float32(std))
+        return (I8, q, s)
+    w = rng.standard_normal((rows, cols), dtype=np.float32) * np.float32(std)
+    if wdtype == BF16:
+        from .tensor import float32_to_bfloat16
+        return (BF16, float32_to_bfloat16(w), None)
+    return (F32, w, None)
+
+
+def tensor_specs(cfg):
+    """(name, rows, cols, kind) for every tensor of a Llama checkpoint; kind in {'linear','norm','embed','head'}."""
+    E, H, V = cfg["E"], cfg["H"], cfg["vocab"]
+    hs = E // cfg["heads"]
+    kvl = cfg["kv_heads"] * hs
+    specs = [("model.embed_tokens.weight", V, E, "embed")]
+    for i in range(cfg["layers"]):
+        b = "model.layers.%d." % i
+        specs += [
+            (b + "input_layernorm.weight", 1, E, "norm"),
+            (b + "self_attn.q_proj.weight", E, E, "linear"),
+            (b + "self_attn.k_proj.weight", kvl, E, "linear"),
+            (b + "self_attn.v_proj.weight", kvl, E, "linear"),
+            (b + "self_attn.o_proj.weight", E, E, "linear"),
+            (b + "post_attention_layernorm.weight", 1, E, "norm"),
+            (b + "mlp.gate_proj.weight", H, E, "linear"),
+            (b + "mlp.down_proj.weight", E, H, "linear"),
+            (b + "mlp.up_proj.weight", H, E, "linear"),
+        ]
+    specs.append(("model.norm.weight", 1, E, "norm"))
+    if not cfg.get("tied"):
+        specs.append(("lm_head.weight", V, E, "head"))
+    return specs
+
+
+def tensor_seed(cfg, name):
+    import zlib
+    return (SEED0 + zlib.crc32(name.encode())) & 0x7FFFFFFFFFFFFFFF
+
+
+def make_one(cfg, name, rows, cols, kind, wdtype=Q4, mode="quantize", embed_dtype=None):
+    seed = tensor_seed(cfg, name)
+    if kind == "norm":
+        rng = np.random.default_rng(seed)
+        return (F32, (1.0 + 0.1 * rng.standard_normal((rows, cols), dtype=np.float32)).astype(np.float32), None)
+    if kind == "embed":
+        # Jlama's quantiser also quantises the embedding table (skip pattern is only "norm",
+        # QuantizeCommand.java:36-38), so a JQ4 checkpoint has a Q4 embedding (LlamaModel.java:91-97)
+        dt = wdtype if embed_dtype is None else embed_dtype
+        return make_tensor(seed, rows, cols, dt, mode, std=0.02 if dt in (Q4, I8) else 1.0)
+    return make_tensor(seed, rows, cols, wdtype, mode)
+
+
+def make_weights(cfg, wdtype=Q4, mode="quantize", embed_dtype=None):
+    """Full synthetic checkpoint in host memory."""
+    return {name: make_one(cfg, name, r, c, kind, wdtype, mode, embed_dtype) for name, r, c, kind in tensor_specs(cfg)}
+
+
+def linear_weight_count(cfg):
+    """Parameters streamed per decoded token: all linear layers + lm_head."""
+    E, H, V = cfg["E"], cfg["H"], cfg["vocab"]
+    hs = E // cfg["heads"]
+    kvl = cfg["kv_heads"] * hs
+    per_layer = E * E * 2 + kvl * E * 2 + H * E * 3
+    return per_layer * cfg["layers"] + V * E
+
+
+def random_prompt(cfg, n, seed=1234):
+    return np.random.default_rng(seed).integers(0, cfg["vocab"], size=n, dtype=np.int32)

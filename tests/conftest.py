@@ -1,0 +1,34 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import oracle as o
+    o.lib()
+    return o
+
+
+@pytest.fixture(scope="session")
+def cuda_ctx():
+    """One jl_ctx for the whole GPU test session; fails loudly if the CUDA library is missing."""
+    from jlama_b200 import native
+    ctx = native.Context(0)
+    yield ctx
+    ctx.close()
+
+
+@pytest.fixture(scope="session")
+def cuda_ops(cuda_ctx):
+    from jlama_b200.ops import CudaTensorOperations
+    return CudaTensorOperations(cuda_ctx)

@@ -1,0 +1,119 @@
+"""CPU tests of the product's host-side logic (numpy mirrors + pure host functions of the C ABI) against the
+oracle, and of the C-ABI library itself: it must load without a GPU and export every declared symbol."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from jlama_b200 import native
+    return native.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "jlama_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(jl_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 40
+    from jlama_b200 import native
+    assert declared == set(native.SIGNATURES), declared ^ set(native.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_init_fails_loudly_without_gpu_or_succeeds_on_sm100(lib):
+    h = C.c_void_p()
+    rc = lib.jl_init(0, C.byref(h), None)
+    if rc == 0:
+        lib.jl_shutdown(h)  # on the GPU box
+    else:
+        assert rc < 0 and not h.value
+        assert b"no CPU fallback" in lib.jl_last_error(None) or b"sm_" in lib.jl_last_error(None)
+
+
+def test_quantiser_mirrors_match_oracle_bit_for_bit(oracle):
+    from jlama_b200 import tensor as T
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal((64, 256)) * 0.02).astype(np.float32)
+    x[3, :32] = 0
+    x[5, 40] = np.float32(1e-45)
+    x[7, 64:96] = -x[7, 64:96].max()  # ties on |v|: first index wins
+    q1, s1 = oracle.quantize_q4(x)
+    q2, s2 = T.quantize_q4(x)
+    assert np.array_equal(q1, q2) and np.array_equal(s1.view(np.uint32), s2.view(np.uint32))
+    assert np.array_equal(oracle.dequantize_q4(q1, s1), T.dequantize_q4(q2, s2))
+    q1, s1 = oracle.quantize_q8_weights(x)
+    q2, s2 = T.quantize_q8_weights(x)
+    assert np.array_equal(q1, q2) and np.array_equal(s1.view(np.uint32), s2.view(np.uint32))
+    a = rng.uniform(-1, 100, (8, 256)).astype(np.float32)
+    a[2, 32:64] = 0
+    q1, s1 = oracle.quantize_q8_act(a)
+    q2, s2 = T.quantize_q8_activations(a)
+    assert np.array_equal(q1, q2) and np.array_equal(s1.view(np.uint32), s2.view(np.uint32))
+    sp = np.concatenate([a.ravel(), np.array([np.nan, np.inf, -np.inf, 1.00390625, 1.01171875], dtype=np.float32)])
+    assert np.array_equal(oracle.f32_to_bf16(sp), T.float32_to_bfloat16(sp))
+
+
+def test_host_functions_match_oracle(lib, oracle):
+    from jlama_b200 import native
+    t = np.empty((300 * 32, 2), dtype=np.float32)
+    assert lib.jl_precompute_freqs_cis(64, 300, 500000.0, 1.0, native.ptr(t)) == 0
+    assert np.array_equal(t, oracle.precompute_freqs_cis(64, 300, 500000.0, 1.0))
+    for args in [(32, 8192, 1024, 4), (16, 131072, 512, 4), (32, 8192, 1024, 2), (2, 256, 128, 4), (4, 512, 128, 4)]:
+        a, b = C.c_int(), C.c_int()
+        assert lib.jl_kv_page_geometry(*args, 1 << 23, C.byref(a), C.byref(b)) == 0
+        assert (a.value, b.value) == oracle.kv_page_solver(args[0], args[1], args[2], args[3])
+    for shard in range(8):
+        d = native.Dctx()
+        assert lib.jl_dctx_build(4096, 4096, 14336, 128, 4, 32, shard, 8, 0, 1, C.byref(d)) == 0
+        o = oracle.dctx(4096, 4096, 14336, 128, 4, 32, shard, 8)
+        for name, _ in native.Dctx._fields_:
+            assert getattr(d, name) == getattr(o, name), name
+    assert lib.jl_dctx_build(4096, 4096, 14336, 128, 4, 32, 8, 8, 0, 1, C.byref(native.Dctx())) < 0
+
+
+def test_synthetic_checkpoint_is_seeded_and_well_formed():
+    from jlama_b200 import synth
+    from jlama_b200.native import F32, Q4
+    cfg = synth.get_config("tiny")
+    w1, w2 = synth.make_weights(cfg), synth.make_weights(cfg)
+    assert set(w1) == {n for n, *_ in synth.tensor_specs(cfg)}
+    for k in w1:
+        assert w1[k][0] == w2[k][0] and np.array_equal(w1[k][1], w2[k][1])
+    dt, q, s = w1["model.layers.0.self_attn.q_proj.weight"]
+    assert dt == Q4 and q.shape == (256, 128) and s.shape == (256, 8) and q.dtype == np.uint8
+    assert w1["model.norm.weight"][0] == F32
+    wd = synth.make_weights(cfg, mode="direct")
+    assert wd["model.layers.1.mlp.down_proj.weight"][1].shape == (256, 256)
+    # 8B weight bytes per token = 4.690 GB
+    n = synth.linear_weight_count(synth.get_config("llama-3-8b"))
+    assert abs(n * 0.625 / 1e9 - 4.690) < 0.01
+
+
+def test_tensor_parallel_slicing_reassembles(oracle):
+    from jlama_b200 import synth
+    from jlama_b200.model import DistributedContext, _slice_cols, _slice_rows
+    cfg = synth.get_config("small")
+    w = synth.make_weights(cfg)
+    t = w["model.layers.0.self_attn.o_proj.weight"]
+    full = oracle.dequantize_q4(t[1], t[2])
+    parts = []
+    for r in range(2):
+        d = DistributedContext(cfg, r, 2)
+        dt, q, s = _slice_cols(t, d.attentionSegmentStart, d.attentionSegmentLength)
+        parts.append(oracle.dequantize_q4(q, s))
+    assert np.array_equal(np.concatenate(parts, axis=1), full)
+    t = w["model.layers.0.self_attn.k_proj.weight"]
+    full = oracle.dequantize_q4(t[1], t[2])
+    parts = []
+    for r in range(2):
+        d = DistributedContext(cfg, r, 2)
+        dt, q, s = _slice_rows(t, d.kvSegmentStart, d.kvSegmentLength)
+        parts.append(oracle.dequantize_q4(q, s))
+    assert np.array_equal(np.concatenate(parts, axis=0), full)
