@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- decode tokens/s of the quantized forward pass (BASELINE.json metric) on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+  python bench.py --impl reference --steps K --warmup W  # the reference's CPU path (jlama-native C kernels
+                                                         # + restated orchestration) on the box's host cores
+
+Workload (config.workload): Llama-3-8B, Jlama-Q4 weights (synthetic, real dims), Q8 activations, F32 KV,
+batch-1 greedy decode after a short prompt.  One "step" = one decoded token (forward(token, pos) + sample).
+
+  value : tokens/s with the token ids resident in HBM (device-side feedback loop, CUDA-graph replays),
+          timed with CUDA events on the model stream, max over ranks.
+  e2e   : tokens/s through the reference-facing C-ABI call jl_model_decode with HOST buffers: every step
+          copies token/position/session ids host->device from pinned memory and the sampled token back.
+  roofline : dominant kernel = the quantised GEMV; achieved = algorithmic weight bytes per token
+          (0.625 B/weight Q4 incl. f32 block scales) / summed GEMV launch durations per token
+          measured with CUDA events around every GEMV launch (eager, un-overlapped); peak = MEASURED_PEAKS.json.
+          step_frac = the same bytes / whole-step time (the north-star "fraction of HBM roofline").
+  cpu_baseline : the oracle driving the reference's own C kernels (oracle/_ref) on a bounded sample.
+
+Timing hygiene: W>=3 warm-up steps; weights (4.7 GB/token) are far larger than the 126 MB L2, so no L2
+flush is needed ("inputs larger than L2"); clocks sampled with nvidia-smi during the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.proc, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_model_weights(cfg, mode):
+    from jlama_b200 import native, synth
+    t0 = time.time()
+    w = synth.make_weights(cfg, wdtype=native.Q4, mode=mode)
+    log("[bench] synthetic %s checkpoint (%s) generated in %.1fs" % (cfg["name"], mode, time.time() - t0))
+    return w
+
+
+def cpu_reference_decode(cfg, weights, prompt, n_new, threads=None):
+    """Reference-equivalent CPU path: restated orchestration + the reference's own C kernels (oracle/_ref)."""
+    from oracle import oracle as o
+    label = o.load_reference_kernels()
+    o.use_reference_kernels(label is not None)
+    # the reference's default executor: max(2, availableProcessors/2) threads (PhysicalCoreExecutor.java:27)
+    o.set_num_threads(threads or max(2, o.available_cpus() // 2))
+    m = o.OracleLlama(cfg, weights, act_q8=True)
+    m.reset()
+    t0 = time.time()
+    hidden = m.batch_forward(prompt, 0)
+    tok, logits0 = m.sample(hidden)
+    t1 = time.time()
+    toks, step_logits = [tok], [logits0]
+    for i in range(1, n_new):
+        hidden = m.batch_forward([toks[-1]], len(prompt) + i - 1)
+        tok, lg = m.sample(hidden)
+        toks.append(tok)
+        step_logits.append(lg)
+    t2 = time.time()
+    m.close()
+    return dict(tokens=toks, logits=step_logits, prefill_s=t1 - t0, decode_s=t2 - t1, kind="reference" if label else "port",
+                label=label or "plain-C restatement (oracle/jlama_oracle.c)", threads=o.num_threads())
+
+
+def run_reference_arm(args):
+    from jlama_b200 import synth
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = synth.get_config(args.model)
+    w = make_model_weights(cfg, args.weights)
+    prompt = synth.random_prompt(cfg, args.prompt)
+    n = args.warmup + args.steps
+    from oracle import oracle as o
+    label = o.load_reference_kernels()
+    o.use_reference_kernels(label is not None)
+    # "all the host threads it can use", capped where more threads stop helping a bandwidth-bound GEMV
+    o.set_num_threads(args.cpu_threads or min(o.available_cpus(), 64))
+    log("[bench] reference arm: %s, %d threads (of %d available CPUs)" % (label, o.num_threads(), o.available_cpus()))
+    m = o.OracleLlama(cfg, w, act_q8=True)
+    m.reset()
+    hidden = m.batch_forward(prompt, 0)
+    tok, _ = m.sample(hidden)
+    pos = len(prompt)
+    for _ in range(args.warmup):
+        hidden = m.batch_forward([tok], pos)
+        tok, _ = m.sample(hidden)
+        pos += 1
+    t0 = time.time()
+    for _ in range(args.steps):
+        hidden = m.batch_forward([tok], pos)
+        tok, _ = m.sample(hidden)
+        pos += 1
+    dt = time.time() - t0
+    val = args.steps / dt
+    cores = o.num_threads()
+    out = {
+        "impl": "reference", "metric": "decode tokens/s", "value": val, "unit": "tokens/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "int8xint4->f32", "data": "synthetic",
+        "config": {"workload": "%s JQ4, batch=1 greedy decode after %d-token prompt (CPU: %s, %d threads)" % (
+            cfg["name"], args.prompt, label or "plain-C restatement", cores), "parallelism": "cpu"},
+        "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": cores, "kind": "reference" if label else "port",
+                         "sample": "%d decode steps after a %d-token prompt" % (args.steps, args.prompt)},
+        "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--warmup", type=int, default=16)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="llama-3-8b")
+    ap.add_argument("--weights", default="direct", choices=["direct", "quantize"])
+    ap.add_argument("--prompt", type=int, default=32)
+    ap.add_argument("--cpu-tokens", type=int, default=6, help="decode steps of the cpu_baseline sample")
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-mega", action="store_true", help="kernel-per-op decode instead of the persistent megakernel")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    from jlama_b200 import native, synth
+    from jlama_b200.model import LlamaModel
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        log("[bench] WORLD_SIZE=%d but --gpus %d; using WORLD_SIZE" % (world, args.gpus))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl")
+
+    cfg = synth.get_config(args.model)
+    ctx = native.Context(local_rank)
+    if world > 1:
+        import torch
+        idbuf = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            ctx.check(ctx.lib.jl_comm_unique_id(ctx.h, native.ptr(idbuf)))
+        t = torch.from_numpy(idbuf).cuda()
+        dist.broadcast(t, 0)
+        idbuf = t.cpu().numpy()
+        ctx.check(ctx.lib.jl_comm_init(ctx.h, native.ptr(idbuf), rank, world))
+
+    weights = make_model_weights(cfg, args.weights)
+    prompt = synth.random_prompt(cfg, args.prompt)
+    n_total = args.prompt + 2 * (args.warmup + args.steps) + 64
+    t0 = time.time()
+    model = LlamaModel(ctx, cfg, weights, max_context=min(cfg["ctx"], max(512, n_total)), tp_rank=rank, tp_size=world,
+                       flags=native.MODEL_NO_MEGA if args.no_mega else 0)
+    log("[bench] rank %d: weights uploaded in %.1fs (%.3f GB streamed per token on this rank)" % (
+        rank, time.time() - t0, model.weight_bytes() / 1e9))
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- prefill + parity reference tokens -------------------------------------------------------------
+    model.reset_session(0)
+    barrier()
+    t0 = time.time()
+    model.batch_forward(prompt, 0)
+    first, _ = model.sample(want_logits=False)
+    ctx.sync()
+    prefill_s = max_over_ranks(time.time() - t0)
+
+    # ---- value: resident decode loop (CUDA graph replays, token ids stay in HBM) --------------------------
+    pos = len(prompt)
+    launches0 = ctx.kernel_launches()
+    warm = model.decode_resident(first, pos, args.warmup)
+    pos += args.warmup
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.15)
+    l0 = ctx.kernel_launches()
+    toks = model.decode_resident(int(warm[-1]), pos, args.steps)
+    total_ms, _ = model.last_timing()
+    barrier()
+    launches = ctx.kernel_launches() - l0
+    total_ms = max_over_ranks(total_ms)
+    pos += args.steps
+    value = args.steps / (total_ms / 1000.0)
+
+    # ---- e2e: the C-ABI call with host buffers, every step ---------------------------------------------------
+    tok = np.array([toks[-1]], dtype=np.int32)
+    for i in range(args.warmup):
+        tok, _ = model.decode(tok, np.array([pos], dtype=np.int32), np.array([0], dtype=np.int32))
+        pos += 1
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        tok, _ = model.decode(tok, np.array([pos], dtype=np.int32), np.array([0], dtype=np.int32))
+        pos += 1
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop()
+    e2e = args.steps / e2e_s
+
+    peak, peak_src = measured_peaks()
+    wbytes = model.weight_bytes()
+    result = {
+        "metric": "decode tokens/s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "int8xint4->f32", "data": "synthetic",
+        "config": {"workload": "%s JQ4 (Q4 weights + f32 block scales, Q8 activations, F32 KV), batch=1 greedy decode, "
+                               "%d-token prompt, %s synthetic weights" % (cfg["name"], args.prompt, args.weights),
+                   "parallelism": "tp%d" % world if world > 1 else "single-gpu",
+                   "l2": "inputs larger than L2 (%.2f GB of weights per token per rank vs 126 MB L2)" % (wbytes / 1e9),
+                   "prefill_tokens_per_s": args.prompt / prefill_s},
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 12, "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+    }
+
+    # ---- roofline of the dominant kernel -------------------------------------------------------------------------------
+    mode = model.decode_mode(1)
+    step_frac = (wbytes / 1e9) / (total_ms / args.steps / 1e3) / peak
+    if mode == 2:
+        # the persistent megakernel IS the step: one launch per token, timed with CUDA events on the model stream
+        achieved = (wbytes / 1e9) / (total_ms / args.steps / 1e3)
+        result["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                              "traffic": None, "kernel": "mega_decode_kernel (one launch per decoded token)",
+                              "bytes_per_launch": wbytes, "us_per_launch": 1000.0 * total_ms / args.steps,
+                              "peak_source": peak_src, "step_frac": step_frac}
+    elif not args.no_roofline:
+        # kernel-per-op path: eager, event-timed GEMV launches (rank 0 shard; same on every rank)
+        model.close()
+        model = LlamaModel(ctx, cfg, weights, max_context=min(cfg["ctx"], max(512, n_total)), tp_rank=rank, tp_size=world,
+                           flags=native.MODEL_NO_GRAPH | native.MODEL_NO_PDL | native.MODEL_NO_MEGA)
+        model.reset_session(0)
+        model.batch_forward(prompt, 0)
+        f2, _ = model.sample(want_logits=False)
+        model.decode_resident(f2, len(prompt), 8)
+        nprof = min(32, args.steps)
+        model.decode_resident(f2, len(prompt) + 8, nprof)
+        tot, gemv = model.last_timing()
+        gemv_ms = max_over_ranks(gemv) / nprof
+        achieved = wbytes / 1e9 / (gemv_ms / 1e3)
+        result["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                              "traffic": None, "kernel": "gemv_kernel (all quantised GEMV launches of one token)",
+                              "bytes_per_launch_set": wbytes, "gemv_ms_per_token": gemv_ms, "peak_source": peak_src,
+                              "step_frac": step_frac}
+    else:
+        result["roofline"] = {"bound": "hbm", "achieved": step_frac * peak, "peak": peak, "unit": "GB/s", "frac": step_frac,
+                              "traffic": None, "peak_source": peak_src, "note": "whole-step time used (roofline pass skipped)"}
+    result["config"]["decode_mode"] = {2: "persistent megakernel", 1: "cuda graph of per-op kernels", 0: "eager"}[mode]
+
+    # ---- cpu_baseline + in-run parity (rank 0, N=1 only) --------------------------------------------------------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_cpu = max(2, args.cpu_tokens)
+        cp = prompt[:min(len(prompt), 8)]
+        r = cpu_reference_decode(cfg, weights, cp, n_cpu, threads=args.cpu_threads or None)
+        gt, gl = model.generate(cp, n_cpu, want_logits=True)
+        rel = max(float(np.abs(gl[i] - r["logits"][i]).max() / np.abs(r["logits"][i]).max()) for i in range(n_cpu))
+        result["cpu_baseline"] = {"value": (n_cpu - 1) / r["decode_s"], "unit": "tokens/s", "cores": r["threads"], "kind": r["kind"],
+                                  "sample": "%d decode steps after an %d-token prompt, %s" % (n_cpu - 1, len(cp), r["label"]),
+                                  "prefill_tokens_per_s": len(cp) / r["prefill_s"]}
+        result["parity"] = {"tokens_equal": [int(a) for a in gt] == [int(b) for b in r["tokens"]], "max_logit_rel_err": rel,
+                            "tolerance": 1e-2}
+    model.close()
+    if rank == 0:
+        print(json.dumps(result), flush=True)
+    if dist is not None:
+        dist.barrier()
+        ctx.lib.jl_comm_destroy(ctx.h)
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

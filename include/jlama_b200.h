@@ -55,6 +55,13 @@ int jl_sync(jl_ctx *ctx);
 /* number of kernels this library launched since jl_init (bench.py's gpu_launches claim) */
 int64_t jl_kernel_launches(jl_ctx *ctx);
 
+/* diagnostic: time the quantised GEMV kernel on device-resident operands.  `b_id` is a registered weight
+ * [rows, k]; each of `iters` launches handles `n` consecutive rows starting at a rotating offset so that the
+ * stream of weights is larger than L2; activations [m, k] f32 live in HBM.  mode: 0 = Q8-quantising prologue +
+ * store, 1 = RMSNorm + Q8 prologue + store, 2 = f32 activations + store, 3 = Q8 prologue + residual epilogue.
+ * Returns the average microseconds per launch measured with CUDA events around the whole sequence. */
+int jl_debug_gemv_bench(jl_ctx *ctx, int64_t b_id, int n, int m, int mode, int iters, int use_pdl, double *avg_us);
+
 /* ---- TensorOperations.registerModelTensor (core/tensor/operations/TensorOperations.java:39;
  *      NativeGPUTensorOperations.java:104-151 -> register_tensor, vector_gpu.h:10) ------------
  * Copies a weight (and its Q4/I8 block scales) to HBM once; returns a tensor id, -1 on failure.
@@ -162,6 +169,7 @@ typedef struct {
 
 #define JL_MODEL_NO_GRAPH 1 /* launch decode kernels eagerly instead of through a CUDA graph */
 #define JL_MODEL_NO_PDL 2   /* disable programmatic dependent launch between decode kernels */
+#define JL_MODEL_NO_MEGA 4  /* decode with one kernel per op instead of the persistent megakernel */
 
 /* tensor slots */
 #define JL_T_EMBED 0
@@ -210,6 +218,8 @@ int jl_model_decode_resident(jl_model *m, int session, int32_t first_token, int 
 /* test hooks: copy a K/V row (f32) or the hidden rows of the last batch_forward chunk to HOST */
 int jl_model_read_kv(jl_model *m, int session, int layer, int position, int which /*0=K,1=V*/, float *out);
 int jl_model_read_hidden(jl_model *m, int session, float *out /* [embedding_length] last row */);
+/* how jl_model_decode executes for n sessions: 2 = persistent megakernel, 1 = CUDA-graph of per-op kernels, 0 = eager */
+int jl_model_decode_mode(jl_model *m, int n);
 /* per-token algorithmic bytes of the decode weight stream on this rank (roofline numerator) */
 int64_t jl_model_weight_bytes(jl_model *m);
 /* event-timed duration (ms) of the last jl_model_decode / decode_resident GPU work, and of its

@@ -69,83 +69,152 @@ __device__ __forceinline__ void load_chunk(WBuf<WDT> &b, const uint8_t *wrow, co
 // F32 layout in smem: f[m][c4(8)][blk][4] floats
 __device__ __forceinline__ size_t q8_bytes_per_row(int nblk) { return (size_t)nblk * 32 + (size_t)nblk * 8; }
 
+// One thread owns one 32-element block: 8 independent 128-bit loads, the block max, the Q8 rounding
+// and the packing all stay in registers (no shuffles), so the prologue costs about one L2 round trip.
 template <bool ACTQ8, int MM>
 __device__ void stage_activations(const GemvParams &p, int prologue, unsigned char *smem, int nblk) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __shared__ double red[GEMV_WARPS];
-    __shared__ float rs_sh;
+    __shared__ double red[MM][GEMV_WARPS];
+    __shared__ float rs_sh[MM];
     int8_t *aq = (int8_t *)smem;
     float *asc = (float *)(smem + (size_t)MM * nblk * 32);
     int *asum = (int *)(smem + (size_t)MM * nblk * 32 + (size_t)MM * nblk * 4);
-    float *af = (float *)smem;
+    float4 *af4 = (float4 *)smem;
     const int K = p.K;
+    const bool norm = (prologue == PRO_RMSNORM_QUANT || prologue == PRO_RMSNORM_F32);
 
-    for (int m = 0; m < MM; m++) {
-        const bool live = m < p.M;
-        float rsf = 1.0f;
-        const bool norm = (prologue == PRO_RMSNORM_QUANT || prologue == PRO_RMSNORM_F32);
-        const float *x = (const float *)p.a + (size_t)m * p.lda + p.a_col_off;
-        if (norm && live) {
-            // RMSNorm.java:41-52: float products summed in double over [0, E)
-            double ss = 0.0;
-            for (int i = tid; i < K; i += GEMV_THREADS) {
-                float v = x[i];
-                ss += (double)__fmul_rn(v, v);
+    if (norm) {
+        // RMSNorm.java:41-52: float products summed in double over [0, E), all rows in one pass
+        double ss[MM];
+#pragma unroll
+        for (int m = 0; m < MM; m++) ss[m] = 0.0;
+        for (int i4 = tid; i4 < K / 4; i4 += GEMV_THREADS) {
+            float4 v[MM];
+#pragma unroll
+            for (int m = 0; m < MM; m++)
+                v[m] = m < p.M ? *(const float4 *)((const float *)p.a + (size_t)m * p.lda + p.a_col_off + i4 * 4)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int m = 0; m < MM; m++) {
+                ss[m] += (double)__fmul_rn(v[m].x, v[m].x);
+                ss[m] += (double)__fmul_rn(v[m].y, v[m].y);
+                ss[m] += (double)__fmul_rn(v[m].z, v[m].z);
+                ss[m] += (double)__fmul_rn(v[m].w, v[m].w);
             }
-            ss = warp_sum_d(ss);
-            if (lane == 0) red[warp] = ss;
-            __syncthreads();
-            if (tid == 0) {
-                double t = 0;
-                for (int w = 0; w < GEMV_WARPS; w++) t += red[w];
-                t /= (double)p.norm_E;
-                t += (double)p.norm_eps;
-                rs_sh = (float)(1.0 / sqrt(t));
-            }
-            __syncthreads();
-            rsf = rs_sh;
         }
-        // one warp per 32-element block
-        for (int b = warp; b < nblk; b += GEMV_WARPS) {
-            float v = 0.0f;
+#pragma unroll
+        for (int m = 0; m < MM; m++) {
+            ss[m] = warp_sum_d(ss[m]);
+            if (lane == 0) red[m][warp] = ss[m];
+        }
+        __syncthreads();
+        if (tid < MM) {
+            double t = 0;
+            for (int w = 0; w < GEMV_WARPS; w++) t += red[tid][w];
+            t /= (double)p.norm_E;
+            t += (double)p.norm_eps;
+            rs_sh[tid] = (float)(1.0 / sqrt(t));
+        }
+        __syncthreads();
+    }
+
+    for (int idx = tid; idx < MM * nblk; idx += GEMV_THREADS) {
+        const int m = idx / nblk, b = idx - m * nblk;
+        const bool live = m < p.M;
+        if (prologue == PRO_Q8_GLOBAL) {
+            uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+            float sc = 0.0f;
             if (live) {
-                if (prologue == PRO_Q8_GLOBAL) {
-                    int8_t qv = ((const int8_t *)p.a)[(size_t)m * p.lda + p.a_col_off + b * 32 + lane];
-                    int s = __reduce_add_sync(0xffffffffu, (int)qv);
-                    aq[(((size_t)m * 2 + (lane >> 4)) * nblk + b) * 16 + (lane & 15)] = qv;
-                    if (lane == 0) {
-                        asc[m * nblk + b] = p.a_scales[(size_t)m * (p.lda / 32) + p.a_col_off / 32 + b];
-                        asum[m * nblk + b] = s;
+                const int8_t *src = (const int8_t *)p.a + (size_t)m * p.lda + p.a_col_off + b * 32;
+                lo = *(const uint4 *)src;
+                hi = *(const uint4 *)(src + 16);
+                sc = p.a_scales[(size_t)m * (p.lda / 32) + p.a_col_off / 32 + b];
+            }
+            int sum = 0;
+            sum = __dp4a((int)lo.x, 0x01010101, sum);
+            sum = __dp4a((int)lo.y, 0x01010101, sum);
+            sum = __dp4a((int)lo.z, 0x01010101, sum);
+            sum = __dp4a((int)lo.w, 0x01010101, sum);
+            sum = __dp4a((int)hi.x, 0x01010101, sum);
+            sum = __dp4a((int)hi.y, 0x01010101, sum);
+            sum = __dp4a((int)hi.z, 0x01010101, sum);
+            sum = __dp4a((int)hi.w, 0x01010101, sum);
+            *(uint4 *)(aq + (((size_t)m * 2 + 0) * nblk + b) * 16) = lo;
+            *(uint4 *)(aq + (((size_t)m * 2 + 1) * nblk + b) * 16) = hi;
+            asc[m * nblk + b] = sc;
+            asum[m * nblk + b] = sum;
+            continue;
+        }
+        float v[32];
+        if (!live) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = 0.0f;
+        } else if (prologue == PRO_BF16_GLOBAL) {
+            const uint4 *src = (const uint4 *)((const uint16_t *)p.a + (size_t)m * p.lda + p.a_col_off + b * 32);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint4 u = src[i];
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    v[i * 8 + t * 2] = __uint_as_float(w[t] << 16);
+                    v[i * 8 + t * 2 + 1] = __uint_as_float(w[t] & 0xffff0000u);
+                }
+            }
+        } else {
+            const float4 *src = (const float4 *)((const float *)p.a + (size_t)m * p.lda + p.a_col_off + b * 32);
+            float4 x4[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) x4[i] = src[i];
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i * 4] = x4[i].x, v[i * 4 + 1] = x4[i].y, v[i * 4 + 2] = x4[i].z, v[i * 4 + 3] = x4[i].w;
+            if (norm) {
+                const float rsf = rs_sh[m];
+                if (p.norm_w_dtype == JL_BF16) {
+                    const uint16_t *wp = (const uint16_t *)p.norm_w + b * 32;
+#pragma unroll
+                    for (int i = 0; i < 32; i++)
+                        v[i] = __fmul_rn(__fadd_rn(p.norm_adj, bf16_bits_to_f32(wp[i])), __fmul_rn(rsf, v[i]));
+                } else {
+                    const float4 *wp = (const float4 *)((const float *)p.norm_w + b * 32);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const float4 w4 = wp[i];
+                        v[i * 4] = __fmul_rn(__fadd_rn(p.norm_adj, w4.x), __fmul_rn(rsf, v[i * 4]));
+                        v[i * 4 + 1] = __fmul_rn(__fadd_rn(p.norm_adj, w4.y), __fmul_rn(rsf, v[i * 4 + 1]));
+                        v[i * 4 + 2] = __fmul_rn(__fadd_rn(p.norm_adj, w4.z), __fmul_rn(rsf, v[i * 4 + 2]));
+                        v[i * 4 + 3] = __fmul_rn(__fadd_rn(p.norm_adj, w4.w), __fmul_rn(rsf, v[i * 4 + 3]));
                     }
-                    continue;
-                }
-                if (prologue == PRO_BF16_GLOBAL)
-                    v = bf16_bits_to_f32(((const uint16_t *)p.a)[(size_t)m * p.lda + p.a_col_off + b * 32 + lane]);
-                else
-                    v = x[b * 32 + lane];
-                if (norm) {
-                    int col = b * 32 + lane;
-                    float w = p.norm_w_dtype == JL_BF16 ? bf16_bits_to_f32(((const uint16_t *)p.norm_w)[col])
-                                                        : ((const float *)p.norm_w)[col];
-                    v = __fmul_rn(__fadd_rn(p.norm_adj, w), __fmul_rn(rsf, v));
                 }
             }
-            if (ACTQ8) {
-                // PanamaTensorOperations.java:1696-1710
-                float mx = warp_max(fabsf(v));
-                float d = __fdiv_rn(mx, 127.0f);
-                float id = mx != 0.0f ? __fdiv_rn(127.0f, mx) : 0.0f;
-                int qi = (int)__fadd_rn(__fmul_rn(v, id), 0.5f); // F2B truncation toward zero
-                int8_t qv = (int8_t)qi;
-                int s = __reduce_add_sync(0xffffffffu, (int)qv);
-                aq[(((size_t)m * 2 + (lane >> 4)) * nblk + b) * 16 + (lane & 15)] = qv;
-                if (lane == 0) {
-                    asc[m * nblk + b] = d;
-                    asum[m * nblk + b] = s;
-                }
-            } else {
-                af[(((size_t)m * 8 + (lane >> 2)) * nblk + b) * 4 + (lane & 3)] = v;
+        }
+        if (ACTQ8) {
+            // PanamaTensorOperations.java:1696-1710: d = max/127, q = (byte)(x*(127/max) + 0.5f), F2B truncates
+            float mx = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 32; i++) mx = fmaxf(mx, fabsf(v[i]));
+            const float d = __fdiv_rn(mx, 127.0f);
+            const float id = mx != 0.0f ? __fdiv_rn(127.0f, mx) : 0.0f;
+            uint32_t w[8];
+            int sum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int q0 = (int)__fadd_rn(__fmul_rn(v[i * 4], id), 0.5f);
+                const int q1 = (int)__fadd_rn(__fmul_rn(v[i * 4 + 1], id), 0.5f);
+                const int q2 = (int)__fadd_rn(__fmul_rn(v[i * 4 + 2], id), 0.5f);
+                const int q3 = (int)__fadd_rn(__fmul_rn(v[i * 4 + 3], id), 0.5f);
+                sum += q0 + q1 + q2 + q3;
+                w[i] = (uint32_t)(q0 & 0xFF) | ((uint32_t)(q1 & 0xFF) << 8) | ((uint32_t)(q2 & 0xFF) << 16) |
+                       ((uint32_t)(q3 & 0xFF) << 24);
             }
+            *(uint4 *)(aq + (((size_t)m * 2 + 0) * nblk + b) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+            *(uint4 *)(aq + (((size_t)m * 2 + 1) * nblk + b) * 16) = make_uint4(w[4], w[5], w[6], w[7]);
+            asc[m * nblk + b] = d;
+            asum[m * nblk + b] = sum;
+        } else {
+#pragma unroll
+            for (int c4 = 0; c4 < 8; c4++)
+                af4[((size_t)m * 8 + c4) * nblk + b] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
         }
     }
     __syncthreads();
@@ -237,7 +306,7 @@ __device__ __forceinline__ void compute_chunk(const WBuf<WDT> &w, float (&acc)[M
 }
 
 template <int WDT, bool ACTQ8, int EPI, int MM>
-__global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvParams p, const int prologue) {
+__global__ void __launch_bounds__(GEMV_THREADS, (MM == 1 && WDT == JL_Q4) ? 3 : (MM <= 2 ? 2 : 1)) gemv_kernel(const GemvParams p, const int prologue) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nblk = p.K / 32;
@@ -441,7 +510,7 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_dense_kernel(const GemvPara
 template <int WDT, bool ACTQ8, int EPI, int MM>
 static int launch_q(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int prologue, bool pdl, int grid, size_t smem) {
     auto kern = gemv_kernel<WDT, ACTQ8, EPI, MM>;
-    if (smem > 48 * 1024) {
+    if (smem > 40 * 1024) { // static shared memory of the prologue counts against the 48 KB default too
         static thread_local size_t configured = 0; // per-instantiation high-water mark
         if (smem > configured) {
             JL_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -477,7 +546,7 @@ static int launch_dense(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, i
     auto kern = gemv_dense_kernel<WDT, EPI, MM>;
     size_t smem = (size_t)MM * p.K * 4;
     if (smem > 200 * 1024) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "dense gemv: M*K too large for shared memory");
-    if (smem > 48 * 1024)
+    if (smem > 40 * 1024)
         JL_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     JL_CUDA_CHECK(ctx, jl_launch_kernel(kern, dim3(grid), dim3(GEMV_THREADS), smem, stream, pdl, p, prologue));
     ctx->launches++;

@@ -6,6 +6,7 @@
 // never leave HBM, KV lives in device pages shaped like KvBufferCache's, and the per-token decode
 // step is captured once into a CUDA graph with programmatic dependent launch between kernels.
 #include "jl_common.cuh"
+#include "jl_mega.cuh"
 
 #include <chrono>
 #include <map>
@@ -45,6 +46,7 @@ struct jl_model {
     int hist_cap = 0;
     // graphs keyed by (n, splits, resident)
     std::map<long long, cudaGraphExec_t> graphs;
+    std::map<long long, long long> graph_launches; // kernels per graph replay
     // eager-mode event timing of the GEMV launches
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
@@ -52,6 +54,11 @@ struct jl_model {
     double last_total_ms = 0, last_gemv_ms = 0;
     bool timing_valid = false;
     int64_t weight_bytes = 0;
+    // persistent megakernel
+    bool mega_ok = false;
+    MegaLayer *mega_layers = nullptr;
+    unsigned *mega_sync = nullptr, *mega_att_done = nullptr;
+    unsigned long long *mega_slots = nullptr;
 };
 
 #define M_CHECK(expr)                 \
@@ -62,6 +69,7 @@ struct jl_model {
 
 static bool use_pdl(const jl_model *m) { return !(m->cfg.flags & JL_MODEL_NO_PDL); }
 static bool use_graph(const jl_model *m) { return !(m->cfg.flags & JL_MODEL_NO_GRAPH); }
+static bool use_mega(const jl_model *m) { return m->mega_ok && !(m->cfg.flags & JL_MODEL_NO_MEGA); }
 
 extern "C" int jl_model_create(jl_ctx *ctx, const jl_model_config *cfg, jl_model **out) {
     if (!ctx || !cfg || !out) return JL_ERR_INVALID;
@@ -226,6 +234,34 @@ extern "C" int jl_model_finalize(jl_model *m) {
         for (int s : {JL_L_Q, JL_L_K, JL_L_V, JL_L_O, JL_L_GATE, JL_L_DOWN, JL_L_UP}) wb += tb(m->l[(size_t)L * 9 + s]);
     wb += tb(m->g_set[JL_T_LM_HEAD] ? m->g[JL_T_LM_HEAD] : m->g[JL_T_EMBED]);
     m->weight_bytes = wb;
+    // ---- persistent megakernel eligibility: all linear weights Q4, Q8 activations, single rank ----
+    {
+        bool ok = c.working_qtype == JL_I8 && c.tp_size == 1;
+        const DevTensor &head = m->g_set[JL_T_LM_HEAD] ? m->g[JL_T_LM_HEAD] : m->g[JL_T_EMBED];
+        ok = ok && head.dtype == JL_Q4;
+        for (int L = 0; L < c.num_layers && ok; L++)
+            for (int sl : {JL_L_Q, JL_L_K, JL_L_V, JL_L_O, JL_L_GATE, JL_L_DOWN, JL_L_UP}) ok = ok && m->l[(size_t)L * 9 + sl].dtype == JL_Q4;
+        if (ok) {
+            std::vector<MegaLayer> ml(c.num_layers);
+            const int order[7] = {JL_L_Q, JL_L_K, JL_L_V, JL_L_O, JL_L_GATE, JL_L_UP, JL_L_DOWN};
+            for (int L = 0; L < c.num_layers; L++) {
+                for (int i = 0; i < 7; i++) {
+                    ml[L].w[i] = (const uint8_t *)m->l[(size_t)L * 9 + order[i]].data;
+                    ml[L].s[i] = m->l[(size_t)L * 9 + order[i]].scales;
+                }
+                ml[L].attn_norm = m->l[(size_t)L * 9 + JL_L_ATTN_NORM].data;
+                ml[L].attn_norm_dt = m->l[(size_t)L * 9 + JL_L_ATTN_NORM].dtype;
+                ml[L].ffn_norm = m->l[(size_t)L * 9 + JL_L_FFN_NORM].data;
+                ml[L].ffn_norm_dt = m->l[(size_t)L * 9 + JL_L_FFN_NORM].dtype;
+            }
+            M_CHECK(dev_alloc(ctx, (void **)&m->mega_layers, ml.size() * sizeof(MegaLayer)));
+            JL_CUDA_CHECK(ctx, cudaMemcpy(m->mega_layers, ml.data(), ml.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice));
+            M_CHECK(dev_alloc(ctx, (void **)&m->mega_sync, jl_mega_sync_words(c.num_layers) * sizeof(unsigned)));
+            M_CHECK(dev_alloc(ctx, (void **)&m->mega_att_done, (size_t)c.num_layers * MEGA_MAX_M * m->kv_heads_local * sizeof(unsigned)));
+            M_CHECK(dev_alloc(ctx, (void **)&m->mega_slots, (size_t)MEGA_MAX_M * ctx->sm_count * sizeof(unsigned long long)));
+            m->mega_ok = true;
+        }
+    }
     m->finalized = true;
     return JL_OK;
 }
@@ -242,7 +278,7 @@ extern "C" int jl_model_free(jl_model *m) {
         if (p) cudaFree(p);
     void *bufs[] = {m->rope, m->page_table_dev, m->x, m->xb, m->q, m->k, m->v, m->att, m->hbuf, m->partial, m->logits,
                     m->last_hidden, m->attn_ws, m->d_tokens, m->d_positions, m->d_sessions, m->d_next, m->d_hist, m->d_counter,
-                    m->argmax_scratch};
+                    m->argmax_scratch, m->mega_layers, m->mega_sync, m->mega_att_done, m->mega_slots};
     for (void *p : bufs)
         if (p) cudaFree(p);
     if (m->h_pinned) cudaFreeHost(m->h_pinned);
@@ -519,7 +555,8 @@ extern "C" int jl_model_batch_forward(jl_model *m, int session, const int32_t *t
     return JL_OK;
 }
 
-__global__ void softmax_sample_kernel(float *logits, int vocab, float temperature, float uniform, int32_t *out);
+__global__ void __launch_bounds__(256) softmax_sample_kernel(float *logits, int vocab, float temperature, float uniform,
+                                                             int32_t *out);
 
 extern "C" int jl_model_sample(jl_model *m, int session, float temperature, float uniform, int32_t *token_out,
                                float *logits_out) {
@@ -530,7 +567,7 @@ extern "C" int jl_model_sample(jl_model *m, int session, float temperature, floa
     M_CHECK(sample_rows(m, m->last_hidden + (size_t)session * E, 1, false));
     if (temperature != 0.0f) {
         // AbstractModel.java:475-487: exp((l - max)/T), float prefix sum against the uniform sample
-        softmax_sample_kernel<<<1, 1024, 0, m->stream>>>(m->logits, V, temperature, uniform, m->d_next);
+        softmax_sample_kernel<<<1, 256, 0, m->stream>>>(m->logits, V, temperature, uniform, m->d_next);
         ctx->launches++;
         JL_CUDA_CHECK(ctx, cudaGetLastError());
     }
@@ -544,10 +581,11 @@ extern "C" int jl_model_sample(jl_model *m, int session, float temperature, floa
 
 // exp((l-max)/T) then the first index whose running sum reaches `uniform` (AbstractModel.java:475-489).
 // Sequential prefix order is part of the semantics, so one thread walks the normalised values.
-__global__ void softmax_sample_kernel(float *logits, int vocab, float temperature, float uniform, int32_t *out) {
+__global__ void __launch_bounds__(256) softmax_sample_kernel(float *logits, int vocab, float temperature, float uniform,
+                                                             int32_t *out) {
     __shared__ float red[32];
     __shared__ float bc;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     float mx = -INFINITY;
     for (int i = tid; i < vocab; i += blockDim.x) mx = fmaxf(mx, logits[i]);
     mx = warp_max(mx);
@@ -555,7 +593,7 @@ __global__ void softmax_sample_kernel(float *logits, int vocab, float temperatur
     __syncthreads();
     if (tid == 0) {
         float t = red[0];
-        for (int i = 1; i < 32; i++) t = fmaxf(t, red[i]);
+        for (int i = 1; i < nw; i++) t = fmaxf(t, red[i]);
         bc = t;
     }
     __syncthreads();
@@ -572,7 +610,7 @@ __global__ void softmax_sample_kernel(float *logits, int vocab, float temperatur
     __syncthreads();
     if (tid == 0) {
         float t = 0.0f;
-        for (int i = 0; i < 32; i++) t += red[i];
+        for (int i = 0; i < nw; i++) t += red[i];
         float acc = 0.0f;
         int pick = vocab - 1;
         for (int i = 0; i < vocab; i++) {
@@ -615,9 +653,44 @@ static int decode_body(jl_model *m, int n, int max_pos, int splits, bool residen
     return JL_OK;
 }
 
-// run the decode body through a cached CUDA graph (or eagerly)
+static bool fill_mega(jl_model *m, int n, int max_pos, bool resident, MegaParams &p) {
+    const jl_model_config &c = m->cfg;
+    p = MegaParams();
+    p.layers = c.num_layers, p.E = c.embedding_length, p.H = m->h_seg, p.attn_seg = m->attn_seg, p.kv_seg = m->kv_seg;
+    p.heads = m->heads_local, p.kv_heads = m->kv_heads_local, p.head_size = c.head_size, p.vocab = c.vocab_size;
+    p.head0_global = m->d.headStart, p.kv_head0_global = m->d.groupHeadStart;
+    p.M = n;
+    p.eps = c.layer_norm_eps;
+    p.attn_scale = (float)(1.0 / sqrt((double)c.head_size));
+    p.lw = m->mega_layers;
+    p.embed_dt = m->g[JL_T_EMBED].dtype, p.embed_w = m->g[JL_T_EMBED].data, p.embed_s = m->g[JL_T_EMBED].scales;
+    p.out_norm = m->g[JL_T_OUT_NORM].data, p.out_norm_dt = m->g[JL_T_OUT_NORM].dtype;
+    const DevTensor &head = m->g_set[JL_T_LM_HEAD] ? m->g[JL_T_LM_HEAD] : m->g[JL_T_EMBED];
+    p.lm_w = (const uint8_t *)head.data, p.lm_s = head.scales;
+    p.x = m->x, p.xb = m->xb, p.q = m->q, p.k = m->k, p.v = m->v, p.att = m->att, p.h = m->hbuf, p.logits = m->logits;
+    p.attn_ws = m->attn_ws;
+    p.rope = m->rope;
+    p.kv = m->kv;
+    p.tokens = m->d_tokens, p.positions = m->d_positions, p.next = m->d_next, p.sessions = m->d_sessions;
+    p.hist = m->d_hist, p.counter = m->d_counter, p.hist_cap = m->hist_cap, p.resident = resident ? 1 : 0;
+    p.sync = m->mega_sync, p.argmax_slots = m->mega_slots, p.att_done = m->mega_att_done;
+    // one split per 64 positions, bounded by the CTAs available for (row, kv head) tasks
+    int s = (max_pos + 1 + 63) / 64;
+    const int cap = m->ctx->sm_count / (n * m->kv_heads_local);
+    if (s > cap) s = cap;
+    if (s > m->max_splits) s = m->max_splits;
+    if (s < 1) s = 1;
+    p.splits = s;
+    return n * m->kv_heads_local <= m->ctx->sm_count && jl_mega_supported(p);
+}
+
+// run the decode body through the persistent megakernel, a cached CUDA graph, or eagerly
 static int run_decode(jl_model *m, int n, int max_pos, bool resident) {
     jl_ctx *ctx = m->ctx;
+    if (use_mega(m)) {
+        MegaParams mp;
+        if (fill_mega(m, n, max_pos, resident, mp)) return jl_launch_mega(ctx, m->stream, mp);
+    }
     const int splits = pick_splits(m, max_pos, n);
     if (!use_graph(m)) {
         m->ev_used = 0;
@@ -645,11 +718,11 @@ static int run_decode(jl_model *m, int n, int max_pos, bool resident) {
         cudaGraphDestroy(graph);
         if (ce != cudaSuccess) return jl_set_error(ctx, JL_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
         m->graphs[key] = exec;
-        m->graphs[-key - 1] = (cudaGraphExec_t)(intptr_t)per_graph; // launch count of this graph (not a real exec)
+        m->graph_launches[key] = per_graph;
         it = m->graphs.find(key);
     }
     JL_CUDA_CHECK(ctx, cudaGraphLaunch(it->second, m->stream));
-    ctx->launches += (long long)(intptr_t)m->graphs[-key - 1];
+    ctx->launches += m->graph_launches[key];
     return JL_OK;
 }
 
@@ -736,6 +809,15 @@ extern "C" int jl_model_decode_resident(jl_model *m, int session, int32_t first_
     m->last_total_ms = ms;
     m->last_gemv_ms = gemv;
     return JL_OK;
+}
+
+extern "C" int jl_model_decode_mode(jl_model *m, int n) {
+    if (!m || !m->finalized) return JL_ERR_INVALID;
+    if (use_mega(m)) {
+        MegaParams mp;
+        if (fill_mega(m, n, 0, false, mp)) return 2;
+    }
+    return use_graph(m) ? 1 : 0;
 }
 
 extern "C" int jl_model_last_timing(jl_model *m, double *total_ms, double *gemv_ms) {

@@ -547,3 +547,65 @@ extern "C" int jl_kv_page_geometry(int num_layers, int context_length, int kv_se
     *ctx_per_page = optC;
     return JL_OK;
 }
+
+// ---- diagnostic micro-benchmark of the GEMV kernel ----------------------------------------------------------
+extern "C" int jl_debug_gemv_bench(jl_ctx *ctx, int64_t b_id, int n, int m, int mode, int iters, int use_pdl, double *avg_us) {
+    HOST_OP_PROLOGUE();
+    auto it = ctx->tensors.find(b_id);
+    if (it == ctx->tensors.end() || !avg_us || iters <= 0 || m < 1 || m > GEMV_MAX_M)
+        return jl_set_error(ctx, JL_ERR_INVALID, "gemv_bench: bad arguments");
+    const DevTensor &B = it->second;
+    if (n <= 0 || n > B.rows) return jl_set_error(ctx, JL_ERR_INVALID, "gemv_bench: n out of range");
+    const int k = (int)B.cols;
+    float *da = (float *)jl_scratch(ctx, 0, (size_t)m * k * 4);
+    float *dr = (float *)jl_scratch(ctx, 1, (size_t)m * B.rows * 4);
+    float *dw = (float *)jl_scratch(ctx, 2, (size_t)k * 4);
+    if (!da || !dr || !dw) return JL_ERR_OOM;
+    std::vector<float> ha((size_t)m * k), hw(k, 1.0f);
+    for (size_t i = 0; i < ha.size(); i++) ha[i] = (float)((int)(i * 2654435761u % 2001) - 1000) / 500.0f;
+    JL_CUDA_CHECK(ctx, cudaMemcpy(da, ha.data(), ha.size() * 4, cudaMemcpyHostToDevice));
+    JL_CUDA_CHECK(ctx, cudaMemcpy(dw, hw.data(), hw.size() * 4, cudaMemcpyHostToDevice));
+    JL_CUDA_CHECK(ctx, cudaMemset(dr, 0, (size_t)m * B.rows * 4));
+    cudaEvent_t e0, e1;
+    JL_CUDA_CHECK(ctx, cudaEventCreate(&e0));
+    JL_CUDA_CHECK(ctx, cudaEventCreate(&e1));
+    const int slots = (int)(B.rows / n);
+    for (int pass = 0; pass < 2; pass++) { // pass 0 = warm-up
+        if (pass == 1) JL_CUDA_CHECK(ctx, cudaEventRecord(e0, ctx->stream));
+        for (int i = 0; i < (pass == 0 ? (iters < 8 ? iters : 8) : iters); i++) {
+            GemvParams p = {};
+            p.nseg = 1;
+            p.seg[0].w = B.data;
+            p.seg[0].ws = B.scales;
+            p.seg[0].out = dr;
+            p.seg[0].rows = n;
+            p.seg[0].out_ld = (int)B.rows;
+            p.seg[0].out_off = 0;
+            p.w_dtype = B.dtype;
+            p.ldw = k;
+            p.K = k;
+            p.M = m;
+            p.a = da;
+            p.lda = k;
+            p.row0 = (i % slots) * n;
+            p.total_rows = n;
+            p.norm_w = dw;
+            p.norm_w_dtype = JL_F32;
+            p.norm_eps = 1e-5f;
+            p.norm_E = k;
+            p.residual = dr;
+            p.res_ld = (int)B.rows;
+            const int pro = mode == 1 ? PRO_RMSNORM_QUANT : (mode == 2 ? PRO_F32 : PRO_F32_QUANT);
+            int rc = jl_launch_gemv(ctx, ctx->stream, p, pro, mode == 3 ? EPI_ADD_RESIDUAL : EPI_STORE, use_pdl != 0);
+            if (rc) return rc;
+        }
+    }
+    JL_CUDA_CHECK(ctx, cudaEventRecord(e1, ctx->stream));
+    JL_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *avg_us = (double)ms * 1000.0 / iters;
+    return JL_OK;
+}

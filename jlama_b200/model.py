@@ -163,6 +163,9 @@ class LlamaModel:
         self.ctx.check(self.lib.jl_model_read_hidden(self.h, session, ptr(out)))
         return out
 
+    def decode_mode(self, n=1):
+        return int(self.lib.jl_model_decode_mode(self.h, n))
+
     def weight_bytes(self):
         return int(self.lib.jl_model_weight_bytes(self.h))
 

@@ -3,8 +3,9 @@
 There are no checkpoints or network here, so benchmarks and parity tests run on synthetic weights of
 the real architecture:
 
-  mode "quantize": W ~ N(0, 0.02^2) f32, norm weights 1 + N(0, 0.1^2), then quantised with the
-                   reference quantiser semantics (tensor.quantize_q4 / quantize_q8_weights).
+  mode "quantize": W ~ N(0, 0.02^2) f32 (o_proj/down_proj: 0.02/sqrt(2L); embedding N(0,1)), norm weights
+                   1 + N(0, 0.1^2), then quantised with the reference quantiser semantics
+                   (tensor.quantize_q4 / quantize_q8_weights).
   mode "direct"  : the packed Q4 bytes and the f32 block scales are drawn directly (uniform nibbles,
                    scales of magnitude ~0.02/4.6 with random sign) -- every byte pattern is a valid JQ4
                    tensor, and an 8B model is generated in seconds instead of minutes.
@@ -115,13 +116,25 @@ def make_one(cfg, name, rows, cols, kind, wdtype=Q4, mode="quantize", embed_dtyp
         # Jlama's quantiser also quantises the embedding table (skip pattern is only "norm",
         # QuantizeCommand.java:36-38), so a JQ4 checkpoint has a Q4 embedding (LlamaModel.java:91-97)
         dt = wdtype if embed_dtype is None else embed_dtype
-        return make_tensor(seed, rows, cols, dt, mode, std=0.02 if dt in (Q4, I8) else 1.0)
-    return make_tensor(seed, rows, cols, wdtype, mode)
+        return make_tensor(seed, rows, cols, dt, mode, std=1.0)
+    # residual-branch output projections are down-scaled by 1/sqrt(2L) (GPT-2 / Llama style init) so that the
+    # synthetic network is residual-dominated and well-conditioned like a trained one; with every matrix at
+    # std 0.02 a random transformer amplifies 1e-7 summation-order differences into O(1) logit changes.
+    std = 0.02
+    if name.endswith("o_proj.weight") or name.endswith("down_proj.weight"):
+        std = 0.02 / float(np.sqrt(2.0 * cfg["layers"]))
+    return make_tensor(seed, rows, cols, wdtype, mode, std=std)
 
 
-def make_weights(cfg, wdtype=Q4, mode="quantize", embed_dtype=None):
-    """Full synthetic checkpoint in host memory."""
-    return {name: make_one(cfg, name, r, c, kind, wdtype, mode, embed_dtype) for name, r, c, kind in tensor_specs(cfg)}
+def make_weights(cfg, wdtype=Q4, mode="quantize", embed_dtype=None, threads=None):
+    """Full synthetic checkpoint in host memory (tensors generated in parallel; each has its own seed)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    specs = tensor_specs(cfg)
+    threads = threads or min(32, os.cpu_count() or 1)
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        vals = list(ex.map(lambda sp: make_one(cfg, sp[0], sp[1], sp[2], sp[3], wdtype, mode, embed_dtype), specs))
+    return {sp[0]: v for sp, v in zip(specs, vals)}
 
 
 def linear_weight_count(cfg):

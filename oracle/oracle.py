@@ -44,9 +44,38 @@ def build(force=False):
 _lib = None
 
 
+def available_cpus():
+    """CPUs this process may really use: affinity mask capped by the cgroup CPU quota (what Java's
+    Runtime.availableProcessors(), the input of PhysicalCoreExecutor.java:27, reports)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.999)))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, (q + per - 1) // per))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return max(1, n)
+
+
 def lib():
     global _lib
     if _lib is None:
+        # worker threads must sleep, not spin, between the many small parallel regions of a decode step
+        os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
+        os.environ.setdefault("OMP_PROC_BIND", "false")
+        if "OMP_NUM_THREADS" not in os.environ:
+            os.environ["OMP_NUM_THREADS"] = str(available_cpus())
         so = build()
         L = C.CDLL(so)
         L.jo_model_create.restype = C.c_void_p

@@ -114,11 +114,13 @@ def test_graph_eager_and_resident_decode_agree_bitwise(cuda_ctx, oracle):
     w = synth.make_weights(cfg)
     prompt = synth.random_prompt(cfg, 11)
     outs = []
-    for flags in (0, native.MODEL_NO_PDL, native.MODEL_NO_GRAPH | native.MODEL_NO_PDL):
+    NM = native.MODEL_NO_MEGA
+    for flags in (NM, NM | native.MODEL_NO_PDL, NM | native.MODEL_NO_GRAPH | native.MODEL_NO_PDL):
         m = LlamaModel(cuda_ctx, cfg, w, flags=flags)
+        assert m.decode_mode() == (0 if flags & native.MODEL_NO_GRAPH else 1)
         t, l = m.generate(prompt, 10, want_logits=True)
         outs.append((t.copy(), l.copy()))
-        if flags == 0:
+        if flags == NM:
             # resident decode loop (tokens stay on the device) reproduces generate()
             m.reset_session(0)
             m.batch_forward(prompt, 0)
@@ -128,6 +130,66 @@ def test_graph_eager_and_resident_decode_agree_bitwise(cuda_ctx, oracle):
         m.close()
     for t, l in outs[1:]:
         assert np.array_equal(t, outs[0][0]) and np.array_equal(l, outs[0][1])
+
+
+@pytest.mark.parametrize("name", ["tiny", "small", "small-hs128"])
+def test_megakernel_matches_per_op_kernels(cuda_ctx, oracle, name):
+    """The persistent megakernel and the kernel-per-op path share their arithmetic: same tokens, logits equal to
+    float rounding (attention tiles differ), incl. the device-resident feedback loop and batched sessions."""
+    from jlama_b200 import native, synth
+    from jlama_b200.model import LlamaModel
+    cfg = synth.get_config(name)
+    w = synth.make_weights(cfg)
+    prompt = synth.random_prompt(cfg, 21)
+    mega = LlamaModel(cuda_ctx, cfg, w, max_sessions=4)
+    ref = LlamaModel(cuda_ctx, cfg, w, max_sessions=4, flags=native.MODEL_NO_MEGA)
+    assert mega.decode_mode(1) == 2 and mega.decode_mode(3) == 2 and ref.decode_mode(1) == 1
+    t1, l1 = mega.generate(prompt, 40, want_logits=True)
+    t2, l2 = ref.generate(prompt, 40, want_logits=True)
+    assert list(t1) == list(t2)
+    assert np.abs(l1 - l2).max() <= 5e-4 * np.abs(l2).max()
+    # resident loop
+    mega.reset_session(0)
+    mega.batch_forward(prompt, 0)
+    first, _ = mega.sample()
+    rest = mega.decode_resident(first, len(prompt), 39)
+    assert [first] + list(rest) == list(t1)
+    # three sessions in one launch (MM = 4 with a dead row)
+    outs = []
+    for mdl in (mega, ref):
+        toks = []
+        for s in range(3):
+            mdl.reset_session(s)
+            mdl.batch_forward(prompt[: 7 + 5 * s], 0, session=s)
+            toks.append(mdl.sample(session=s)[0])
+        toks = np.array(toks, dtype=np.int32)
+        pos = np.array([7, 12, 17], dtype=np.int32)
+        hist = []
+        for _ in range(6):
+            toks, lg = mdl.decode(toks, pos, want_logits=True)
+            pos = pos + 1
+            hist.append((toks.copy(), lg.copy()))
+        outs.append(hist)
+    for (ta, la), (tb, lb) in zip(*outs):
+        assert list(ta) == list(tb)
+        assert np.abs(la - lb).max() <= 5e-4 * np.abs(lb).max()
+    mega.close()
+    ref.close()
+
+
+def test_megakernel_long_context_splits(cuda_ctx, oracle):
+    """context long enough for several attention splits per (row, kv head) inside the megakernel"""
+    from jlama_b200 import synth
+    cfg, w, gm, om = _models(cuda_ctx, oracle, "tiny", max_batch=64)
+    prompt = synth.random_prompt(cfg, 150)
+    gt, gl = gm.generate(prompt, 12, want_logits=True)
+    om.reset()
+    ot, ol = om.generate(prompt, 12, max_batch=64)
+    assert gm.decode_mode() == 2
+    assert list(gt) == list(ot)
+    assert max(_rel(gl[i], ol[i]) for i in range(12)) <= 1e-2
+    gm.close()
+    om.close()
 
 
 def test_concurrent_sessions_batch_decode(cuda_ctx, oracle):
