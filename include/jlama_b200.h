@@ -218,6 +218,10 @@ int jl_model_decode_resident(jl_model *m, int session, int32_t first_token, int 
 /* test hooks: copy a K/V row (f32) or the hidden rows of the last batch_forward chunk to HOST */
 int jl_model_read_kv(jl_model *m, int session, int layer, int position, int which /*0=K,1=V*/, float *out);
 int jl_model_read_hidden(jl_model *m, int session, float *out /* [embedding_length] last row */);
+/* diagnostic: run one megakernel decode step (token/position as given) with phase tracing; out receives
+ * [3 CTAs (first, middle, last)][layers*4+1 ops][8] SM clock stamps: 0 op start, 1 after attention phase,
+ * 2 dependency satisfied, 3 activations staged, 4 stages consumed, 5 signalled. */
+int jl_model_debug_trace(jl_model *m, int session, int32_t token, int position, int64_t *out, int64_t out_words);
 /* how jl_model_decode executes for n sessions: 2 = persistent megakernel, 1 = CUDA-graph of per-op kernels, 0 = eager */
 int jl_model_decode_mode(jl_model *m, int n);
 /* per-token algorithmic bytes of the decode weight stream on this rank (roofline numerator) */

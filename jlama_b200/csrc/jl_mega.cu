@@ -9,7 +9,7 @@
 //     it with TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx) into a shared-memory ring; it never
 //     waits for activations, only for free ring slots, and when the ring is full it keeps HBM busy by issuing
 //     L2 prefetches (cp.async.bulk.prefetch.L2) for the next stages of its schedule;
-//   * 16 CONSUMER warps wait on the ring's mbarriers, run the dp4a block dot products against the Q8
+//   * 8 CONSUMER warps (two row-units each) wait on the ring's mbarriers, run the dp4a block dot products against the Q8
 //     activations staged in shared memory, and apply the fused epilogues (residual add, SiLU*up, arg-max);
 //   * ops are ordered by per-op completion counters in global memory (release/acquire), not kernel boundaries;
 //     RMSNorm + Q8 quantisation are recomputed per CTA in the op prologue (one L2 round trip);
@@ -20,16 +20,17 @@
 // order, so GEMV results are bit-identical; the launch is cooperative so the spin waits cannot deadlock.
 #include "jl_mega.cuh"
 
-#define MG_CWARPS 16
+#define MG_CWARPS 8   // consumer warps; each handles two of the 16 row-units of a stage
+#define MG_UNITS 16
 #define MG_CONSUMERS (MG_CWARPS * 32)
 #define MG_THREADS (MG_CONSUMERS + 32)
-#define MG_ROWS 16
-#define MG_SLICE 4096
-#define MG_PSLICE 2048
 #define MG_STAGE_NIB 32768
 #define MG_STAGE_SC 8192
 #define MG_STAGE_BYTES (MG_STAGE_NIB + MG_STAGE_SC)
-#define MG_L2_AHEAD 8
+#define MG_REC_BYTES 96
+#define MG_EROWS 112   // max rows (or pairs) of one op owned by one CTA (lm_head excluded)
+#define MG_MAX_OPS 520 // 4 * layers + 1
+#define MG_DB 4 // stage records per descriptor batch
 #define MG_ATT_TILE 32
 #define MG_MAX_GROUP 8
 
@@ -73,155 +74,177 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {
     return v;
 }
 
-// ---- static schedule ------------------------------------------------------------------------------------------------
+// ---- static schedule (host-built table) --------------------------------------------------------------------------------
 // ops: for each layer QKV, O, GATEUP, DOWN; then LMHEAD.
 enum { OP_QKV = 0, OP_O, OP_GATEUP, OP_DOWN, OP_LMHEAD };
-struct OpInfo {
-    int type, layer, nseg, K, pair;
-    int seg_rows[3];
-    const uint8_t *w[3];
-    const float *s[3];
+// A stage = R FULL weight rows (contiguous in HBM -> one bulk copy for the nibbles, one for the scales):
+//   plain op: R = min(16, 32 KB / row bytes) rows, 16/R units per row (each a K-range of the row);
+//   pair op (gate/up): R pairs = R gate rows + R up rows (two + two copies), 16/(2R) units per row.
+// A stage always has 16 units; consumer warp w owns units w and w+8, which share their K-range (so the
+// activations of that range live in the warp's registers) and, for pair ops, are the gate and up row of one pair.
+// slot layout: nibbles of row i at i*(K/2) (pair: gate rows first, up rows at R*(K/2)); scales at
+// MG_STAGE_NIB + i*(K/8) (pair: up scales at MG_STAGE_NIB + R*(K/8)).
+struct Stage {
+    int seg, row0, nrows, R, wpr, K, pair, type, wpr_shift, r_shift;
 };
-__device__ __forceinline__ OpInfo op_info(const MegaParams &P, int op) {
-    OpInfo o;
-    if (op >= P.layers * 4) {
-        o.type = OP_LMHEAD, o.layer = P.layers, o.nseg = 1, o.K = P.E, o.pair = 0;
-        o.seg_rows[0] = P.vocab, o.w[0] = P.lm_w, o.s[0] = P.lm_s;
-        return o;
-    }
-    o.layer = op >> 2, o.type = op & 3, o.pair = 0;
-    const MegaLayer &L = P.lw[o.layer];
-    switch (o.type) {
-        case OP_QKV:
-            o.nseg = 3, o.K = P.E;
-            o.seg_rows[0] = P.attn_seg, o.seg_rows[1] = P.kv_seg, o.seg_rows[2] = P.kv_seg;
-            o.w[0] = L.w[MW_Q], o.w[1] = L.w[MW_K], o.w[2] = L.w[MW_V];
-            o.s[0] = L.s[MW_Q], o.s[1] = L.s[MW_K], o.s[2] = L.s[MW_V];
-            break;
-        case OP_O:
-            o.nseg = 1, o.K = P.attn_seg, o.seg_rows[0] = P.E, o.w[0] = L.w[MW_O], o.s[0] = L.s[MW_O];
-            break;
-        case OP_GATEUP: // seg0 = gate rows, w[1]/s[1] = up rows of the same pair
-            o.nseg = 1, o.K = P.E, o.pair = 1, o.seg_rows[0] = P.H;
-            o.w[0] = L.w[MW_GATE], o.s[0] = L.s[MW_GATE], o.w[1] = L.w[MW_UP], o.s[1] = L.s[MW_UP];
-            break;
-        default:
-            o.nseg = 1, o.K = P.H, o.seg_rows[0] = P.E, o.w[0] = L.w[MW_DOWN], o.s[0] = L.s[MW_DOWN];
-            break;
-    }
-    return o;
+__device__ __forceinline__ int stage_rows_dev(int K, int pair) {
+    const int rb = K / 2;
+    int R = pair ? 8 : 16;
+    const int budget = pair ? MG_STAGE_NIB / 2 : MG_STAGE_NIB;
+    while (R > 1 && R * rb > budget) R >>= 1;
+    return R;
+}
+static int stage_rows(int K, int pair) {
+    const int rb = K / 2;
+    int R = pair ? 8 : 16;
+    const int budget = pair ? MG_STAGE_NIB / 2 : MG_STAGE_NIB;
+    while (R > 1 && R * rb > budget) R >>= 1;
+    return R;
 }
 
-struct Sched {
-    int op, seg, rg, c0;
-};
-struct Stage {
-    int op, seg, row0, nrows, c0, ncols, K, pair, last_slice, type;
-    const uint8_t *w0, *w1;
-    const float *s0, *s1;
-    uint32_t bytes;
-};
-// Normalise the cursor to the next non-empty stage of this CTA; false at the end of the schedule.
-__device__ bool sched_get(const MegaParams &P, Sched &s, Stage &d, int limit_op = 1 << 30) {
-    const int G = gridDim.x, cta = blockIdx.x;
+void jl_mega_build_table(const MegaParams &P, const MegaLayer *layers, int G, std::vector<unsigned char> &records,
+                         std::vector<int> &cta_first, std::vector<int> &op_first) {
     const int n_ops = P.layers * 4 + 1;
-    while (s.op < n_ops && s.op < limit_op) {
-        const OpInfo oi = op_info(P, s.op);
-        long long T = 0;
-        for (int i = 0; i < oi.nseg; i++) T += oi.seg_rows[i];
-        const int a = (int)((T * cta) / G), b = (int)((T * (cta + 1)) / G);
-        int seg_start = 0;
-        for (int i = 0; i < s.seg; i++) seg_start += oi.seg_rows[i];
-        while (s.seg < oi.nseg) {
-            const int seg_end = seg_start + oi.seg_rows[s.seg];
-            const int p0 = max(a, seg_start) - seg_start, p1 = min(b, seg_end) - seg_start;
-            if (s.rg < p0) s.rg = p0;
-            if (s.rg < p1) {
-                const int slice = oi.pair ? MG_PSLICE : MG_SLICE;
-                d.op = s.op, d.seg = s.seg, d.row0 = s.rg, d.nrows = min(MG_ROWS, p1 - s.rg);
-                d.c0 = s.c0, d.ncols = min(slice, oi.K - s.c0), d.K = oi.K, d.pair = oi.pair, d.type = oi.type;
-                d.last_slice = (s.c0 + slice >= oi.K);
-                d.w0 = oi.w[s.seg], d.s0 = oi.s[s.seg];
-                d.w1 = oi.pair ? oi.w[1] : nullptr, d.s1 = oi.pair ? oi.s[1] : nullptr;
-                d.bytes = (uint32_t)d.nrows * (uint32_t)(d.ncols / 2 + d.ncols / 8) * (oi.pair ? 2u : 1u);
-                return true;
+    std::vector<MegaCopy> copies;
+    std::vector<MegaMeta> metas;
+    cta_first.assign(G + 1, 0);
+    op_first.assign((size_t)G * (n_ops + 1), 0);
+    for (int cta = 0; cta < G; cta++) {
+        cta_first[cta] = (int)metas.size();
+        for (int op = 0; op < n_ops; op++) {
+            op_first[(size_t)cta * (n_ops + 1) + op] = (int)metas.size();
+            int type, K, pair = 0, nseg = 1, seg_rows[3] = {0, 0, 0};
+            const uint8_t *w[3] = {nullptr, nullptr, nullptr};
+            const float *sc[3] = {nullptr, nullptr, nullptr};
+            if (op == n_ops - 1) {
+                type = OP_LMHEAD, K = P.E, seg_rows[0] = P.vocab, w[0] = P.lm_w, sc[0] = P.lm_s;
+            } else {
+                const MegaLayer &L = layers[op >> 2];
+                type = op & 3;
+                if (type == OP_QKV) {
+                    nseg = 3, K = P.E;
+                    seg_rows[0] = P.attn_seg, seg_rows[1] = P.kv_seg, seg_rows[2] = P.kv_seg;
+                    w[0] = L.w[MW_Q], w[1] = L.w[MW_K], w[2] = L.w[MW_V];
+                    sc[0] = L.s[MW_Q], sc[1] = L.s[MW_K], sc[2] = L.s[MW_V];
+                } else if (type == OP_O) {
+                    K = P.attn_seg, seg_rows[0] = P.E, w[0] = L.w[MW_O], sc[0] = L.s[MW_O];
+                } else if (type == OP_GATEUP) {
+                    K = P.E, pair = 1, seg_rows[0] = P.H;
+                    w[0] = L.w[MW_GATE], sc[0] = L.s[MW_GATE], w[1] = L.w[MW_UP], sc[1] = L.s[MW_UP];
+                } else {
+                    K = P.H, seg_rows[0] = P.E, w[0] = L.w[MW_DOWN], sc[0] = L.s[MW_DOWN];
+                }
             }
-            seg_start = seg_end;
-            s.seg++, s.rg = 0, s.c0 = 0;
+            long long T = 0;
+            for (int i = 0; i < nseg; i++) T += seg_rows[i];
+            const int a = (int)((T * cta) / G), b = (int)((T * (cta + 1)) / G);
+            const int R = stage_rows(K, pair);
+            const uint32_t rb = K / 2, sbp = K / 8;
+            int seg_start = 0;
+            for (int seg = 0; seg < nseg; seg++) {
+                const int seg_end = seg_start + seg_rows[seg];
+                const int p0 = std::max(a, seg_start) - seg_start, p1 = std::min(b, seg_end) - seg_start;
+                for (int rg = p0; rg < p1; rg += R) {
+                    const int nrows = std::min(R, p1 - rg);
+                    MegaMeta md = {};
+                    md.total_bytes = (uint32_t)nrows * (rb + sbp) * (pair ? 2u : 1u);
+                    md.row0 = rg, md.nrows = (int16_t)nrows, md.R = (int16_t)R, md.wpr = (int16_t)(MG_UNITS / (pair ? 2 * R : R));
+                    md.seg = (int16_t)seg, md.pair = (uint8_t)pair, md.type = (uint8_t)type, md.op = op, md.K = K;
+                    for (int t = md.wpr; t > 1; t >>= 1) md.wpr_shift++;
+                    for (int t = R; t > 1; t >>= 1) md.r_shift++;
+                    metas.push_back(md);
+                    for (int c = 0; c < 4; c++) {
+                        MegaCopy cp = {0, 0, 0};
+                        const int up = c >> 1, is_sc = c & 1;
+                        if (c < (pair ? 4 : 2)) {
+                            const uint8_t *wp = pair ? (up ? w[1] : w[0]) : w[seg];
+                            const float *sp = pair ? (up ? sc[1] : sc[0]) : sc[seg];
+                            cp.src = is_sc ? (unsigned long long)(sp + (size_t)rg * (K / 32)) : (unsigned long long)(wp + (size_t)rg * rb);
+                            cp.bytes = (uint32_t)nrows * (is_sc ? sbp : rb);
+                            cp.dst = is_sc ? (uint32_t)(MG_STAGE_NIB + (size_t)up * R * sbp) : (uint32_t)((size_t)up * R * rb);
+                        }
+                        copies.push_back(cp);
+                    }
+                }
+                seg_start = seg_end;
+            }
         }
-        s.op++, s.seg = 0, s.rg = 0, s.c0 = 0;
+        op_first[(size_t)cta * (n_ops + 1) + n_ops] = (int)metas.size();
     }
-    return false;
-}
-__device__ __forceinline__ void sched_advance(Sched &s, const Stage &d) {
-    s.c0 += d.pair ? MG_PSLICE : MG_SLICE;
-    if (s.c0 >= d.K) s.c0 = 0, s.rg += MG_ROWS;
+    cta_first[G] = (int)metas.size();
+    records.resize(metas.size() * MG_REC_BYTES);
+    for (size_t i = 0; i < metas.size(); i++) {
+        memcpy(&records[i * MG_REC_BYTES], &copies[i * 4], 4 * sizeof(MegaCopy));
+        memcpy(&records[i * MG_REC_BYTES + 64], &metas[i], sizeof(MegaMeta));
+    }
 }
 
 // ---- producer ----------------------------------------------------------------------------------------------------------
-// slot layout: normal stage: row r nibbles at r*2048, scales at r*512 bytes;
-//              pair stage:   gate r at r*2048 / r*512, up r at r*2048+1024 / r*512+256.
-template <bool PREFETCH>
-__device__ __forceinline__ void issue_stage(const Stage &d, unsigned char *slot, uint64_t *full, int lane) {
-    const int ncopies = d.nrows * (d.pair ? 2 : 1);
-    const uint32_t nb = d.ncols / 2, sb = d.ncols / 8;
-    for (int i = lane; i < ncopies; i += 32) {
-        const int r = d.pair ? (i >> 1) : i, up = d.pair ? (i & 1) : 0;
-        const uint8_t *w = up ? d.w1 : d.w0;
-        const float *s = up ? d.s1 : d.s0;
-        const size_t row = (size_t)(d.row0 + r);
-        const uint8_t *src_n = w + row * (size_t)(d.K / 2) + d.c0 / 2;
-        const float *src_s = s + row * (size_t)(d.K / 32) + d.c0 / 32;
-        if (PREFETCH) {
-            l2_prefetch(src_n, nb);
-            l2_prefetch(src_s, sb);
-        } else {
-            tma_load_1d(slot + r * 2048 + up * 1024, src_n, nb, full);
-            tma_load_1d(slot + MG_STAGE_NIB + r * 512 + up * 256, src_s, sb, full);
-        }
-    }
-}
-
+// The warp never touches global memory on its critical path: stage records arrive in shared memory in
+// batches of MG_DB through their own bulk copies (double buffered), two batches ahead of use.
 template <int NSTAGE>
-__device__ void producer_loop(const MegaParams &P, unsigned char *ring, uint64_t *full, uint64_t *empty, int lane) {
-    Sched rs = {0, 0, 0, 0}, ls = {0, 0, 0, 0};
-    Stage rd, ld;
-    bool rvalid = sched_get(P, rs, rd), lvalid = sched_get(P, ls, ld);
-    unsigned it = 0;   // stages put into the ring
-    unsigned lit = 0;  // stages prefetched into L2 (>= it)
-    while (rvalid) {
-        const unsigned slot = it % NSTAGE, use = it / NSTAGE;
-        const bool free_slot = __shfl_sync(0xffffffffu, lane == 0 ? (int)mbar_try_wait(&empty[slot], (use & 1) ^ 1) : 0, 0) != 0;
-        if (free_slot) {
-            if (lane == 0) mbar_expect_tx(&full[slot], rd.bytes);
-            __syncwarp();
-            issue_stage<false>(rd, ring + (size_t)slot * MG_STAGE_BYTES, &full[slot], lane);
-            sched_advance(rs, rd);
-            rvalid = sched_get(P, rs, rd);
-            it++;
-            if (lit < it) { // keep the L2 cursor at or ahead of the ring cursor
-                sched_advance(ls, ld);
-                lvalid = sched_get(P, ls, ld);
-                lit = it;
-            }
-        } else if (lvalid && lit < it + MG_L2_AHEAD) {
-            issue_stage<true>(ld, nullptr, nullptr, lane);
-            sched_advance(ls, ld);
-            lvalid = sched_get(P, ls, ld);
-            lit++;
-        } else {
-            __nanosleep(100);
+__device__ void producer_loop(const MegaParams &P, unsigned char *ring, uint64_t *full, uint64_t *empty, MegaMeta *sdesc,
+                              unsigned char *dbuf /*[2][MG_DB*96]*/, uint64_t *dfull /*[2]*/, int lane) {
+    const int s0 = __ldg(&P.cta_first[blockIdx.x]), s1 = __ldg(&P.cta_first[blockIdx.x + 1]);
+    const int nst = s1 - s0, nbatch = (nst + MG_DB - 1) / MG_DB;
+    auto fetch_batch = [&](int b) {
+        if (b < nbatch && lane == 0) {
+            const int cnt = min(MG_DB, nst - b * MG_DB);
+            mbar_expect_tx(&dfull[b & 1], (uint32_t)cnt * MG_REC_BYTES);
+            tma_load_1d(dbuf + (size_t)(b & 1) * MG_DB * MG_REC_BYTES, P.records + (size_t)(s0 + b * MG_DB) * MG_REC_BYTES,
+                        (uint32_t)cnt * MG_REC_BYTES, &dfull[b & 1]);
         }
+    };
+    auto prefetch_batch = [&](int b) { // L2 prefetch of every stage of batch b (its records must have arrived)
+        if (!P.l2_ahead || b >= nbatch) return;
+        const int cnt = min(MG_DB, nst - b * MG_DB);
+        const unsigned char *rec = dbuf + (size_t)(b & 1) * MG_DB * MG_REC_BYTES;
+        for (int i = lane; i < cnt * 4; i += 32) {
+            const uint4 v = *(const uint4 *)(rec + (size_t)(i >> 2) * MG_REC_BYTES + (i & 3) * 16);
+            if (v.z) l2_prefetch((const void *)(((unsigned long long)v.y << 32) | v.x), v.z);
+        }
+    };
+    fetch_batch(0);
+    fetch_batch(1);
+    if (nbatch > 0) {
+        while (!mbar_try_wait(&dfull[0], 0)) {
+        }
+        prefetch_batch(0);
+    }
+    for (int b = 0; b < nbatch; b++) {
+        if (b + 1 < nbatch) {
+            while (!mbar_try_wait(&dfull[(b + 1) & 1], ((b + 1) >> 1) & 1)) {
+            }
+            prefetch_batch(b + 1);
+        }
+        const int cnt = min(MG_DB, nst - b * MG_DB);
+        const unsigned char *rec = dbuf + (size_t)(b & 1) * MG_DB * MG_REC_BYTES;
+        for (int j = 0; j < cnt; j++) {
+            const unsigned k = (unsigned)(b * MG_DB + j), slot = k % NSTAGE, use = k / NSTAGE;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (lane < 6) v = *(const uint4 *)(rec + (size_t)j * MG_REC_BYTES + lane * 16);
+            const uint32_t total_bytes = __shfl_sync(0xffffffffu, v.x, 4); // first word of the MegaMeta
+            while (!mbar_try_wait(&empty[slot], (use & 1) ^ 1)) {
+                __nanosleep(32);
+            }
+            if (lane == 4) ((uint4 *)&sdesc[slot])[0] = v;
+            if (lane == 5) ((uint4 *)&sdesc[slot])[1] = v;
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(&full[slot], total_bytes);
+            __syncwarp();
+            if (lane < 4 && v.z)
+                tma_load_1d(ring + (size_t)slot * MG_STAGE_BYTES + v.w, (const void *)(((unsigned long long)v.y << 32) | v.x), v.z,
+                            &full[slot]);
+        }
+        __syncwarp();
+        fetch_batch(b + 2); // this buffer is free again
     }
 }
 
 // ---- cross-CTA ordering ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void op_signal(unsigned *cnt) { // all consumer threads call
     consumer_bar();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(cnt, 1u);
-    }
+    if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt) : "memory");
 }
 __device__ __forceinline__ void op_wait(const unsigned *cnt, unsigned expected) { // all consumer threads call
     if (threadIdx.x == 0) {
@@ -252,26 +275,66 @@ __device__ __forceinline__ ActView act_view(unsigned char *acts, int nblk) {
 __device__ __forceinline__ float4 ldcg4(const float *p) { return __ldcg((const float4 *)p); }
 
 // src: [M, ld] f32 in global (written by other CTAs -> read through L2).  norm_w == nullptr: no RMSNorm.
+// Four threads own one 32-element block (8 consecutive elements each): global loads are fully coalesced, the
+// block max / sum are two xor-shuffles, and for the RMSNorm ops the values stay in registers between the
+// sum-of-squares pass and the quantisation pass, so a prologue costs ONE L2 round trip and one barrier.
+#define MG_MAXP 4
 template <int MM, bool ACTQ8>
 __device__ void stage_acts(const MegaParams &P, unsigned char *acts, const float *src, int ld, int K, const void *norm_w,
-                           int norm_dt, double *red /*[MM][16]*/, float *rs /*[MM]*/) {
+                           int norm_dt, double *red /*[MM][16]*/) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nblk = K / 32;
     ActView av = act_view<MM>(acts, nblk);
-    if (norm_w) { // RMSNorm.java:41-52
+    const int per_row = K / 8;            // 8-element tasks per row
+    const int total = MM * per_row;
+    const int passes = (total + MG_CONSUMERS - 1) / MG_CONSUMERS;
+    const bool keep = passes <= MG_MAXP;   // values fit in registers across the norm barrier
+    float xv[MG_MAXP][8];
+    float rsv[MM];
+#pragma unroll
+    for (int m = 0; m < MM; m++) rsv[m] = 1.0f;
+
+    auto load8 = [&](int task, float (&v)[8]) {
+        const int m = task / per_row, j = task - m * per_row;
+        if (task < total && m < P.M) {
+            const float4 a = ldcg4(src + (size_t)m * ld + j * 8), b = ldcg4(src + (size_t)m * ld + j * 8 + 4);
+            v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = 0.0f;
+        }
+    };
+
+    if (norm_w) { // RMSNorm.java:41-52: float products summed in double, /E, +eps, 1/sqrt, cast to float
         double ss[MM];
 #pragma unroll
         for (int m = 0; m < MM; m++) ss[m] = 0.0;
-        for (int i4 = tid; i4 < K / 4; i4 += MG_CONSUMERS) {
-            float4 v[MM];
+        if (keep) {
 #pragma unroll
-            for (int m = 0; m < MM; m++) v[m] = m < P.M ? ldcg4(src + (size_t)m * ld + i4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int p = 0; p < MG_MAXP; p++)
+                if (p < passes) load8(p * MG_CONSUMERS + tid, xv[p]);
 #pragma unroll
-            for (int m = 0; m < MM; m++) {
-                ss[m] += (double)__fmul_rn(v[m].x, v[m].x);
-                ss[m] += (double)__fmul_rn(v[m].y, v[m].y);
-                ss[m] += (double)__fmul_rn(v[m].z, v[m].z);
-                ss[m] += (double)__fmul_rn(v[m].w, v[m].w);
+            for (int p = 0; p < MG_MAXP; p++)
+                if (p < passes) {
+                    const int m = (p * MG_CONSUMERS + tid) / per_row;
+                    double t = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) t += (double)__fmul_rn(xv[p][i], xv[p][i]);
+#pragma unroll
+                    for (int mm = 0; mm < MM; mm++)
+                        if (mm == m) ss[mm] += t;
+                }
+        } else {
+            for (int task = tid; task < total; task += MG_CONSUMERS) {
+                float v[8];
+                load8(task, v);
+                const int m = task / per_row;
+                double t = 0.0;
+#pragma unroll
+                for (int i = 0; i < 8; i++) t += (double)__fmul_rn(v[i], v[i]);
+#pragma unroll
+                for (int mm = 0; mm < MM; mm++)
+                    if (mm == m) ss[mm] += t;
             }
         }
 #pragma unroll
@@ -280,147 +343,241 @@ __device__ void stage_acts(const MegaParams &P, unsigned char *acts, const float
             if (lane == 0) red[m * MG_CWARPS + warp] = ss[m];
         }
         consumer_bar();
-        if (tid < MM) {
+#pragma unroll
+        for (int m = 0; m < MM; m++) { // every thread finishes the reduction itself: no second barrier
             double t = 0;
-            for (int w = 0; w < MG_CWARPS; w++) t += red[tid * MG_CWARPS + w];
+#pragma unroll
+            for (int w = 0; w < MG_CWARPS; w++) t += red[m * MG_CWARPS + w];
             t /= (double)P.E;
             t += (double)P.eps;
-            rs[tid] = (float)(1.0 / sqrt(t));
+            rsv[m] = (float)(1.0 / sqrt(t));
         }
-        consumer_bar();
     }
-    for (int idx = tid; idx < MM * nblk; idx += MG_CONSUMERS) {
-        const int m = idx / nblk, b = idx - m * nblk;
-        float v[32];
-        if (m < P.M) {
-            const float *sp = src + (size_t)m * ld + b * 32;
-            float4 x4[8];
+
+    auto process = [&](int task, float (&v)[8]) {
+        const int m = task / per_row, j = task - m * per_row;
+        const int b = j >> 2, sub = j & 3; // block, 8-element part of the block
+        if (norm_w && task < total) {
+            float rsf = 1.0f;
 #pragma unroll
-            for (int i = 0; i < 8; i++) x4[i] = ldcg4(sp + i * 4);
-#pragma unroll
-            for (int i = 0; i < 8; i++) v[i * 4] = x4[i].x, v[i * 4 + 1] = x4[i].y, v[i * 4 + 2] = x4[i].z, v[i * 4 + 3] = x4[i].w;
-            if (norm_w) {
-                const float rsf = rs[m];
-#pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    const float w = norm_dt == JL_BF16 ? bf16_bits_to_f32(((const uint16_t *)norm_w)[b * 32 + i])
-                                                       : ((const float *)norm_w)[b * 32 + i];
-                    v[i] = __fmul_rn(__fadd_rn(0.0f, w), __fmul_rn(rsf, v[i]));
-                }
+            for (int mm = 0; mm < MM; mm++)
+                if (mm == m) rsf = rsv[mm];
+            float w[8];
+            if (norm_dt == JL_BF16) {
+                const uint4 u = __ldg((const uint4 *)((const uint16_t *)norm_w + j * 8));
+                w[0] = __uint_as_float(u.x << 16), w[1] = __uint_as_float(u.x & 0xffff0000u);
+                w[2] = __uint_as_float(u.y << 16), w[3] = __uint_as_float(u.y & 0xffff0000u);
+                w[4] = __uint_as_float(u.z << 16), w[5] = __uint_as_float(u.z & 0xffff0000u);
+                w[6] = __uint_as_float(u.w << 16), w[7] = __uint_as_float(u.w & 0xffff0000u);
+            } else {
+                const float4 a = __ldg((const float4 *)((const float *)norm_w + j * 8));
+                const float4 c = __ldg((const float4 *)((const float *)norm_w + j * 8 + 4));
+                w[0] = a.x, w[1] = a.y, w[2] = a.z, w[3] = a.w, w[4] = c.x, w[5] = c.y, w[6] = c.z, w[7] = c.w;
             }
-        } else {
 #pragma unroll
-            for (int i = 0; i < 32; i++) v[i] = 0.0f;
+            for (int i = 0; i < 8; i++) v[i] = __fmul_rn(__fadd_rn(0.0f, w[i]), __fmul_rn(rsf, v[i]));
         }
         if (ACTQ8) { // PanamaTensorOperations.java:1696-1710
             float mx = 0.0f;
 #pragma unroll
-            for (int i = 0; i < 32; i++) mx = fmaxf(mx, fabsf(v[i]));
+            for (int i = 0; i < 8; i++) mx = fmaxf(mx, fabsf(v[i]));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
             const float d = __fdiv_rn(mx, 127.0f);
             const float id = mx != 0.0f ? __fdiv_rn(127.0f, mx) : 0.0f;
-            uint32_t w[8];
-            int sum = 0;
+            int q[8], sum = 0;
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                const int q0 = (int)__fadd_rn(__fmul_rn(v[i * 4], id), 0.5f);
-                const int q1 = (int)__fadd_rn(__fmul_rn(v[i * 4 + 1], id), 0.5f);
-                const int q2 = (int)__fadd_rn(__fmul_rn(v[i * 4 + 2], id), 0.5f);
-                const int q3 = (int)__fadd_rn(__fmul_rn(v[i * 4 + 3], id), 0.5f);
-                sum += q0 + q1 + q2 + q3;
-                w[i] = (uint32_t)(q0 & 0xFF) | ((uint32_t)(q1 & 0xFF) << 8) | ((uint32_t)(q2 & 0xFF) << 16) |
-                       ((uint32_t)(q3 & 0xFF) << 24);
+                q[i] = (int)__fadd_rn(__fmul_rn(v[i], id), 0.5f);
+                sum += q[i];
             }
-            *(uint4 *)(av.aq + (((size_t)m * 2 + 0) * nblk + b) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-            *(uint4 *)(av.aq + (((size_t)m * 2 + 1) * nblk + b) * 16) = make_uint4(w[4], w[5], w[6], w[7]);
-            av.asc[m * nblk + b] = d;
-            av.asum[m * nblk + b] = sum;
-        } else {
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            if (task < total) {
+                uint2 w2;
+                w2.x = (uint32_t)(q[0] & 0xFF) | ((uint32_t)(q[1] & 0xFF) << 8) | ((uint32_t)(q[2] & 0xFF) << 16) | ((uint32_t)(q[3] & 0xFF) << 24);
+                w2.y = (uint32_t)(q[4] & 0xFF) | ((uint32_t)(q[5] & 0xFF) << 8) | ((uint32_t)(q[6] & 0xFF) << 16) | ((uint32_t)(q[7] & 0xFF) << 24);
+                *(uint2 *)(av.aq + (((size_t)m * 2 + (sub >> 1)) * nblk + b) * 16 + (sub & 1) * 8) = w2;
+                if (sub == 0) {
+                    av.asc[m * nblk + b] = d;
+                    av.asum[m * nblk + b] = sum;
+                }
+            }
+        } else if (task < total) {
+            av.af4[((size_t)m * 8 + sub * 2) * nblk + b] = make_float4(v[0], v[1], v[2], v[3]);
+            av.af4[((size_t)m * 8 + sub * 2 + 1) * nblk + b] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+    };
+    if (norm_w && keep) {
 #pragma unroll
-            for (int c4 = 0; c4 < 8; c4++)
-                av.af4[((size_t)m * 8 + c4) * nblk + b] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+        for (int p = 0; p < MG_MAXP; p++)
+            if (p < passes) process(p * MG_CONSUMERS + tid, xv[p]);
+    } else {
+        for (int p = 0; p < passes; p += 2) { // two independent tasks in flight per thread
+            float v0[8], v1[8];
+            load8(p * MG_CONSUMERS + tid, v0);
+            if (p + 1 < passes) load8((p + 1) * MG_CONSUMERS + tid, v1);
+            process(p * MG_CONSUMERS + tid, v0);
+            if (p + 1 < passes) process((p + 1) * MG_CONSUMERS + tid, v1);
         }
     }
     consumer_bar();
 }
 
 // ---- consumer math on one ring stage -----------------------------------------------------------------------------------
-// Q8 activations x Q4 weights; acc[0] = row (or gate), acc[1] = up (pair stages)
-template <int MM>
-__device__ __forceinline__ void consume_q8(const Stage &d, const unsigned char *slot, const ActView &av, int nblk_total,
-                                           float (&acc)[2][MM], int warp, int lane) {
-    if (warp >= d.nrows) return;
-    const int nb = d.ncols / 32, blk0 = d.c0 / 32;
-    const int nsub = d.pair ? 2 : 1;
+// unit u -> row slot i = u / wpr, K-range qd = u % wpr.
+struct WarpRow {
+    const unsigned char *nib;
+    const float *sc;
+    int b0, nb; // first block and number of blocks of this unit's K-range
+    int row;    // row (or pair) index inside the stage
+    int up;     // pair stages: 1 = up row
+    bool valid;
+};
+__device__ __forceinline__ WarpRow warp_row(const Stage &d, const unsigned char *slot, int unit) {
+    WarpRow r;
+    const int i = unit >> d.wpr_shift, qd = unit & (d.wpr - 1);
+    r.up = d.pair ? (i >= d.R) : 0;
+    r.row = d.pair ? (i & (d.R - 1)) : i;
+    r.valid = r.row < d.nrows && i < (d.pair ? 2 * d.R : d.R);
+    r.nb = (d.K >> 5) >> d.wpr_shift;
+    r.b0 = qd * r.nb;
+    r.nib = slot + (size_t)i * (d.K >> 1);
+    r.sc = (const float *)(slot + MG_STAGE_NIB + (size_t)i * (d.K >> 3));
+    return r;
+}
+
+// Q8 activations of the (up to four) blocks a lane owns in its warp's K-range, kept in registers for a whole op
+struct ActRegs {
+    uint4 lo[4], hi[4];
+    float sc[4];
+    int sum[4];
+};
+__device__ __forceinline__ void load_act_regs(ActRegs &ar, const ActView &av, int nblk_total, int b0, int nb, int lane) {
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
-        if (u >= nsub) break;
-        const unsigned char *nib = slot + warp * 2048 + u * 1024;
-        const float *sc = (const float *)(slot + MG_STAGE_NIB + warp * 512 + u * 256);
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int b = lane + 32 * j;
-            if (b >= nb) break;
-            const uint4 q = *(const uint4 *)(nib + b * 16);
-            const float sb = sc[b];
-            const int gb = blk0 + b;
-#pragma unroll
-            for (int m = 0; m < MM; m++) {
-                const uint4 alo = *(const uint4 *)(av.aq + (((size_t)m * 2 + 0) * nblk_total + gb) * 16);
-                const uint4 ahi = *(const uint4 *)(av.aq + (((size_t)m * 2 + 1) * nblk_total + gb) * 16);
-                int s = 0;
-                s = __dp4a((int)(q.x & 0x0F0F0F0Fu), (int)alo.x, s);
-                s = __dp4a((int)((q.x >> 4) & 0x0F0F0F0Fu), (int)ahi.x, s);
-                s = __dp4a((int)(q.y & 0x0F0F0F0Fu), (int)alo.y, s);
-                s = __dp4a((int)((q.y >> 4) & 0x0F0F0F0Fu), (int)ahi.y, s);
-                s = __dp4a((int)(q.z & 0x0F0F0F0Fu), (int)alo.z, s);
-                s = __dp4a((int)((q.z >> 4) & 0x0F0F0F0Fu), (int)ahi.z, s);
-                s = __dp4a((int)(q.w & 0x0F0F0F0Fu), (int)alo.w, s);
-                s = __dp4a((int)((q.w >> 4) & 0x0F0F0F0Fu), (int)ahi.w, s);
-                s -= 8 * av.asum[m * nblk_total + gb];
-                acc[u][m] = fmaf(__fmul_rn(av.asc[m * nblk_total + gb], sb), (float)s, acc[u][m]);
-            }
+    for (int j = 0; j < 4; j++) {
+        const int b = b0 + lane + 32 * j;
+        if (lane + 32 * j < nb) {
+            ar.lo[j] = *(const uint4 *)(av.aq + ((size_t)0 * nblk_total + b) * 16);
+            ar.hi[j] = *(const uint4 *)(av.aq + ((size_t)1 * nblk_total + b) * 16);
+            ar.sc[j] = av.asc[b];
+            ar.sum[j] = av.asum[b];
+        } else {
+            ar.lo[j] = make_uint4(0, 0, 0, 0), ar.hi[j] = ar.lo[j], ar.sc[j] = 0.0f, ar.sum[j] = 0;
         }
     }
 }
 
-// F32 activations x Q4 weights (lm_head; AbstractModel.java:444-449)
+// Q8 activations x Q4 weights for the warp's two units (same K-range).  All weight loads are issued before the
+// math, the two halves of a block run on independent dp4a chains, and the per-row accumulation order (blocks
+// lane, lane+32, ...) is the same as in jl_gemv.cu.  REGS: activations come from ActRegs (MM == 1).
+template <int MM, bool REGS>
+__device__ __forceinline__ void consume2_q8(const WarpRow (&r)[2], const ActView &av, const ActRegs &ar, int nblk_total,
+                                            float (&acc)[2][MM], int lane) {
+    const int b0 = r[0].b0, nb = r[0].nb;
+    for (int off = lane; off < nb; off += 128) {
+        uint4 q[2][4];
+        float sb[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int b = b0 + off + 32 * j;
+                if (r[u].valid && off + 32 * j < nb) {
+                    q[u][j] = *(const uint4 *)(r[u].nib + (size_t)b * 16);
+                    sb[u][j] = r[u].sc[b];
+                } else {
+                    q[u][j] = make_uint4(0, 0, 0, 0), sb[u][j] = 0.0f;
+                }
+            }
+#pragma unroll
+        for (int m = 0; m < MM; m++) {
+            int s[2][4];
+            float sc[2][4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int b = b0 + off + 32 * j;
+                const bool ok = off + 32 * j < nb;
+                uint4 alo, ahi;
+                float asc;
+                int asum;
+                if (REGS) {
+                    alo = ar.lo[j], ahi = ar.hi[j], asc = ar.sc[j], asum = ar.sum[j];
+                } else if (ok) {
+                    alo = *(const uint4 *)(av.aq + (((size_t)m * 2 + 0) * nblk_total + b) * 16);
+                    ahi = *(const uint4 *)(av.aq + (((size_t)m * 2 + 1) * nblk_total + b) * 16);
+                    asc = av.asc[m * nblk_total + b];
+                    asum = av.asum[m * nblk_total + b];
+                } else {
+                    alo = make_uint4(0, 0, 0, 0), ahi = alo, asc = 0.0f, asum = 0;
+                }
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    int s0 = 0, s1 = 0;
+                    s0 = __dp4a((int)(q[u][j].x & 0x0F0F0F0Fu), (int)alo.x, s0);
+                    s1 = __dp4a((int)((q[u][j].x >> 4) & 0x0F0F0F0Fu), (int)ahi.x, s1);
+                    s0 = __dp4a((int)(q[u][j].y & 0x0F0F0F0Fu), (int)alo.y, s0);
+                    s1 = __dp4a((int)((q[u][j].y >> 4) & 0x0F0F0F0Fu), (int)ahi.y, s1);
+                    s0 = __dp4a((int)(q[u][j].z & 0x0F0F0F0Fu), (int)alo.z, s0);
+                    s1 = __dp4a((int)((q[u][j].z >> 4) & 0x0F0F0F0Fu), (int)ahi.z, s1);
+                    s0 = __dp4a((int)(q[u][j].w & 0x0F0F0F0Fu), (int)alo.w, s0);
+                    s1 = __dp4a((int)((q[u][j].w >> 4) & 0x0F0F0F0Fu), (int)ahi.w, s1);
+                    s[u][j] = s0 + s1 - 8 * asum;
+                    sc[u][j] = __fmul_rn(asc, sb[u][j]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (off + 32 * j < nb) acc[u][m] = fmaf(sc[u][j], (float)s[u][j], acc[u][m]);
+        }
+    }
+}
+
+// F32 activations x Q4 weights (lm_head; AbstractModel.java:444-449): the two rows share every activation load
 template <int MM>
-__device__ __forceinline__ void consume_f32(const Stage &d, const unsigned char *slot, const ActView &av, int nblk_total,
-                                            float (&acc)[2][MM], int warp, int lane) {
-    if (warp >= d.nrows) return;
-    const int nb = d.ncols / 32, blk0 = d.c0 / 32;
-    const unsigned char *nib = slot + warp * 2048;
-    const float *sc = (const float *)(slot + MG_STAGE_NIB + warp * 512);
+__device__ __forceinline__ void consume2_f32(const WarpRow (&r)[2], const ActView &av, int nblk_total, float (&acc)[2][MM],
+                                             int lane) {
+    const int b0 = r[0].b0, nb = r[0].nb;
+    for (int off = lane; off < nb; off += 32) {
+        const int b = b0 + off;
+        float wf[2][32], sb[2];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int b = lane + 32 * j;
-        if (b >= nb) break;
-        const uint4 q = *(const uint4 *)(nib + b * 16);
-        const float sb = sc[b];
-        const int gb = blk0 + b;
-        float wf[32];
-        const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+        for (int u = 0; u < 2; u++) {
+            uint4 q = make_uint4(0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u);
+            sb[u] = 0.0f;
+            if (r[u].valid) {
+                q = *(const uint4 *)(r[u].nib + (size_t)b * 16);
+                sb[u] = r[u].sc[b];
+            }
+            const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const uint32_t lo = qw[i] & 0x0F0F0F0Fu, hi = (qw[i] >> 4) & 0x0F0F0F0Fu;
+            for (int i = 0; i < 4; i++) {
+                const uint32_t lo = qw[i] & 0x0F0F0F0Fu, hi = (qw[i] >> 4) & 0x0F0F0F0Fu;
 #pragma unroll
-            for (int t = 0; t < 4; t++) {
-                wf[i * 4 + t] = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7540 | t)) - 8388616.0f;
-                wf[16 + i * 4 + t] = __uint_as_float(__byte_perm(hi, 0x4B000000u, 0x7540 | t)) - 8388616.0f;
+                for (int t = 0; t < 4; t++) {
+                    wf[u][i * 4 + t] = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7540 | t)) - 8388616.0f;
+                    wf[u][16 + i * 4 + t] = __uint_as_float(__byte_perm(hi, 0x4B000000u, 0x7540 | t)) - 8388616.0f;
+                }
             }
         }
 #pragma unroll
         for (int m = 0; m < MM; m++) {
-            float part = 0.0f;
+            float part[2] = {0.0f, 0.0f};
 #pragma unroll
             for (int c4 = 0; c4 < 8; c4++) {
-                const float4 a4 = av.af4[((size_t)m * 8 + c4) * nblk_total + gb];
-                part = fmaf(a4.x, wf[c4 * 4 + 0], part);
-                part = fmaf(a4.y, wf[c4 * 4 + 1], part);
-                part = fmaf(a4.z, wf[c4 * 4 + 2], part);
-                part = fmaf(a4.w, wf[c4 * 4 + 3], part);
+                const float4 a4 = av.af4[((size_t)m * 8 + c4) * nblk_total + b];
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    part[u] = fmaf(a4.x, wf[u][c4 * 4 + 0], part[u]);
+                    part[u] = fmaf(a4.y, wf[u][c4 * 4 + 1], part[u]);
+                    part[u] = fmaf(a4.z, wf[u][c4 * 4 + 2], part[u]);
+                    part[u] = fmaf(a4.w, wf[u][c4 * 4 + 3], part[u]);
+                }
             }
-            acc[0][m] = fmaf(sb, part, acc[0][m]);
+#pragma unroll
+            for (int u = 0; u < 2; u++) acc[u][m] = fmaf(sb[u], part[u], acc[u][m]);
         }
     }
 }
@@ -446,10 +603,14 @@ __device__ __forceinline__ uint16_t mg_bf16(float n) {
 
 // One (row m, kv head, split) task.  smem `u` (sized by uarea_bytes) aliases the
 // activation staging area, which is dead between the QKV stages and the o_proj prologue.
+// Latency plan: the RoPE inputs, the KV append and the first K/V tile are all requested before the first
+// barrier; the next tile is prefetched into registers while the current one is processed; the row of the
+// current position is taken from shared memory (never re-read from the page it was just written to).
 template <int HS>
 __device__ void attention_task(const MegaParams &P, int layer, int m, int kvh, int split, unsigned char *u) {
     constexpr int C4 = HS / 4;
     constexpr int PARTS = MG_CONSUMERS / HS; // P.V position groups
+    constexpr int NF = (MG_ATT_TILE * C4 + MG_CONSUMERS - 1) / MG_CONSUMERS; // float4 per thread per tile
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int group = P.heads / P.kv_heads;
     float4 *Ks = (float4 *)u;                    // [TILE][C4] swizzled
@@ -459,7 +620,9 @@ __device__ void attention_task(const MegaParams &P, int layer, int m, int kvh, i
     float *hm = ps + MG_ATT_TILE * MG_MAX_GROUP; // running max / sum / correction per head
     float *hl = hm + MG_MAX_GROUP;
     float *hc = hl + MG_MAX_GROUP;
-    float *comb = hc + MG_MAX_GROUP + 8;         // [PARTS][MAX_GROUP][HS] P.V combine buffer
+    float *knew = hc + MG_MAX_GROUP + 8;         // [HS] rotated key of the current position
+    float *vnew = knew + HS;                     // [HS]
+    float *comb = vnew + HS;                     // [PARTS][MAX_GROUP][HS] P.V combine buffer
 
     const int session = P.sessions[m], pos = P.positions[m];
     const int n = pos + 1;
@@ -469,33 +632,65 @@ __device__ void attention_task(const MegaParams &P, int layer, int m, int kvh, i
     const int hp = HS / 2;
     const int h0 = kvh * group, xoff = kvh * HS, dt = P.kv.kv_dtype;
     const size_t poffset = (size_t)pos * hp;
+    const bool owner = pos >= t0 && pos < t1;
+
+    float4 kreg[NF], vreg[NF];
+    auto fetch_tile = [&](int tb) {
+#pragma unroll
+        for (int i = 0; i < NF; i++) {
+            const int f = tid + i * MG_CONSUMERS;
+            const int r = f / C4, c4 = f % C4;
+            kreg[i] = make_float4(0.f, 0.f, 0.f, 0.f), vreg[i] = kreg[i];
+            if (f < MG_ATT_TILE * C4 && tb + r < t1 && tb + r != pos) {
+                const char *kr = mg_kv_row(P.kv, session, layer, tb + r, 0);
+                const char *vr = mg_kv_row(P.kv, session, layer, tb + r, 1);
+                if (dt == JL_F32) {
+                    kreg[i] = __ldcg((const float4 *)((const float *)kr + xoff + c4 * 4));
+                    vreg[i] = __ldcg((const float4 *)((const float *)vr + xoff + c4 * 4));
+                } else {
+                    const uint2 uk = __ldcg((const uint2 *)((const uint16_t *)kr + xoff + c4 * 4));
+                    const uint2 uv = __ldcg((const uint2 *)((const uint16_t *)vr + xoff + c4 * 4));
+                    kreg[i] = make_float4(__uint_as_float(uk.x << 16), __uint_as_float(uk.x & 0xffff0000u),
+                                          __uint_as_float(uk.y << 16), __uint_as_float(uk.y & 0xffff0000u));
+                    vreg[i] = make_float4(__uint_as_float(uv.x << 16), __uint_as_float(uv.x & 0xffff0000u),
+                                          __uint_as_float(uv.y << 16), __uint_as_float(uv.y & 0xffff0000u));
+                }
+            }
+        }
+    };
+    if (t0 < t1) fetch_tile(t0);
 
     // RoPE on this group's queries (CausalSelfAttention.java:260-268: table index poffset + kvh_global*hs + j)
     for (int idx = tid; idx < group * hp; idx += MG_CONSUMERS) {
         const int h = idx / hp, j = idx % hp;
-        const float2 f = ((const float2 *)P.rope)[poffset + (size_t)(P.kv_head0_global + kvh) * HS + j];
+        const float2 f = __ldg((const float2 *)P.rope + poffset + (size_t)(P.kv_head0_global + kvh) * HS + j);
         const float *qr = P.q + (size_t)m * P.attn_seg + (h0 + h) * HS;
         const float q0 = __ldcg(qr + j), q1 = __ldcg(qr + j + hp);
         qs[h * HS + j] = __fsub_rn(__fmul_rn(q0, f.x), __fmul_rn(q1, f.y));
         qs[h * HS + j + hp] = __fadd_rn(__fmul_rn(q0, f.y), __fmul_rn(q1, f.x));
     }
-    // the split that contains `pos` appends the rotated key and the value to the page (:230-243,279-285)
-    if (pos >= t0 && pos < t1) {
-        char *krow = (char *)mg_kv_row(P.kv, session, layer, pos, 0);
-        char *vrow = (char *)mg_kv_row(P.kv, session, layer, pos, 1);
-        for (int j = tid; j < hp; j += MG_CONSUMERS) {
-            const float2 f = ((const float2 *)P.rope)[poffset + (size_t)(P.kv_head0_global + kvh) * HS + j];
+    // the split that contains `pos` rotates the key, appends key and value to the page (:230-243,279-285)
+    // and keeps both in shared memory for its own scores
+    if (owner) {
+        for (int j = MG_CONSUMERS - 1 - tid; j < hp; j += MG_CONSUMERS) { // use the warps the q loop leaves idle
+            const float2 f = __ldg((const float2 *)P.rope + poffset + (size_t)(P.kv_head0_global + kvh) * HS + j);
             const float *kr = P.k + (size_t)m * P.kv_seg + xoff, *vr = P.v + (size_t)m * P.kv_seg + xoff;
             const float k0 = __ldcg(kr + j), k1 = __ldcg(kr + j + hp);
-            const float r0 = __fsub_rn(__fmul_rn(k0, f.x), __fmul_rn(k1, f.y));
-            const float r1 = __fadd_rn(__fmul_rn(k0, f.y), __fmul_rn(k1, f.x));
             const float v0 = __ldcg(vr + j), v1 = __ldcg(vr + j + hp);
+            float r0 = __fsub_rn(__fmul_rn(k0, f.x), __fmul_rn(k1, f.y));
+            float r1 = __fadd_rn(__fmul_rn(k0, f.y), __fmul_rn(k1, f.x));
+            char *krow = (char *)mg_kv_row(P.kv, session, layer, pos, 0);
+            char *vrow = (char *)mg_kv_row(P.kv, session, layer, pos, 1);
             if (dt == JL_F32) {
                 ((float *)krow)[xoff + j] = r0, ((float *)krow)[xoff + j + hp] = r1;
                 ((float *)vrow)[xoff + j] = v0, ((float *)vrow)[xoff + j + hp] = v1;
-            } else {
-                ((uint16_t *)krow)[xoff + j] = mg_bf16(r0), ((uint16_t *)krow)[xoff + j + hp] = mg_bf16(r1);
-                ((uint16_t *)vrow)[xoff + j] = mg_bf16(v0), ((uint16_t *)vrow)[xoff + j + hp] = mg_bf16(v1);
+                knew[j] = r0, knew[j + hp] = r1, vnew[j] = v0, vnew[j + hp] = v1;
+            } else { // the scores see the values as stored (bf16-rounded), like a later read of the page would
+                const uint16_t b0 = mg_bf16(r0), b1 = mg_bf16(r1), c0 = mg_bf16(v0), c1 = mg_bf16(v1);
+                ((uint16_t *)krow)[xoff + j] = b0, ((uint16_t *)krow)[xoff + j + hp] = b1;
+                ((uint16_t *)vrow)[xoff + j] = c0, ((uint16_t *)vrow)[xoff + j + hp] = c1;
+                knew[j] = bf16_bits_to_f32(b0), knew[j + hp] = bf16_bits_to_f32(b1);
+                vnew[j] = bf16_bits_to_f32(c0), vnew[j + hp] = bf16_bits_to_f32(c1);
             }
         }
     }
@@ -508,36 +703,32 @@ __device__ void attention_task(const MegaParams &P, int layer, int m, int kvh, i
 
     for (int tb = t0; tb < t1; tb += MG_ATT_TILE) {
         const int cnt = min(MG_ATT_TILE, t1 - tb);
-        // stage K and V rows of the tile (coalesced 128-bit loads through L2)
-        for (int f = tid; f < cnt * C4; f += MG_CONSUMERS) {
+        // registers -> shared (the current position's row comes from knew/vnew)
+#pragma unroll
+        for (int i = 0; i < NF; i++) {
+            const int f = tid + i * MG_CONSUMERS;
             const int r = f / C4, c4 = f % C4;
-            const char *kr = mg_kv_row(P.kv, session, layer, tb + r, 0);
-            const char *vr = mg_kv_row(P.kv, session, layer, tb + r, 1);
-            float4 k4, v4;
-            if (dt == JL_F32) {
-                k4 = __ldcg((const float4 *)((const float *)kr + xoff + c4 * 4));
-                v4 = __ldcg((const float4 *)((const float *)vr + xoff + c4 * 4));
-            } else {
-                const uint2 uk = __ldcg((const uint2 *)((const uint16_t *)kr + xoff + c4 * 4));
-                const uint2 uv = __ldcg((const uint2 *)((const uint16_t *)vr + xoff + c4 * 4));
-                k4 = make_float4(__uint_as_float(uk.x << 16), __uint_as_float(uk.x & 0xffff0000u), __uint_as_float(uk.y << 16),
-                                 __uint_as_float(uk.y & 0xffff0000u));
-                v4 = make_float4(__uint_as_float(uv.x << 16), __uint_as_float(uv.x & 0xffff0000u), __uint_as_float(uv.y << 16),
-                                 __uint_as_float(uv.y & 0xffff0000u));
+            if (f < MG_ATT_TILE * C4 && r < cnt) {
+                float4 k4 = kreg[i], v4 = vreg[i];
+                if (tb + r == pos) {
+                    k4 = *(const float4 *)(knew + c4 * 4);
+                    v4 = *(const float4 *)(vnew + c4 * 4);
+                }
+                Ks[r * C4 + (c4 ^ (r & 7))] = k4;
+                Vs[r * C4 + c4] = v4;
             }
-            Ks[r * C4 + (c4 ^ (r & 7))] = k4;
-            Vs[r * C4 + c4] = v4;
         }
+        if (tb + MG_ATT_TILE < t1) fetch_tile(tb + MG_ATT_TILE); // in flight while this tile is processed
         consumer_bar();
-        // scores (batchDotProduct :324-330, scale :332)
-        for (int idx = tid; idx < group * MG_ATT_TILE; idx += MG_CONSUMERS) {
-            const int h = idx / MG_ATT_TILE, t = idx % MG_ATT_TILE;
-            float s = -INFINITY;
+        // scores (batchDotProduct :324-330, scale :332): 4 threads per (head, position), 1/4 of the head each
+        for (int idx = tid; idx < group * MG_ATT_TILE * 4; idx += MG_CONSUMERS) {
+            const int qd = idx & 3, t = (idx >> 2) % MG_ATT_TILE, h = idx / (4 * MG_ATT_TILE);
+            float a = 0.0f;
             if (t < cnt) {
-                float a = 0.0f;
                 const float4 *q4 = (const float4 *)(qs + h * HS);
-#pragma unroll 8
-                for (int c4 = 0; c4 < C4; c4++) {
+#pragma unroll
+                for (int c = 0; c < C4 / 4; c++) {
+                    const int c4 = qd * (C4 / 4) + c;
                     const float4 k4 = Ks[t * C4 + (c4 ^ (t & 7))];
                     const float4 qq = q4[c4];
                     a = fmaf(qq.x, k4.x, a);
@@ -545,9 +736,10 @@ __device__ void attention_task(const MegaParams &P, int layer, int m, int kvh, i
                     a = fmaf(qq.z, k4.z, a);
                     a = fmaf(qq.w, k4.w, a);
                 }
-                s = __fmul_rn(a, P.attn_scale);
             }
-            ps[t * MG_MAX_GROUP + h] = s;
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            if (qd == 0) ps[t * MG_MAX_GROUP + h] = t < cnt ? __fmul_rn(a, P.attn_scale) : -INFINITY;
         }
         consumer_bar();
         // online softmax: warp h owns head h (TILE == 32: one score per lane)
@@ -624,6 +816,11 @@ __device__ __forceinline__ unsigned long long pack_arg(float v, int idx) {
     return ((unsigned long long)b << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)idx);
 }
 
+#define MG_TRACE(slot_)                                                                     \
+    do {                                                                                    \
+        if (tr && tid == 0) tr[(size_t)op * 8 + (slot_)] = clock64();                      \
+    } while (0)
+
 template <int MM, int NSTAGE>
 __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const MegaParams P) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -631,9 +828,14 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const MegaPa
     unsigned char *uarea = smem + (size_t)NSTAGE * MG_STAGE_BYTES;
     __shared__ uint64_t full[NSTAGE], empty[NSTAGE];
     __shared__ double red[MM * MG_CWARPS];
-    __shared__ float rs[MM];
     __shared__ unsigned long long wbest[MM][MG_CWARPS];
     __shared__ int s_last;
+    __shared__ float ebuf[MG_EROWS * 2 * 8 * MM];
+    __shared__ int emeta[MG_EROWS];
+    __shared__ int s_op_first[MG_MAX_OPS + 1];
+    __shared__ __align__(16) MegaMeta sdesc[NSTAGE];
+    __shared__ __align__(16) unsigned char dbuf[2 * MG_DB * MG_REC_BYTES];
+    __shared__ uint64_t dfull[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, cta = blockIdx.x;
@@ -642,18 +844,21 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const MegaPa
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], MG_CWARPS);
         }
+        mbar_init(&dfull[0], 1);
+        mbar_init(&dfull[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     if (warp == MG_CWARPS) { // ===== producer warp =====
-        producer_loop<NSTAGE>(P, ring, full, empty, lane);
+        producer_loop<NSTAGE>(P, ring, full, empty, sdesc, dbuf, dfull, lane);
         return;
     }
 
     // ===== consumers =====
     unsigned *sync = P.sync;
     const int n_ops = P.layers * 4 + 1;
+    for (int i = tid; i <= n_ops; i += MG_CONSUMERS) s_op_first[i] = __ldg(&P.op_first[(size_t)cta * (n_ops + 1) + i]);
     // embedding lookup (LlamaModel.java:68-100): columns split over the grid
     {
         const int c_a = (int)(((long long)P.E * cta) / G), c_b = (int)(((long long)P.E * (cta + 1)) / G);
@@ -677,21 +882,31 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const MegaPa
         op_signal(&sync[0]);
     }
 
-    Sched s = {0, 0, 0, 0};
     Stage d;
     unsigned cit = 0;
+    long long *tr = nullptr;
+    if (P.trace) {
+        const int which = cta == 0 ? 0 : (cta == G / 2 ? 1 : (cta == G - 1 ? 2 : -1));
+        if (which >= 0) tr = P.trace + (size_t)which * (P.layers * 4 + 1) * 8;
+    }
     float best_v[MM];
     int best_i[MM];
 #pragma unroll
     for (int m = 0; m < MM; m++) best_v[m] = -INFINITY, best_i[m] = 0x7fffffff;
 
     for (int op = 0; op < n_ops; op++) {
-        const OpInfo oi = op_info(P, op);
-        const int L = oi.layer;
+        struct {
+            int type, K, pair;
+        } oi;
+        oi.type = op < P.layers * 4 ? (op & 3) : OP_LMHEAD;
+        oi.pair = oi.type == OP_GATEUP;
+        oi.K = oi.type == OP_O ? P.attn_seg : (oi.type == OP_DOWN ? P.H : P.E);
+        const int L = op < P.layers * 4 ? (op >> 2) : P.layers;
         unsigned *cnt = &sync[1 + (op < P.layers * 4 ? L * 5 + (oi.type == OP_QKV ? 0 : oi.type == OP_O ? 2 : oi.type == OP_GATEUP ? 3 : 4)
                                                       : P.layers * 5)];
+        MG_TRACE(0);
         // ---- attention phase sits between QKV and O ----
-        if (oi.type == OP_O) {
+        if (oi.type == OP_O && !(P.dbg & 2)) {
             const int ntasks = P.M * P.kv_heads * P.splits;
             if (cta < ntasks) {
                 const int split = cta % P.splits, kvh = (cta / P.splits) % P.kv_heads, m = cta / (P.splits * P.kv_heads);
@@ -723,87 +938,143 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const MegaPa
                 }
             }
         }
+        MG_TRACE(1);
         // ---- does this CTA own rows of the op? ----
-        Sched probe = s;
-        const bool has = sched_get(P, probe, d, op + 1) && d.op == op;
-        if (has) {
+        const void *nw_attn = nullptr, *nw_ffn = nullptr;
+        int nw_attn_dt = 0, nw_ffn_dt = 0;
+        if (op < P.layers * 4) {
+            nw_attn = P.lw[L].attn_norm, nw_attn_dt = P.lw[L].attn_norm_dt;
+            nw_ffn = P.lw[L].ffn_norm, nw_ffn_dt = P.lw[L].ffn_norm_dt;
+        }
+        const int nst = s_op_first[op + 1] - s_op_first[op];
+        if (nst > 0) {
             // dependency + prologue
             const int K = oi.K, nblk = K / 32;
             ActView av;
-            if (oi.type == OP_QKV) {
+            if (P.dbg & 2) {
+            } else if (oi.type == OP_QKV) {
                 op_wait(L == 0 ? &sync[0] : &sync[1 + (L - 1) * 5 + 4], (unsigned)G);
-                stage_acts<MM, true>(P, uarea, P.x, P.E, K, P.lw[L].attn_norm, P.lw[L].attn_norm_dt, red, rs);
+                MG_TRACE(2);
+                stage_acts<MM, true>(P, uarea, P.x, P.E, K, nw_attn, nw_attn_dt, red);
             } else if (oi.type == OP_O) {
                 op_wait(&sync[1 + L * 5 + 1], (unsigned)(P.M * P.kv_heads));
-                stage_acts<MM, true>(P, uarea, P.att, P.attn_seg, K, nullptr, 0, red, rs);
+                MG_TRACE(2);
+                stage_acts<MM, true>(P, uarea, P.att, P.attn_seg, K, nullptr, 0, red);
             } else if (oi.type == OP_GATEUP) {
                 op_wait(&sync[1 + L * 5 + 2], (unsigned)G);
-                stage_acts<MM, true>(P, uarea, P.xb, P.E, K, P.lw[L].ffn_norm, P.lw[L].ffn_norm_dt, red, rs);
+                MG_TRACE(2);
+                stage_acts<MM, true>(P, uarea, P.xb, P.E, K, nw_ffn, nw_ffn_dt, red);
             } else if (oi.type == OP_DOWN) {
                 op_wait(&sync[1 + L * 5 + 3], (unsigned)G);
-                stage_acts<MM, true>(P, uarea, P.h, P.H, K, nullptr, 0, red, rs);
+                MG_TRACE(2);
+                stage_acts<MM, true>(P, uarea, P.h, P.H, K, nullptr, 0, red);
             } else {
                 op_wait(&sync[1 + (P.layers - 1) * 5 + 4], (unsigned)G);
-                stage_acts<MM, false>(P, uarea, P.x, P.E, K, P.out_norm, P.out_norm_dt, red, rs);
+                MG_TRACE(2);
+                stage_acts<MM, false>(P, uarea, P.x, P.E, K, P.out_norm, P.out_norm_dt, red);
             }
             av = act_view<MM>(uarea, nblk);
+            // the warp's fixed K-range for this op, and (single session) its activations in registers
+            const int op_wpr = MG_UNITS / (oi.pair ? 2 * stage_rows_dev(oi.K, 1) : stage_rows_dev(oi.K, 0));
+            ActRegs ar;
+            if (MM == 1 && oi.type != OP_LMHEAD) {
+                const int nbw = nblk / op_wpr;
+                load_act_regs(ar, av, nblk, (warp & (op_wpr - 1)) * nbw, nbw, lane);
+            }
+            MG_TRACE(3);
 
-            float acc[2][MM];
-#pragma unroll
-            for (int m = 0; m < MM; m++) acc[0][m] = 0.0f, acc[1][m] = 0.0f;
-            while (sched_get(P, s, d, op + 1) && d.op == op) {
+            int erow = 0;
+            for (int st = 0; st < nst; st++) {
                 const unsigned slot = cit % NSTAGE, use = cit / NSTAGE;
+#define MG_ST(k_) do { if (tr && (P.dbg & 4) && cta == 0 && tid == 0 && cit < 128) P.trace[(size_t)3 * n_ops * 8 + cit * 8 + (k_)] = clock64(); } while (0)
+                MG_ST(0);
                 mbar_wait(&full[slot], use & 1);
+                MG_ST(1);
+                {
+                    const MegaMeta md = sdesc[slot];
+                    d.seg = md.seg, d.row0 = md.row0, d.nrows = md.nrows, d.R = md.R, d.wpr = md.wpr, d.K = md.K, d.pair = md.pair, d.type = md.type, d.wpr_shift = md.wpr_shift, d.r_shift = md.r_shift;
+                }
                 const unsigned char *sp = ring + (size_t)slot * MG_STAGE_BYTES;
-                if (oi.type == OP_LMHEAD) consume_f32<MM>(d, sp, av, nblk, acc, warp, lane);
-                else consume_q8<MM>(d, sp, av, nblk, acc, warp, lane);
+                const WarpRow wr[2] = {warp_row(d, sp, warp), warp_row(d, sp, warp + MG_CWARPS)};
+                MG_ST(2);
+                float acc[2][MM];
+#pragma unroll
+                for (int m = 0; m < MM; m++) acc[0][m] = 0.0f, acc[1][m] = 0.0f;
+                if ((wr[0].valid || wr[1].valid) && !(P.dbg & 1)) {
+                    if (oi.type == OP_LMHEAD) consume2_f32<MM>(wr, av, nblk, acc, lane);
+                    else consume2_q8<MM, MM == 1>(wr, av, ar, nblk, acc, lane);
+                }
+                MG_ST(3);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[slot]);
-                cit++;
-                if (d.last_slice) {
-                    if (warp < d.nrows) {
-                        const int row = d.row0 + warp;
+                MG_ST(4);
 #pragma unroll
-                        for (int m = 0; m < MM; m++) {
-                            acc[0][m] = warp_sum(acc[0][m]);
-                            if (oi.pair) acc[1][m] = warp_sum(acc[1][m]);
-                        }
-                        if (lane == 0) {
+                for (int m = 0; m < MM; m++) acc[0][m] = warp_sum(acc[0][m]), acc[1][m] = warp_sum(acc[1][m]);
+                MG_ST(5);
+                cit++;
+                if (oi.type == OP_LMHEAD) {
+                    // logits + running arg-max (strict '>', lowest index wins); K = E is one unit per row
+                    if (lane == 0) {
+#pragma unroll
+                        for (int u = 0; u < 2; u++) {
+                            if (!wr[u].valid) continue;
+                            const int row = d.row0 + wr[u].row;
 #pragma unroll
                             for (int m = 0; m < MM; m++) {
                                 if (m >= P.M) continue;
-                                const float v = acc[0][m];
-                                switch (oi.type) {
-                                    case OP_QKV: {
-                                        float *out = d.seg == 0 ? P.q + (size_t)m * P.attn_seg
-                                                                : (d.seg == 1 ? P.k : P.v) + (size_t)m * P.kv_seg;
-                                        out[row] = v;
-                                    } break;
-                                    case OP_O: // TransformerBlock.java:185
-                                        P.xb[(size_t)m * P.E + row] = __fadd_rn(v, __ldcg(P.x + (size_t)m * P.E + row));
-                                        break;
-                                    case OP_GATEUP: // MLPBlock.java:132-141
-                                        P.h[(size_t)m * P.H + row] = __fmul_rn(silu_ref(v), acc[1][m]);
-                                        break;
-                                    case OP_DOWN: // TransformerBlock.java:203
-                                        P.x[(size_t)m * P.E + row] = __fadd_rn(v, __ldcg(P.xb + (size_t)m * P.E + row));
-                                        break;
-                                    default: // logits + running arg-max (strict '>', lowest index wins)
-                                        P.logits[(size_t)m * P.vocab + row] = v;
-                                        if (v > best_v[m] || (v == best_v[m] && row < best_i[m])) best_v[m] = v, best_i[m] = row;
-                                        break;
-                                }
+                                const float v = acc[u][m];
+                                P.logits[(size_t)m * P.vocab + row] = v;
+                                if (v > best_v[m] || (v == best_v[m] && row < best_i[m])) best_v[m] = v, best_i[m] = row;
                             }
                         }
                     }
+                } else {
+                    // park the (partial) sums in shared memory; the op-end pass combines K-ranges / gate+up and
+                    // applies the epilogue for all rows at once (no barrier, load or double math per stage)
+                    if (lane == 0) {
 #pragma unroll
-                    for (int m = 0; m < MM; m++) acc[0][m] = 0.0f, acc[1][m] = 0.0f;
+                        for (int u = 0; u < 2; u++) {
+                            if (!wr[u].valid) continue;
+                            const int e = erow + wr[u].row;
+                            const int qd = (warp + u * MG_CWARPS) & (d.wpr - 1);
+#pragma unroll
+                            for (int m = 0; m < MM; m++) ebuf[(((size_t)e * 2 + wr[u].up) * 8 + qd) * MM + m] = acc[u][m];
+                            if (qd == 0 && !wr[u].up) emeta[e] = (d.seg << 28) | (d.row0 + wr[u].row);
+                        }
+                    }
+                    erow += d.nrows;
                 }
-                sched_advance(s, d);
             }
-        } else {
-            s = probe; // nothing of this op here: cursor already skipped past it
+            if (oi.type != OP_LMHEAD) {
+                consumer_bar();
+                const int wpr = MG_UNITS / (oi.pair ? 2 * stage_rows_dev(oi.K, 1) : stage_rows_dev(oi.K, 0));
+                for (int t = tid; t < erow * MM; t += MG_CONSUMERS) {
+                    const int e = t / MM, m = t - e * MM;
+                    if (m >= P.M) continue;
+                    const int seg = emeta[e] >> 28, row = emeta[e] & 0x0FFFFFFF;
+                    float v = ebuf[(((size_t)e * 2 + 0) * 8 + 0) * MM + m];
+                    for (int qd = 1; qd < wpr; qd++) v += ebuf[(((size_t)e * 2 + 0) * 8 + qd) * MM + m];
+                    switch (oi.type) {
+                        case OP_QKV: {
+                            float *out = seg == 0 ? P.q + (size_t)m * P.attn_seg : (seg == 1 ? P.k : P.v) + (size_t)m * P.kv_seg;
+                            out[row] = v;
+                        } break;
+                        case OP_O: // TransformerBlock.java:185
+                            P.xb[(size_t)m * P.E + row] = __fadd_rn(v, __ldcg(P.x + (size_t)m * P.E + row));
+                            break;
+                        case OP_GATEUP: { // MLPBlock.java:132-141
+                            float u = ebuf[(((size_t)e * 2 + 1) * 8 + 0) * MM + m];
+                            for (int qd = 1; qd < wpr; qd++) u += ebuf[(((size_t)e * 2 + 1) * 8 + qd) * MM + m];
+                            P.h[(size_t)m * P.H + row] = __fmul_rn(silu_ref(v), u);
+                        } break;
+                        default: // OP_DOWN, TransformerBlock.java:203
+                            P.x[(size_t)m * P.E + row] = __fadd_rn(v, __ldcg(P.xb + (size_t)m * P.E + row));
+                            break;
+                    }
+                }
+            }
         }
+        MG_TRACE(4);
         if (oi.type == OP_LMHEAD) {
             // CTA-level arg-max, published as one packed 64-bit candidate per row
             if (lane == 0)
@@ -816,6 +1087,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const MegaPa
             }
         }
         op_signal(cnt);
+        MG_TRACE(5);
     }
 
     // ---- final arg-max across CTAs + device-side feedback for the resident loop ----
@@ -862,6 +1134,7 @@ static size_t uarea_bytes(const MegaParams &p, int MM) {
     const int hs = p.head_size;
     size_t att = (size_t)2 * MG_ATT_TILE * hs * 4 + (size_t)MG_MAX_GROUP * hs * 4 + (size_t)MG_ATT_TILE * MG_MAX_GROUP * 4 + 256;
     att += (size_t)(MG_CONSUMERS / hs) * MG_MAX_GROUP * hs * 4; // P.V combine buffer
+    att += (size_t)2 * hs * 4;                                  // current position's key / value row
     return (acts > att ? acts : att) + 256;
 }
 
@@ -869,7 +1142,19 @@ bool jl_mega_supported(const MegaParams &p) {
     if (p.M < 1 || p.M > MEGA_MAX_M) return false;
     if (p.head_size != 32 && p.head_size != 64 && p.head_size != 128) return false;
     if (p.heads % p.kv_heads || p.heads / p.kv_heads > MG_MAX_GROUP) return false;
-    if ((p.E % 128) || (p.H % 128) || (p.attn_seg % 128)) return false; // TMA: 16-byte aligned scale slices
+    if ((p.E % 128) || (p.H % 128) || (p.attn_seg % 128)) return false; // TMA: 16-byte aligned rows of scales
+    for (int K : {p.E, p.H, p.attn_seg}) {
+        if (K / 2 > MG_STAGE_NIB) return false;
+        int R = 16;
+        while (R > 1 && R * (K / 2) > MG_STAGE_NIB) R >>= 1;
+        if ((K / 32) % (MG_UNITS / R) || MG_UNITS / R > 8) return false; // K-ranges of the units sharing a row
+    }
+    if (p.layers * 4 + 1 > MG_MAX_OPS || p.E > 4096) return false; // lm_head rows are one warp each (K = E <= 4096)
+    if (p.grid > 0) {
+        const int G = p.grid;
+        if ((p.attn_seg + 2 * p.kv_seg + G - 1) / G + 3 > MG_EROWS || (p.H + G - 1) / G + 1 > MG_EROWS || (p.E + G - 1) / G + 1 > MG_EROWS)
+            return false;
+    }
     const int MM = p.M <= 1 ? 1 : (p.M <= 2 ? 2 : 4);
     const int nstage = MM == 1 ? 4 : 3;
     return (size_t)nstage * MG_STAGE_BYTES + uarea_bytes(p, MM) <= 225 * 1024;

@@ -11,6 +11,7 @@
 #include <chrono>
 #include <map>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 int jl_comm_allreduce_dev(jl_ctx *ctx, cudaStream_t stream, float *buf, size_t count);
@@ -59,6 +60,9 @@ struct jl_model {
     MegaLayer *mega_layers = nullptr;
     unsigned *mega_sync = nullptr, *mega_att_done = nullptr;
     unsigned long long *mega_slots = nullptr;
+    unsigned char *mega_records = nullptr;
+    int mega_l2_ahead = 1;
+    int *mega_cta_first = nullptr, *mega_op_first = nullptr;
 };
 
 #define M_CHECK(expr)                 \
@@ -259,6 +263,23 @@ extern "C" int jl_model_finalize(jl_model *m) {
             M_CHECK(dev_alloc(ctx, (void **)&m->mega_sync, jl_mega_sync_words(c.num_layers) * sizeof(unsigned)));
             M_CHECK(dev_alloc(ctx, (void **)&m->mega_att_done, (size_t)c.num_layers * MEGA_MAX_M * m->kv_heads_local * sizeof(unsigned)));
             M_CHECK(dev_alloc(ctx, (void **)&m->mega_slots, (size_t)MEGA_MAX_M * ctx->sm_count * sizeof(unsigned long long)));
+            // static schedule of the persistent kernel (one CTA per SM)
+            {
+                MegaParams shape = MegaParams();
+                shape.layers = c.num_layers, shape.E = E, shape.H = m->h_seg, shape.attn_seg = m->attn_seg, shape.kv_seg = m->kv_seg;
+                shape.vocab = c.vocab_size;
+                shape.lm_w = (const uint8_t *)head.data, shape.lm_s = head.scales;
+                std::vector<unsigned char> records;
+                std::vector<int> cta_first, op_first;
+                jl_mega_build_table(shape, ml.data(), ctx->sm_count, records, cta_first, op_first);
+                M_CHECK(dev_alloc(ctx, (void **)&m->mega_records, records.size()));
+                if (const char *e = getenv("JL_MEGA_L2_AHEAD")) m->mega_l2_ahead = atoi(e);
+                M_CHECK(dev_alloc(ctx, (void **)&m->mega_cta_first, cta_first.size() * sizeof(int)));
+                M_CHECK(dev_alloc(ctx, (void **)&m->mega_op_first, op_first.size() * sizeof(int)));
+                JL_CUDA_CHECK(ctx, cudaMemcpy(m->mega_records, records.data(), records.size(), cudaMemcpyHostToDevice));
+                JL_CUDA_CHECK(ctx, cudaMemcpy(m->mega_cta_first, cta_first.data(), cta_first.size() * sizeof(int), cudaMemcpyHostToDevice));
+                JL_CUDA_CHECK(ctx, cudaMemcpy(m->mega_op_first, op_first.data(), op_first.size() * sizeof(int), cudaMemcpyHostToDevice));
+            }
             m->mega_ok = true;
         }
     }
@@ -278,7 +299,8 @@ extern "C" int jl_model_free(jl_model *m) {
         if (p) cudaFree(p);
     void *bufs[] = {m->rope, m->page_table_dev, m->x, m->xb, m->q, m->k, m->v, m->att, m->hbuf, m->partial, m->logits,
                     m->last_hidden, m->attn_ws, m->d_tokens, m->d_positions, m->d_sessions, m->d_next, m->d_hist, m->d_counter,
-                    m->argmax_scratch, m->mega_layers, m->mega_sync, m->mega_att_done, m->mega_slots};
+                    m->argmax_scratch, m->mega_layers, m->mega_sync, m->mega_att_done, m->mega_slots, m->mega_records, m->mega_cta_first,
+                    m->mega_op_first};
     for (void *p : bufs)
         if (p) cudaFree(p);
     if (m->h_pinned) cudaFreeHost(m->h_pinned);
@@ -674,6 +696,9 @@ static bool fill_mega(jl_model *m, int n, int max_pos, bool resident, MegaParams
     p.tokens = m->d_tokens, p.positions = m->d_positions, p.next = m->d_next, p.sessions = m->d_sessions;
     p.hist = m->d_hist, p.counter = m->d_counter, p.hist_cap = m->hist_cap, p.resident = resident ? 1 : 0;
     p.sync = m->mega_sync, p.argmax_slots = m->mega_slots, p.att_done = m->mega_att_done;
+    if (const char *e = getenv("JL_MEGA_DBG")) p.dbg = atoi(e);
+    p.grid = m->ctx->sm_count;
+    p.records = m->mega_records, p.l2_ahead = m->mega_l2_ahead, p.cta_first = m->mega_cta_first, p.op_first = m->mega_op_first;
     // one split per 64 positions, bounded by the CTAs available for (row, kv head) tasks
     int s = (max_pos + 1 + 63) / 64;
     const int cap = m->ctx->sm_count / (n * m->kv_heads_local);
@@ -809,6 +834,34 @@ extern "C" int jl_model_decode_resident(jl_model *m, int session, int32_t first_
     m->last_total_ms = ms;
     m->last_gemv_ms = gemv;
     return JL_OK;
+}
+
+extern "C" int jl_model_debug_trace(jl_model *m, int session, int32_t token, int position, int64_t *out, int64_t out_words) {
+    if (!m || !m->finalized || !out || session < 0 || session >= m->cfg.max_sessions) return JL_ERR_INVALID;
+    jl_ctx *ctx = m->ctx;
+    JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    MegaParams mp;
+    if (!use_mega(m) || !fill_mega(m, 1, position, false, mp)) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "megakernel not active");
+    const size_t words = (size_t)3 * (m->cfg.num_layers * 4 + 1) * 8 + 1024;
+    if ((size_t)out_words < words) return jl_set_error(ctx, JL_ERR_INVALID, "trace buffer too small (%zu words needed)", words);
+    M_CHECK(ensure_pages(m, session, position, position));
+    long long *dtr = nullptr;
+    M_CHECK(dev_alloc(ctx, (void **)&dtr, words * 8));
+    JL_CUDA_CHECK(ctx, cudaMemsetAsync(dtr, 0, words * 8, m->stream));
+    int32_t *hp = m->h_pinned;
+    hp[0] = token, hp[m->maxB] = position, hp[2 * m->maxB] = session;
+    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_tokens, hp, 4, cudaMemcpyHostToDevice, m->stream));
+    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_positions, hp + m->maxB, 4, cudaMemcpyHostToDevice, m->stream));
+    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_sessions, hp + 2 * m->maxB, 4, cudaMemcpyHostToDevice, m->stream));
+    mp.trace = dtr;
+    int rc = jl_launch_mega(ctx, m->stream, mp);
+    if (rc == JL_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, dtr, words * 8, cudaMemcpyDeviceToHost, m->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+        if (e != cudaSuccess) rc = jl_set_error(ctx, JL_ERR_CUDA, "trace copy failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(dtr);
+    return rc;
 }
 
 extern "C" int jl_model_decode_mode(jl_model *m, int n) {

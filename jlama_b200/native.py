@@ -88,6 +88,7 @@ SIGNATURES = {
     "jl_model_read_kv": (_i, [_vp, _i, _i, _i, _i, _vp]),
     "jl_model_read_hidden": (_i, [_vp, _i, _vp]),
     "jl_model_decode_mode": (_i, [_vp, _i]),
+    "jl_model_debug_trace": (_i, [_vp, _i, C.c_int32, _i, _vp, _i64]),
     "jl_model_weight_bytes": (_i64, [_vp]),
     "jl_model_last_timing": (_i, [_vp, C.POINTER(_d), C.POINTER(_d)]),
     "jl_comm_unique_id": (_i, [_vp, _vp]),
