@@ -186,7 +186,7 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
-    ap.add_argument("--no-mega", action="store_true", help="kernel-per-op decode instead of the persistent megakernel")
+    ap.add_argument("--mega", action="store_true", help="decode with the persistent megakernel instead of the CUDA-graph path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -225,7 +225,7 @@ def main():
     n_total = args.prompt + 2 * (args.warmup + args.steps) + 64
     t0 = time.time()
     model = LlamaModel(ctx, cfg, weights, max_context=min(cfg["ctx"], max(512, n_total)), tp_rank=rank, tp_size=world,
-                       flags=native.MODEL_NO_MEGA if args.no_mega else 0)
+                       flags=native.MODEL_MEGA if args.mega else 0)
     log("[bench] rank %d: weights uploaded in %.1fs (%.3f GB streamed per token on this rank)" % (
         rank, time.time() - t0, model.weight_bytes() / 1e9))
 
@@ -316,7 +316,7 @@ def main():
         # kernel-per-op path: eager, event-timed GEMV launches (rank 0 shard; same on every rank)
         model.close()
         model = LlamaModel(ctx, cfg, weights, max_context=min(cfg["ctx"], max(512, n_total)), tp_rank=rank, tp_size=world,
-                           flags=native.MODEL_NO_GRAPH | native.MODEL_NO_PDL | native.MODEL_NO_MEGA)
+                           flags=native.MODEL_NO_GRAPH)
         model.reset_session(0)
         model.batch_forward(prompt, 0)
         f2, _ = model.sample(want_logits=False)

@@ -10,6 +10,7 @@
 // HBM/L2-bound: K/V rows are read with 128-bit coalesced loads (one head row = hs*4 bytes
 // contiguous inside a page row of kv_len floats), reductions are warp shuffles.
 #include "jl_common.cuh"
+#include "jl_attn_task.cuh"
 
 #define ATT_THREADS 128
 
@@ -292,6 +293,65 @@ int jl_launch_paged_attention(jl_ctx *ctx, cudaStream_t s, const AttnParams &p, 
         case 32: return launch_att<32>(ctx, s, p, use_pdl);
         case 64: return launch_att<64>(ctx, s, p, use_pdl);
         case 128: return launch_att<128>(ctx, s, p, use_pdl);
+    }
+    return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "attention: head_size %d (supported: 32, 64, 128)", p.head_size);
+}
+
+// ---- fused decode attention: RoPE + KV append + scores + softmax + P.V in ONE kernel -------------------------------------
+// For decode steps every row is a different session, so a (row, kv head, split) task can append the row's own
+// K/V and attend in the same kernel (no separate rope_kv_append launch).  grid = (kv_heads, rows, splits).
+#define FDA_THREADS 256
+template <int HS>
+__global__ void __launch_bounds__(FDA_THREADS) fused_decode_attention_kernel(const AttnTask t, const int layer,
+                                                                              unsigned *done_cnt) {
+    pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ __align__(16) unsigned char fda_smem[];
+    __shared__ int s_last;
+    const int kvh = blockIdx.x, m = blockIdx.y, split = blockIdx.z;
+    attention_task<HS, FDA_THREADS>(t, layer, m, kvh, split, fda_smem);
+    if (t.splits > 1) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            unsigned *c = &done_cnt[m * t.kv_heads + kvh];
+            const unsigned old = atomicAdd(c, 1u);
+            s_last = (old == (unsigned)t.splits - 1);
+            if (s_last) *c = 0; // ready for the next launch
+            __threadfence();
+        }
+        __syncthreads();
+        if (s_last) attention_merge<HS, FDA_THREADS>(t, m, kvh);
+    }
+}
+
+template <int HS>
+static int launch_fda(jl_ctx *ctx, cudaStream_t s, const AttnTask &t, int layer, int rows, unsigned *done_cnt, bool pdl) {
+    const size_t smem = attention_task_smem<HS, FDA_THREADS>();
+    static bool configured = false;
+    if (!configured && smem > 40 * 1024) {
+        JL_CUDA_CHECK(ctx, cudaFuncSetAttribute(fused_decode_attention_kernel<HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    JL_CUDA_CHECK(ctx, jl_launch_kernel(fused_decode_attention_kernel<HS>, dim3(t.kv_heads, rows, t.splits), dim3(FDA_THREADS), smem, s,
+                                        pdl, t, layer, done_cnt));
+    ctx->launches++;
+    return JL_OK;
+}
+
+int jl_launch_fused_decode_attention(jl_ctx *ctx, cudaStream_t s, const AttnParams &p, unsigned *done_cnt, bool use_pdl) {
+    if (p.rows <= 0) return JL_OK;
+    if (p.heads % p.kv_heads || p.heads / p.kv_heads > MG_MAX_GROUP)
+        return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "attention: head group size %d/%d unsupported", p.heads, p.kv_heads);
+    AttnTask t;
+    t.heads = p.heads, t.kv_heads = p.kv_heads, t.head_size = p.head_size, t.attn_seg = p.q_ld, t.kv_seg = p.kv_ld;
+    t.kv_head0_global = p.kv_head0_global, t.splits = p.splits, t.attn_scale = p.scale;
+    t.q = p.q, t.k = p.k, t.v = p.v, t.att = p.out, t.attn_ws = p.ws, t.rope = p.rope, t.kv = p.kv;
+    t.sessions = p.sessions, t.positions = p.positions;
+    switch (p.head_size) {
+        case 32: return launch_fda<32>(ctx, s, t, p.layer, p.rows, done_cnt, use_pdl);
+        case 64: return launch_fda<64>(ctx, s, t, p.layer, p.rows, done_cnt, use_pdl);
+        case 128: return launch_fda<128>(ctx, s, t, p.layer, p.rows, done_cnt, use_pdl);
     }
     return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "attention: head_size %d (supported: 32, 64, 128)", p.head_size);
 }

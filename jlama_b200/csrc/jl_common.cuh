@@ -169,6 +169,9 @@ struct AttnParams {
 int jl_launch_rope_kv_append(jl_ctx *ctx, cudaStream_t s, const AttnParams &p, float *q_inplace, bool use_pdl);
 // Causal attention of each row against positions [0, pos] of its session (CausalSelfAttention.java:314-356).
 int jl_launch_paged_attention(jl_ctx *ctx, cudaStream_t s, const AttnParams &p, int max_pos, bool use_pdl);
+// Decode steps (every row a different session): RoPE + KV append + attention fused in one kernel; q/k/v are the raw
+// projections.  done_cnt: [rows * kv_heads] zero-initialised split-arrival counters (self-resetting).
+int jl_launch_fused_decode_attention(jl_ctx *ctx, cudaStream_t s, const AttnParams &p, unsigned *done_cnt, bool use_pdl);
 
 // ---------------------------------------------------------------------------------------------
 // Larger-M GEMM paths for prefill (jl_gemm.cu)

@@ -16,6 +16,7 @@
 // programmatic dependent launch the weight stream of kernel N+1 is already in flight while
 // kernel N drains (the activations are the only true dependency).
 #include "jl_common.cuh"
+#include <stdlib.h>
 
 #define GEMV_THREADS 256
 #define GEMV_WARPS 8
@@ -568,6 +569,14 @@ int jl_launch_gemv(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int pr
     const int rows = p.total_rows;
     // grid: a multiple of the SM count; every warp gets >= 1 row when possible
     int per_sm = rows >= ctx->sm_count * GEMV_WARPS * 4 ? 3 : (rows >= ctx->sm_count * GEMV_WARPS * 2 ? 2 : 1);
+    {
+        static int forced = -1;
+        if (forced < 0) {
+            const char *e = getenv("JL_GEMV_PER_SM");
+            forced = e ? atoi(e) : 0;
+        }
+        if (forced > 0 && per_sm > forced) per_sm = forced;
+    }
     int grid = ctx->sm_count * per_sm;
     int max_grid = (rows + GEMV_WARPS - 1) / GEMV_WARPS;
     if (grid > max_grid) grid = max_grid;

@@ -58,11 +58,9 @@ struct jl_model {
     // persistent megakernel
     bool mega_ok = false;
     MegaLayer *mega_layers = nullptr;
-    unsigned *mega_sync = nullptr, *mega_att_done = nullptr;
+    unsigned *mega_sync = nullptr, *mega_att_done = nullptr, *fda_done = nullptr;
     unsigned long long *mega_slots = nullptr;
-    unsigned char *mega_records = nullptr;
     int mega_l2_ahead = 1;
-    int *mega_cta_first = nullptr, *mega_op_first = nullptr;
 };
 
 #define M_CHECK(expr)                 \
@@ -71,9 +69,9 @@ struct jl_model {
         if (_rc != JL_OK) return _rc; \
     } while (0)
 
-static bool use_pdl(const jl_model *m) { return !(m->cfg.flags & JL_MODEL_NO_PDL); }
+static bool use_pdl(const jl_model *m) { return (m->cfg.flags & JL_MODEL_PDL) && !(m->cfg.flags & JL_MODEL_NO_PDL); }
 static bool use_graph(const jl_model *m) { return !(m->cfg.flags & JL_MODEL_NO_GRAPH); }
-static bool use_mega(const jl_model *m) { return m->mega_ok && !(m->cfg.flags & JL_MODEL_NO_MEGA); }
+static bool use_mega(const jl_model *m) { return m->mega_ok && (m->cfg.flags & JL_MODEL_MEGA) && !(m->cfg.flags & JL_MODEL_NO_MEGA); }
 
 extern "C" int jl_model_create(jl_ctx *ctx, const jl_model_config *cfg, jl_model **out) {
     if (!ctx || !cfg || !out) return JL_ERR_INVALID;
@@ -228,6 +226,8 @@ extern "C" int jl_model_finalize(jl_model *m) {
     M_CHECK(dev_alloc(ctx, (void **)&m->d_hist, (size_t)m->hist_cap * 4));
     M_CHECK(dev_alloc(ctx, (void **)&m->d_counter, 4));
     M_CHECK(dev_alloc(ctx, &m->argmax_scratch, jl_argmax_scratch_bytes(c.max_sessions)));
+    M_CHECK(dev_alloc(ctx, (void **)&m->fda_done, (size_t)m->maxB * m->kv_heads_local * sizeof(unsigned)));
+    JL_CUDA_CHECK(ctx, cudaMemset(m->fda_done, 0, (size_t)m->maxB * m->kv_heads_local * sizeof(unsigned)));
     JL_CUDA_CHECK(ctx, cudaMallocHost((void **)&m->h_pinned, B * 4 * 4));
     JL_CUDA_CHECK(ctx, cudaEventCreate(&m->ev_begin));
     JL_CUDA_CHECK(ctx, cudaEventCreate(&m->ev_end));
@@ -263,23 +263,7 @@ extern "C" int jl_model_finalize(jl_model *m) {
             M_CHECK(dev_alloc(ctx, (void **)&m->mega_sync, jl_mega_sync_words(c.num_layers) * sizeof(unsigned)));
             M_CHECK(dev_alloc(ctx, (void **)&m->mega_att_done, (size_t)c.num_layers * MEGA_MAX_M * m->kv_heads_local * sizeof(unsigned)));
             M_CHECK(dev_alloc(ctx, (void **)&m->mega_slots, (size_t)MEGA_MAX_M * ctx->sm_count * sizeof(unsigned long long)));
-            // static schedule of the persistent kernel (one CTA per SM)
-            {
-                MegaParams shape = MegaParams();
-                shape.layers = c.num_layers, shape.E = E, shape.H = m->h_seg, shape.attn_seg = m->attn_seg, shape.kv_seg = m->kv_seg;
-                shape.vocab = c.vocab_size;
-                shape.lm_w = (const uint8_t *)head.data, shape.lm_s = head.scales;
-                std::vector<unsigned char> records;
-                std::vector<int> cta_first, op_first;
-                jl_mega_build_table(shape, ml.data(), ctx->sm_count, records, cta_first, op_first);
-                M_CHECK(dev_alloc(ctx, (void **)&m->mega_records, records.size()));
-                if (const char *e = getenv("JL_MEGA_L2_AHEAD")) m->mega_l2_ahead = atoi(e);
-                M_CHECK(dev_alloc(ctx, (void **)&m->mega_cta_first, cta_first.size() * sizeof(int)));
-                M_CHECK(dev_alloc(ctx, (void **)&m->mega_op_first, op_first.size() * sizeof(int)));
-                JL_CUDA_CHECK(ctx, cudaMemcpy(m->mega_records, records.data(), records.size(), cudaMemcpyHostToDevice));
-                JL_CUDA_CHECK(ctx, cudaMemcpy(m->mega_cta_first, cta_first.data(), cta_first.size() * sizeof(int), cudaMemcpyHostToDevice));
-                JL_CUDA_CHECK(ctx, cudaMemcpy(m->mega_op_first, op_first.data(), op_first.size() * sizeof(int), cudaMemcpyHostToDevice));
-            }
+            if (const char *e = getenv("JL_MEGA_L2_AHEAD")) m->mega_l2_ahead = atoi(e);
             m->mega_ok = true;
         }
     }
@@ -299,8 +283,7 @@ extern "C" int jl_model_free(jl_model *m) {
         if (p) cudaFree(p);
     void *bufs[] = {m->rope, m->page_table_dev, m->x, m->xb, m->q, m->k, m->v, m->att, m->hbuf, m->partial, m->logits,
                     m->last_hidden, m->attn_ws, m->d_tokens, m->d_positions, m->d_sessions, m->d_next, m->d_hist, m->d_counter,
-                    m->argmax_scratch, m->mega_layers, m->mega_sync, m->mega_att_done, m->mega_slots, m->mega_records, m->mega_cta_first,
-                    m->mega_op_first};
+                    m->argmax_scratch, m->fda_done, m->mega_layers, m->mega_sync, m->mega_att_done, m->mega_slots};
     for (void *p : bufs)
         if (p) cudaFree(p);
     if (m->h_pinned) cudaFreeHost(m->h_pinned);
@@ -387,7 +370,7 @@ static void set_w(GemvParams &p, int seg, const DevTensor &t, float *out, int ou
 }
 
 // AbstractModel.forward (:314-329) over M rows whose tokens/positions/sessions are already on the device.
-static int forward_rows(jl_model *m, int M, int max_pos, int splits, bool timed) {
+static int forward_rows(jl_model *m, int M, int max_pos, int splits, bool timed, bool distinct_sessions = false) {
     jl_ctx *ctx = m->ctx;
     const jl_model_config &c = m->cfg;
     const int E = c.embedding_length, hs = c.head_size;
@@ -441,8 +424,13 @@ static int forward_rows(jl_model *m, int M, int max_pos, int splits, bool timed)
         ap.scale = (float)(1.0 / sqrt((double)hs)); // CausalSelfAttention.java:134
         ap.ws = m->attn_ws;
         ap.splits = splits;
-        M_CHECK(jl_launch_rope_kv_append(ctx, m->stream, ap, m->q, pdl));
-        M_CHECK(jl_launch_paged_attention(ctx, m->stream, ap, max_pos, pdl));
+        if (distinct_sessions) {
+            // decode: one fused kernel (RoPE + KV append + attention); `splits` = about one per 64 positions
+            M_CHECK(jl_launch_fused_decode_attention(ctx, m->stream, ap, m->fda_done, pdl));
+        } else {
+            M_CHECK(jl_launch_rope_kv_append(ctx, m->stream, ap, m->q, pdl));
+            M_CHECK(jl_launch_paged_attention(ctx, m->stream, ap, max_pos, pdl));
+        }
         // ---- o_proj (+ reducer) + residual (CausalSelfAttention.java:363-378, TransformerBlock.java:185) ----
         {
             GemvParams p = {};
@@ -665,7 +653,7 @@ __global__ void advance_kernel(int32_t *tokens, int32_t *positions, const int32_
 
 static int decode_body(jl_model *m, int n, int max_pos, int splits, bool resident, bool timed) {
     jl_ctx *ctx = m->ctx;
-    M_CHECK(forward_rows(m, n, max_pos, splits, timed));
+    M_CHECK(forward_rows(m, n, max_pos, splits, timed, true));
     M_CHECK(sample_rows(m, m->x, n, timed));
     if (resident) {
         JL_CUDA_CHECK(ctx, jl_launch_kernel(advance_kernel, dim3(1), dim3(256), 0, m->stream, false, m->d_tokens, m->d_positions,
@@ -698,7 +686,7 @@ static bool fill_mega(jl_model *m, int n, int max_pos, bool resident, MegaParams
     p.sync = m->mega_sync, p.argmax_slots = m->mega_slots, p.att_done = m->mega_att_done;
     if (const char *e = getenv("JL_MEGA_DBG")) p.dbg = atoi(e);
     p.grid = m->ctx->sm_count;
-    p.records = m->mega_records, p.l2_ahead = m->mega_l2_ahead, p.cta_first = m->mega_cta_first, p.op_first = m->mega_op_first;
+    p.l2_ahead = m->mega_l2_ahead;
     // one split per 64 positions, bounded by the CTAs available for (row, kv head) tasks
     int s = (max_pos + 1 + 63) / 64;
     const int cap = m->ctx->sm_count / (n * m->kv_heads_local);
@@ -716,7 +704,18 @@ static int run_decode(jl_model *m, int n, int max_pos, bool resident) {
         MegaParams mp;
         if (fill_mega(m, n, max_pos, resident, mp)) return jl_launch_mega(ctx, m->stream, mp);
     }
-    const int splits = pick_splits(m, max_pos, n);
+    // fused decode attention: one split per 64 positions, bucketed so that few graphs are captured
+    int splits = (max_pos + 1 + 63) / 64;
+    {
+        static const int buckets[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32};
+        int b = 32;
+        for (int v : buckets)
+            if (v >= splits) {
+                b = v;
+                break;
+            }
+        splits = b > m->max_splits ? m->max_splits : b;
+    }
     if (!use_graph(m)) {
         m->ev_used = 0;
         int rc = decode_body(m, n, max_pos, splits, resident, true);
@@ -842,7 +841,7 @@ extern "C" int jl_model_debug_trace(jl_model *m, int session, int32_t token, int
     JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
     MegaParams mp;
     if (!use_mega(m) || !fill_mega(m, 1, position, false, mp)) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "megakernel not active");
-    const size_t words = (size_t)3 * (m->cfg.num_layers * 4 + 1) * 8 + 1024;
+    const size_t words = (size_t)3 * (m->cfg.num_layers * 4 + 1) * 8;
     if ((size_t)out_words < words) return jl_set_error(ctx, JL_ERR_INVALID, "trace buffer too small (%zu words needed)", words);
     M_CHECK(ensure_pages(m, session, position, position));
     long long *dtr = nullptr;

@@ -114,8 +114,8 @@ def test_graph_eager_and_resident_decode_agree_bitwise(cuda_ctx, oracle):
     w = synth.make_weights(cfg)
     prompt = synth.random_prompt(cfg, 11)
     outs = []
-    NM = native.MODEL_NO_MEGA
-    for flags in (NM, NM | native.MODEL_NO_PDL, NM | native.MODEL_NO_GRAPH | native.MODEL_NO_PDL):
+    NM = 0
+    for flags in (NM, native.MODEL_PDL, native.MODEL_NO_GRAPH):
         m = LlamaModel(cuda_ctx, cfg, w, flags=flags)
         assert m.decode_mode() == (0 if flags & native.MODEL_NO_GRAPH else 1)
         t, l = m.generate(prompt, 10, want_logits=True)
@@ -141,8 +141,8 @@ def test_megakernel_matches_per_op_kernels(cuda_ctx, oracle, name):
     cfg = synth.get_config(name)
     w = synth.make_weights(cfg)
     prompt = synth.random_prompt(cfg, 21)
-    mega = LlamaModel(cuda_ctx, cfg, w, max_sessions=4)
-    ref = LlamaModel(cuda_ctx, cfg, w, max_sessions=4, flags=native.MODEL_NO_MEGA)
+    mega = LlamaModel(cuda_ctx, cfg, w, max_sessions=4, flags=native.MODEL_MEGA)
+    ref = LlamaModel(cuda_ctx, cfg, w, max_sessions=4)
     assert mega.decode_mode(1) == 2 and mega.decode_mode(3) == 2 and ref.decode_mode(1) == 1
     t1, l1 = mega.generate(prompt, 40, want_logits=True)
     t2, l2 = ref.generate(prompt, 40, want_logits=True)
@@ -179,8 +179,8 @@ def test_megakernel_matches_per_op_kernels(cuda_ctx, oracle, name):
 
 def test_megakernel_long_context_splits(cuda_ctx, oracle):
     """context long enough for several attention splits per (row, kv head) inside the megakernel"""
-    from jlama_b200 import synth
-    cfg, w, gm, om = _models(cuda_ctx, oracle, "tiny", max_batch=64)
+    from jlama_b200 import native, synth
+    cfg, w, gm, om = _models(cuda_ctx, oracle, "tiny", max_batch=64, flags=native.MODEL_MEGA)
     prompt = synth.random_prompt(cfg, 150)
     gt, gl = gm.generate(prompt, 12, want_logits=True)
     om.reset()

@@ -11,7 +11,12 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 cfg = synth.get_config(name)
 w = synth.make_weights(cfg, mode="direct")
 ctx = native.Context(0)
-m = LlamaModel(ctx, cfg, w, max_context=512)
+flags = native.MODEL_MEGA
+if os.environ.get('JL_NO_MEGA'):
+    flags = 0
+if os.environ.get('JL_PDL'):
+    flags |= native.MODEL_PDL
+m = LlamaModel(ctx, cfg, w, max_context=512, flags=flags)
 prompt = synth.random_prompt(cfg, 32)
 m.reset_session(0)
 m.batch_forward(prompt, 0)

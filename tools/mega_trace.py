@@ -14,7 +14,7 @@ def main():
     cfg = synth.get_config(name)
     w = synth.make_weights(cfg, mode="direct")
     ctx = native.Context(0)
-    m = LlamaModel(ctx, cfg, w, max_context=512)
+    m = LlamaModel(ctx, cfg, w, max_context=512, flags=native.MODEL_MEGA)
     prompt = synth.random_prompt(cfg, 32)
     m.reset_session(0)
     m.batch_forward(prompt, 0)
@@ -22,15 +22,8 @@ def main():
     if not os.environ.get('JL_MEGA_DBG'):
         m.decode_resident(first, 32, 8)
     n_ops = cfg["layers"] * 4 + 1
-    raw = np.zeros(3 * n_ops * 8 + 1024, dtype=np.int64)
-    ctx.check(ctx.lib.jl_model_debug_trace(m.h, 0, int(first), 40, native.ptr(raw), raw.size))
-    buf = raw[:3 * n_ops * 8].reshape(3, n_ops, 8)
-    st = raw[3 * n_ops * 8:].reshape(128, 8).astype(np.float64) / 1965.0
-    base = buf[0, 0, 0] / 1965.0
-    if os.environ.get('JL_TRACE_STAGES'):
-        print('stage: wait_begin wait_end (us, cta0)')
-        for i in range(int(os.environ['JL_TRACE_STAGES'])):
-            print('  %3d  t=%8.2f  wait %.2f desc %.2f math %.2f arrive %.2f wsum %.2f' % (i, st[i, 0] - base, st[i, 1] - st[i, 0], st[i, 2] - st[i, 1], st[i, 3] - st[i, 2], st[i, 4] - st[i, 3], st[i, 5] - st[i, 4]))
+    buf = np.zeros((3, n_ops, 8), dtype=np.int64)
+    ctx.check(ctx.lib.jl_model_debug_trace(m.h, 0, int(first), 40, native.ptr(buf), buf.size))
     ghz = 1.965
     names = ["qkv", "o", "gateup", "down"]
     for c, cname in enumerate(("cta0", "ctaMid", "ctaLast")):
