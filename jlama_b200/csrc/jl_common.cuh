@@ -176,9 +176,9 @@ int jl_launch_fused_decode_attention(jl_ctx *ctx, cudaStream_t s, const AttnPara
 // ---------------------------------------------------------------------------------------------
 // Larger-M GEMM paths for prefill (jl_gemm.cu)
 // ---------------------------------------------------------------------------------------------
-// C[M,N] (+epilogue) = A[M,K] * W[N,K]^T for M > GEMV_MAX_M.  exact integer (dp4a) SIMT path for
-// Q8-activation x Q4, FMA path for f32 activations.
-int jl_launch_gemm_simt(jl_ctx *ctx, cudaStream_t s, const GemvParams &p, int prologue_kind, int epilogue);
+// tcgen05 tensor-core GEMM (jl_gemm_tc.cu): C[T, out_col_off+n] (+residual) = A_bf16[T,K] * dequant(W[n, w_col_off+k])^T
+int jl_launch_gemm_tc(jl_ctx *ctx, cudaStream_t stream, const uint16_t *a_bf16, int lda, int T, const DevTensor &W, int n_rows,
+                      int w_col_off, int K, float *out, int ldc, int out_col_off, const float *residual, int res_ld);
 
 // ---------------------------------------------------------------------------------------------
 // helpers

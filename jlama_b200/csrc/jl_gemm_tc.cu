@@ -1,0 +1,249 @@
+// Prefill GEMM on the 5th-generation tensor cores:  C[T, N] (+residual) = A[T, K] * W[N, K]^T
+//
+// The prefill counterpart of jl_gemv.cu for M = T tokens >= 16 (AbstractModel.batchForward chunks of up to 256
+// tokens, core/model/AbstractModel.java:295-312).  Replaces the reference's GemmerF32Q4 / GemmerI8Q4 tiles
+// (PanamaTensorOperations.java:148-1044, vector_simd.c:261-964) and the WebGPU gemm_q4.wgsl / gemm_i8q4.wgsl.
+//
+//   * tcgen05.mma kind::f16 (BF16 x BF16 -> F32) issued by one elected thread, accumulator in TMEM;
+//   * the WEIGHT tile is the UMMA "A" operand (M = 128 weight rows), the token tile the "B" operand (N = 128
+//     tokens), so the instruction's M is always full and D comes out as [weight row][token];
+//   * per-block dequantisation (nibble - 8) * f32 scale -> BF16 is fused into the shared-memory fill of the
+//     weight tile: four producer warps read the packed Q4 blocks with 128-bit loads straight from HBM/L2
+//     and write the 128-byte-swizzled K-major tile the tensor core consumes; the activation tile (already BF16
+//     in HBM) is copied into the same swizzled layout;
+//   * 4-stage mbarrier pipeline: producers -> full[s] -> MMA warp -> tcgen05.commit -> empty[s];
+//   * epilogue: tcgen05.ld (32 lanes x 16 columns per warp) -> optional residual add -> coalesced f32 stores.
+//
+// Numerics: operands are rounded to BF16 (8-bit mantissa), accumulation is F32.  This is the "F32/BF16 x Q4"
+// flavour of the reference (tolerance class 1e-2 rel on logits); the exact-integer Q8 x Q4 arithmetic stays
+// available through the GEMV path (jl_model: prefill_tensor_core = 0).
+#include "jl_common.cuh"
+
+#define TC_THREADS 160 // warps 0-3: producers + epilogue, warp 4: TMEM allocator + MMA issuer
+#define TC_BM 128      // weight rows per CTA (UMMA M)
+#define TC_BN 128      // tokens per CTA (UMMA N)
+#define TC_BK 64       // K per pipeline stage: 64 bf16 = one 128-byte swizzle atom
+#define TC_STAGES 4
+#define TC_TILE_BYTES (TC_BM * TC_BK * 2) // 16 KB per operand tile
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(tc_smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (tcgen05): rows are 128 bytes, 8-row groups are 1024 bytes
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address, 16-byte units
+    d |= (uint64_t)0 << 16;                       // leading byte offset: unused for swizzled K-major
+    d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                       // layout type: SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = 128
+__device__ __forceinline__ uint32_t tc_instr_desc() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *(uint32_t *)&v;
+}
+
+struct TcParams {
+    const uint16_t *a; // activations bf16 [T, lda]
+    int lda, T;
+    const uint8_t *w;  // Q4 nibbles, row pitch K_total/2
+    const float *ws;   // scales, row pitch K_total/32
+    int ldw;           // K_total (elements)
+    int w_col_off;     // first weight column (multiple of 64)
+    int K;             // reduction length (multiple of 64)
+    int N;             // weight rows handled (multiple of 128)
+    float *out;        // [T, ldc]
+    int ldc, out_col_off;
+    const float *residual; // nullable [T, res_ld]
+    int res_ld;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_q4_tc_kernel(const TcParams p) {
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    unsigned char *wtile = tc_smem;                                   // [STAGES][16 KB] weight tiles (UMMA A)
+    unsigned char *atile = tc_smem + TC_STAGES * TC_TILE_BYTES;       // [STAGES][16 KB] token tiles (UMMA B)
+    __shared__ uint64_t full[TC_STAGES], empty[TC_STAGES], tmem_full;
+    __shared__ uint32_t tmem_base_sh;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n0 = blockIdx.x * TC_BM;  // first weight row of this CTA
+    const int t0 = blockIdx.y * TC_BN;  // first token of this CTA
+    const int nk = p.K / TC_BK;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; s++) {
+            tc_mbar_init(&full[s], 4);  // one arrival per producer warp
+            tc_mbar_init(&empty[s], 1); // tcgen05.commit
+        }
+        tc_mbar_init(&tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) { // TMEM: 128 columns x 128 lanes of f32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_base_sh)), "n"(TC_BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_sh;
+
+    if (warp < 4) {
+        // ===== producers: thread r fills row r of both tiles (128 bytes each, 16-byte chunks XOR-swizzled by r & 7) =====
+        const int r = tid; // 0..127
+        const size_t wrow = (size_t)(n0 + r);
+        const uint8_t *wq = p.w + wrow * (size_t)(p.ldw / 2) + p.w_col_off / 2;
+        const float *wsc = p.ws + wrow * (size_t)(p.ldw / 32) + p.w_col_off / 32;
+        const bool tok_ok = (t0 + r) < p.T;
+        const uint16_t *arow = p.a + (size_t)(tok_ok ? t0 + r : 0) * p.lda;
+        for (int kc = 0; kc < nk; kc++) {
+            const int s = kc % TC_STAGES, use = kc / TC_STAGES;
+            // issue the global loads first, then wait for the slot
+            const uint4 q0 = ldg_nc_u4(wq + (size_t)kc * 32), q1 = ldg_nc_u4(wq + (size_t)kc * 32 + 16);
+            const float s0 = ldg_nc_f32(wsc + kc * 2), s1 = ldg_nc_f32(wsc + kc * 2 + 1);
+            uint4 av[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++)
+                av[c] = tok_ok ? *(const uint4 *)(arow + (size_t)kc * TC_BK + c * 8) : make_uint4(0, 0, 0, 0);
+            tc_mbar_wait(&empty[s], (use & 1) ^ 1);
+            unsigned char *wdst = wtile + (size_t)s * TC_TILE_BYTES + (size_t)r * 128;
+            unsigned char *adst = atile + (size_t)s * TC_TILE_BYTES + (size_t)r * 128;
+            // dequantise: block = 16 bytes, element j = low nibble of byte j, element j+16 = high nibble of byte j
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                const uint4 q = b ? q1 : q0;
+                const float sc = b ? s1 : s0;
+                const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+                float lo[16], hi[16];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        const int byte = (qw[i] >> (8 * t)) & 0xFF;
+                        lo[i * 4 + t] = __fmul_rn((float)((byte & 0x0F) - 8), sc);
+                        hi[i * 4 + t] = __fmul_rn((float)((byte >> 4) - 8), sc);
+                    }
+                // chunks: b*4 + 0,1 = low-nibble elements 0..15; b*4 + 2,3 = high-nibble elements 16..31
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const float *src = c < 2 ? lo + c * 8 : hi + (c - 2) * 8;
+                    uint4 o;
+                    o.x = pack_bf16x2(src[0], src[1]);
+                    o.y = pack_bf16x2(src[2], src[3]);
+                    o.z = pack_bf16x2(src[4], src[5]);
+                    o.w = pack_bf16x2(src[6], src[7]);
+                    const int chunk = b * 4 + c;
+                    *(uint4 *)(wdst + ((chunk ^ (r & 7)) * 16)) = o;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 8; c++) *(uint4 *)(adst + ((c ^ (r & 7)) * 16)) = av[c];
+            // make the generic-proxy writes visible to the tensor core (async proxy), then signal
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(&full[s]);
+        }
+        // ===== epilogue: warp w owns TMEM lanes 32w..32w+31 = weight rows n0 + 32w + lane =====
+        tc_mbar_wait(&tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int col_out = p.out_col_off + n0 + warp * 32 + lane;
+        for (int c0 = 0; c0 < TC_BN; c0 += 16) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                  "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int tok = t0 + c0 + i;
+                if (tok < p.T) {
+                    float x = __uint_as_float(v[i]);
+                    if (p.residual) x = __fadd_rn(x, p.residual[(size_t)tok * p.res_ld + (n0 + warp * 32 + lane)]);
+                    p.out[(size_t)tok * p.ldc + col_out] = x;
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else {
+        // ===== MMA issuer (one elected lane of warp 4) =====
+        const uint32_t idesc = tc_instr_desc();
+        for (int kc = 0; kc < nk; kc++) {
+            const int s = kc % TC_STAGES, use = kc / TC_STAGES;
+            tc_mbar_wait(&full[s], use & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t wa = tc_smem_u32(wtile + (size_t)s * TC_TILE_BYTES);
+                const uint32_t aa = tc_smem_u32(atile + (size_t)s * TC_TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; k++) {
+                    const uint64_t adesc = tc_smem_desc(wa + k * 32); // +16 bf16 along K inside the swizzle atom
+                    const uint64_t bdesc = tc_smem_desc(aa + k * 32);
+                    const uint32_t accum = (kc | k) ? 1u : 0u;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                        ::"r"(tmem_base), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+                        : "memory");
+                }
+                // frees the smem slot when these MMAs have consumed it (implies fence::before_thread_sync)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(&empty[s]))
+                             : "memory");
+                if (kc == nk - 1)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(&tmem_full))
+                                 : "memory");
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_BN) : "memory");
+    }
+}
+
+// C[T, out_col_off + n] (+= residual) = sum_k A_bf16[T, a_col_off + k] * dequant(W[n, w_col_off + k]),  n in [0, N)
+int jl_launch_gemm_tc(jl_ctx *ctx, cudaStream_t stream, const uint16_t *a_bf16, int lda, int T, const DevTensor &W, int n_rows,
+                      int w_col_off, int K, float *out, int ldc, int out_col_off, const float *residual, int res_ld) {
+    if (W.dtype != JL_Q4) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "gemm_tc: weights must be Q4");
+    if ((K % TC_BK) || (n_rows % TC_BM) || (w_col_off % TC_BK) || T <= 0 || (lda % 8))
+        return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "gemm_tc: needs K %% 64 == 0 and N %% 128 == 0 (K=%d N=%d)", K, n_rows);
+    TcParams p;
+    p.a = a_bf16, p.lda = lda, p.T = T;
+    p.w = (const uint8_t *)W.data, p.ws = W.scales, p.ldw = (int)W.cols, p.w_col_off = w_col_off, p.K = K, p.N = n_rows;
+    p.out = out, p.ldc = ldc, p.out_col_off = out_col_off, p.residual = residual, p.res_ld = res_ld;
+    const size_t smem = (size_t)2 * TC_STAGES * TC_TILE_BYTES + 1024;
+    static bool configured = false;
+    if (!configured) {
+        JL_CUDA_CHECK(ctx, cudaFuncSetAttribute(gemm_q4_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid(n_rows / TC_BM, (T + TC_BN - 1) / TC_BN);
+    gemm_q4_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(p);
+    ctx->launches++;
+    JL_CUDA_CHECK(ctx, cudaGetLastError());
+    return JL_OK;
+}

@@ -38,7 +38,9 @@ struct jl_model {
     // scratch
     int maxB = 0;
     float *x = nullptr, *xb = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *att = nullptr, *hbuf = nullptr,
-          *partial = nullptr, *logits = nullptr, *attn_ws = nullptr, *last_hidden = nullptr;
+          *partial = nullptr, *logits = nullptr, *attn_ws = nullptr, *last_hidden = nullptr, *ln = nullptr, *hbuf2 = nullptr;
+    uint16_t *abf = nullptr; // bf16 activations for the tensor-core prefill GEMMs
+    bool tc_ok = false;
     int max_splits = 32;
     int32_t *d_tokens = nullptr, *d_positions = nullptr, *d_sessions = nullptr, *d_next = nullptr, *d_hist = nullptr,
             *d_counter = nullptr;
@@ -215,6 +217,17 @@ extern "C" int jl_model_finalize(jl_model *m) {
     M_CHECK(dev_alloc(ctx, (void **)&m->att, B * m->attn_seg * 4));
     M_CHECK(dev_alloc(ctx, (void **)&m->hbuf, B * m->h_seg * 4));
     M_CHECK(dev_alloc(ctx, (void **)&m->partial, B * E * 4));
+    if (c.prefill_tensor_core) {
+        size_t kmax = E > m->h_seg ? E : m->h_seg;
+        if ((size_t)m->attn_seg > kmax) kmax = m->attn_seg;
+        M_CHECK(dev_alloc(ctx, (void **)&m->ln, B * E * 4));
+        M_CHECK(dev_alloc(ctx, (void **)&m->hbuf2, B * m->h_seg * 4));
+        M_CHECK(dev_alloc(ctx, (void **)&m->abf, B * kmax * 2));
+        bool ok = c.tp_size == 1 && (E % 128) == 0 && (m->h_seg % 128) == 0 && (m->attn_seg % 128) == 0 && (m->kv_seg % 128) == 0;
+        for (int L = 0; L < c.num_layers && ok; L++)
+            for (int sl : {JL_L_Q, JL_L_K, JL_L_V, JL_L_O, JL_L_GATE, JL_L_DOWN, JL_L_UP}) ok = ok && m->l[(size_t)L * 9 + sl].dtype == JL_Q4;
+        m->tc_ok = ok;
+    }
     M_CHECK(dev_alloc(ctx, (void **)&m->logits, (size_t)c.max_sessions * c.vocab_size * 4));
     M_CHECK(dev_alloc(ctx, (void **)&m->last_hidden, (size_t)c.max_sessions * E * 4));
     M_CHECK(dev_alloc(ctx, (void **)&m->attn_ws, B * m->heads_local * m->max_splits * (hs + 2) * 4));
@@ -281,7 +294,7 @@ extern "C" int jl_model_free(jl_model *m) {
     for (auto &kv : m->graphs) cudaGraphExecDestroy(kv.second);
     for (void *p : m->page_table_host)
         if (p) cudaFree(p);
-    void *bufs[] = {m->rope, m->page_table_dev, m->x, m->xb, m->q, m->k, m->v, m->att, m->hbuf, m->partial, m->logits,
+    void *bufs[] = {m->ln, m->hbuf2, m->abf, m->rope, m->page_table_dev, m->x, m->xb, m->q, m->k, m->v, m->att, m->hbuf, m->partial, m->logits,
                     m->last_hidden, m->attn_ws, m->d_tokens, m->d_positions, m->d_sessions, m->d_next, m->d_hist, m->d_counter,
                     m->argmax_scratch, m->fda_done, m->mega_layers, m->mega_sync, m->mega_att_done, m->mega_slots};
     for (void *p : bufs)
@@ -498,6 +511,43 @@ static int forward_rows(jl_model *m, int M, int max_pos, int splits, bool timed,
     return JL_OK;
 }
 
+// Prefill chunk on the tensor cores: the same op sequence as forward_rows with every weight GEMM on tcgen05
+// (BF16 operands, F32 accumulate; jl_gemm_tc.cu).  Norms, RoPE, attention, SiLU stay f32.
+static int forward_rows_tc(jl_model *m, int M, int max_pos, int splits) {
+    jl_ctx *ctx = m->ctx;
+    const jl_model_config &c = m->cfg;
+    const int E = c.embedding_length, hs = c.head_size, H = m->h_seg;
+    M_CHECK(jl_launch_embed(ctx, m->stream, m->g[JL_T_EMBED], m->d_tokens, M, m->x, E));
+    for (int L = 0; L < c.num_layers; L++) {
+        const DevTensor *lw = &m->l[(size_t)L * 9];
+        M_CHECK(jl_launch_rmsnorm(ctx, m->stream, m->x, M, E, lw[JL_L_ATTN_NORM].dtype, lw[JL_L_ATTN_NORM].data, 0.0f, c.layer_norm_eps, E, 0,
+                                  E, m->ln));
+        M_CHECK(jl_launch_quantize_bf16(ctx, m->stream, m->ln, M, E, 0, E, m->abf));
+        M_CHECK(jl_launch_gemm_tc(ctx, m->stream, m->abf, E, M, lw[JL_L_Q], m->attn_seg, 0, E, m->q, m->attn_seg, 0, nullptr, 0));
+        M_CHECK(jl_launch_gemm_tc(ctx, m->stream, m->abf, E, M, lw[JL_L_K], m->kv_seg, 0, E, m->k, m->kv_seg, 0, nullptr, 0));
+        M_CHECK(jl_launch_gemm_tc(ctx, m->stream, m->abf, E, M, lw[JL_L_V], m->kv_seg, 0, E, m->v, m->kv_seg, 0, nullptr, 0));
+        AttnParams ap = {};
+        ap.kv = m->kv, ap.layer = L, ap.heads = m->heads_local, ap.kv_heads = m->kv_heads_local, ap.head_size = hs;
+        ap.head0_global = m->d.headStart, ap.kv_head0_global = m->d.groupHeadStart;
+        ap.q = m->q, ap.k = m->k, ap.v = m->v, ap.q_ld = m->attn_seg, ap.kv_ld = m->kv_seg, ap.out = m->att, ap.rope = m->rope;
+        ap.rows = M, ap.sessions = m->d_sessions, ap.positions = m->d_positions;
+        ap.scale = (float)(1.0 / sqrt((double)hs)), ap.ws = m->attn_ws, ap.splits = splits;
+        M_CHECK(jl_launch_rope_kv_append(ctx, m->stream, ap, m->q, false));
+        M_CHECK(jl_launch_paged_attention(ctx, m->stream, ap, max_pos, false));
+        M_CHECK(jl_launch_quantize_bf16(ctx, m->stream, m->att, M, m->attn_seg, 0, m->attn_seg, m->abf));
+        M_CHECK(jl_launch_gemm_tc(ctx, m->stream, m->abf, m->attn_seg, M, lw[JL_L_O], E, 0, m->attn_seg, m->xb, E, 0, m->x, E));
+        M_CHECK(jl_launch_rmsnorm(ctx, m->stream, m->xb, M, E, lw[JL_L_FFN_NORM].dtype, lw[JL_L_FFN_NORM].data, 0.0f, c.layer_norm_eps, E, 0, E,
+                                  m->ln));
+        M_CHECK(jl_launch_quantize_bf16(ctx, m->stream, m->ln, M, E, 0, E, m->abf));
+        M_CHECK(jl_launch_gemm_tc(ctx, m->stream, m->abf, E, M, lw[JL_L_GATE], H, 0, E, m->hbuf, H, 0, nullptr, 0));
+        M_CHECK(jl_launch_gemm_tc(ctx, m->stream, m->abf, E, M, lw[JL_L_UP], H, 0, E, m->hbuf2, H, 0, nullptr, 0));
+        M_CHECK(jl_launch_silu_mul(ctx, m->stream, m->hbuf, m->hbuf2, M, H, 0, H));
+        M_CHECK(jl_launch_quantize_bf16(ctx, m->stream, m->hbuf, M, H, 0, H, m->abf));
+        M_CHECK(jl_launch_gemm_tc(ctx, m->stream, m->abf, H, M, lw[JL_L_DOWN], E, 0, H, m->x, E, 0, m->xb, E));
+    }
+    return JL_OK;
+}
+
 // AbstractModel.sample (:443-473) for `n` hidden rows [n, E] -> logits [n, vocab] -> argmax tokens
 static int sample_rows(jl_model *m, const float *hidden, int n, bool timed) {
     jl_ctx *ctx = m->ctx;
@@ -556,7 +606,8 @@ extern "C" int jl_model_batch_forward(jl_model *m, int session, const int32_t *t
         JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_positions, hp + m->maxB, (size_t)cnt * 4, cudaMemcpyHostToDevice, m->stream));
         JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_sessions, hp + 2 * m->maxB, (size_t)cnt * 4, cudaMemcpyHostToDevice, m->stream));
         const int max_pos = start_pos + i + cnt - 1;
-        M_CHECK(forward_rows(m, cnt, max_pos, pick_splits(m, max_pos, cnt), false));
+        if (m->tc_ok && cnt >= 16) M_CHECK(forward_rows_tc(m, cnt, max_pos, pick_splits(m, max_pos, cnt)));
+        else M_CHECK(forward_rows(m, cnt, max_pos, pick_splits(m, max_pos, cnt), false));
         // keep the last row for sample()
         JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->last_hidden + (size_t)session * E, m->x + (size_t)(cnt - 1) * E, (size_t)E * 4,
                                            cudaMemcpyDeviceToDevice, m->stream));

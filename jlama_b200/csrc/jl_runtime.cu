@@ -251,6 +251,46 @@ extern "C" int jl_gemm(jl_ctx *ctx, int a_dtype, const void *a, const float *a_s
     return gemm_locked(ctx, a_dtype, a, a_scales, a_col_off, lda, it->second, b_col_off, r, roffset, m, n0, n, k, ldc);
 }
 
+extern "C" int jl_gemm_tc(jl_ctx *ctx, int a_dtype, const void *a, int a_col_off, int lda, int64_t b_id, int b_col_off, float *r,
+                          int roffset, int m, int n0, int n, int k, int ldc) {
+    if (!ctx) return JL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    auto it = ctx->tensors.find(b_id);
+    if (it == ctx->tensors.end()) return jl_set_error(ctx, JL_ERR_INVALID, "gemm_tc: unknown tensor id %lld", (long long)b_id);
+    const DevTensor &B = it->second;
+    if (m <= 0 || n <= 0 || k <= 0) return JL_OK;
+    if (!a || !r) return jl_set_error(ctx, JL_ERR_INVALID, "gemm_tc: null buffer");
+    if (a_dtype != JL_F32 && a_dtype != JL_BF16) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "gemm_tc: activations must be F32 or BF16");
+    if (n0 < 0 || n0 + n > B.rows || b_col_off < 0 || b_col_off + k > B.cols || a_col_off < 0 || a_col_off + k > lda)
+        return jl_set_error(ctx, JL_ERR_INVALID, "gemm_tc: slice out of range");
+    if ((n0 % 128) || (a_col_off % 8) || (lda % 8)) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "gemm_tc: n0 %% 128, a_col_off %% 8, lda %% 8 required");
+    const int c0 = n0 - roffset;
+    if (c0 < 0 || c0 + n > ldc) return jl_set_error(ctx, JL_ERR_INVALID, "gemm_tc: result offset out of range");
+    const size_t a_elems = (size_t)m * lda;
+    uint16_t *dab = (uint16_t *)jl_scratch(ctx, 0, a_elems * 2);
+    float *dr = (float *)jl_scratch(ctx, 1, (size_t)m * n * 4);
+    if (!dab || !dr) return JL_ERR_OOM;
+    if (a_dtype == JL_F32) {
+        float *daf = (float *)jl_scratch(ctx, 2, a_elems * 4);
+        if (!daf) return JL_ERR_OOM;
+        JL_CUDA_CHECK(ctx, cudaMemcpyAsync(daf, a, a_elems * 4, cudaMemcpyHostToDevice, ctx->stream));
+        int rc = jl_launch_quantize_bf16(ctx, ctx->stream, daf, m, lda, 0, lda, dab); // FloatConversions.float32ToBFloat16 (RNE)
+        if (rc) return rc;
+    } else {
+        JL_CUDA_CHECK(ctx, cudaMemcpyAsync(dab, a, a_elems * 2, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    // view of B starting at row n0: the kernel indexes weight rows from 0
+    DevTensor Bv = B;
+    Bv.data = (uint8_t *)B.data + (size_t)n0 * (B.cols / 2);
+    Bv.scales = B.scales + (size_t)n0 * (B.cols / 32);
+    int rc = jl_launch_gemm_tc(ctx, ctx->stream, dab + a_col_off, lda, m, Bv, n, b_col_off, k, dr, n, 0, nullptr, 0);
+    if (rc) return rc;
+    JL_CUDA_CHECK(ctx, cudaMemcpy2DAsync(r + c0, (size_t)ldc * 4, dr, (size_t)n * 4, (size_t)n * 4, m, cudaMemcpyDeviceToHost, ctx->stream));
+    JL_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return JL_OK;
+}
+
 extern "C" int jl_gemm_batch(jl_ctx *ctx, int batch_num, int a_dtype, const void *a, const float *a_scales, int a_col_off,
                              int lda, const int64_t *b_ids, int b_col_off, float *const *r, int roffset, int m, int n0, int n,
                              int k, int ldc) {

@@ -53,7 +53,7 @@ def _slice_cols(t, start, length):
 
 class LlamaModel:
     def __init__(self, ctx, cfg, weights, working_qtype=I8, kv_dtype=F32, max_batch=256, max_sessions=1, max_context=0,
-                 tp_rank=0, tp_size=1, flags=0):
+                 tp_rank=0, tp_size=1, flags=0, prefill_tensor_core=0):
         self.ctx, self.cfg, self.lib = ctx, cfg, ctx.lib
         self.dctx = DistributedContext(cfg, tp_rank, tp_size)
         mc = native.ModelConfig(
@@ -61,7 +61,7 @@ class LlamaModel:
             num_kv_heads=cfg["kv_heads"], num_layers=cfg["layers"], vocab_size=cfg["vocab"], head_size=cfg["E"] // cfg["heads"],
             layer_norm_eps=cfg["eps"], rope_theta=cfg["rope_theta"], rope_scaling=cfg.get("rope_scale", 1.0),
             working_qtype=working_qtype, kv_dtype=kv_dtype, max_batch=max_batch, max_sessions=max_sessions,
-            max_context=max_context, tp_rank=tp_rank, tp_size=tp_size, prefill_tensor_core=0, flags=flags)
+            max_context=max_context, tp_rank=tp_rank, tp_size=tp_size, prefill_tensor_core=prefill_tensor_core, flags=flags)
         h = C.c_void_p()
         ctx.check(self.lib.jl_model_create(ctx.h, C.byref(mc), C.byref(h)))
         self.h = h

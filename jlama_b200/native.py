@@ -59,6 +59,7 @@ SIGNATURES = {
     "jl_register_tensor": (_i64, [_vp, _i, _i64, _i64, _vp, _vp]),
     "jl_unregister_tensor": (_i, [_vp, _i64]),
     "jl_gemm": (_i, [_vp, _i, _vp, _vp, _i, _i, _i64, _i, _vp, _i, _i, _i, _i, _i, _i]),
+    "jl_gemm_tc": (_i, [_vp, _i, _vp, _i, _i, _i64, _i, _vp, _i, _i, _i, _i, _i, _i]),
     "jl_gemm_batch": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i]),
     "jl_gemm_host": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i]),
     "jl_accumulate": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i]),

@@ -86,6 +86,15 @@ class CudaTensorOperations:
                                        row_chunk_size, column_limit, result.cols)
         self.ctx.check(rc)
 
+    def batch_dot_product_tensor_core(self, result, a, b, a_column_offset, b_column_offset, column_limit, r_row_offset=0,
+                                      b_row_offset=0, row_chunk_size=None):
+        """batchDotProduct on tcgen05 (BF16 operands, F32 accumulate) for prefill-shaped calls; B must be registered Q4."""
+        if row_chunk_size is None:
+            row_chunk_size = b.rows
+        self.ctx.check(self.lib.jl_gemm_tc(self.ctx.h, a.dtype, ptr(a.data), a_column_offset, a.cols, self._registered[b.uid],
+                                           b_column_offset, ptr(result.data), -r_row_offset, a.rows, b_row_offset, row_chunk_size,
+                                           column_limit, result.cols))
+
     def dot_product_chunk(self, result, a, b, column_offset, column_limit, row_offset, row_chunk_size):
         # TensorOperations.java:74-84
         self.batch_dot_product(result, a, b, column_offset, column_offset, column_limit, 0, row_offset, row_chunk_size)

@@ -247,3 +247,26 @@ def test_error_paths_do_not_abort(cuda_ctx):
     h = C.c_void_p()
     assert lib.jl_model_create(cuda_ctx.h, C.byref(bad), C.byref(h)) == native.JL_ERR_INVALID
     assert b"config" in lib.jl_last_error(cuda_ctx.h)
+
+
+def test_tensor_core_prefill_matches_oracle(cuda_ctx, oracle):
+    """prefill with the tcgen05 GEMMs (BF16 operands): logits of the first sampled token within the Q4 tolerance
+    of the F32-activation oracle, decode afterwards token-for-token on the integer path."""
+    from jlama_b200 import native, synth
+    from jlama_b200.model import LlamaModel
+    cfg = synth.get_config("small-hs128")
+    w = synth.make_weights(cfg)
+    gm = LlamaModel(cuda_ctx, cfg, w, prefill_tensor_core=1)
+    ref = LlamaModel(cuda_ctx, cfg, w)
+    om = oracle.OracleLlama(cfg, w, act_q8=False)
+    prompt = synth.random_prompt(cfg, 150)
+    gt, gl = gm.generate(prompt, 4, want_logits=True)
+    rt, rl = ref.generate(prompt, 4, want_logits=True)
+    om.reset()
+    ot, ol = om.generate(prompt, 1)
+    assert _rel(gl[0], ol[0]) <= 1e-2
+    assert _rel(gl[0], rl[0]) <= 2e-2
+    assert gt[0] == ot[0]
+    gm.close()
+    ref.close()
+    om.close()

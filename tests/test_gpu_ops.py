@@ -244,3 +244,29 @@ def test_gemv_model_shapes_full_size(cuda_ops, oracle, K, N):
     ref = oracle.batch_dot(oracle.OTensor(oracle.I8, q, s), oracle.OTensor(oracle.Q4, w.data, w.scales), 0, 0, K, 0, 0, N)
     assert np.abs(c.data - ref).max() <= 2e-5 * np.abs(ref).max()
     cuda_ops.unregister_model_tensor(w)
+
+
+@pytest.mark.parametrize("M,N,K", [(16, 128, 64), (128, 256, 512), (100, 384, 4096), (256, 1024, 2048)])
+def test_tensor_core_gemm_matches_bf16_reference(cuda_ops, oracle, M, N, K):
+    """tcgen05 prefill GEMM (BF16 operands, F32 accumulate, dequant fused into the smem fill) against a float64
+    product of the SAME BF16-rounded operands (tight), and against the reference's F32 x Q4 arithmetic (1e-2 class)."""
+    from jlama_b200 import tensor as T
+    rng = np.random.default_rng(M * 7 + N)
+    w = T.Q4ByteBufferTensor(rng.integers(0, 256, (N, K // 2), dtype=np.uint8),
+                             ((0.5 + rng.random((N, K // 32))) * 0.01 * np.where(rng.random((N, K // 32)) < 0.5, -1, 1)).astype(np.float32))
+    cuda_ops.register_model_tensor(w)
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    c = T.FloatBufferTensor(np.zeros((M, N), dtype=np.float32))
+    cuda_ops.batch_dot_product_tensor_core(c, T.FloatBufferTensor(a), w, 0, 0, K)
+    a16 = T.bfloat16_to_float32(T.float32_to_bfloat16(a)).astype(np.float64)
+    w16 = T.bfloat16_to_float32(T.float32_to_bfloat16(w.to_float())).astype(np.float64)
+    ref = a16 @ w16.T
+    assert np.abs(c.data - ref).max() <= 2e-5 * np.abs(ref).max() * np.sqrt(K / 64)
+    exact = oracle.batch_dot(oracle.f32(a), oracle.OTensor(oracle.Q4, w.data, w.scales), 0, 0, K, 0, 0, N)
+    assert np.abs(c.data - exact).max() <= 1e-2 * np.abs(exact).max()
+    # row-chunk / result-offset semantics are those of batchDotProduct
+    if N >= 256:
+        c2 = T.FloatBufferTensor(np.zeros((M, N), dtype=np.float32))
+        cuda_ops.batch_dot_product_tensor_core(c2, T.FloatBufferTensor(a), w, 0, 0, K, 0, 128, 128)
+        assert np.all(c2.data[:, :128] == 0) and np.array_equal(c2.data[:, 128:256], c.data[:, 128:256])
+    cuda_ops.unregister_model_tensor(w)
