@@ -62,6 +62,10 @@ int64_t jl_kernel_launches(jl_ctx *ctx);
  * Returns the average microseconds per launch measured with CUDA events around the whole sequence. */
 int jl_debug_gemv_bench(jl_ctx *ctx, int64_t b_id, int n, int m, int mode, int iters, int use_pdl, double *avg_us);
 
+/* diagnostic: average microseconds of one tcgen05 prefill GEMM launch C[t, rows] = A_bf16[t, k] * W^T on
+ * device-resident operands (W = registered Q4 tensor [rows, k]). */
+int jl_debug_gemm_tc_bench(jl_ctx *ctx, int64_t b_id, int t, int iters, double *avg_us);
+
 /* ---- TensorOperations.registerModelTensor (core/tensor/operations/TensorOperations.java:39;
  *      NativeGPUTensorOperations.java:104-151 -> register_tensor, vector_gpu.h:10) ------------
  * Copies a weight (and its Q4/I8 block scales) to HBM once; returns a tensor id, -1 on failure.

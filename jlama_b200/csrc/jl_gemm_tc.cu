@@ -19,12 +19,12 @@
 // available through the GEMV path (jl_model: prefill_tensor_core = 0).
 #include "jl_common.cuh"
 
-#define TC_THREADS 160 // warps 0-3: producers + epilogue, warp 4: TMEM allocator + MMA issuer
-#define TC_BM 128      // weight rows per CTA (UMMA M)
-#define TC_BN 128      // tokens per CTA (UMMA N)
-#define TC_BK 64       // K per pipeline stage: 64 bf16 = one 128-byte swizzle atom
+#define TC_PWARPS 8                      // producer / epilogue warps
+#define TC_THREADS (TC_PWARPS * 32 + 32) // + warp 8: TMEM allocator and MMA issuer
+#define TC_BM 128                        // weight rows per CTA (UMMA M)
+#define TC_BK 64                         // K per pipeline stage: 64 bf16 = one 128-byte swizzle atom
 #define TC_STAGES 4
-#define TC_TILE_BYTES (TC_BM * TC_BK * 2) // 16 KB per operand tile
+#define TC_WTILE_BYTES (TC_BM * TC_BK * 2) // 16 KB weight tile
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tc_mbar_init(uint64_t *bar, uint32_t count) {
@@ -54,9 +54,10 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                       // layout type: SWIZZLE_128B
     return d;
 }
-// instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = 128
+// instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = BN
+template <int BN>
 __device__ __forceinline__ uint32_t tc_instr_desc() {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -78,28 +79,31 @@ struct TcParams {
     int res_ld;
 };
 
+// BN = tokens per CTA (UMMA N): 128, or 256 to amortise the weight dequantisation over twice the tokens
+template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_q4_tc_kernel(const TcParams p) {
+    constexpr int ATILE = BN * TC_BK * 2;
     extern __shared__ __align__(1024) unsigned char tc_smem[];
-    unsigned char *wtile = tc_smem;                                   // [STAGES][16 KB] weight tiles (UMMA A)
-    unsigned char *atile = tc_smem + TC_STAGES * TC_TILE_BYTES;       // [STAGES][16 KB] token tiles (UMMA B)
+    unsigned char *wtile = tc_smem;                                // [STAGES][16 KB] weight tiles (UMMA A)
+    unsigned char *atile = tc_smem + TC_STAGES * TC_WTILE_BYTES;   // [STAGES][BN x 128 B] token tiles (UMMA B)
     __shared__ uint64_t full[TC_STAGES], empty[TC_STAGES], tmem_full;
     __shared__ uint32_t tmem_base_sh;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n0 = blockIdx.x * TC_BM;  // first weight row of this CTA
-    const int t0 = blockIdx.y * TC_BN;  // first token of this CTA
+    const int n0 = blockIdx.x * TC_BM; // first weight row of this CTA
+    const int t0 = blockIdx.y * BN;    // first token of this CTA
     const int nk = p.K / TC_BK;
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; s++) {
-            tc_mbar_init(&full[s], 4);  // one arrival per producer warp
-            tc_mbar_init(&empty[s], 1); // tcgen05.commit
+            tc_mbar_init(&full[s], TC_PWARPS); // one arrival per producer warp
+            tc_mbar_init(&empty[s], 1);        // tcgen05.commit
         }
         tc_mbar_init(&tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) { // TMEM: 128 columns x 128 lanes of f32 accumulators
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_base_sh)), "n"(TC_BN)
+    if (warp == TC_PWARPS) { // TMEM: BN columns x 128 lanes of f32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_base_sh)), "n"(BN)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -108,68 +112,71 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_q4_tc_kernel(const TcParam
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_sh;
 
-    if (warp < 4) {
-        // ===== producers: thread r fills row r of both tiles (128 bytes each, 16-byte chunks XOR-swizzled by r & 7) =====
-        const int r = tid; // 0..127
+    if (warp < TC_PWARPS) {
+        // ===== producers.  Weight tile: thread (r = tid & 127, half = tid >> 7) dequantises one 32-element block of
+        // row r (four 16-byte chunks).  Token tile: 256 threads copy BN rows of 128 bytes.  Chunks are XOR-swizzled
+        // by (row & 7) -- the SWIZZLE_128B K-major layout the tensor core reads. =====
+        const int r = tid & 127, half = tid >> 7;
         const size_t wrow = (size_t)(n0 + r);
-        const uint8_t *wq = p.w + wrow * (size_t)(p.ldw / 2) + p.w_col_off / 2;
-        const float *wsc = p.ws + wrow * (size_t)(p.ldw / 32) + p.w_col_off / 32;
-        const bool tok_ok = (t0 + r) < p.T;
-        const uint16_t *arow = p.a + (size_t)(tok_ok ? t0 + r : 0) * p.lda;
+        const uint8_t *wq = p.w + wrow * (size_t)(p.ldw / 2) + p.w_col_off / 2 + half * 16;
+        const float *wsc = p.ws + wrow * (size_t)(p.ldw / 32) + p.w_col_off / 32 + half;
+        // token tile mapping: BN == 256: thread t copies row t (8 chunks); BN == 128: row r, chunks half*4 .. half*4+3
+        constexpr int ACH = BN == 256 ? 8 : 4;
+        const int arow_i = BN == 256 ? tid : r;
+        const int ach0 = BN == 256 ? 0 : half * 4;
+        const bool tok_ok = (t0 + arow_i) < p.T;
+        const uint16_t *arow = p.a + (size_t)(tok_ok ? t0 + arow_i : 0) * p.lda + ach0 * 8;
         for (int kc = 0; kc < nk; kc++) {
             const int s = kc % TC_STAGES, use = kc / TC_STAGES;
             // issue the global loads first, then wait for the slot
-            const uint4 q0 = ldg_nc_u4(wq + (size_t)kc * 32), q1 = ldg_nc_u4(wq + (size_t)kc * 32 + 16);
-            const float s0 = ldg_nc_f32(wsc + kc * 2), s1 = ldg_nc_f32(wsc + kc * 2 + 1);
-            uint4 av[8];
+            const uint4 q = ldg_nc_u4(wq + (size_t)kc * 32);
+            const float sc = ldg_nc_f32(wsc + kc * 2);
+            uint4 av[ACH];
 #pragma unroll
-            for (int c = 0; c < 8; c++)
-                av[c] = tok_ok ? *(const uint4 *)(arow + (size_t)kc * TC_BK + c * 8) : make_uint4(0, 0, 0, 0);
+            for (int c = 0; c < ACH; c++) av[c] = tok_ok ? *(const uint4 *)(arow + (size_t)kc * TC_BK + c * 8) : make_uint4(0, 0, 0, 0);
             tc_mbar_wait(&empty[s], (use & 1) ^ 1);
-            unsigned char *wdst = wtile + (size_t)s * TC_TILE_BYTES + (size_t)r * 128;
-            unsigned char *adst = atile + (size_t)s * TC_TILE_BYTES + (size_t)r * 128;
-            // dequantise: block = 16 bytes, element j = low nibble of byte j, element j+16 = high nibble of byte j
+            unsigned char *wdst = wtile + (size_t)s * TC_WTILE_BYTES + (size_t)r * 128;
+            unsigned char *adst = atile + (size_t)s * ATILE + (size_t)arow_i * 128;
+            // block = 16 bytes: element j = low nibble of byte j, element j+16 = high nibble of byte j.
+            // nibble -> float through the 2^23 magic number (PRMT + FADD), * scale, round once to BF16.
+            const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+            float lo[16], hi[16];
 #pragma unroll
-            for (int b = 0; b < 2; b++) {
-                const uint4 q = b ? q1 : q0;
-                const float sc = b ? s1 : s0;
-                const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
-                float lo[16], hi[16];
+            for (int i = 0; i < 4; i++) {
+                const uint32_t l4 = qw[i] & 0x0F0F0F0Fu, h4 = (qw[i] >> 4) & 0x0F0F0F0Fu;
 #pragma unroll
-                for (int i = 0; i < 4; i++)
-#pragma unroll
-                    for (int t = 0; t < 4; t++) {
-                        const int byte = (qw[i] >> (8 * t)) & 0xFF;
-                        lo[i * 4 + t] = __fmul_rn((float)((byte & 0x0F) - 8), sc);
-                        hi[i * 4 + t] = __fmul_rn((float)((byte >> 4) - 8), sc);
-                    }
-                // chunks: b*4 + 0,1 = low-nibble elements 0..15; b*4 + 2,3 = high-nibble elements 16..31
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const float *src = c < 2 ? lo + c * 8 : hi + (c - 2) * 8;
-                    uint4 o;
-                    o.x = pack_bf16x2(src[0], src[1]);
-                    o.y = pack_bf16x2(src[2], src[3]);
-                    o.z = pack_bf16x2(src[4], src[5]);
-                    o.w = pack_bf16x2(src[6], src[7]);
-                    const int chunk = b * 4 + c;
-                    *(uint4 *)(wdst + ((chunk ^ (r & 7)) * 16)) = o;
+                for (int t = 0; t < 4; t++) {
+                    lo[i * 4 + t] = __fmul_rn(__uint_as_float(__byte_perm(l4, 0x4B000000u, 0x7540 | t)) - 8388616.0f, sc);
+                    hi[i * 4 + t] = __fmul_rn(__uint_as_float(__byte_perm(h4, 0x4B000000u, 0x7540 | t)) - 8388616.0f, sc);
                 }
             }
 #pragma unroll
-            for (int c = 0; c < 8; c++) *(uint4 *)(adst + ((c ^ (r & 7)) * 16)) = av[c];
+            for (int c = 0; c < 4; c++) { // chunks half*4 + {0,1}: elements 0..15 (low nibbles); {2,3}: elements 16..31
+                const float *src = c < 2 ? lo + c * 8 : hi + (c - 2) * 8;
+                uint4 o;
+                o.x = pack_bf16x2(src[0], src[1]);
+                o.y = pack_bf16x2(src[2], src[3]);
+                o.z = pack_bf16x2(src[4], src[5]);
+                o.w = pack_bf16x2(src[6], src[7]);
+                *(uint4 *)(wdst + (((half * 4 + c) ^ (r & 7)) * 16)) = o;
+            }
+#pragma unroll
+            for (int c = 0; c < ACH; c++) *(uint4 *)(adst + (((ach0 + c) ^ (arow_i & 7)) * 16)) = av[c];
             // make the generic-proxy writes visible to the tensor core (async proxy), then signal
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) tc_mbar_arrive(&full[s]);
         }
-        // ===== epilogue: warp w owns TMEM lanes 32w..32w+31 = weight rows n0 + 32w + lane =====
+        // ===== epilogue: warp w reads TMEM lanes 32*(w%4) .. +31 (weight rows), column half w/4 =====
         tc_mbar_wait(&tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int col_out = p.out_col_off + n0 + warp * 32 + lane;
-        for (int c0 = 0; c0 < TC_BN; c0 += 16) {
+        const int lq = warp & 3, chalf = warp >> 2;
+        const int nrow = n0 + lq * 32 + lane;
+        const int col_out = p.out_col_off + nrow;
+        for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 16) {
+            if (t0 + c0 >= p.T) break;
             uint32_t v[16];
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0;
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
@@ -181,22 +188,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_q4_tc_kernel(const TcParam
                 const int tok = t0 + c0 + i;
                 if (tok < p.T) {
                     float x = __uint_as_float(v[i]);
-                    if (p.residual) x = __fadd_rn(x, p.residual[(size_t)tok * p.res_ld + (n0 + warp * 32 + lane)]);
+                    if (p.residual) x = __fadd_rn(x, p.residual[(size_t)tok * p.res_ld + nrow]);
                     p.out[(size_t)tok * p.ldc + col_out] = x;
                 }
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     } else {
-        // ===== MMA issuer (one elected lane of warp 4) =====
-        const uint32_t idesc = tc_instr_desc();
+        // ===== MMA issuer (one elected lane of the last warp) =====
+        const uint32_t idesc = tc_instr_desc<BN>();
         for (int kc = 0; kc < nk; kc++) {
             const int s = kc % TC_STAGES, use = kc / TC_STAGES;
             tc_mbar_wait(&full[s], use & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
-                const uint32_t wa = tc_smem_u32(wtile + (size_t)s * TC_TILE_BYTES);
-                const uint32_t aa = tc_smem_u32(atile + (size_t)s * TC_TILE_BYTES);
+                const uint32_t wa = tc_smem_u32(wtile + (size_t)s * TC_WTILE_BYTES);
+                const uint32_t aa = tc_smem_u32(atile + (size_t)s * ATILE);
 #pragma unroll
                 for (int k = 0; k < TC_BK / 16; k++) {
                     const uint64_t adesc = tc_smem_desc(wa + k * 32); // +16 bf16 along K inside the swizzle atom
@@ -219,10 +226,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_q4_tc_kernel(const TcParam
         }
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == TC_PWARPS) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
     }
+}
+
+template <int BN>
+static int launch_tc(jl_ctx *ctx, cudaStream_t stream, const TcParams &p) {
+    const size_t smem = (size_t)TC_STAGES * (TC_WTILE_BYTES + (size_t)BN * TC_BK * 2) + 1024;
+    static bool configured = false;
+    if (!configured) {
+        JL_CUDA_CHECK(ctx, cudaFuncSetAttribute(gemm_q4_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid(p.N / TC_BM, (p.T + BN - 1) / BN);
+    gemm_q4_tc_kernel<BN><<<grid, TC_THREADS, smem, stream>>>(p);
+    ctx->launches++;
+    JL_CUDA_CHECK(ctx, cudaGetLastError());
+    return JL_OK;
 }
 
 // C[T, out_col_off + n] (+= residual) = sum_k A_bf16[T, a_col_off + k] * dequant(W[n, w_col_off + k]),  n in [0, N)
@@ -235,15 +257,7 @@ int jl_launch_gemm_tc(jl_ctx *ctx, cudaStream_t stream, const uint16_t *a_bf16, 
     p.a = a_bf16, p.lda = lda, p.T = T;
     p.w = (const uint8_t *)W.data, p.ws = W.scales, p.ldw = (int)W.cols, p.w_col_off = w_col_off, p.K = K, p.N = n_rows;
     p.out = out, p.ldc = ldc, p.out_col_off = out_col_off, p.residual = residual, p.res_ld = res_ld;
-    const size_t smem = (size_t)2 * TC_STAGES * TC_TILE_BYTES + 1024;
-    static bool configured = false;
-    if (!configured) {
-        JL_CUDA_CHECK(ctx, cudaFuncSetAttribute(gemm_q4_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    dim3 grid(n_rows / TC_BM, (T + TC_BN - 1) / TC_BN);
-    gemm_q4_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(p);
-    ctx->launches++;
-    JL_CUDA_CHECK(ctx, cudaGetLastError());
-    return JL_OK;
+    // 256-token tiles amortise the dequantisation better; use them when they do not starve the grid
+    if (T > 128 && (size_t)(n_rows / TC_BM) * ((T + 255) / 256) >= (size_t)ctx->sm_count / 2) return launch_tc<256>(ctx, stream, p);
+    return launch_tc<128>(ctx, stream, p);
 }

@@ -649,3 +649,33 @@ extern "C" int jl_debug_gemv_bench(jl_ctx *ctx, int64_t b_id, int n, int m, int 
     *avg_us = (double)ms * 1000.0 / iters;
     return JL_OK;
 }
+
+extern "C" int jl_debug_gemm_tc_bench(jl_ctx *ctx, int64_t b_id, int t, int iters, double *avg_us) {
+    HOST_OP_PROLOGUE();
+    auto it = ctx->tensors.find(b_id);
+    if (it == ctx->tensors.end() || !avg_us || iters <= 0 || t <= 0) return jl_set_error(ctx, JL_ERR_INVALID, "gemm_tc_bench: bad arguments");
+    const DevTensor &B = it->second;
+    const int k = (int)B.cols, n = (int)B.rows;
+    uint16_t *da = (uint16_t *)jl_scratch(ctx, 0, (size_t)t * k * 2);
+    float *dr = (float *)jl_scratch(ctx, 1, (size_t)t * n * 4);
+    if (!da || !dr) return JL_ERR_OOM;
+    JL_CUDA_CHECK(ctx, cudaMemsetAsync(da, 0x3c, (size_t)t * k * 2, ctx->stream)); // bf16 ~0.0115
+    cudaEvent_t e0, e1;
+    JL_CUDA_CHECK(ctx, cudaEventCreate(&e0));
+    JL_CUDA_CHECK(ctx, cudaEventCreate(&e1));
+    for (int pass = 0; pass < 2; pass++) {
+        if (pass == 1) JL_CUDA_CHECK(ctx, cudaEventRecord(e0, ctx->stream));
+        for (int i = 0; i < (pass == 0 ? 3 : iters); i++) {
+            int rc = jl_launch_gemm_tc(ctx, ctx->stream, da, k, t, B, n, 0, k, dr, n, 0, nullptr, 0);
+            if (rc) return rc;
+        }
+    }
+    JL_CUDA_CHECK(ctx, cudaEventRecord(e1, ctx->stream));
+    JL_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *avg_us = (double)ms * 1000.0 / iters;
+    return JL_OK;
+}

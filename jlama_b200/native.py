@@ -56,6 +56,7 @@ SIGNATURES = {
     "jl_sync": (_i, [_vp]),
     "jl_kernel_launches": (_i64, [_vp]),
     "jl_debug_gemv_bench": (_i, [_vp, _i64, _i, _i, _i, _i, _i, C.POINTER(_d)]),
+    "jl_debug_gemm_tc_bench": (_i, [_vp, _i64, _i, _i, C.POINTER(_d)]),
     "jl_register_tensor": (_i64, [_vp, _i, _i64, _i64, _vp, _vp]),
     "jl_unregister_tensor": (_i, [_vp, _i64]),
     "jl_gemm": (_i, [_vp, _i, _vp, _vp, _i, _i, _i64, _i, _vp, _i, _i, _i, _i, _i, _i]),
