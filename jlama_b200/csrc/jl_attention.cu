@@ -303,9 +303,11 @@ int jl_launch_paged_attention(jl_ctx *ctx, cudaStream_t s, const AttnParams &p, 
 #define FDA_THREADS 256
 template <int HS>
 __global__ void __launch_bounds__(FDA_THREADS) fused_decode_attention_kernel(const AttnTask t, const int layer,
-                                                                              unsigned *done_cnt) {
+                                                                              unsigned *done_cnt, unsigned long long *trace) {
+    ktrace_begin(trace, 0xA00u | (unsigned long long)t.splits << 16);
     pdl_launch_dependents();
     pdl_wait();
+    ktrace_mid(trace);
     extern __shared__ __align__(16) unsigned char fda_smem[];
     __shared__ int s_last;
     const int kvh = blockIdx.x, m = blockIdx.y, split = blockIdx.z;
@@ -323,6 +325,10 @@ __global__ void __launch_bounds__(FDA_THREADS) fused_decode_attention_kernel(con
         __syncthreads();
         if (s_last) attention_merge<HS, FDA_THREADS>(t, m, kvh);
     }
+    if (trace) {
+        __syncthreads();
+        ktrace_end(trace);
+    }
 }
 
 template <int HS>
@@ -333,8 +339,9 @@ static int launch_fda(jl_ctx *ctx, cudaStream_t s, const AttnTask &t, int layer,
         JL_CUDA_CHECK(ctx, cudaFuncSetAttribute(fused_decode_attention_kernel<HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
+    unsigned long long *trace = jl_ktrace_slot(ctx);
     JL_CUDA_CHECK(ctx, jl_launch_kernel(fused_decode_attention_kernel<HS>, dim3(t.kv_heads, rows, t.splits), dim3(FDA_THREADS), smem, s,
-                                        pdl, t, layer, done_cnt));
+                                        pdl, t, layer, done_cnt, trace));
     ctx->launches++;
     return JL_OK;
 }

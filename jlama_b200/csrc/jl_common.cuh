@@ -33,6 +33,9 @@ struct jl_ctx {
     // op-level scratch (grown on demand)
     void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t scratch_bytes[4] = {0, 0, 0, 0};
+    // kernel timeline diagnostics (jl_debug_ktrace): device [cap][4] globaltimer stamps, one slot per traced launch
+    unsigned long long *ktrace = nullptr;
+    int ktrace_cap = 0, ktrace_n = 0;
     // comm
     void *nccl_comm = nullptr;
     int rank = 0, world = 1;
@@ -98,6 +101,7 @@ struct GemvParams {
     int res_ld;
     int row0;                // first global row handled by this launch (n0)
     int total_rows;          // rows handled by this launch
+    unsigned long long *trace; // diagnostics slot (jl_debug_ktrace) or nullptr
 };
 
 #define GEMV_MAX_M 8
@@ -209,6 +213,37 @@ __device__ __forceinline__ float ldg_nc_f32(const float *p) {
     float r;
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
     return r;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define KTRACE_WORDS 16 // per slot: first CTA start, last CTA end, CTA 0 after prologue, tag, CTA 0 start, 11 free stamps
+__device__ __forceinline__ void ktrace_begin(unsigned long long *t, unsigned long long tag) {
+    if (t && threadIdx.x == 0) {
+        const unsigned long long now = globaltimer_ns();
+        atomicMin(&t[0], now);
+        if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) t[3] = tag, t[4] = now;
+    }
+}
+// extra stamp `idx` (5..15) by thread 0 of CTA 0, ordered after `dep` has been computed
+__device__ __forceinline__ void ktrace_stamp(unsigned long long *t, int idx, float dep) {
+    if (t && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) : "f"(dep));
+        t[idx] = now;
+    }
+}
+__device__ __forceinline__ void ktrace_mid(unsigned long long *t) {
+    if (t && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) t[2] = globaltimer_ns();
+}
+__device__ __forceinline__ void ktrace_end(unsigned long long *t) {
+    if (t && threadIdx.x == 0) atomicMax(&t[1], globaltimer_ns());
+}
+inline unsigned long long *jl_ktrace_slot(jl_ctx *ctx) {
+    if (!ctx->ktrace || ctx->ktrace_n >= ctx->ktrace_cap) return nullptr;
+    return ctx->ktrace + (size_t)KTRACE_WORDS * ctx->ktrace_n++;
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -12,15 +12,21 @@
 // ld.global.nc loads straight into registers (one 16-byte Q4 block per lane, 512 B per warp
 // request), activations are staged once per CTA in shared memory in a bank-conflict-free
 // [half][block][16B] layout, integer dot products use dp4a, the reduction is a warp shuffle.
-// The first weight chunk of every warp is requested BEFORE griddepcontrol.wait, so with
-// programmatic dependent launch the weight stream of kernel N+1 is already in flight while
-// kernel N drains (the activations are the only true dependency).
+//
+// Decode shape of the kernel (M = 1, Q4 weights, Q8 activations; DESIGN.md "GEMV v3"): ONE 768-thread CTA per SM.
+// A B200 SM keeps about 64 KB of loads in flight, which 24 warps x one 2.5 KB chunk already fill, so more CTAs per SM
+// only repeat the prologue: with three 256-thread CTAs the RMSNorm + Q8 quantisation ran three times per SM and its
+// loads queued behind the 60 KB of weight requests (5 us of a 8.6 us QKV launch, tools/ktrace.py).  Here the first
+// warps ("stagers") request the hidden row BEFORE any weight load, every warp then puts its first weight chunk in
+// flight, and the stagers normalise / quantise into shared memory while the weights stream.
 #include "jl_common.cuh"
 #include <stdlib.h>
 
-#define GEMV_THREADS 256
+#define GEMV_THREADS 256 // generic kernels
 #define GEMV_WARPS 8
-#define CH 4 // 32-element blocks per lane per chunk
+#define GEMV_THREADS_DECODE 768 // decode hot path: one CTA per SM
+// CH = 32-element blocks per lane per chunk (a chunk is CH*32 blocks = CH*1024 weights of one row), NBUF = register
+// chunk buffers per warp (NBUF-1 chunks are in flight while one is being consumed)
 
 struct GemvSmem {
     // offsets into dynamic shared memory, computed identically on host and device
@@ -28,7 +34,7 @@ struct GemvSmem {
     int M;
 };
 
-template <int WDT>
+template <int WDT, int CH>
 struct WBuf {
     uint4 q[CH * (WDT == JL_I8 ? 2 : 1)];
     float s[CH];
@@ -47,8 +53,8 @@ __device__ __forceinline__ void seg_lookup(const GemvParams &p, int row, int &se
     }
 }
 
-template <int WDT>
-__device__ __forceinline__ void load_chunk(WBuf<WDT> &b, const uint8_t *wrow, const float *srow, int blk0, int nblk,
+template <int WDT, int CH>
+__device__ __forceinline__ void load_chunk(WBuf<WDT, CH> &b, const uint8_t *wrow, const float *srow, int blk0, int nblk,
                                            int lane) {
 #pragma unroll
     for (int j = 0; j < CH; j++) {
@@ -221,9 +227,204 @@ __device__ void stage_activations(const GemvParams &p, int prologue, unsigned ch
     __syncthreads();
 }
 
+
+// ---- fast F32 -> (RMSNorm) -> Q8 staging ------------------------------------------------------------------------
+// Thread pair (t, t^1) owns one 32-element Q8 block: thread t holds the 16 contiguous floats that become one 16-byte
+// half of the smem layout, so a 4096-element tile is quantised by all 256 threads at once with a single shuffle for the
+// block max and one for the block sum.  For the decode case (one row, K <= 4096) the hidden row and the norm weights
+// are requested together and stay in registers: the whole prologue costs one L2 round trip instead of three.
+__device__ __forceinline__ void quant_half_block(const float (&v)[16], int8_t *aq, float *asc, int *asum, int m, int nblk,
+                                                 int blk, int half, bool in) {
+    // PanamaTensorOperations.java:1696-1710: d = max/127, q = (byte)(x*(127/max) + 0.5f), F2B truncates
+    float mx = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) mx = fmaxf(mx, fabsf(v[i]));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    const float d = __fdiv_rn(mx, 127.0f);
+    const float id = mx != 0.0f ? __fdiv_rn(127.0f, mx) : 0.0f;
+    uint32_t w[4];
+    int sum = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int q0 = (int)__fadd_rn(__fmul_rn(v[i * 4], id), 0.5f);
+        const int q1 = (int)__fadd_rn(__fmul_rn(v[i * 4 + 1], id), 0.5f);
+        const int q2 = (int)__fadd_rn(__fmul_rn(v[i * 4 + 2], id), 0.5f);
+        const int q3 = (int)__fadd_rn(__fmul_rn(v[i * 4 + 3], id), 0.5f);
+        sum += q0 + q1 + q2 + q3;
+        w[i] = (uint32_t)(q0 & 0xFF) | ((uint32_t)(q1 & 0xFF) << 8) | ((uint32_t)(q2 & 0xFF) << 16) | ((uint32_t)(q3 & 0xFF) << 24);
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    if (in) {
+        *(uint4 *)(aq + (((size_t)m * 2 + half) * nblk + blk) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+        if (half == 0) {
+            asc[m * nblk + blk] = d;
+            asum[m * nblk + blk] = sum;
+        }
+    }
+}
+
+__device__ __forceinline__ void load16(float (&v)[16], const float *src, bool in) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float4 t = in ? *(const float4 *)(src + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i * 4] = t.x, v[i * 4 + 1] = t.y, v[i * 4 + 2] = t.z, v[i * 4 + 3] = t.w;
+    }
+}
+__device__ __forceinline__ void load16_normw(float (&v)[16], const GemvParams &p, int e0, bool in) {
+    if (p.norm_w_dtype == JL_BF16) {
+        const uint4 *src = (const uint4 *)((const uint16_t *)p.norm_w + e0);
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const uint4 u = in ? src[i] : make_uint4(0, 0, 0, 0);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                v[i * 8 + t * 2] = __uint_as_float(w[t] << 16);
+                v[i * 8 + t * 2 + 1] = __uint_as_float(w[t] & 0xffff0000u);
+            }
+        }
+    } else {
+        load16(v, (const float *)p.norm_w + e0, in);
+    }
+}
+
+// RMSNorm.java:41-52 scale factor from the double sum of float squares.  rsqrt() is the correctly rounded double
+// reciprocal square root to within 1 ulp(double); after the cast to float it equals (float)(1.0 / sqrt(t)).
+__device__ __forceinline__ float rms_scale(double sumsq, int E, float eps) {
+    double t = sumsq / (double)E;
+    t += (double)eps;
+    return (float)rsqrt(t);
+}
+
+// Stagers = the first ceil(K/16/32) warps (at most all of them).  `xr`/`wr` were loaded by stage_q8_issue() before the
+// weight loads were queued.  NT = threads per CTA.  Up to two 16*NT tiles of the row live in registers.
+template <bool NORM, int NT>
+struct StageRegs {
+    float x0[16], x1[16], w[16];
+};
+
+template <bool NORM, int NT>
+__device__ __forceinline__ void stage_q8_issue(const GemvParams &p, StageRegs<NORM, NT> &r) {
+    const int tid = threadIdx.x;
+    const float *x0 = (const float *)p.a + p.a_col_off;
+    const int e0 = tid * 16, e1 = (NT + tid) * 16;
+    load16(r.x0, x0 + e0, e0 < p.K);
+    if (NORM) {
+        load16_normw(r.w, p, e0, e0 < p.K);
+    } else {
+        load16(r.x1, x0 + e1, e1 < p.K);
+    }
+}
+
+template <bool NORM, int NT>
+__device__ __forceinline__ void stage_q8_finish(const GemvParams &p, StageRegs<NORM, NT> &r, unsigned char *smem, const int nblk) {
+    constexpr int NWARP = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ double red[NWARP];
+    int8_t *aq = (int8_t *)smem;
+    float *asc = (float *)(smem + (size_t)nblk * 32);
+    int *asum = (int *)(smem + (size_t)nblk * 32 + (size_t)nblk * 4);
+    const int K = p.K;
+    const int half = tid & 1;
+    const int e0 = tid * 16, e1 = (NT + tid) * 16;
+    // warps that hold part of the row (whole warps, so the pair shuffles and the named barrier see full warps)
+    const int nsw = min(NWARP, (K / 16 + 31) / 32);
+    if (warp < nsw) {
+        if (NORM) {
+            double ss = 0.0;
+#pragma unroll
+            for (int i = 0; i < 16; i++) ss += (double)__fmul_rn(r.x0[i], r.x0[i]); // float products, double sum
+            ss = warp_sum_d(ss);
+            if (lane == 0) red[warp] = ss;
+            asm volatile("bar.sync 1, %0;" ::"r"(nsw * 32) : "memory");
+            double t = 0.0;
+            for (int i = 0; i < nsw; i++) t += red[i];
+            const float rsf = rms_scale(t, p.norm_E, p.norm_eps);
+#pragma unroll
+            for (int i = 0; i < 16; i++) r.x0[i] = __fmul_rn(__fadd_rn(p.norm_adj, r.w[i]), __fmul_rn(rsf, r.x0[i])); // RMSNorm.java:50-52
+        }
+        quant_half_block(r.x0, aq, asc, asum, 0, nblk, e0 >> 5, half, e0 < K);
+        if (!NORM && K > NT * 16) quant_half_block(r.x1, aq, asc, asum, 0, nblk, e1 >> 5, half, e1 < K);
+    }
+    if (!NORM) {
+        // rows longer than two register tiles: the rest goes tile by tile (all warps)
+        const float *x0 = (const float *)p.a + p.a_col_off;
+        for (int e = (2 * NT + tid) * 16; e - tid * 16 < K; e += NT * 16) {
+            float x[16];
+            load16(x, x0 + e, e < K);
+            quant_half_block(x, aq, asc, asum, 0, nblk, e >> 5, half, e < K);
+        }
+    }
+    __syncthreads();
+}
+
+template <int MM>
+__device__ void stage_q8_pairs(const GemvParams &p, const bool norm, unsigned char *smem, const int nblk) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ double red[MM][GEMV_WARPS];
+    int8_t *aq = (int8_t *)smem;
+    float *asc = (float *)(smem + (size_t)MM * nblk * 32);
+    int *asum = (int *)(smem + (size_t)MM * nblk * 32 + (size_t)MM * nblk * 4);
+    const int K = p.K;
+    const int half = tid & 1;
+    const float *x0 = (const float *)p.a + p.a_col_off;
+
+    float rsf[MM];
+#pragma unroll
+    for (int m = 0; m < MM; m++) rsf[m] = 1.0f;
+    if (norm) {
+        double ss[MM];
+#pragma unroll
+        for (int m = 0; m < MM; m++) ss[m] = 0.0;
+        for (int e0 = tid * 16; e0 < K; e0 += 16 * GEMV_THREADS) {
+#pragma unroll
+            for (int m = 0; m < MM; m++) {
+                float x[16];
+                load16(x, x0 + (size_t)m * p.lda + e0, m < p.M);
+#pragma unroll
+                for (int i = 0; i < 16; i++) ss[m] += (double)__fmul_rn(x[i], x[i]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < MM; m++) {
+            ss[m] = warp_sum_d(ss[m]);
+            if (lane == 0) red[m][warp] = ss[m];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < MM; m++) {
+            double t = 0.0;
+#pragma unroll
+            for (int i = 0; i < GEMV_WARPS; i++) t += red[m][i];
+            t /= (double)p.norm_E;
+            t += (double)p.norm_eps;
+            rsf[m] = (float)(1.0 / sqrt(t));
+        }
+    }
+    // tiles of 16*GEMV_THREADS elements; the trip count is uniform so the pair shuffles see full warps
+    const int ntiles = (K + 16 * GEMV_THREADS - 1) / (16 * GEMV_THREADS);
+    for (int j = 0; j < ntiles; j++) {
+        const int e0 = j * 16 * GEMV_THREADS + tid * 16;
+        const bool in = e0 < K;
+        float w[16];
+        if (norm) load16_normw(w, p, e0, in);
+#pragma unroll
+        for (int m = 0; m < MM; m++) {
+            float x[16];
+            load16(x, x0 + (size_t)m * p.lda + e0, in && m < p.M);
+            if (norm) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) x[i] = __fmul_rn(__fadd_rn(p.norm_adj, w[i]), __fmul_rn(rsf[m], x[i]));
+            }
+            quant_half_block(x, aq, asc, asum, m, nblk, e0 >> 5, half, in);
+        }
+    }
+    __syncthreads();
+}
+
 // ---- per-chunk math -------------------------------------------------------------------------------
-template <int WDT, bool ACTQ8, int MM>
-__device__ __forceinline__ void compute_chunk(const WBuf<WDT> &w, float (&acc)[MM], const unsigned char *smem, int blk0,
+template <int WDT, bool ACTQ8, int MM, int CH>
+__device__ __forceinline__ void compute_chunk(const WBuf<WDT, CH> &w, float (&acc)[MM], const unsigned char *smem, int blk0,
                                               int nblk, int lane) {
     const int8_t *aq = (const int8_t *)smem;
     const float *asc = (const float *)(smem + (size_t)MM * nblk * 32);
@@ -306,110 +507,144 @@ __device__ __forceinline__ void compute_chunk(const WBuf<WDT> &w, float (&acc)[M
     }
 }
 
-template <int WDT, bool ACTQ8, int EPI, int MM>
-__global__ void __launch_bounds__(GEMV_THREADS, (MM == 1 && WDT == JL_Q4) ? 3 : (MM <= 2 ? 2 : 1)) gemv_kernel(const GemvParams p, const int prologue) {
+// End of an output row.
+template <int EPI, int MM>
+__device__ __forceinline__ void finish_row_fn(const GemvParams &p, int rr, int wrr, float (&acc)[MM], float (&gate)[MM]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int m = 0; m < MM; m++) acc[m] = warp_sum(acc[m]);
+    if (EPI == EPI_SILU_MUL && wrr == 0) {
+#pragma unroll
+        for (int m = 0; m < MM; m++) gate[m] = acc[m], acc[m] = 0.0f;
+        return;
+    }
+    if (lane == 0) {
+        int seg = 0, local = rr;
+        if (EPI != EPI_SILU_MUL) seg_lookup(p, rr, seg, local);
+        const GemvSeg &sg = p.seg[seg];
+        const int col = p.row0 + local + sg.out_off;
+#pragma unroll
+        for (int m = 0; m < MM; m++) {
+            if (m < p.M) {
+                float v = acc[m];
+                if (EPI == EPI_ADD_RESIDUAL) v = __fadd_rn(v, p.residual[(size_t)m * p.res_ld + (p.row0 + local)]);
+                if (EPI == EPI_SILU_MUL) v = __fmul_rn(silu_ref(gate[m]), v);
+                sg.out[(size_t)m * sg.out_ld + col] = v;
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < MM; m++) acc[m] = 0.0f;
+}
+
+// PRO >= 0: the prologue is fixed at compile time (the decode hot path: only that prologue's code is in the kernel);
+// PRO < 0: chosen at run time from `prologue`.
+// PRO >= 0: decode hot path, prologue fixed at compile time (PRO_F32_QUANT or PRO_RMSNORM_QUANT, M = 1, register staging);
+// PRO < 0: generic, prologue chosen at run time from `prologue_rt`.
+template <int WDT, bool ACTQ8, int EPI, int MM, int CH, int NBUF, int NT, int MINB, int PRO>
+__global__ void __launch_bounds__(NT, MINB) gemv_kernel(const GemvParams p, const int prologue_rt) {
     extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int NWARP = NT / 32;
+    constexpr bool HOT = PRO >= 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nblk = p.K / 32;
     const int nchunks = (nblk + 32 * CH - 1) / (32 * CH);
     constexpr int NW = (EPI == EPI_SILU_MUL) ? 2 : 1; // weight rows per output row
     const int wbytes_per_blk = (WDT == JL_Q4) ? 16 : 32;
+    ktrace_begin(p.trace, 0x100u | (unsigned)EPI | ((unsigned long long)(HOT ? PRO : prologue_rt) << 4) |
+                              ((unsigned long long)p.total_rows << 16) | ((unsigned long long)p.K << 40));
 
     // balanced static partition of output rows over all warps of the grid
-    const long long gw = (long long)blockIdx.x * GEMV_WARPS + warp;
-    const long long tw = (long long)gridDim.x * GEMV_WARPS;
+    const long long gw = (long long)blockIdx.x * NWARP + warp;
+    const long long tw = (long long)gridDim.x * NWARP;
     const int r0 = (int)(((long long)p.total_rows * gw) / tw);
     const int r1 = (int)(((long long)p.total_rows * (gw + 1)) / tw);
 
     // item iterator: (row r, weight-row wr, chunk c)
-    int r = r0, wr = 0, c = 0;
-    auto row_ptrs = [&](int rr, int wrr, const uint8_t *&wrow, const float *&srow) {
+    struct It {
+        int r, wr, c;
+    };
+    auto row_ptrs = [&](const It &it, const uint8_t *&wrow, const float *&srow) {
         int seg, local;
         if (EPI == EPI_SILU_MUL) {
-            seg = wrr;
-            local = rr;
+            seg = it.wr;
+            local = it.r;
         } else {
-            seg_lookup(p, rr, seg, local);
+            seg_lookup(p, it.r, seg, local);
         }
         const GemvSeg &sg = p.seg[seg];
         const size_t grow = (size_t)(p.row0 + local);
         wrow = (const uint8_t *)sg.w + (grow * (size_t)(p.ldw / 32) + (size_t)(p.w_col_off / 32)) * wbytes_per_blk;
         srow = sg.ws + grow * (size_t)(p.ldw / 32) + (size_t)(p.w_col_off / 32);
     };
-    auto advance = [&](int &rr, int &wrr, int &cc) {
-        if (++cc == nchunks) {
-            cc = 0;
-            if (++wrr == NW) {
-                wrr = 0;
-                ++rr;
+    auto advance = [&](It &it) {
+        if (++it.c == nchunks) {
+            it.c = 0;
+            if (++it.wr == NW) {
+                it.wr = 0;
+                ++it.r;
             }
         }
     };
 
-    WBuf<WDT> buf0, buf1;
+    // hot path: the hidden row is requested first, so it is not queued behind this SM's weight requests
+    StageRegs<PRO == PRO_RMSNORM_QUANT, NT> sr;
+    if (HOT) {
+        pdl_wait();
+        stage_q8_issue<PRO == PRO_RMSNORM_QUANT, NT>(p, sr);
+    }
+
+    WBuf<WDT, CH> buf[NBUF];
     const uint8_t *wrow;
     const float *srow;
-    if (r < r1) {
-        row_ptrs(r, wr, wrow, srow);
-        load_chunk<WDT>(buf0, wrow, srow, c * 32 * CH, nblk, lane);
+    It cur = {r0, 0, 0}, ld = cur;
+    // NBUF-1 chunks per warp go in flight now
+#pragma unroll
+    for (int b = 0; b < NBUF - 1; b++) {
+        if (ld.r < r1) {
+            row_ptrs(ld, wrow, srow);
+            load_chunk<WDT, CH>(buf[b], wrow, srow, ld.c * 32 * CH, nblk, lane);
+            advance(ld);
+        }
     }
-    // weights are in flight; let the next kernel in the stream start its own prefetch
     pdl_launch_dependents();
-    // activations are produced by the previous kernel
-    pdl_wait();
-    stage_activations<ACTQ8, MM>(p, prologue, smem, nblk);
+    ktrace_stamp(p.trace, 5, 0.f);
+    if (HOT) {
+        stage_q8_finish<PRO == PRO_RMSNORM_QUANT, NT>(p, sr, smem, nblk);
+    } else {
+        pdl_wait(); // activations are produced by the previous kernel
+        if (ACTQ8 && (prologue_rt == PRO_F32_QUANT || prologue_rt == PRO_RMSNORM_QUANT))
+            stage_q8_pairs<MM>(p, prologue_rt == PRO_RMSNORM_QUANT, smem, nblk);
+        else
+            stage_activations<ACTQ8, MM>(p, prologue_rt, smem, nblk);
+    }
+    ktrace_mid(p.trace);
 
     float acc[MM];
     float gate[MM];
 #pragma unroll
     for (int m = 0; m < MM; m++) acc[m] = 0.0f, gate[m] = 0.0f;
 
-    auto finish_row = [&](int rr, int wrr) {
+    while (cur.r < r1) {
 #pragma unroll
-        for (int m = 0; m < MM; m++) acc[m] = warp_sum(acc[m]);
-        if (EPI == EPI_SILU_MUL && wrr == 0) {
-#pragma unroll
-            for (int m = 0; m < MM; m++) gate[m] = acc[m], acc[m] = 0.0f;
-            return;
-        }
-        if (lane == 0) {
-            int seg = 0, local = rr;
-            if (EPI != EPI_SILU_MUL) seg_lookup(p, rr, seg, local);
-            const GemvSeg &sg = p.seg[seg];
-            const int col = p.row0 + local + sg.out_off;
-#pragma unroll
-            for (int m = 0; m < MM; m++) {
-                if (m < p.M) {
-                    float v = acc[m];
-                    if (EPI == EPI_ADD_RESIDUAL) v = __fadd_rn(v, p.residual[(size_t)m * p.res_ld + (p.row0 + local)]);
-                    if (EPI == EPI_SILU_MUL) v = __fmul_rn(silu_ref(gate[m]), v);
-                    sg.out[(size_t)m * sg.out_ld + col] = v;
+        for (int b = 0; b < NBUF; b++) {
+            if (cur.r < r1) {
+                if (ld.r < r1) {
+                    row_ptrs(ld, wrow, srow);
+                    load_chunk<WDT, CH>(buf[(b + NBUF - 1) % NBUF], wrow, srow, ld.c * 32 * CH, nblk, lane);
+                    advance(ld);
                 }
+                compute_chunk<WDT, ACTQ8, MM, CH>(buf[b], acc, smem, cur.c * 32 * CH, nblk, lane);
+                if (cur.r == r0 && cur.wr == 0 && cur.c == 0) ktrace_stamp(p.trace, 11, acc[0]);
+                if (cur.c == nchunks - 1) finish_row_fn<EPI, MM>(p, cur.r, cur.wr, acc, gate);
+                advance(cur);
             }
         }
-#pragma unroll
-        for (int m = 0; m < MM; m++) acc[m] = 0.0f;
-    };
-
-    while (r < r1) {
-        int nr = r, nwr = wr, nc = c;
-        advance(nr, nwr, nc);
-        if (nr < r1) {
-            row_ptrs(nr, nwr, wrow, srow);
-            load_chunk<WDT>(buf1, wrow, srow, nc * 32 * CH, nblk, lane);
-        }
-        compute_chunk<WDT, ACTQ8, MM>(buf0, acc, smem, c * 32 * CH, nblk, lane);
-        if (c == nchunks - 1) finish_row(r, wr);
-        r = nr, wr = nwr, c = nc;
-        if (r >= r1) break;
-        advance(nr, nwr, nc);
-        if (nr < r1) {
-            row_ptrs(nr, nwr, wrow, srow);
-            load_chunk<WDT>(buf0, wrow, srow, nc * 32 * CH, nblk, lane);
-        }
-        compute_chunk<WDT, ACTQ8, MM>(buf1, acc, smem, c * 32 * CH, nblk, lane);
-        if (c == nchunks - 1) finish_row(r, wr);
-        r = nr, wr = nwr, c = nc;
+    }
+    ktrace_stamp(p.trace, 12, acc[0]);
+    if (p.trace) {
+        __syncthreads();
+        ktrace_end(p.trace);
     }
 }
 
@@ -508,36 +743,62 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_dense_kernel(const GemvPara
 }
 
 // ---- host launcher ---------------------------------------------------------------------------------
-template <int WDT, bool ACTQ8, int EPI, int MM>
-static int launch_q(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int prologue, bool pdl, int grid, size_t smem) {
-    auto kern = gemv_kernel<WDT, ACTQ8, EPI, MM>;
-    if (smem > 40 * 1024) { // static shared memory of the prologue counts against the 48 KB default too
-        static thread_local size_t configured = 0; // per-instantiation high-water mark
-        if (smem > configured) {
-            JL_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
+template <typename KERN>
+static int launch_kern(jl_ctx *ctx, cudaStream_t stream, KERN kern, const GemvParams &p, int prologue, bool pdl, int grid,
+                       int threads, size_t smem, size_t &configured) {
+    if (smem > 40 * 1024 && smem > configured) { // static shared memory of the prologue counts against the 48 KB default too
+        JL_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
     }
-    JL_CUDA_CHECK(ctx, jl_launch_kernel(kern, dim3(grid), dim3(GEMV_THREADS), smem, stream, pdl, p, prologue));
+    JL_CUDA_CHECK(ctx, jl_launch_kernel(kern, dim3(grid), dim3(threads), smem, stream, pdl, p, prologue));
     ctx->launches++;
     return JL_OK;
 }
 
+// grid for the generic 256-thread kernels: a multiple of the SM count; every warp gets >= 1 row when possible
+static int generic_grid(jl_ctx *ctx, int rows, int max_per_sm) {
+    int per_sm = rows >= ctx->sm_count * GEMV_WARPS * 4 ? 3 : (rows >= ctx->sm_count * GEMV_WARPS * 2 ? 2 : 1);
+    if (per_sm > max_per_sm) per_sm = max_per_sm;
+    int grid = ctx->sm_count * per_sm;
+    const int max_grid = (rows + GEMV_WARPS - 1) / GEMV_WARPS;
+    if (grid > max_grid) grid = max_grid;
+    return grid < 1 ? 1 : grid;
+}
+
+template <int WDT, bool ACTQ8, int EPI, int MM>
+static int launch_q(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int prologue, bool pdl, size_t smem) {
+    if (WDT == JL_Q4 && ACTQ8 && MM == 1 && (prologue == PRO_F32_QUANT || prologue == PRO_RMSNORM_QUANT) &&
+        !(prologue == PRO_RMSNORM_QUANT && p.K > 16 * GEMV_THREADS_DECODE)) {
+        // decode hot path: one 768-thread CTA per SM, prologue fixed at compile time
+        constexpr int NT = GEMV_THREADS_DECODE;
+        int grid = ctx->sm_count;
+        const int max_grid = (p.total_rows + NT / 32 - 1) / (NT / 32);
+        if (grid > max_grid) grid = max_grid;
+        static thread_local size_t cfg_a = 0, cfg_b = 0;
+        if (prologue == PRO_F32_QUANT)
+            return launch_kern(ctx, stream, gemv_kernel<WDT, ACTQ8, EPI, 1, 4, 2, NT, 1, PRO_F32_QUANT>, p, prologue, pdl, grid, NT, smem, cfg_a);
+        return launch_kern(ctx, stream, gemv_kernel<WDT, ACTQ8, EPI, 1, 4, 2, NT, 1, PRO_RMSNORM_QUANT>, p, prologue, pdl, grid, NT, smem, cfg_b);
+    }
+    constexpr int MINB = (MM <= 2) ? 2 : 1;
+    static thread_local size_t cfg = 0;
+    return launch_kern(ctx, stream, gemv_kernel<WDT, ACTQ8, EPI, MM, 4, 2, GEMV_THREADS, MINB, -1>, p, prologue, pdl,
+                       generic_grid(ctx, p.total_rows, MINB), GEMV_THREADS, smem, cfg);
+}
+
 template <int WDT, bool ACTQ8, int EPI>
-static int launch_m(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int prologue, bool pdl, int grid, size_t smem1) {
-    if (p.M <= 1) return launch_q<WDT, ACTQ8, EPI, 1>(ctx, stream, p, prologue, pdl, grid, smem1);
-    if (p.M <= 2) return launch_q<WDT, ACTQ8, EPI, 2>(ctx, stream, p, prologue, pdl, grid, smem1 * 2);
-    if (p.M <= 4) return launch_q<WDT, ACTQ8, EPI, 4>(ctx, stream, p, prologue, pdl, grid, smem1 * 4);
-    return launch_q<WDT, ACTQ8, EPI, 8>(ctx, stream, p, prologue, pdl, grid, smem1 * 8);
+static int launch_m(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int prologue, bool pdl, size_t smem1) {
+    if (p.M <= 1) return launch_q<WDT, ACTQ8, EPI, 1>(ctx, stream, p, prologue, pdl, smem1);
+    if (p.M <= 2) return launch_q<WDT, ACTQ8, EPI, 2>(ctx, stream, p, prologue, pdl, smem1 * 2);
+    if (p.M <= 4) return launch_q<WDT, ACTQ8, EPI, 4>(ctx, stream, p, prologue, pdl, smem1 * 4);
+    return launch_q<WDT, ACTQ8, EPI, 8>(ctx, stream, p, prologue, pdl, smem1 * 8);
 }
 
 template <int WDT, bool ACTQ8>
-static int launch_e(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int prologue, int epi, bool pdl, int grid,
-                    size_t smem1) {
+static int launch_e(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int prologue, int epi, bool pdl, size_t smem1) {
     switch (epi) {
-        case EPI_STORE: return launch_m<WDT, ACTQ8, EPI_STORE>(ctx, stream, p, prologue, pdl, grid, smem1);
-        case EPI_ADD_RESIDUAL: return launch_m<WDT, ACTQ8, EPI_ADD_RESIDUAL>(ctx, stream, p, prologue, pdl, grid, smem1);
-        case EPI_SILU_MUL: return launch_m<WDT, ACTQ8, EPI_SILU_MUL>(ctx, stream, p, prologue, pdl, grid, smem1);
+        case EPI_STORE: return launch_m<WDT, ACTQ8, EPI_STORE>(ctx, stream, p, prologue, pdl, smem1);
+        case EPI_ADD_RESIDUAL: return launch_m<WDT, ACTQ8, EPI_ADD_RESIDUAL>(ctx, stream, p, prologue, pdl, smem1);
+        case EPI_SILU_MUL: return launch_m<WDT, ACTQ8, EPI_SILU_MUL>(ctx, stream, p, prologue, pdl, smem1);
     }
     return jl_set_error(ctx, JL_ERR_INVALID, "bad epilogue %d", epi);
 }
@@ -562,25 +823,14 @@ static int launch_dense_m(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p,
     return launch_dense<WDT, EPI, 8>(ctx, stream, p, prologue, pdl, grid);
 }
 
-int jl_launch_gemv(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int prologue, int epilogue, bool use_pdl) {
+int jl_launch_gemv(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p_in, int prologue, int epilogue, bool use_pdl) {
+    GemvParams p = p_in;
+    p.trace = jl_ktrace_slot(ctx);
     if (p.M < 1 || p.M > GEMV_MAX_M) return jl_set_error(ctx, JL_ERR_INVALID, "gemv: M=%d out of range", p.M);
     if (p.K <= 0 || p.total_rows <= 0) return jl_set_error(ctx, JL_ERR_INVALID, "gemv: empty problem");
     const bool quant_w = (p.w_dtype == JL_Q4 || p.w_dtype == JL_I8);
     const int rows = p.total_rows;
-    // grid: a multiple of the SM count; every warp gets >= 1 row when possible
-    int per_sm = rows >= ctx->sm_count * GEMV_WARPS * 4 ? 3 : (rows >= ctx->sm_count * GEMV_WARPS * 2 ? 2 : 1);
-    {
-        static int forced = -1;
-        if (forced < 0) {
-            const char *e = getenv("JL_GEMV_PER_SM");
-            forced = e ? atoi(e) : 0;
-        }
-        if (forced > 0 && per_sm > forced) per_sm = forced;
-    }
-    int grid = ctx->sm_count * per_sm;
-    int max_grid = (rows + GEMV_WARPS - 1) / GEMV_WARPS;
-    if (grid > max_grid) grid = max_grid;
-    if (grid < 1) grid = 1;
+    const int grid = generic_grid(ctx, rows, 3);
 
     if (!quant_w) {
         if (prologue != PRO_F32 && prologue != PRO_RMSNORM_F32 && prologue != PRO_BF16_GLOBAL)
@@ -601,8 +851,8 @@ int jl_launch_gemv(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int pr
     if (smem1 * mm > 200 * 1024)
         return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "gemv: activations (M=%d,K=%d) exceed shared memory", p.M, p.K);
     if (p.w_dtype == JL_Q4)
-        return actq8 ? launch_e<JL_Q4, true>(ctx, stream, p, prologue, epilogue, use_pdl, grid, smem1)
-                     : launch_e<JL_Q4, false>(ctx, stream, p, prologue, epilogue, use_pdl, grid, smem1);
-    return actq8 ? launch_e<JL_I8, true>(ctx, stream, p, prologue, epilogue, use_pdl, grid, smem1)
-                 : launch_e<JL_I8, false>(ctx, stream, p, prologue, epilogue, use_pdl, grid, smem1);
+        return actq8 ? launch_e<JL_Q4, true>(ctx, stream, p, prologue, epilogue, use_pdl, smem1)
+                     : launch_e<JL_Q4, false>(ctx, stream, p, prologue, epilogue, use_pdl, smem1);
+    return actq8 ? launch_e<JL_I8, true>(ctx, stream, p, prologue, epilogue, use_pdl, smem1)
+                 : launch_e<JL_I8, false>(ctx, stream, p, prologue, epilogue, use_pdl, smem1);
 }

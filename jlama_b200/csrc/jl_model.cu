@@ -11,6 +11,7 @@
 #include <chrono>
 #include <map>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -819,16 +820,32 @@ extern "C" int jl_model_decode(jl_model *m, int n, const int32_t *sessions, cons
         hp[m->maxB + i] = positions[i];
         hp[2 * m->maxB + i] = sessions[i];
     }
+    static const bool dbg_timing = getenv("JL_DEBUG_TIMING") != nullptr;
+    auto c0 = std::chrono::steady_clock::now();
     JL_CUDA_CHECK(ctx, cudaEventRecord(m->ev_begin, m->stream));
     JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_tokens, hp, (size_t)n * 4, cudaMemcpyHostToDevice, m->stream));
     JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_positions, hp + m->maxB, (size_t)n * 4, cudaMemcpyHostToDevice, m->stream));
     JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_sessions, hp + 2 * m->maxB, (size_t)n * 4, cudaMemcpyHostToDevice, m->stream));
+    auto c1 = std::chrono::steady_clock::now();
     M_CHECK(run_decode(m, n, max_pos, false));
+    auto c2 = std::chrono::steady_clock::now();
     JL_CUDA_CHECK(ctx, cudaMemcpyAsync(hp + 3 * m->maxB, m->d_next, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
     if (logits_out)
         JL_CUDA_CHECK(ctx, cudaMemcpyAsync(logits_out, m->logits, (size_t)n * m->cfg.vocab_size * 4, cudaMemcpyDeviceToHost, m->stream));
     JL_CUDA_CHECK(ctx, cudaEventRecord(m->ev_end, m->stream));
+    auto c3 = std::chrono::steady_clock::now();
     JL_CUDA_CHECK(ctx, cudaStreamSynchronize(m->stream));
+    auto c4 = std::chrono::steady_clock::now();
+    if (dbg_timing) {
+        static int calls = 0;
+        if ((++calls % 32) == 0) {
+            auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+            float gms = 0;
+            cudaEventElapsedTime(&gms, m->ev_begin, m->ev_end);
+            fprintf(stderr, "[decode] h2d-enqueue %.1f us, launch %.1f us, d2h-enqueue %.1f us, sync-wait %.1f us, gpu(events) %.1f us\n",
+                    us(c0, c1), us(c1, c2), us(c2, c3), us(c3, c4), gms * 1000.0);
+        }
+    }
     for (int i = 0; i < n; i++) next_tokens[i] = hp[3 * m->maxB + i];
     float ms = 0;
     cudaEventElapsedTime(&ms, m->ev_begin, m->ev_end);

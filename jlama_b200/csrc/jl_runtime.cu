@@ -679,3 +679,40 @@ extern "C" int jl_debug_gemm_tc_bench(jl_ctx *ctx, int64_t b_id, int t, int iter
     *avg_us = (double)ms * 1000.0 / iters;
     return JL_OK;
 }
+
+// ---- kernel timeline diagnostics ---------------------------------------------------------------------------------------
+// capacity > 0: allocate [capacity][4] stamps and hand one slot to every traced launch from now on (graphs captured
+// afterwards keep their slots, every replay re-stamps them); capacity == 0: stop tracing.
+extern "C" int jl_debug_ktrace(jl_ctx *ctx, int capacity) {
+    if (!ctx || capacity < 0) return JL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    if (ctx->ktrace) cudaFree(ctx->ktrace);
+    ctx->ktrace = nullptr, ctx->ktrace_cap = 0, ctx->ktrace_n = 0;
+    if (capacity == 0) return JL_OK;
+    JL_CUDA_CHECK(ctx, cudaMalloc(&ctx->ktrace, (size_t)capacity * KTRACE_WORDS * 8));
+    ctx->ktrace_cap = capacity;
+    return jl_debug_ktrace_clear(ctx);
+}
+static __global__ void ktrace_clear_kernel(unsigned long long *t, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        t[(size_t)KTRACE_WORDS * i] = ~0ull;
+        for (int j = 1; j < KTRACE_WORDS; j++) t[(size_t)KTRACE_WORDS * i + j] = 0;
+    }
+}
+extern "C" int jl_debug_ktrace_clear(jl_ctx *ctx) {
+    if (!ctx || !ctx->ktrace) return JL_ERR_INVALID;
+    JL_CUDA_CHECK(ctx, cudaDeviceSynchronize());
+    ktrace_clear_kernel<<<(ctx->ktrace_cap + 255) / 256, 256>>>(ctx->ktrace, ctx->ktrace_cap);
+    JL_CUDA_CHECK(ctx, cudaDeviceSynchronize());
+    return JL_OK;
+}
+// copies min(slots handed out, max_slots) * 16 words to `out`; returns the number of slots, or < 0
+extern "C" int jl_debug_ktrace_read(jl_ctx *ctx, uint64_t *out, int max_slots) {
+    if (!ctx || !ctx->ktrace || !out) return JL_ERR_INVALID;
+    const int n = ctx->ktrace_n < max_slots ? ctx->ktrace_n : max_slots;
+    if (cudaDeviceSynchronize() != cudaSuccess) return JL_ERR_CUDA;
+    if (n > 0 && cudaMemcpy(out, ctx->ktrace, (size_t)n * KTRACE_WORDS * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return JL_ERR_CUDA;
+    return n;
+}

@@ -55,6 +55,9 @@ SIGNATURES = {
     "jl_version": (C.c_char_p, []),
     "jl_sync": (_i, [_vp]),
     "jl_kernel_launches": (_i64, [_vp]),
+    "jl_debug_ktrace": (_i, [_vp, _i]),
+    "jl_debug_ktrace_clear": (_i, [_vp]),
+    "jl_debug_ktrace_read": (_i, [_vp, C.POINTER(C.c_uint64), _i]),
     "jl_debug_gemv_bench": (_i, [_vp, _i64, _i, _i, _i, _i, _i, C.POINTER(_d)]),
     "jl_debug_gemm_tc_bench": (_i, [_vp, _i64, _i, _i, C.POINTER(_d)]),
     "jl_register_tensor": (_i64, [_vp, _i, _i64, _i64, _vp, _vp]),

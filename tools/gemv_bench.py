@@ -15,13 +15,16 @@ SHAPES = [("qkv 8B", 6144, 4096), ("o 8B", 4096, 4096), ("gate 8B", 14336, 4096)
 
 
 def main():
+    quick = "--quick" in sys.argv  # M=1, no PDL, 8B shapes only: for comparing JL_GEMV_CFG / JL_GEMV_AHEAD variants
+    tag = "cfg=%s ahead=%s per_sm=%s" % (os.environ.get("JL_GEMV_CFG", "0"), os.environ.get("JL_GEMV_AHEAD", "0"),
+                                        os.environ.get("JL_GEMV_PER_SM", "-"))
     peak = 6563.9
     if os.path.exists("MEASURED_PEAKS.json"):
         peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"]
     ctx = native.Context(0)
     rng = np.random.default_rng(0)
     rows_out = []
-    for name, n, k in SHAPES:
+    for name, n, k in (SHAPES[:5] if quick else SHAPES):
         reps = max(1, int(400e6 // (n * k * 0.625)) + 1)  # > 3x L2 of distinct weights
         if n * reps > 400000:
             reps = max(1, 400000 // n)
@@ -29,16 +32,19 @@ def main():
         s = ((0.5 + rng.random((n * reps, k // 32))) * 0.004).astype(np.float32)
         tid = ctx.lib.jl_register_tensor(ctx.h, native.Q4, n * reps, k, native.ptr(q), native.ptr(s))
         assert tid > 0
-        for m in (1, 4):
+        for m in ((1,) if quick else (1, 4)):
             for mode, mname in ((0, "q8"), (1, "norm+q8"), (2, "f32")):
                 if mode == 2 and m * k * 4 > 190 * 1024:
                     continue
-                for pdl in (0, 1):
+                if quick and mode == 2 and n < 100000:
+                    continue
+                for pdl in ((0,) if quick else (0, 1)):
                     us = C.c_double()
                     ctx.check(ctx.lib.jl_debug_gemv_bench(ctx.h, tid, n, m, mode, 200, pdl, C.byref(us)))
                     gbs = n * k * 0.625 / 1e9 / (us.value * 1e-6)
                     rows_out.append((name, n, k, m, mname, pdl, us.value, gbs, gbs / peak))
-                    print("%-11s N=%6d K=%5d M=%d %-8s pdl=%d  %8.2f us  %7.1f GB/s  %.3f of measured peak" % rows_out[-1], flush=True)
+                    print(("[%s] " % tag if quick else "") +
+                          "%-11s N=%6d K=%5d M=%d %-8s pdl=%d  %8.2f us  %7.1f GB/s  %.3f of measured peak" % rows_out[-1], flush=True)
         ctx.check(ctx.lib.jl_unregister_tensor(ctx.h, tid))
     ctx.close()
 
