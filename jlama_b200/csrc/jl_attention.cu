@@ -301,7 +301,7 @@ int jl_launch_paged_attention(jl_ctx *ctx, cudaStream_t s, const AttnParams &p, 
 // For decode steps every row is a different session, so a (row, kv head, split) task can append the row's own
 // K/V and attend in the same kernel (no separate rope_kv_append launch).  grid = (kv_heads, rows, splits).
 #define FDA_THREADS 256
-template <int HS>
+template <int HS, int KVDT>
 __global__ void __launch_bounds__(FDA_THREADS) fused_decode_attention_kernel(const AttnTask t, const int layer,
                                                                               unsigned *done_cnt, unsigned long long *trace) {
     ktrace_begin(trace, 0xA00u | (unsigned long long)t.splits << 16);
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(FDA_THREADS) fused_decode_attention_kernel(con
     extern __shared__ __align__(16) unsigned char fda_smem[];
     __shared__ int s_last;
     const int kvh = blockIdx.x, m = blockIdx.y, split = blockIdx.z;
-    attention_task<HS, FDA_THREADS>(t, layer, m, kvh, split, fda_smem);
+    attention_task<HS, FDA_THREADS, KVDT>(t, layer, m, kvh, split, fda_smem);
     if (t.splits > 1) {
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -331,19 +331,25 @@ __global__ void __launch_bounds__(FDA_THREADS) fused_decode_attention_kernel(con
     }
 }
 
-template <int HS>
-static int launch_fda(jl_ctx *ctx, cudaStream_t s, const AttnTask &t, int layer, int rows, unsigned *done_cnt, bool pdl) {
+template <int HS, int KVDT>
+static int launch_fda_k(jl_ctx *ctx, cudaStream_t s, const AttnTask &t, int layer, int rows, unsigned *done_cnt, bool pdl) {
     const size_t smem = attention_task_smem<HS, FDA_THREADS>();
     static bool configured = false;
     if (!configured && smem > 40 * 1024) {
-        JL_CUDA_CHECK(ctx, cudaFuncSetAttribute(fused_decode_attention_kernel<HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        JL_CUDA_CHECK(ctx, cudaFuncSetAttribute(fused_decode_attention_kernel<HS, KVDT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     unsigned long long *trace = jl_ktrace_slot(ctx);
-    JL_CUDA_CHECK(ctx, jl_launch_kernel(fused_decode_attention_kernel<HS>, dim3(t.kv_heads, rows, t.splits), dim3(FDA_THREADS), smem, s,
-                                        pdl, t, layer, done_cnt, trace));
+    JL_CUDA_CHECK(ctx, jl_launch_kernel(fused_decode_attention_kernel<HS, KVDT>, dim3(t.kv_heads, rows, t.splits), dim3(FDA_THREADS), smem,
+                                        s, pdl, t, layer, done_cnt, trace));
     ctx->launches++;
     return JL_OK;
+}
+
+template <int HS>
+static int launch_fda(jl_ctx *ctx, cudaStream_t s, const AttnTask &t, int layer, int rows, unsigned *done_cnt, bool pdl) {
+    if (t.kv.kv_dtype == JL_F32) return launch_fda_k<HS, JL_F32>(ctx, s, t, layer, rows, done_cnt, pdl);
+    return launch_fda_k<HS, JL_BF16>(ctx, s, t, layer, rows, done_cnt, pdl);
 }
 
 int jl_launch_fused_decode_attention(jl_ctx *ctx, cudaStream_t s, const AttnParams &p, unsigned *done_cnt, bool use_pdl) {

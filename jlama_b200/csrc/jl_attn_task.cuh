@@ -18,6 +18,10 @@ struct AttnTask {
     const int32_t *sessions, *positions;
 };
 
+// softmax exponent exactly as the reference computes it: (float)Math.exp((double)x) (one out-of-line copy: the double exp
+// is ~150 instructions and the attention kernel starts with a cold instruction cache every layer)
+static __device__ __noinline__ float exp_ref(float x) { return (float)exp((double)x); }
+
 template <int NT>
 __device__ __forceinline__ void task_bar() {
     asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
@@ -53,7 +57,8 @@ __device__ __forceinline__ uint16_t mg_bf16(float n) {
 // Latency plan: the RoPE inputs, the KV append and the first K/V tile are all requested before the first
 // barrier; the next tile is prefetched into registers while the current one is processed; the row of the
 // current position is taken from shared memory (never re-read from the page it was just written to).
-template <int HS, int NT>
+// KVDT: JL_F32 / JL_BF16 fix the page element type at compile time (half the fetch / append code); -1 = run time.
+template <int HS, int NT, int KVDT = -1>
 __device__ void attention_task(const AttnTask &P, int layer, int m, int kvh, int split, unsigned char *u) {
     constexpr int C4 = HS / 4;
     constexpr int PARTS = NT / HS; // P.V position groups
@@ -77,20 +82,34 @@ __device__ void attention_task(const AttnTask &P, int layer, int m, int kvh, int
     const int per = (((n + S - 1) / S) + MG_ATT_TILE - 1) / MG_ATT_TILE * MG_ATT_TILE;
     const int t0 = split * per, t1 = min(n, t0 + per);
     const int hp = HS / 2;
-    const int h0 = kvh * group, xoff = kvh * HS, dt = P.kv.kv_dtype;
+    const int h0 = kvh * group, xoff = kvh * HS, dt = KVDT >= 0 ? KVDT : P.kv.kv_dtype;
     const size_t poffset = (size_t)pos * hp;
     const bool owner = pos >= t0 && pos < t1;
 
+    // page addressing (KvBufferCache.java:160-199 geometry): the layer split is fixed for the task, the context split is
+    // resolved once per tile (a tile of consecutive positions touches at most two pages when ctx_per_page >= TILE)
+    const int lpage = layer / P.kv.layers_per_page, rlayer = layer - lpage * P.kv.layers_per_page;
+    const size_t esz = dt == JL_F32 ? 4 : 2;
+    const size_t v_off = (size_t)P.kv.ctx_per_page * P.kv.kv_len * esz;          // K block -> V block of the same layer
+    const size_t layer_off = (size_t)rlayer * 2 * P.kv.ctx_per_page * P.kv.kv_len * esz;
+    char *const *ptab = (char *const *)P.kv.page_table + ((size_t)session * P.kv.n_layer_pages + lpage) * P.kv.n_ctx_pages;
+    auto k_row = [&](int position) -> char * { // one division: used for single rows only
+        const int cp = position / P.kv.ctx_per_page, rc = position - cp * P.kv.ctx_per_page;
+        return ptab[cp] + layer_off + (size_t)rc * P.kv.kv_len * esz;
+    };
     float4 kreg[NF], vreg[NF];
     auto fetch_tile = [&](int tb) {
+        const int cp0 = tb / P.kv.ctx_per_page, rc0 = tb - cp0 * P.kv.ctx_per_page;
 #pragma unroll
         for (int i = 0; i < NF; i++) {
             const int f = tid + i * NT;
             const int r = f / C4, c4 = f % C4;
             kreg[i] = make_float4(0.f, 0.f, 0.f, 0.f), vreg[i] = kreg[i];
             if (f < MG_ATT_TILE * C4 && tb + r < t1 && tb + r != pos) {
-                const char *kr = mg_kv_row(P.kv, session, layer, tb + r, 0);
-                const char *vr = mg_kv_row(P.kv, session, layer, tb + r, 1);
+                int cp = cp0, rc = rc0 + r;
+                while (rc >= P.kv.ctx_per_page) rc -= P.kv.ctx_per_page, cp++;
+                const char *kr = ptab[cp] + layer_off + (size_t)rc * P.kv.kv_len * esz;
+                const char *vr = kr + v_off;
                 if (dt == JL_F32) {
                     kreg[i] = __ldcg((const float4 *)((const float *)kr + xoff + c4 * 4));
                     vreg[i] = __ldcg((const float4 *)((const float *)vr + xoff + c4 * 4));
@@ -126,8 +145,8 @@ __device__ void attention_task(const AttnTask &P, int layer, int m, int kvh, int
             const float v0 = __ldcg(vr + j), v1 = __ldcg(vr + j + hp);
             float r0 = __fsub_rn(__fmul_rn(k0, f.x), __fmul_rn(k1, f.y));
             float r1 = __fadd_rn(__fmul_rn(k0, f.y), __fmul_rn(k1, f.x));
-            char *krow = (char *)mg_kv_row(P.kv, session, layer, pos, 0);
-            char *vrow = (char *)mg_kv_row(P.kv, session, layer, pos, 1);
+            char *krow = k_row(pos);
+            char *vrow = krow + v_off;
             if (dt == JL_F32) {
                 ((float *)krow)[xoff + j] = r0, ((float *)krow)[xoff + j + hp] = r1;
                 ((float *)vrow)[xoff + j] = v0, ((float *)vrow)[xoff + j + hp] = v1;
@@ -195,11 +214,11 @@ __device__ void attention_task(const AttnTask &P, int layer, int m, int kvh, int
             const float s0 = ps[lane * MG_MAX_GROUP + h];
             const float m_old = hm[h];
             const float m_new = fmaxf(m_old, warp_max(s0));
-            const float e0 = s0 == -INFINITY ? 0.0f : (float)exp((double)__fsub_rn(s0, m_new));
+            const float e0 = s0 == -INFINITY ? 0.0f : exp_ref(__fsub_rn(s0, m_new));
             const float ts = warp_sum(e0);
             ps[lane * MG_MAX_GROUP + h] = e0;
             if (lane == 0) {
-                const float corr = m_old == -INFINITY ? 0.0f : (float)exp((double)__fsub_rn(m_old, m_new));
+                const float corr = m_old == -INFINITY ? 0.0f : exp_ref(__fsub_rn(m_old, m_new));
                 hc[h] = corr, hm[h] = m_new, hl[h] = fmaf(hl[h], corr, ts);
             }
         }
@@ -247,7 +266,7 @@ __device__ void attention_merge(const AttnTask &P, int m, int kvh) {
         for (int s = 0; s < S; s++) {
             const float ms = __ldcg(w + s * (HS + 2) + HS);
             if (ms == -INFINITY) continue;
-            const float f = (float)exp((double)__fsub_rn(ms, M));
+            const float f = exp_ref(__fsub_rn(ms, M));
             num = fmaf(__ldcg(w + s * (HS + 2) + d), f, num);
             den = fmaf(__ldcg(w + s * (HS + 2) + HS + 1), f, den);
         }

@@ -96,6 +96,7 @@ struct GemvParams {
     int norm_w_dtype;
     float norm_adj, norm_eps;
     int norm_E;
+    double norm_inv_E;       // filled by jl_launch_gemv
     // epilogue
     const float *residual;   // [M, res_ld]
     int res_ld;
@@ -214,6 +215,39 @@ __device__ __forceinline__ float ldg_nc_f32(const float *p) {
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
     return r;
 }
+// Loads that should stay in L2 across decode steps (norm weights: 16 KB per layer, re-read every token but otherwise
+// flushed by the 4.7 GB weight stream in between): L2 evict_last policy.
+__device__ __forceinline__ unsigned long long l2_evict_last_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint4 ldg_keep_u4(const void *p, unsigned long long pol) {
+    uint4 r;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+// The decode weight stream (4.7 GB per token through a 126 MB L2) is tagged evict_first, so that it recycles its own
+// lines instead of flushing what the step re-reads: activations, KV pages, RoPE and norm tables -- and kernel code.
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint4 ldg_stream_u4(const void *p, unsigned long long pol) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ float ldg_stream_f32(const float *p, unsigned long long pol) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
+    return r;
+}
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -231,7 +265,7 @@ __device__ __forceinline__ void ktrace_begin(unsigned long long *t, unsigned lon
 __device__ __forceinline__ void ktrace_stamp(unsigned long long *t, int idx, float dep) {
     if (t && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
         unsigned long long now;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) : "f"(dep));
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) : "f"(dep) : "memory");
         t[idx] = now;
     }
 }

@@ -13,18 +13,17 @@
 // request), activations are staged once per CTA in shared memory in a bank-conflict-free
 // [half][block][16B] layout, integer dot products use dp4a, the reduction is a warp shuffle.
 //
-// Decode shape of the kernel (M = 1, Q4 weights, Q8 activations; DESIGN.md "GEMV v3"): ONE 768-thread CTA per SM.
-// A B200 SM keeps about 64 KB of loads in flight, which 24 warps x one 2.5 KB chunk already fill, so more CTAs per SM
-// only repeat the prologue: with three 256-thread CTAs the RMSNorm + Q8 quantisation ran three times per SM and its
-// loads queued behind the 60 KB of weight requests (5 us of a 8.6 us QKV launch, tools/ktrace.py).  Here the first
-// warps ("stagers") request the hidden row BEFORE any weight load, every warp then puts its first weight chunk in
+// Decode shape of the kernel (M = 1, Q4 weights, Q8 activations; DESIGN.md "GEMV v3"): ONE 512-thread CTA per SM with
+// a three-deep register ring (two 2.5 KB chunks per warp = 80 KB per SM in flight; a B200 SM sustains about 64 KB).
+// More CTAs per SM only repeat the prologue: with three 256-thread CTAs the RMSNorm + Q8 quantisation ran three times
+// per SM and its loads queued behind the weight requests (5 us of a 8.6 us QKV launch, tools/ktrace.py).  Here the
+// first warps ("stagers") request the hidden row BEFORE any weight load, every warp then puts its first chunks in
 // flight, and the stagers normalise / quantise into shared memory while the weights stream.
 #include "jl_common.cuh"
 #include <stdlib.h>
 
 #define GEMV_THREADS 256 // generic kernels
 #define GEMV_WARPS 8
-#define GEMV_THREADS_DECODE 768 // decode hot path: one CTA per SM
 // CH = 32-element blocks per lane per chunk (a chunk is CH*32 blocks = CH*1024 weights of one row), NBUF = register
 // chunk buffers per warp (NBUF-1 chunks are in flight while one is being consumed)
 
@@ -55,18 +54,18 @@ __device__ __forceinline__ void seg_lookup(const GemvParams &p, int row, int &se
 
 template <int WDT, int CH>
 __device__ __forceinline__ void load_chunk(WBuf<WDT, CH> &b, const uint8_t *wrow, const float *srow, int blk0, int nblk,
-                                           int lane) {
+                                           int lane, unsigned long long pol) {
 #pragma unroll
     for (int j = 0; j < CH; j++) {
         int bi = blk0 + j * 32 + lane;
         if (bi < nblk) {
             if (WDT == JL_Q4) {
-                b.q[j] = ldg_nc_u4(wrow + (size_t)bi * 16);
+                b.q[j] = ldg_stream_u4(wrow + (size_t)bi * 16, pol);
             } else {
-                b.q[2 * j] = ldg_nc_u4(wrow + (size_t)bi * 32);
-                b.q[2 * j + 1] = ldg_nc_u4(wrow + (size_t)bi * 32 + 16);
+                b.q[2 * j] = ldg_stream_u4(wrow + (size_t)bi * 32, pol);
+                b.q[2 * j + 1] = ldg_stream_u4(wrow + (size_t)bi * 32 + 16, pol);
             }
-            b.s[j] = ldg_nc_f32(srow + bi);
+            b.s[j] = ldg_stream_f32(srow + bi, pol);
         }
     }
 }
@@ -271,11 +270,12 @@ __device__ __forceinline__ void load16(float (&v)[16], const float *src, bool in
     }
 }
 __device__ __forceinline__ void load16_normw(float (&v)[16], const GemvParams &p, int e0, bool in) {
+    const unsigned long long pol = l2_evict_last_policy();
     if (p.norm_w_dtype == JL_BF16) {
         const uint4 *src = (const uint4 *)((const uint16_t *)p.norm_w + e0);
 #pragma unroll
         for (int i = 0; i < 2; i++) {
-            const uint4 u = in ? src[i] : make_uint4(0, 0, 0, 0);
+            const uint4 u = in ? ldg_keep_u4(src + i, pol) : make_uint4(0, 0, 0, 0);
             const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
             for (int t = 0; t < 4; t++) {
@@ -284,53 +284,57 @@ __device__ __forceinline__ void load16_normw(float (&v)[16], const GemvParams &p
             }
         }
     } else {
-        load16(v, (const float *)p.norm_w + e0, in);
+        const uint4 *src = (const uint4 *)((const float *)p.norm_w + e0);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint4 u = in ? ldg_keep_u4(src + i, pol) : make_uint4(0, 0, 0, 0);
+            v[i * 4] = __uint_as_float(u.x), v[i * 4 + 1] = __uint_as_float(u.y);
+            v[i * 4 + 2] = __uint_as_float(u.z), v[i * 4 + 3] = __uint_as_float(u.w);
+        }
     }
 }
 
-// RMSNorm.java:41-52 scale factor from the double sum of float squares.  rsqrt() is the correctly rounded double
-// reciprocal square root to within 1 ulp(double); after the cast to float it equals (float)(1.0 / sqrt(t)).
-__device__ __forceinline__ float rms_scale(double sumsq, int E, float eps) {
-    double t = sumsq / (double)E;
+// RMSNorm.java:41-52 scale factor from the double sum of float squares.  inv_E = 1.0 / E (exact for the power-of-two
+// embedding lengths of every Llama-family model; otherwise within 1 ulp(double) of the division, far below float
+// resolution).  rsqrt() is within 1 ulp(double) of 1.0 / sqrt(t); after the cast to float the two agree.
+__device__ __forceinline__ float rms_scale(double sumsq, double inv_E, float eps) {
+    double t = sumsq * inv_E;
     t += (double)eps;
     return (float)rsqrt(t);
 }
 
-// Stagers = the first ceil(K/16/32) warps (at most all of them).  `xr`/`wr` were loaded by stage_q8_issue() before the
-// weight loads were queued.  NT = threads per CTA.  Up to two 16*NT tiles of the row live in registers.
-template <bool NORM, int NT>
+// Stagers = the first ceil(K/16/32) warps (at most all of them).  The registers were loaded by stage_q8_issue() before
+// the weight loads were queued.  NT = threads per CTA.  LONG (K > 16*NT, no norm): a second register tile and a tail loop.
+template <bool NORM, bool LONG>
 struct StageRegs {
-    float x0[16], x1[16], w[16];
+    float x0[16], x1[LONG ? 16 : 1], w[NORM ? 16 : 1];
 };
 
-template <bool NORM, int NT>
-__device__ __forceinline__ void stage_q8_issue(const GemvParams &p, StageRegs<NORM, NT> &r) {
+template <bool NORM, bool LONG, int NT>
+__device__ __forceinline__ void stage_q8_issue(const GemvParams &p, StageRegs<NORM, LONG> &r) {
     const int tid = threadIdx.x;
     const float *x0 = (const float *)p.a + p.a_col_off;
-    const int e0 = tid * 16, e1 = (NT + tid) * 16;
+    const int e0 = tid * 16;
     load16(r.x0, x0 + e0, e0 < p.K);
-    if (NORM) {
-        load16_normw(r.w, p, e0, e0 < p.K);
-    } else {
-        load16(r.x1, x0 + e1, e1 < p.K);
-    }
+    if constexpr (NORM) load16_normw(r.w, p, e0, e0 < p.K);
+    if constexpr (LONG) load16(r.x1, x0 + (NT + tid) * 16, (NT + tid) * 16 < p.K);
 }
 
-template <bool NORM, int NT>
-__device__ __forceinline__ void stage_q8_finish(const GemvParams &p, StageRegs<NORM, NT> &r, unsigned char *smem, const int nblk) {
+template <bool NORM, bool LONG, int NT>
+__device__ __forceinline__ void stage_q8_finish(const GemvParams &p, StageRegs<NORM, LONG> &r, unsigned char *smem, const int nblk) {
     constexpr int NWARP = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __shared__ double red[NWARP];
+    __shared__ double red[NORM ? NWARP : 1];
     int8_t *aq = (int8_t *)smem;
     float *asc = (float *)(smem + (size_t)nblk * 32);
     int *asum = (int *)(smem + (size_t)nblk * 32 + (size_t)nblk * 4);
     const int K = p.K;
     const int half = tid & 1;
-    const int e0 = tid * 16, e1 = (NT + tid) * 16;
+    const int e0 = tid * 16;
     // warps that hold part of the row (whole warps, so the pair shuffles and the named barrier see full warps)
     const int nsw = min(NWARP, (K / 16 + 31) / 32);
     if (warp < nsw) {
-        if (NORM) {
+        if constexpr (NORM) {
             double ss = 0.0;
 #pragma unroll
             for (int i = 0; i < 16; i++) ss += (double)__fmul_rn(r.x0[i], r.x0[i]); // float products, double sum
@@ -339,20 +343,20 @@ __device__ __forceinline__ void stage_q8_finish(const GemvParams &p, StageRegs<N
             asm volatile("bar.sync 1, %0;" ::"r"(nsw * 32) : "memory");
             double t = 0.0;
             for (int i = 0; i < nsw; i++) t += red[i];
-            const float rsf = rms_scale(t, p.norm_E, p.norm_eps);
+            const float rsf = rms_scale(t, p.norm_inv_E, p.norm_eps);
 #pragma unroll
             for (int i = 0; i < 16; i++) r.x0[i] = __fmul_rn(__fadd_rn(p.norm_adj, r.w[i]), __fmul_rn(rsf, r.x0[i])); // RMSNorm.java:50-52
         }
         quant_half_block(r.x0, aq, asc, asum, 0, nblk, e0 >> 5, half, e0 < K);
-        if (!NORM && K > NT * 16) quant_half_block(r.x1, aq, asc, asum, 0, nblk, e1 >> 5, half, e1 < K);
     }
-    if (!NORM) {
-        // rows longer than two register tiles: the rest goes tile by tile (all warps)
+    if constexpr (LONG) {
+        // second register tile, then the rest of the row tile by tile (uniform trip count: all warps)
+        const int e1 = (NT + tid) * 16;
+        quant_half_block(r.x1, aq, asc, asum, 0, nblk, e1 >> 5, half, e1 < K);
         const float *x0 = (const float *)p.a + p.a_col_off;
         for (int e = (2 * NT + tid) * 16; e - tid * 16 < K; e += NT * 16) {
-            float x[16];
-            load16(x, x0 + e, e < K);
-            quant_half_block(x, aq, asc, asum, 0, nblk, e >> 5, half, e < K);
+            load16(r.x1, x0 + e, e < K);
+            quant_half_block(r.x1, aq, asc, asum, 0, nblk, e >> 5, half, e < K);
         }
     }
     __syncthreads();
@@ -537,26 +541,21 @@ __device__ __forceinline__ void finish_row_fn(const GemvParams &p, int rr, int w
     for (int m = 0; m < MM; m++) acc[m] = 0.0f;
 }
 
-// PRO >= 0: the prologue is fixed at compile time (the decode hot path: only that prologue's code is in the kernel);
-// PRO < 0: chosen at run time from `prologue`.
-// PRO >= 0: decode hot path, prologue fixed at compile time (PRO_F32_QUANT or PRO_RMSNORM_QUANT, M = 1, register staging);
-// PRO < 0: generic, prologue chosen at run time from `prologue_rt`.
-template <int WDT, bool ACTQ8, int EPI, int MM, int CH, int NBUF, int NT, int MINB, int PRO>
-__global__ void __launch_bounds__(NT, MINB) gemv_kernel(const GemvParams p, const int prologue_rt) {
+// ---- generic kernel: any M <= 8, any prologue (run time), 256 threads -------------------------------------------
+template <int WDT, bool ACTQ8, int EPI, int MM, int CH, int NBUF, int MINB>
+__global__ void __launch_bounds__(GEMV_THREADS, MINB) gemv_kernel(const GemvParams p, const int prologue) {
     extern __shared__ __align__(16) unsigned char smem[];
-    constexpr int NWARP = NT / 32;
-    constexpr bool HOT = PRO >= 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nblk = p.K / 32;
     const int nchunks = (nblk + 32 * CH - 1) / (32 * CH);
     constexpr int NW = (EPI == EPI_SILU_MUL) ? 2 : 1; // weight rows per output row
     const int wbytes_per_blk = (WDT == JL_Q4) ? 16 : 32;
-    ktrace_begin(p.trace, 0x100u | (unsigned)EPI | ((unsigned long long)(HOT ? PRO : prologue_rt) << 4) |
-                              ((unsigned long long)p.total_rows << 16) | ((unsigned long long)p.K << 40));
+    ktrace_begin(p.trace, 0x100u | (unsigned)EPI | ((unsigned long long)prologue << 4) | ((unsigned long long)p.total_rows << 16) |
+                              ((unsigned long long)p.K << 40));
 
     // balanced static partition of output rows over all warps of the grid
-    const long long gw = (long long)blockIdx.x * NWARP + warp;
-    const long long tw = (long long)gridDim.x * NWARP;
+    const long long gw = (long long)blockIdx.x * GEMV_WARPS + warp;
+    const long long tw = (long long)gridDim.x * GEMV_WARPS;
     const int r0 = (int)(((long long)p.total_rows * gw) / tw);
     const int r1 = (int)(((long long)p.total_rows * (gw + 1)) / tw);
 
@@ -587,37 +586,26 @@ __global__ void __launch_bounds__(NT, MINB) gemv_kernel(const GemvParams p, cons
         }
     };
 
-    // hot path: the hidden row is requested first, so it is not queued behind this SM's weight requests
-    StageRegs<PRO == PRO_RMSNORM_QUANT, NT> sr;
-    if (HOT) {
-        pdl_wait();
-        stage_q8_issue<PRO == PRO_RMSNORM_QUANT, NT>(p, sr);
-    }
-
     WBuf<WDT, CH> buf[NBUF];
     const uint8_t *wrow;
     const float *srow;
+    const unsigned long long pol = l2_evict_first_policy();
     It cur = {r0, 0, 0}, ld = cur;
-    // NBUF-1 chunks per warp go in flight now
+    // NBUF-1 chunks per warp go in flight before anything else: the weight stream does not depend on the previous kernel
 #pragma unroll
     for (int b = 0; b < NBUF - 1; b++) {
         if (ld.r < r1) {
             row_ptrs(ld, wrow, srow);
-            load_chunk<WDT, CH>(buf[b], wrow, srow, ld.c * 32 * CH, nblk, lane);
+            load_chunk<WDT, CH>(buf[b], wrow, srow, ld.c * 32 * CH, nblk, lane, pol);
             advance(ld);
         }
     }
     pdl_launch_dependents();
-    ktrace_stamp(p.trace, 5, 0.f);
-    if (HOT) {
-        stage_q8_finish<PRO == PRO_RMSNORM_QUANT, NT>(p, sr, smem, nblk);
-    } else {
-        pdl_wait(); // activations are produced by the previous kernel
-        if (ACTQ8 && (prologue_rt == PRO_F32_QUANT || prologue_rt == PRO_RMSNORM_QUANT))
-            stage_q8_pairs<MM>(p, prologue_rt == PRO_RMSNORM_QUANT, smem, nblk);
-        else
-            stage_activations<ACTQ8, MM>(p, prologue_rt, smem, nblk);
-    }
+    pdl_wait(); // activations are produced by the previous kernel
+    if (ACTQ8 && (prologue == PRO_F32_QUANT || prologue == PRO_RMSNORM_QUANT))
+        stage_q8_pairs<MM>(p, prologue == PRO_RMSNORM_QUANT, smem, nblk);
+    else
+        stage_activations<ACTQ8, MM>(p, prologue, smem, nblk);
     ktrace_mid(p.trace);
 
     float acc[MM];
@@ -631,17 +619,180 @@ __global__ void __launch_bounds__(NT, MINB) gemv_kernel(const GemvParams p, cons
             if (cur.r < r1) {
                 if (ld.r < r1) {
                     row_ptrs(ld, wrow, srow);
-                    load_chunk<WDT, CH>(buf[(b + NBUF - 1) % NBUF], wrow, srow, ld.c * 32 * CH, nblk, lane);
+                    load_chunk<WDT, CH>(buf[(b + NBUF - 1) % NBUF], wrow, srow, ld.c * 32 * CH, nblk, lane, pol);
                     advance(ld);
                 }
                 compute_chunk<WDT, ACTQ8, MM, CH>(buf[b], acc, smem, cur.c * 32 * CH, nblk, lane);
-                if (cur.r == r0 && cur.wr == 0 && cur.c == 0) ktrace_stamp(p.trace, 11, acc[0]);
                 if (cur.c == nchunks - 1) finish_row_fn<EPI, MM>(p, cur.r, cur.wr, acc, gate);
                 advance(cur);
             }
         }
     }
-    ktrace_stamp(p.trace, 12, acc[0]);
+    if (p.trace) {
+        __syncthreads();
+        ktrace_end(p.trace);
+    }
+}
+
+// ---- decode kernel: M = 1, Q8 activations, prologue fixed at compile time, one big CTA per SM -----------------------
+// Work split: output rows are dealt to the CTAs; inside a CTA the (row, weight-row, chunk) items are dealt to the warps.
+// LONG = false (a weight row is one chunk, K <= 1024*CH): whole rows go to warps, a warp finishes its rows alone.
+// LONG = true (down_proj: K = 14336 = 3.5 chunks): rows are split at chunk granularity, so every warp streams the same
+// number of bytes (+-1 chunk) however few rows the CTA has; a warp leaves one partial sum per (row, weight-row) it
+// touched in shared memory and, after a barrier, one thread per output row adds the partials in chunk order
+// (deterministic).  The kernel is kept small on purpose: five different kernels alternate every ~50 us, each starts
+// with a cold instruction cache, and every kilobyte on the prologue path showed up in the timeline (tools/ktrace.py).
+__device__ __forceinline__ int item_owner(int i, int items, int nwarp) { return (int)((((long long)(i + 1)) * nwarp - 1) / items); }
+
+template <int WDT, int EPI, int PRO, int CH, int NBUF, int NT, bool PDL, bool LONG>
+__global__ void __launch_bounds__(NT, 1) gemv_decode_kernel(const GemvParams p, const int) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int NWARP = NT / 32;
+    constexpr bool NORM = PRO == PRO_RMSNORM_QUANT;
+    constexpr int NW = (EPI == EPI_SILU_MUL) ? 2 : 1; // weight rows per output row
+    constexpr int WB = (WDT == JL_Q4) ? 16 : 32;      // weight bytes per 32-element block
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nblk = p.K / 32;
+    const int nchunks = LONG ? (nblk + 32 * CH - 1) / (32 * CH) : 1;
+    ktrace_begin(p.trace, 0x100u | (unsigned)EPI | ((unsigned long long)PRO << 4) | ((unsigned long long)p.total_rows << 16) |
+                              ((unsigned long long)p.K << 40));
+
+    // rows of this CTA, items of this warp
+    const int R0 = (int)(((long long)p.total_rows * blockIdx.x) / gridDim.x);
+    const int R1 = (int)(((long long)p.total_rows * (blockIdx.x + 1)) / gridDim.x);
+    const int nrows = R1 - R0;
+    const int per_row = NW * nchunks;
+    const int items = nrows * per_row;
+    int i0, i1;
+    if (LONG) {
+        i0 = (int)(((long long)items * warp) / NWARP);
+        i1 = (int)(((long long)items * (warp + 1)) / NWARP);
+    } else {
+        i0 = (int)(((long long)nrows * warp) / NWARP) * per_row;
+        i1 = (int)(((long long)nrows * (warp + 1)) / NWARP) * per_row;
+    }
+    // load cursor: (row relative to R0, weight-row, chunk) plus the byte/element offset of that weight row
+    struct It {
+        int r, wr, c;
+    };
+    const size_t row_blocks = (size_t)(p.ldw / 32), col_blocks = (size_t)(p.w_col_off / 32);
+    auto row_ptrs = [&](const It &it, const uint8_t *&wrow, const float *&srow) {
+        int seg, local;
+        if (EPI == EPI_SILU_MUL) {
+            seg = it.wr;
+            local = R0 + it.r;
+        } else {
+            seg_lookup(p, R0 + it.r, seg, local);
+        }
+        const size_t blk = (size_t)(p.row0 + local) * row_blocks + col_blocks;
+        wrow = (const uint8_t *)p.seg[seg].w + blk * WB;
+        srow = p.seg[seg].ws + blk;
+    };
+    auto advance = [&](It &it) {
+        if (!LONG || ++it.c == nchunks) {
+            it.c = 0;
+            if (++it.wr == NW) {
+                it.wr = 0;
+                ++it.r;
+            }
+        }
+    };
+    It cur, ld;
+    {
+        cur.r = i0 / per_row;
+        const int rem = i0 - cur.r * per_row;
+        cur.wr = rem / nchunks;
+        cur.c = rem - cur.wr * nchunks;
+        ld = cur;
+    }
+
+    StageRegs<NORM, LONG && !NORM> sr;
+    WBuf<WDT, CH> buf[NBUF];
+    const uint8_t *wrow;
+    const float *srow;
+    const unsigned long long pol = l2_evict_first_policy();
+    int ci = i0, li = i0;
+    if (PDL) {
+        // programmatic dependent launch: this CTA may start while the producer of the hidden row is still running, so the
+        // weight stream goes first and the row is only touched after the wait
+#pragma unroll
+        for (int b = 0; b < NBUF - 1; b++) {
+            if (li < i1) {
+                row_ptrs(ld, wrow, srow);
+                load_chunk<WDT, CH>(buf[b], wrow, srow, ld.c * 32 * CH, nblk, lane, pol);
+                advance(ld);
+                li++;
+            }
+        }
+        pdl_launch_dependents();
+        pdl_wait();
+        stage_q8_issue<NORM, LONG && !NORM, NT>(p, sr);
+    } else {
+        // the hidden row (and the norm weights) are requested before this SM's ~80 KB of weight requests
+        stage_q8_issue<NORM, LONG && !NORM, NT>(p, sr);
+#pragma unroll
+        for (int b = 0; b < NBUF - 1; b++) {
+            if (li < i1) {
+                row_ptrs(ld, wrow, srow);
+                load_chunk<WDT, CH>(buf[b], wrow, srow, ld.c * 32 * CH, nblk, lane, pol);
+                advance(ld);
+                li++;
+            }
+        }
+    }
+    stage_q8_finish<NORM, LONG && !NORM, NT>(p, sr, smem, nblk);
+    ktrace_mid(p.trace);
+
+    float *parts = (float *)(smem + (((size_t)nblk * 40 + 15) & ~(size_t)15));
+    const int maxsplit = nchunks < NWARP ? nchunks : NWARP;
+    float acc[1] = {0.0f}, gate[1] = {0.0f};
+    while (ci < i1) {
+#pragma unroll
+        for (int b = 0; b < NBUF; b++) {
+            if (ci < i1) {
+                if (li < i1) {
+                    row_ptrs(ld, wrow, srow);
+                    load_chunk<WDT, CH>(buf[(b + NBUF - 1) % NBUF], wrow, srow, ld.c * 32 * CH, nblk, lane, pol);
+                    advance(ld);
+                    li++;
+                }
+                compute_chunk<WDT, true, 1, CH>(buf[b], acc, smem, cur.c * 32 * CH, nblk, lane);
+                if (!LONG) {
+                    finish_row_fn<EPI, 1>(p, R0 + cur.r, cur.wr, acc, gate); // every item ends a weight row
+                } else if (cur.c == nchunks - 1 || ci == i1 - 1) {
+                    // partial of (row, weight-row) from this warp
+                    const float v = warp_sum(acc[0]);
+                    const int rw = cur.r * NW + cur.wr;
+                    if (lane == 0) parts[rw * maxsplit + (warp - item_owner(rw * nchunks, items, NWARP))] = v;
+                    acc[0] = 0.0f;
+                }
+                advance(cur);
+                ci++;
+            }
+        }
+    }
+    if (LONG) {
+        __syncthreads();
+        for (int o = tid; o < nrows; o += NT) {
+            float sums[NW];
+#pragma unroll
+            for (int wr = 0; wr < NW; wr++) {
+                const int rw = o * NW + wr;
+                const int wa = item_owner(rw * nchunks, items, NWARP), wb = item_owner(rw * nchunks + nchunks - 1, items, NWARP);
+                float t = 0.0f;
+                for (int w = wa; w <= wb; w++) t = __fadd_rn(t, parts[rw * maxsplit + (w - wa)]);
+                sums[wr] = t;
+            }
+            int seg = 0, local = R0 + o;
+            if (EPI != EPI_SILU_MUL) seg_lookup(p, R0 + o, seg, local);
+            const GemvSeg &sg = p.seg[seg];
+            const int col = p.row0 + local + sg.out_off;
+            float v = sums[NW - 1];
+            if (EPI == EPI_ADD_RESIDUAL) v = __fadd_rn(v, p.residual[p.row0 + local]);
+            if (EPI == EPI_SILU_MUL) v = __fmul_rn(silu_ref(sums[0]), v);
+            sg.out[col] = v;
+        }
+    }
     if (p.trace) {
         __syncthreads();
         ktrace_end(p.trace);
@@ -765,23 +916,47 @@ static int generic_grid(jl_ctx *ctx, int rows, int max_per_sm) {
     return grid < 1 ? 1 : grid;
 }
 
+// decode hot path: one big CTA per SM, prologue fixed at compile time
+template <int WDT, int EPI, int PRO, int NT, int NBUF, int CH, bool PDL, bool LONG>
+static int launch_decode_k(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int grid, size_t smem) {
+    static thread_local size_t configured = 0;
+    return launch_kern(ctx, stream, gemv_decode_kernel<WDT, EPI, PRO, CH, NBUF, NT, PDL, LONG>, p, 0, PDL, grid, NT, smem, configured);
+}
+
+template <int WDT, int EPI, int PRO, int NT, int NBUF, int CH>
+static int launch_decode(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, bool pdl, size_t smem) {
+    if (PRO == PRO_RMSNORM_QUANT && p.K > 16 * NT)
+        return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "gemv: RMSNorm prologue supports rows up to %d", 16 * NT);
+    int grid = ctx->sm_count;
+    const int max_grid = (p.total_rows + NT / 32 - 1) / (NT / 32);
+    if (grid > max_grid) grid = max_grid;
+    const int nchunks = (p.K / 32 + 32 * CH - 1) / (32 * CH);
+    const bool lng = nchunks > 1;
+    size_t smem_d = ((smem + 15) & ~(size_t)15);
+    if (lng) { // partial sums of split rows live behind the staged activations
+        const int rows_per_cta = (p.total_rows + grid - 1) / grid;
+        const int maxsplit = nchunks < NT / 32 ? nchunks : NT / 32;
+        smem_d += (size_t)rows_per_cta * (EPI == EPI_SILU_MUL ? 2 : 1) * maxsplit * 4;
+    }
+    if (smem_d > 200 * 1024) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "gemv: shape exceeds shared memory");
+    if (pdl) {
+        if (lng) return launch_decode_k<WDT, EPI, PRO, NT, NBUF, CH, true, true>(ctx, stream, p, grid, smem_d);
+        return launch_decode_k<WDT, EPI, PRO, NT, NBUF, CH, true, false>(ctx, stream, p, grid, smem_d);
+    }
+    if (lng) return launch_decode_k<WDT, EPI, PRO, NT, NBUF, CH, false, true>(ctx, stream, p, grid, smem_d);
+    return launch_decode_k<WDT, EPI, PRO, NT, NBUF, CH, false, false>(ctx, stream, p, grid, smem_d);
+}
+
 template <int WDT, bool ACTQ8, int EPI, int MM>
 static int launch_q(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int prologue, bool pdl, size_t smem) {
-    if (WDT == JL_Q4 && ACTQ8 && MM == 1 && (prologue == PRO_F32_QUANT || prologue == PRO_RMSNORM_QUANT) &&
-        !(prologue == PRO_RMSNORM_QUANT && p.K > 16 * GEMV_THREADS_DECODE)) {
-        // decode hot path: one 768-thread CTA per SM, prologue fixed at compile time
-        constexpr int NT = GEMV_THREADS_DECODE;
-        int grid = ctx->sm_count;
-        const int max_grid = (p.total_rows + NT / 32 - 1) / (NT / 32);
-        if (grid > max_grid) grid = max_grid;
-        static thread_local size_t cfg_a = 0, cfg_b = 0;
-        if (prologue == PRO_F32_QUANT)
-            return launch_kern(ctx, stream, gemv_kernel<WDT, ACTQ8, EPI, 1, 4, 2, NT, 1, PRO_F32_QUANT>, p, prologue, pdl, grid, NT, smem, cfg_a);
-        return launch_kern(ctx, stream, gemv_kernel<WDT, ACTQ8, EPI, 1, 4, 2, NT, 1, PRO_RMSNORM_QUANT>, p, prologue, pdl, grid, NT, smem, cfg_b);
+    if constexpr (WDT == JL_Q4 && ACTQ8 && MM == 1) {
+        if (prologue == PRO_F32_QUANT) return launch_decode<WDT, EPI, PRO_F32_QUANT, 512, 3, 4>(ctx, stream, p, pdl, smem);
+        if (prologue == PRO_RMSNORM_QUANT && p.K <= 16 * 512)
+            return launch_decode<WDT, EPI, PRO_RMSNORM_QUANT, 512, 3, 4>(ctx, stream, p, pdl, smem);
     }
     constexpr int MINB = (MM <= 2) ? 2 : 1;
     static thread_local size_t cfg = 0;
-    return launch_kern(ctx, stream, gemv_kernel<WDT, ACTQ8, EPI, MM, 4, 2, GEMV_THREADS, MINB, -1>, p, prologue, pdl,
+    return launch_kern(ctx, stream, gemv_kernel<WDT, ACTQ8, EPI, MM, 4, 2, MINB>, p, prologue, pdl,
                        generic_grid(ctx, p.total_rows, MINB), GEMV_THREADS, smem, cfg);
 }
 
@@ -825,7 +1000,19 @@ static int launch_dense_m(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p,
 
 int jl_launch_gemv(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p_in, int prologue, int epilogue, bool use_pdl) {
     GemvParams p = p_in;
-    p.trace = jl_ktrace_slot(ctx);
+    {
+        static int dup = -1; // diagnostics: every GEMV launched twice, the traced second launch finds warm caches
+        if (dup < 0) dup = getenv("JL_GEMV_DUP") ? 1 : 0;
+        if (dup == 1) {
+            dup = 2;
+            int rc = jl_launch_gemv(ctx, stream, p_in, prologue, epilogue, use_pdl);
+            dup = 1;
+            if (rc) return rc;
+        }
+        p.trace = dup == 2 ? nullptr : jl_ktrace_slot(ctx);
+    }
+    p.norm_inv_E = p.norm_E > 0 ? 1.0 / (double)p.norm_E : 0.0;
+
     if (p.M < 1 || p.M > GEMV_MAX_M) return jl_set_error(ctx, JL_ERR_INVALID, "gemv: M=%d out of range", p.M);
     if (p.K <= 0 || p.total_rows <= 0) return jl_set_error(ctx, JL_ERR_INVALID, "gemv: empty problem");
     const bool quant_w = (p.w_dtype == JL_Q4 || p.w_dtype == JL_I8);
