@@ -183,11 +183,11 @@ typedef struct {
 } jl_model_config;
 
 #define JL_MODEL_NO_GRAPH 1 /* launch decode kernels eagerly instead of through a CUDA graph */
-#define JL_MODEL_NO_PDL 2   /* (default) no programmatic dependent launch between decode kernels */
+#define JL_MODEL_NO_PDL 2   /* (default) no programmatic dependent launch between the decode kernels */
 #define JL_MODEL_NO_MEGA 4  /* (default) decode with one kernel per op */
 #define JL_MODEL_MEGA 8     /* opt in: decode with the persistent cooperative megakernel (jl_mega.cu); measured slower than
                                the CUDA-graph path on B200 in round 1, kept as the basis for round 2 */
-#define JL_MODEL_PDL 16     /* opt in: programmatic dependent launch between the per-op decode kernels (measured slower) */
+#define JL_MODEL_PDL 16     /* opt in: programmatic dependent launch between the per-op decode kernels (measured: no gain) */
 
 /* tensor slots */
 #define JL_T_EMBED 0

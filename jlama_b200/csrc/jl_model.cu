@@ -72,7 +72,20 @@ struct jl_model {
         if (_rc != JL_OK) return _rc; \
     } while (0)
 
-static bool use_pdl(const jl_model *m) { return (m->cfg.flags & JL_MODEL_PDL) && !(m->cfg.flags & JL_MODEL_NO_PDL); }
+// Programmatic dependent launch between the decode kernels: opt in with JL_MODEL_PDL or JL_PDL=1.  Measured on the 8B
+// decode step (tools/ktrace.py): launch gaps turn into ~0.6 us overlaps, but the latency-bound attention kernel runs
+// ~4 us longer, so the step is no faster (1.76-1.83 ms with, 1.80 ms without).  Every PDL-launched kernel only issues
+// read-only weight loads before griddepcontrol.wait.
+static bool use_pdl(const jl_model *m) {
+    static int env = -1;
+    if (env < 0) {
+        const char *e = getenv("JL_PDL");
+        env = e ? (atoi(e) ? 1 : 0) : 2;
+    }
+    if (m->cfg.flags & JL_MODEL_NO_PDL) return false;
+    if (env != 2) return env == 1;
+    return (m->cfg.flags & JL_MODEL_PDL) != 0;
+}
 static bool use_graph(const jl_model *m) { return !(m->cfg.flags & JL_MODEL_NO_GRAPH); }
 static bool use_mega(const jl_model *m) { return m->mega_ok && (m->cfg.flags & JL_MODEL_MEGA) && !(m->cfg.flags & JL_MODEL_NO_MEGA); }
 
@@ -359,7 +372,8 @@ static cudaEvent_t next_event(jl_model *m) {
 
 // one quantised/dense GEMM call site; M rows of `a` against W; splits M into GEMV_MAX_M chunks.
 // `timed`: bracket with events (eager mode only) for the roofline numerator.
-static int run_gemm(jl_model *m, GemvParams p, int prologue, int epilogue, int M, size_t a_row_bytes, bool timed) {
+static int run_gemm(jl_model *m, GemvParams p, int prologue, int epilogue, int M, size_t a_row_bytes, bool timed,
+                    bool allow_pdl = true) {
     jl_ctx *ctx = m->ctx;
     if (timed) cudaEventRecord(next_event(m), m->stream);
     for (int m0 = 0; m0 < M; m0 += GEMV_MAX_M) {
@@ -368,7 +382,7 @@ static int run_gemm(jl_model *m, GemvParams p, int prologue, int epilogue, int M
         c.a = (const char *)p.a + (size_t)m0 * a_row_bytes;
         for (int s = 0; s < c.nseg; s++) c.seg[s].out = p.seg[s].out + (size_t)m0 * p.seg[s].out_ld;
         if (c.residual) c.residual = p.residual + (size_t)m0 * p.res_ld;
-        M_CHECK(jl_launch_gemv(ctx, m->stream, c, prologue, epilogue, use_pdl(m)));
+        M_CHECK(jl_launch_gemv(ctx, m->stream, c, prologue, epilogue, allow_pdl && use_pdl(m)));
     }
     if (timed) cudaEventRecord(next_event(m), m->stream);
     return JL_OK;
@@ -459,8 +473,10 @@ static int forward_rows(jl_model *m, int M, int max_pos, int splits, bool timed,
             p.residual = m->x;
             p.res_ld = E;
             p.total_rows = E;
+            // never an early launch for o_proj: its weight requests would flood the memory system under the latency-bound
+            // attention kernel
             M_CHECK(run_gemm(m, p, act_q(lw[JL_L_O]) ? PRO_F32_QUANT : PRO_F32, tp ? EPI_STORE : EPI_ADD_RESIDUAL, M,
-                             (size_t)m->attn_seg * 4, timed));
+                             (size_t)m->attn_seg * 4, timed, false));
             if (tp) {
                 M_CHECK(jl_comm_allreduce_dev(ctx, m->stream, m->partial, (size_t)M * E));
                 // xb = reduced + x
