@@ -55,16 +55,16 @@ int jl_sync(jl_ctx *ctx);
 /* number of kernels this library launched since jl_init (bench.py's gpu_launches claim) */
 int64_t jl_kernel_launches(jl_ctx *ctx);
 
-/* diagnostic: time the quantised GEMV kernel on device-resident operands.  `b_id` is a registered weight
- * [rows, k]; each of `iters` launches handles `n` consecutive rows starting at a rotating offset so that the
- * stream of weights is larger than L2; activations [m, k] f32 live in HBM.  mode: 0 = Q8-quantising prologue +
- * store, 1 = RMSNorm + Q8 prologue + store, 2 = f32 activations + store, 3 = Q8 prologue + residual epilogue.
- * Returns the average microseconds per launch measured with CUDA events around the whole sequence. */
 /* kernel timeline: every GEMV / decode-attention launch made while tracing is on gets a slot of 16 words
  * {first CTA start ns, last CTA end ns, CTA 0 after its prologue ns, tag, CTA 0 start ns, 11 stage stamps}; tools/ktrace.py */
 int jl_debug_ktrace(jl_ctx *ctx, int capacity);
 int jl_debug_ktrace_clear(jl_ctx *ctx);
 int jl_debug_ktrace_read(jl_ctx *ctx, uint64_t *out, int max_slots);
+/* diagnostic: time the quantised GEMV kernel on device-resident operands.  `b_id` is a registered weight
+ * [rows, k]; each of `iters` launches handles `n` consecutive rows starting at a rotating offset so that the
+ * stream of weights is larger than L2; activations [m, k] f32 live in HBM.  mode: 0 = Q8-quantising prologue +
+ * store, 1 = RMSNorm + Q8 prologue + store, 2 = f32 activations + store, 3 = Q8 prologue + residual epilogue.
+ * Returns the average microseconds per launch measured with CUDA events around the whole sequence. */
 int jl_debug_gemv_bench(jl_ctx *ctx, int64_t b_id, int n, int m, int mode, int iters, int use_pdl, double *avg_us);
 
 /* diagnostic: average microseconds of one tcgen05 prefill GEMM launch C[t, rows] = A_bf16[t, k] * W^T on

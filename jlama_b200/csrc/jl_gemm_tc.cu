@@ -8,7 +8,7 @@
 //   * the WEIGHT tile is the UMMA "A" operand (M = 128 weight rows), the token tile the "B" operand (N = 128
 //     tokens), so the instruction's M is always full and D comes out as [weight row][token];
 //   * per-block dequantisation (nibble - 8) * f32 scale -> BF16 is fused into the shared-memory fill of the
-//     weight tile: four producer warps read the packed Q4 blocks with 128-bit loads straight from HBM/L2
+//     weight tile: eight producer warps read the packed Q4 blocks with 128-bit loads straight from HBM/L2
 //     and write the 128-byte-swizzled K-major tile the tensor core consumes; the activation tile (already BF16
 //     in HBM) is copied into the same swizzled layout;
 //   * 4-stage mbarrier pipeline: producers -> full[s] -> MMA warp -> tcgen05.commit -> empty[s];
