@@ -94,6 +94,18 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(cfg):
+    """DRAM bytes of one token's quantised GEMV launches from the committed ncu capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    if d.get("model") != cfg["name"]:
+        return None
+    per = d["per_launch_bytes"]
+    return d["layers"] * (per["qkv"] + per["o_proj"] + per["gate_up"] + per["down"]) + d["algorithmic_bytes"]["lm_head"]
+
+
 def make_model_weights(cfg, mode):
     from jlama_b200 import native, synth
     t0 = time.time()
@@ -327,7 +339,8 @@ def main():
         gemv_ms = max_over_ranks(gemv) / nprof
         achieved = wbytes / 1e9 / (gemv_ms / 1e3)
         result["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                              "traffic": None, "kernel": "gemv_kernel (all quantised GEMV launches of one token)",
+                              "traffic": measured_traffic(cfg) if world == 1 else None,
+                              "kernel": "gemv_decode_kernel x4 per layer + lm_head gemv_kernel (all quantised GEMV launches of one token)",
                               "bytes_per_launch_set": wbytes, "gemv_ms_per_token": gemv_ms, "peak_source": peak_src,
                               "step_frac": step_frac}
     else:
