@@ -745,7 +745,25 @@ __global__ void __launch_bounds__(NT, 1) gemv_decode_kernel(const GemvParams p, 
 
     float *parts = (float *)(smem + (((size_t)nblk * 40 + 15) & ~(size_t)15));
     const int maxsplit = nchunks < NWARP ? nchunks : NWARP;
-    float acc[1] = {0.0f}, gate[1] = {0.0f};
+    float acc[1] = {0.0f};
+    // !LONG: finished rows are parked one per lane (lane i holds the i-th finished row of this warp) and the epilogue --
+    // residual add or the double-precision SiLU -- runs for all parked rows at once with coalesced stores, instead of
+    // lane 0 doing it serially after every row (gate+up: 18.7 vs 19.9 us per launch)
+    float park0 = 0.0f, park1 = 0.0f; // value (or gate), up
+    int nparked = 0, park_row0 = R0 + cur.r;
+    auto flush = [&]() {
+        if (lane < nparked) {
+            int seg = 0, local = park_row0 + lane;
+            if (EPI != EPI_SILU_MUL) seg_lookup(p, park_row0 + lane, seg, local);
+            const GemvSeg &sg = p.seg[seg];
+            float v = NW == 2 ? park1 : park0;
+            if (EPI == EPI_ADD_RESIDUAL) v = __fadd_rn(v, p.residual[p.row0 + local]);
+            if (EPI == EPI_SILU_MUL) v = __fmul_rn(silu_ref(park0), v);
+            sg.out[p.row0 + local + sg.out_off] = v;
+        }
+        park_row0 += nparked;
+        nparked = 0;
+    };
     while (ci < i1) {
 #pragma unroll
         for (int b = 0; b < NBUF; b++) {
@@ -758,7 +776,14 @@ __global__ void __launch_bounds__(NT, 1) gemv_decode_kernel(const GemvParams p, 
                 }
                 compute_chunk<WDT, true, 1, CH>(buf[b], acc, smem, cur.c * 32 * CH, nblk, lane);
                 if (!LONG) {
-                    finish_row_fn<EPI, 1>(p, R0 + cur.r, cur.wr, acc, gate); // every item ends a weight row
+                    const float v = warp_sum(acc[0]); // every lane has the total
+                    acc[0] = 0.0f;
+                    if (NW == 2 && cur.wr == 0) {
+                        if (lane == nparked) park0 = v;
+                    } else {
+                        if (lane == nparked) (NW == 2 ? park1 : park0) = v;
+                        ++nparked;
+                    }
                 } else if (cur.c == nchunks - 1 || ci == i1 - 1) {
                     // partial of (row, weight-row) from this warp
                     const float v = warp_sum(acc[0]);
@@ -770,7 +795,9 @@ __global__ void __launch_bounds__(NT, 1) gemv_decode_kernel(const GemvParams p, 
                 ci++;
             }
         }
+        if (!LONG && nparked > 32 - NBUF) flush(); // checked once per ring revolution: at most NBUF rows arrive in between
     }
+    if (!LONG) flush();
     if (LONG) {
         __syncthreads();
         for (int o = tid; o < nrows; o += NT) {

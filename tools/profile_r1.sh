@@ -12,5 +12,5 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:fuse
 # 3. the lm_head GEMV (generic kernel, F32 activations)
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemv_kernel -s 3 -c 1 -f -o $O/lm_head_r1 $B > $O/lmhead_full_r1.log 2>&1
 # 4. tcgen05 prefill GEMM
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 30 -c 1 -f -o $O/gemm_tc_r1 python tools/gemm_tc_bench.py > $O/gemm_tc_full_r1.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_q4_tc_kernel -s 30 -c 1 -f -o $O/gemm_tc_r1 python tools/gemm_tc_bench.py > $O/gemm_tc_full_r1.log 2>&1
 ls -la $O/*.ncu-rep
