@@ -86,6 +86,28 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    """Route fd 1 to stderr for the whole run (NCCL and friends print banners to stdout); the JSON line is written to
+    the original stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, line)
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -182,7 +204,7 @@ def run_reference_arm(args):
         "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def main():
@@ -203,6 +225,7 @@ def main():
     ap.add_argument("--mega", action="store_true", help="decode with the persistent megakernel instead of the CUDA-graph path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    capture_stdout()
 
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -394,7 +417,7 @@ def main():
                                                    "max_logit_rel_err": relp, "tokens": n_p}
     model.close()
     if rank == 0:
-        print(json.dumps(result), flush=True)
+        emit(result)
     if dist is not None:
         dist.barrier()
         ctx.lib.jl_comm_destroy(ctx.h)

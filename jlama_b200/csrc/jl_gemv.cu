@@ -977,9 +977,18 @@ static int launch_decode(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, 
 template <int WDT, bool ACTQ8, int EPI, int MM>
 static int launch_q(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int prologue, bool pdl, size_t smem) {
     if constexpr (WDT == JL_Q4 && ACTQ8 && MM == 1) {
-        if (prologue == PRO_F32_QUANT) return launch_decode<WDT, EPI, PRO_F32_QUANT, 512, 3, 4>(ctx, stream, p, pdl, smem);
-        if (prologue == PRO_RMSNORM_QUANT && p.K <= 16 * 512)
-            return launch_decode<WDT, EPI, PRO_RMSNORM_QUANT, 512, 3, 4>(ctx, stream, p, pdl, smem);
+#ifdef JL_DECODE_NT
+        constexpr int NT = JL_DECODE_NT, NB = JL_DECODE_NBUF; // diagnostic builds (tools/build_variant.sh)
+#else
+        // CTA shape per launch kind, from A/B timelines on the 8B step (tools/ktrace.py; us per launch QKV / o / gate+up / down):
+        //   512 threads x 3-deep ring 5.92 / 4.43 / 16.58 / 10.41      640 x 2: 6.28 / 4.53 / 15.38 / 10.53
+        //   704 x 2: 5.98 / 4.62 / 15.93 / 11.10    768 x 2: 6.17 / 4.77 / 16.07 / 11.12    384 x 4: 6.32 / 4.75 / 17.01 / 11.42
+        // The long gate+up stream wants warps (issue slots), the short launches want the deeper ring.
+        constexpr int NT = EPI == EPI_SILU_MUL ? 640 : 512, NB = EPI == EPI_SILU_MUL ? 2 : 3;
+#endif
+        if (prologue == PRO_F32_QUANT) return launch_decode<WDT, EPI, PRO_F32_QUANT, NT, NB, 4>(ctx, stream, p, pdl, smem);
+        if (prologue == PRO_RMSNORM_QUANT && p.K <= 16 * NT)
+            return launch_decode<WDT, EPI, PRO_RMSNORM_QUANT, NT, NB, 4>(ctx, stream, p, pdl, smem);
     }
     constexpr int MINB = (MM <= 2) ? 2 : 1;
     static thread_local size_t cfg = 0;

@@ -793,25 +793,37 @@ static int run_decode(jl_model *m, int n, int max_pos, bool resident) {
     const long long key = ((long long)n << 32) | ((long long)splits << 1) | (resident ? 1 : 0);
     auto it = m->graphs.find(key);
     if (it == m->graphs.end()) {
-        cudaGraph_t graph = nullptr;
-        const long long before = ctx->launches;
-        JL_CUDA_CHECK(ctx, cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
-        int rc = decode_body(m, n, max_pos, splits, resident, false);
-        cudaError_t ce = cudaStreamEndCapture(m->stream, &graph);
-        const long long per_graph = ctx->launches - before;
-        ctx->launches = before;
-        if (rc != JL_OK) {
-            if (graph) cudaGraphDestroy(graph);
-            return rc;
+        // First decode of this (sessions, resident) kind: capture the graph of EVERY context-split bucket now, so that a
+        // generation never pays a capture + instantiate (~8 ms) when its context crosses a bucket boundary later.
+        // Capturing records launches only; nothing executes and no KV page is touched.
+        static const int buckets[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32};
+        for (int b : buckets) {
+            const int sp = b > m->max_splits ? m->max_splits : b;
+            const long long k2 = ((long long)n << 32) | ((long long)sp << 1) | (resident ? 1 : 0);
+            if (m->graphs.count(k2)) continue;
+            cudaGraph_t graph = nullptr;
+            const long long before = ctx->launches;
+            const int before_trace = ctx->ktrace_n;
+            JL_CUDA_CHECK(ctx, cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
+            int rc = decode_body(m, n, max_pos, sp, resident, false);
+            cudaError_t ce = cudaStreamEndCapture(m->stream, &graph);
+            const long long per_graph = ctx->launches - before;
+            ctx->launches = before;
+            if (sp != splits) ctx->ktrace_n = before_trace; // timeline slots only for the graph that is about to run
+            if (rc != JL_OK) {
+                if (graph) cudaGraphDestroy(graph);
+                return rc;
+            }
+            if (ce != cudaSuccess) return jl_set_error(ctx, JL_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+            cudaGraphExec_t exec = nullptr;
+            ce = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) return jl_set_error(ctx, JL_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+            m->graphs[k2] = exec;
+            m->graph_launches[k2] = per_graph;
         }
-        if (ce != cudaSuccess) return jl_set_error(ctx, JL_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-        cudaGraphExec_t exec = nullptr;
-        ce = cudaGraphInstantiate(&exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (ce != cudaSuccess) return jl_set_error(ctx, JL_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
-        m->graphs[key] = exec;
-        m->graph_launches[key] = per_graph;
         it = m->graphs.find(key);
+        if (it == m->graphs.end()) return jl_set_error(ctx, JL_ERR_INVALID, "decode: no graph for %d splits", splits);
     }
     JL_CUDA_CHECK(ctx, cudaGraphLaunch(it->second, m->stream));
     ctx->launches += m->graph_launches[key];
