@@ -403,8 +403,10 @@ def main():
                                   "prefill_tokens_per_s": len(cp) / r["prefill_s"]}
         result["parity"] = {"tokens_equal": [int(a) for a in gt] == [int(b) for b in r["tokens"]], "max_logit_rel_err": rel,
                             "tolerance": 1e-2, "against": r["label"],
-                            "note": "different summation order than the GPU (8-lane AVX partial sums); Q8 re-quantisation of the "
-                                    "activations amplifies 1e-7 differences, see DESIGN.md"}
+                            "note": "the 32-layer synthetic network amplifies summation-order differences through the per-layer Q8 "
+                                    "re-quantisation: the reference's AVX kernels and the plain-C port of the same arithmetic "
+                                    "differ from each other by the same amount (cpu_reference_kernels_vs_plain_c_port); on "
+                                    "test-size models the GPU matches the oracle to 1e-5 (tests/), see DESIGN.md section 6"}
         if args.parity_port_tokens > 0:
             from oracle import oracle as o
             o.use_reference_kernels(False)
@@ -415,6 +417,9 @@ def main():
             relp = max(float(np.abs(gl[i] - pl[i]).max() / np.abs(pl[i]).max()) for i in range(n_p))
             result["parity"]["vs_plain_c_port"] = {"tokens_equal": [int(a) for a in gt[:n_p]] == [int(b) for b in pt],
                                                    "max_logit_rel_err": relp, "tokens": n_p}
+            # yardstick: how far the two CPU implementations of the same arithmetic are from each other on this network
+            relc = max(float(np.abs(np.asarray(r["logits"][i]) - pl[i]).max() / np.abs(pl[i]).max()) for i in range(n_p))
+            result["parity"]["cpu_reference_kernels_vs_plain_c_port"] = relc
     model.close()
     if rank == 0:
         emit(result)
