@@ -1036,17 +1036,7 @@ static int launch_dense_m(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p,
 
 int jl_launch_gemv(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p_in, int prologue, int epilogue, bool use_pdl) {
     GemvParams p = p_in;
-    {
-        static int dup = -1; // diagnostics: every GEMV launched twice, the traced second launch finds warm caches
-        if (dup < 0) dup = getenv("JL_GEMV_DUP") ? 1 : 0;
-        if (dup == 1) {
-            dup = 2;
-            int rc = jl_launch_gemv(ctx, stream, p_in, prologue, epilogue, use_pdl);
-            dup = 1;
-            if (rc) return rc;
-        }
-        p.trace = dup == 2 ? nullptr : jl_ktrace_slot(ctx);
-    }
+    p.trace = jl_ktrace_slot(ctx);
     p.norm_inv_E = p.norm_E > 0 ? 1.0 / (double)p.norm_E : 0.0;
 
     if (p.M < 1 || p.M > GEMV_MAX_M) return jl_set_error(ctx, JL_ERR_INVALID, "gemv: M=%d out of range", p.M);

@@ -1,5 +1,8 @@
 """Micro-benchmark of the quantised GEMV kernel at Llama-3-8B / 1B layer shapes (diagnostic, run on the GPU box):
-   python tools/gemv_bench.py        -> achieved GB/s per shape, with and without PDL overlap"""
+   python tools/gemv_bench.py        -> achieved GB/s per shape, with and without PDL overlap
+CAVEAT: these are back-to-back launches in a stream, and stream launches are quantised to about
+2.05 us on this stack, so 5-15 us kernels report multiples of 2.05 us.  Use tools/ktrace.py (timeline inside the replayed
+CUDA graph) to compare kernel variants."""
 import ctypes as C
 import json
 import os
@@ -16,8 +19,7 @@ SHAPES = [("qkv 8B", 6144, 4096), ("o 8B", 4096, 4096), ("gate 8B", 14336, 4096)
 
 def main():
     quick = "--quick" in sys.argv  # M=1, no PDL, 8B shapes only: for comparing JL_GEMV_CFG / JL_GEMV_AHEAD variants
-    tag = "cfg=%s ahead=%s per_sm=%s" % (os.environ.get("JL_GEMV_CFG", "0"), os.environ.get("JL_GEMV_AHEAD", "0"),
-                                        os.environ.get("JL_GEMV_PER_SM", "-"))
+    tag = "quick"
     peak = 6563.9
     if os.path.exists("MEASURED_PEAKS.json"):
         peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"]
