@@ -78,12 +78,12 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("cfg_name", ["tiny"])
-def test_two_rank_shards_and_allreduce_reproduce_the_unsharded_layer(cfg_name):
+@pytest.mark.parametrize("cfg_name,world", [("tiny", 2), ("small", 4)])
+def test_shards_and_allreduce_reproduce_the_unsharded_layer(cfg_name, world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, cfg_name, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cfg_name, q)) for r in range(world)]
     for p in procs:
         p.start()
     status, err, segs = q.get(timeout=120)
@@ -94,7 +94,10 @@ def test_two_rank_shards_and_allreduce_reproduce_the_unsharded_layer(cfg_name):
     assert err < 1e-12  # float64 arithmetic, only the summation order differs
     cfg = synth.get_config(cfg_name)
     hs = cfg["E"] // cfg["heads"]
-    (h0, hl, a0, al, k0, kl), (h1, hl1, a1, al1, k1, kl1) = segs
-    assert (h0, h0 + hl, h1 + hl1) == (0, h1, cfg["H"])                 # hidden rows tile [0, H)
-    assert (a0, a0 + al, a1 + al1) == (0, a1, cfg["heads"] * hs)         # attention columns tile [0, heads*hs)
-    assert (k0, k0 + kl, k1 + kl1) == (0, k1, cfg["kv_heads"] * hs)      # kv rows tile [0, kv_heads*hs)
+    # hidden rows tile [0, H), attention columns tile [0, heads*hs), kv rows tile [0, kv_heads*hs), in rank order
+    for col, total in ((0, cfg["H"]), (2, cfg["heads"] * hs), (4, cfg["kv_heads"] * hs)):
+        pos = 0
+        for seg in segs:
+            assert seg[col] == pos
+            pos += seg[col + 1]
+        assert pos == total
