@@ -10,13 +10,17 @@ batch-1 greedy decode after a short prompt.  One "step" = one decoded token (for
 
   value : tokens/s with the token ids resident in HBM (device-side feedback loop, CUDA-graph replays),
           timed with CUDA events on the model stream, max over ranks.
-  e2e   : tokens/s through the reference-facing C-ABI call jl_model_decode with HOST buffers: every step
-          copies token/position/session ids host->device from pinned memory and the sampled token back.
+  e2e   : tokens/s through the reference-facing call -- jl_model_generate (AbstractModel.generate at temperature 0)
+          with HOST token buffers: every decoded token copies token/position/session ids host->device from pinned
+          memory and the sampled token back (a host round trip per step inside the timed region).
   roofline : dominant kernel = the quantised GEMV; achieved = algorithmic weight bytes per token
           (0.625 B/weight Q4 incl. f32 block scales) / summed GEMV launch durations per token
           measured with CUDA events around every GEMV launch (eager, un-overlapped); peak = MEASURED_PEAKS.json.
           step_frac = the same bytes / whole-step time (the north-star "fraction of HBM roofline").
-  cpu_baseline : the oracle driving the reference's own C kernels (oracle/_ref) on a bounded sample.
+  cpu_baseline : the oracle driving the reference's own C kernels (oracle/_ref) on a bounded sample, with Jlama's default
+          thread count (half the available CPUs); `--impl reference` uses all of them.
+  config.prefill : tokens/s of a 2048-token prompt on the tcgen05 prefill path (N = 1 only).
+  parity : in-run check of tokens and logits against both CPU implementations, plus their distance from each other.
 
 Timing hygiene: W>=3 warm-up steps; weights (4.7 GB/token) are far larger than the 126 MB L2, so no L2
 flush is needed ("inputs larger than L2"); clocks sampled with nvidia-smi during the timed region.

@@ -18,7 +18,9 @@
 // More CTAs per SM only repeat the prologue: with three 256-thread CTAs the RMSNorm + Q8 quantisation ran three times
 // per SM and its loads queued behind the weight requests (5 us of a 8.6 us QKV launch, tools/ktrace.py).  Here the
 // first warps ("stagers") request the hidden row BEFORE any weight load, every warp then puts its first chunks in
-// flight, and the stagers normalise / quantise into shared memory while the weights stream.
+// flight, and the stagers normalise / quantise into shared memory while the weights stream.  The gate+up launch uses
+// 640 threads with a two-deep ring instead (more issue slots for the long stream); finished rows are parked one per lane
+// and their epilogues run together.  DESIGN.md section 5 has the measurements behind each of these choices.
 #include "jl_common.cuh"
 #include <stdlib.h>
 
@@ -26,12 +28,6 @@
 #define GEMV_WARPS 8
 // CH = 32-element blocks per lane per chunk (a chunk is CH*32 blocks = CH*1024 weights of one row), NBUF = register
 // chunk buffers per warp (NBUF-1 chunks are in flight while one is being consumed)
-
-struct GemvSmem {
-    // offsets into dynamic shared memory, computed identically on host and device
-    int nblk;  // K/32
-    int M;
-};
 
 template <int WDT, int CH>
 struct WBuf {
