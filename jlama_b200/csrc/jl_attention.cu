@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(FDA_THREADS) fused_decode_attention_kernel(con
             __threadfence();
         }
         __syncthreads();
-        if (s_last) attention_merge<HS, FDA_THREADS>(t, m, kvh);
+        if (s_last) attention_merge<HS, FDA_THREADS>(t, m, kvh, fda_smem);
     }
     if (trace) {
         __syncthreads();

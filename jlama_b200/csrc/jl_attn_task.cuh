@@ -21,6 +21,9 @@ struct AttnTask {
 // softmax exponent exactly as the reference computes it: (float)Math.exp((double)x) (one out-of-line copy: the double exp
 // is ~150 instructions and the attention kernel starts with a cold instruction cache every layer)
 static __device__ __noinline__ float exp_ref(float x) { return (float)exp((double)x); }
+// two independent exponentials in one call: the two double-precision dependency chains interleave, so the pair costs
+// about the latency of one (the softmax needs exp(s - m_new) and the running-sum correction exp(m_old - m_new) together)
+static __device__ __noinline__ float2 exp_ref2(float a, float b) { return make_float2((float)exp((double)a), (float)exp((double)b)); }
 
 template <int NT>
 __device__ __forceinline__ void task_bar() {
@@ -214,11 +217,14 @@ __device__ void attention_task(const AttnTask &P, int layer, int m, int kvh, int
             const float s0 = ps[lane * MG_MAX_GROUP + h];
             const float m_old = hm[h];
             const float m_new = fmaxf(m_old, warp_max(s0));
-            const float e0 = s0 == -INFINITY ? 0.0f : exp_ref(__fsub_rn(s0, m_new));
+            // exp(s - m_new) for this lane's score and, in the same call, the correction exp(m_old - m_new) of the running
+            // sum (every lane computes the same correction; lane 0 uses it)
+            const float2 ee = exp_ref2(s0 == -INFINITY ? 0.0f : __fsub_rn(s0, m_new), m_old == -INFINITY ? 0.0f : __fsub_rn(m_old, m_new));
+            const float e0 = s0 == -INFINITY ? 0.0f : ee.x;
             const float ts = warp_sum(e0);
             ps[lane * MG_MAX_GROUP + h] = e0;
             if (lane == 0) {
-                const float corr = m_old == -INFINITY ? 0.0f : exp_ref(__fsub_rn(m_old, m_new));
+                const float corr = m_old == -INFINITY ? 0.0f : ee.y;
                 hc[h] = corr, hm[h] = m_new, hl[h] = fmaf(hl[h], corr, ts);
             }
         }
@@ -255,22 +261,30 @@ __device__ void attention_task(const AttnTask &P, int layer, int m, int kvh, int
 
 // merge the split partials of one (row, kv head): out = sum_s acc_s*exp(m_s-M) / sum_s l_s*exp(m_s-M)
 template <int HS, int NT>
-__device__ void attention_merge(const AttnTask &P, int m, int kvh) {
+__device__ void attention_merge(const AttnTask &P, int m, int kvh, unsigned char *u) {
     const int group = P.heads / P.kv_heads, S = P.splits;
-    for (int idx = threadIdx.x; idx < group * HS; idx += NT) {
-        const int h = kvh * group + idx / HS, d = idx % HS;
-        const float *w = P.attn_ws + ((size_t)m * P.heads + h) * S * (HS + 2);
+    // rescaling factors exp(m_s - M), one per (head, split), computed once (one exponential deep) instead of S serial
+    // exponentials in every (head, d) thread
+    float *fac = (float *)u; // [group][S] in the task's shared-memory area (dead once the task's partials are written)
+    for (int idx = threadIdx.x; idx < group * S; idx += NT) {
+        const int hl = idx / S, s = idx - hl * S;
+        const float *w = P.attn_ws + ((size_t)m * P.heads + kvh * group + hl) * S * (HS + 2);
         float M = -INFINITY;
-        for (int s = 0; s < S; s++) M = fmaxf(M, __ldcg(w + s * (HS + 2) + HS));
+        for (int t = 0; t < S; t++) M = fmaxf(M, __ldcg(w + t * (HS + 2) + HS));
+        const float ms = __ldcg(w + s * (HS + 2) + HS);
+        fac[idx] = ms == -INFINITY ? 0.0f : exp_ref(__fsub_rn(ms, M));
+    }
+    task_bar<NT>(); // all NT task threads call this function (whole CTA in the fused kernel, the consumer warps in the megakernel)
+    for (int idx = threadIdx.x; idx < group * HS; idx += NT) {
+        const int hl = idx / HS, h = kvh * group + hl, d = idx % HS;
+        const float *w = P.attn_ws + ((size_t)m * P.heads + h) * S * (HS + 2);
         float num = 0.0f, den = 0.0f;
         for (int s = 0; s < S; s++) {
-            const float ms = __ldcg(w + s * (HS + 2) + HS);
-            if (ms == -INFINITY) continue;
-            const float f = exp_ref(__fsub_rn(ms, M));
+            const float f = fac[hl * S + s];
+            if (f == 0.0f) continue; // empty split (or a contribution that underflows to nothing)
             num = fmaf(__ldcg(w + s * (HS + 2) + d), f, num);
             den = fmaf(__ldcg(w + s * (HS + 2) + HS + 1), f, den);
         }
         P.att[(size_t)m * P.attn_seg + h * HS + d] = __fdiv_rn(num, den);
     }
 }
-

@@ -554,9 +554,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const MegaPa
                     consumer_bar();
                     if (s_last) {
                         switch (P.head_size) {
-                            case 32: attention_merge<32, MG_CONSUMERS>(at, m, kvh); break;
-                            case 64: attention_merge<64, MG_CONSUMERS>(at, m, kvh); break;
-                            default: attention_merge<128, MG_CONSUMERS>(at, m, kvh); break;
+                            case 32: attention_merge<32, MG_CONSUMERS>(at, m, kvh, uarea); break;
+                            case 64: attention_merge<64, MG_CONSUMERS>(at, m, kvh, uarea); break;
+                            default: attention_merge<128, MG_CONSUMERS>(at, m, kvh, uarea); break;
                         }
                         op_signal(&sync[1 + L * 5 + 1]);
                     }
