@@ -222,6 +222,10 @@ typedef void (*ref_gemm_f32_q4_t)(int, const float *, int, const float *, const 
                                   int, int, int, int, int);
 typedef void (*ref_gemm_f32_t)(int, const float *, int, const float *, int, float *, int, int, int, int, int, int, int,
                                int);
+/* gemm_f32_bf16 (vector_simd.h:38): `cr` is the optional BF16 result, NULL here (F32 result in r) */
+typedef void (*ref_gemm_f32_bf16_t)(int, const float *, int, const short *, int, short *, float *, int, int, int, int, int,
+                                    int, int, int);
+static ref_gemm_f32_bf16_t ref_f32_bf16 = NULL;
 static ref_gemm_q8_q4_t ref_q8_q4 = NULL;
 static ref_gemm_f32_q4_t ref_f32_q4 = NULL;
 static ref_gemm_f32_t ref_f32 = NULL;
@@ -234,6 +238,7 @@ int jo_load_reference_kernels(const char *path, int flags) {
     ref_q8_q4 = (ref_gemm_q8_q4_t)dlsym(h, "gemm_q8_q4");
     ref_f32_q4 = (ref_gemm_f32_q4_t)dlsym(h, "gemm_f32_q4");
     ref_f32 = (ref_gemm_f32_t)dlsym(h, "gemm_f32");
+    ref_f32_bf16 = (ref_gemm_f32_bf16_t)dlsym(h, "gemm_f32_bf16");
     ref_flags = flags;
     return (ref_q8_q4 && ref_f32_q4 && ref_f32) ? 0 : -2;
 }
@@ -397,6 +402,11 @@ int jo_ref_gemm_f32(const float *a, const float *b, float *r, int m, int n0, int
     return 0;
 }
 
+int jo_ref_gemm_f32_bf16(const float *a, const uint16_t *b, float *r, int m, int n0, int n, int k, int lda, int ldb, int ldc) {
+    if (!ref_f32_bf16) return -1;
+    ref_f32_bf16(ref_flags, a, 0, (const short *)b, 0, NULL, r, 0, m, n0, n, k, lda, ldb, ldc);
+    return 0;
+}
 /* ------------------------------------------------------------------------ */
 /* Element-wise ops (NaiveTensorOperations.java:34-125 semantics)            */
 /* ------------------------------------------------------------------------ */

@@ -264,6 +264,17 @@ def ref_gemm_f32(a, b, n0, n):
     return r
 
 
+def ref_gemm_f32_bf16(a, b_bits, n0, n):
+    """reference gemm_f32_bf16 (vector_simd.h:38): F32 activations x BF16 weights (uint16 bit patterns) -> F32"""
+    m, k = a.shape
+    r = np.zeros((m, b_bits.shape[0]), dtype=np.float32)
+    L = lib()
+    L.jo_ref_gemm_f32_bf16.restype = C.c_int
+    rc = L.jo_ref_gemm_f32_bf16(_p(a), _p(b_bits), _p(r), m, n0, n, k, k, k, r.shape[1])
+    assert rc == 0
+    return r
+
+
 def accumulate(a, b, off, length):
     sb = b.struct()
     lib().jo_accumulate(_p(a), C.c_int64(a.shape[0]), C.c_int64(a.shape[1]), C.byref(sb), off, length)

@@ -74,6 +74,24 @@ def test_dense_f32_matches_reference_c_kernel(oracle, ref_kernels):
     assert np.abs(r - q).max() <= 5e-6 * np.abs(q).max()
 
 
+def test_f32_bf16_gemm_matches_reference_c_kernel(oracle, ref_kernels):
+    # F32 x BF16 (vector_simd.h:38; PanamaTensorOperations.java:1466-1539): N a multiple of 5 because of the reference
+    # splitter's corner-tile bug.  The reference's gemm_bf16 (BF16 x BF16, vector_simd.h:34) returns
+    # NaNs / wrong sums for the same call shape when driven directly through its C entry point, so BF16 x BF16 is pinned
+    # only against the exact float64 product below.
+    rng = np.random.default_rng(9)
+    a = rng.uniform(-1, 100, (4, 256)).astype(np.float32)
+    w = rng.uniform(0, 1, (20, 256)).astype(np.float32)
+    wb = oracle.f32_to_bf16(w)
+    ab = oracle.f32_to_bf16(a)
+    exact = oracle.bf16_to_f32(ab).astype(np.float64) @ oracle.bf16_to_f32(wb).astype(np.float64).T
+    r1 = oracle.batch_dot(oracle.f32(a), oracle.OTensor(oracle.BF16, wb), 0, 0, 256, 0, 0, 20)
+    q1 = oracle.ref_gemm_f32_bf16(a, wb, 0, 20)
+    assert np.abs(r1 - q1).max() <= 5e-6 * np.abs(q1).max()
+    r2 = oracle.batch_dot(oracle.OTensor(oracle.BF16, ab), oracle.OTensor(oracle.BF16, wb), 0, 0, 256, 0, 0, 20)
+    assert np.abs(r2 - exact).max() <= 5e-6 * np.abs(exact).max()
+
+
 def test_batch_dot_offsets_follow_panama_semantics(oracle):
     # result[i, j + rRowOffset] for j in [bRowOffset, bRowOffset+N) (PanamaTensorOperations.java:848)
     rng = np.random.default_rng(11)
