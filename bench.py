@@ -17,6 +17,9 @@ batch-1 greedy decode after a short prompt.  One "step" = one decoded token (for
           (0.625 B/weight Q4 incl. f32 block scales) / summed GEMV launch durations per token
           measured with CUDA events around every GEMV launch (eager, un-overlapped); peak = MEASURED_PEAKS.json.
           step_frac = the same bytes / whole-step time (the north-star "fraction of HBM roofline").
+          in_graph = the same bytes / the GEMV launches' summed durations inside one replayed CUDA graph, from device-side
+          %globaltimer stamps (tools/ktrace.py run as a child process): the eager event timing above also contains the
+          stream's ~2 us launch quantum per launch.
   cpu_baseline : the oracle driving the reference's own C kernels (oracle/_ref) on a bounded sample, with Jlama's default
           thread count (half the available CPUs); `--impl reference` uses all of them.
   config.prefill : tokens/s of a 2048-token prompt on the tcgen05 prefill path (N = 1 only).
@@ -425,6 +428,24 @@ def main():
             relc = max(float(np.abs(np.asarray(r["logits"][i]) - pl[i]).max() / np.abs(pl[i]).max()) for i in range(n_p))
             result["parity"]["cpu_reference_kernels_vs_plain_c_port"] = relc
     model.close()
+    if rank == 0 and world == 1 and not args.no_roofline and "roofline" in result:
+        # The event-timed eager launches above include the stream's launch overhead (back-to-back 5-15 us launches are
+        # quantised to ~2 us on this stack).  For the kernels' duration inside the replayed CUDA graph, a child process
+        # runs tools/ktrace.py (device-side %globaltimer stamps per launch); a failure there only omits the field.
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ktrace.py"), "--json", "--model", args.model],
+                               cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=240)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            if r.returncode == 0 and lines:
+                t = json.loads(lines[-1])
+                ach = wbytes / 1e9 / (t["gemv_us"] * 1e-6)
+                result["roofline"]["in_graph"] = {
+                    "achieved": ach, "frac": ach / peak, "gemv_us_per_token": t["gemv_us"], "attention_us_per_token": t["attention_us"],
+                    "step_ms": t["step_ms_events"], "position": t["position"],
+                    "method": "sum of per-launch (last CTA end - first CTA start) from %globaltimer stamps inside one replayed "
+                              "decode graph (tools/ktrace.py); stamps add ~1% to the step"}
+        except Exception as e:  # noqa: BLE001 -- diagnostics must never break the bench line
+            log("[bench] in-graph timeline skipped: %r" % (e,))
     if rank == 0:
         emit(result)
     if dist is not None:

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--prompt", type=int, default=32)
     ap.add_argument("--layers", type=int, default=2, help="layers printed in full")
+    ap.add_argument("--json", action="store_true", help="print one JSON summary line instead of the table (used by bench.py)")
     a = ap.parse_args()
     cfg = synth.get_config(a.model)
     ctx = native.Context(0)
@@ -39,6 +40,16 @@ def main():
     rows = [buf[i] for i in range(n0, n) if buf[i][1] > 0]
     rows.sort(key=lambda r: int(r[0]))
     t0 = int(rows[0][0])
+    if a.json:
+        import json
+        gemv_us = sum((int(r[1]) - int(r[0])) / 1e3 for r in rows if (int(r[3]) & 0xF00) == 0x100)
+        attn_us = sum((int(r[1]) - int(r[0])) / 1e3 for r in rows if (int(r[3]) & 0xF00) == 0xA00)
+        print(json.dumps({"model": a.model, "position": a.prompt + 8, "traced_launches": len(rows), "step_ms_events": tot_ms,
+                          "gemv_launches": sum(1 for r in rows if (int(r[3]) & 0xF00) == 0x100), "gemv_us": gemv_us,
+                          "attention_us": attn_us, "span_us": (int(rows[-1][1]) - t0) / 1e3}), flush=True)
+        m.close()
+        ctx.close()
+        return
     print("# %s flags=%d JL_PF=%s: %d traced launches, event-timed step %.3f ms, trace span %.3f ms" % (
         a.model, a.flags, os.environ.get("JL_PF", "0"), len(rows), tot_ms, (int(rows[-1][1]) - t0) / 1e6))
     print("# kind                        start_us   dur_us  prologue_us  gap_before_us")
