@@ -26,3 +26,19 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+def test_product_arm_fails_loudly_without_a_gpu():
+    """No CPU fallback: without a CUDA device the product arm must exit non-zero with a clear message and print no JSON."""
+    import pytest
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--model", "tiny", "--steps", "3", "--warmup", "3"], cwd=ROOT,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0
+    assert "no CPU fallback" in r.stderr
+    assert not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
