@@ -13,13 +13,11 @@ batch-1 greedy decode after a short prompt.  One "step" = one decoded token (for
   e2e   : tokens/s through the reference-facing call -- jl_model_generate (AbstractModel.generate at temperature 0)
           with HOST token buffers: every decoded token copies token/position/session ids host->device from pinned
           memory and the sampled token back (a host round trip per step inside the timed region).
-  roofline : dominant kernel = the quantised GEMV; achieved = algorithmic weight bytes per token
-          (0.625 B/weight Q4 incl. f32 block scales) / summed GEMV launch durations per token
-          measured with CUDA events around every GEMV launch (eager, un-overlapped); peak = MEASURED_PEAKS.json.
-          step_frac = the same bytes / whole-step time (the north-star "fraction of HBM roofline").
-          in_graph = the same bytes / the GEMV launches' summed durations inside one replayed CUDA graph, from device-side
-          %globaltimer stamps (tools/ktrace.py run as a child process): the eager event timing above also contains the
-          stream's ~2 us launch quantum per launch.
+  roofline : achieved = algorithmic weight bytes per token (0.625 B/weight Q4 incl. f32 block scales) / the time
+          of the weight-streaming kernel inside the timed region: the persistent decode kernel is the step itself (one
+          launch per token, CUDA events over the timed region); for the per-op graph path the GEMV launches' summed
+          durations come from device-side %globaltimer stamps inside one replayed graph (tools/ktrace.py child process).
+          step_frac = the same bytes / whole-step time (the north-star "fraction of HBM roofline"); peak = MEASURED_PEAKS.json.
   cpu_baseline : the oracle driving the reference's own C kernels (oracle/_ref) on a bounded sample, with Jlama's default
           thread count (half the available CPUs); `--impl reference` uses all of them.
   config.prefill : tokens/s of a 2048-token prompt on the tcgen05 prefill path (N = 1 only).
@@ -135,12 +133,35 @@ def measured_traffic(cfg):
     return d["layers"] * (per["qkv"] + per["o_proj"] + per["gate_up"] + per["down"]) + d["algorithmic_bytes"]["lm_head"]
 
 
-def make_model_weights(cfg, mode):
+def make_model_weights(cfg, mode, q4_fn=None):
+    """Synthetic checkpoint with the real dims.  mode "quantize" (default): W ~ N(0, 0.02^2) f32 quantised with the
+    reference quantiser semantics -- by the GPU weight quantiser (jl_quantize_q4_weights, byte-identical to
+    the reference's Q4ByteBufferTensor constructor, tests/test_gpu_ops.py) in the product arm, by the oracle's C
+    quantiser in the reference arm; same seeds, same bytes."""
     from jlama_b200 import native, synth
     t0 = time.time()
-    w = synth.make_weights(cfg, wdtype=native.Q4, mode=mode)
+    w = synth.make_weights(cfg, wdtype=native.Q4, mode=mode, q4_fn=q4_fn)
     log("[bench] synthetic %s checkpoint (%s) generated in %.1fs" % (cfg["name"], mode, time.time() - t0))
     return w
+
+
+def gpu_q4_quantizer(ctx):
+    from jlama_b200 import native
+
+    def q4(x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        q = np.empty((x.shape[0], x.shape[1] // 2), dtype=np.uint8)
+        sc = np.empty((x.shape[0], x.shape[1] // 32), dtype=np.float32)
+        ctx.check(ctx.lib.jl_quantize_q4_weights(ctx.h, native.ptr(x), x.shape[0], x.shape[1], native.ptr(q), native.ptr(sc)))
+        return q, sc
+    return q4
+
+
+def first_divergence(a, b):
+    for i, (x, y) in enumerate(zip(a, b)):
+        if int(x) != int(y):
+            return i
+    return None
 
 
 def cpu_reference_decode(cfg, weights, prompt, n_new, threads=None):
@@ -174,10 +195,10 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cfg = synth.get_config(args.model)
-    w = make_model_weights(cfg, args.weights)
+    from oracle import oracle as o
+    w = make_model_weights(cfg, args.weights, q4_fn=o.quantize_q4)
     prompt = synth.random_prompt(cfg, args.prompt)
     n = args.warmup + args.steps
-    from oracle import oracle as o
     label = o.load_reference_kernels()
     o.use_reference_kernels(label is not None)
     # "all the host threads it can use", capped where more threads stop helping a bandwidth-bound GEMV
@@ -221,9 +242,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="llama-3-8b")
-    ap.add_argument("--weights", default="direct", choices=["direct", "quantize"])
+    ap.add_argument("--weights", default="quantize", choices=["direct", "quantize"])
     ap.add_argument("--prompt", type=int, default=32)
-    ap.add_argument("--cpu-tokens", type=int, default=6, help="decode steps of the cpu_baseline sample")
+    ap.add_argument("--cpu-tokens", type=int, default=33, help="tokens generated by the cpu_baseline / parity sample (1 + decode steps)")
     ap.add_argument("--prefill-tokens", type=int, default=2048, help="prompt length of the tensor-core prefill measurement (0 = skip)")
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -264,7 +285,7 @@ def main():
         idbuf = t.cpu().numpy()
         ctx.check(ctx.lib.jl_comm_init(ctx.h, native.ptr(idbuf), rank, world))
 
-    weights = make_model_weights(cfg, args.weights)
+    weights = make_model_weights(cfg, args.weights, q4_fn=gpu_q4_quantizer(ctx))
     prompt = synth.random_prompt(cfg, args.prompt)
     n_total = args.prompt + 2 * (args.warmup + args.steps) + 64
     t0 = time.time()
@@ -345,44 +366,29 @@ def main():
     }
 
     # ---- roofline of the dominant kernel -------------------------------------------------------------------------------
+    # step_frac: algorithmic weight bytes of one token / the whole event-timed step (the north-star number).
+    # frac: the same bytes / the time the weight-streaming kernel(s) actually ran inside the step -- for the persistent
+    # decode kernel that IS the step (one launch per token); for the graph of per-op kernels it is the summed
+    # (last CTA end - first CTA start) of the GEMV launches inside one replayed graph from device-side %globaltimer
+    # stamps (tools/ktrace.py in a child process).  Never an eager per-launch event sum.
     mode = model.decode_mode(1)
-    step_frac = (wbytes / 1e9) / (total_ms / args.steps / 1e3) / peak
-    if mode == 2:
-        # the persistent megakernel IS the step: one launch per token, timed with CUDA events on the model stream
-        achieved = (wbytes / 1e9) / (total_ms / args.steps / 1e3)
-        result["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                              "traffic": None, "kernel": "mega_decode_kernel (one launch per decoded token)",
-                              "bytes_per_launch": wbytes, "us_per_launch": 1000.0 * total_ms / args.steps,
-                              "peak_source": peak_src, "step_frac": step_frac}
-    elif not args.no_roofline:
-        # kernel-per-op path: eager, event-timed GEMV launches (rank 0 shard; same on every rank)
-        model.close()
-        model = LlamaModel(ctx, cfg, weights, max_context=min(cfg["ctx"], max(512, n_total)), tp_rank=rank, tp_size=world,
-                           flags=native.MODEL_NO_GRAPH)
-        model.reset_session(0)
-        model.batch_forward(prompt, 0)
-        f2, _ = model.sample(want_logits=False)
-        model.decode_resident(f2, len(prompt), 8)
-        nprof = min(32, args.steps)
-        model.decode_resident(f2, len(prompt) + 8, nprof)
-        tot, gemv = model.last_timing()
-        gemv_ms = max_over_ranks(gemv) / nprof
-        achieved = wbytes / 1e9 / (gemv_ms / 1e3)
-        result["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                              "traffic": measured_traffic(cfg) if world == 1 else None,
-                              "kernel": "gemv_decode_kernel x4 per layer + lm_head gemv_kernel (all quantised GEMV launches of one token)",
-                              "bytes_per_launch_set": wbytes, "gemv_ms_per_token": gemv_ms, "peak_source": peak_src,
-                              "step_frac": step_frac}
-    else:
-        result["roofline"] = {"bound": "hbm", "achieved": step_frac * peak, "peak": peak, "unit": "GB/s", "frac": step_frac,
-                              "traffic": None, "peak_source": peak_src, "note": "whole-step time used (roofline pass skipped)"}
-    result["config"]["decode_mode"] = {2: "persistent megakernel", 1: "cuda graph of per-op kernels", 0: "eager"}[mode]
+    step_ms = total_ms / args.steps
+    step_frac = (wbytes / 1e9) / (step_ms / 1e3) / peak
+    mode_name = {3: "persistent decode kernel (one cooperative launch per token)", 2: "persistent megakernel (round 1)",
+                 1: "cuda graph of per-op kernels", 0: "eager"}.get(mode, str(mode))
+    result["config"]["decode_mode"] = mode_name
+    result["roofline"] = {"bound": "hbm", "achieved": step_frac * peak, "peak": peak, "unit": "GB/s", "frac": step_frac,
+                          "traffic": measured_traffic(cfg) if world == 1 else None, "peak_source": peak_src, "step_frac": step_frac,
+                          "bytes_per_token": wbytes, "us_per_token": 1000.0 * step_ms,
+                          "kernel": "pdecode_kernel (all weight GEMVs, attention, lm_head + argmax of one token)" if mode >= 2 else
+                                    "gemv_decode_kernel x4 per layer + lm_head gemv_kernel",
+                          "method": "algorithmic bytes per token / CUDA-event time of the timed region / steps"}
 
-    # ---- prefill throughput on the tcgen05 GEMM path (BASELINE config 3 shape: 2048-token prompt) -----------------------
+    # ---- prefill throughput (BASELINE config 3 shape: 2048-token prompt) and a long-context decode point ----------------
     if world == 1 and args.prefill_tokens > 0:
         model.close()
-        ptoks = min(args.prefill_tokens, cfg["ctx"] - 8)
-        pm = LlamaModel(ctx, cfg, weights, max_context=ptoks + 8, prefill_tensor_core=1)
+        ptoks = min(args.prefill_tokens, cfg["ctx"] - 72)
+        pm = LlamaModel(ctx, cfg, weights, max_context=ptoks + 72, prefill_tensor_core=1)
         long_prompt = synth.random_prompt(cfg, ptoks, seed=99)
         pm.reset_session(0)
         pm.batch_forward(long_prompt[:512], 0)  # warm-up
@@ -395,43 +401,75 @@ def main():
         flops = 2.0 * (synth.linear_weight_count(cfg) - cfg["vocab"] * cfg["E"]) * ptoks
         result["config"]["prefill"] = {"tokens": ptoks, "tokens_per_s": ptoks / dt, "path": "tcgen05 BF16 GEMM (fused Q4 dequant) + f32 paged attention",
                                        "linear_tflops": flops / dt / 1e12}
+        # decode at position ~ptoks: the KV read (layers * 2 * kvLength * 4 B * (p+1), F32 KV) joins the numerator
+        lf, _ = pm.sample(want_logits=False)
+        pm.decode_resident(lf, ptoks, 8)
+        nlong = 32
+        pm.decode_resident(lf, ptoks + 8, nlong)
+        lms, _ = pm.last_timing()
+        hs = cfg["E"] // cfg["heads"]
+        kv_bytes = cfg["layers"] * 2 * cfg["kv_heads"] * hs * 4 * (ptoks + 8 + nlong / 2.0 + 1)
+        lstep = lms / nlong / 1e3
+        result["config"]["decode_long_context"] = {
+            "position": ptoks + 8, "tokens_per_s": 1.0 / lstep, "ms_per_step": 1e3 * lstep, "kv_bytes_per_token": kv_bytes,
+            "frac_of_hbm_peak_weights_plus_kv": (wbytes + kv_bytes) / 1e9 / lstep / peak}
         pm.close()
         model = LlamaModel(ctx, cfg, weights, max_context=min(cfg["ctx"], max(512, n_total)))
 
-    # ---- cpu_baseline + in-run parity (rank 0, N=1 only) --------------------------------------------------------------
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_cpu = max(2, args.cpu_tokens)
-        cp = prompt[:min(len(prompt), 8)]
-        r = cpu_reference_decode(cfg, weights, cp, n_cpu, threads=args.cpu_threads or None)
+    # ---- cpu_baseline + in-run parity ----------------------------------------------------------------------------------
+    # N = 1: the GPU generates 1 + 32 tokens after the 32-token prompt and is compared with the reference-equivalent CPU
+    # path (reference C kernels under the restated orchestration) on the same prompt; logits are compared up to and
+    # including the first divergent token (afterwards the two sides see different inputs).
+    # N > 1: rank 0 runs OracleLlama(tp=N) -- shard-wise partial sums added in rank order -- on a shorter sample.
+    if not args.no_cpu_baseline:
+        n_cpu = max(2, args.cpu_tokens if world == 1 else min(args.cpu_tokens, 9))
+        cp = prompt if world == 1 else prompt[:min(len(prompt), 8)]
+        r = None
+        if rank == 0:
+            if world == 1:
+                r = cpu_reference_decode(cfg, weights, cp, n_cpu, threads=args.cpu_threads or None)
+            else:
+                from oracle import oracle as o
+                label = o.load_reference_kernels()
+                o.use_reference_kernels(label is not None)
+                o.set_num_threads(args.cpu_threads or o.available_cpus())
+                om = o.OracleLlama(cfg, weights, act_q8=True, tp=world)
+                t0 = time.time()
+                pt, pl = om.generate(cp, n_cpu)
+                om.close()
+                r = dict(tokens=list(pt), logits=pl, label="OracleLlama(tp=%d), %s" % (world, label or "plain-C port"),
+                         decode_s=time.time() - t0, threads=o.num_threads())
+        barrier()
         gt, gl = model.generate(cp, n_cpu, want_logits=True)
-        rel = max(float(np.abs(gl[i] - r["logits"][i]).max() / np.abs(r["logits"][i]).max()) for i in range(n_cpu))
-        result["cpu_baseline"] = {"value": (n_cpu - 1) / r["decode_s"], "unit": "tokens/s", "cores": r["threads"], "kind": r["kind"],
-                                  "sample": "%d decode steps after an %d-token prompt, %s" % (n_cpu - 1, len(cp), r["label"]),
-                                  "prefill_tokens_per_s": len(cp) / r["prefill_s"]}
-        result["parity"] = {"tokens_equal": [int(a) for a in gt] == [int(b) for b in r["tokens"]], "max_logit_rel_err": rel,
-                            "tolerance": 1e-2, "against": r["label"],
-                            "note": "the 32-layer synthetic network amplifies summation-order differences through the per-layer Q8 "
-                                    "re-quantisation: the reference's AVX kernels and the plain-C port of the same arithmetic "
-                                    "differ from each other by the same amount (cpu_reference_kernels_vs_plain_c_port); on "
-                                    "test-size models the GPU matches the oracle to 1e-5 (tests/), see DESIGN.md section 6"}
-        if args.parity_port_tokens > 0:
-            from oracle import oracle as o
-            o.use_reference_kernels(False)
-            om = o.OracleLlama(cfg, weights, act_q8=True)
-            n_p = args.parity_port_tokens
-            pt, pl = om.generate(cp, n_p)
-            om.close()
-            relp = max(float(np.abs(gl[i] - pl[i]).max() / np.abs(pl[i]).max()) for i in range(n_p))
-            result["parity"]["vs_plain_c_port"] = {"tokens_equal": [int(a) for a in gt[:n_p]] == [int(b) for b in pt],
-                                                   "max_logit_rel_err": relp, "tokens": n_p}
-            # yardstick: how far the two CPU implementations of the same arithmetic are from each other on this network
-            relc = max(float(np.abs(np.asarray(r["logits"][i]) - pl[i]).max() / np.abs(pl[i]).max()) for i in range(n_p))
-            result["parity"]["cpu_reference_kernels_vs_plain_c_port"] = relc
+        if rank == 0:
+            div = first_divergence(gt, r["tokens"])
+            upto = n_cpu if div is None else div + 1
+            rel = max(float(np.abs(gl[i] - r["logits"][i]).max() / np.abs(r["logits"][i]).max()) for i in range(upto))
+            if world == 1:
+                result["cpu_baseline"] = {"value": (n_cpu - 1) / r["decode_s"], "unit": "tokens/s", "cores": r["threads"], "kind": r["kind"],
+                                          "sample": "%d decode steps after a %d-token prompt, %s" % (n_cpu - 1, len(cp), r["label"]),
+                                          "prefill_tokens_per_s": len(cp) / r["prefill_s"]}
+            result["parity"] = {"tokens_equal": div is None, "tokens_compared": n_cpu, "tokens_equal_count": n_cpu if div is None else div,
+                                "first_divergent_position": div, "max_logit_rel_err": rel, "logits_compared_steps": upto,
+                                "tolerance": 1e-2, "against": r["label"], "prompt_tokens": len(cp), "weights": args.weights}
+            if world == 1 and args.parity_port_tokens > 0:
+                from oracle import oracle as o
+                o.use_reference_kernels(False)
+                om = o.OracleLlama(cfg, weights, act_q8=True)
+                n_p = args.parity_port_tokens
+                pt, pl = om.generate(cp, n_p)
+                om.close()
+                relp = max(float(np.abs(gl[i] - pl[i]).max() / np.abs(pl[i]).max()) for i in range(n_p))
+                result["parity"]["vs_plain_c_port"] = {"tokens_equal": [int(a) for a in gt[:n_p]] == [int(b) for b in pt],
+                                                       "max_logit_rel_err": relp, "tokens": n_p}
+                # yardstick: how far the two CPU implementations of the same arithmetic are from each other on this network
+                relc = max(float(np.abs(np.asarray(r["logits"][i]) - pl[i]).max() / np.abs(pl[i]).max()) for i in range(n_p))
+                result["parity"]["cpu_reference_kernels_vs_plain_c_port"] = relc
+                result["parity"]["note"] = ("single-layer teacher-forced parity at the 8B shapes is in tests/test_gpu_layer8b.py; "
+                                            "cpu_reference_kernels_vs_plain_c_port is the distance between two CPU implementations of "
+                                            "the same arithmetic on this 32-layer network (summation order only)")
     model.close()
-    if rank == 0 and world == 1 and not args.no_roofline and "roofline" in result:
-        # The event-timed eager launches above include the stream's launch overhead (back-to-back 5-15 us launches are
-        # quantised to ~2 us on this stack).  For the kernels' duration inside the replayed CUDA graph, a child process
-        # runs tools/ktrace.py (device-side %globaltimer stamps per launch); a failure there only omits the field.
+    if rank == 0 and world == 1 and not args.no_roofline and mode == 1:
         try:
             r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ktrace.py"), "--json", "--model", args.model],
                                cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=240)
@@ -439,11 +477,11 @@ def main():
             if r.returncode == 0 and lines:
                 t = json.loads(lines[-1])
                 ach = wbytes / 1e9 / (t["gemv_us"] * 1e-6)
-                result["roofline"]["in_graph"] = {
+                result["roofline"].update({
                     "achieved": ach, "frac": ach / peak, "gemv_us_per_token": t["gemv_us"], "attention_us_per_token": t["attention_us"],
-                    "step_ms": t["step_ms_events"], "position": t["position"],
-                    "method": "sum of per-launch (last CTA end - first CTA start) from %globaltimer stamps inside one replayed "
-                              "decode graph (tools/ktrace.py); stamps add ~1% to the step"}
+                    "timeline_step_ms": t["step_ms_events"], "position": t["position"],
+                    "method": "algorithmic bytes / sum of per-launch (last CTA end - first CTA start) of the GEMV launches inside one "
+                              "replayed decode graph, %globaltimer stamps (tools/ktrace.py); stamps add ~1% to the step"})
         except Exception as e:  # noqa: BLE001 -- diagnostics must never break the bench line
             log("[bench] in-graph timeline skipped: %r" % (e,))
     if rank == 0:

@@ -178,7 +178,7 @@ typedef struct {
     int max_sessions;    /* concurrent KvBuffers (KvBufferCache.java:58-60) */
     int max_context;     /* positions to reserve pages for (<= context_length); 0 = context_length */
     int tp_rank, tp_size; /* jlama-net model shard (DistributedContext modelShard/numModelShards) */
-    int prefill_tensor_core; /* 1: M>=64 GEMMs use the tcgen05 BF16 path; 0: exact-integer SIMT path */
+    int prefill_tensor_core; /* 1: prompt chunks of >= 16 rows use the tcgen05 BF16 GEMM path; 0: exact-integer SIMT path */
     int flags;           /* JL_MODEL_* */
 } jl_model_config;
 

@@ -267,12 +267,8 @@ static size_t att_smem_bytes() {
 template <int HS>
 static int launch_att(jl_ctx *ctx, cudaStream_t s, const AttnParams &p, bool pdl) {
     const size_t smem = att_smem_bytes<HS>();
-    static bool configured = false;
-    if (!configured && smem > 48 * 1024) {
-        JL_CUDA_CHECK(ctx, cudaFuncSetAttribute(paged_attention_kernel<HS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)smem));
-        configured = true;
-    }
+    static size_t configured[JL_MAX_DEVICES] = {};
+    JL_CUDA_CHECK(ctx, jl_ensure_dyn_smem(paged_attention_kernel<HS>, ctx->device, smem, configured));
     JL_CUDA_CHECK(ctx, jl_launch_kernel(paged_attention_kernel<HS>, dim3(p.kv_heads, p.rows, p.splits), dim3(ATT_THREADS),
                                         smem, s, pdl, p));
     ctx->launches++;
@@ -334,11 +330,8 @@ __global__ void __launch_bounds__(FDA_THREADS) fused_decode_attention_kernel(con
 template <int HS, int KVDT>
 static int launch_fda_k(jl_ctx *ctx, cudaStream_t s, const AttnTask &t, int layer, int rows, unsigned *done_cnt, bool pdl) {
     const size_t smem = attention_task_smem<HS, FDA_THREADS>();
-    static bool configured = false;
-    if (!configured && smem > 40 * 1024) {
-        JL_CUDA_CHECK(ctx, cudaFuncSetAttribute(fused_decode_attention_kernel<HS, KVDT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static size_t configured[JL_MAX_DEVICES] = {};
+    JL_CUDA_CHECK(ctx, (jl_ensure_dyn_smem(fused_decode_attention_kernel<HS, KVDT>, ctx->device, smem, configured)));
     unsigned long long *trace = jl_ktrace_slot(ctx);
     JL_CUDA_CHECK(ctx, jl_launch_kernel(fused_decode_attention_kernel<HS, KVDT>, dim3(t.kv_heads, rows, t.splits), dim3(FDA_THREADS), smem,
                                         s, pdl, t, layer, done_cnt, trace));

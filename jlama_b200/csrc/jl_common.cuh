@@ -19,6 +19,8 @@ struct DevTensor {
     void *data = nullptr;    // f32 / bf16 / packed nibbles / int8
     float *scales = nullptr; // [rows, cols/32] for Q4 / I8
     size_t bytes = 0;
+    int64_t id = 0;          // registry id (0 for views / temporaries)
+    int refs = 0;            // models this tensor is bound to (jl_model_set_tensor); unregister refuses while > 0
 };
 
 struct jl_ctx {
@@ -28,6 +30,7 @@ struct jl_ctx {
     std::mutex mu;
     std::string last_error;
     std::unordered_map<int64_t, DevTensor> tensors;
+    std::vector<struct jl_model *> models; // live models (freed by jl_shutdown before the tensors they point at)
     int64_t next_id = 1;
     long long launches = 0;
     // op-level scratch (grown on demand)
@@ -51,6 +54,20 @@ int jl_set_error(jl_ctx *ctx, int code, const char *fmt, ...);
     } while (0)
 
 void *jl_scratch(jl_ctx *ctx, int slot, size_t bytes); // nullptr on OOM
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: remember what was set per (device, kernel)
+// so that a second context on another GPU of the same process configures its own copy.
+#define JL_MAX_DEVICES 64
+template <typename K>
+static inline cudaError_t jl_ensure_dyn_smem(K kernel, int device, size_t bytes, size_t (&configured)[JL_MAX_DEVICES]) {
+    if (bytes <= 40 * 1024) return cudaSuccess; // static shared memory counts against the 48 KB default too
+    const int d = device >= 0 && device < JL_MAX_DEVICES ? device : 0;
+    if (bytes <= configured[d]) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) configured[d] = bytes;
+    return e;
+}
+// called when the timeline buffer is replaced: captured graphs hold the old slot pointers
+void jl_models_invalidate_graphs(jl_ctx *ctx);
 
 // ---------------------------------------------------------------------------------------------
 // Quantised GEMV / small-M GEMM (jl_gemv.cu)
@@ -109,6 +126,7 @@ struct GemvParams {
 
 // Launch on `stream`.  use_pdl: launch with the programmatic-stream-serialization attribute.
 int jl_launch_gemv(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int prologue, int epilogue, bool use_pdl);
+int jl_gemv_max_m(int w_dtype, int prologue, int K); // largest M chunk (1/2/4/8) that fits shared memory, 0 if none
 
 // ---------------------------------------------------------------------------------------------
 // Element-wise / normalisation / sampling kernels (jl_elementwise.cu)

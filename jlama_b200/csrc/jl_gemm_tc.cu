@@ -235,11 +235,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_q4_tc_kernel(const TcParam
 template <int BN>
 static int launch_tc(jl_ctx *ctx, cudaStream_t stream, const TcParams &p) {
     const size_t smem = (size_t)TC_STAGES * (TC_WTILE_BYTES + (size_t)BN * TC_BK * 2) + 1024;
-    static bool configured = false;
-    if (!configured) {
-        JL_CUDA_CHECK(ctx, cudaFuncSetAttribute(gemm_q4_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static size_t configured[JL_MAX_DEVICES] = {};
+    JL_CUDA_CHECK(ctx, jl_ensure_dyn_smem(gemm_q4_tc_kernel<BN>, ctx->device, smem, configured));
     dim3 grid(p.N / TC_BM, (p.T + BN - 1) / BN);
     gemm_q4_tc_kernel<BN><<<grid, TC_THREADS, smem, stream>>>(p);
     ctx->launches++;

@@ -919,11 +919,8 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_dense_kernel(const GemvPara
 // ---- host launcher ---------------------------------------------------------------------------------
 template <typename KERN>
 static int launch_kern(jl_ctx *ctx, cudaStream_t stream, KERN kern, const GemvParams &p, int prologue, bool pdl, int grid,
-                       int threads, size_t smem, size_t &configured) {
-    if (smem > 40 * 1024 && smem > configured) { // static shared memory of the prologue counts against the 48 KB default too
-        JL_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+                       int threads, size_t smem, size_t (&configured)[JL_MAX_DEVICES]) {
+    JL_CUDA_CHECK(ctx, jl_ensure_dyn_smem(kern, ctx->device, smem, configured));
     JL_CUDA_CHECK(ctx, jl_launch_kernel(kern, dim3(grid), dim3(threads), smem, stream, pdl, p, prologue));
     ctx->launches++;
     return JL_OK;
@@ -942,7 +939,7 @@ static int generic_grid(jl_ctx *ctx, int rows, int max_per_sm) {
 // decode hot path: one big CTA per SM, prologue fixed at compile time
 template <int WDT, int EPI, int PRO, int NT, int NBUF, int CH, bool PDL, bool LONG>
 static int launch_decode_k(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int grid, size_t smem) {
-    static thread_local size_t configured = 0;
+    static size_t configured[JL_MAX_DEVICES] = {};
     return launch_kern(ctx, stream, gemv_decode_kernel<WDT, EPI, PRO, CH, NBUF, NT, PDL, LONG>, p, 0, PDL, grid, NT, smem, configured);
 }
 
@@ -987,7 +984,7 @@ static int launch_q(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int p
             return launch_decode<WDT, EPI, PRO_RMSNORM_QUANT, NT, NB, 4>(ctx, stream, p, pdl, smem);
     }
     constexpr int MINB = (MM <= 2) ? 2 : 1;
-    static thread_local size_t cfg = 0;
+    static size_t cfg[JL_MAX_DEVICES] = {};
     return launch_kern(ctx, stream, gemv_kernel<WDT, ACTQ8, EPI, MM, 4, 2, MINB>, p, prologue, pdl,
                        generic_grid(ctx, p.total_rows, MINB), GEMV_THREADS, smem, cfg);
 }
@@ -1015,8 +1012,8 @@ static int launch_dense(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, i
     auto kern = gemv_dense_kernel<WDT, EPI, MM>;
     size_t smem = (size_t)MM * p.K * 4;
     if (smem > 200 * 1024) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "dense gemv: M*K too large for shared memory");
-    if (smem > 40 * 1024)
-        JL_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t cfg[JL_MAX_DEVICES] = {};
+    JL_CUDA_CHECK(ctx, jl_ensure_dyn_smem(kern, ctx->device, smem, cfg));
     JL_CUDA_CHECK(ctx, jl_launch_kernel(kern, dim3(grid), dim3(GEMV_THREADS), smem, stream, pdl, p, prologue));
     ctx->launches++;
     return JL_OK;
@@ -1028,6 +1025,18 @@ static int launch_dense_m(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p,
     if (p.M <= 2) return launch_dense<WDT, EPI, 2>(ctx, stream, p, prologue, pdl, grid);
     if (p.M <= 4) return launch_dense<WDT, EPI, 4>(ctx, stream, p, prologue, pdl, grid);
     return launch_dense<WDT, EPI, 8>(ctx, stream, p, prologue, pdl, grid);
+}
+
+// Largest activation-row chunk (1, 2, 4 or 8) whose staged activations fit the kernels' shared-memory budget; 0 = even one
+// row does not fit.  Callers split M into chunks of this size (the reference's F32 x Q4 GEMM has no such limit,
+// PanamaTensorOperations.java:289-548).
+int jl_gemv_max_m(int w_dtype, int prologue, int K) {
+    const bool quant_w = (w_dtype == JL_Q4 || w_dtype == JL_I8);
+    const bool actq8 = quant_w && (prologue == PRO_Q8_GLOBAL || prologue == PRO_F32_QUANT || prologue == PRO_RMSNORM_QUANT);
+    const size_t smem1 = actq8 ? (size_t)(K / 32) * 40 : (size_t)K * 4;
+    for (int mm = GEMV_MAX_M; mm >= 1; mm >>= 1)
+        if (smem1 * mm <= 200 * 1024) return mm;
+    return 0;
 }
 
 int jl_launch_gemv(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p_in, int prologue, int epilogue, bool use_pdl) {

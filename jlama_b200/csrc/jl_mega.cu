@@ -756,11 +756,8 @@ static int launch_mega(jl_ctx *ctx, cudaStream_t stream, MegaParams p) {
     auto kern = mega_decode_kernel<MM>;
     p.uarea_bytes = (int)uarea_bytes(p, MM);
     const size_t smem = (size_t)p.uarea_bytes + (size_t)p.layers * sizeof(MegaLayer);
-    static size_t configured = 0;
-    if (smem > configured) {
-        JL_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static size_t configured[JL_MAX_DEVICES] = {};
+    JL_CUDA_CHECK(ctx, jl_ensure_dyn_smem(kern, ctx->device, smem, configured));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ctx->sm_count);
     cfg.blockDim = dim3(MG_THREADS);

@@ -27,6 +27,7 @@ struct jl_model {
     bool g_set[3] = {false, false, false};
     std::vector<DevTensor> l; // [layers][9]
     std::vector<char> l_set;
+    std::vector<int64_t> bound_ids; // registry ids whose refs this model holds (one entry per set_tensor call)
     int group = 1, attn_seg = 0, kv_seg = 0, h_seg = 0, heads_local = 0, kv_heads_local = 0;
     // rope
     float *rope = nullptr;
@@ -124,6 +125,10 @@ extern "C" int jl_model_create(jl_ctx *ctx, const jl_model_config *cfg, jl_model
     m->l.resize((size_t)c.num_layers * 9);
     m->l_set.assign((size_t)c.num_layers * 9, 0);
     m->max_context = c.max_context > 0 && c.max_context < c.context_length ? c.max_context : c.context_length;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->models.push_back(m);
+    }
     *out = m;
     return JL_OK;
 }
@@ -134,7 +139,22 @@ extern "C" int jl_model_set_tensor(jl_model *m, int layer, int slot, int64_t ten
     std::lock_guard<std::mutex> lk(ctx->mu);
     auto it = ctx->tensors.find(tensor_id);
     if (it == ctx->tensors.end()) return jl_set_error(ctx, JL_ERR_INVALID, "model_set_tensor: unknown tensor id");
-    const DevTensor &t = it->second;
+    if (m->finalized) return jl_set_error(ctx, JL_ERR_INVALID, "model_set_tensor: model already finalized");
+    DevTensor &t = it->second;
+    auto bind = [&](DevTensor &slot_t, bool was_set) {
+        if (was_set && slot_t.id) {
+            auto old = ctx->tensors.find(slot_t.id);
+            if (old != ctx->tensors.end() && old->second.refs > 0) old->second.refs--;
+            for (size_t i = 0; i < m->bound_ids.size(); i++)
+                if (m->bound_ids[i] == slot_t.id) {
+                    m->bound_ids.erase(m->bound_ids.begin() + i);
+                    break;
+                }
+        }
+        t.refs++;
+        m->bound_ids.push_back(t.id);
+        slot_t = t;
+    };
     const jl_model_config &c = m->cfg;
     const int E = c.embedding_length;
     auto expect = [&](int64_t rows, int64_t cols) {
@@ -150,7 +170,7 @@ extern "C" int jl_model_set_tensor(jl_model *m, int layer, int slot, int64_t ten
             if (t.dtype != JL_F32 && t.dtype != JL_BF16) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "norm weights must be F32/BF16");
         } else
             M_CHECK(expect(c.vocab_size, E));
-        m->g[slot] = t;
+        bind(m->g[slot], m->g_set[slot]);
         m->g_set[slot] = true;
         return JL_OK;
     }
@@ -169,7 +189,7 @@ extern "C" int jl_model_set_tensor(jl_model *m, int layer, int slot, int64_t ten
         case JL_L_UP: M_CHECK(expect(m->h_seg, E)); break;
         case JL_L_DOWN: M_CHECK(expect(E, m->h_seg)); break;
     }
-    m->l[(size_t)layer * 9 + slot] = t;
+    bind(m->l[(size_t)layer * 9 + slot], m->l_set[(size_t)layer * 9 + slot] != 0);
     m->l_set[(size_t)layer * 9 + slot] = 1;
     return JL_OK;
 }
@@ -192,6 +212,17 @@ extern "C" int jl_model_finalize(jl_model *m) {
         if (!m->g_set[i]) return jl_set_error(ctx, JL_ERR_INVALID, "model_finalize: global tensor %d missing", i);
     for (size_t i = 0; i < m->l_set.size(); i++)
         if (!m->l_set[i]) return jl_set_error(ctx, JL_ERR_INVALID, "model_finalize: layer %zu slot %zu missing", i / 9, i % 9);
+    // the fused QKV and gate+up launches decode all their segments with one weight dtype: a checkpoint that mixes
+    // precisions inside a fused group (e.g. Q in Q4, K/V left in BF16) must be rejected, not mis-read
+    for (int L = 0; L < c.num_layers; L++) {
+        const DevTensor *lw = &m->l[(size_t)L * 9];
+        if (lw[JL_L_K].dtype != lw[JL_L_Q].dtype || lw[JL_L_V].dtype != lw[JL_L_Q].dtype)
+            return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "model_finalize: layer %d q/k/v weights must share one dtype (got %d/%d/%d)", L,
+                                lw[JL_L_Q].dtype, lw[JL_L_K].dtype, lw[JL_L_V].dtype);
+        if (lw[JL_L_UP].dtype != lw[JL_L_GATE].dtype)
+            return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "model_finalize: layer %d gate/up weights must share one dtype (got %d/%d)", L,
+                                lw[JL_L_GATE].dtype, lw[JL_L_UP].dtype);
+    }
     const int E = c.embedding_length, hs = c.head_size;
     JL_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     // RoPE table (Config.java:271-276) padded by 2*kv_heads positions: head h reads position pos+2*kvh
@@ -300,11 +331,33 @@ extern "C" int jl_model_finalize(jl_model *m) {
 
 extern "C" int64_t jl_model_weight_bytes(jl_model *m) { return m ? m->weight_bytes : -1; }
 
+// The timeline buffer was replaced (jl_debug_ktrace): drop every captured decode graph, they are re-captured on demand.
+void jl_models_invalidate_graphs(jl_ctx *ctx) {
+    for (jl_model *m : ctx->models) {
+        if (m->stream) cudaStreamSynchronize(m->stream);
+        for (auto &kv : m->graphs) cudaGraphExecDestroy(kv.second);
+        m->graphs.clear();
+        m->graph_launches.clear();
+    }
+}
+
 extern "C" int jl_model_free(jl_model *m) {
     if (!m) return JL_ERR_INVALID;
     jl_ctx *ctx = m->ctx;
     cudaSetDevice(ctx->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        for (int64_t id : m->bound_ids) {
+            auto it = ctx->tensors.find(id);
+            if (it != ctx->tensors.end() && it->second.refs > 0) it->second.refs--;
+        }
+        for (size_t i = 0; i < ctx->models.size(); i++)
+            if (ctx->models[i] == m) {
+                ctx->models.erase(ctx->models.begin() + i);
+                break;
+            }
+    }
     for (auto &kv : m->graphs) cudaGraphExecDestroy(kv.second);
     for (void *p : m->page_table_host)
         if (p) cudaFree(p);
@@ -376,9 +429,12 @@ static int run_gemm(jl_model *m, GemvParams p, int prologue, int epilogue, int M
                     bool allow_pdl = true) {
     jl_ctx *ctx = m->ctx;
     if (timed) cudaEventRecord(next_event(m), m->stream);
-    for (int m0 = 0; m0 < M; m0 += GEMV_MAX_M) {
+    // rows per launch: as many as the staged activations allow (F32 activations at K = 14336 fit 2 rows, Q8 all 8)
+    const int chunk = jl_gemv_max_m(p.w_dtype, prologue, p.K);
+    if (chunk < 1) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "gemm: K=%d does not fit shared memory", p.K);
+    for (int m0 = 0; m0 < M; m0 += chunk) {
         GemvParams c = p;
-        c.M = M - m0 < GEMV_MAX_M ? M - m0 : GEMV_MAX_M;
+        c.M = M - m0 < chunk ? M - m0 : chunk;
         c.a = (const char *)p.a + (size_t)m0 * a_row_bytes;
         for (int s = 0; s < c.nseg; s++) c.seg[s].out = p.seg[s].out + (size_t)m0 * p.seg[s].out_ld;
         if (c.residual) c.residual = p.residual + (size_t)m0 * p.res_ld;

@@ -65,6 +65,7 @@ extern "C" int jl_shutdown(jl_ctx *ctx) {
     if (!ctx) return JL_ERR_INVALID;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    while (!ctx->models.empty()) jl_model_free(ctx->models.back()); // models first: their graphs point at the tensors
     jl_comm_destroy(ctx);
     for (auto &kv : ctx->tensors) {
         cudaFree(kv.second.data);
@@ -161,6 +162,7 @@ extern "C" int64_t jl_register_tensor(jl_ctx *ctx, int dtype, int64_t rows, int6
         t.bytes += sb;
     }
     int64_t id = ctx->next_id++;
+    t.id = id;
     ctx->tensors[id] = t;
     return id;
 }
@@ -170,8 +172,11 @@ extern "C" int jl_unregister_tensor(jl_ctx *ctx, int64_t id) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     auto it = ctx->tensors.find(id);
     if (it == ctx->tensors.end()) return jl_set_error(ctx, JL_ERR_INVALID, "unknown tensor id %lld", (long long)id);
+    if (it->second.refs > 0)
+        return jl_set_error(ctx, JL_ERR_INVALID, "tensor %lld is bound to %d live model slot(s); free the model first", (long long)id,
+                            it->second.refs);
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    cudaDeviceSynchronize(); // model streams may still be reading it
     cudaFree(it->second.data);
     if (it->second.scales) cudaFree(it->second.scales);
     ctx->tensors.erase(it);
@@ -210,8 +215,11 @@ static int gemm_locked(jl_ctx *ctx, int a_dtype, const void *a, const float *a_s
         if (!das) return JL_ERR_OOM;
         JL_CUDA_CHECK(ctx, cudaMemcpyAsync(das, a_scales, (size_t)m * (lda / 32) * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
-    for (int m0 = 0; m0 < m; m0 += GEMV_MAX_M) {
-        const int mc = m - m0 < GEMV_MAX_M ? m - m0 : GEMV_MAX_M;
+    const int pro = a_dtype == JL_I8 ? PRO_Q8_GLOBAL : (a_dtype == JL_BF16 ? PRO_BF16_GLOBAL : PRO_F32);
+    const int chunk = jl_gemv_max_m(B.dtype, pro, k);
+    if (chunk < 1) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "gemm: k=%d does not fit shared memory", k);
+    for (int m0 = 0; m0 < m; m0 += chunk) {
+        const int mc = m - m0 < chunk ? m - m0 : chunk;
         GemvParams p = {};
         p.nseg = 1;
         p.seg[0].w = B.data;
@@ -231,7 +239,6 @@ static int gemm_locked(jl_ctx *ctx, int a_dtype, const void *a, const float *a_s
         p.a_col_off = a_col_off;
         p.row0 = n0;
         p.total_rows = n;
-        int pro = a_dtype == JL_I8 ? PRO_Q8_GLOBAL : (a_dtype == JL_BF16 ? PRO_BF16_GLOBAL : PRO_F32);
         int rc = jl_launch_gemv(ctx, ctx->stream, p, pro, EPI_STORE, false);
         if (rc != JL_OK) return rc;
     }
@@ -687,6 +694,8 @@ extern "C" int jl_debug_ktrace(jl_ctx *ctx, int capacity) {
     if (!ctx || capacity < 0) return JL_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
     JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    JL_CUDA_CHECK(ctx, cudaDeviceSynchronize());
+    jl_models_invalidate_graphs(ctx); // captured graphs carry the old slot pointers in their kernel parameters
     if (ctx->ktrace) cudaFree(ctx->ktrace);
     ctx->ktrace = nullptr, ctx->ktrace_cap = 0, ctx->ktrace_n = 0;
     if (capacity == 0) return JL_OK;

@@ -67,6 +67,13 @@ class LlamaModel:
         self.h = h
         self._ids = []
         self.max_sessions = max_sessions
+        try:
+            self._load(ctx, cfg, weights, tp_size)
+        except Exception:
+            self.close()  # a rejected checkpoint must not leak the half-built model or its tensors
+            raise
+
+    def _load(self, ctx, cfg, weights, tp_size):
         if callable(weights):
             get = weights
         else:

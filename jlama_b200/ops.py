@@ -165,10 +165,6 @@ class CudaTensorOperations:
             return BFloat16BufferTensor(out)
         raise native.UnsupportedOperation(native.JL_ERR_UNSUPPORTED, "quantize to dtype %d" % qtype)
 
-    def sum(self, a):
-        # TensorOperations.java:154-160 (testing helper; host arithmetic by definition)
-        return float(np.sum(a.to_float(), dtype=np.float32))
-
     # -- fused layer-level entry points (outside the reference interface) -------------
     def rmsnorm(self, x, weights, eps, embedding_length=None, weight_adjustment=0.0, offset=0, length=None):
         length = x.cols - offset if length is None else length

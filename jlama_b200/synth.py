@@ -24,6 +24,8 @@ CONFIGS = {
     "tiny-mha": dict(ctx=128, E=128, H=256, heads=4, kv_heads=4, layers=2, vocab=320, eps=1e-5, rope_theta=10000.0),
     "small": dict(ctx=512, E=512, H=1536, heads=8, kv_heads=2, layers=4, vocab=2048, eps=1e-5, rope_theta=500000.0),
     "small-hs128": dict(ctx=512, E=1024, H=2048, heads=8, kv_heads=2, layers=2, vocab=1024, eps=1e-5, rope_theta=500000.0),
+    # 8 KV heads so that the jlama-net model-shard split reaches 8 ranks (JlamaService.java:65-68 caps shards at KV heads)
+    "llama-tp8-test": dict(ctx=512, E=1024, H=3584, heads=16, kv_heads=8, layers=3, vocab=4096, eps=1e-5, rope_theta=500000.0),
     # BASELINE.json configs (public HF config.json dims)
     "llama-3.2-1b": dict(ctx=131072, E=2048, H=8192, heads=32, kv_heads=8, layers=16, vocab=128256, eps=1e-5,
                          rope_theta=500000.0, tied=True),
@@ -56,13 +58,15 @@ def _direct_q8(rng, rows, cols, std):
     return q, mag.astype(np.float32)
 
 
-def make_tensor(seed, rows, cols, wdtype, mode, std=0.02):
+def make_tensor(seed, rows, cols, wdtype, mode, std=0.02, q4_fn=None):
+    """q4_fn: optional drop-in for tensor.quantize_q4 (same bytes, faster): the GPU weight quantiser
+    (CudaTensorOperations.quantize_q4_weights) in bench.py, the oracle's C quantiser in tests."""
     rng = np.random.default_rng(seed)
     if wdtype == Q4:
         if mode == "direct":
             q, s = _direct_q4(rng, rows, cols, std)
         else:
-            q, s = quantize_q4(rng.standard_normal((rows, cols), dtype=np.float32) * np.float32(std))
+            q, s = (q4_fn or quantize_q4)(rng.standard_normal((rows, cols), dtype=np.float32) * np.float32(std))
         return (Q4, q, s)
     if wdtype == I8:
         if mode == "direct":
@@ -107,7 +111,7 @@ def tensor_seed(cfg, name):
     return (SEED0 + zlib.crc32(name.encode())) & 0x7FFFFFFFFFFFFFFF
 
 
-def make_one(cfg, name, rows, cols, kind, wdtype=Q4, mode="quantize", embed_dtype=None):
+def make_one(cfg, name, rows, cols, kind, wdtype=Q4, mode="quantize", embed_dtype=None, q4_fn=None):
     seed = tensor_seed(cfg, name)
     if kind == "norm":
         rng = np.random.default_rng(seed)
@@ -116,24 +120,24 @@ def make_one(cfg, name, rows, cols, kind, wdtype=Q4, mode="quantize", embed_dtyp
         # Jlama's quantiser also quantises the embedding table (skip pattern is only "norm",
         # QuantizeCommand.java:36-38), so a JQ4 checkpoint has a Q4 embedding (LlamaModel.java:91-97)
         dt = wdtype if embed_dtype is None else embed_dtype
-        return make_tensor(seed, rows, cols, dt, mode, std=1.0)
+        return make_tensor(seed, rows, cols, dt, mode, std=1.0, q4_fn=q4_fn)
     # residual-branch output projections are down-scaled by 1/sqrt(2L) (GPT-2 / Llama style init) so that the
     # synthetic network is residual-dominated and well-conditioned like a trained one; with every matrix at
     # std 0.02 a random transformer amplifies 1e-7 summation-order differences into O(1) logit changes.
     std = 0.02
     if name.endswith("o_proj.weight") or name.endswith("down_proj.weight"):
         std = 0.02 / float(np.sqrt(2.0 * cfg["layers"]))
-    return make_tensor(seed, rows, cols, wdtype, mode, std=std)
+    return make_tensor(seed, rows, cols, wdtype, mode, std=std, q4_fn=q4_fn)
 
 
-def make_weights(cfg, wdtype=Q4, mode="quantize", embed_dtype=None, threads=None):
+def make_weights(cfg, wdtype=Q4, mode="quantize", embed_dtype=None, threads=None, q4_fn=None):
     """Full synthetic checkpoint in host memory (tensors generated in parallel; each has its own seed)."""
     import os
     from concurrent.futures import ThreadPoolExecutor
     specs = tensor_specs(cfg)
     threads = threads or min(32, os.cpu_count() or 1)
     with ThreadPoolExecutor(max_workers=threads) as ex:
-        vals = list(ex.map(lambda sp: make_one(cfg, sp[0], sp[1], sp[2], sp[3], wdtype, mode, embed_dtype), specs))
+        vals = list(ex.map(lambda sp: make_one(cfg, sp[0], sp[1], sp[2], sp[3], wdtype, mode, embed_dtype, q4_fn), specs))
     return {sp[0]: v for sp, v in zip(specs, vals)}
 
 

@@ -1,0 +1,142 @@
+"""Teacher-forced single-layer parity at the REAL Llama-3-8B layer dimensions (E=4096, H=14336, 32 heads / 8 KV heads,
+K=14336 down_proj): separates "a 32-layer synthetic network amplifies 1e-7 differences" from "a kernel is wrong at the
+headline shapes" (VERDICT r1, weak #1).
+
+The model under test has ONE transformer layer with the 8B shapes; its input is an embedding row, identical on both
+sides, so nothing upstream can amplify: what is compared is exactly one TransformerBlock.forward
+(TransformerBlock.java:158-215) -- RMSNorm -> Q8 -> QKV -> RoPE/KV append -> attention -> Q8 -> o_proj + residual ->
+RMSNorm -> Q8 -> gate/up -> SiLU*up -> Q8 -> down_proj + residual -- plus the final norm + lm_head.  Weights are
+N(0, 0.02^2) quantised with the reference quantiser semantics (the oracle's C quantiser here), for the seeds
+of layer 0 and of layer 31.  Prompt rows go through the batched (M<=8) kernels, decode steps through the decode fast
+path (and the persistent kernel when enabled); every step is teacher-forced with the oracle's token.
+
+Bars: K/V rows 2e-5 of their max; hidden row and logits 1e-4 of max (the four Q8 re-quantisations inside the layer turn a
+1e-7 summation-order difference into an occasional +-1 int8 step of one activation, ~1e-5..1e-4 of the row maximum; the
+measured values are printed)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+DIMS = dict(ctx=512, E=4096, H=14336, heads=32, kv_heads=8, layers=1, vocab=2048, eps=1e-5, rope_theta=500000.0)
+
+
+def _layer_weights(oracle, src_layer, wdtype=None):
+    """Checkpoint of the 1-layer model whose layer 0 carries the seeds of `src_layer` of the 8B checkpoint."""
+    from jlama_b200 import native, synth
+    cfg = synth.get_config("llama-3-8b", **DIMS)
+    cfg["name"] = "llama-3-8b-layer%d" % src_layer
+    big = synth.get_config("llama-3-8b")
+    w = {}
+    for name, rows, cols, kind in synth.tensor_specs(cfg):
+        src = name.replace("model.layers.0.", "model.layers.%d." % src_layer)
+        # 1/sqrt(2L) residual scaling of the 32-layer checkpoint (synth.make_one reads cfg["layers"])
+        w[name] = synth.make_one(big, src, rows, cols, kind, native.Q4 if wdtype is None else wdtype, "quantize",
+                                 q4_fn=oracle.quantize_q4)
+    return cfg, w
+
+
+def _rel(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / np.abs(np.asarray(b)).max())
+
+
+@pytest.mark.parametrize("src_layer", [0, 31])
+def test_one_8b_layer_teacher_forced_q8_activations(cuda_ctx, oracle, src_layer):
+    from jlama_b200 import synth
+    from jlama_b200.model import LlamaModel
+    cfg, w = _layer_weights(oracle, src_layer)
+    gm = LlamaModel(cuda_ctx, cfg, w, max_context=128)
+    om = oracle.OracleLlama(cfg, w, act_q8=True)
+    prompt = synth.random_prompt(cfg, 11, seed=100 + src_layer)
+    # prefill (M <= 8 tiles of the generic kernel)
+    gm.reset_session(0)
+    om.reset()
+    gm.batch_forward(prompt, 0)
+    oh = om.batch_forward(prompt, 0)
+    gh = gm.read_hidden()
+    worst = {"hidden": _rel(gh, oh), "kv": 0.0, "logits": 0.0}
+    for pos in (0, 5, 10):
+        for which in (0, 1):
+            worst["kv"] = max(worst["kv"], _rel(gm.read_kv(0, pos, which), om.kv_row(0, pos, which)))
+    gt, gl = gm.sample()
+    ot, ol = om.sample(oh)
+    worst["logits"] = _rel(gl, ol)
+    assert gt == ot
+    # decode fast path, teacher-forced with the oracle's token
+    tok = ot
+    for step in range(6):
+        pos = len(prompt) + step
+        nxt, lg = gm.decode([tok], [pos], sessions=[0], want_logits=True)
+        oh = om.batch_forward([tok], pos)
+        ot, ol = om.sample(oh)
+        worst["logits"] = max(worst["logits"], _rel(lg[0], ol))
+        for which in (0, 1):
+            worst["kv"] = max(worst["kv"], _rel(gm.read_kv(0, pos, which), om.kv_row(0, pos, which)))
+        assert int(nxt[0]) == ot, "step %d: gpu %d oracle %d" % (step, int(nxt[0]), ot)
+        tok = ot
+    print("8B-dims layer %d (teacher-forced): hidden %.2e, kv %.2e, logits %.2e of max" % (
+        src_layer, worst["hidden"], worst["kv"], worst["logits"]))
+    assert worst["kv"] <= 2e-5
+    assert worst["hidden"] <= 1e-4
+    assert worst["logits"] <= 1e-4
+    gm.close()
+    om.close()
+
+
+def test_one_8b_layer_f32_working_type(cuda_ctx, oracle):
+    """working_qtype = F32 at the 8B shapes: a 3-row prompt chunk against down_proj (K = 14336) needs
+    4 * 14336 * 4 B = 229 KB of staged activations; the driver must split the rows instead of failing."""
+    from jlama_b200 import native, synth
+    from jlama_b200.model import LlamaModel
+    cfg, w = _layer_weights(oracle, 0)
+    gm = LlamaModel(cuda_ctx, cfg, w, working_qtype=native.F32, max_context=64)
+    om = oracle.OracleLlama(cfg, w, act_q8=False)
+    prompt = synth.random_prompt(cfg, 7, seed=5)
+    gm.reset_session(0)
+    om.reset()
+    gm.batch_forward(prompt, 0)
+    oh = om.batch_forward(prompt, 0)
+    assert _rel(gm.read_hidden(), oh) <= 1e-4
+    gt, gl = gm.sample()
+    ot, ol = om.sample(oh)
+    assert gt == ot and _rel(gl, ol) <= 1e-3
+    nxt, lg = gm.decode([ot], [len(prompt)], sessions=[0], want_logits=True)
+    oh = om.batch_forward([ot], len(prompt))
+    ot2, ol2 = om.sample(oh)
+    assert int(nxt[0]) == ot2 and _rel(lg[0], ol2) <= 1e-3
+    gm.close()
+    om.close()
+
+
+def test_mixed_dtype_fused_groups_are_rejected(cuda_ctx):
+    """K/V (or UP) in another dtype than Q (GATE) must fail at finalize, not read F32 rows as nibbles."""
+    from jlama_b200 import native, synth
+    from jlama_b200.model import LlamaModel
+    cfg = synth.get_config("tiny")
+    w = synth.make_weights(cfg)
+    name = "model.layers.1.self_attn.k_proj.weight"
+    rows, cols = w[name][1].shape[0], w[name][1].shape[1] * 2
+    w[name] = synth.make_tensor(1, rows, cols, native.F32, "quantize")
+    with pytest.raises(native.JlamaNativeError) as ei:
+        LlamaModel(cuda_ctx, cfg, w)
+    assert "share one dtype" in str(ei.value)
+    w = synth.make_weights(cfg)
+    name = "model.layers.0.mlp.up_proj.weight"
+    rows, cols = w[name][1].shape[0], w[name][1].shape[1] * 2
+    w[name] = synth.make_tensor(2, rows, cols, native.I8, "quantize")
+    with pytest.raises(native.JlamaNativeError):
+        LlamaModel(cuda_ctx, cfg, w)
+
+
+def test_unregister_refuses_tensors_bound_to_a_model(cuda_ctx):
+    """the C ABI itself keeps weights alive while a model (and its captured graphs) points at them."""
+    from jlama_b200 import synth
+    from jlama_b200.model import LlamaModel
+    cfg = synth.get_config("tiny")
+    gm = LlamaModel(cuda_ctx, cfg, synth.make_weights(cfg))
+    tid = gm._ids[3]
+    assert cuda_ctx.lib.jl_unregister_tensor(cuda_ctx.h, tid) < 0
+    assert b"bound" in cuda_ctx.lib.jl_last_error(cuda_ctx.h)
+    toks, _ = gm.generate(synth.random_prompt(cfg, 5), 4)  # still works
+    assert len(toks) == 4
+    gm.close()  # frees the model, then unregisters: must succeed now
