@@ -250,7 +250,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity-port-tokens", type=int, default=2, help="tokens also checked against the plain-C oracle port")
     ap.add_argument("--no-roofline", action="store_true")
-    ap.add_argument("--mega", action="store_true", help="decode with the persistent megakernel instead of the CUDA-graph path")
+    ap.add_argument("--no-persistent", action="store_true", help="decode through the CUDA graph of per-op kernels instead of the persistent kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     capture_stdout()
@@ -290,7 +290,7 @@ def main():
     n_total = args.prompt + 2 * (args.warmup + args.steps) + 64
     t0 = time.time()
     model = LlamaModel(ctx, cfg, weights, max_context=min(cfg["ctx"], max(512, n_total)), tp_rank=rank, tp_size=world,
-                       flags=native.MODEL_MEGA if args.mega else 0)
+                       flags=native.MODEL_NO_PERSISTENT if args.no_persistent else 0)
     log("[bench] rank %d: weights uploaded in %.1fs (%.3f GB streamed per token on this rank)" % (
         rank, time.time() - t0, model.weight_bytes() / 1e9))
 

@@ -184,9 +184,7 @@ typedef struct {
 
 #define JL_MODEL_NO_GRAPH 1 /* launch decode kernels eagerly instead of through a CUDA graph */
 #define JL_MODEL_NO_PDL 2   /* (default) no programmatic dependent launch between the decode kernels */
-#define JL_MODEL_NO_MEGA 4  /* (default) decode with one kernel per op */
-#define JL_MODEL_MEGA 8     /* opt in: decode with the persistent cooperative megakernel (jl_mega.cu); measured slower than
-                               the CUDA-graph path on B200 in round 1, kept as the basis for round 2 */
+#define JL_MODEL_NO_PERSISTENT 4 /* decode through the CUDA graph of per-op kernels instead of the persistent decode kernel */
 #define JL_MODEL_PDL 16     /* opt in: programmatic dependent launch between the per-op decode kernels (measured: no gain) */
 
 /* tensor slots */
@@ -236,11 +234,15 @@ int jl_model_decode_resident(jl_model *m, int session, int32_t first_token, int 
 /* test hooks: copy a K/V row (f32) or the hidden rows of the last batch_forward chunk to HOST */
 int jl_model_read_kv(jl_model *m, int session, int layer, int position, int which /*0=K,1=V*/, float *out);
 int jl_model_read_hidden(jl_model *m, int session, float *out /* [embedding_length] last row */);
-/* diagnostic: run one megakernel decode step (token/position as given) with phase tracing; out receives
- * [3 CTAs (first, middle, last)][layers*4+1 ops][8] SM clock stamps: 0 op start, 1 after attention phase,
- * 2 dependency satisfied, 3 activations staged, 4 stages consumed, 5 signalled. */
-int jl_model_debug_trace(jl_model *m, int session, int32_t token, int position, int64_t *out, int64_t out_words);
-/* how jl_model_decode executes for n sessions: 2 = persistent megakernel, 1 = CUDA-graph of per-op kernels, 0 = eager */
+/* test hook: copy `n` floats of an internal activation buffer of the LAST forward/decode call to HOST (row 0 first).
+ * which: 0 = x (hidden after the last layer), 1 = xb (after attention + residual), 2 = q, 3 = k, 4 = v (raw projections),
+ * 5 = att (attention output), 6 = h (silu(gate) * up), 7 = logits. */
+int jl_model_debug_read(jl_model *m, int which, float *out, int64_t n);
+/* diagnostic: CTA 0's phase stamps (globaltimer ns) of the last persistent decode launch (tools/ptrace.py); phase tracing
+ * is enabled with JL_PD_TRACE=1 in the environment when the model is created.  Returns the number of words written. */
+int jl_model_debug_trace(jl_model *m, uint64_t *out, int64_t out_words);
+/* how jl_model_decode executes for n sessions: 3 = persistent decode kernel (one cooperative launch per token, n == 1),
+ * 1 = CUDA graph of per-op kernels, 0 = eager */
 int jl_model_decode_mode(jl_model *m, int n);
 /* per-token algorithmic bytes of the decode weight stream on this rank (roofline numerator) */
 int64_t jl_model_weight_bytes(jl_model *m);

@@ -11,7 +11,7 @@ typedef struct {
     char internal[128];
 } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclFloat32 = 7 };
+enum { ncclInt8 = 0, ncclFloat32 = 7 };
 enum { ncclSum = 0 };
 
 struct NcclApi {
@@ -20,6 +20,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi g_nccl;
@@ -39,6 +40,7 @@ static int nccl_load(jl_ctx *ctx) {
     g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
     g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(h, "ncclAllGather");
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce)
         return jl_set_error(ctx, JL_ERR_NCCL, "libnccl is missing required symbols");
@@ -84,6 +86,13 @@ int jl_comm_allreduce_dev(jl_ctx *ctx, cudaStream_t stream, float *buf, size_t c
     if (ctx->world <= 1) return JL_OK;
     if (!ctx->nccl_comm) return jl_set_error(ctx, JL_ERR_NCCL, "communicator not initialised");
     JL_NCCL_CHECK(ctx, g_nccl.AllReduce(buf, buf, count, ncclFloat32, ncclSum, (ncclComm_t)ctx->nccl_comm, stream));
+    return JL_OK;
+}
+
+// device-buffer all-gather of raw bytes (the CUDA IPC handles of the in-kernel exchange buffers travel this way)
+int jl_comm_allgather_dev(jl_ctx *ctx, cudaStream_t stream, const void *send, void *recv, size_t bytes_per_rank) {
+    if (!ctx->nccl_comm || !g_nccl.AllGather) return jl_set_error(ctx, JL_ERR_NCCL, "communicator not initialised");
+    JL_NCCL_CHECK(ctx, g_nccl.AllGather(send, recv, bytes_per_rank, ncclInt8, (ncclComm_t)ctx->nccl_comm, stream));
     return JL_OK;
 }
 

@@ -6,7 +6,7 @@
 // never leave HBM, KV lives in device pages shaped like KvBufferCache's, and the per-token decode
 // step is captured once into a CUDA graph with programmatic dependent launch between kernels.
 #include "jl_common.cuh"
-#include "jl_mega.cuh"
+#include "jl_pdecode.cuh"
 
 #include <chrono>
 #include <map>
@@ -16,6 +16,7 @@
 #include <string.h>
 
 int jl_comm_allreduce_dev(jl_ctx *ctx, cudaStream_t stream, float *buf, size_t count);
+int jl_comm_allgather_dev(jl_ctx *ctx, cudaStream_t stream, const void *send, void *recv, size_t bytes_per_rank);
 
 struct jl_model {
     jl_ctx *ctx = nullptr;
@@ -59,12 +60,19 @@ struct jl_model {
     double last_total_ms = 0, last_gemv_ms = 0;
     bool timing_valid = false;
     int64_t weight_bytes = 0;
-    // persistent megakernel
-    bool mega_ok = false;
-    MegaLayer *mega_layers = nullptr;
-    unsigned *mega_sync = nullptr, *mega_att_done = nullptr, *fda_done = nullptr;
-    unsigned long long *mega_slots = nullptr;
-    int mega_l2_ahead = 1;
+    unsigned *fda_done = nullptr;
+    // persistent decode kernel (jl_pdecode.cu)
+    bool pd_ok = false;
+    int pd_wdtype = JL_Q4;
+    PdLayer *pd_layers = nullptr;
+    unsigned long long *pd_sync = nullptr, *pd_slots = nullptr, *pd_trace = nullptr;
+    unsigned *pd_att_done = nullptr;
+    int pd_vocab0 = 0, pd_vocab_rows = 0;
+    // tensor-parallel exchange buffers: local allocations + every rank's copy opened through CUDA IPC
+    uint4 *ll_o = nullptr, *ll_d = nullptr, *ll_a = nullptr;
+    uint4 *peer_ll_o[PD_MAX_TP] = {}, *peer_ll_d[PD_MAX_TP] = {}, *peer_ll_a[PD_MAX_TP] = {};
+    float *peer_logits[PD_MAX_TP] = {};
+    std::vector<void *> ipc_opened;
 };
 
 #define M_CHECK(expr)                 \
@@ -88,7 +96,14 @@ static bool use_pdl(const jl_model *m) {
     return (m->cfg.flags & JL_MODEL_PDL) != 0;
 }
 static bool use_graph(const jl_model *m) { return !(m->cfg.flags & JL_MODEL_NO_GRAPH); }
-static bool use_mega(const jl_model *m) { return m->mega_ok && (m->cfg.flags & JL_MODEL_MEGA) && !(m->cfg.flags & JL_MODEL_NO_MEGA); }
+static bool use_pd(const jl_model *m) {
+    static int env = -1;
+    if (env < 0) {
+        const char *e = getenv("JL_PERSISTENT");
+        env = e ? (atoi(e) ? 1 : 0) : 1;
+    }
+    return m->pd_ok && env == 1 && !(m->cfg.flags & (JL_MODEL_NO_PERSISTENT | JL_MODEL_NO_GRAPH));
+}
 
 extern "C" int jl_model_create(jl_ctx *ctx, const jl_model_config *cfg, jl_model **out) {
     if (!ctx || !cfg || !out) return JL_ERR_INVALID;
@@ -296,33 +311,93 @@ extern "C" int jl_model_finalize(jl_model *m) {
         for (int s : {JL_L_Q, JL_L_K, JL_L_V, JL_L_O, JL_L_GATE, JL_L_DOWN, JL_L_UP}) wb += tb(m->l[(size_t)L * 9 + s]);
     wb += tb(m->g_set[JL_T_LM_HEAD] ? m->g[JL_T_LM_HEAD] : m->g[JL_T_EMBED]);
     m->weight_bytes = wb;
-    // ---- persistent megakernel eligibility: all linear weights Q4, Q8 activations, single rank ----
+    // ---- persistent decode kernel eligibility: Q8 activations, every linear weight (and the lm_head) in ONE quantised dtype ----
     {
-        bool ok = c.working_qtype == JL_I8 && c.tp_size == 1;
         const DevTensor &head = m->g_set[JL_T_LM_HEAD] ? m->g[JL_T_LM_HEAD] : m->g[JL_T_EMBED];
-        ok = ok && head.dtype == JL_Q4;
+        const int wd = m->l[JL_L_Q].dtype;
+        bool ok = c.working_qtype == JL_I8 && (wd == JL_Q4 || wd == JL_I8) && head.dtype == wd;
         for (int L = 0; L < c.num_layers && ok; L++)
-            for (int sl : {JL_L_Q, JL_L_K, JL_L_V, JL_L_O, JL_L_GATE, JL_L_DOWN, JL_L_UP}) ok = ok && m->l[(size_t)L * 9 + sl].dtype == JL_Q4;
+            for (int sl : {JL_L_Q, JL_L_K, JL_L_V, JL_L_O, JL_L_GATE, JL_L_DOWN, JL_L_UP}) ok = ok && m->l[(size_t)L * 9 + sl].dtype == wd;
+        // lm_head rows of this rank (vocabulary-sharded under tensor parallelism: SURVEY 8e; the reference computes the
+        // full GEMV on the coordinator, AbstractModel.java:444-449)
+        const int W = c.tp_size, V = c.vocab_size;
+        m->pd_vocab0 = (int)(((long long)V * c.tp_rank) / W);
+        m->pd_vocab_rows = (int)(((long long)V * (c.tp_rank + 1)) / W) - m->pd_vocab0;
+        if (ok && W > 1 && !ctx->nccl_comm) ok = false; // the IPC handles travel over the communicator
         if (ok) {
-            std::vector<MegaLayer> ml(c.num_layers);
+            PdParams probe = {};
+            probe.layers = c.num_layers, probe.E = E, probe.H = m->h_seg, probe.attn_seg = m->attn_seg, probe.kv_seg = m->kv_seg;
+            probe.heads = m->heads_local, probe.kv_heads = m->kv_heads_local, probe.head_size = hs, probe.world = W;
+            ok = jl_pdecode_supported(probe, wd, ctx->sm_count);
+        }
+        if (ok) {
+            std::vector<PdLayer> pl(c.num_layers);
             const int order[7] = {JL_L_Q, JL_L_K, JL_L_V, JL_L_O, JL_L_GATE, JL_L_UP, JL_L_DOWN};
             for (int L = 0; L < c.num_layers; L++) {
                 for (int i = 0; i < 7; i++) {
-                    ml[L].w[i] = (const uint8_t *)m->l[(size_t)L * 9 + order[i]].data;
-                    ml[L].s[i] = m->l[(size_t)L * 9 + order[i]].scales;
+                    pl[L].w[i] = (const uint8_t *)m->l[(size_t)L * 9 + order[i]].data;
+                    pl[L].s[i] = m->l[(size_t)L * 9 + order[i]].scales;
                 }
-                ml[L].attn_norm = m->l[(size_t)L * 9 + JL_L_ATTN_NORM].data;
-                ml[L].attn_norm_dt = m->l[(size_t)L * 9 + JL_L_ATTN_NORM].dtype;
-                ml[L].ffn_norm = m->l[(size_t)L * 9 + JL_L_FFN_NORM].data;
-                ml[L].ffn_norm_dt = m->l[(size_t)L * 9 + JL_L_FFN_NORM].dtype;
+                pl[L].attn_norm = m->l[(size_t)L * 9 + JL_L_ATTN_NORM].data;
+                pl[L].attn_norm_dt = m->l[(size_t)L * 9 + JL_L_ATTN_NORM].dtype;
+                pl[L].ffn_norm = m->l[(size_t)L * 9 + JL_L_FFN_NORM].data;
+                pl[L].ffn_norm_dt = m->l[(size_t)L * 9 + JL_L_FFN_NORM].dtype;
             }
-            M_CHECK(dev_alloc(ctx, (void **)&m->mega_layers, ml.size() * sizeof(MegaLayer)));
-            JL_CUDA_CHECK(ctx, cudaMemcpy(m->mega_layers, ml.data(), ml.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice));
-            M_CHECK(dev_alloc(ctx, (void **)&m->mega_sync, jl_mega_sync_words(c.num_layers) * sizeof(unsigned)));
-            M_CHECK(dev_alloc(ctx, (void **)&m->mega_att_done, (size_t)c.num_layers * MEGA_MAX_M * m->kv_heads_local * sizeof(unsigned)));
-            M_CHECK(dev_alloc(ctx, (void **)&m->mega_slots, (size_t)MEGA_MAX_M * ctx->sm_count * sizeof(unsigned long long)));
-            if (const char *e = getenv("JL_MEGA_L2_AHEAD")) m->mega_l2_ahead = atoi(e);
-            m->mega_ok = true;
+            M_CHECK(dev_alloc(ctx, (void **)&m->pd_layers, pl.size() * sizeof(PdLayer)));
+            JL_CUDA_CHECK(ctx, cudaMemcpy(m->pd_layers, pl.data(), pl.size() * sizeof(PdLayer), cudaMemcpyHostToDevice));
+            M_CHECK(dev_alloc(ctx, (void **)&m->pd_sync, PD_SYNC_WORDS * 8));
+            JL_CUDA_CHECK(ctx, cudaMemset(m->pd_sync, 0, PD_SYNC_WORDS * 8));
+            M_CHECK(dev_alloc(ctx, (void **)&m->pd_slots, (size_t)ctx->sm_count * 8));
+            M_CHECK(dev_alloc(ctx, (void **)&m->pd_att_done, (size_t)m->kv_heads_local * sizeof(unsigned)));
+            JL_CUDA_CHECK(ctx, cudaMemset(m->pd_att_done, 0, (size_t)m->kv_heads_local * sizeof(unsigned)));
+            m->pd_wdtype = wd;
+            if (W > 1) {
+                // LL receive buffers of this rank and the peers' copies (cudaIpc: one process per GPU)
+                const size_t lines = (size_t)W * E / 2 + 8;
+                M_CHECK(dev_alloc(ctx, (void **)&m->ll_o, lines * 16));
+                M_CHECK(dev_alloc(ctx, (void **)&m->ll_d, lines * 16));
+                M_CHECK(dev_alloc(ctx, (void **)&m->ll_a, (size_t)PD_MAX_TP * 16));
+                JL_CUDA_CHECK(ctx, cudaMemset(m->ll_o, 0, lines * 16));
+                JL_CUDA_CHECK(ctx, cudaMemset(m->ll_d, 0, lines * 16));
+                JL_CUDA_CHECK(ctx, cudaMemset(m->ll_a, 0, (size_t)PD_MAX_TP * 16));
+                void *local[4] = {m->ll_o, m->ll_d, m->ll_a, m->logits};
+                cudaIpcMemHandle_t mine[4];
+                for (int i = 0; i < 4; i++) JL_CUDA_CHECK(ctx, cudaIpcGetMemHandle(&mine[i], local[i]));
+                cudaIpcMemHandle_t *d_send = nullptr, *d_recv = nullptr;
+                M_CHECK(dev_alloc(ctx, (void **)&d_send, sizeof mine));
+                M_CHECK(dev_alloc(ctx, (void **)&d_recv, sizeof mine * W));
+                JL_CUDA_CHECK(ctx, cudaMemcpy(d_send, mine, sizeof mine, cudaMemcpyHostToDevice));
+                int rc = jl_comm_allgather_dev(ctx, m->stream, d_send, d_recv, sizeof mine);
+                if (rc == JL_OK && cudaStreamSynchronize(m->stream) != cudaSuccess) rc = jl_set_error(ctx, JL_ERR_CUDA, "handle exchange failed");
+                std::vector<cudaIpcMemHandle_t> all((size_t)4 * W);
+                if (rc == JL_OK) JL_CUDA_CHECK(ctx, cudaMemcpy(all.data(), d_recv, sizeof mine * W, cudaMemcpyDeviceToHost));
+                cudaFree(d_send);
+                cudaFree(d_recv);
+                if (rc != JL_OK) return rc;
+                for (int r = 0; r < W; r++) {
+                    void *ptrs[4];
+                    for (int i = 0; i < 4; i++) {
+                        if (r == c.tp_rank) {
+                            ptrs[i] = local[i];
+                        } else {
+                            cudaError_t e = cudaIpcOpenMemHandle(&ptrs[i], all[(size_t)r * 4 + i], cudaIpcMemLazyEnablePeerAccess);
+                            if (e != cudaSuccess)
+                                return jl_set_error(ctx, JL_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s (peer access over NVLink is required)", r,
+                                                    cudaGetErrorString(e));
+                            m->ipc_opened.push_back(ptrs[i]);
+                        }
+                    }
+                    m->peer_ll_o[r] = (uint4 *)ptrs[0], m->peer_ll_d[r] = (uint4 *)ptrs[1], m->peer_ll_a[r] = (uint4 *)ptrs[2];
+                    m->peer_logits[r] = (float *)ptrs[3];
+                }
+            }
+            if (getenv("JL_PD_TRACE")) {
+                M_CHECK(dev_alloc(ctx, (void **)&m->pd_trace, ((size_t)c.num_layers * 8 + 16) * 8));
+                JL_CUDA_CHECK(ctx, cudaMemset(m->pd_trace, 0, ((size_t)c.num_layers * 8 + 16) * 8));
+            }
+            m->pd_ok = true;
+            // per-token stream of this rank: the lm_head is vocabulary-sharded on the persistent path
+            if (W > 1) m->weight_bytes += -tb(head) + (int64_t)((double)tb(head) * m->pd_vocab_rows / V);
         }
     }
     m->finalized = true;
@@ -359,11 +434,12 @@ extern "C" int jl_model_free(jl_model *m) {
             }
     }
     for (auto &kv : m->graphs) cudaGraphExecDestroy(kv.second);
+    for (void *p : m->ipc_opened) cudaIpcCloseMemHandle(p);
     for (void *p : m->page_table_host)
         if (p) cudaFree(p);
     void *bufs[] = {m->ln, m->hbuf2, m->abf, m->rope, m->page_table_dev, m->x, m->xb, m->q, m->k, m->v, m->att, m->hbuf, m->partial, m->logits,
                     m->last_hidden, m->attn_ws, m->d_tokens, m->d_positions, m->d_sessions, m->d_next, m->d_hist, m->d_counter,
-                    m->argmax_scratch, m->fda_done, m->mega_layers, m->mega_sync, m->mega_att_done, m->mega_slots};
+                    m->argmax_scratch, m->fda_done, m->pd_layers, m->pd_sync, m->pd_slots, m->pd_att_done, m->pd_trace, m->ll_o, m->ll_d, m->ll_a};
     for (void *p : bufs)
         if (p) cudaFree(p);
     if (m->h_pinned) cudaFreeHost(m->h_pinned);
@@ -787,46 +863,61 @@ static int decode_body(jl_model *m, int n, int max_pos, int splits, bool residen
     return JL_OK;
 }
 
-static bool fill_mega(jl_model *m, int n, int max_pos, bool resident, MegaParams &p) {
+static void fill_pd(jl_model *m, int max_pos, bool resident, bool want_logits, PdParams &p) {
     const jl_model_config &c = m->cfg;
-    p = MegaParams();
+    p = PdParams();
     p.layers = c.num_layers, p.E = c.embedding_length, p.H = m->h_seg, p.attn_seg = m->attn_seg, p.kv_seg = m->kv_seg;
-    p.heads = m->heads_local, p.kv_heads = m->kv_heads_local, p.head_size = c.head_size, p.vocab = c.vocab_size;
+    p.heads = m->heads_local, p.kv_heads = m->kv_heads_local, p.head_size = c.head_size;
+    p.vocab = c.vocab_size, p.vocab_rows = m->pd_vocab_rows, p.vocab0 = m->pd_vocab0;
     p.head0_global = m->d.headStart, p.kv_head0_global = m->d.groupHeadStart;
-    p.M = n;
     p.eps = c.layer_norm_eps;
-    p.attn_scale = (float)(1.0 / sqrt((double)c.head_size));
-    p.lw = m->mega_layers;
+    p.attn_scale = (float)(1.0 / sqrt((double)c.head_size)); // CausalSelfAttention.java:134
+    p.lw = m->pd_layers;
     p.embed_dt = m->g[JL_T_EMBED].dtype, p.embed_w = m->g[JL_T_EMBED].data, p.embed_s = m->g[JL_T_EMBED].scales;
     p.out_norm = m->g[JL_T_OUT_NORM].data, p.out_norm_dt = m->g[JL_T_OUT_NORM].dtype;
     const DevTensor &head = m->g_set[JL_T_LM_HEAD] ? m->g[JL_T_LM_HEAD] : m->g[JL_T_EMBED];
-    p.lm_w = (const uint8_t *)head.data, p.lm_s = head.scales;
+    const size_t rb = (size_t)c.embedding_length / 32 * (head.dtype == JL_Q4 ? 16 : 32);
+    p.lm_w = (const uint8_t *)head.data + (size_t)m->pd_vocab0 * rb;
+    p.lm_s = head.scales + (size_t)m->pd_vocab0 * (c.embedding_length / 32);
     p.x = m->x, p.xb = m->xb, p.q = m->q, p.k = m->k, p.v = m->v, p.att = m->att, p.h = m->hbuf, p.logits = m->logits;
     p.attn_ws = m->attn_ws;
     p.rope = m->rope;
     p.kv = m->kv;
     p.tokens = m->d_tokens, p.positions = m->d_positions, p.next = m->d_next, p.sessions = m->d_sessions;
     p.hist = m->d_hist, p.counter = m->d_counter, p.hist_cap = m->hist_cap, p.resident = resident ? 1 : 0;
-    p.sync = m->mega_sync, p.argmax_slots = m->mega_slots, p.att_done = m->mega_att_done;
-    if (const char *e = getenv("JL_MEGA_DBG")) p.dbg = atoi(e);
-    p.grid = m->ctx->sm_count;
-    p.l2_ahead = m->mega_l2_ahead;
-    // one split per 64 positions, bounded by the CTAs available for (row, kv head) tasks
+    p.sync = m->pd_sync, p.argmax_slots = m->pd_slots, p.att_done = m->pd_att_done;
+    // one context split per 64 positions, bounded by the CTAs available for (kv head, split) tasks
     int s = (max_pos + 1 + 63) / 64;
-    const int cap = m->ctx->sm_count / (n * m->kv_heads_local);
+    const int cap = m->ctx->sm_count / m->kv_heads_local;
     if (s > cap) s = cap;
     if (s > m->max_splits) s = m->max_splits;
     if (s < 1) s = 1;
     p.splits = s;
-    return n * m->kv_heads_local <= m->ctx->sm_count && jl_mega_supported(p);
+    p.world = c.tp_size, p.rank = c.tp_rank;
+    for (int r = 0; r < c.tp_size && r < PD_MAX_TP; r++)
+        p.ll_o[r] = m->peer_ll_o[r], p.ll_d[r] = m->peer_ll_d[r], p.ll_a[r] = m->peer_ll_a[r], p.logits_peer[r] = m->peer_logits[r];
+    p.want_logits = want_logits && c.tp_size > 1 ? 1 : 0;
+    p.trace = m->pd_trace;
 }
 
-// run the decode body through the persistent megakernel, a cached CUDA graph, or eagerly
-static int run_decode(jl_model *m, int n, int max_pos, bool resident) {
+// after a synchronise: did the last persistent launches drain on a timeout?  Resets the protocol state if so.
+static int pd_check(jl_model *m) {
+    if (!m->pd_ok) return JL_OK;
+    unsigned long long st[2] = {0, 0};
+    if (cudaMemcpy(st, m->pd_sync, sizeof st, cudaMemcpyDeviceToHost) != cudaSuccess) return jl_set_error(m->ctx, JL_ERR_CUDA, "decode status read failed");
+    if (st[1] == 0) return JL_OK;
+    cudaMemset(m->pd_sync, 0, PD_SYNC_WORDS * 8);
+    cudaMemset(m->pd_att_done, 0, (size_t)m->kv_heads_local * sizeof(unsigned));
+    return jl_set_error(m->ctx, JL_ERR_CUDA, "persistent decode kernel timed out waiting on counter %llu (token %llu); state reset", st[1], st[0]);
+}
+
+// run the decode body through the persistent kernel (one session), a cached CUDA graph, or eagerly
+static int run_decode(jl_model *m, int n, int max_pos, bool resident, bool want_logits = false) {
     jl_ctx *ctx = m->ctx;
-    if (use_mega(m)) {
-        MegaParams mp;
-        if (fill_mega(m, n, max_pos, resident, mp)) return jl_launch_mega(ctx, m->stream, mp);
+    if (n == 1 && use_pd(m)) {
+        PdParams pp;
+        fill_pd(m, max_pos, resident, want_logits, pp);
+        return jl_launch_pdecode(ctx, m->stream, pp, m->pd_wdtype);
     }
     // fused decode attention: one split per 64 positions, bucketed so that few graphs are captured
     int splits = (max_pos + 1 + 63) / 64;
@@ -911,7 +1002,7 @@ extern "C" int jl_model_decode(jl_model *m, int n, const int32_t *sessions, cons
     JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_positions, hp + m->maxB, (size_t)n * 4, cudaMemcpyHostToDevice, m->stream));
     JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_sessions, hp + 2 * m->maxB, (size_t)n * 4, cudaMemcpyHostToDevice, m->stream));
     auto c1 = std::chrono::steady_clock::now();
-    M_CHECK(run_decode(m, n, max_pos, false));
+    M_CHECK(run_decode(m, n, max_pos, false, logits_out != nullptr));
     auto c2 = std::chrono::steady_clock::now();
     JL_CUDA_CHECK(ctx, cudaMemcpyAsync(hp + 3 * m->maxB, m->d_next, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
     if (logits_out)
@@ -930,6 +1021,7 @@ extern "C" int jl_model_decode(jl_model *m, int n, const int32_t *sessions, cons
                     us(c0, c1), us(c1, c2), us(c2, c3), us(c3, c4), gms * 1000.0);
         }
     }
+    if (n == 1 && use_pd(m)) M_CHECK(pd_check(m));
     for (int i = 0; i < n; i++) next_tokens[i] = hp[3 * m->maxB + i];
     float ms = 0;
     cudaEventElapsedTime(&ms, m->ev_begin, m->ev_end);
@@ -980,6 +1072,7 @@ extern "C" int jl_model_decode_resident(jl_model *m, int session, int32_t first_
     JL_CUDA_CHECK(ctx, cudaEventRecord(m->ev_end, m->stream));
     JL_CUDA_CHECK(ctx, cudaMemcpyAsync(out_tokens, m->d_hist, (size_t)n_new * 4, cudaMemcpyDeviceToHost, m->stream));
     JL_CUDA_CHECK(ctx, cudaStreamSynchronize(m->stream));
+    if (use_pd(m)) M_CHECK(pd_check(m));
     float ms = 0;
     cudaEventElapsedTime(&ms, m->ev_begin, m->ev_end);
     m->last_total_ms = ms;
@@ -987,40 +1080,24 @@ extern "C" int jl_model_decode_resident(jl_model *m, int session, int32_t first_
     return JL_OK;
 }
 
-extern "C" int jl_model_debug_trace(jl_model *m, int session, int32_t token, int position, int64_t *out, int64_t out_words) {
-    if (!m || !m->finalized || !out || session < 0 || session >= m->cfg.max_sessions) return JL_ERR_INVALID;
+// diagnostic: CTA 0's phase stamps (globaltimer ns) of the last persistent decode launch; needs JL_PD_TRACE=1 at finalize.
+// out[0] = kernel start, out[1 + L*8 + k]: k 0 qkv dependency met, 1 qkv done, 2 attention done (attention CTAs only), 3 o_proj dependency
+// met, 4 o_proj done, 5 gate/up dependency met, 6 gate/up done, 7 down dependency met; then lm_head dependency met, token published.
+extern "C" int jl_model_debug_trace(jl_model *m, uint64_t *out, int64_t out_words) {
+    if (!m || !m->finalized || !out) return JL_ERR_INVALID;
     jl_ctx *ctx = m->ctx;
-    JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
-    MegaParams mp;
-    if (!use_mega(m) || !fill_mega(m, 1, position, false, mp)) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "megakernel not active");
-    const size_t words = (size_t)3 * (m->cfg.num_layers * 4 + 1) * 8;
+    if (!m->pd_trace) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "phase tracing is off (set JL_PD_TRACE=1 before creating the model)");
+    const size_t words = (size_t)m->cfg.num_layers * 8 + 16;
     if ((size_t)out_words < words) return jl_set_error(ctx, JL_ERR_INVALID, "trace buffer too small (%zu words needed)", words);
-    M_CHECK(ensure_pages(m, session, position, position));
-    long long *dtr = nullptr;
-    M_CHECK(dev_alloc(ctx, (void **)&dtr, words * 8));
-    JL_CUDA_CHECK(ctx, cudaMemsetAsync(dtr, 0, words * 8, m->stream));
-    int32_t *hp = m->h_pinned;
-    hp[0] = token, hp[m->maxB] = position, hp[2 * m->maxB] = session;
-    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_tokens, hp, 4, cudaMemcpyHostToDevice, m->stream));
-    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_positions, hp + m->maxB, 4, cudaMemcpyHostToDevice, m->stream));
-    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_sessions, hp + 2 * m->maxB, 4, cudaMemcpyHostToDevice, m->stream));
-    mp.trace = dtr;
-    int rc = jl_launch_mega(ctx, m->stream, mp);
-    if (rc == JL_OK) {
-        cudaError_t e = cudaMemcpyAsync(out, dtr, words * 8, cudaMemcpyDeviceToHost, m->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
-        if (e != cudaSuccess) rc = jl_set_error(ctx, JL_ERR_CUDA, "trace copy failed: %s", cudaGetErrorString(e));
-    }
-    cudaFree(dtr);
-    return rc;
+    JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    JL_CUDA_CHECK(ctx, cudaStreamSynchronize(m->stream));
+    JL_CUDA_CHECK(ctx, cudaMemcpy(out, m->pd_trace, words * 8, cudaMemcpyDeviceToHost));
+    return (int)words;
 }
 
 extern "C" int jl_model_decode_mode(jl_model *m, int n) {
     if (!m || !m->finalized) return JL_ERR_INVALID;
-    if (use_mega(m)) {
-        MegaParams mp;
-        if (fill_mega(m, n, 0, false, mp)) return 2;
-    }
+    if (n == 1 && use_pd(m)) return 3;
     return use_graph(m) ? 1 : 0;
 }
 
@@ -1080,6 +1157,20 @@ extern "C" int jl_model_read_kv(jl_model *m, int session, int layer, int positio
             memcpy(&out[i], &u, 4);
         }
     }
+    return JL_OK;
+}
+
+extern "C" int jl_model_debug_read(jl_model *m, int which, float *out, int64_t n) {
+    if (!m || !m->finalized || !out || n <= 0) return JL_ERR_INVALID;
+    jl_ctx *ctx = m->ctx;
+    JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    const float *src[8] = {m->x, m->xb, m->q, m->k, m->v, m->att, m->hbuf, m->logits};
+    const size_t B = m->maxB;
+    const size_t cap[8] = {B * m->cfg.embedding_length, B * m->cfg.embedding_length, B * m->attn_seg, B * m->kv_seg, B * m->kv_seg,
+                           B * m->attn_seg, B * m->h_seg, (size_t)m->cfg.max_sessions * m->cfg.vocab_size};
+    if (which < 0 || which > 7 || (size_t)n > cap[which]) return jl_set_error(ctx, JL_ERR_INVALID, "debug_read: bad buffer / size");
+    JL_CUDA_CHECK(ctx, cudaStreamSynchronize(m->stream));
+    JL_CUDA_CHECK(ctx, cudaMemcpy(out, src[which], (size_t)n * 4, cudaMemcpyDeviceToHost));
     return JL_OK;
 }
 

@@ -170,6 +170,12 @@ class LlamaModel:
         self.ctx.check(self.lib.jl_model_read_hidden(self.h, session, ptr(out)))
         return out
 
+    def debug_read(self, which, n):
+        """Test hook: internal activation buffer of the last forward/decode call (0 x, 1 xb, 2 q, 3 k, 4 v, 5 att, 6 h, 7 logits)."""
+        out = np.empty(n, dtype=np.float32)
+        self.ctx.check(self.lib.jl_model_debug_read(self.h, which, ptr(out), n))
+        return out
+
     def decode_mode(self, n=1):
         return int(self.lib.jl_model_decode_mode(self.h, n))
 

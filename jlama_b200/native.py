@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libjlama_b200.so")
 
 JL_OK, JL_ERR_INVALID, JL_ERR_CUDA, JL_ERR_OOM, JL_ERR_UNSUPPORTED, JL_ERR_NCCL = 0, -1, -2, -3, -4, -5
 F32, BF16, Q4, I8 = 0, 1, 2, 3
-MODEL_NO_GRAPH, MODEL_NO_PDL, MODEL_NO_MEGA, MODEL_MEGA, MODEL_PDL = 1, 2, 4, 8, 16
+MODEL_NO_GRAPH, MODEL_NO_PDL, MODEL_NO_PERSISTENT, MODEL_PDL = 1, 2, 4, 16
 
 T_EMBED, T_OUT_NORM, T_LM_HEAD = 0, 1, 2
 L_ATTN_NORM, L_Q, L_K, L_V, L_O, L_FFN_NORM, L_GATE, L_DOWN, L_UP = range(9)
@@ -92,8 +92,9 @@ SIGNATURES = {
     "jl_model_decode_resident": (_i, [_vp, _i, C.c_int32, _i, _i, _vp]),
     "jl_model_read_kv": (_i, [_vp, _i, _i, _i, _i, _vp]),
     "jl_model_read_hidden": (_i, [_vp, _i, _vp]),
+    "jl_model_debug_read": (_i, [_vp, _i, _vp, _i64]),
     "jl_model_decode_mode": (_i, [_vp, _i]),
-    "jl_model_debug_trace": (_i, [_vp, _i, C.c_int32, _i, _vp, _i64]),
+    "jl_model_debug_trace": (_i, [_vp, _vp, _i64]),
     "jl_model_weight_bytes": (_i64, [_vp]),
     "jl_model_last_timing": (_i, [_vp, C.POINTER(_d), C.POINTER(_d)]),
     "jl_comm_unique_id": (_i, [_vp, _vp]),

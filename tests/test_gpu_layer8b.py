@@ -61,21 +61,26 @@ def test_one_8b_layer_teacher_forced_q8_activations(cuda_ctx, oracle, src_layer)
     gt, gl = gm.sample()
     ot, ol = om.sample(oh)
     worst["logits"] = _rel(gl, ol)
+    steps = ["prefill: hidden %.2e logits %.2e" % (worst["hidden"], worst["logits"])]
     assert gt == ot
     # decode fast path, teacher-forced with the oracle's token
     tok = ot
     for step in range(6):
         pos = len(prompt) + step
         nxt, lg = gm.decode([tok], [pos], sessions=[0], want_logits=True)
+        gx = gm.debug_read(0, cfg["E"])  # hidden row after the layer, decode path
         oh = om.batch_forward([tok], pos)
         ot, ol = om.sample(oh)
-        worst["logits"] = max(worst["logits"], _rel(lg[0], ol))
+        hr, lr = _rel(gx, oh), _rel(lg[0], ol)
+        steps.append("decode pos %d: hidden %.2e logits %.2e" % (pos, hr, lr))
+        worst["hidden"] = max(worst["hidden"], hr)
+        worst["logits"] = max(worst["logits"], lr)
         for which in (0, 1):
             worst["kv"] = max(worst["kv"], _rel(gm.read_kv(0, pos, which), om.kv_row(0, pos, which)))
         assert int(nxt[0]) == ot, "step %d: gpu %d oracle %d" % (step, int(nxt[0]), ot)
         tok = ot
-    print("8B-dims layer %d (teacher-forced): hidden %.2e, kv %.2e, logits %.2e of max" % (
-        src_layer, worst["hidden"], worst["kv"], worst["logits"]))
+    print("8B-dims layer %d (teacher-forced): hidden %.2e, kv %.2e, logits %.2e of max\n  " % (
+        src_layer, worst["hidden"], worst["kv"], worst["logits"]) + "\n  ".join(steps))
     assert worst["kv"] <= 2e-5
     assert worst["hidden"] <= 1e-4
     assert worst["logits"] <= 1e-4

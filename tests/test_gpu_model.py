@@ -114,8 +114,8 @@ def test_graph_eager_and_resident_decode_agree_bitwise(cuda_ctx, oracle):
     w = synth.make_weights(cfg)
     prompt = synth.random_prompt(cfg, 11)
     outs = []
-    NM = 0
-    for flags in (NM, native.MODEL_PDL, native.MODEL_NO_GRAPH):
+    NM = native.MODEL_NO_PERSISTENT  # the three forms of the kernel-per-op path
+    for flags in (NM, NM | native.MODEL_PDL, NM | native.MODEL_NO_GRAPH):
         m = LlamaModel(cuda_ctx, cfg, w, flags=flags)
         assert m.decode_mode() == (0 if flags & native.MODEL_NO_GRAPH else 1)
         t, l = m.generate(prompt, 10, want_logits=True)
@@ -132,60 +132,73 @@ def test_graph_eager_and_resident_decode_agree_bitwise(cuda_ctx, oracle):
         assert np.array_equal(t, outs[0][0]) and np.array_equal(l, outs[0][1])
 
 
-@pytest.mark.parametrize("name", ["tiny", "small", "small-hs128"])
-def test_megakernel_matches_per_op_kernels(cuda_ctx, oracle, name):
-    """The persistent megakernel and the kernel-per-op path share their arithmetic: same tokens, logits equal to
-    float rounding (attention tiles differ), incl. the device-resident feedback loop and batched sessions."""
+@pytest.mark.parametrize("name", ["tiny", "tiny-mha", "small", "small-hs128"])
+def test_persistent_kernel_matches_per_op_kernels(cuda_ctx, oracle, name):
+    """The persistent decode kernel (default for one session) and the graph of per-op kernels share their arithmetic:
+    same tokens, logits equal to float rounding, incl. the device-resident feedback loop."""
     from jlama_b200 import native, synth
     from jlama_b200.model import LlamaModel
     cfg = synth.get_config(name)
     w = synth.make_weights(cfg)
     prompt = synth.random_prompt(cfg, 21)
-    mega = LlamaModel(cuda_ctx, cfg, w, max_sessions=4, flags=native.MODEL_MEGA)
-    ref = LlamaModel(cuda_ctx, cfg, w, max_sessions=4)
-    assert mega.decode_mode(1) == 2 and mega.decode_mode(3) == 2 and ref.decode_mode(1) == 1
-    t1, l1 = mega.generate(prompt, 40, want_logits=True)
+    pk = LlamaModel(cuda_ctx, cfg, w, max_sessions=2)
+    ref = LlamaModel(cuda_ctx, cfg, w, max_sessions=2, flags=native.MODEL_NO_PERSISTENT)
+    assert pk.decode_mode(1) == 3 and pk.decode_mode(2) == 1 and ref.decode_mode(1) == 1
+    t1, l1 = pk.generate(prompt, 40, want_logits=True)
     t2, l2 = ref.generate(prompt, 40, want_logits=True)
     assert list(t1) == list(t2)
     assert np.abs(l1 - l2).max() <= 5e-4 * np.abs(l2).max()
-    # resident loop
-    mega.reset_session(0)
-    mega.batch_forward(prompt, 0)
-    first, _ = mega.sample()
-    rest = mega.decode_resident(first, len(prompt), 39)
+    ot, ol = oracle.OracleLlama(cfg, w, act_q8=True).generate(prompt, 40)
+    assert list(t1) == list(ot)
+    assert max(_rel(l1[i], ol[i]) for i in range(40)) <= 1e-2
+    # resident loop (token ids fed back on the device)
+    pk.reset_session(0)
+    pk.batch_forward(prompt, 0)
+    first, _ = pk.sample()
+    rest = pk.decode_resident(first, len(prompt), 39)
     assert [first] + list(rest) == list(t1)
-    # three sessions in one launch (MM = 4 with a dead row)
-    outs = []
-    for mdl in (mega, ref):
-        toks = []
-        for s in range(3):
-            mdl.reset_session(s)
-            mdl.batch_forward(prompt[: 7 + 5 * s], 0, session=s)
-            toks.append(mdl.sample(session=s)[0])
-        toks = np.array(toks, dtype=np.int32)
-        pos = np.array([7, 12, 17], dtype=np.int32)
-        hist = []
-        for _ in range(6):
-            toks, lg = mdl.decode(toks, pos, want_logits=True)
-            pos = pos + 1
-            hist.append((toks.copy(), lg.copy()))
-        outs.append(hist)
-    for (ta, la), (tb, lb) in zip(*outs):
-        assert list(ta) == list(tb)
-        assert np.abs(la - lb).max() <= 5e-4 * np.abs(lb).max()
-    mega.close()
+    # a second session on the same model keeps its own pages
+    pk.reset_session(1)
+    pk.batch_forward(prompt[:9], 0, session=1)
+    f1, _ = pk.sample(session=1)
+    r1 = pk.decode_resident(f1, 9, 7, session=1)
+    ref.reset_session(1)
+    ref.batch_forward(prompt[:9], 0, session=1)
+    f2, _ = ref.sample(session=1)
+    r2 = ref.decode_resident(f2, 9, 7, session=1)
+    assert f1 == f2 and list(r1) == list(r2)
+    pk.close()
     ref.close()
 
 
-def test_megakernel_long_context_splits(cuda_ctx, oracle):
-    """context long enough for several attention splits per (row, kv head) inside the megakernel"""
+def test_persistent_kernel_q8_weights(cuda_ctx, oracle):
+    """Q8_0 checkpoint (I8 weights, Q8ByteBufferTensor.java:37-223) x Q8 activations through the persistent kernel
+    (BASELINE config 3's weight format) against the oracle."""
     from jlama_b200 import native, synth
-    cfg, w, gm, om = _models(cuda_ctx, oracle, "tiny", max_batch=64, flags=native.MODEL_MEGA)
+    from jlama_b200.model import LlamaModel
+    cfg = synth.get_config("small")
+    w = synth.make_weights(cfg, wdtype=native.I8)
+    gm = LlamaModel(cuda_ctx, cfg, w)
+    assert gm.decode_mode(1) == 3
+    om = oracle.OracleLlama(cfg, w, act_q8=True)
+    prompt = synth.random_prompt(cfg, 13)
+    gt, gl = gm.generate(prompt, 20, want_logits=True)
+    ot, ol = om.generate(prompt, 20)
+    assert list(gt) == list(ot)
+    assert max(_rel(gl[i], ol[i]) for i in range(20)) <= 1e-2
+    gm.close()
+    om.close()
+
+
+def test_persistent_kernel_long_context_splits(cuda_ctx, oracle):
+    """context long enough for several attention splits per kv head inside the persistent kernel"""
+    from jlama_b200 import synth
+    cfg, w, gm, om = _models(cuda_ctx, oracle, "tiny", max_batch=64)
     prompt = synth.random_prompt(cfg, 150)
     gt, gl = gm.generate(prompt, 12, want_logits=True)
     om.reset()
     ot, ol = om.generate(prompt, 12, max_batch=64)
-    assert gm.decode_mode() == 2
+    assert gm.decode_mode() == 3
     assert list(gt) == list(ot)
     assert max(_rel(gl[i], ol[i]) for i in range(12)) <= 1e-2
     gm.close()

@@ -76,7 +76,7 @@ __device__ __forceinline__ unsigned long long ld_acq(const unsigned long long *c
 #define SPIN_UNTIL(cond)                                   \
     do {                                                   \
         unsigned _n = 0;                                   \
-        while (!(cond) && ++_n < (1u << 27)) {}            \
+        while (!(cond) && ++_n < (1u << 22)) {}            \
     } while (0)
 __device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(NT + 32, 1) probe_kernel(const Params P) {
                 const uint8_t *w = ph.w + (size_t)L * P.layer_stride_w;
                 const float *s = ph.s + (size_t)L * P.layer_stride_s;
                 for (long long c = c0 + lane; c - lane < c1; c += 32) {
-                    { unsigned n_ = 0; while (issued - s_consumed > lead && ++n_ < (1u << 24)) __nanosleep(100); }
+                    { unsigned n_ = 0; while (issued - s_consumed > lead && ++n_ < (1u << 16)) __nanosleep(100); }
                     if (c < c1) {
                         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(w + (size_t)c * CHUNK_WB), "r"(CHUNK_WB) : "memory");
                         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(s + (size_t)c * CHUNK_BLK), "r"(CHUNK_BLK * 4) : "memory");
@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(NT, 1) barrier_kernel(unsigned long long *cnt,
     } while (0)
 
 int main() {
+    setvbuf(stdout, NULL, _IONBF, 0);
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
     const int layers = 32;
