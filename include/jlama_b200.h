@@ -130,6 +130,9 @@ int jl_quantize_bf16(jl_ctx *ctx, const float *x, int rows, int ldx, int offset,
 /* AbstractTensor.quantize(Q4) weight quantiser on the GPU (Q4ByteBufferTensor.java:66-120);
  * byte-identical to the reference's files. */
 int jl_quantize_q4_weights(jl_ctx *ctx, const float *x, int64_t rows, int64_t cols, uint8_t *q, float *scales);
+/* AbstractTensor.quantize(I8) weight quantiser on the GPU (Q8ByteBufferTensor.java:47-90): iscale = 127/max,
+ * q = (byte)Math.round(x * iscale) -- round half up, unlike the truncating activation quantiser above. */
+int jl_quantize_q8_weights(jl_ctx *ctx, const float *x, int64_t rows, int64_t cols, int8_t *q, float *scales);
 
 /* ---- layer-level fused entry points on HOST buffers --------------------------------------
  * The reference does these as scalar Java loops outside TensorOperations (SURVEY 7 "hard parts");
@@ -249,6 +252,38 @@ int64_t jl_model_weight_bytes(jl_model *m);
 /* event-timed duration (ms) of the last jl_model_decode / decode_resident GPU work, and of its
  * dominant kernel class (the quantised GEMV), measured with CUDA events on the model stream */
 int jl_model_last_timing(jl_model *m, double *total_ms, double *gemv_ms);
+
+/* ---- JQ4 / JQ8 checkpoints: safetensors with Jlama's dtype strings "Q4" / "I8" + "<name>.qb" f32 block scales ------------
+ * core/safetensors/SafeTensorSupport.java:54-102,215-332; Weights.java:49-66,99-179; SafeTensorIndex.java:59-236.
+ * Files are mapped whole (64-bit), so the reference's <= 2 GiB mmap splits (SafeTensorIndex.java:121-236) are not needed. */
+typedef struct jl_st jl_st;
+#define JL_ST_F16 4 /* dtype code reported for F16 tensors (read-only; bound to a model as F32, Weights.java:137-152) */
+/* path: a .safetensors file, or a directory with model.safetensors or model.safetensors.index.json + shards */
+int jl_st_open(const char *path, jl_st **out);
+int jl_st_close(jl_st *st);
+const char *jl_st_last_error(void);
+int jl_st_count(jl_st *st);
+int jl_st_find(jl_st *st, const char *name); /* index or -1 */
+/* tensors are ordered by data offset (TensorInfo.compareTo); dtype -1 = a dtype string this library does not know */
+int jl_st_info(jl_st *st, int i, const char **name, int *dtype, int *ndim, int64_t *shape4, int64_t *nbytes);
+const void *jl_st_data(jl_st *st, int i); /* pointer into the read-only mapping */
+const char *jl_st_metadata(jl_st *st, const char *key); /* "__metadata__" entry or NULL */
+int jl_st_majority_dtype(jl_st *st); /* Weights.findDType: ".qb" tensors not counted, F16 counts as F32 */
+/* one file: 8-byte LE header length, JSON header (data_offsets relative to the data section), raw bytes in the given order */
+int jl_st_write(const char *path, int n, const char *const *names, const int *dtypes, const int *ndims, const int64_t *shapes4,
+                const void *const *data, const int64_t *nbytes, int n_meta, const char *const *meta_kv);
+/* SafeTensorSupport.quantizeModel with the block quantisers on the GPU (byte-identical files): 2-D tensors whose name contains
+ * none of the comma-separated `skip_csv` substrings (NULL = "norm", QuantizeCommand.java:36-38) and whose first dim is not 1
+ * (AbstractTensor.java:284) become qtype (JL_Q4 / JL_I8) + "<name>.qb"; names starting with a `drop_csv` prefix are omitted. */
+int jl_quantize_model(jl_ctx *ctx, const char *src_dir, const char *dst_dir, int qtype, const char *skip_csv, const char *drop_csv);
+/* config.json -> jl_model_config (safetensors/Config.java:253-287, llama/LlamaConfig.java:27-57); working_qtype I8, F32 KV, tp 1 */
+int jl_config_from_json(const char *config_json_path, jl_model_config *cfg);
+/* LlamaModel.loadInputWeights / loadTransformerBlockWeights / loadOutputWeights (llama/LlamaModel.java:68-156): registers this
+ * rank's shard of every tensor of the checkpoint (rows per Weights.getLoadOffsets :99-117, columns per AbstractTensor.sparsify)
+ * and binds it; call jl_model_finalize afterwards.  ids_out receives the registered tensor ids (for jl_unregister_tensor). */
+int jl_model_load_safetensors(jl_model *m, jl_ctx *ctx, jl_st *st, int64_t *ids_out, int ids_cap, int *n_ids);
+/* this model's DistributedContext and shard count */
+int jl_model_tp_layout(jl_model *m, jl_dctx *out, int *tp_size);
 
 /* ---- jlama-net replacement: NCCL over NVLink instead of gRPC -------------------------------
  * JlamaService.combine (jlama-net/src/main/java/com/github/tjake/jlama/net/grpc/JlamaService.java:300-359)

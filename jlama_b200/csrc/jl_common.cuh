@@ -144,6 +144,7 @@ int jl_launch_quantize_bf16(jl_ctx *ctx, cudaStream_t s, const float *x, int row
                             uint16_t *out);
 int jl_launch_quantize_q4w(jl_ctx *ctx, cudaStream_t s, const float *x, int64_t rows, int64_t cols, uint8_t *q,
                            float *scales);
+int jl_launch_quantize_q8w(jl_ctx *ctx, cudaStream_t s, const float *x, int64_t rows, int64_t cols, int8_t *q, float *scales);
 int jl_launch_rmsnorm(jl_ctx *ctx, cudaStream_t s, const float *x, int rows, int ldx, int w_dtype, const void *w, float adj,
                       float eps, int E, int offset, int length, float *out);
 int jl_launch_softmax(jl_ctx *ctx, cudaStream_t s, float *x, int offset, int length);

@@ -183,6 +183,40 @@ int jl_launch_quantize_q4w(jl_ctx *ctx, cudaStream_t s, const float *x, int64_t 
     return JL_OK;
 }
 
+// ---- Q8 weight quantiser (Q8ByteBufferTensor.java:47-90): max from Float.MIN_VALUE, iscale = 127/max, q = (byte)Math.round(x*iscale)
+__global__ void quantize_q8w_kernel(const float *x, long long rows, long long cols, int8_t *q, float *scales) {
+    const int lane = threadIdx.x & 31;
+    const long long nblk = cols / 32, total = rows * nblk;
+    for (long long w = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5); w < total;
+         w += (long long)gridDim.x * (blockDim.x / 32)) {
+        const float v = x[w * 32 + lane];
+        float mx = fmaxf(warp_max(fabsf(v)), 1.401298464e-45f); // 'absv > max' never replaces max with NaN
+        const float iscale = __fdiv_rn(127.0f, mx);
+        const float scale = iscale != 0.0f ? __fdiv_rn(1.0f, iscale) : 0.0f;
+        const float f0 = __fmul_rn(v, iscale);
+        // Math.round(float) = floor(f0 + 1/2) evaluated exactly; NaN -> 0; (int) saturates, (byte) wraps
+        int r;
+        if (f0 != f0) r = 0;
+        else {
+            const double t = floor((double)f0 + 0.5);
+            r = t >= 2147483647.0 ? 2147483647 : (t <= -2147483648.0 ? (int)0x80000000 : (int)t);
+        }
+        q[w * 32 + lane] = (int8_t)r;
+        if (lane == 0) scales[w] = scale;
+    }
+}
+int jl_launch_quantize_q8w(jl_ctx *ctx, cudaStream_t s, const float *x, int64_t rows, int64_t cols, int8_t *q, float *scales) {
+    if (cols % 32) return jl_set_error(ctx, JL_ERR_INVALID, "quantize_q8_weights: cols must be a multiple of 32");
+    long long total = rows * (cols / 32);
+    if (total <= 0) return JL_OK;
+    long long blocks = (total + 7) / 8;
+    if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+    quantize_q8w_kernel<<<(int)blocks, 256, 0, s>>>(x, rows, cols, q, scales);
+    ctx->launches++;
+    JL_CUDA_CHECK(ctx, cudaGetLastError());
+    return JL_OK;
+}
+
 // ---- RMSNorm (RMSNorm.java:34-56): one CTA per row -------------------------------------------------------------
 __global__ void rmsnorm_kernel(const float *x, int ldx, int w_dtype, const void *w, float adj, float eps, int E,
                                int offset, int length, float *out) {

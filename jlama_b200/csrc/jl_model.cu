@@ -1160,6 +1160,14 @@ extern "C" int jl_model_read_kv(jl_model *m, int session, int layer, int positio
     return JL_OK;
 }
 
+// DistributedContext of this model (which rows / columns of every tensor this rank holds) and its shard count
+extern "C" int jl_model_tp_layout(jl_model *m, jl_dctx *out, int *tp_size) {
+    if (!m || !out) return JL_ERR_INVALID;
+    *out = m->d;
+    if (tp_size) *tp_size = m->cfg.tp_size;
+    return JL_OK;
+}
+
 extern "C" int jl_model_debug_read(jl_model *m, int which, float *out, int64_t n) {
     if (!m || !m->finalized || !out || n <= 0) return JL_ERR_INVALID;
     jl_ctx *ctx = m->ctx;

@@ -476,6 +476,23 @@ extern "C" int jl_quantize_q4_weights(jl_ctx *ctx, const float *x, int64_t rows,
     return JL_OK;
 }
 
+extern "C" int jl_quantize_q8_weights(jl_ctx *ctx, const float *x, int64_t rows, int64_t cols, int8_t *q, float *scales) {
+    HOST_OP_PROLOGUE();
+    if (!x || !q || !scales || rows <= 0 || cols <= 0) return jl_set_error(ctx, JL_ERR_INVALID, "quantize_q8_weights: bad arguments");
+    const size_t xb = (size_t)rows * cols * 4, qb = (size_t)rows * cols, sb = (size_t)rows * (cols / 32) * 4;
+    float *dx = (float *)jl_scratch(ctx, 0, xb);
+    int8_t *dq = (int8_t *)jl_scratch(ctx, 1, qb);
+    float *ds = (float *)jl_scratch(ctx, 2, sb);
+    if (!dx || !dq || !ds) return JL_ERR_OOM;
+    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(dx, x, xb, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = jl_launch_quantize_q8w(ctx, ctx->stream, dx, rows, cols, dq, ds);
+    if (rc) return rc;
+    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(q, dq, qb, cudaMemcpyDeviceToHost, ctx->stream));
+    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(scales, ds, sb, cudaMemcpyDeviceToHost, ctx->stream));
+    JL_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return JL_OK;
+}
+
 extern "C" int jl_rmsnorm(jl_ctx *ctx, const float *x, int rows, int ldx, int w_dtype, const void *w, float weight_adjustment,
                           float eps, int embedding_length, int offset, int length, float *out) {
     HOST_OP_PROLOGUE();

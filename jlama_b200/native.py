@@ -74,6 +74,21 @@ SIGNATURES = {
     "jl_quantize_q8": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "jl_quantize_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "jl_quantize_q4_weights": (_i, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "jl_quantize_q8_weights": (_i, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "jl_st_open": (_i, [C.c_char_p, C.POINTER(_vp)]),
+    "jl_st_close": (_i, [_vp]),
+    "jl_st_last_error": (C.c_char_p, []),
+    "jl_st_count": (_i, [_vp]),
+    "jl_st_find": (_i, [_vp, C.c_char_p]),
+    "jl_st_info": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i64), C.POINTER(_i64)]),
+    "jl_st_data": (_vp, [_vp, _i]),
+    "jl_st_metadata": (C.c_char_p, [_vp, C.c_char_p]),
+    "jl_st_majority_dtype": (_i, [_vp]),
+    "jl_st_write": (_i, [C.c_char_p, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "jl_quantize_model": (_i, [_vp, C.c_char_p, C.c_char_p, _i, C.c_char_p, C.c_char_p]),
+    "jl_config_from_json": (_i, [C.c_char_p, C.POINTER(ModelConfig)]),
+    "jl_model_load_safetensors": (_i, [_vp, _vp, _vp, _vp, _i, C.POINTER(_i)]),
+    "jl_model_tp_layout": (_i, [_vp, C.POINTER(Dctx), C.POINTER(_i)]),
     "jl_rmsnorm": (_i, [_vp, _vp, _i, _i, _i, _vp, _f, _f, _i, _i, _i, _vp]),
     "jl_softmax": (_i, [_vp, _vp, _i, _i]),
     "jl_silu_mul": (_i, [_vp, _vp, _vp, _i, _i, _i, _i]),
