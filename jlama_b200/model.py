@@ -73,6 +73,40 @@ class LlamaModel:
             self.close()  # a rejected checkpoint must not leak the half-built model or its tensors
             raise
 
+    @classmethod
+    def from_checkpoint(cls, ctx, path, max_context=0, max_sessions=1, tp_rank=0, tp_size=1, working_qtype=I8, kv_dtype=F32,
+                        flags=0, prefill_tensor_core=0, max_batch=256):
+        """ModelSupport.loadModel: a Jlama checkpoint directory (config.json + model.safetensors[.index.json]) read, sharded
+        and bound entirely behind the C ABI (jl_config_from_json, jl_st_open, jl_model_load_safetensors)."""
+        import os
+        from . import safetensors_io as sio
+        mc = sio.config_from_json(os.path.join(path, "config.json"))
+        mc.working_qtype, mc.kv_dtype, mc.max_batch, mc.max_sessions, mc.max_context = working_qtype, kv_dtype, max_batch, max_sessions, max_context
+        mc.tp_rank, mc.tp_size, mc.flags, mc.prefill_tensor_core = tp_rank, tp_size, flags, prefill_tensor_core
+        self = cls.__new__(cls)
+        self.ctx, self.lib = ctx, ctx.lib
+        self.cfg = dict(ctx=mc.context_length, E=mc.embedding_length, H=mc.hidden_length, heads=mc.num_heads, kv_heads=mc.num_kv_heads,
+                        layers=mc.num_layers, vocab=mc.vocab_size, eps=mc.layer_norm_eps, rope_theta=mc.rope_theta, name=os.path.basename(path))
+        self.dctx = DistributedContext(self.cfg, tp_rank, tp_size)
+        self.max_sessions = max_sessions
+        self._ids = []
+        h = C.c_void_p()
+        ctx.check(self.lib.jl_model_create(ctx.h, C.byref(mc), C.byref(h)))
+        self.h = h
+        try:
+            with sio.SafeTensors(path) as st:
+                cap = 16 * mc.num_layers + 8
+                ids = (C.c_int64 * cap)()
+                n = C.c_int()
+                rc = self.lib.jl_model_load_safetensors(self.h, ctx.h, st.h, ids, cap, C.byref(n))
+                self._ids = [ids[i] for i in range(min(n.value, cap))]
+                ctx.check(rc)
+            ctx.check(self.lib.jl_model_finalize(self.h))
+        except Exception:
+            self.close()
+            raise
+        return self
+
     def _load(self, ctx, cfg, weights, tp_size):
         if callable(weights):
             get = weights

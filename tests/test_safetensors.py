@@ -1,0 +1,95 @@
+"""Checkpoint I/O on CPU (no GPU): the reader against the reference's own parser fixture (jlama-tests/.../safetensors/
+TestParser.java:41-69), Jlama's Q4/I8 + ".qb" conventions (SafeTensorSupport.java:264-277, Weights.java:49-66,153-171), the
+writer round trip, index.json shard maps and the header-length guards (SafeTensorSupport.java:59-70)."""
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from jlama_b200 import native, synth
+from jlama_b200 import safetensors_io as sio
+
+
+def test_reference_parser_fixture(tmp_path):
+    # TestParser.simpleTest: preamble 0x59 = 89 header bytes, one F32 [2,2] tensor, __metadata__ {"foo":"bar"}
+    header = b'{"test":{"dtype":"F32","shape":[2,2],"data_offsets":[0,16]},"__metadata__":{"foo":"bar"}}'
+    assert len(header) == 0x59
+    blob = bytes.fromhex("5900000000000000") + header + struct.pack("<4f", 1.0, 2.0, 3.0, 4.0)
+    p = tmp_path / "t.safetensors"
+    p.write_bytes(blob)
+    with sio.SafeTensors(str(p)) as st:
+        assert st.names() == ["test"]
+        assert st.info("test") == {"dtype": "F32", "dtype_code": native.F32, "shape": (2, 2), "nbytes": 16}
+        t = st.get("test")
+        assert t.shape == (2, 2) and t.tolist() == [[1.0, 2.0], [3.0, 4.0]]
+        assert st.metadata("foo") == "bar" and st.metadata("nope") is None
+
+
+def test_header_length_guards(tmp_path):
+    p = tmp_path / "neg.safetensors"
+    p.write_bytes(struct.pack("<q", -5) + b"{}")
+    with pytest.raises(sio.SafeTensorsError, match="negative"):
+        sio.SafeTensors(str(p))
+    p2 = tmp_path / "big.safetensors"
+    p2.write_bytes(struct.pack("<q", (1 << 30) + 1) + b"{}")
+    with pytest.raises(sio.SafeTensorsError, match="exceeds"):
+        sio.SafeTensors(str(p2))
+    p3 = tmp_path / "off.safetensors"
+    h = b'{"t":{"dtype":"F32","shape":[4],"data_offsets":[0,16]}}'
+    p3.write_bytes(struct.pack("<q", len(h)) + h + b"\0" * 8)  # data shorter than the offsets claim
+    with pytest.raises(sio.SafeTensorsError):
+        sio.SafeTensors(str(p3))
+
+
+def test_jq4_checkpoint_round_trip(tmp_path):
+    cfg = synth.get_config("tiny")
+    w = synth.make_weights(cfg)
+    d = tmp_path / "tiny-JQ4"
+    sio.save_checkpoint(str(d), w, cfg)
+    raw = (d / "model.safetensors").read_bytes()
+    hlen = struct.unpack("<q", raw[:8])[0]
+    hdr = json.loads(raw[8:8 + hlen])
+    q = hdr["model.layers.0.self_attn.q_proj.weight"]
+    assert q["dtype"] == "Q4" and q["shape"] == [cfg["E"], cfg["E"]]
+    assert q["data_offsets"][1] - q["data_offsets"][0] == cfg["E"] * cfg["E"] // 2  # N*K/2 bytes
+    qb = hdr["model.layers.0.self_attn.q_proj.weight.qb"]
+    assert qb["dtype"] == "F32" and qb["shape"] == [cfg["E"], cfg["E"] // 32]
+    assert hdr["model.norm.weight"]["dtype"] == "F32"
+    with sio.SafeTensors(str(d)) as st:
+        assert st.majority_dtype() == native.Q4  # .qb tensors are not counted (Weights.java:52)
+        offs = [hdr[n]["data_offsets"][0] for n in st.names()]
+        assert offs == sorted(offs)  # TensorInfo.compareTo order
+        for name, (dt, data, scales) in w.items():
+            dt2, data2, scales2 = st.load(name)
+            assert dt2 == dt and np.array_equal(data2, data)
+            assert (scales is None and scales2 is None) or np.array_equal(scales2, scales)
+    mc = sio.config_from_json(str(d / "config.json"))
+    assert (mc.embedding_length, mc.hidden_length, mc.num_heads, mc.num_kv_heads, mc.num_layers, mc.vocab_size, mc.head_size) == (
+        cfg["E"], cfg["H"], cfg["heads"], cfg["kv_heads"], cfg["layers"], cfg["vocab"], cfg["E"] // cfg["heads"])
+    assert mc.rope_theta == cfg["rope_theta"] and abs(mc.layer_norm_eps - cfg["eps"]) < 1e-12
+
+
+def test_index_json_shards_and_i8(tmp_path):
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((4, 64)).astype(np.float32)
+    q8 = rng.integers(-127, 128, (8, 64), dtype=np.int8)
+    s8 = rng.random((8, 2), dtype=np.float32)
+    bf = rng.integers(0, 65536, (2, 32), dtype=np.uint16)
+    d = tmp_path / "sharded"
+    d.mkdir()
+    sio.write_safetensors(str(d / "model-00001-of-00002.safetensors"), {"a": (native.F32, a, None), "b": (native.BF16, bf, None)})
+    sio.write_safetensors(str(d / "model-00002-of-00002.safetensors"), {"w": (native.I8, q8, None), "w.qb": (native.F32, s8, None)},
+                          metadata={"format": "pt"})
+    (d / "model.safetensors.index.json").write_text(json.dumps({"metadata": {}, "weight_map": {
+        "a": "model-00001-of-00002.safetensors", "b": "model-00001-of-00002.safetensors",
+        "w": "model-00002-of-00002.safetensors", "w.qb": "model-00002-of-00002.safetensors"}}))
+    with sio.SafeTensors(str(d)) as st:
+        assert sorted(st.names()) == ["a", "b", "w", "w.qb"]
+        assert np.array_equal(st.get("a"), a) and np.array_equal(st.get("b"), bf)
+        dt, data, scales = st.load("w")
+        assert dt == native.I8 and np.array_equal(data, q8) and np.array_equal(scales, s8)
+        assert st.metadata("format") == "pt"
+    with pytest.raises(sio.SafeTensorsError):
+        sio.SafeTensors(str(tmp_path / "missing-dir-or-file"))
