@@ -140,6 +140,16 @@ int jl_quantize_q8_weights(jl_ctx *ctx, const float *x, int64_t rows, int64_t co
 /* RMSNorm.forward (core/model/RMSNorm.java:34-56) */
 int jl_rmsnorm(jl_ctx *ctx, const float *x, int rows, int ldx, int w_dtype, const void *w, float weight_adjustment,
                float eps, int embedding_length, int offset, int length, float *out);
+/* LayerNorm.forward (core/model/LayerNorm.java:41-67; GPT-2 family): statistics over [offset, offset+length) divided by
+ * embedding_length, out = (x - mean) * invStddev * w + bias.  Weights / bias F32 or BF16. */
+int jl_layernorm(jl_ctx *ctx, const float *x, int rows, int ldx, int w_dtype, const void *w, int b_dtype, const void *bias, float eps,
+                 int embedding_length, int offset, int length, float *out);
+/* ActivationFunction.eval in place (core/math/ActivationFunction.java:29-37): type 0 SILU, 1 GELU (tanh form, also
+ * GELU_PYTORCH_TANH), 2 TANH; double-precision math cast to float like the reference. */
+#define JL_ACT_SILU 0
+#define JL_ACT_GELU 1
+#define JL_ACT_TANH 2
+int jl_activation(jl_ctx *ctx, int type, float *x, int rows, int ld, int offset, int length);
 /* VectorMath.softMax (core/math/VectorMath.java:69-90) */
 int jl_softmax(jl_ctx *ctx, float *x, int offset, int length);
 /* MLPBlock activation loop + maccumulate (core/model/MLPBlock.java:132-141): gate = silu(gate) * up */

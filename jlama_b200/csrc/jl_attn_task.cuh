@@ -20,10 +20,13 @@ struct AttnTask {
 
 // softmax exponent exactly as the reference computes it: (float)Math.exp((double)x) (one out-of-line copy: the double exp
 // is ~150 instructions and the attention kernel starts with a cold instruction cache every layer)
-static __device__ __noinline__ float exp_ref(float x) { return (float)exp((double)x); }
+#ifndef JL_EXP_FN
+#define JL_EXP_FN __noinline__
+#endif
+static __device__ JL_EXP_FN float exp_ref(float x) { return (float)exp((double)x); }
 // two independent exponentials in one call: the two double-precision dependency chains interleave, so the pair costs
 // about the latency of one (the softmax needs exp(s - m_new) and the running-sum correction exp(m_old - m_new) together)
-static __device__ __noinline__ float2 exp_ref2(float a, float b) { return make_float2((float)exp((double)a), (float)exp((double)b)); }
+static __device__ JL_EXP_FN float2 exp_ref2(float a, float b) { return make_float2((float)exp((double)a), (float)exp((double)b)); }
 
 template <int NT>
 __device__ __forceinline__ void task_bar() {

@@ -147,6 +147,9 @@ int jl_launch_quantize_q4w(jl_ctx *ctx, cudaStream_t s, const float *x, int64_t 
 int jl_launch_quantize_q8w(jl_ctx *ctx, cudaStream_t s, const float *x, int64_t rows, int64_t cols, int8_t *q, float *scales);
 int jl_launch_rmsnorm(jl_ctx *ctx, cudaStream_t s, const float *x, int rows, int ldx, int w_dtype, const void *w, float adj,
                       float eps, int E, int offset, int length, float *out);
+int jl_launch_layernorm(jl_ctx *ctx, cudaStream_t s, const float *x, int rows, int ldx, int w_dtype, const void *w, int b_dtype,
+                        const void *bias, float eps, int E, int offset, int length, float *out);
+int jl_launch_activation(jl_ctx *ctx, cudaStream_t s, int type, float *x, int rows, int ld, int offset, int length);
 int jl_launch_softmax(jl_ctx *ctx, cudaStream_t s, float *x, int offset, int length);
 int jl_launch_silu_mul(jl_ctx *ctx, cudaStream_t s, float *gate, const float *up, int rows, int ld, int offset, int length);
 // embedding rows -> f32 hidden (LlamaModel.java:68-100); tokens on device

@@ -256,6 +256,76 @@ int jl_launch_rmsnorm(jl_ctx *ctx, cudaStream_t s, const float *x, int rows, int
     return JL_OK;
 }
 
+// ---- LayerNorm (model/LayerNorm.java:41-67, GPT-2 family): mean and E[x^2] over [offset, offset+length) divided by
+// embeddingLength, variance = E[x^2] - mean^2, invStddev = 1 / (float)sqrt(variance + eps), out = (x - mean) * invStddev * w + b.
+// The reference accumulates sum and sumSq sequentially in float; here the float products are summed in double and rounded to
+// float once (closer to the exact sums than either order; 1e-6-level differences, the tests' tolerance says so).
+__global__ void layernorm_kernel(const float *x, int ldx, int w_dtype, const void *w, int b_dtype, const void *bias, float eps, int E,
+                                 int offset, int length, float *out) {
+    const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ double red[2][8];
+    __shared__ float stat[2];
+    const float *xr = x + (size_t)r * ldx;
+    double s = 0.0, ss = 0.0;
+    for (int i = tid; i < length; i += blockDim.x) {
+        const float v = xr[offset + i];
+        s += (double)v;
+        ss += (double)__fmul_rn(v, v);
+    }
+    s = warp_sum_d(s), ss = warp_sum_d(ss);
+    if (lane == 0) red[0][warp] = s, red[1][warp] = ss;
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0, b = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) a += red[0][i], b += red[1][i];
+        const float sum = (float)a, sumSq = (float)b;
+        const float mean = __fdiv_rn(sum, (float)E);
+        const float variance = __fsub_rn(__fdiv_rn(sumSq, (float)E), __fmul_rn(mean, mean));
+        stat[0] = mean;
+        stat[1] = __fdiv_rn(1.0f, (float)sqrt((double)__fadd_rn(variance, eps)));
+    }
+    __syncthreads();
+    const float mean = stat[0], inv = stat[1];
+    for (int i = tid; i < length; i += blockDim.x) {
+        const int c = offset + i;
+        const float wv = w_dtype == JL_BF16 ? bf16_bits_to_f32(((const uint16_t *)w)[c]) : ((const float *)w)[c];
+        const float bv = b_dtype == JL_BF16 ? bf16_bits_to_f32(((const uint16_t *)bias)[c]) : ((const float *)bias)[c];
+        out[(size_t)r * ldx + c] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(xr[c], mean), inv), wv), bv);
+    }
+}
+int jl_launch_layernorm(jl_ctx *ctx, cudaStream_t s, const float *x, int rows, int ldx, int w_dtype, const void *w, int b_dtype,
+                        const void *bias, float eps, int E, int offset, int length, float *out) {
+    if (rows <= 0 || length <= 0) return JL_OK;
+    layernorm_kernel<<<rows, 256, 0, s>>>(x, ldx, w_dtype, w, b_dtype, bias, eps, E, offset, length, out);
+    ctx->launches++;
+    JL_CUDA_CHECK(ctx, cudaGetLastError());
+    return JL_OK;
+}
+
+// ---- ActivationFunction.eval (math/ActivationFunction.java:29-37) in place: 0 SILU, 1 GELU / GELU_PYTORCH_TANH, 2 TANH; double math
+__global__ void activation_kernel(int type, float *x, int rows, int ld, int offset, int length) {
+    const long long n = (long long)rows * length;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float *p = x + (size_t)(i / length) * ld + offset + (i % length);
+        const float v = *p;
+        float o;
+        if (type == 0) o = silu_ref(v);
+        else if (type == 1) o = (float)(0.5 * (double)v * (1.0 + tanh(sqrt(2.0 / 3.14159265358979323846) * ((double)v + 0.044715 * pow((double)v, 3.0)))));
+        else o = (float)tanh((double)v);
+        *p = o;
+    }
+}
+int jl_launch_activation(jl_ctx *ctx, cudaStream_t s, int type, float *x, int rows, int ld, int offset, int length) {
+    if (rows <= 0 || length <= 0) return JL_OK;
+    long long n = (long long)rows * length;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    activation_kernel<<<blocks, 256, 0, s>>>(type, x, rows, ld, offset, length);
+    ctx->launches++;
+    JL_CUDA_CHECK(ctx, cudaGetLastError());
+    return JL_OK;
+}
+
 // ---- softmax (VectorMath.java:69-90), single row, one CTA ---------------------------------------------------------
 __global__ void softmax_kernel(float *x, int offset, int length) {
     __shared__ float red[32];

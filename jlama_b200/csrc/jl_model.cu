@@ -64,7 +64,7 @@ struct jl_model {
     // persistent decode kernel (jl_pdecode.cu)
     bool pd_ok = false;
     int pd_wdtype = JL_Q4;
-    PdLayer *pd_layers = nullptr;
+    std::vector<PdLayer> pd_layers; // host copy; uploaded to constant memory by jl_launch_pdecode
     unsigned long long *pd_sync = nullptr, *pd_slots = nullptr, *pd_trace = nullptr;
     unsigned *pd_att_done = nullptr;
     int pd_vocab0 = 0, pd_vocab_rows = 0;
@@ -343,8 +343,7 @@ extern "C" int jl_model_finalize(jl_model *m) {
                 pl[L].ffn_norm = m->l[(size_t)L * 9 + JL_L_FFN_NORM].data;
                 pl[L].ffn_norm_dt = m->l[(size_t)L * 9 + JL_L_FFN_NORM].dtype;
             }
-            M_CHECK(dev_alloc(ctx, (void **)&m->pd_layers, pl.size() * sizeof(PdLayer)));
-            JL_CUDA_CHECK(ctx, cudaMemcpy(m->pd_layers, pl.data(), pl.size() * sizeof(PdLayer), cudaMemcpyHostToDevice));
+            m->pd_layers = pl;
             M_CHECK(dev_alloc(ctx, (void **)&m->pd_sync, PD_SYNC_WORDS * 8));
             JL_CUDA_CHECK(ctx, cudaMemset(m->pd_sync, 0, PD_SYNC_WORDS * 8));
             M_CHECK(dev_alloc(ctx, (void **)&m->pd_slots, (size_t)ctx->sm_count * 8));
@@ -433,13 +432,14 @@ extern "C" int jl_model_free(jl_model *m) {
                 break;
             }
     }
+    jl_pdecode_forget(ctx->device, m);
     for (auto &kv : m->graphs) cudaGraphExecDestroy(kv.second);
     for (void *p : m->ipc_opened) cudaIpcCloseMemHandle(p);
     for (void *p : m->page_table_host)
         if (p) cudaFree(p);
     void *bufs[] = {m->ln, m->hbuf2, m->abf, m->rope, m->page_table_dev, m->x, m->xb, m->q, m->k, m->v, m->att, m->hbuf, m->partial, m->logits,
                     m->last_hidden, m->attn_ws, m->d_tokens, m->d_positions, m->d_sessions, m->d_next, m->d_hist, m->d_counter,
-                    m->argmax_scratch, m->fda_done, m->pd_layers, m->pd_sync, m->pd_slots, m->pd_att_done, m->pd_trace, m->ll_o, m->ll_d, m->ll_a};
+                    m->argmax_scratch, m->fda_done, m->pd_sync, m->pd_slots, m->pd_att_done, m->pd_trace, m->ll_o, m->ll_d, m->ll_a};
     for (void *p : bufs)
         if (p) cudaFree(p);
     if (m->h_pinned) cudaFreeHost(m->h_pinned);
@@ -872,7 +872,7 @@ static void fill_pd(jl_model *m, int max_pos, bool resident, bool want_logits, P
     p.head0_global = m->d.headStart, p.kv_head0_global = m->d.groupHeadStart;
     p.eps = c.layer_norm_eps;
     p.attn_scale = (float)(1.0 / sqrt((double)c.head_size)); // CausalSelfAttention.java:134
-    p.lw = m->pd_layers;
+    p.lw = nullptr;
     p.embed_dt = m->g[JL_T_EMBED].dtype, p.embed_w = m->g[JL_T_EMBED].data, p.embed_s = m->g[JL_T_EMBED].scales;
     p.out_norm = m->g[JL_T_OUT_NORM].data, p.out_norm_dt = m->g[JL_T_OUT_NORM].dtype;
     const DevTensor &head = m->g_set[JL_T_LM_HEAD] ? m->g[JL_T_LM_HEAD] : m->g[JL_T_EMBED];
@@ -917,7 +917,7 @@ static int run_decode(jl_model *m, int n, int max_pos, bool resident, bool want_
     if (n == 1 && use_pd(m)) {
         PdParams pp;
         fill_pd(m, max_pos, resident, want_logits, pp);
-        return jl_launch_pdecode(ctx, m->stream, pp, m->pd_wdtype);
+        return jl_launch_pdecode(ctx, m->stream, pp, m->pd_layers.data(), m, m->pd_wdtype);
     }
     // fused decode attention: one split per 64 positions, bucketed so that few graphs are captured
     int splits = (max_pos + 1 + 63) / 64;

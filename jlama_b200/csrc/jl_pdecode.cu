@@ -28,6 +28,8 @@
 #include "jl_pdecode.cuh"
 #include "jl_gemv_body.cuh"
 #include "jl_attn_task.cuh"
+#include <stddef.h>
+#include <string.h>
 
 #define PD_NT PD_THREADS
 #define PD_NWARP (PD_NT / 32)
@@ -36,6 +38,27 @@
 #define PD_SPIN_LOCAL (1u << 22)
 #define PD_SPIN_PEER (1u << 26)
 #define EPI_LL 3 // partial sums to every rank's LL receive buffer (tensor parallel o_proj / down_proj)
+#ifndef PD_PHASE_FN
+#define PD_PHASE_FN __forceinline__
+#endif
+
+// ---- model constants ----------------------------------------------------------------------------------------------------
+// Everything a phase needs -- dims, buffers, per-layer weight pointers -- lives in __constant__ memory, so the phase bodies use
+// constant-bank operands exactly like the stand-alone kernels use their kernel parameters.  (First version: descriptors built
+// in registers / local memory and handed to the phase functions by reference cost ~40 local loads per chunk in the hot loop
+// and made every phase 2x slower than its stand-alone kernel: 4.5 ms/token.)  The host uploads the block when another model
+// takes the device over (jl_launch_pdecode); token-varying values (context splits, flags) are kernel arguments.
+#define PD_MAX_LAYERS 128
+struct PdConst {
+    PdParams P[1];
+    PdLayer layers[PD_MAX_LAYERS];
+};
+__constant__ PdConst c_pd;
+#define CP (c_pd.P[0])
+// (the helpers below still carry a `pz` argument from an experiment with opaque-indexed constant reads; it is unused)
+#define PD_OPAQUE_ZERO(name) const int name = 0
+
+enum { PH_QKV = 0, PH_O, PH_GU, PH_DOWN };
 
 // ---- cross-CTA ordering ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long pd_ld_acquire(const unsigned long long *p) {
@@ -49,13 +72,14 @@ __device__ __forceinline__ unsigned long long pd_ld_volatile(const unsigned long
     return v;
 }
 // all threads of the CTA call; publishes everything the CTA wrote in this phase
-__device__ __forceinline__ void pd_arrive(const PdParams &P, int which) {
+__device__ __forceinline__ void pd_arrive(const int pz, int which) {
     __syncthreads();
-    if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(P.sync + which) : "memory");
+    if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(CP.sync + which) : "memory");
 }
-// all threads of the CTA call; sync = P.sync
-__device__ __forceinline__ void pd_wait_raw(unsigned long long *sync, int which, unsigned long long target) {
+// all threads of the CTA call
+__device__ __forceinline__ void pd_wait(const int pz, int which, unsigned long long target) {
     if (threadIdx.x == 0) {
+        unsigned long long *sync = CP.sync;
         const unsigned long long *c = sync + which;
         unsigned n = 0;
         while (pd_ld_acquire(c) < target) {
@@ -70,39 +94,32 @@ __device__ __forceinline__ void pd_wait_raw(unsigned long long *sync, int which,
     }
     __syncthreads();
 }
-__device__ __forceinline__ void pd_wait(const PdParams &P, int which, unsigned long long target) { pd_wait_raw(P.sync, which, target); }
-// dependency of a phase: counter index + cumulative target (+ optional timeline stamp written once the wait is over)
-struct PdDep {
-    unsigned long long *sync;
-    int which;
-    unsigned long long target;
-    unsigned long long *stamp; // nullptr or the slot of CTA 0
-};
-__device__ __forceinline__ void pd_dep_wait(const PdDep &d) {
-    pd_wait_raw(d.sync, d.which, d.target);
-    if (d.stamp && blockIdx.x == 0 && threadIdx.x == 0) *d.stamp = globaltimer_ns();
+__device__ __forceinline__ void pd_stamp(const int pz, int idx) {
+    if (CP.trace && blockIdx.x == 0 && threadIdx.x == 0) CP.trace[idx] = globaltimer_ns();
 }
 
 // ---- LL exchange ----------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void ll_store(uint4 *const *bufs, int world, int src_rank, int E, int row, float v, uint32_t tag) {
-    // half-line (8 bytes) of row `row` in the [src_rank] block of every rank's receive buffer
+// half-line (8 bytes {value, tag}) of row `row` in the [this rank] block of every rank's receive buffer
+template <int PH>
+__device__ __forceinline__ void ll_store(const int pz, int row, float v, uint32_t tag) {
+    const int world = CP.world;
 #pragma unroll 1
     for (int d = 0; d < world; d++) {
-        uint32_t *dst = (uint32_t *)bufs[d] + ((size_t)src_rank * E + row) * 2;
+        uint32_t *dst = (uint32_t *)(PH == PH_O ? CP.ll_o[d] : CP.ll_d[d]) + ((size_t)CP.rank * CP.E + row) * 2;
         asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(__float_as_uint(v)), "r"(tag) : "memory");
     }
 }
-__device__ __forceinline__ float ll_load(unsigned long long *sync, const uint4 *mine, int src_rank, int E, int row, uint32_t tag) {
-    const uint32_t *src = (const uint32_t *)mine + ((size_t)src_rank * E + row) * 2;
+__device__ __forceinline__ float ll_load(const int pz, const uint4 *mine, int src_rank, int row, uint32_t tag) {
+    const uint32_t *src = (const uint32_t *)mine + ((size_t)src_rank * CP.E + row) * 2;
     uint32_t v, t;
     unsigned n = 0;
     for (;;) {
         asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "l"(src) : "memory");
         if (t == tag) break;
         if ((++n & 0x3ff) == 0) {
-            if (pd_ld_volatile(sync + 1) != 0) break;
+            if (pd_ld_volatile(CP.sync + 1) != 0) break;
             if (n > PD_SPIN_PEER) {
-                sync[1] = 100 + (unsigned long long)src_rank;
+                CP.sync[1] = 100 + (unsigned long long)src_rank;
                 break;
             }
         }
@@ -112,28 +129,6 @@ __device__ __forceinline__ float ll_load(unsigned long long *sync, const uint4 *
 
 __device__ __forceinline__ int item_owner_pd(int i, int items, int nwarp) { return (int)((((long long)(i + 1)) * nwarp - 1) / items); }
 
-struct PdEpi {
-    // EPI_LL
-    uint4 *const *ll;
-    int world, rank, E;
-    uint32_t tag;
-};
-// weight / output segments of a phase as scalars (a runtime-indexed array would force the whole descriptor into local memory)
-struct PdSegs {
-    const uint8_t *w0, *w1, *w2;
-    const float *s0, *s1, *s2;
-    float *o0, *o1, *o2;
-    int r0, r1, nseg;
-    const float *residual;
-};
-__device__ __forceinline__ void pd_seg_lookup(const PdSegs &S, int row, int &seg, int &local) {
-    seg = 0, local = row;
-    if (S.nseg > 1 && local >= S.r0) {
-        local -= S.r0, seg = 1;
-        if (S.nseg > 2 && local >= S.r1) local -= S.r1, seg = 2;
-    }
-}
-
 __device__ __forceinline__ unsigned long long pd_pack_arg(float v, int idx) {
     if (!(v == v)) return 0ull; // NaN never wins (AbstractModel.java:465: 'v > maxv' is false)
     uint32_t b = __float_as_uint(v);
@@ -141,26 +136,69 @@ __device__ __forceinline__ unsigned long long pd_pack_arg(float v, int idx) {
     return ((unsigned long long)b << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)idx);
 }
 
-__device__ __forceinline__ void pd_stamp(const PdParams &P, int idx) {
-    if (P.trace && blockIdx.x == 0 && threadIdx.x == 0) P.trace[idx] = globaltimer_ns();
+// ---- phase descriptors straight from constant memory ---------------------------------------------------------------------
+template <int PH>
+__device__ __forceinline__ int ph_K(const int pz) { return PH == PH_O ? CP.attn_seg : (PH == PH_DOWN ? CP.H : CP.E); }
+template <int PH>
+__device__ __forceinline__ int ph_rows(const int pz) { return PH == PH_QKV ? CP.attn_seg + 2 * CP.kv_seg : (PH == PH_GU ? CP.H : CP.E); }
+// concatenated row -> (segment, row inside the segment); only QKV has more than one segment (gate/up pairs use wr)
+template <int PH>
+__device__ __forceinline__ void ph_seg(const int pz, int row, int &seg, int &local) {
+    seg = 0, local = row;
+    if (PH == PH_QKV && local >= CP.attn_seg) {
+        local -= CP.attn_seg, seg = 1;
+        if (local >= CP.kv_seg) local -= CP.kv_seg, seg = 2;
+    }
+}
+template <int PH>
+__device__ __forceinline__ void ph_weights(int L, int seg, const uint8_t *&w, const float *&s) {
+    const PdLayer &l = c_pd.layers[L];
+    const int slot = PH == PH_QKV ? PW_Q + seg : (PH == PH_O ? PW_O : (PH == PH_GU ? PW_GATE + seg : PW_DOWN));
+    w = l.w[slot], s = l.s[slot];
+}
+template <int PH>
+__device__ __forceinline__ float *ph_out(const int pz, int seg) {
+    return PH == PH_QKV ? (seg == 0 ? CP.q : (seg == 1 ? CP.k : CP.v)) : (PH == PH_O ? CP.xb : (PH == PH_GU ? CP.h : CP.x));
+}
+
+// The ring registers are only ever written under conditions (rows left, block inside the row).  With several phases inlined into
+// one kernel a conditionally-defined register is live from the kernel entry to its last use: every phase's ring then overlaps all
+// earlier phases and the allocator spills the rings to local memory (LDG -> STL -> LDL, 2x slower phases).  A definite
+// definition at the start of the phase ends that.
+template <int WDT, int CH, int NBUF>
+__device__ __forceinline__ void pd_ring_clear(WBuf<WDT, CH> (&buf)[NBUF]) {
+#pragma unroll
+    for (int b = 0; b < NBUF; b++) {
+#pragma unroll
+        for (int j = 0; j < CH * (WDT == JL_I8 ? 2 : 1); j++) buf[b].q[j] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int j = 0; j < CH; j++) buf[b].s[j] = 0.0f;
+    }
 }
 
 // ---- one quantised GEMV phase (M = 1, Q8 activations) -------------------------------------------------------------------
 // Work split as in gemv_decode_kernel (jl_gemv.cu): output rows are dealt to the CTAs, inside a CTA the (row, weight-row,
-// chunk) items to the warps; LONG rows (K > 4096) are split at chunk granularity with per-warp partial sums combined in
-// chunk order.  `dep()` is called by all threads after the ring has been primed and before the activations are touched.
+// chunk) items to the warps; LONG rows (longer than one register chunk) are split at chunk granularity with per-warp partial
+// sums combined in chunk order.  The ring is primed BEFORE the dependency counter is polled.
 // __noinline__: every phase gets its own register allocation (inlined into one kernel the ring buffers spilled).
-template <int WDT, int EPI, int PRO, bool LONG>
-__device__ __noinline__ void pd_gemv(const GemvParams &p, const PdSegs &S, const PdEpi &X, unsigned char *smem, const PdDep dep) {
+template <int WDT, int PH, int EPI, bool LONG>
+__device__ PD_PHASE_FN void pd_gemv(const int, const int L, const uint32_t tag, const int dep_which, const unsigned long long dep_target,
+                                     const int stamp_idx, unsigned char *smem) {
+    PD_OPAQUE_ZERO(pz);
     constexpr int NT = PD_NT, NWARP = PD_NWARP, CH = PD_CH(WDT), NBUF = PD_NBUF;
-    constexpr bool NORM = PRO == PRO_RMSNORM_QUANT;
+    constexpr bool NORM = PH == PH_QKV || PH == PH_GU;
     constexpr int NW = (EPI == EPI_SILU_MUL) ? 2 : 1; // weight rows per output row
     constexpr int WB = (WDT == JL_Q4) ? 16 : 32;      // weight bytes per 32-element block
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nblk = p.K / 32;
+    // The phases are inlined into one loop over the layers and all their index arithmetic (row ranges, item ranges, ...) is
+    // loop-invariant: hoisted out of the layer loop it stayed live across every phase (~60 registers) and the weight ring
+    // spilled to local memory.  An opaque copy of the thread / CTA ids keeps each phase's bookkeeping inside the phase.
+    int tid = threadIdx.x, cta_id = blockIdx.x, ncta = gridDim.x;
+    asm volatile("" : "+r"(tid), "+r"(cta_id), "+r"(ncta));
+    const int lane = tid & 31, warp = tid >> 5;
+    const int nblk = ph_K<PH>(pz) / 32;
     const int nchunks = LONG ? (nblk + 32 * CH - 1) / (32 * CH) : 1;
-    const int R0 = (int)(((long long)p.total_rows * blockIdx.x) / gridDim.x);
-    const int R1 = (int)(((long long)p.total_rows * (blockIdx.x + 1)) / gridDim.x);
+    const int R0 = (int)(((long long)ph_rows<PH>(pz) * cta_id) / ncta);
+    const int R1 = (int)(((long long)ph_rows<PH>(pz) * (cta_id + 1)) / ncta);
     const int nrows = R1 - R0;
     const int per_row = NW * nchunks;
     const int items = nrows * per_row;
@@ -175,18 +213,24 @@ __device__ __noinline__ void pd_gemv(const GemvParams &p, const PdSegs &S, const
     struct It {
         int r, wr, c;
     };
-    const size_t row_blocks = (size_t)nblk;
     auto row_ptrs = [&](const It &it, const uint8_t *&wrow, const float *&srow) {
         int seg, local;
         if (EPI == EPI_SILU_MUL) {
             seg = it.wr;
             local = R0 + it.r;
         } else {
-            pd_seg_lookup(S, R0 + it.r, seg, local);
+            ph_seg<PH>(pz, R0 + it.r, seg, local);
         }
-        const size_t blk = (size_t)local * row_blocks;
-        wrow = (seg == 0 ? S.w0 : (seg == 1 ? S.w1 : S.w2)) + blk * WB;
-        srow = (seg == 0 ? S.s0 : (seg == 1 ? S.s1 : S.s2)) + blk;
+        const uint8_t *w;
+        const float *s;
+#ifdef PD_X_FIXEDW
+        w = CP.lm_w, s = CP.lm_s;
+#else
+        ph_weights<PH>(L, seg, w, s);
+#endif
+        const size_t blk = (size_t)local * (size_t)nblk;
+        wrow = w + blk * WB;
+        srow = s + blk;
     };
     auto advance = [&](It &it) {
         if (!LONG || ++it.c == nchunks) {
@@ -206,11 +250,11 @@ __device__ __noinline__ void pd_gemv(const GemvParams &p, const PdSegs &S, const
         ld = cur;
     }
     WBuf<WDT, CH> buf[NBUF];
+    pd_ring_clear<WDT, CH, NBUF>(buf);
     const uint8_t *wrow;
     const float *srow;
     const unsigned long long pol = l2_evict_first_policy();
     int ci = i0, li = i0;
-    // the ring is primed before the dependency is polled: the weight stream does not depend on the previous phase
 #pragma unroll
     for (int b = 0; b < NBUF - 1; b++) {
         if (li < i1) {
@@ -220,8 +264,17 @@ __device__ __noinline__ void pd_gemv(const GemvParams &p, const PdSegs &S, const
             li++;
         }
     }
-    pd_dep_wait(dep);
+#ifndef PD_X_NOWAIT
+    pd_wait(pz, dep_which, dep_target);
+    pd_stamp(pz, stamp_idx);
+#endif
     {
+        GemvParams p; // only the staging fields; dead after the prologue
+        p.a = PH == PH_QKV ? CP.x : (PH == PH_O ? CP.att : (PH == PH_GU ? CP.xb : CP.h));
+        p.a_col_off = 0, p.K = ph_K<PH>(pz), p.lda = p.K;
+        p.norm_w = PH == PH_QKV ? c_pd.layers[L].attn_norm : c_pd.layers[L].ffn_norm;
+        p.norm_w_dtype = PH == PH_QKV ? c_pd.layers[L].attn_norm_dt : c_pd.layers[L].ffn_norm_dt;
+        p.norm_adj = 0.0f, p.norm_eps = CP.eps, p.norm_E = CP.E, p.norm_inv_E = 1.0 / (double)CP.E;
         StageRegs<NORM, LONG && !NORM> sr;
         stage_q8_issue<NORM, LONG && !NORM, NT>(p, sr);
         stage_q8_finish<NORM, LONG && !NORM, NT>(p, sr, smem, nblk);
@@ -231,14 +284,14 @@ __device__ __noinline__ void pd_gemv(const GemvParams &p, const PdSegs &S, const
     float acc[1] = {0.0f};
     float park0 = 0.0f, park1 = 0.0f; // value (or gate), up
     int nparked = 0, park_row0 = R0 + cur.r;
-    auto store_row = [&](int row, float v0, float v1) { // row = index in the concatenated row space of the launch
+    auto store_row = [&](int row, float v0, float v1) { // row = index in the concatenated row space of the phase
         int seg = 0, local = row;
-        if (EPI != EPI_SILU_MUL) pd_seg_lookup(S, row, seg, local);
+        if (EPI != EPI_SILU_MUL) ph_seg<PH>(pz, row, seg, local);
         float v = NW == 2 ? v1 : v0;
-        if (EPI == EPI_ADD_RESIDUAL) v = __fadd_rn(v, __ldcg(S.residual + local));
+        if (EPI == EPI_ADD_RESIDUAL) v = __fadd_rn(v, __ldcg((PH == PH_O ? CP.x : CP.xb) + local));
         if (EPI == EPI_SILU_MUL) v = __fmul_rn(silu_ref(v0), v);
-        if (EPI == EPI_LL) ll_store(X.ll, X.world, X.rank, X.E, local, v, X.tag);
-        else (seg == 0 ? S.o0 : (seg == 1 ? S.o1 : S.o2))[local] = v;
+        if (EPI == EPI_LL) ll_store<PH>(pz, local, v, tag);
+        else ph_out<PH>(pz, seg)[local] = v;
     };
     auto flush = [&]() {
         if (lane < nparked) store_row(park_row0 + lane, park0, park1);
@@ -297,36 +350,42 @@ __device__ __noinline__ void pd_gemv(const GemvParams &p, const PdSegs &S, const
 
 // ---- lm_head: F32 activations (RMSNorm, not re-quantised: AbstractModel.java:444-449) x quantised rows + running arg-max --
 template <int WDT>
-__device__ __noinline__ void pd_lm_head(const PdParams &P, unsigned char *smem, const PdDep dep, unsigned long long &cta_best) {
+__device__ PD_PHASE_FN unsigned long long pd_lm_head(const int, const int dep_which, const unsigned long long dep_target, const int stamp_idx,
+                                                     const int want_logits, unsigned char *smem) {
+    PD_OPAQUE_ZERO(pz);
     constexpr int NT = PD_NT, NWARP = PD_NWARP, CH = PD_CH(WDT), NBUF = PD_NBUF;
     constexpr int WB = (WDT == JL_Q4) ? 16 : 32;
     __shared__ double red[NWARP];
     __shared__ unsigned long long wbest[NWARP];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int K = P.E, nblk = K / 32;
-    const int R0 = (int)(((long long)P.vocab_rows * blockIdx.x) / gridDim.x);
-    const int R1 = (int)(((long long)P.vocab_rows * (blockIdx.x + 1)) / gridDim.x);
+    int tid = threadIdx.x, cta_id = blockIdx.x, ncta = gridDim.x;
+    asm volatile("" : "+r"(tid), "+r"(cta_id), "+r"(ncta)); // see pd_gemv
+    const int lane = tid & 31, warp = tid >> 5;
+    const int K = CP.E, nblk = K / 32;
+    const int R0 = (int)(((long long)CP.vocab_rows * cta_id) / ncta);
+    const int R1 = (int)(((long long)CP.vocab_rows * (cta_id + 1)) / ncta);
     const int nrows = R1 - R0;
     const int r0 = R0 + (int)(((long long)nrows * warp) / NWARP), r1 = R0 + (int)(((long long)nrows * (warp + 1)) / NWARP);
     const int nchunks = (nblk + 32 * CH - 1) / (32 * CH);
     WBuf<WDT, CH> buf[NBUF];
+    pd_ring_clear<WDT, CH, NBUF>(buf);
     const unsigned long long pol = l2_evict_first_policy();
     int lr = r0, lc = 0, cr = r0, cc = 0;
     auto issue = [&](WBuf<WDT, CH> &b) {
         const size_t blk = (size_t)lr * nblk;
-        load_chunk<WDT, CH>(b, P.lm_w + blk * WB, P.lm_s + blk, lc * 32 * CH, nblk, lane, pol);
+        load_chunk<WDT, CH>(b, CP.lm_w + blk * WB, CP.lm_s + blk, lc * 32 * CH, nblk, lane, pol);
         if (++lc == nchunks) lc = 0, ++lr;
     };
 #pragma unroll
     for (int b = 0; b < NBUF - 1; b++)
         if (lr < r1) issue(buf[b]);
-    pd_dep_wait(dep);
+    pd_wait(pz, dep_which, dep_target);
+    pd_stamp(pz, stamp_idx);
     // final RMSNorm into the [c4(8)][blk][4] float layout of compute_chunk<.., ACTQ8 = false>
     {
         float4 *af4 = (float4 *)smem;
         double ss = 0.0;
         for (int i4 = tid; i4 < K / 4; i4 += NT) {
-            const float4 v = __ldcg((const float4 *)(P.x + i4 * 4));
+            const float4 v = __ldcg((const float4 *)(CP.x + i4 * 4));
             ss += (double)__fmul_rn(v.x, v.x);
             ss += (double)__fmul_rn(v.y, v.y);
             ss += (double)__fmul_rn(v.z, v.z);
@@ -338,16 +397,16 @@ __device__ __noinline__ void pd_lm_head(const PdParams &P, unsigned char *smem, 
         double t = 0.0;
 #pragma unroll
         for (int w = 0; w < NWARP; w++) t += red[w];
-        const float rsf = rms_scale(t, 1.0 / (double)P.E, P.eps);
+        const float rsf = rms_scale(t, 1.0 / (double)CP.E, CP.eps);
         for (int i4 = tid; i4 < K / 4; i4 += NT) {
-            const float4 v = __ldcg((const float4 *)(P.x + i4 * 4));
+            const float4 v = __ldcg((const float4 *)(CP.x + i4 * 4));
             float w[4];
-            if (P.out_norm_dt == JL_BF16) {
-                const uint2 u = __ldg((const uint2 *)((const uint16_t *)P.out_norm + i4 * 4));
+            if (CP.out_norm_dt == JL_BF16) {
+                const uint2 u = __ldg((const uint2 *)((const uint16_t *)CP.out_norm + i4 * 4));
                 w[0] = __uint_as_float(u.x << 16), w[1] = __uint_as_float(u.x & 0xffff0000u);
                 w[2] = __uint_as_float(u.y << 16), w[3] = __uint_as_float(u.y & 0xffff0000u);
             } else {
-                const float4 f = __ldg((const float4 *)((const float *)P.out_norm + i4 * 4));
+                const float4 f = __ldg((const float4 *)((const float *)CP.out_norm + i4 * 4));
                 w[0] = f.x, w[1] = f.y, w[2] = f.z, w[3] = f.w;
             }
             const int b = i4 >> 3, c4 = i4 & 7;
@@ -368,12 +427,12 @@ __device__ __noinline__ void pd_lm_head(const PdParams &P, unsigned char *smem, 
                 if (++cc == nchunks) {
                     const float v = warp_sum(acc[0]);
                     acc[0] = 0.0f;
-                    const int grow = P.vocab0 + cr;
+                    const int grow = CP.vocab0 + cr;
                     if (lane == 0) {
-                        P.logits[grow] = v;
-                        if (P.want_logits)
-                            for (int d = 0; d < P.world; d++)
-                                if (d != P.rank) P.logits_peer[d][grow] = v;
+                        CP.logits[grow] = v;
+                        if (want_logits)
+                            for (int d = 0; d < CP.world; d++)
+                                if (d != CP.rank) CP.logits_peer[d][grow] = v;
                     }
                     if (v > best_v) best_v = v, best_i = grow; // rows ascend: strict '>' keeps the lowest index
                     cc = 0, ++cr;
@@ -383,35 +442,40 @@ __device__ __noinline__ void pd_lm_head(const PdParams &P, unsigned char *smem, 
     }
     if (lane == 0) wbest[warp] = best_i == 0x7fffffff ? 0ull : pd_pack_arg(best_v, best_i);
     __syncthreads();
-    if (tid == 0) {
-        unsigned long long b = 0ull;
+    unsigned long long b = 0ull;
+    if (tid == 0)
         for (int w = 0; w < NWARP; w++) b = wbest[w] > b ? wbest[w] : b;
-        cta_best = b;
-    }
+    return b; // valid in thread 0
 }
 
-__device__ __forceinline__ float pd_embed_value(const PdParams &P, size_t tok, int c) {
+__device__ __forceinline__ float pd_embed_value(const int pz, size_t tok, int c) {
     // LlamaModel.java:68-100 (Q4 / I8 rows are read through get(): Q4ByteBufferTensor.java:179-197)
-    if (P.embed_dt == JL_F32) return ((const float *)P.embed_w)[tok * P.E + c];
-    if (P.embed_dt == JL_BF16) return bf16_bits_to_f32(((const uint16_t *)P.embed_w)[tok * P.E + c]);
-    if (P.embed_dt == JL_Q4) {
+    const int E = CP.E;
+    if (CP.embed_dt == JL_F32) return ((const float *)CP.embed_w)[tok * E + c];
+    if (CP.embed_dt == JL_BF16) return bf16_bits_to_f32(((const uint16_t *)CP.embed_w)[tok * E + c]);
+    if (CP.embed_dt == JL_Q4) {
         const int blk = c / 32, in = c % 32;
-        const uint8_t byte = ((const uint8_t *)P.embed_w)[(tok * P.E + blk * 32) / 2 + (in & 15)];
+        const uint8_t byte = ((const uint8_t *)CP.embed_w)[(tok * E + blk * 32) / 2 + (in & 15)];
         const int nib = in < 16 ? (byte & 0x0F) : (byte >> 4);
-        return __fmul_rn((float)(nib - 8), P.embed_s[tok * (P.E / 32) + blk]);
+        return __fmul_rn((float)(nib - 8), CP.embed_s[tok * (E / 32) + blk]);
     }
-    return __fmul_rn((float)((const int8_t *)P.embed_w)[tok * P.E + c], P.embed_s[tok * (P.E / 32) + c / 32]);
+    return __fmul_rn((float)((const int8_t *)CP.embed_w)[tok * E + c], CP.embed_s[tok * (E / 32) + c / 32]);
 }
 
 // reduce the LL partials of this CTA's rows in rank order, add the residual, store the new hidden rows (local global)
-__device__ __noinline__ void pd_ll_reduce(const PdParams &P, const uint4 *mine, uint32_t tag, const float *residual, float *out,
-                                             float *scratch /* smem [rows][world] */) {
+template <int PH>
+__device__ PD_PHASE_FN void pd_ll_reduce(const int, uint32_t tag, float *scratch /* smem [rows][world] */) {
+    PD_OPAQUE_ZERO(pz);
     const int tid = threadIdx.x;
-    const int R0 = (int)(((long long)P.E * blockIdx.x) / gridDim.x), R1 = (int)(((long long)P.E * (blockIdx.x + 1)) / gridDim.x);
-    const int nrows = R1 - R0, W = P.world;
+    const int E = CP.E, W = CP.world;
+    const int R0 = (int)(((long long)E * blockIdx.x) / gridDim.x), R1 = (int)(((long long)E * (blockIdx.x + 1)) / gridDim.x);
+    const int nrows = R1 - R0;
+    const uint4 *mine = PH == PH_O ? CP.ll_o[CP.rank] : CP.ll_d[CP.rank];
+    const float *residual = PH == PH_O ? CP.x : CP.xb;
+    float *out = PH == PH_O ? CP.xb : CP.x;
     for (int t = tid; t < nrows * W; t += PD_NT) {
         const int r = t / W, src = t - r * W;
-        scratch[t] = ll_load(P.sync, mine, src, P.E, R0 + r, tag);
+        scratch[t] = ll_load(pz, mine, src, R0 + r, tag);
     }
     __syncthreads();
     for (int r = tid; r < nrows; r += PD_NT) {
@@ -422,146 +486,125 @@ __device__ __noinline__ void pd_ll_reduce(const PdParams &P, const uint4 *mine, 
 }
 
 template <int HS>
-__device__ __noinline__ void pd_attention(const AttnTask &at, int layer, int kvh, int split, unsigned char *smem) {
-    attention_task<HS, PD_NT, -1>(at, layer, 0, kvh, split, smem);
+__device__ PD_PHASE_FN void pd_attention(const int, const int layer, const int kvh, const int split, const int splits, const bool merge, unsigned char *smem) {
+    PD_OPAQUE_ZERO(pz);
+    AttnTask at;
+    at.heads = CP.heads, at.kv_heads = CP.kv_heads, at.head_size = CP.head_size, at.attn_seg = CP.attn_seg, at.kv_seg = CP.kv_seg;
+    at.kv_head0_global = CP.kv_head0_global, at.splits = splits, at.attn_scale = CP.attn_scale;
+    at.q = CP.q, at.k = CP.k, at.v = CP.v, at.att = CP.att, at.attn_ws = CP.attn_ws, at.rope = CP.rope, at.kv = CP.kv;
+    at.sessions = CP.sessions, at.positions = CP.positions;
+    if (merge) attention_merge<HS, PD_NT>(at, 0, kvh, smem);
+    else attention_task<HS, PD_NT, -1>(at, layer, 0, kvh, split, smem);
 }
 
 template <int WDT, int HS>
-__global__ void __launch_bounds__(PD_NT, 1) pdecode_kernel(const PdParams P) {
+__global__ void __launch_bounds__(PD_NT, 1) pdecode_kernel(const int splits, const int resident, const int want_logits) {
+    PD_OPAQUE_ZERO(pz);
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ int s_last;
     const int tid = threadIdx.x;
     const int G = gridDim.x, cta = blockIdx.x;
-    const unsigned long long epoch = pd_ld_volatile(P.sync); // tokens decoded by this model so far
+    const unsigned long long epoch = pd_ld_volatile(CP.sync); // tokens decoded by this model so far
     const unsigned long long uG = (unsigned long long)G;
-    const bool tp = P.world > 1;
-    const bool lng_E = P.E > 32 * 32 * PD_CH(WDT), lng_A = P.attn_seg > 32 * 32 * PD_CH(WDT); // rows longer than one register chunk
-    auto stamp_slot = [&](int idx) -> unsigned long long * { return P.trace ? P.trace + idx : nullptr; };
-    pd_stamp(P, 0);
+    const bool tp = CP.world > 1;
+    const int layers = CP.layers;
+    // rows longer than one register chunk run in the split-row form
+    const bool lng_E = CP.E > 32 * 32 * PD_CH(WDT), lng_A = CP.attn_seg > 32 * 32 * PD_CH(WDT), lng_H = CP.H > 32 * 32 * PD_CH(WDT);
+    pd_stamp(pz, 0);
 
     // ---- embedding row (columns split over the grid) ----
     {
-        const int c_a = (int)(((long long)P.E * cta) / G), c_b = (int)(((long long)P.E * (cta + 1)) / G);
-        const size_t tok = (size_t)P.tokens[0];
-        for (int c = c_a + tid; c < c_b; c += PD_NT) P.x[c] = pd_embed_value(P, tok, c);
-        pd_arrive(P, PC_EMBED);
+        const int E = CP.E;
+        const int c_a = (int)(((long long)E * cta) / G), c_b = (int)(((long long)E * (cta + 1)) / G);
+        const size_t tok = (size_t)CP.tokens[0];
+        for (int c = c_a + tid; c < c_b; c += PD_NT) CP.x[c] = pd_embed_value(pz, tok, c);
+        pd_arrive(pz, PC_EMBED);
     }
-    AttnTask at;
-    at.heads = P.heads, at.kv_heads = P.kv_heads, at.head_size = P.head_size, at.attn_seg = P.attn_seg, at.kv_seg = P.kv_seg;
-    at.kv_head0_global = P.kv_head0_global, at.splits = P.splits, at.attn_scale = P.attn_scale;
-    at.q = P.q, at.k = P.k, at.v = P.v, at.att = P.att, at.attn_ws = P.attn_ws, at.rope = P.rope, at.kv = P.kv;
-    at.sessions = P.sessions, at.positions = P.positions;
-    const int ntasks = P.kv_heads * P.splits;
-    PdEpi X;
-    X.world = P.world, X.rank = P.rank, X.E = P.E, X.ll = nullptr, X.tag = 0;
+    const int ntasks = CP.kv_heads * splits;
 
-    for (int L = 0; L < P.layers; L++) {
-        const PdLayer &lw = P.lw[L];
-        const unsigned long long use = epoch * (unsigned long long)P.layers + (unsigned long long)L + 1; // 1-based use count
+    for (int L = 0; L < layers; L++) {
+        PD_OPAQUE_ZERO(pz); // per-iteration: see the note at c_pd
+        const unsigned long long use = epoch * (unsigned long long)layers + (unsigned long long)L + 1; // 1-based use count
         const uint32_t tag_o = (uint32_t)(use * 2), tag_d = (uint32_t)(use * 2 + 1);
         // ---- QKV: RMSNorm(x) -> Q8 -> q | k | v ----
         {
-            GemvParams p = {};
-            PdSegs S = {lw.w[PW_Q], lw.w[PW_K], lw.w[PW_V], lw.s[PW_Q], lw.s[PW_K], lw.s[PW_V], P.q, P.k, P.v, P.attn_seg, P.kv_seg, 3, nullptr};
-            p.K = P.E, p.a = P.x, p.lda = P.E;
-            p.norm_w = lw.attn_norm, p.norm_w_dtype = lw.attn_norm_dt, p.norm_eps = P.eps, p.norm_E = P.E, p.norm_inv_E = 1.0 / (double)P.E;
-            p.total_rows = P.attn_seg + 2 * P.kv_seg;
-            const PdDep dep = {P.sync, L == 0 ? PC_EMBED : PC_DOWN, L == 0 ? (epoch + 1) * uG : (use - 1) * uG, stamp_slot(1 + L * 8 + 0)};
-            if (lng_E) pd_gemv<WDT, EPI_STORE, PRO_RMSNORM_QUANT, true>(p, S, X, smem, dep);
-            else pd_gemv<WDT, EPI_STORE, PRO_RMSNORM_QUANT, false>(p, S, X, smem, dep);
-            pd_arrive(P, PC_QKV);
-            pd_stamp(P, 1 + L * 8 + 1);
+            const int dw = L == 0 ? PC_EMBED : PC_DOWN;
+            const unsigned long long dt = L == 0 ? (epoch + 1) * uG : (use - 1) * uG;
+            if (lng_E) pd_gemv<WDT, PH_QKV, EPI_STORE, true>(pz, L, 0u, dw, dt, 1 + L * 8 + 0, smem);
+            else pd_gemv<WDT, PH_QKV, EPI_STORE, false>(pz, L, 0u, dw, dt, 1 + L * 8 + 0, smem);
+            pd_arrive(pz, PC_QKV);
+            pd_stamp(pz, 1 + L * 8 + 1);
         }
         // ---- attention tasks on the first CTAs (RoPE, KV append, scores, softmax, P.V) ----
         if (cta < ntasks) {
-            pd_wait(P, PC_QKV, use * uG);
-            const int split = cta % P.splits, kvh = cta / P.splits;
-            pd_attention<HS>(at, L, kvh, split, smem);
+            pd_wait(pz, PC_QKV, use * uG);
+            const int split = cta % splits, kvh = cta / splits;
+            pd_attention<HS>(pz, L, kvh, split, splits, false, smem);
             bool signal = true;
-            if (P.splits > 1) {
+            if (splits > 1) {
                 __syncthreads();
                 if (tid == 0) {
                     __threadfence();
-                    unsigned *c = &P.att_done[kvh];
+                    unsigned *c = &CP.att_done[kvh];
                     const unsigned old = atomicAdd(c, 1u);
-                    s_last = (old == (unsigned)P.splits - 1);
+                    s_last = (old == (unsigned)splits - 1);
                     if (s_last) *c = 0;
                     __threadfence();
                 }
                 __syncthreads();
                 signal = s_last != 0;
-                if (signal) attention_merge<HS, PD_NT>(at, 0, kvh, smem);
+                if (signal) pd_attention<HS>(pz, L, kvh, split, splits, true, smem);
             }
             __syncthreads();
-            if (signal && tid == 0) asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(P.sync + PC_ATT) : "memory");
-            pd_stamp(P, 1 + L * 8 + 2);
+            if (signal && tid == 0) asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(CP.sync + PC_ATT) : "memory");
+            pd_stamp(pz, 1 + L * 8 + 2);
         }
         // ---- o_proj: Q8(att) -> x + o (single rank) or LL partials -> rank-ordered reduce + residual (tensor parallel) ----
         {
-            GemvParams p = {};
-            PdSegs S = {lw.w[PW_O], nullptr, nullptr, lw.s[PW_O], nullptr, nullptr, P.xb, nullptr, nullptr, P.E, 0, 1, P.x};
-            p.K = P.attn_seg, p.a = P.att, p.lda = P.attn_seg, p.total_rows = P.E;
-            const PdDep dep = {P.sync, PC_ATT, use * (unsigned long long)P.kv_heads, stamp_slot(1 + L * 8 + 3)};
+            const unsigned long long dt = use * (unsigned long long)CP.kv_heads;
             if (tp) {
-                X.ll = P.ll_o, X.tag = tag_o;
-                if (lng_A) pd_gemv<WDT, EPI_LL, PRO_F32_QUANT, true>(p, S, X, smem, dep);
-                else pd_gemv<WDT, EPI_LL, PRO_F32_QUANT, false>(p, S, X, smem, dep);
+                if (lng_A) pd_gemv<WDT, PH_O, EPI_LL, true>(pz, L, tag_o, PC_ATT, dt, 1 + L * 8 + 3, smem);
+                else pd_gemv<WDT, PH_O, EPI_LL, false>(pz, L, tag_o, PC_ATT, dt, 1 + L * 8 + 3, smem);
                 __syncthreads();
-                pd_ll_reduce(P, P.ll_o[P.rank], tag_o, P.x, P.xb, (float *)smem);
+                pd_ll_reduce<PH_O>(pz, tag_o, (float *)smem);
             } else {
-                if (lng_A) pd_gemv<WDT, EPI_ADD_RESIDUAL, PRO_F32_QUANT, true>(p, S, X, smem, dep);
-                else pd_gemv<WDT, EPI_ADD_RESIDUAL, PRO_F32_QUANT, false>(p, S, X, smem, dep);
+                if (lng_A) pd_gemv<WDT, PH_O, EPI_ADD_RESIDUAL, true>(pz, L, 0u, PC_ATT, dt, 1 + L * 8 + 3, smem);
+                else pd_gemv<WDT, PH_O, EPI_ADD_RESIDUAL, false>(pz, L, 0u, PC_ATT, dt, 1 + L * 8 + 3, smem);
             }
-            pd_arrive(P, PC_O);
-            pd_stamp(P, 1 + L * 8 + 4);
+            pd_arrive(pz, PC_O);
+            pd_stamp(pz, 1 + L * 8 + 4);
         }
         // ---- gate / up: RMSNorm(xb) -> Q8 -> silu(gate) * up ----
         {
-            GemvParams p = {};
-            PdSegs S = {lw.w[PW_GATE], lw.w[PW_UP], nullptr, lw.s[PW_GATE], lw.s[PW_UP], nullptr, P.h, P.h, nullptr, P.H, P.H, 2, nullptr};
-            p.K = P.E, p.a = P.xb, p.lda = P.E;
-            p.norm_w = lw.ffn_norm, p.norm_w_dtype = lw.ffn_norm_dt, p.norm_eps = P.eps, p.norm_E = P.E, p.norm_inv_E = 1.0 / (double)P.E;
-            p.total_rows = P.H;
-            const PdDep dep = {P.sync, PC_O, use * uG, stamp_slot(1 + L * 8 + 5)};
-            if (lng_E) pd_gemv<WDT, EPI_SILU_MUL, PRO_RMSNORM_QUANT, true>(p, S, X, smem, dep);
-            else pd_gemv<WDT, EPI_SILU_MUL, PRO_RMSNORM_QUANT, false>(p, S, X, smem, dep);
-            pd_arrive(P, PC_GU);
-            pd_stamp(P, 1 + L * 8 + 6);
+            if (lng_E) pd_gemv<WDT, PH_GU, EPI_SILU_MUL, true>(pz, L, 0u, PC_O, use * uG, 1 + L * 8 + 5, smem);
+            else pd_gemv<WDT, PH_GU, EPI_SILU_MUL, false>(pz, L, 0u, PC_O, use * uG, 1 + L * 8 + 5, smem);
+            pd_arrive(pz, PC_GU);
+            pd_stamp(pz, 1 + L * 8 + 6);
         }
         // ---- down_proj: Q8(h) -> xb + down ----
         {
-            GemvParams p = {};
-            PdSegs S = {lw.w[PW_DOWN], nullptr, nullptr, lw.s[PW_DOWN], nullptr, nullptr, P.x, nullptr, nullptr, P.E, 0, 1, P.xb};
-            p.K = P.H, p.a = P.h, p.lda = P.H, p.total_rows = P.E;
-            const PdDep dep = {P.sync, PC_GU, use * uG, stamp_slot(1 + L * 8 + 7)};
-            const bool lng = P.H > 32 * 32 * PD_CH(WDT);
             if (tp) {
-                X.ll = P.ll_d, X.tag = tag_d;
-                if (lng) pd_gemv<WDT, EPI_LL, PRO_F32_QUANT, true>(p, S, X, smem, dep);
-                else pd_gemv<WDT, EPI_LL, PRO_F32_QUANT, false>(p, S, X, smem, dep);
+                if (lng_H) pd_gemv<WDT, PH_DOWN, EPI_LL, true>(pz, L, tag_d, PC_GU, use * uG, 1 + L * 8 + 7, smem);
+                else pd_gemv<WDT, PH_DOWN, EPI_LL, false>(pz, L, tag_d, PC_GU, use * uG, 1 + L * 8 + 7, smem);
                 __syncthreads();
-                pd_ll_reduce(P, P.ll_d[P.rank], tag_d, P.xb, P.x, (float *)smem);
+                pd_ll_reduce<PH_DOWN>(pz, tag_d, (float *)smem);
             } else {
-                if (lng) pd_gemv<WDT, EPI_ADD_RESIDUAL, PRO_F32_QUANT, true>(p, S, X, smem, dep);
-                else pd_gemv<WDT, EPI_ADD_RESIDUAL, PRO_F32_QUANT, false>(p, S, X, smem, dep);
+                if (lng_H) pd_gemv<WDT, PH_DOWN, EPI_ADD_RESIDUAL, true>(pz, L, 0u, PC_GU, use * uG, 1 + L * 8 + 7, smem);
+                else pd_gemv<WDT, PH_DOWN, EPI_ADD_RESIDUAL, false>(pz, L, 0u, PC_GU, use * uG, 1 + L * 8 + 7, smem);
             }
-            pd_arrive(P, PC_DOWN);
+            pd_arrive(pz, PC_DOWN);
         }
     }
     // ---- final norm + lm_head + arg-max ----
-    unsigned long long cta_best = 0ull;
-    {
-        const PdDep dep = {P.sync, PC_DOWN, (epoch + 1) * (unsigned long long)P.layers * uG, stamp_slot(1 + P.layers * 8 + 0)};
-        pd_lm_head<WDT>(P, smem, dep, cta_best);
-    }
-    if (tid == 0) P.argmax_slots[cta] = cta_best;
-    pd_arrive(P, PC_LM);
+    const unsigned long long cta_best = pd_lm_head<WDT>(pz, PC_DOWN, (epoch + 1) * (unsigned long long)layers * uG, 1 + layers * 8 + 0, want_logits, smem);
+    if (tid == 0) CP.argmax_slots[cta] = cta_best;
+    pd_arrive(pz, PC_LM);
     if (cta == 0) {
-        pd_wait(P, PC_LM, (epoch + 1) * uG);
+        pd_wait(pz, PC_LM, (epoch + 1) * uG);
         if (tid < 32) {
             unsigned long long b = 0ull;
             for (int i = tid; i < G; i += 32) {
-                const unsigned long long c = __ldcg(&P.argmax_slots[i]);
+                const unsigned long long c = __ldcg(&CP.argmax_slots[i]);
                 b = c > b ? c : b;
             }
 #pragma unroll
@@ -572,24 +615,24 @@ __global__ void __launch_bounds__(PD_NT, 1) pdecode_kernel(const PdParams P) {
             if (tp) {
                 // exchange the per-rank candidates (lm_head is sharded by vocabulary rows): LL line {lo, tag, hi, tag}
                 const uint32_t tag = (uint32_t)(epoch + 1);
-                if (tid < P.world) {
-                    uint4 line = make_uint4((uint32_t)b, tag, (uint32_t)(b >> 32), tag);
-                    uint4 *dst = P.ll_a[tid] + P.rank;
-                    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(line.x), "r"(line.y), "r"(line.z), "r"(line.w)
+                const int world = CP.world, rank = CP.rank;
+                if (tid < world) {
+                    uint4 *dst = CP.ll_a[tid] + rank;
+                    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"((uint32_t)b), "r"(tag), "r"((uint32_t)(b >> 32)), "r"(tag)
                                  : "memory");
                 }
                 unsigned long long c = 0ull;
-                if (tid < P.world) {
-                    const uint4 *src = P.ll_a[P.rank] + tid;
+                if (tid < world) {
+                    const uint4 *src = CP.ll_a[rank] + tid;
                     uint4 v;
                     unsigned n = 0;
                     for (;;) {
                         asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src) : "memory");
                         if (v.y == tag && v.w == tag) break;
                         if ((++n & 0x3ff) == 0) {
-                            if (pd_ld_volatile(P.sync + 1) != 0) break;
+                            if (pd_ld_volatile(CP.sync + 1) != 0) break;
                             if (n > PD_SPIN_PEER) {
-                                P.sync[1] = 200 + (unsigned long long)tid;
+                                CP.sync[1] = 200 + (unsigned long long)tid;
                                 break;
                             }
                         }
@@ -605,16 +648,16 @@ __global__ void __launch_bounds__(PD_NT, 1) pdecode_kernel(const PdParams P) {
             }
             if (tid == 0) {
                 const int tok = b == 0ull ? 0 : (int)(0xFFFFFFFFu - (uint32_t)(b & 0xFFFFFFFFull));
-                P.next[0] = tok;
-                if (P.resident) {
-                    const int cntv = *P.counter;
-                    P.tokens[0] = tok;
-                    P.positions[0] += 1;
-                    if (cntv < P.hist_cap) P.hist[cntv] = tok;
-                    *P.counter = cntv + 1;
+                CP.next[0] = tok;
+                if (resident) {
+                    const int cntv = *CP.counter;
+                    CP.tokens[0] = tok;
+                    CP.positions[0] += 1;
+                    if (cntv < CP.hist_cap) CP.hist[cntv] = tok;
+                    *CP.counter = cntv + 1;
                 }
-                P.sync[0] = epoch + 1;
-                pd_stamp(P, 1 + P.layers * 8 + 1);
+                CP.sync[0] = epoch + 1;
+                pd_stamp(pz, 1 + layers * 8 + 1);
             }
         }
     }
@@ -647,9 +690,18 @@ bool jl_pdecode_supported(const PdParams &p, int w_dtype, int grid) {
     if ((p.E % 32) || (p.H % 32) || (p.attn_seg % 32) || (p.E % 8)) return false;
     if (p.E > 16 * PD_NT) return false;        // RMSNorm prologue keeps the row in registers (16 floats per thread)
     if (p.kv_heads * 1 > grid) return false;
-    if (p.world > PD_MAX_TP) return false;
+    if (p.world > PD_MAX_TP || p.layers > PD_MAX_LAYERS) return false;
     if (PD_NT % p.head_size) return false;
     return pd_smem_bytes(p) <= 200 * 1024;
+}
+
+// The constant block belongs to one model per device at a time: (owner id, version) of the last upload.
+static const void *g_pd_owner[JL_MAX_DEVICES] = {};
+static std::mutex g_pd_mu;
+
+void jl_pdecode_forget(int device, const void *owner) {
+    std::lock_guard<std::mutex> lk(g_pd_mu);
+    if (device >= 0 && device < JL_MAX_DEVICES && g_pd_owner[device] == owner) g_pd_owner[device] = nullptr;
 }
 
 template <int WDT, int HS>
@@ -668,21 +720,43 @@ static int launch_pd(jl_ctx *ctx, cudaStream_t stream, const PdParams &p) {
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    JL_CUDA_CHECK(ctx, cudaLaunchKernelEx(&cfg, kern, p));
+    JL_CUDA_CHECK(ctx, cudaLaunchKernelEx(&cfg, kern, p.splits, p.resident, p.want_logits));
     ctx->launches++;
     return JL_OK;
 }
 
 template <int WDT>
 static int launch_pd_hs(jl_ctx *ctx, cudaStream_t stream, const PdParams &p) {
+#ifdef PD_EXPERIMENT_ONLY_128
+    return launch_pd<WDT, 128>(ctx, stream, p);
+#else
     switch (p.head_size) {
         case 32: return launch_pd<WDT, 32>(ctx, stream, p);
         case 64: return launch_pd<WDT, 64>(ctx, stream, p);
         default: return launch_pd<WDT, 128>(ctx, stream, p);
     }
+#endif
 }
 
-int jl_launch_pdecode(jl_ctx *ctx, cudaStream_t stream, const PdParams &p, int w_dtype) {
+// `owner`: identity of the model the constants belong to; `layers_host`: its PdLayer table (host copy).
+int jl_launch_pdecode(jl_ctx *ctx, cudaStream_t stream, const PdParams &p, const PdLayer *layers_host, const void *owner, int w_dtype) {
     if (!jl_pdecode_supported(p, w_dtype, ctx->sm_count)) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "persistent decode: unsupported shape");
+    {
+        std::lock_guard<std::mutex> lk(g_pd_mu);
+        const int d = ctx->device >= 0 && ctx->device < JL_MAX_DEVICES ? ctx->device : 0;
+        if (g_pd_owner[d] != owner) {
+            // another model's launches may still be reading the block: drain the device before replacing it
+            JL_CUDA_CHECK(ctx, cudaDeviceSynchronize());
+            PdParams hp = p;
+            hp.lw = nullptr;
+            JL_CUDA_CHECK(ctx, cudaMemcpyToSymbol(c_pd, &hp, sizeof(PdParams), offsetof(PdConst, P)));
+            JL_CUDA_CHECK(ctx, cudaMemcpyToSymbol(c_pd, layers_host, sizeof(PdLayer) * p.layers, offsetof(PdConst, layers)));
+            g_pd_owner[d] = owner;
+        }
+    }
+#ifdef PD_EXPERIMENT_ONLY_128
+    return launch_pd_hs<JL_Q4>(ctx, stream, p);
+#else
     return w_dtype == JL_Q4 ? launch_pd_hs<JL_Q4>(ctx, stream, p) : launch_pd_hs<JL_I8>(ctx, stream, p);
+#endif
 }

@@ -2,7 +2,9 @@
 #pragma once
 #include "jl_common.cuh"
 
+#ifndef PD_THREADS
 #define PD_THREADS 512
+#endif
 #define PD_MAX_TP 8
 #define PD_SYNC_WORDS 32 // u64 words: [0] epoch, [1] status (0 ok, else the phase id that timed out), [8..] barrier counters
 
@@ -22,7 +24,7 @@ struct PdParams {
     int vocab, vocab_rows, vocab0; // total vocabulary, lm_head rows held by this rank, first of them
     int head0_global, kv_head0_global;
     float eps, attn_scale;
-    const PdLayer *lw; // device array [layers]
+    const PdLayer *lw; // unused (the layer table travels in constant memory)
     int embed_dt;
     const void *embed_w;
     const float *embed_s;
@@ -52,5 +54,9 @@ struct PdParams {
 };
 
 bool jl_pdecode_supported(const PdParams &p, int w_dtype, int grid);
-// one decoded token; `stream` order serialises consecutive tokens
-int jl_launch_pdecode(jl_ctx *ctx, cudaStream_t stream, const PdParams &p, int w_dtype);
+// one decoded token; `stream` order serialises consecutive tokens.  The model constants (dims, buffers, per-layer weight
+// pointers) live in __constant__ memory and are uploaded when `owner` (the model) differs from the previous launch's owner on
+// this device; splits / resident / want_logits travel as kernel arguments.
+int jl_launch_pdecode(jl_ctx *ctx, cudaStream_t stream, const PdParams &p, const PdLayer *layers_host, const void *owner, int w_dtype);
+// the owner is going away (or its constants changed): the next launch re-uploads
+void jl_pdecode_forget(int device, const void *owner);

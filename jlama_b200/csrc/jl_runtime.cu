@@ -476,6 +476,44 @@ extern "C" int jl_quantize_q4_weights(jl_ctx *ctx, const float *x, int64_t rows,
     return JL_OK;
 }
 
+extern "C" int jl_layernorm(jl_ctx *ctx, const float *x, int rows, int ldx, int w_dtype, const void *w, int b_dtype, const void *bias, float eps,
+                            int embedding_length, int offset, int length, float *out) {
+    HOST_OP_PROLOGUE();
+    if (!x || !w || !bias || !out || offset < 0 || offset + length > ldx || (w_dtype != JL_F32 && w_dtype != JL_BF16) ||
+        (b_dtype != JL_F32 && b_dtype != JL_BF16))
+        return jl_set_error(ctx, JL_ERR_INVALID, "layernorm: bad arguments");
+    const size_t xb = (size_t)rows * ldx * 4, n = (size_t)(offset + length);
+    const size_t wb = n * (w_dtype == JL_F32 ? 4 : 2), bb = n * (b_dtype == JL_F32 ? 4 : 2);
+    float *dx = (float *)jl_scratch(ctx, 0, xb);
+    float *dout = (float *)jl_scratch(ctx, 1, xb);
+    char *dw = (char *)jl_scratch(ctx, 2, wb + bb + 32);
+    if (!dx || !dout || !dw) return JL_ERR_OOM;
+    char *dbias = dw + ((wb + 15) & ~(size_t)15);
+    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(dx, x, xb, cudaMemcpyHostToDevice, ctx->stream));
+    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(dout, out, xb, cudaMemcpyHostToDevice, ctx->stream)); // columns outside the slice keep their values
+    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(dw, w, wb, cudaMemcpyHostToDevice, ctx->stream));
+    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(dbias, bias, bb, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = jl_launch_layernorm(ctx, ctx->stream, dx, rows, ldx, w_dtype, dw, b_dtype, dbias, eps, embedding_length, offset, length, dout);
+    if (rc) return rc;
+    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(out, dout, xb, cudaMemcpyDeviceToHost, ctx->stream));
+    JL_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return JL_OK;
+}
+
+extern "C" int jl_activation(jl_ctx *ctx, int type, float *x, int rows, int ld, int offset, int length) {
+    HOST_OP_PROLOGUE();
+    if (!x || type < 0 || type > 2 || offset < 0 || offset + length > ld) return jl_set_error(ctx, JL_ERR_INVALID, "activation: bad arguments");
+    const size_t xb = (size_t)rows * ld * 4;
+    float *dx = (float *)jl_scratch(ctx, 0, xb);
+    if (!dx) return JL_ERR_OOM;
+    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(dx, x, xb, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = jl_launch_activation(ctx, ctx->stream, type, dx, rows, ld, offset, length);
+    if (rc) return rc;
+    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(x, dx, xb, cudaMemcpyDeviceToHost, ctx->stream));
+    JL_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return JL_OK;
+}
+
 extern "C" int jl_quantize_q8_weights(jl_ctx *ctx, const float *x, int64_t rows, int64_t cols, int8_t *q, float *scales) {
     HOST_OP_PROLOGUE();
     if (!x || !q || !scales || rows <= 0 || cols <= 0) return jl_set_error(ctx, JL_ERR_INVALID, "quantize_q8_weights: bad arguments");

@@ -91,6 +91,8 @@ SIGNATURES = {
     "jl_model_tp_layout": (_i, [_vp, C.POINTER(Dctx), C.POINTER(_i)]),
     "jl_rmsnorm": (_i, [_vp, _vp, _i, _i, _i, _vp, _f, _f, _i, _i, _i, _vp]),
     "jl_softmax": (_i, [_vp, _vp, _i, _i]),
+    "jl_layernorm": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _f, _i, _i, _i, _vp]),
+    "jl_activation": (_i, [_vp, _i, _vp, _i, _i, _i, _i]),
     "jl_silu_mul": (_i, [_vp, _vp, _vp, _i, _i, _i, _i]),
     "jl_precompute_freqs_cis": (_i, [_i, _i, _d, _d, _vp]),
     "jl_dctx_build": (_i, [_i] * 10 + [C.POINTER(Dctx)]),

@@ -174,6 +174,20 @@ class CudaTensorOperations:
                                            length, ptr(out)))
         return FloatBufferTensor(out)
 
+    def layernorm(self, x, weights, bias, eps, embedding_length=None, offset=0, length=None):
+        """LayerNorm.forward (model/LayerNorm.java:41-67)"""
+        length = x.cols - offset if length is None else length
+        out = np.zeros_like(x.data)
+        self.ctx.check(self.lib.jl_layernorm(self.ctx.h, ptr(x.data), x.rows, x.cols, weights.dtype, ptr(weights.data), bias.dtype,
+                                             ptr(bias.data), C.c_float(eps), embedding_length or x.cols, offset, length, ptr(out)))
+        return FloatBufferTensor(out)
+
+    def activation(self, kind, x, offset=0, length=None):
+        """ActivationFunction.eval in place: kind in {"silu", "gelu", "tanh"} (math/ActivationFunction.java:29-37)"""
+        length = x.cols - offset if length is None else length
+        code = {"silu": 0, "gelu": 1, "gelu_pytorch_tanh": 1, "tanh": 2}[kind]
+        self.ctx.check(self.lib.jl_activation(self.ctx.h, code, ptr(x.data), x.rows, x.cols, offset, length))
+
     def softmax(self, x, offset, length):
         self.ctx.check(self.lib.jl_softmax(self.ctx.h, ptr(x.data), offset, length))
 

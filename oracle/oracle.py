@@ -322,6 +322,22 @@ def rmsnorm(x, w, eps, E=None, adj=0.0):
     return out
 
 
+def layernorm(x, w, bias, eps, E=None):
+    """model/LayerNorm.java:41-67 (sequential float sums, as the reference)"""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty_like(x)
+    sw, sb = w.struct(), bias.struct()
+    E = E or x.shape[1]
+    L = lib()
+    L.jo_layernorm.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.jo_layernorm(_p(x), C.c_int64(x.shape[0]), C.c_int64(x.shape[1]), C.byref(sw), C.byref(sb), C.c_float(eps), E, 0, x.shape[1], _p(out))
+    return out
+
+
+def gelu(x):
+    return np.array([lib().jo_gelu(float(v)) for v in np.asarray(x, dtype=np.float32).ravel()], dtype=np.float32).reshape(np.shape(x))
+
+
 def precompute_freqs_cis(dim, end, theta, scaling=1.0):
     out = np.empty((end * (dim // 2), 2), dtype=np.float32)
     lib().jo_precompute_freqs_cis(dim, end, C.c_double(theta), C.c_double(scaling), _p(out))

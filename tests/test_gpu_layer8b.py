@@ -10,9 +10,13 @@ N(0, 0.02^2) quantised with the reference quantiser semantics (the or
 of layer 0 and of layer 31.  Prompt rows go through the batched (M<=8) kernels, decode steps through the decode fast
 path (and the persistent kernel when enabled); every step is teacher-forced with the oracle's token.
 
-Bars: K/V rows 2e-5 of their max; hidden row and logits 1e-4 of max (the four Q8 re-quantisations inside the layer turn a
-1e-7 summation-order difference into an occasional +-1 int8 step of one activation, ~1e-5..1e-4 of the row maximum; the
-measured values are printed)."""
+Bars: K/V rows 2e-5 of their max.  Hidden row and logits: every step is either "clean" (<= 1e-5 of the row maximum; measured
+2e-7 hidden / 2e-6 logits) or a "rounding flip" step (<= 5e-3): the four Q8 re-quantisations inside a layer
+(PanamaTensorOperations.java:1696-1710, q = (byte)(x * (127/max) + 0.5f)) turn a 1-ulp summation-order difference into a +-1
+step of ONE int8 activation when x * (127/max) + 0.5 sits on an integer -- measured 1.2e-3 of the row maximum, about one
+step in seven at these shapes, gone again at the next position.  The same happens between any two implementations of the
+reference arithmetic with different summation orders (the reference's AVX-512 kernels vs its scalar loops).  At most a third
+of the steps may be flip steps, the median must be clean; the per-step values are printed."""
 import numpy as np
 import pytest
 
@@ -62,10 +66,11 @@ def test_one_8b_layer_teacher_forced_q8_activations(cuda_ctx, oracle, src_layer)
     ot, ol = om.sample(oh)
     worst["logits"] = _rel(gl, ol)
     steps = ["prefill: hidden %.2e logits %.2e" % (worst["hidden"], worst["logits"])]
+    step_err = [max(worst["hidden"], worst["logits"])]
     assert gt == ot
     # decode fast path, teacher-forced with the oracle's token
     tok = ot
-    for step in range(6):
+    for step in range(12):
         pos = len(prompt) + step
         nxt, lg = gm.decode([tok], [pos], sessions=[0], want_logits=True)
         gx = gm.debug_read(0, cfg["E"])  # hidden row after the layer, decode path
@@ -73,6 +78,7 @@ def test_one_8b_layer_teacher_forced_q8_activations(cuda_ctx, oracle, src_layer)
         ot, ol = om.sample(oh)
         hr, lr = _rel(gx, oh), _rel(lg[0], ol)
         steps.append("decode pos %d: hidden %.2e logits %.2e" % (pos, hr, lr))
+        step_err.append(max(hr, lr))
         worst["hidden"] = max(worst["hidden"], hr)
         worst["logits"] = max(worst["logits"], lr)
         for which in (0, 1):
@@ -82,8 +88,10 @@ def test_one_8b_layer_teacher_forced_q8_activations(cuda_ctx, oracle, src_layer)
     print("8B-dims layer %d (teacher-forced): hidden %.2e, kv %.2e, logits %.2e of max\n  " % (
         src_layer, worst["hidden"], worst["kv"], worst["logits"]) + "\n  ".join(steps))
     assert worst["kv"] <= 2e-5
-    assert worst["hidden"] <= 1e-4
-    assert worst["logits"] <= 1e-4
+    errs = sorted(step_err)
+    flips = [e for e in errs if e > 1e-5]
+    assert errs[-1] <= 5e-3, errs
+    assert len(flips) * 3 <= len(errs) and errs[len(errs) // 2] <= 1e-5, errs
     gm.close()
     om.close()
 

@@ -270,3 +270,34 @@ def test_tensor_core_gemm_matches_bf16_reference(cuda_ops, oracle, M, N, K):
         cuda_ops.batch_dot_product_tensor_core(c2, T.FloatBufferTensor(a), w, 0, 0, K, 0, 128, 128)
         assert np.all(c2.data[:, :128] == 0) and np.array_equal(c2.data[:, 128:256], c.data[:, 128:256])
     cuda_ops.unregister_model_tensor(w)
+
+
+def test_layernorm_matches_reference_restatement(cuda_ops, oracle):
+    """LayerNorm.forward (model/LayerNorm.java:41-67, GPT-2 family).  The reference sums sequentially in float; any other
+    summation order moves the statistics by ~1e-6 relative (bar: 2e-5 of the row maximum)."""
+    from jlama_b200.tensor import BFloat16BufferTensor, FloatBufferTensor, float32_to_bfloat16
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((5, 768)) * 3 + 0.7).astype(np.float32)
+    w = (1 + 0.1 * rng.standard_normal((1, 768))).astype(np.float32)
+    b = (0.1 * rng.standard_normal((1, 768))).astype(np.float32)
+    out = cuda_ops.layernorm(FloatBufferTensor(x), FloatBufferTensor(w), FloatBufferTensor(b), 1e-5)
+    ref = oracle.layernorm(x, oracle.f32(w), oracle.f32(b), 1e-5)
+    assert np.abs(out.data - ref).max() <= 2e-5 * np.abs(ref).max()
+    wb = float32_to_bfloat16(w)
+    out2 = cuda_ops.layernorm(FloatBufferTensor(x), BFloat16BufferTensor(wb), FloatBufferTensor(b), 1e-5)
+    ref2 = oracle.layernorm(x, oracle.OTensor(oracle.BF16, wb), oracle.f32(b), 1e-5)
+    assert np.abs(out2.data - ref2).max() <= 2e-5 * np.abs(ref2).max()
+
+
+def test_activation_functions_match_reference(cuda_ops, oracle):
+    """ActivationFunction.eval (math/ActivationFunction.java:29-37): SILU and the tanh-form GELU in double, cast to float."""
+    from jlama_b200.tensor import FloatBufferTensor
+    rng = np.random.default_rng(6)
+    x = (rng.standard_normal((3, 320)) * 4).astype(np.float32)
+    for kind, ref in (("gelu", oracle.gelu), ("silu", oracle.silu)):
+        t = FloatBufferTensor(x.copy())
+        cuda_ops.activation(kind, t, 32, 256)
+        want = x.copy()
+        want[:, 32:288] = ref(x[:, 32:288])
+        assert np.array_equal(t.data[:, :32], x[:, :32]) and np.array_equal(t.data[:, 288:], x[:, 288:])
+        assert np.abs(t.data - want).max() <= 2e-7 * max(1.0, np.abs(want).max())
