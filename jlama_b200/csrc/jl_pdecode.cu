@@ -27,7 +27,9 @@
 // Every spin is bounded: a protocol error sets sync[1] and the launch drains instead of hanging the GPU.
 #include "jl_pdecode.cuh"
 #include "jl_gemv_body.cuh"
+#define JL_EXP_FN __forceinline__ // no ABI calls inside the persistent kernel
 #include "jl_attn_task.cuh"
+#include "jl_attn_flat.cuh"
 #include <stddef.h>
 #include <string.h>
 
@@ -485,16 +487,30 @@ __device__ PD_PHASE_FN void pd_ll_reduce(const int, uint32_t tag, float *scratch
     }
 }
 
+// One attention task.  qkv_target != 0: the QKV barrier is waited for inside (after the first K/V rows have been requested).
 template <int HS>
-__device__ PD_PHASE_FN void pd_attention(const int, const int layer, const int kvh, const int split, const int splits, const bool merge, unsigned char *smem) {
+__device__ PD_PHASE_FN void pd_attention(const int, const int layer, const int kvh, const int split, const int splits, const bool merge,
+                                         const unsigned long long qkv_target, unsigned char *smem) {
     PD_OPAQUE_ZERO(pz);
     AttnTask at;
     at.heads = CP.heads, at.kv_heads = CP.kv_heads, at.head_size = CP.head_size, at.attn_seg = CP.attn_seg, at.kv_seg = CP.kv_seg;
     at.kv_head0_global = CP.kv_head0_global, at.splits = splits, at.attn_scale = CP.attn_scale;
     at.q = CP.q, at.k = CP.k, at.v = CP.v, at.att = CP.att, at.attn_ws = CP.attn_ws, at.rope = CP.rope, at.kv = CP.kv;
     at.sessions = CP.sessions, at.positions = CP.positions;
-    if (merge) attention_merge<HS, PD_NT>(at, 0, kvh, smem);
-    else attention_task<HS, PD_NT, -1>(at, layer, 0, kvh, split, smem);
+    if (merge) {
+        attention_merge<HS, PD_NT>(at, 0, kvh, smem);
+        return;
+    }
+    const int group = at.heads / at.kv_heads;
+    const int n = at.positions[0] + 1;
+    const int per = (((n + splits - 1) / splits) + 31) / 32 * 32;
+    const bool flat = (group & (group - 1)) == 0 && per <= FA_MAX_POS;
+    if (flat) {
+        attention_flat<HS, PD_NT>(at, layer, 0, kvh, split, smem, [&]() { pd_wait(pz, PC_QKV, qkv_target); });
+    } else {
+        pd_wait(pz, PC_QKV, qkv_target);
+        attention_task<HS, PD_NT, -1>(at, layer, 0, kvh, split, smem);
+    }
 }
 
 template <int WDT, int HS>
@@ -537,9 +553,8 @@ __global__ void __launch_bounds__(PD_NT, 1) pdecode_kernel(const int splits, con
         }
         // ---- attention tasks on the first CTAs (RoPE, KV append, scores, softmax, P.V) ----
         if (cta < ntasks) {
-            pd_wait(pz, PC_QKV, use * uG);
             const int split = cta % splits, kvh = cta / splits;
-            pd_attention<HS>(pz, L, kvh, split, splits, false, smem);
+            pd_attention<HS>(pz, L, kvh, split, splits, false, use * uG, smem);
             bool signal = true;
             if (splits > 1) {
                 __syncthreads();
@@ -553,7 +568,7 @@ __global__ void __launch_bounds__(PD_NT, 1) pdecode_kernel(const int splits, con
                 }
                 __syncthreads();
                 signal = s_last != 0;
-                if (signal) pd_attention<HS>(pz, L, kvh, split, splits, true, smem);
+                if (signal) pd_attention<HS>(pz, L, kvh, split, splits, true, 0ull, smem);
             }
             __syncthreads();
             if (signal && tid == 0) asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(CP.sync + PC_ATT) : "memory");
@@ -677,6 +692,8 @@ static size_t pd_smem_bytes(const PdParams &p) {
     const int hs = p.head_size;
     size_t att = hs == 32 ? attention_task_smem<32, PD_NT>() : (hs == 64 ? attention_task_smem<64, PD_NT>() : attention_task_smem<128, PD_NT>());
     att += 1024; // merge factors
+    const size_t flat = hs == 32 ? attention_flat_smem<32, PD_NT>() : (hs == 64 ? attention_flat_smem<64, PD_NT>() : attention_flat_smem<128, PD_NT>());
+    if (flat > att) att = flat;
     size_t m = acts > att ? acts : att;
     const size_t red = (size_t)((p.E + G - 1) / G + 2) * PD_MAX_TP * 4;
     if (red > m) m = red;
