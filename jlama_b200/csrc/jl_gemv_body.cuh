@@ -297,7 +297,9 @@ __device__ __forceinline__ void stage_q8_issue(const GemvParams &p, StageRegs<NO
     if constexpr (LONG) load16(r.x1, x0 + (NT + tid) * 16, (NT + tid) * 16 < p.K);
 }
 
-template <bool NORM, bool LONG, int NT>
+// FULLBAR: 0 = the closing barrier is __syncthreads(); otherwise bar.sync FULLBAR over NT threads (a CTA that carries extra
+// non-consumer warps, e.g. the TMA producer warp of the persistent decode kernel)
+template <bool NORM, bool LONG, int NT, int FULLBAR = 0>
 __device__ __forceinline__ void stage_q8_finish(const GemvParams &p, StageRegs<NORM, LONG> &r, unsigned char *smem, const int nblk) {
     constexpr int NWARP = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -317,7 +319,7 @@ __device__ __forceinline__ void stage_q8_finish(const GemvParams &p, StageRegs<N
             for (int i = 0; i < 16; i++) ss += (double)__fmul_rn(r.x0[i], r.x0[i]); // float products, double sum
             ss = warp_sum_d(ss);
             if (lane == 0) red[warp] = ss;
-            asm volatile("bar.sync 1, %0;" ::"r"(nsw * 32) : "memory");
+            asm volatile("bar.sync 2, %0;" ::"r"(nsw * 32) : "memory");
             double t = 0.0;
             for (int i = 0; i < nsw; i++) t += red[i];
             const float rsf = rms_scale(t, p.norm_inv_E, p.norm_eps);
@@ -336,7 +338,8 @@ __device__ __forceinline__ void stage_q8_finish(const GemvParams &p, StageRegs<N
             quant_half_block(r.x1, aq, asc, asum, 0, nblk, e >> 5, half, e < K);
         }
     }
-    __syncthreads();
+    if (FULLBAR == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"n"(FULLBAR), "n"(NT) : "memory");
 }
 
 template <int MM>

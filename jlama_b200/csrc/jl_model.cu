@@ -329,6 +329,10 @@ extern "C" int jl_model_finalize(jl_model *m) {
             probe.layers = c.num_layers, probe.E = E, probe.H = m->h_seg, probe.attn_seg = m->attn_seg, probe.kv_seg = m->kv_seg;
             probe.heads = m->heads_local, probe.kv_heads = m->kv_heads_local, probe.head_size = hs, probe.world = W;
             ok = jl_pdecode_supported(probe, wd, ctx->sm_count);
+            // flat decode attention: at most 1024 positions per (kv head, split) task
+            int cap = ctx->sm_count / (m->kv_heads_local > 0 ? m->kv_heads_local : 1);
+            if (cap > m->max_splits) cap = m->max_splits;
+            if (cap < 1 || (m->max_context + cap - 1) / cap > 1024 - 32) ok = false;
         }
         if (ok) {
             std::vector<PdLayer> pl(c.num_layers);

@@ -31,6 +31,7 @@
 #include "jl_attn_task.cuh"
 #include "jl_attn_flat.cuh"
 #include <stddef.h>
+#include <stdlib.h>
 #include <string.h>
 
 #define PD_NT PD_THREADS
@@ -62,6 +63,9 @@ __constant__ PdConst c_pd;
 
 enum { PH_QKV = 0, PH_O, PH_GU, PH_DOWN };
 
+// The CTA = PD_NT consumer threads + one TMA producer warp: every CTA-wide barrier of the consumers is the named barrier 1.
+__device__ __forceinline__ void pd_cta_bar() { asm volatile("bar.sync 1, %0;" ::"n"(PD_NT) : "memory"); }
+
 // ---- cross-CTA ordering ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long pd_ld_acquire(const unsigned long long *p) {
     unsigned long long v;
@@ -75,7 +79,7 @@ __device__ __forceinline__ unsigned long long pd_ld_volatile(const unsigned long
 }
 // all threads of the CTA call; publishes everything the CTA wrote in this phase
 __device__ __forceinline__ void pd_arrive(const int pz, int which) {
-    __syncthreads();
+    pd_cta_bar();
     if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(CP.sync + which) : "memory");
 }
 // all threads of the CTA call
@@ -94,7 +98,7 @@ __device__ __forceinline__ void pd_wait(const int pz, int which, unsigned long l
             }
         }
     }
-    __syncthreads();
+    pd_cta_bar();
 }
 __device__ __forceinline__ void pd_stamp(const int pz, int idx) {
     if (CP.trace && blockIdx.x == 0 && threadIdx.x == 0) CP.trace[idx] = globaltimer_ns();
@@ -279,7 +283,7 @@ __device__ PD_PHASE_FN void pd_gemv(const int, const int L, const uint32_t tag, 
         p.norm_adj = 0.0f, p.norm_eps = CP.eps, p.norm_E = CP.E, p.norm_inv_E = 1.0 / (double)CP.E;
         StageRegs<NORM, LONG && !NORM> sr;
         stage_q8_issue<NORM, LONG && !NORM, NT>(p, sr);
-        stage_q8_finish<NORM, LONG && !NORM, NT>(p, sr, smem, nblk);
+        stage_q8_finish<NORM, LONG && !NORM, NT, 1>(p, sr, smem, nblk);
     }
     float *parts = (float *)(smem + (((size_t)nblk * 40 + 15) & ~(size_t)15));
     const int maxsplit = nchunks < NWARP ? nchunks : NWARP;
@@ -334,7 +338,7 @@ __device__ PD_PHASE_FN void pd_gemv(const int, const int L, const uint32_t tag, 
     }
     if (!LONG) flush();
     if (LONG) {
-        __syncthreads();
+        pd_cta_bar();
         for (int o = tid; o < nrows; o += NT) {
             float sums[NW];
 #pragma unroll
@@ -346,6 +350,292 @@ __device__ PD_PHASE_FN void pd_gemv(const int, const int L, const uint32_t tag, 
                 sums[wr] = t;
             }
             store_row(R0 + o, sums[0], sums[NW - 1]);
+        }
+    }
+}
+
+
+// ======================================================================================================================
+// TMA weight ring.  The register ring above keeps ~2 chunks per warp in flight and restarts at every phase: after a grid
+// barrier each warp holds its two primed chunks and then waits a full DRAM latency for the third.  Here ONE producer warp
+// streams the CTA's weights of phase after phase into a shared-memory ring with cp.async.bulk (TMA), bounded only by free
+// slots -- it runs through barriers, prologues and the attention phase, so up to the whole ring (~100 KB per SM, 15 MB per
+// GPU) is in flight or landed when the consumers come out of a barrier.  Consumers read the 16-byte blocks back with
+// LDS.128 and -- for rows of exactly 4096 elements (one 128-block chunk) -- keep their four Q8 activation blocks in
+// REGISTERS, so the ring adds 40 B of shared-memory traffic per 20 B of weights instead of 100 B (the round-1 TMA ring
+// variant read activations from shared memory as well and was shared-memory-bandwidth bound).
+// A chunk = 128 consecutive blocks of the CTA's row range (rows are contiguous in memory, so are their scales).
+// ======================================================================================================================
+#define PD_CHUNK_BLK 128
+template <int WDT>
+struct RingCfg {
+    static constexpr int WB = (WDT == JL_Q4) ? 16 : 32;
+    static constexpr int SLOT = PD_CHUNK_BLK * WB + PD_CHUNK_BLK * 4; // weights then scales
+};
+#define PD_MAX_SLOTS 64
+struct PdRing {
+    unsigned char *slots; // [nslots][SLOT]
+    uint64_t *full, *empty; // mbarriers
+    int nslots;
+};
+__device__ __forceinline__ uint32_t pd_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pd_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pd_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void pd_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pd_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pd_mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pd_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool pd_mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(pd_smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+// bounded wait; false = gave up (status word set)
+__device__ __forceinline__ bool pd_mbar_wait(const int pz, uint64_t *bar, uint32_t parity, int code) {
+    unsigned n = 0;
+    while (!pd_mbar_try_wait(bar, parity)) {
+        if ((++n & 0xfff) == 0) {
+            if (pd_ld_volatile(CP.sync + 1) != 0) return false;
+            if (n > (1u << 24)) {
+                CP.sync[1] = (unsigned long long)code;
+                return false;
+            }
+        }
+    }
+    return true;
+}
+__device__ __forceinline__ void pd_tma_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar, unsigned long long pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(pd_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(pd_smem_u32(bar)), "l"(pol)
+                 : "memory");
+}
+
+// The CTA's share of a phase as up to three contiguous pieces (one per weight tensor it touches).
+struct PdPiece {
+    const uint8_t *w; // first block of the piece
+    const float *s;
+    int blocks;       // rows * nblk
+    int chunk0;       // first chunk of the piece in the CTA's chunk sequence of this phase
+    int slot0;        // row slot (index into the CTA's partial-sum table) of the piece's first row
+    int row0;         // first row, local to the segment (QKV: row inside q / k / v; gate/up: row inside H)
+    int seg;          // QKV: 0 q, 1 k, 2 v; gate/up: 0 gate, 1 up; else 0
+};
+template <int WDT, int PH>
+__device__ __forceinline__ int pd_pieces(const int pz, const int L, const int cta_id, const int ncta, PdPiece (&pc)[3], int &nrows_out) {
+    constexpr int WB = RingCfg<WDT>::WB;
+    const int nblk = ph_K<PH>(pz) / 32;
+    const int R0 = (int)(((long long)ph_rows<PH>(pz) * cta_id) / ncta);
+    const int R1 = (int)(((long long)ph_rows<PH>(pz) * (cta_id + 1)) / ncta);
+    int np = 0, chunk = 0;
+    auto add = [&](int seg, int r0, int r1, int slot0) { // rows [r0, r1) of segment `seg`
+        if (r1 <= r0) return;
+        const uint8_t *w;
+        const float *sc;
+        ph_weights<PH>(L, seg, w, sc);
+        pc[np].w = w + (size_t)r0 * nblk * WB;
+        pc[np].s = sc + (size_t)r0 * nblk;
+        pc[np].blocks = (r1 - r0) * nblk;
+        pc[np].chunk0 = chunk;
+        pc[np].slot0 = slot0;
+        pc[np].row0 = r0;
+        pc[np].seg = seg;
+        chunk += (pc[np].blocks + PD_CHUNK_BLK - 1) / PD_CHUNK_BLK;
+        np++;
+    };
+    if (PH == PH_QKV) {
+        const int a = CP.attn_seg, kv = CP.kv_seg;
+        add(0, min(R0, a), min(R1, a), 0);
+        add(1, min(max(R0 - a, 0), kv), min(max(R1 - a, 0), kv), max(a - R0, 0));
+        add(2, min(max(R0 - a - kv, 0), kv), min(max(R1 - a - kv, 0), kv), max(a + kv - R0, 0));
+    } else if (PH == PH_GU) {
+        add(0, R0, R1, 0);
+        add(1, R0, R1, R1 - R0);
+    } else {
+        add(0, R0, R1, 0);
+    }
+    for (int i = np; i < 3; i++) pc[i].blocks = 0, pc[i].chunk0 = chunk;
+    nrows_out = R1 - R0;
+    return chunk; // chunks of this CTA in this phase
+}
+// is the ring usable for a phase?  (32-lane groups of a chunk must not straddle rows)
+template <int PH>
+__device__ __forceinline__ bool pd_ring_phase(const int pz) {
+    const int nblk = ph_K<PH>(pz) / 32;
+    return (nblk % 32) == 0;
+}
+
+// ---- producer: one lane streams the chunks of one phase ----
+template <int WDT, int PH>
+__device__ __forceinline__ void pd_produce(const int pz, const int L, const PdRing &R, unsigned &g, const unsigned long long pol) {
+    constexpr int WB = RingCfg<WDT>::WB, SLOT = RingCfg<WDT>::SLOT;
+    PdPiece pc[3];
+    int nrows;
+    const int total = pd_pieces<WDT, PH>(pz, L, blockIdx.x, gridDim.x, pc, nrows);
+#pragma unroll 1
+    for (int i = 0; i < 3; i++) {
+        const int nch = (pc[i].blocks + PD_CHUNK_BLK - 1) / PD_CHUNK_BLK;
+#pragma unroll 1
+        for (int c = 0; c < nch; c++, g++) {
+            const unsigned slot = g % (unsigned)R.nslots, par = (g / (unsigned)R.nslots) & 1u;
+            if (!pd_mbar_wait(pz, &R.empty[slot], par ^ 1u, 300)) return;
+            const int nb = min(PD_CHUNK_BLK, pc[i].blocks - c * PD_CHUNK_BLK);
+            unsigned char *dst = R.slots + (size_t)slot * SLOT;
+            pd_mbar_expect_tx(&R.full[slot], (uint32_t)nb * (WB + 4));
+            pd_tma_load(dst, pc[i].w + (size_t)c * PD_CHUNK_BLK * WB, (uint32_t)nb * WB, &R.full[slot], pol);
+            pd_tma_load(dst + PD_CHUNK_BLK * WB, pc[i].s + (size_t)c * PD_CHUNK_BLK, (uint32_t)nb * 4, &R.full[slot], pol);
+        }
+    }
+    (void)total;
+}
+
+// ---- consumer: one GEMV phase fed from the ring ----
+// ACTREG: rows are exactly one chunk (K = 4096): each lane owns blocks {lane, 32+lane, 64+lane, 96+lane} of every row and keeps
+// their Q8 activations (2 x 16 bytes, scale, sum) in registers.
+template <int WDT, int PH, int EPI, bool ACTREG>
+__device__ PD_PHASE_FN void pd_gemv_ring(const int, const int L, const uint32_t tag, const int dep_which, const unsigned long long dep_target,
+                                         const int stamp_idx, unsigned char *smem, const PdRing &R, unsigned &g) {
+    PD_OPAQUE_ZERO(pz);
+    constexpr int NT = PD_NT, NWARP = PD_NWARP;
+    constexpr bool NORM = PH == PH_QKV || PH == PH_GU;
+    constexpr int WB = RingCfg<WDT>::WB, SLOT = RingCfg<WDT>::SLOT;
+    int tid = threadIdx.x, cta_id = blockIdx.x, ncta = gridDim.x;
+    asm volatile("" : "+r"(tid), "+r"(cta_id), "+r"(ncta));
+    const int lane = tid & 31, warp = tid >> 5;
+    const int K = ph_K<PH>(pz), nblk = K / 32;
+    PdPiece pc[3];
+    int nrows;
+    const int total = pd_pieces<WDT, PH>(pz, L, cta_id, ncta, pc, nrows);
+    const int maxp = nblk / PD_CHUNK_BLK + 2; // partial sums per row (chunks that touch a row)
+    pd_wait(pz, dep_which, dep_target);
+    pd_stamp(pz, stamp_idx);
+    {
+        GemvParams p; // only the staging fields; dead after the prologue
+        p.a = PH == PH_QKV ? CP.x : (PH == PH_O ? CP.att : (PH == PH_GU ? CP.xb : CP.h));
+        p.a_col_off = 0, p.K = K, p.lda = K;
+        p.norm_w = PH == PH_QKV ? c_pd.layers[L].attn_norm : c_pd.layers[L].ffn_norm;
+        p.norm_w_dtype = PH == PH_QKV ? c_pd.layers[L].attn_norm_dt : c_pd.layers[L].ffn_norm_dt;
+        p.norm_adj = 0.0f, p.norm_eps = CP.eps, p.norm_E = CP.E, p.norm_inv_E = 1.0 / (double)CP.E;
+        constexpr bool LNG = !NORM; // the un-normalised prologue handles any K with its tail loop
+        StageRegs<NORM, LNG> sr;
+        stage_q8_issue<NORM, LNG, NT>(p, sr);
+        stage_q8_finish<NORM, LNG, NT, 1>(p, sr, smem, nblk);
+    }
+    const int8_t *aq = (const int8_t *)smem;
+    const float *asc = (const float *)(smem + (size_t)nblk * 32);
+    const int *asum = (const int *)(smem + (size_t)nblk * 32 + (size_t)nblk * 4);
+    float *parts = (float *)(smem + (((size_t)nblk * 40 + 15) & ~(size_t)15));
+    // register-resident activations (ACTREG)
+    uint4 alo[ACTREG ? 4 : 1], ahi[ACTREG ? 4 : 1];
+    float asc_r[ACTREG ? 4 : 1];
+    int asum_r[ACTREG ? 4 : 1];
+    if (ACTREG) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int bi = j * 32 + lane;
+            alo[j] = *(const uint4 *)(aq + (size_t)bi * 16);
+            ahi[j] = *(const uint4 *)(aq + ((size_t)nblk + bi) * 16);
+            asc_r[j] = asc[bi];
+            asum_r[j] = asum[bi];
+        }
+    }
+    for (int c = warp; c < total; c += NWARP) {
+        // piece of this chunk
+        const int pi = c >= pc[2].chunk0 && pc[2].blocks > 0 ? 2 : (c >= pc[1].chunk0 && pc[1].blocks > 0 ? 1 : 0);
+        const int cc = c - pc[pi].chunk0;
+        const int nb = min(PD_CHUNK_BLK, pc[pi].blocks - cc * PD_CHUNK_BLK);
+        const unsigned gg = g + (unsigned)c, slot = gg % (unsigned)R.nslots, par = (gg / (unsigned)R.nslots) & 1u;
+        const unsigned char *sw = R.slots + (size_t)slot * SLOT;
+        const float *ss = (const float *)(sw + PD_CHUNK_BLK * WB);
+        pd_mbar_wait(pz, &R.full[slot], par, 400);
+        float acc = 0.0f;
+        int cur_row = (cc * PD_CHUNK_BLK) / nblk; // row inside the piece
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (j * 32 < nb) { // uniform
+                const int gb0 = cc * PD_CHUNK_BLK + j * 32;
+                const int row = gb0 / nblk, col0 = gb0 - row * nblk;
+                if (row != cur_row) { // uniform: the previous row ends inside this chunk
+                    const float v = warp_sum(acc);
+                    if (lane == 0) parts[(pc[pi].slot0 + cur_row) * maxp + (cc - (cur_row * nblk) / PD_CHUNK_BLK)] = v;
+                    acc = 0.0f, cur_row = row;
+                }
+                const int bl = j * 32 + lane;
+                const float sb = ss[bl];
+                uint4 xlo, xhi;
+                float xs;
+                int xsum;
+                if (ACTREG) {
+                    xlo = alo[j], xhi = ahi[j], xs = asc_r[j], xsum = asum_r[j];
+                } else {
+                    const int bi = col0 + lane;
+                    xlo = *(const uint4 *)(aq + (size_t)bi * 16);
+                    xhi = *(const uint4 *)(aq + ((size_t)nblk + bi) * 16);
+                    xs = asc[bi], xsum = asum[bi];
+                }
+                int sdot = 0;
+                if (WDT == JL_Q4) {
+                    const uint4 q = *(const uint4 *)(sw + (size_t)bl * 16);
+                    sdot = __dp4a((int)(q.x & 0x0F0F0F0Fu), (int)xlo.x, sdot);
+                    sdot = __dp4a((int)((q.x >> 4) & 0x0F0F0F0Fu), (int)xhi.x, sdot);
+                    sdot = __dp4a((int)(q.y & 0x0F0F0F0Fu), (int)xlo.y, sdot);
+                    sdot = __dp4a((int)((q.y >> 4) & 0x0F0F0F0Fu), (int)xhi.y, sdot);
+                    sdot = __dp4a((int)(q.z & 0x0F0F0F0Fu), (int)xlo.z, sdot);
+                    sdot = __dp4a((int)((q.z >> 4) & 0x0F0F0F0Fu), (int)xhi.z, sdot);
+                    sdot = __dp4a((int)(q.w & 0x0F0F0F0Fu), (int)xlo.w, sdot);
+                    sdot = __dp4a((int)((q.w >> 4) & 0x0F0F0F0Fu), (int)xhi.w, sdot);
+                    sdot -= 8 * xsum; // sum a*(nib-8) = sum a*nib - 8*sum a   (exact)
+                } else {
+                    const uint4 q0 = *(const uint4 *)(sw + (size_t)bl * 32), q1 = *(const uint4 *)(sw + (size_t)bl * 32 + 16);
+                    sdot = __dp4a((int)q0.x, (int)xlo.x, sdot);
+                    sdot = __dp4a((int)q0.y, (int)xlo.y, sdot);
+                    sdot = __dp4a((int)q0.z, (int)xlo.z, sdot);
+                    sdot = __dp4a((int)q0.w, (int)xlo.w, sdot);
+                    sdot = __dp4a((int)q1.x, (int)xhi.x, sdot);
+                    sdot = __dp4a((int)q1.y, (int)xhi.y, sdot);
+                    sdot = __dp4a((int)q1.z, (int)xhi.z, sdot);
+                    sdot = __dp4a((int)q1.w, (int)xhi.w, sdot);
+                }
+                acc = fmaf(__fmul_rn(xs, sb), (float)sdot, acc); // acc += (sa*sb) * isum   (vector_simd.c:384-420)
+            }
+        }
+        {
+            const float v = warp_sum(acc);
+            if (lane == 0) parts[(pc[pi].slot0 + cur_row) * maxp + (cc - (cur_row * nblk) / PD_CHUNK_BLK)] = v;
+        }
+        __syncwarp();
+        if (lane == 0) pd_mbar_arrive(&R.empty[slot]);
+    }
+    g += (unsigned)total;
+    pd_cta_bar();
+    // ---- per-row pass: partial sums in chunk order, fused epilogue ----
+    const int npr = (nblk + PD_CHUNK_BLK - 1) / PD_CHUNK_BLK; // chunks of an aligned row
+    auto row_sum = [&](int slot, int row_in_piece) {
+        const int first = (row_in_piece * nblk) / PD_CHUNK_BLK, last = ((row_in_piece + 1) * nblk - 1) / PD_CHUNK_BLK;
+        float t = 0.0f;
+        for (int q = first; q <= last; q++) t = __fadd_rn(t, parts[slot * maxp + (q - first)]);
+        return t;
+    };
+    (void)npr;
+    const int nout = PH == PH_GU ? nrows : nrows; // output rows of this CTA
+    for (int o = tid; o < nout; o += NT) {
+        if (PH == PH_GU) {
+            const float gsum = row_sum(o, o), usum = row_sum(nrows + o, o); // both pieces start at row R0: row_in_piece = o
+            CP.h[pc[0].row0 + o] = __fmul_rn(silu_ref(gsum), usum);
+        } else {
+            // locate the piece of slot o
+            const int pi = (pc[2].blocks > 0 && o >= pc[2].slot0) ? 2 : ((pc[1].blocks > 0 && o >= pc[1].slot0) ? 1 : 0);
+            const int rip = o - pc[pi].slot0;
+            float v = row_sum(o, rip);
+            const int local = pc[pi].row0 + rip;
+            if (EPI == EPI_ADD_RESIDUAL) v = __fadd_rn(v, __ldcg((PH == PH_O ? CP.x : CP.xb) + local));
+            if (EPI == EPI_LL) ll_store<PH>(pz, local, v, tag);
+            else ph_out<PH>(pz, pc[pi].seg)[local] = v;
         }
     }
 }
@@ -395,7 +685,7 @@ __device__ PD_PHASE_FN unsigned long long pd_lm_head(const int, const int dep_wh
         }
         ss = warp_sum_d(ss);
         if (lane == 0) red[warp] = ss;
-        __syncthreads();
+        pd_cta_bar();
         double t = 0.0;
 #pragma unroll
         for (int w = 0; w < NWARP; w++) t += red[w];
@@ -415,7 +705,7 @@ __device__ PD_PHASE_FN unsigned long long pd_lm_head(const int, const int dep_wh
             af4[(size_t)c4 * nblk + b] = make_float4(__fmul_rn(__fadd_rn(0.0f, w[0]), __fmul_rn(rsf, v.x)), __fmul_rn(__fadd_rn(0.0f, w[1]), __fmul_rn(rsf, v.y)),
                                                      __fmul_rn(__fadd_rn(0.0f, w[2]), __fmul_rn(rsf, v.z)), __fmul_rn(__fadd_rn(0.0f, w[3]), __fmul_rn(rsf, v.w)));
         }
-        __syncthreads();
+        pd_cta_bar();
     }
     float acc[1] = {0.0f};
     float best_v = -INFINITY;
@@ -443,7 +733,7 @@ __device__ PD_PHASE_FN unsigned long long pd_lm_head(const int, const int dep_wh
         }
     }
     if (lane == 0) wbest[warp] = best_i == 0x7fffffff ? 0ull : pd_pack_arg(best_v, best_i);
-    __syncthreads();
+    pd_cta_bar();
     unsigned long long b = 0ull;
     if (tid == 0)
         for (int w = 0; w < NWARP; w++) b = wbest[w] > b ? wbest[w] : b;
@@ -479,7 +769,7 @@ __device__ PD_PHASE_FN void pd_ll_reduce(const int, uint32_t tag, float *scratch
         const int r = t / W, src = t - r * W;
         scratch[t] = ll_load(pz, mine, src, R0 + r, tag);
     }
-    __syncthreads();
+    pd_cta_bar();
     for (int r = tid; r < nrows; r += PD_NT) {
         float s = scratch[r * W];
         for (int src = 1; src < W; src++) s = __fadd_rn(s, scratch[r * W + src]); // rank order: identical on every rank
@@ -504,22 +794,49 @@ __device__ PD_PHASE_FN void pd_attention(const int, const int layer, const int k
     const int group = at.heads / at.kv_heads;
     const int n = at.positions[0] + 1;
     const int per = (((n + splits - 1) / splits) + 31) / 32 * 32;
-    const bool flat = (group & (group - 1)) == 0 && per <= FA_MAX_POS;
-    if (flat) {
-        attention_flat<HS, PD_NT>(at, layer, 0, kvh, split, smem, [&]() { pd_wait(pz, PC_QKV, qkv_target); });
-    } else {
-        pd_wait(pz, PC_QKV, qkv_target);
-        attention_task<HS, PD_NT, -1>(at, layer, 0, kvh, split, smem);
-    }
+    // (the host only selects this kernel for power-of-two head groups and <= FA_MAX_POS positions per split)
+    (void)n;
+    (void)per;
+    (void)group;
+    attention_flat<HS, PD_NT>(at, layer, 0, kvh, split, smem, [&]() { pd_wait(pz, PC_QKV, qkv_target); });
 }
 
 template <int WDT, int HS>
-__global__ void __launch_bounds__(PD_NT, 1) pdecode_kernel(const int splits, const int resident, const int want_logits) {
+__global__ void __launch_bounds__(PD_NT + 32, 1) pdecode_kernel(const int splits, const int resident, const int want_logits, const int act_bytes,
+                                                                 const int nslots) {
     PD_OPAQUE_ZERO(pz);
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ int s_last;
+    __shared__ __align__(8) uint64_t s_bars[2 * PD_MAX_SLOTS];
     const int tid = threadIdx.x;
     const int G = gridDim.x, cta = blockIdx.x;
+    PdRing R;
+    R.slots = smem + act_bytes, R.full = s_bars, R.empty = s_bars + PD_MAX_SLOTS, R.nslots = nslots;
+    const bool ring = nslots > 0;
+    if (ring && tid == 0) {
+        for (int i = 0; i < nslots; i++) pd_mbar_init(&R.full[i], 1), pd_mbar_init(&R.empty[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads(); // the only CTA-wide barrier that includes the producer warp
+    if (tid >= PD_NT) {
+        // ===== TMA producer: lane 0 walks the same phase sequence as the consumers, bounded only by free ring slots =====
+        if (ring && tid == PD_NT) {
+            const unsigned long long pol = l2_evict_first_policy();
+            unsigned g = 0;
+            const int nl = CP.layers;
+            const bool rE = pd_ring_phase<PH_QKV>(pz), rA = pd_ring_phase<PH_O>(pz), rH = pd_ring_phase<PH_DOWN>(pz);
+            for (int L = 0; L < nl; L++) {
+                if (rE) pd_produce<WDT, PH_QKV>(pz, L, R, g, pol);
+                if (rA) pd_produce<WDT, PH_O>(pz, L, R, g, pol);
+                if (rE) pd_produce<WDT, PH_GU>(pz, L, R, g, pol);
+                if (rH) pd_produce<WDT, PH_DOWN>(pz, L, R, g, pol);
+            }
+        }
+        return;
+    }
+    unsigned g = 0; // chunks of this CTA consumed from the ring so far (same sequence as the producer's)
+    const bool rE = ring && pd_ring_phase<PH_QKV>(pz), rA = ring && pd_ring_phase<PH_O>(pz), rH = ring && pd_ring_phase<PH_DOWN>(pz);
+    const bool regE = CP.E == 32 * PD_CHUNK_BLK, regA = CP.attn_seg == 32 * PD_CHUNK_BLK; // rows of exactly one chunk: activations in registers
     const unsigned long long epoch = pd_ld_volatile(CP.sync); // tokens decoded by this model so far
     const unsigned long long uG = (unsigned long long)G;
     const bool tp = CP.world > 1;
@@ -546,7 +863,10 @@ __global__ void __launch_bounds__(PD_NT, 1) pdecode_kernel(const int splits, con
         {
             const int dw = L == 0 ? PC_EMBED : PC_DOWN;
             const unsigned long long dt = L == 0 ? (epoch + 1) * uG : (use - 1) * uG;
-            if (lng_E) pd_gemv<WDT, PH_QKV, EPI_STORE, true>(pz, L, 0u, dw, dt, 1 + L * 8 + 0, smem);
+            if (rE) {
+                if (regE) pd_gemv_ring<WDT, PH_QKV, EPI_STORE, true>(pz, L, 0u, dw, dt, 1 + L * 8 + 0, smem, R, g);
+                else pd_gemv_ring<WDT, PH_QKV, EPI_STORE, false>(pz, L, 0u, dw, dt, 1 + L * 8 + 0, smem, R, g);
+            } else if (lng_E) pd_gemv<WDT, PH_QKV, EPI_STORE, true>(pz, L, 0u, dw, dt, 1 + L * 8 + 0, smem);
             else pd_gemv<WDT, PH_QKV, EPI_STORE, false>(pz, L, 0u, dw, dt, 1 + L * 8 + 0, smem);
             pd_arrive(pz, PC_QKV);
             pd_stamp(pz, 1 + L * 8 + 1);
@@ -557,7 +877,7 @@ __global__ void __launch_bounds__(PD_NT, 1) pdecode_kernel(const int splits, con
             pd_attention<HS>(pz, L, kvh, split, splits, false, use * uG, smem);
             bool signal = true;
             if (splits > 1) {
-                __syncthreads();
+                pd_cta_bar();
                 if (tid == 0) {
                     __threadfence();
                     unsigned *c = &CP.att_done[kvh];
@@ -566,11 +886,11 @@ __global__ void __launch_bounds__(PD_NT, 1) pdecode_kernel(const int splits, con
                     if (s_last) *c = 0;
                     __threadfence();
                 }
-                __syncthreads();
+                pd_cta_bar();
                 signal = s_last != 0;
                 if (signal) pd_attention<HS>(pz, L, kvh, split, splits, true, 0ull, smem);
             }
-            __syncthreads();
+            pd_cta_bar();
             if (signal && tid == 0) asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(CP.sync + PC_ATT) : "memory");
             pd_stamp(pz, 1 + L * 8 + 2);
         }
@@ -578,12 +898,18 @@ __global__ void __launch_bounds__(PD_NT, 1) pdecode_kernel(const int splits, con
         {
             const unsigned long long dt = use * (unsigned long long)CP.kv_heads;
             if (tp) {
-                if (lng_A) pd_gemv<WDT, PH_O, EPI_LL, true>(pz, L, tag_o, PC_ATT, dt, 1 + L * 8 + 3, smem);
+                if (rA) {
+                    if (regA) pd_gemv_ring<WDT, PH_O, EPI_LL, true>(pz, L, tag_o, PC_ATT, dt, 1 + L * 8 + 3, smem, R, g);
+                    else pd_gemv_ring<WDT, PH_O, EPI_LL, false>(pz, L, tag_o, PC_ATT, dt, 1 + L * 8 + 3, smem, R, g);
+                } else if (lng_A) pd_gemv<WDT, PH_O, EPI_LL, true>(pz, L, tag_o, PC_ATT, dt, 1 + L * 8 + 3, smem);
                 else pd_gemv<WDT, PH_O, EPI_LL, false>(pz, L, tag_o, PC_ATT, dt, 1 + L * 8 + 3, smem);
-                __syncthreads();
+                pd_cta_bar();
                 pd_ll_reduce<PH_O>(pz, tag_o, (float *)smem);
             } else {
-                if (lng_A) pd_gemv<WDT, PH_O, EPI_ADD_RESIDUAL, true>(pz, L, 0u, PC_ATT, dt, 1 + L * 8 + 3, smem);
+                if (rA) {
+                    if (regA) pd_gemv_ring<WDT, PH_O, EPI_ADD_RESIDUAL, true>(pz, L, 0u, PC_ATT, dt, 1 + L * 8 + 3, smem, R, g);
+                    else pd_gemv_ring<WDT, PH_O, EPI_ADD_RESIDUAL, false>(pz, L, 0u, PC_ATT, dt, 1 + L * 8 + 3, smem, R, g);
+                } else if (lng_A) pd_gemv<WDT, PH_O, EPI_ADD_RESIDUAL, true>(pz, L, 0u, PC_ATT, dt, 1 + L * 8 + 3, smem);
                 else pd_gemv<WDT, PH_O, EPI_ADD_RESIDUAL, false>(pz, L, 0u, PC_ATT, dt, 1 + L * 8 + 3, smem);
             }
             pd_arrive(pz, PC_O);
@@ -591,7 +917,10 @@ __global__ void __launch_bounds__(PD_NT, 1) pdecode_kernel(const int splits, con
         }
         // ---- gate / up: RMSNorm(xb) -> Q8 -> silu(gate) * up ----
         {
-            if (lng_E) pd_gemv<WDT, PH_GU, EPI_SILU_MUL, true>(pz, L, 0u, PC_O, use * uG, 1 + L * 8 + 5, smem);
+            if (rE) {
+                if (regE) pd_gemv_ring<WDT, PH_GU, EPI_SILU_MUL, true>(pz, L, 0u, PC_O, use * uG, 1 + L * 8 + 5, smem, R, g);
+                else pd_gemv_ring<WDT, PH_GU, EPI_SILU_MUL, false>(pz, L, 0u, PC_O, use * uG, 1 + L * 8 + 5, smem, R, g);
+            } else if (lng_E) pd_gemv<WDT, PH_GU, EPI_SILU_MUL, true>(pz, L, 0u, PC_O, use * uG, 1 + L * 8 + 5, smem);
             else pd_gemv<WDT, PH_GU, EPI_SILU_MUL, false>(pz, L, 0u, PC_O, use * uG, 1 + L * 8 + 5, smem);
             pd_arrive(pz, PC_GU);
             pd_stamp(pz, 1 + L * 8 + 6);
@@ -599,12 +928,14 @@ __global__ void __launch_bounds__(PD_NT, 1) pdecode_kernel(const int splits, con
         // ---- down_proj: Q8(h) -> xb + down ----
         {
             if (tp) {
-                if (lng_H) pd_gemv<WDT, PH_DOWN, EPI_LL, true>(pz, L, tag_d, PC_GU, use * uG, 1 + L * 8 + 7, smem);
+                if (rH) pd_gemv_ring<WDT, PH_DOWN, EPI_LL, false>(pz, L, tag_d, PC_GU, use * uG, 1 + L * 8 + 7, smem, R, g);
+                else if (lng_H) pd_gemv<WDT, PH_DOWN, EPI_LL, true>(pz, L, tag_d, PC_GU, use * uG, 1 + L * 8 + 7, smem);
                 else pd_gemv<WDT, PH_DOWN, EPI_LL, false>(pz, L, tag_d, PC_GU, use * uG, 1 + L * 8 + 7, smem);
-                __syncthreads();
+                pd_cta_bar();
                 pd_ll_reduce<PH_DOWN>(pz, tag_d, (float *)smem);
             } else {
-                if (lng_H) pd_gemv<WDT, PH_DOWN, EPI_ADD_RESIDUAL, true>(pz, L, 0u, PC_GU, use * uG, 1 + L * 8 + 7, smem);
+                if (rH) pd_gemv_ring<WDT, PH_DOWN, EPI_ADD_RESIDUAL, false>(pz, L, 0u, PC_GU, use * uG, 1 + L * 8 + 7, smem, R, g);
+                else if (lng_H) pd_gemv<WDT, PH_DOWN, EPI_ADD_RESIDUAL, true>(pz, L, 0u, PC_GU, use * uG, 1 + L * 8 + 7, smem);
                 else pd_gemv<WDT, PH_DOWN, EPI_ADD_RESIDUAL, false>(pz, L, 0u, PC_GU, use * uG, 1 + L * 8 + 7, smem);
             }
             pd_arrive(pz, PC_DOWN);
@@ -690,10 +1021,8 @@ static size_t pd_smem_bytes(const PdParams &p) {
     const size_t lm = (size_t)p.E * 4;
     if (lm > acts) acts = lm;
     const int hs = p.head_size;
-    size_t att = hs == 32 ? attention_task_smem<32, PD_NT>() : (hs == 64 ? attention_task_smem<64, PD_NT>() : attention_task_smem<128, PD_NT>());
+    size_t att = hs == 32 ? attention_flat_smem<32, PD_NT>() : (hs == 64 ? attention_flat_smem<64, PD_NT>() : attention_flat_smem<128, PD_NT>());
     att += 1024; // merge factors
-    const size_t flat = hs == 32 ? attention_flat_smem<32, PD_NT>() : (hs == 64 ? attention_flat_smem<64, PD_NT>() : attention_flat_smem<128, PD_NT>());
-    if (flat > att) att = flat;
     size_t m = acts > att ? acts : att;
     const size_t red = (size_t)((p.E + G - 1) / G + 2) * PD_MAX_TP * 4;
     if (red > m) m = red;
@@ -708,7 +1037,10 @@ bool jl_pdecode_supported(const PdParams &p, int w_dtype, int grid) {
     if (p.E > 16 * PD_NT) return false;        // RMSNorm prologue keeps the row in registers (16 floats per thread)
     if (p.kv_heads * 1 > grid) return false;
     if (p.world > PD_MAX_TP || p.layers > PD_MAX_LAYERS) return false;
-    if (PD_NT % p.head_size) return false;
+    {
+        const int group = p.heads / p.kv_heads;
+        if (group & (group - 1)) return false; // flat attention: power-of-two head groups
+    }
     return pd_smem_bytes(p) <= 200 * 1024;
 }
 
@@ -724,12 +1056,19 @@ void jl_pdecode_forget(int device, const void *owner) {
 template <int WDT, int HS>
 static int launch_pd(jl_ctx *ctx, cudaStream_t stream, const PdParams &p) {
     auto kern = pdecode_kernel<WDT, HS>;
-    const size_t smem = pd_smem_bytes(p);
+    const size_t act = pd_smem_bytes(p);
+    // the ring takes what is left of the 227 KB: at least 24 slots or none (JL_PD_RING=0 disables it)
+    static const int ring_env = getenv("JL_PD_RING") ? atoi(getenv("JL_PD_RING")) : 1;
+    const size_t budget = 224 * 1024 - 2048;
+    int nslots = ring_env && budget > act ? (int)((budget - act) / RingCfg<WDT>::SLOT) : 0;
+    if (nslots > PD_MAX_SLOTS) nslots = PD_MAX_SLOTS;
+    if (nslots < 24) nslots = 0;
+    const size_t smem = act + (size_t)nslots * RingCfg<WDT>::SLOT;
     static size_t configured[JL_MAX_DEVICES] = {};
     JL_CUDA_CHECK(ctx, jl_ensure_dyn_smem(kern, ctx->device, smem, configured));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ctx->sm_count);
-    cfg.blockDim = dim3(PD_NT);
+    cfg.blockDim = dim3(PD_NT + 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -737,7 +1076,7 @@ static int launch_pd(jl_ctx *ctx, cudaStream_t stream, const PdParams &p) {
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    JL_CUDA_CHECK(ctx, cudaLaunchKernelEx(&cfg, kern, p.splits, p.resident, p.want_logits));
+    JL_CUDA_CHECK(ctx, cudaLaunchKernelEx(&cfg, kern, p.splits, p.resident, p.want_logits, (int)act, nslots));
     ctx->launches++;
     return JL_OK;
 }

@@ -3,7 +3,7 @@
 #include "jl_common.cuh"
 
 #ifndef PD_THREADS
-#define PD_THREADS 512
+#define PD_THREADS 480 // consumer threads (15 warps); + one TMA producer warp = 512 threads per CTA, 128 registers each
 #endif
 #define PD_MAX_TP 8
 #define PD_SYNC_WORDS 32 // u64 words: [0] epoch, [1] status (0 ok, else the phase id that timed out), [8..] barrier counters
