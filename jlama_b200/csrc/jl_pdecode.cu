@@ -366,17 +366,24 @@ __device__ PD_PHASE_FN void pd_gemv(const int, const int L, const uint32_t tag, 
 // variant read activations from shared memory as well and was shared-memory-bandwidth bound).
 // A chunk = 128 consecutive blocks of the CTA's row range (rows are contiguous in memory, so are their scales).
 // ======================================================================================================================
+// Chunks travel in GROUPS of PD_GRP consecutive chunks of one tensor: one bulk copy for the group's weights, one for its scales
+// (a single producer lane issuing two 2.5 KB copies per chunk topped out at 1.5 TB/s), one full / one empty barrier per group.
 #define PD_CHUNK_BLK 128
+#define PD_GRP 4
+#define PD_PRODUCER_LANES 4
 template <int WDT>
 struct RingCfg {
     static constexpr int WB = (WDT == JL_Q4) ? 16 : 32;
-    static constexpr int SLOT = PD_CHUNK_BLK * WB + PD_CHUNK_BLK * 4; // weights then scales
+    static constexpr int CHW = PD_CHUNK_BLK * WB;  // weight bytes of a chunk
+    static constexpr int CHS = PD_CHUNK_BLK * 4;   // scale bytes of a chunk
+    static constexpr int SLOT = CHW + CHS;         // shared memory per chunk slot
 };
 #define PD_MAX_SLOTS 64
 struct PdRing {
-    unsigned char *slots; // [nslots][SLOT]
-    uint64_t *full, *empty; // mbarriers
-    int nslots;
+    unsigned char *w;  // [ngroups * PD_GRP][CHW]   weights of consecutive slots are contiguous
+    unsigned char *s;  // [ngroups * PD_GRP][CHS]
+    uint64_t *full, *empty; // mbarriers per group
+    int ngroups;
 };
 __device__ __forceinline__ uint32_t pd_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void pd_mbar_init(uint64_t *bar, uint32_t count) {
@@ -422,17 +429,19 @@ struct PdPiece {
     const float *s;
     int blocks;       // rows * nblk
     int chunk0;       // first chunk of the piece in the CTA's chunk sequence of this phase
+    int group0;       // first group of the piece in the CTA's group sequence of this phase
     int slot0;        // row slot (index into the CTA's partial-sum table) of the piece's first row
     int row0;         // first row, local to the segment (QKV: row inside q / k / v; gate/up: row inside H)
     int seg;          // QKV: 0 q, 1 k, 2 v; gate/up: 0 gate, 1 up; else 0
 };
 template <int WDT, int PH>
-__device__ __forceinline__ int pd_pieces(const int pz, const int L, const int cta_id, const int ncta, PdPiece (&pc)[3], int &nrows_out) {
+__device__ __forceinline__ int pd_pieces(const int pz, const int L, const int cta_id, const int ncta, PdPiece (&pc)[3], int &nrows_out,
+                                         int &ngroups_out) {
     constexpr int WB = RingCfg<WDT>::WB;
     const int nblk = ph_K<PH>(pz) / 32;
     const int R0 = (int)(((long long)ph_rows<PH>(pz) * cta_id) / ncta);
     const int R1 = (int)(((long long)ph_rows<PH>(pz) * (cta_id + 1)) / ncta);
-    int np = 0, chunk = 0;
+    int np = 0, chunk = 0, group = 0;
     auto add = [&](int seg, int r0, int r1, int slot0) { // rows [r0, r1) of segment `seg`
         if (r1 <= r0) return;
         const uint8_t *w;
@@ -442,10 +451,13 @@ __device__ __forceinline__ int pd_pieces(const int pz, const int L, const int ct
         pc[np].s = sc + (size_t)r0 * nblk;
         pc[np].blocks = (r1 - r0) * nblk;
         pc[np].chunk0 = chunk;
+        pc[np].group0 = group;
         pc[np].slot0 = slot0;
         pc[np].row0 = r0;
         pc[np].seg = seg;
-        chunk += (pc[np].blocks + PD_CHUNK_BLK - 1) / PD_CHUNK_BLK;
+        const int nch = (pc[np].blocks + PD_CHUNK_BLK - 1) / PD_CHUNK_BLK;
+        chunk += nch;
+        group += (nch + PD_GRP - 1) / PD_GRP;
         np++;
     };
     if (PH == PH_QKV) {
@@ -459,8 +471,9 @@ __device__ __forceinline__ int pd_pieces(const int pz, const int L, const int ct
     } else {
         add(0, R0, R1, 0);
     }
-    for (int i = np; i < 3; i++) pc[i].blocks = 0, pc[i].chunk0 = chunk;
+    for (int i = np; i < 3; i++) pc[i].blocks = 0, pc[i].chunk0 = chunk, pc[i].group0 = group;
     nrows_out = R1 - R0;
+    ngroups_out = group;
     return chunk; // chunks of this CTA in this phase
 }
 // is the ring usable for a phase?  (32-lane groups of a chunk must not straddle rows)
@@ -470,28 +483,32 @@ __device__ __forceinline__ bool pd_ring_phase(const int pz) {
     return (nblk % 32) == 0;
 }
 
-// ---- producer: one lane streams the chunks of one phase ----
+// ---- producer: PD_PRODUCER_LANES lanes stream the groups of one phase (lane = group index mod lanes) ----
 template <int WDT, int PH>
-__device__ __forceinline__ void pd_produce(const int pz, const int L, const PdRing &R, unsigned &g, const unsigned long long pol) {
-    constexpr int WB = RingCfg<WDT>::WB, SLOT = RingCfg<WDT>::SLOT;
+__device__ __forceinline__ void pd_produce(const int pz, const int L, const PdRing &R, unsigned &g, const unsigned long long pol, const int plane) {
+    constexpr int WB = RingCfg<WDT>::WB, CHW = RingCfg<WDT>::CHW, CHS = RingCfg<WDT>::CHS;
     PdPiece pc[3];
-    int nrows;
-    const int total = pd_pieces<WDT, PH>(pz, L, blockIdx.x, gridDim.x, pc, nrows);
+    int nrows, ngroups;
+    pd_pieces<WDT, PH>(pz, L, blockIdx.x, gridDim.x, pc, nrows, ngroups);
 #pragma unroll 1
     for (int i = 0; i < 3; i++) {
         const int nch = (pc[i].blocks + PD_CHUNK_BLK - 1) / PD_CHUNK_BLK;
+        const int ngr = (nch + PD_GRP - 1) / PD_GRP;
 #pragma unroll 1
-        for (int c = 0; c < nch; c++, g++) {
-            const unsigned slot = g % (unsigned)R.nslots, par = (g / (unsigned)R.nslots) & 1u;
-            if (!pd_mbar_wait(pz, &R.empty[slot], par ^ 1u, 300)) return;
-            const int nb = min(PD_CHUNK_BLK, pc[i].blocks - c * PD_CHUNK_BLK);
-            unsigned char *dst = R.slots + (size_t)slot * SLOT;
-            pd_mbar_expect_tx(&R.full[slot], (uint32_t)nb * (WB + 4));
-            pd_tma_load(dst, pc[i].w + (size_t)c * PD_CHUNK_BLK * WB, (uint32_t)nb * WB, &R.full[slot], pol);
-            pd_tma_load(dst + PD_CHUNK_BLK * WB, pc[i].s + (size_t)c * PD_CHUNK_BLK, (uint32_t)nb * 4, &R.full[slot], pol);
+        for (int gr = 0; gr < ngr; gr++) {
+            const unsigned gg = g + (unsigned)(pc[i].group0 + gr);
+            if ((int)(gg % PD_PRODUCER_LANES) != plane) continue;
+            const unsigned gslot = gg % (unsigned)R.ngroups, par = (gg / (unsigned)R.ngroups) & 1u;
+            if (!pd_mbar_wait(pz, &R.empty[gslot], par ^ 1u, 300)) return;
+            const int c0 = gr * PD_GRP, k = min(PD_GRP, nch - c0);
+            const int nb = min(k * PD_CHUNK_BLK, pc[i].blocks - c0 * PD_CHUNK_BLK);
+            for (int q = k; q < PD_GRP; q++) pd_mbar_arrive(&R.empty[gslot]); // chunks this group does not have
+            pd_mbar_expect_tx(&R.full[gslot], (uint32_t)nb * (WB + 4));
+            pd_tma_load(R.w + (size_t)gslot * PD_GRP * CHW, pc[i].w + (size_t)c0 * CHW, (uint32_t)nb * WB, &R.full[gslot], pol);
+            pd_tma_load(R.s + (size_t)gslot * PD_GRP * CHS, pc[i].s + (size_t)c0 * PD_CHUNK_BLK, (uint32_t)nb * 4, &R.full[gslot], pol);
         }
     }
-    (void)total;
+    g += (unsigned)ngroups;
 }
 
 // ---- consumer: one GEMV phase fed from the ring ----
@@ -503,14 +520,14 @@ __device__ PD_PHASE_FN void pd_gemv_ring(const int, const int L, const uint32_t 
     PD_OPAQUE_ZERO(pz);
     constexpr int NT = PD_NT, NWARP = PD_NWARP;
     constexpr bool NORM = PH == PH_QKV || PH == PH_GU;
-    constexpr int WB = RingCfg<WDT>::WB, SLOT = RingCfg<WDT>::SLOT;
+    constexpr int WB = RingCfg<WDT>::WB, CHW = RingCfg<WDT>::CHW, CHS = RingCfg<WDT>::CHS;
     int tid = threadIdx.x, cta_id = blockIdx.x, ncta = gridDim.x;
     asm volatile("" : "+r"(tid), "+r"(cta_id), "+r"(ncta));
     const int lane = tid & 31, warp = tid >> 5;
     const int K = ph_K<PH>(pz), nblk = K / 32;
     PdPiece pc[3];
-    int nrows;
-    const int total = pd_pieces<WDT, PH>(pz, L, cta_id, ncta, pc, nrows);
+    int nrows, ngroups;
+    const int total = pd_pieces<WDT, PH>(pz, L, cta_id, ncta, pc, nrows, ngroups);
     const int maxp = nblk / PD_CHUNK_BLK + 2; // partial sums per row (chunks that touch a row)
     pd_wait(pz, dep_which, dep_target);
     pd_stamp(pz, stamp_idx);
@@ -549,10 +566,11 @@ __device__ PD_PHASE_FN void pd_gemv_ring(const int, const int L, const uint32_t 
         const int pi = c >= pc[2].chunk0 && pc[2].blocks > 0 ? 2 : (c >= pc[1].chunk0 && pc[1].blocks > 0 ? 1 : 0);
         const int cc = c - pc[pi].chunk0;
         const int nb = min(PD_CHUNK_BLK, pc[pi].blocks - cc * PD_CHUNK_BLK);
-        const unsigned gg = g + (unsigned)c, slot = gg % (unsigned)R.nslots, par = (gg / (unsigned)R.nslots) & 1u;
-        const unsigned char *sw = R.slots + (size_t)slot * SLOT;
-        const float *ss = (const float *)(sw + PD_CHUNK_BLK * WB);
-        pd_mbar_wait(pz, &R.full[slot], par, 400);
+        const unsigned gg = g + (unsigned)(pc[pi].group0 + cc / PD_GRP), gslot = gg % (unsigned)R.ngroups, par = (gg / (unsigned)R.ngroups) & 1u;
+        const unsigned cslot = gslot * PD_GRP + (unsigned)(cc % PD_GRP);
+        const unsigned char *sw = R.w + (size_t)cslot * CHW;
+        const float *ss = (const float *)(R.s + (size_t)cslot * CHS);
+        pd_mbar_wait(pz, &R.full[gslot], par, 400);
         float acc = 0.0f;
         int cur_row = (cc * PD_CHUNK_BLK) / nblk; // row inside the piece
 #pragma unroll
@@ -609,9 +627,9 @@ __device__ PD_PHASE_FN void pd_gemv_ring(const int, const int L, const uint32_t 
             if (lane == 0) parts[(pc[pi].slot0 + cur_row) * maxp + (cc - (cur_row * nblk) / PD_CHUNK_BLK)] = v;
         }
         __syncwarp();
-        if (lane == 0) pd_mbar_arrive(&R.empty[slot]);
+        if (lane == 0) pd_mbar_arrive(&R.empty[gslot]);
     }
-    g += (unsigned)total;
+    g += (unsigned)ngroups;
     pd_cta_bar();
     // ---- per-row pass: partial sums in chunk order, fused epilogue ----
     const int npr = (nblk + PD_CHUNK_BLK - 1) / PD_CHUNK_BLK; // chunks of an aligned row
@@ -811,25 +829,27 @@ __global__ void __launch_bounds__(PD_NT + 32, 1) pdecode_kernel(const int splits
     const int tid = threadIdx.x;
     const int G = gridDim.x, cta = blockIdx.x;
     PdRing R;
-    R.slots = smem + act_bytes, R.full = s_bars, R.empty = s_bars + PD_MAX_SLOTS, R.nslots = nslots;
-    const bool ring = nslots > 0;
+    R.ngroups = nslots / PD_GRP;
+    R.w = smem + act_bytes, R.s = R.w + (size_t)R.ngroups * PD_GRP * RingCfg<WDT>::CHW, R.full = s_bars, R.empty = s_bars + PD_MAX_SLOTS;
+    const bool ring = R.ngroups > 0;
     if (ring && tid == 0) {
-        for (int i = 0; i < nslots; i++) pd_mbar_init(&R.full[i], 1), pd_mbar_init(&R.empty[i], 1);
+        for (int i = 0; i < R.ngroups; i++) pd_mbar_init(&R.full[i], 1), pd_mbar_init(&R.empty[i], PD_GRP);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads(); // the only CTA-wide barrier that includes the producer warp
     if (tid >= PD_NT) {
         // ===== TMA producer: lane 0 walks the same phase sequence as the consumers, bounded only by free ring slots =====
-        if (ring && tid == PD_NT) {
+        if (ring && tid < PD_NT + PD_PRODUCER_LANES) {
+            const int plane = tid - PD_NT;
             const unsigned long long pol = l2_evict_first_policy();
             unsigned g = 0;
             const int nl = CP.layers;
             const bool rE = pd_ring_phase<PH_QKV>(pz), rA = pd_ring_phase<PH_O>(pz), rH = pd_ring_phase<PH_DOWN>(pz);
             for (int L = 0; L < nl; L++) {
-                if (rE) pd_produce<WDT, PH_QKV>(pz, L, R, g, pol);
-                if (rA) pd_produce<WDT, PH_O>(pz, L, R, g, pol);
-                if (rE) pd_produce<WDT, PH_GU>(pz, L, R, g, pol);
-                if (rH) pd_produce<WDT, PH_DOWN>(pz, L, R, g, pol);
+                if (rE) pd_produce<WDT, PH_QKV>(pz, L, R, g, pol, plane);
+                if (rA) pd_produce<WDT, PH_O>(pz, L, R, g, pol, plane);
+                if (rE) pd_produce<WDT, PH_GU>(pz, L, R, g, pol, plane);
+                if (rH) pd_produce<WDT, PH_DOWN>(pz, L, R, g, pol, plane);
             }
         }
         return;
@@ -1062,6 +1082,7 @@ static int launch_pd(jl_ctx *ctx, cudaStream_t stream, const PdParams &p) {
     const size_t budget = 224 * 1024 - 2048;
     int nslots = ring_env && budget > act ? (int)((budget - act) / RingCfg<WDT>::SLOT) : 0;
     if (nslots > PD_MAX_SLOTS) nslots = PD_MAX_SLOTS;
+    nslots -= nslots % PD_GRP;
     if (nslots < 24) nslots = 0;
     const size_t smem = act + (size_t)nslots * RingCfg<WDT>::SLOT;
     static size_t configured[JL_MAX_DEVICES] = {};
