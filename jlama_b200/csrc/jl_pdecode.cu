@@ -561,70 +561,86 @@ __device__ PD_PHASE_FN void pd_gemv_ring(const int, const int L, const uint32_t 
             asum_r[j] = asum[bi];
         }
     }
+    // nibble dot product of one Q4 block against a Q8 activation block: low nibbles as they are, high nibbles left in place
+    // (16 * nibble as an unsigned byte) and the factor 16 shifted out of the sum at the end -- exact, and four shifts fewer per block
+    auto q4_dot = [](const uint4 q, const uint4 xlo, const uint4 xhi, const int xsum) -> int {
+        int lo = 0, hi = 0;
+        lo = __dp4a((int)(q.x & 0x0F0F0F0Fu), (int)xlo.x, lo);
+        lo = __dp4a((int)(q.y & 0x0F0F0F0Fu), (int)xlo.y, lo);
+        lo = __dp4a((int)(q.z & 0x0F0F0F0Fu), (int)xlo.z, lo);
+        lo = __dp4a((int)(q.w & 0x0F0F0F0Fu), (int)xlo.w, lo);
+        asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(hi) : "r"(q.x & 0xF0F0F0F0u), "r"(xhi.x));
+        asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(hi) : "r"(q.y & 0xF0F0F0F0u), "r"(xhi.y));
+        asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(hi) : "r"(q.z & 0xF0F0F0F0u), "r"(xhi.z));
+        asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(hi) : "r"(q.w & 0xF0F0F0F0u), "r"(xhi.w));
+        return lo + (hi >> 4) - 8 * xsum; // sum a*(nib-8) = sum a*nib - 8*sum a   (exact)
+    };
+    auto i8_dot = [](const uint4 q0, const uint4 q1, const uint4 xlo, const uint4 xhi) -> int {
+        int sd = 0;
+        sd = __dp4a((int)q0.x, (int)xlo.x, sd);
+        sd = __dp4a((int)q0.y, (int)xlo.y, sd);
+        sd = __dp4a((int)q0.z, (int)xlo.z, sd);
+        sd = __dp4a((int)q0.w, (int)xlo.w, sd);
+        sd = __dp4a((int)q1.x, (int)xhi.x, sd);
+        sd = __dp4a((int)q1.y, (int)xhi.y, sd);
+        sd = __dp4a((int)q1.z, (int)xhi.z, sd);
+        sd = __dp4a((int)q1.w, (int)xhi.w, sd);
+        return sd;
+    };
     for (int c = warp; c < total; c += NWARP) {
-        // piece of this chunk
-        const int pi = c >= pc[2].chunk0 && pc[2].blocks > 0 ? 2 : (c >= pc[1].chunk0 && pc[1].blocks > 0 ? 1 : 0);
-        const int cc = c - pc[pi].chunk0;
-        const int nb = min(PD_CHUNK_BLK, pc[pi].blocks - cc * PD_CHUNK_BLK);
-        const unsigned gg = g + (unsigned)(pc[pi].group0 + cc / PD_GRP), gslot = gg % (unsigned)R.ngroups, par = (gg / (unsigned)R.ngroups) & 1u;
+        // piece of this chunk (compact pieces; at most three)
+        int pi = 0;
+        if (pc[1].blocks > 0 && c >= pc[1].chunk0) pi = 1;
+        if (pc[2].blocks > 0 && c >= pc[2].chunk0) pi = 2;
+        const int p_chunk0 = pi == 0 ? pc[0].chunk0 : (pi == 1 ? pc[1].chunk0 : pc[2].chunk0);
+        const int p_group0 = pi == 0 ? pc[0].group0 : (pi == 1 ? pc[1].group0 : pc[2].group0);
+        const int p_blocks = pi == 0 ? pc[0].blocks : (pi == 1 ? pc[1].blocks : pc[2].blocks);
+        const int p_slot0 = pi == 0 ? pc[0].slot0 : (pi == 1 ? pc[1].slot0 : pc[2].slot0);
+        const int cc = c - p_chunk0;
+        const int nb = min(PD_CHUNK_BLK, p_blocks - cc * PD_CHUNK_BLK);
+        const unsigned gg = g + (unsigned)(p_group0 + cc / PD_GRP), gslot = gg % (unsigned)R.ngroups, par = (gg / (unsigned)R.ngroups) & 1u;
         const unsigned cslot = gslot * PD_GRP + (unsigned)(cc % PD_GRP);
         const unsigned char *sw = R.w + (size_t)cslot * CHW;
         const float *ss = (const float *)(R.s + (size_t)cslot * CHS);
         pd_mbar_wait(pz, &R.full[gslot], par, 400);
         float acc = 0.0f;
-        int cur_row = (cc * PD_CHUNK_BLK) / nblk; // row inside the piece
+        if (ACTREG) {
+            // one row per chunk: block j*32 + lane against the register-resident activation block j
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (j * 32 < nb) { // uniform
-                const int gb0 = cc * PD_CHUNK_BLK + j * 32;
-                const int row = gb0 / nblk, col0 = gb0 - row * nblk;
-                if (row != cur_row) { // uniform: the previous row ends inside this chunk
-                    const float v = warp_sum(acc);
-                    if (lane == 0) parts[(pc[pi].slot0 + cur_row) * maxp + (cc - (cur_row * nblk) / PD_CHUNK_BLK)] = v;
-                    acc = 0.0f, cur_row = row;
-                }
+            for (int j = 0; j < 4; j++) {
                 const int bl = j * 32 + lane;
                 const float sb = ss[bl];
-                uint4 xlo, xhi;
-                float xs;
-                int xsum;
-                if (ACTREG) {
-                    xlo = alo[j], xhi = ahi[j], xs = asc_r[j], xsum = asum_r[j];
-                } else {
-                    const int bi = col0 + lane;
-                    xlo = *(const uint4 *)(aq + (size_t)bi * 16);
-                    xhi = *(const uint4 *)(aq + ((size_t)nblk + bi) * 16);
-                    xs = asc[bi], xsum = asum[bi];
-                }
-                int sdot = 0;
-                if (WDT == JL_Q4) {
-                    const uint4 q = *(const uint4 *)(sw + (size_t)bl * 16);
-                    sdot = __dp4a((int)(q.x & 0x0F0F0F0Fu), (int)xlo.x, sdot);
-                    sdot = __dp4a((int)((q.x >> 4) & 0x0F0F0F0Fu), (int)xhi.x, sdot);
-                    sdot = __dp4a((int)(q.y & 0x0F0F0F0Fu), (int)xlo.y, sdot);
-                    sdot = __dp4a((int)((q.y >> 4) & 0x0F0F0F0Fu), (int)xhi.y, sdot);
-                    sdot = __dp4a((int)(q.z & 0x0F0F0F0Fu), (int)xlo.z, sdot);
-                    sdot = __dp4a((int)((q.z >> 4) & 0x0F0F0F0Fu), (int)xhi.z, sdot);
-                    sdot = __dp4a((int)(q.w & 0x0F0F0F0Fu), (int)xlo.w, sdot);
-                    sdot = __dp4a((int)((q.w >> 4) & 0x0F0F0F0Fu), (int)xhi.w, sdot);
-                    sdot -= 8 * xsum; // sum a*(nib-8) = sum a*nib - 8*sum a   (exact)
-                } else {
-                    const uint4 q0 = *(const uint4 *)(sw + (size_t)bl * 32), q1 = *(const uint4 *)(sw + (size_t)bl * 32 + 16);
-                    sdot = __dp4a((int)q0.x, (int)xlo.x, sdot);
-                    sdot = __dp4a((int)q0.y, (int)xlo.y, sdot);
-                    sdot = __dp4a((int)q0.z, (int)xlo.z, sdot);
-                    sdot = __dp4a((int)q0.w, (int)xlo.w, sdot);
-                    sdot = __dp4a((int)q1.x, (int)xhi.x, sdot);
-                    sdot = __dp4a((int)q1.y, (int)xhi.y, sdot);
-                    sdot = __dp4a((int)q1.z, (int)xhi.z, sdot);
-                    sdot = __dp4a((int)q1.w, (int)xhi.w, sdot);
-                }
-                acc = fmaf(__fmul_rn(xs, sb), (float)sdot, acc); // acc += (sa*sb) * isum   (vector_simd.c:384-420)
+                int sdot;
+                if (WDT == JL_Q4) sdot = q4_dot(*(const uint4 *)(sw + (size_t)bl * 16), alo[j], ahi[j], asum_r[j]);
+                else sdot = i8_dot(*(const uint4 *)(sw + (size_t)bl * 32), *(const uint4 *)(sw + (size_t)bl * 32 + 16), alo[j], ahi[j]);
+                acc = fmaf(__fmul_rn(asc_r[j], sb), (float)sdot, acc); // acc += (sa*sb) * isum   (vector_simd.c:384-420)
             }
-        }
-        {
             const float v = warp_sum(acc);
-            if (lane == 0) parts[(pc[pi].slot0 + cur_row) * maxp + (cc - (cur_row * nblk) / PD_CHUNK_BLK)] = v;
+            if (lane == 0) parts[(p_slot0 + cc) * maxp] = v;
+        } else {
+            int cur_row = (cc * PD_CHUNK_BLK) / nblk;           // row inside the piece
+            int row_end = (cur_row + 1) * nblk;                 // first block of the next row
+            int first_chunk = (cur_row * nblk) / PD_CHUNK_BLK;  // first chunk that touches cur_row
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (j * 32 < nb) { // uniform
+                    const int gb0 = cc * PD_CHUNK_BLK + j * 32;
+                    if (gb0 >= row_end) { // uniform: the previous row ended inside this chunk
+                        const float v = warp_sum(acc);
+                        if (lane == 0) parts[(p_slot0 + cur_row) * maxp + (cc - first_chunk)] = v;
+                        acc = 0.0f, cur_row++, first_chunk = cc, row_end += nblk;
+                    }
+                    const int bl = j * 32 + lane, bi = gb0 - (row_end - nblk) + lane;
+                    const float sb = ss[bl];
+                    const uint4 xlo = *(const uint4 *)(aq + (size_t)bi * 16), xhi = *(const uint4 *)(aq + ((size_t)nblk + bi) * 16);
+                    int sdot;
+                    if (WDT == JL_Q4) sdot = q4_dot(*(const uint4 *)(sw + (size_t)bl * 16), xlo, xhi, asum[bi]);
+                    else sdot = i8_dot(*(const uint4 *)(sw + (size_t)bl * 32), *(const uint4 *)(sw + (size_t)bl * 32 + 16), xlo, xhi);
+                    acc = fmaf(__fmul_rn(asc[bi], sb), (float)sdot, acc);
+                }
+            }
+            const float v = warp_sum(acc);
+            if (lane == 0) parts[(p_slot0 + cur_row) * maxp + (cc - first_chunk)] = v;
         }
         __syncwarp();
         if (lane == 0) pd_mbar_arrive(&R.empty[gslot]);
