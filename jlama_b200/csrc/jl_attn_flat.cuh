@@ -47,7 +47,7 @@ __device__ __forceinline__ void attention_flat(const AttnTask &P, const int laye
     float *wsum = wmax + NW * MG_MAX_GROUP;         // [NW][MAX_GROUP]
     float *comb = wsum + NW * MG_MAX_GROUP;         // [NW][FA_HPASS][HS]
 
-    const int session = P.sessions[m], pos = P.positions[m];
+    const int session = P.sessions[m], pos = __ldcg(P.positions + m); // the position may have been advanced inside this launch
     const int n = pos + 1, Sp = P.splits;
     const int per = (((n + Sp - 1) / Sp) + 31) / 32 * 32;
     const int t0 = split * per, t1 = min(n, t0 + per);

@@ -395,8 +395,8 @@ extern "C" int jl_model_finalize(jl_model *m) {
                 }
             }
             if (getenv("JL_PD_TRACE")) {
-                M_CHECK(dev_alloc(ctx, (void **)&m->pd_trace, ((size_t)c.num_layers * 8 + 16) * 8));
-                JL_CUDA_CHECK(ctx, cudaMemset(m->pd_trace, 0, ((size_t)c.num_layers * 8 + 16) * 8));
+                M_CHECK(dev_alloc(ctx, (void **)&m->pd_trace, ((size_t)c.num_layers * 16 + 32) * 8));
+                JL_CUDA_CHECK(ctx, cudaMemset(m->pd_trace, 0, ((size_t)c.num_layers * 16 + 32) * 8));
             }
             m->pd_ok = true;
             // per-token stream of this rank: the lm_head is vocabulary-sharded on the persistent path
@@ -897,6 +897,8 @@ static void fill_pd(jl_model *m, int max_pos, bool resident, bool want_logits, P
     if (s > m->max_splits) s = m->max_splits;
     if (s < 1) s = 1;
     p.splits = s;
+    p.split_cap = cap < m->max_splits ? cap : m->max_splits;
+    p.ntok = 1;
     p.world = c.tp_size, p.rank = c.tp_rank;
     for (int r = 0; r < c.tp_size && r < PD_MAX_TP; r++)
         p.ll_o[r] = m->peer_ll_o[r], p.ll_d[r] = m->peer_ll_d[r], p.ll_a[r] = m->peer_ll_a[r], p.logits_peer[r] = m->peer_logits[r];
@@ -916,11 +918,12 @@ static int pd_check(jl_model *m) {
 }
 
 // run the decode body through the persistent kernel (one session), a cached CUDA graph, or eagerly
-static int run_decode(jl_model *m, int n, int max_pos, bool resident, bool want_logits = false) {
+static int run_decode(jl_model *m, int n, int max_pos, bool resident, bool want_logits = false, int ntok = 1) {
     jl_ctx *ctx = m->ctx;
     if (n == 1 && use_pd(m)) {
         PdParams pp;
         fill_pd(m, max_pos, resident, want_logits, pp);
+        pp.ntok = resident ? ntok : 1;
         return jl_launch_pdecode(ctx, m->stream, pp, m->pd_layers.data(), m, m->pd_wdtype);
     }
     // fused decode attention: one split per 64 positions, bucketed so that few graphs are captured
@@ -1061,8 +1064,13 @@ extern "C" int jl_model_decode_resident(jl_model *m, int session, int32_t first_
     JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_counter, hp + 3 * m->maxB, 4, cudaMemcpyHostToDevice, m->stream));
     JL_CUDA_CHECK(ctx, cudaEventRecord(m->ev_begin, m->stream));
     double gemv = 0;
-    for (int i = 0; i < n_new; i++) {
-        M_CHECK(run_decode(m, 1, start_pos + i, true));
+    // persistent kernel: up to PD_TOKENS_PER_LAUNCH tokens per cooperative launch (the fed-back token crosses a grid barrier
+    // instead of a kernel boundary); other paths: one graph replay per token
+    static const int tpl_env = getenv("JL_PD_TOKENS") ? atoi(getenv("JL_PD_TOKENS")) : 16;
+    const int tpl = use_pd(m) && tpl_env > 1 ? tpl_env : 1;
+    for (int i = 0; i < n_new; i += tpl) {
+        const int nt = n_new - i < tpl ? n_new - i : tpl;
+        M_CHECK(run_decode(m, 1, start_pos + i, true, false, nt));
         if (!use_graph(m)) {
             // eager profiling mode: collect the per-GEMV event pairs of this step
             JL_CUDA_CHECK(ctx, cudaStreamSynchronize(m->stream));
@@ -1091,7 +1099,7 @@ extern "C" int jl_model_debug_trace(jl_model *m, uint64_t *out, int64_t out_word
     if (!m || !m->finalized || !out) return JL_ERR_INVALID;
     jl_ctx *ctx = m->ctx;
     if (!m->pd_trace) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "phase tracing is off (set JL_PD_TRACE=1 before creating the model)");
-    const size_t words = (size_t)m->cfg.num_layers * 8 + 16;
+    const size_t words = (size_t)m->cfg.num_layers * 16 + 32;
     if ((size_t)out_words < words) return jl_set_error(ctx, JL_ERR_INVALID, "trace buffer too small (%zu words needed)", words);
     JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
     JL_CUDA_CHECK(ctx, cudaStreamSynchronize(m->stream));

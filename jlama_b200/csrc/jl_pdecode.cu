@@ -63,7 +63,7 @@ __constant__ PdConst c_pd;
 
 enum { PH_QKV = 0, PH_O, PH_GU, PH_DOWN };
 
-// The CTA = PD_NT consumer threads + one TMA producer warp: every CTA-wide barrier of the consumers is the named barrier 1.
+// Every CTA-wide barrier of the kernel is the named barrier 1 over its PD_NT threads.
 __device__ __forceinline__ void pd_cta_bar() { asm volatile("bar.sync 1, %0;" ::"n"(PD_NT) : "memory"); }
 
 // ---- cross-CTA ordering ---------------------------------------------------------------------------------------------------
@@ -355,325 +355,6 @@ __device__ PD_PHASE_FN void pd_gemv(const int, const int L, const uint32_t tag, 
 }
 
 
-// ======================================================================================================================
-// TMA weight ring.  The register ring above keeps ~2 chunks per warp in flight and restarts at every phase: after a grid
-// barrier each warp holds its two primed chunks and then waits a full DRAM latency for the third.  Here ONE producer warp
-// streams the CTA's weights of phase after phase into a shared-memory ring with cp.async.bulk (TMA), bounded only by free
-// slots -- it runs through barriers, prologues and the attention phase, so up to the whole ring (~100 KB per SM, 15 MB per
-// GPU) is in flight or landed when the consumers come out of a barrier.  Consumers read the 16-byte blocks back with
-// LDS.128 and -- for rows of exactly 4096 elements (one 128-block chunk) -- keep their four Q8 activation blocks in
-// REGISTERS, so the ring adds 40 B of shared-memory traffic per 20 B of weights instead of 100 B (the round-1 TMA ring
-// variant read activations from shared memory as well and was shared-memory-bandwidth bound).
-// A chunk = 128 consecutive blocks of the CTA's row range (rows are contiguous in memory, so are their scales).
-// ======================================================================================================================
-// Chunks travel in GROUPS of PD_GRP consecutive chunks of one tensor: one bulk copy for the group's weights, one for its scales
-// (a single producer lane issuing two 2.5 KB copies per chunk topped out at 1.5 TB/s), one full / one empty barrier per group.
-#define PD_CHUNK_BLK 128
-#define PD_GRP 4
-#define PD_PRODUCER_LANES 4
-template <int WDT>
-struct RingCfg {
-    static constexpr int WB = (WDT == JL_Q4) ? 16 : 32;
-    static constexpr int CHW = PD_CHUNK_BLK * WB;  // weight bytes of a chunk
-    static constexpr int CHS = PD_CHUNK_BLK * 4;   // scale bytes of a chunk
-    static constexpr int SLOT = CHW + CHS;         // shared memory per chunk slot
-};
-#define PD_MAX_SLOTS 64
-struct PdRing {
-    unsigned char *w;  // [ngroups * PD_GRP][CHW]   weights of consecutive slots are contiguous
-    unsigned char *s;  // [ngroups * PD_GRP][CHS]
-    uint64_t *full, *empty; // mbarriers per group
-    int ngroups;
-};
-__device__ __forceinline__ uint32_t pd_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void pd_mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pd_smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void pd_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pd_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void pd_mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pd_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool pd_mbar_try_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok)
-                 : "r"(pd_smem_u32(bar)), "r"(parity)
-                 : "memory");
-    return ok != 0;
-}
-// bounded wait; false = gave up (status word set)
-__device__ __forceinline__ bool pd_mbar_wait(const int pz, uint64_t *bar, uint32_t parity, int code) {
-    unsigned n = 0;
-    while (!pd_mbar_try_wait(bar, parity)) {
-        if ((++n & 0xfff) == 0) {
-            if (pd_ld_volatile(CP.sync + 1) != 0) return false;
-            if (n > (1u << 24)) {
-                CP.sync[1] = (unsigned long long)code;
-                return false;
-            }
-        }
-    }
-    return true;
-}
-__device__ __forceinline__ void pd_tma_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar, unsigned long long pol) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(pd_smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(pd_smem_u32(bar)), "l"(pol)
-                 : "memory");
-}
-
-// The CTA's share of a phase as up to three contiguous pieces (one per weight tensor it touches).
-struct PdPiece {
-    const uint8_t *w; // first block of the piece
-    const float *s;
-    int blocks;       // rows * nblk
-    int chunk0;       // first chunk of the piece in the CTA's chunk sequence of this phase
-    int group0;       // first group of the piece in the CTA's group sequence of this phase
-    int slot0;        // row slot (index into the CTA's partial-sum table) of the piece's first row
-    int row0;         // first row, local to the segment (QKV: row inside q / k / v; gate/up: row inside H)
-    int seg;          // QKV: 0 q, 1 k, 2 v; gate/up: 0 gate, 1 up; else 0
-};
-template <int WDT, int PH>
-__device__ __forceinline__ int pd_pieces(const int pz, const int L, const int cta_id, const int ncta, PdPiece (&pc)[3], int &nrows_out,
-                                         int &ngroups_out) {
-    constexpr int WB = RingCfg<WDT>::WB;
-    const int nblk = ph_K<PH>(pz) / 32;
-    const int R0 = (int)(((long long)ph_rows<PH>(pz) * cta_id) / ncta);
-    const int R1 = (int)(((long long)ph_rows<PH>(pz) * (cta_id + 1)) / ncta);
-    int np = 0, chunk = 0, group = 0;
-    auto add = [&](int seg, int r0, int r1, int slot0) { // rows [r0, r1) of segment `seg`
-        if (r1 <= r0) return;
-        const uint8_t *w;
-        const float *sc;
-        ph_weights<PH>(L, seg, w, sc);
-        pc[np].w = w + (size_t)r0 * nblk * WB;
-        pc[np].s = sc + (size_t)r0 * nblk;
-        pc[np].blocks = (r1 - r0) * nblk;
-        pc[np].chunk0 = chunk;
-        pc[np].group0 = group;
-        pc[np].slot0 = slot0;
-        pc[np].row0 = r0;
-        pc[np].seg = seg;
-        const int nch = (pc[np].blocks + PD_CHUNK_BLK - 1) / PD_CHUNK_BLK;
-        chunk += nch;
-        group += (nch + PD_GRP - 1) / PD_GRP;
-        np++;
-    };
-    if (PH == PH_QKV) {
-        const int a = CP.attn_seg, kv = CP.kv_seg;
-        add(0, min(R0, a), min(R1, a), 0);
-        add(1, min(max(R0 - a, 0), kv), min(max(R1 - a, 0), kv), max(a - R0, 0));
-        add(2, min(max(R0 - a - kv, 0), kv), min(max(R1 - a - kv, 0), kv), max(a + kv - R0, 0));
-    } else if (PH == PH_GU) {
-        add(0, R0, R1, 0);
-        add(1, R0, R1, R1 - R0);
-    } else {
-        add(0, R0, R1, 0);
-    }
-    for (int i = np; i < 3; i++) pc[i].blocks = 0, pc[i].chunk0 = chunk, pc[i].group0 = group;
-    nrows_out = R1 - R0;
-    ngroups_out = group;
-    return chunk; // chunks of this CTA in this phase
-}
-// is the ring usable for a phase?  (32-lane groups of a chunk must not straddle rows)
-template <int PH>
-__device__ __forceinline__ bool pd_ring_phase(const int pz) {
-    const int nblk = ph_K<PH>(pz) / 32;
-    return (nblk % 32) == 0;
-}
-
-// ---- producer: PD_PRODUCER_LANES lanes stream the groups of one phase (lane = group index mod lanes) ----
-template <int WDT, int PH>
-__device__ __forceinline__ void pd_produce(const int pz, const int L, const PdRing &R, unsigned &g, const unsigned long long pol, const int plane) {
-    constexpr int WB = RingCfg<WDT>::WB, CHW = RingCfg<WDT>::CHW, CHS = RingCfg<WDT>::CHS;
-    PdPiece pc[3];
-    int nrows, ngroups;
-    pd_pieces<WDT, PH>(pz, L, blockIdx.x, gridDim.x, pc, nrows, ngroups);
-#pragma unroll 1
-    for (int i = 0; i < 3; i++) {
-        const int nch = (pc[i].blocks + PD_CHUNK_BLK - 1) / PD_CHUNK_BLK;
-        const int ngr = (nch + PD_GRP - 1) / PD_GRP;
-#pragma unroll 1
-        for (int gr = 0; gr < ngr; gr++) {
-            const unsigned gg = g + (unsigned)(pc[i].group0 + gr);
-            if ((int)(gg % PD_PRODUCER_LANES) != plane) continue;
-            const unsigned gslot = gg % (unsigned)R.ngroups, par = (gg / (unsigned)R.ngroups) & 1u;
-            if (!pd_mbar_wait(pz, &R.empty[gslot], par ^ 1u, 300)) return;
-            const int c0 = gr * PD_GRP, k = min(PD_GRP, nch - c0);
-            const int nb = min(k * PD_CHUNK_BLK, pc[i].blocks - c0 * PD_CHUNK_BLK);
-            for (int q = k; q < PD_GRP; q++) pd_mbar_arrive(&R.empty[gslot]); // chunks this group does not have
-            pd_mbar_expect_tx(&R.full[gslot], (uint32_t)nb * (WB + 4));
-            pd_tma_load(R.w + (size_t)gslot * PD_GRP * CHW, pc[i].w + (size_t)c0 * CHW, (uint32_t)nb * WB, &R.full[gslot], pol);
-            pd_tma_load(R.s + (size_t)gslot * PD_GRP * CHS, pc[i].s + (size_t)c0 * PD_CHUNK_BLK, (uint32_t)nb * 4, &R.full[gslot], pol);
-        }
-    }
-    g += (unsigned)ngroups;
-}
-
-// ---- consumer: one GEMV phase fed from the ring ----
-// ACTREG: rows are exactly one chunk (K = 4096): each lane owns blocks {lane, 32+lane, 64+lane, 96+lane} of every row and keeps
-// their Q8 activations (2 x 16 bytes, scale, sum) in registers.
-template <int WDT, int PH, int EPI, bool ACTREG>
-__device__ PD_PHASE_FN void pd_gemv_ring(const int, const int L, const uint32_t tag, const int dep_which, const unsigned long long dep_target,
-                                         const int stamp_idx, unsigned char *smem, const PdRing &R, unsigned &g) {
-    PD_OPAQUE_ZERO(pz);
-    constexpr int NT = PD_NT, NWARP = PD_NWARP;
-    constexpr bool NORM = PH == PH_QKV || PH == PH_GU;
-    constexpr int WB = RingCfg<WDT>::WB, CHW = RingCfg<WDT>::CHW, CHS = RingCfg<WDT>::CHS;
-    int tid = threadIdx.x, cta_id = blockIdx.x, ncta = gridDim.x;
-    asm volatile("" : "+r"(tid), "+r"(cta_id), "+r"(ncta));
-    const int lane = tid & 31, warp = tid >> 5;
-    const int K = ph_K<PH>(pz), nblk = K / 32;
-    PdPiece pc[3];
-    int nrows, ngroups;
-    const int total = pd_pieces<WDT, PH>(pz, L, cta_id, ncta, pc, nrows, ngroups);
-    const int maxp = nblk / PD_CHUNK_BLK + 2; // partial sums per row (chunks that touch a row)
-    pd_wait(pz, dep_which, dep_target);
-    pd_stamp(pz, stamp_idx);
-    {
-        GemvParams p; // only the staging fields; dead after the prologue
-        p.a = PH == PH_QKV ? CP.x : (PH == PH_O ? CP.att : (PH == PH_GU ? CP.xb : CP.h));
-        p.a_col_off = 0, p.K = K, p.lda = K;
-        p.norm_w = PH == PH_QKV ? c_pd.layers[L].attn_norm : c_pd.layers[L].ffn_norm;
-        p.norm_w_dtype = PH == PH_QKV ? c_pd.layers[L].attn_norm_dt : c_pd.layers[L].ffn_norm_dt;
-        p.norm_adj = 0.0f, p.norm_eps = CP.eps, p.norm_E = CP.E, p.norm_inv_E = 1.0 / (double)CP.E;
-        constexpr bool LNG = !NORM; // the un-normalised prologue handles any K with its tail loop
-        StageRegs<NORM, LNG> sr;
-        stage_q8_issue<NORM, LNG, NT>(p, sr);
-        stage_q8_finish<NORM, LNG, NT, 1>(p, sr, smem, nblk);
-    }
-    const int8_t *aq = (const int8_t *)smem;
-    const float *asc = (const float *)(smem + (size_t)nblk * 32);
-    const int *asum = (const int *)(smem + (size_t)nblk * 32 + (size_t)nblk * 4);
-    float *parts = (float *)(smem + (((size_t)nblk * 40 + 15) & ~(size_t)15));
-    // register-resident activations (ACTREG)
-    uint4 alo[ACTREG ? 4 : 1], ahi[ACTREG ? 4 : 1];
-    float asc_r[ACTREG ? 4 : 1];
-    int asum_r[ACTREG ? 4 : 1];
-    if (ACTREG) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int bi = j * 32 + lane;
-            alo[j] = *(const uint4 *)(aq + (size_t)bi * 16);
-            ahi[j] = *(const uint4 *)(aq + ((size_t)nblk + bi) * 16);
-            asc_r[j] = asc[bi];
-            asum_r[j] = asum[bi];
-        }
-    }
-    // nibble dot product of one Q4 block against a Q8 activation block: low nibbles as they are, high nibbles left in place
-    // (16 * nibble as an unsigned byte) and the factor 16 shifted out of the sum at the end -- exact, and four shifts fewer per block
-    auto q4_dot = [](const uint4 q, const uint4 xlo, const uint4 xhi, const int xsum) -> int {
-        int lo = 0, hi = 0;
-        lo = __dp4a((int)(q.x & 0x0F0F0F0Fu), (int)xlo.x, lo);
-        lo = __dp4a((int)(q.y & 0x0F0F0F0Fu), (int)xlo.y, lo);
-        lo = __dp4a((int)(q.z & 0x0F0F0F0Fu), (int)xlo.z, lo);
-        lo = __dp4a((int)(q.w & 0x0F0F0F0Fu), (int)xlo.w, lo);
-        asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(hi) : "r"(q.x & 0xF0F0F0F0u), "r"(xhi.x));
-        asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(hi) : "r"(q.y & 0xF0F0F0F0u), "r"(xhi.y));
-        asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(hi) : "r"(q.z & 0xF0F0F0F0u), "r"(xhi.z));
-        asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(hi) : "r"(q.w & 0xF0F0F0F0u), "r"(xhi.w));
-        return lo + (hi >> 4) - 8 * xsum; // sum a*(nib-8) = sum a*nib - 8*sum a   (exact)
-    };
-    auto i8_dot = [](const uint4 q0, const uint4 q1, const uint4 xlo, const uint4 xhi) -> int {
-        int sd = 0;
-        sd = __dp4a((int)q0.x, (int)xlo.x, sd);
-        sd = __dp4a((int)q0.y, (int)xlo.y, sd);
-        sd = __dp4a((int)q0.z, (int)xlo.z, sd);
-        sd = __dp4a((int)q0.w, (int)xlo.w, sd);
-        sd = __dp4a((int)q1.x, (int)xhi.x, sd);
-        sd = __dp4a((int)q1.y, (int)xhi.y, sd);
-        sd = __dp4a((int)q1.z, (int)xhi.z, sd);
-        sd = __dp4a((int)q1.w, (int)xhi.w, sd);
-        return sd;
-    };
-    for (int c = warp; c < total; c += NWARP) {
-        // piece of this chunk (compact pieces; at most three)
-        int pi = 0;
-        if (pc[1].blocks > 0 && c >= pc[1].chunk0) pi = 1;
-        if (pc[2].blocks > 0 && c >= pc[2].chunk0) pi = 2;
-        const int p_chunk0 = pi == 0 ? pc[0].chunk0 : (pi == 1 ? pc[1].chunk0 : pc[2].chunk0);
-        const int p_group0 = pi == 0 ? pc[0].group0 : (pi == 1 ? pc[1].group0 : pc[2].group0);
-        const int p_blocks = pi == 0 ? pc[0].blocks : (pi == 1 ? pc[1].blocks : pc[2].blocks);
-        const int p_slot0 = pi == 0 ? pc[0].slot0 : (pi == 1 ? pc[1].slot0 : pc[2].slot0);
-        const int cc = c - p_chunk0;
-        const int nb = min(PD_CHUNK_BLK, p_blocks - cc * PD_CHUNK_BLK);
-        const unsigned gg = g + (unsigned)(p_group0 + cc / PD_GRP), gslot = gg % (unsigned)R.ngroups, par = (gg / (unsigned)R.ngroups) & 1u;
-        const unsigned cslot = gslot * PD_GRP + (unsigned)(cc % PD_GRP);
-        const unsigned char *sw = R.w + (size_t)cslot * CHW;
-        const float *ss = (const float *)(R.s + (size_t)cslot * CHS);
-        pd_mbar_wait(pz, &R.full[gslot], par, 400);
-        float acc = 0.0f;
-        if (ACTREG) {
-            // one row per chunk: block j*32 + lane against the register-resident activation block j
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int bl = j * 32 + lane;
-                const float sb = ss[bl];
-                int sdot;
-                if (WDT == JL_Q4) sdot = q4_dot(*(const uint4 *)(sw + (size_t)bl * 16), alo[j], ahi[j], asum_r[j]);
-                else sdot = i8_dot(*(const uint4 *)(sw + (size_t)bl * 32), *(const uint4 *)(sw + (size_t)bl * 32 + 16), alo[j], ahi[j]);
-                acc = fmaf(__fmul_rn(asc_r[j], sb), (float)sdot, acc); // acc += (sa*sb) * isum   (vector_simd.c:384-420)
-            }
-            const float v = warp_sum(acc);
-            if (lane == 0) parts[(p_slot0 + cc) * maxp] = v;
-        } else {
-            int cur_row = (cc * PD_CHUNK_BLK) / nblk;           // row inside the piece
-            int row_end = (cur_row + 1) * nblk;                 // first block of the next row
-            int first_chunk = (cur_row * nblk) / PD_CHUNK_BLK;  // first chunk that touches cur_row
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (j * 32 < nb) { // uniform
-                    const int gb0 = cc * PD_CHUNK_BLK + j * 32;
-                    if (gb0 >= row_end) { // uniform: the previous row ended inside this chunk
-                        const float v = warp_sum(acc);
-                        if (lane == 0) parts[(p_slot0 + cur_row) * maxp + (cc - first_chunk)] = v;
-                        acc = 0.0f, cur_row++, first_chunk = cc, row_end += nblk;
-                    }
-                    const int bl = j * 32 + lane, bi = gb0 - (row_end - nblk) + lane;
-                    const float sb = ss[bl];
-                    const uint4 xlo = *(const uint4 *)(aq + (size_t)bi * 16), xhi = *(const uint4 *)(aq + ((size_t)nblk + bi) * 16);
-                    int sdot;
-                    if (WDT == JL_Q4) sdot = q4_dot(*(const uint4 *)(sw + (size_t)bl * 16), xlo, xhi, asum[bi]);
-                    else sdot = i8_dot(*(const uint4 *)(sw + (size_t)bl * 32), *(const uint4 *)(sw + (size_t)bl * 32 + 16), xlo, xhi);
-                    acc = fmaf(__fmul_rn(asc[bi], sb), (float)sdot, acc);
-                }
-            }
-            const float v = warp_sum(acc);
-            if (lane == 0) parts[(p_slot0 + cur_row) * maxp + (cc - first_chunk)] = v;
-        }
-        __syncwarp();
-        if (lane == 0) pd_mbar_arrive(&R.empty[gslot]);
-    }
-    g += (unsigned)ngroups;
-    pd_cta_bar();
-    // ---- per-row pass: partial sums in chunk order, fused epilogue ----
-    const int npr = (nblk + PD_CHUNK_BLK - 1) / PD_CHUNK_BLK; // chunks of an aligned row
-    auto row_sum = [&](int slot, int row_in_piece) {
-        const int first = (row_in_piece * nblk) / PD_CHUNK_BLK, last = ((row_in_piece + 1) * nblk - 1) / PD_CHUNK_BLK;
-        float t = 0.0f;
-        for (int q = first; q <= last; q++) t = __fadd_rn(t, parts[slot * maxp + (q - first)]);
-        return t;
-    };
-    (void)npr;
-    const int nout = PH == PH_GU ? nrows : nrows; // output rows of this CTA
-    for (int o = tid; o < nout; o += NT) {
-        if (PH == PH_GU) {
-            const float gsum = row_sum(o, o), usum = row_sum(nrows + o, o); // both pieces start at row R0: row_in_piece = o
-            CP.h[pc[0].row0 + o] = __fmul_rn(silu_ref(gsum), usum);
-        } else {
-            // locate the piece of slot o
-            const int pi = (pc[2].blocks > 0 && o >= pc[2].slot0) ? 2 : ((pc[1].blocks > 0 && o >= pc[1].slot0) ? 1 : 0);
-            const int rip = o - pc[pi].slot0;
-            float v = row_sum(o, rip);
-            const int local = pc[pi].row0 + rip;
-            if (EPI == EPI_ADD_RESIDUAL) v = __fadd_rn(v, __ldcg((PH == PH_O ? CP.x : CP.xb) + local));
-            if (EPI == EPI_LL) ll_store<PH>(pz, local, v, tag);
-            else ph_out<PH>(pz, pc[pi].seg)[local] = v;
-        }
-    }
-}
-
 // ---- lm_head: F32 activations (RMSNorm, not re-quantised: AbstractModel.java:444-449) x quantised rows + running arg-max --
 template <int WDT>
 __device__ PD_PHASE_FN unsigned long long pd_lm_head(const int, const int dep_which, const unsigned long long dep_target, const int stamp_idx,
@@ -836,44 +517,25 @@ __device__ PD_PHASE_FN void pd_attention(const int, const int layer, const int k
 }
 
 template <int WDT, int HS>
-__global__ void __launch_bounds__(PD_NT + 32, 1) pdecode_kernel(const int splits, const int resident, const int want_logits, const int act_bytes,
-                                                                 const int nslots) {
+__global__ void __launch_bounds__(PD_NT, 1) pdecode_kernel(const int splits0, const int resident, const int want_logits, const int ntok,
+                                                            const int split_cap) {
     PD_OPAQUE_ZERO(pz);
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ int s_last;
-    __shared__ __align__(8) uint64_t s_bars[2 * PD_MAX_SLOTS];
     const int tid = threadIdx.x;
     const int G = gridDim.x, cta = blockIdx.x;
-    PdRing R;
-    R.ngroups = nslots / PD_GRP;
-    R.w = smem + act_bytes, R.s = R.w + (size_t)R.ngroups * PD_GRP * RingCfg<WDT>::CHW, R.full = s_bars, R.empty = s_bars + PD_MAX_SLOTS;
-    const bool ring = R.ngroups > 0;
-    if (ring && tid == 0) {
-        for (int i = 0; i < R.ngroups; i++) pd_mbar_init(&R.full[i], 1), pd_mbar_init(&R.empty[i], PD_GRP);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    unsigned long long epoch = pd_ld_volatile(CP.sync); // tokens decoded by this model so far
+    const unsigned long long fin0 = pd_ld_volatile(CP.sync + PC_FINAL);
+    // ntok > 1 (device-resident loop only): several tokens per launch; the token fed back by CTA 0 is published to the
+    // grid through one more barrier (PC_FINAL) instead of a kernel boundary
+    for (int tk = 0; tk < ntok; tk++) {
+    int splits = splits0;
+    if (tk > 0) { // context splits of this token: one per 64 positions up to split_cap (the host computes token 0's)
+        pd_wait(pz, PC_FINAL, fin0 + (unsigned long long)tk);
+        const int pos = *(volatile const int32_t *)CP.positions;
+        splits = (pos + 1 + 63) / 64;
+        splits = splits > split_cap ? split_cap : (splits < 1 ? 1 : splits);
     }
-    __syncthreads(); // the only CTA-wide barrier that includes the producer warp
-    if (tid >= PD_NT) {
-        // ===== TMA producer: lane 0 walks the same phase sequence as the consumers, bounded only by free ring slots =====
-        if (ring && tid < PD_NT + PD_PRODUCER_LANES) {
-            const int plane = tid - PD_NT;
-            const unsigned long long pol = l2_evict_first_policy();
-            unsigned g = 0;
-            const int nl = CP.layers;
-            const bool rE = pd_ring_phase<PH_QKV>(pz), rA = pd_ring_phase<PH_O>(pz), rH = pd_ring_phase<PH_DOWN>(pz);
-            for (int L = 0; L < nl; L++) {
-                if (rE) pd_produce<WDT, PH_QKV>(pz, L, R, g, pol, plane);
-                if (rA) pd_produce<WDT, PH_O>(pz, L, R, g, pol, plane);
-                if (rE) pd_produce<WDT, PH_GU>(pz, L, R, g, pol, plane);
-                if (rH) pd_produce<WDT, PH_DOWN>(pz, L, R, g, pol, plane);
-            }
-        }
-        return;
-    }
-    unsigned g = 0; // chunks of this CTA consumed from the ring so far (same sequence as the producer's)
-    const bool rE = ring && pd_ring_phase<PH_QKV>(pz), rA = ring && pd_ring_phase<PH_O>(pz), rH = ring && pd_ring_phase<PH_DOWN>(pz);
-    const bool regE = CP.E == 32 * PD_CHUNK_BLK, regA = CP.attn_seg == 32 * PD_CHUNK_BLK; // rows of exactly one chunk: activations in registers
-    const unsigned long long epoch = pd_ld_volatile(CP.sync); // tokens decoded by this model so far
     const unsigned long long uG = (unsigned long long)G;
     const bool tp = CP.world > 1;
     const int layers = CP.layers;
@@ -885,7 +547,7 @@ __global__ void __launch_bounds__(PD_NT + 32, 1) pdecode_kernel(const int splits
     {
         const int E = CP.E;
         const int c_a = (int)(((long long)E * cta) / G), c_b = (int)(((long long)E * (cta + 1)) / G);
-        const size_t tok = (size_t)CP.tokens[0];
+        const size_t tok = (size_t)__ldcg(CP.tokens); // fed back by CTA 0 of this very launch when ntok > 1
         for (int c = c_a + tid; c < c_b; c += PD_NT) CP.x[c] = pd_embed_value(pz, tok, c);
         pd_arrive(pz, PC_EMBED);
     }
@@ -899,10 +561,7 @@ __global__ void __launch_bounds__(PD_NT + 32, 1) pdecode_kernel(const int splits
         {
             const int dw = L == 0 ? PC_EMBED : PC_DOWN;
             const unsigned long long dt = L == 0 ? (epoch + 1) * uG : (use - 1) * uG;
-            if (rE) {
-                if (regE) pd_gemv_ring<WDT, PH_QKV, EPI_STORE, true>(pz, L, 0u, dw, dt, 1 + L * 8 + 0, smem, R, g);
-                else pd_gemv_ring<WDT, PH_QKV, EPI_STORE, false>(pz, L, 0u, dw, dt, 1 + L * 8 + 0, smem, R, g);
-            } else if (lng_E) pd_gemv<WDT, PH_QKV, EPI_STORE, true>(pz, L, 0u, dw, dt, 1 + L * 8 + 0, smem);
+            if (lng_E) pd_gemv<WDT, PH_QKV, EPI_STORE, true>(pz, L, 0u, dw, dt, 1 + L * 8 + 0, smem);
             else pd_gemv<WDT, PH_QKV, EPI_STORE, false>(pz, L, 0u, dw, dt, 1 + L * 8 + 0, smem);
             pd_arrive(pz, PC_QKV);
             pd_stamp(pz, 1 + L * 8 + 1);
@@ -934,18 +593,12 @@ __global__ void __launch_bounds__(PD_NT + 32, 1) pdecode_kernel(const int splits
         {
             const unsigned long long dt = use * (unsigned long long)CP.kv_heads;
             if (tp) {
-                if (rA) {
-                    if (regA) pd_gemv_ring<WDT, PH_O, EPI_LL, true>(pz, L, tag_o, PC_ATT, dt, 1 + L * 8 + 3, smem, R, g);
-                    else pd_gemv_ring<WDT, PH_O, EPI_LL, false>(pz, L, tag_o, PC_ATT, dt, 1 + L * 8 + 3, smem, R, g);
-                } else if (lng_A) pd_gemv<WDT, PH_O, EPI_LL, true>(pz, L, tag_o, PC_ATT, dt, 1 + L * 8 + 3, smem);
+                if (lng_A) pd_gemv<WDT, PH_O, EPI_LL, true>(pz, L, tag_o, PC_ATT, dt, 1 + L * 8 + 3, smem);
                 else pd_gemv<WDT, PH_O, EPI_LL, false>(pz, L, tag_o, PC_ATT, dt, 1 + L * 8 + 3, smem);
                 pd_cta_bar();
                 pd_ll_reduce<PH_O>(pz, tag_o, (float *)smem);
             } else {
-                if (rA) {
-                    if (regA) pd_gemv_ring<WDT, PH_O, EPI_ADD_RESIDUAL, true>(pz, L, 0u, PC_ATT, dt, 1 + L * 8 + 3, smem, R, g);
-                    else pd_gemv_ring<WDT, PH_O, EPI_ADD_RESIDUAL, false>(pz, L, 0u, PC_ATT, dt, 1 + L * 8 + 3, smem, R, g);
-                } else if (lng_A) pd_gemv<WDT, PH_O, EPI_ADD_RESIDUAL, true>(pz, L, 0u, PC_ATT, dt, 1 + L * 8 + 3, smem);
+                if (lng_A) pd_gemv<WDT, PH_O, EPI_ADD_RESIDUAL, true>(pz, L, 0u, PC_ATT, dt, 1 + L * 8 + 3, smem);
                 else pd_gemv<WDT, PH_O, EPI_ADD_RESIDUAL, false>(pz, L, 0u, PC_ATT, dt, 1 + L * 8 + 3, smem);
             }
             pd_arrive(pz, PC_O);
@@ -953,10 +606,7 @@ __global__ void __launch_bounds__(PD_NT + 32, 1) pdecode_kernel(const int splits
         }
         // ---- gate / up: RMSNorm(xb) -> Q8 -> silu(gate) * up ----
         {
-            if (rE) {
-                if (regE) pd_gemv_ring<WDT, PH_GU, EPI_SILU_MUL, true>(pz, L, 0u, PC_O, use * uG, 1 + L * 8 + 5, smem, R, g);
-                else pd_gemv_ring<WDT, PH_GU, EPI_SILU_MUL, false>(pz, L, 0u, PC_O, use * uG, 1 + L * 8 + 5, smem, R, g);
-            } else if (lng_E) pd_gemv<WDT, PH_GU, EPI_SILU_MUL, true>(pz, L, 0u, PC_O, use * uG, 1 + L * 8 + 5, smem);
+            if (lng_E) pd_gemv<WDT, PH_GU, EPI_SILU_MUL, true>(pz, L, 0u, PC_O, use * uG, 1 + L * 8 + 5, smem);
             else pd_gemv<WDT, PH_GU, EPI_SILU_MUL, false>(pz, L, 0u, PC_O, use * uG, 1 + L * 8 + 5, smem);
             pd_arrive(pz, PC_GU);
             pd_stamp(pz, 1 + L * 8 + 6);
@@ -964,14 +614,12 @@ __global__ void __launch_bounds__(PD_NT + 32, 1) pdecode_kernel(const int splits
         // ---- down_proj: Q8(h) -> xb + down ----
         {
             if (tp) {
-                if (rH) pd_gemv_ring<WDT, PH_DOWN, EPI_LL, false>(pz, L, tag_d, PC_GU, use * uG, 1 + L * 8 + 7, smem, R, g);
-                else if (lng_H) pd_gemv<WDT, PH_DOWN, EPI_LL, true>(pz, L, tag_d, PC_GU, use * uG, 1 + L * 8 + 7, smem);
+                if (lng_H) pd_gemv<WDT, PH_DOWN, EPI_LL, true>(pz, L, tag_d, PC_GU, use * uG, 1 + L * 8 + 7, smem);
                 else pd_gemv<WDT, PH_DOWN, EPI_LL, false>(pz, L, tag_d, PC_GU, use * uG, 1 + L * 8 + 7, smem);
                 pd_cta_bar();
                 pd_ll_reduce<PH_DOWN>(pz, tag_d, (float *)smem);
             } else {
-                if (rH) pd_gemv_ring<WDT, PH_DOWN, EPI_ADD_RESIDUAL, false>(pz, L, 0u, PC_GU, use * uG, 1 + L * 8 + 7, smem, R, g);
-                else if (lng_H) pd_gemv<WDT, PH_DOWN, EPI_ADD_RESIDUAL, true>(pz, L, 0u, PC_GU, use * uG, 1 + L * 8 + 7, smem);
+                if (lng_H) pd_gemv<WDT, PH_DOWN, EPI_ADD_RESIDUAL, true>(pz, L, 0u, PC_GU, use * uG, 1 + L * 8 + 7, smem);
                 else pd_gemv<WDT, PH_DOWN, EPI_ADD_RESIDUAL, false>(pz, L, 0u, PC_GU, use * uG, 1 + L * 8 + 7, smem);
             }
             pd_arrive(pz, PC_DOWN);
@@ -1040,9 +688,15 @@ __global__ void __launch_bounds__(PD_NT + 32, 1) pdecode_kernel(const int splits
                 }
                 CP.sync[0] = epoch + 1;
                 pd_stamp(pz, 1 + layers * 8 + 1);
+                if (tk + 1 < ntok) {
+                    __threadfence();
+                    asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(CP.sync + PC_FINAL) : "memory");
+                }
             }
         }
     }
+    epoch++;
+    } // tokens of this launch
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------------
@@ -1092,20 +746,12 @@ void jl_pdecode_forget(int device, const void *owner) {
 template <int WDT, int HS>
 static int launch_pd(jl_ctx *ctx, cudaStream_t stream, const PdParams &p) {
     auto kern = pdecode_kernel<WDT, HS>;
-    const size_t act = pd_smem_bytes(p);
-    // the ring takes what is left of the 227 KB: at least 24 slots or none (JL_PD_RING=0 disables it)
-    static const int ring_env = getenv("JL_PD_RING") ? atoi(getenv("JL_PD_RING")) : 1;
-    const size_t budget = 224 * 1024 - 2048;
-    int nslots = ring_env && budget > act ? (int)((budget - act) / RingCfg<WDT>::SLOT) : 0;
-    if (nslots > PD_MAX_SLOTS) nslots = PD_MAX_SLOTS;
-    nslots -= nslots % PD_GRP;
-    if (nslots < 24) nslots = 0;
-    const size_t smem = act + (size_t)nslots * RingCfg<WDT>::SLOT;
+    const size_t smem = pd_smem_bytes(p);
     static size_t configured[JL_MAX_DEVICES] = {};
     JL_CUDA_CHECK(ctx, jl_ensure_dyn_smem(kern, ctx->device, smem, configured));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ctx->sm_count);
-    cfg.blockDim = dim3(PD_NT + 32);
+    cfg.blockDim = dim3(PD_NT);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -1113,7 +759,7 @@ static int launch_pd(jl_ctx *ctx, cudaStream_t stream, const PdParams &p) {
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    JL_CUDA_CHECK(ctx, cudaLaunchKernelEx(&cfg, kern, p.splits, p.resident, p.want_logits, (int)act, nslots));
+    JL_CUDA_CHECK(ctx, cudaLaunchKernelEx(&cfg, kern, p.splits, p.resident, p.want_logits, p.ntok > 0 ? p.ntok : 1, p.split_cap));
     ctx->launches++;
     return JL_OK;
 }

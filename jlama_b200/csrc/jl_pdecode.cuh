@@ -3,7 +3,7 @@
 #include "jl_common.cuh"
 
 #ifndef PD_THREADS
-#define PD_THREADS 480 // consumer threads (15 warps); + one TMA producer warp = 512 threads per CTA, 128 registers each
+#define PD_THREADS 512
 #endif
 #define PD_MAX_TP 8
 #define PD_SYNC_WORDS 32 // u64 words: [0] epoch, [1] status (0 ok, else the phase id that timed out), [8..] barrier counters
@@ -43,6 +43,7 @@ struct PdParams {
     unsigned long long *argmax_slots; // [grid] packed (ordered logit bits << 32 | ~index) per CTA
     unsigned *att_done;               // [kv_heads] split arrival counters (self-resetting)
     int splits;
+    int ntok, split_cap;              // tokens per launch (resident loop), upper bound of the context splits
     // tensor parallel exchange over NVLink peer memory (world > 1): LL lines {v0, tag, v1, tag}
     int world, rank;
     uint4 *ll_o[PD_MAX_TP]; // ll_o[d] = rank d's receive buffer for o_proj partials: [world][E/2] lines
