@@ -193,6 +193,8 @@ typedef struct {
     int tp_rank, tp_size; /* jlama-net model shard (DistributedContext modelShard/numModelShards) */
     int prefill_tensor_core; /* 1: prompt chunks of >= 16 rows use the tcgen05 BF16 GEMM path; 0: exact-integer SIMT path */
     int flags;           /* JL_MODEL_* */
+    int num_experts;       /* 0 = dense MLP; > 0: Mixtral-style mixture of experts (core/model/MoEBlock.java) */
+    int experts_per_token; /* top-k (MixtralConfig numberOfExpertsPerToken) */
 } jl_model_config;
 
 #define JL_MODEL_NO_GRAPH 1 /* launch decode kernels eagerly instead of through a CUDA graph */
@@ -219,6 +221,10 @@ int jl_model_create(jl_ctx *ctx, const jl_model_config *cfg, jl_model **out);
  * rank's shard (rows for q/k/v/gate/up, columns for o/down: LlamaModel.java:120-133,
  * Weights.getLoadOffsets core/safetensors/Weights.java:99-117). */
 int jl_model_set_tensor(jl_model *m, int layer, int slot, int64_t tensor_id);
+/* Mixture-of-experts layers (core/model/mixtral/MixtralModel.java:88-105): expert < 0 binds the router
+ * ("block_sparse_moe.gate.weight" [num_experts, E]); otherwise which = 0 w1 (gate_proj [H, E]), 1 w2 (down_proj [E, H]),
+ * 2 w3 (up_proj [H, E]) of that expert.  The dense JL_L_GATE / JL_L_UP / JL_L_DOWN slots stay empty for MoE models. */
+int jl_model_set_expert_tensor(jl_model *m, int layer, int expert, int which, int64_t tensor_id);
 /* allocate scratch + KV page pool, build RoPE table, capture graphs */
 int jl_model_finalize(jl_model *m);
 int jl_model_free(jl_model *m);

@@ -120,7 +120,20 @@ struct GemvParams {
     int row0;                // first global row handled by this launch (n0)
     int total_rows;          // rows handled by this launch
     unsigned long long *trace; // diagnostics slot (jl_debug_ktrace) or nullptr
+    // mixture-of-experts indirection (MoEBlock.java:98-137): when sel != nullptr the weights of segment i are
+    // w_tab[i][*sel] / ws_tab[i][*sel] -- the expert index is only known on the device (router top-k of this row)
+    const int *sel;
+    const void *const *w_tab[2];
+    const float *const *ws_tab[2];
 };
+__device__ __forceinline__ void gemv_seg_base(const GemvParams &p, int seg, const void *&w, const float *&ws) {
+    if (p.sel) {
+        const int e = __ldg(p.sel);
+        w = p.w_tab[seg][e], ws = p.ws_tab[seg][e];
+    } else {
+        w = p.seg[seg].w, ws = p.seg[seg].ws;
+    }
+}
 
 #define GEMV_MAX_M 8
 
@@ -150,6 +163,9 @@ int jl_launch_rmsnorm(jl_ctx *ctx, cudaStream_t s, const float *x, int rows, int
 int jl_launch_layernorm(jl_ctx *ctx, cudaStream_t s, const float *x, int rows, int ldx, int w_dtype, const void *w, int b_dtype,
                         const void *bias, float eps, int E, int offset, int length, float *out);
 int jl_launch_activation(jl_ctx *ctx, cudaStream_t s, int type, float *x, int rows, int ld, int offset, int length);
+// MoE router: softmax over the expert logits of each row (VectorMath.softMax) + top-k by the reference's replace-the-minimum
+// scan (MoEBlock.java:151-168); sel[row * k + i] = i-th selected expert
+int jl_launch_moe_route(jl_ctx *ctx, cudaStream_t s, float *logits, int rows, int n_experts, int k, int32_t *sel);
 int jl_launch_softmax(jl_ctx *ctx, cudaStream_t s, float *x, int offset, int length);
 int jl_launch_silu_mul(jl_ctx *ctx, cudaStream_t s, float *gate, const float *up, int rows, int ld, int offset, int length);
 // embedding rows -> f32 hidden (LlamaModel.java:68-100); tokens on device

@@ -326,6 +326,43 @@ int jl_launch_activation(jl_ctx *ctx, cudaStream_t s, int type, float *x, int ro
     return JL_OK;
 }
 
+// ---- MoE router (MoEBlock.java:90-92,151-168): one warp per row; at most 64 experts ----------------------------------------
+__global__ void moe_route_kernel(float *logits, int n_experts, int k, int32_t *sel) {
+    const int row = blockIdx.x, lane = threadIdx.x;
+    float *x = logits + (size_t)row * n_experts;
+    // VectorMath.softMax (:69-90): max, (float)exp((double)(x - max)), float sum in index order, divide
+    float v0 = lane < n_experts ? x[lane] : -INFINITY, v1 = lane + 32 < n_experts ? x[lane + 32] : -INFINITY;
+    const float mx = warp_max(fmaxf(v0, v1));
+    const float e0 = lane < n_experts ? (float)exp((double)__fsub_rn(v0, mx)) : 0.0f;
+    const float e1 = lane + 32 < n_experts ? (float)exp((double)__fsub_rn(v1, mx)) : 0.0f;
+    __shared__ float pe[64];
+    pe[lane] = e0, pe[lane + 32] = e1;
+    __syncwarp();
+    if (lane == 0) {
+        float sum = 0.0f;
+        for (int i = 0; i < n_experts; i++) sum = __fadd_rn(sum, pe[i]);
+        for (int i = 0; i < n_experts; i++) pe[i] = __fdiv_rn(pe[i], sum), x[i] = pe[i];
+        // topk: the first k experts, then every later expert replaces the current minimum if it is larger (strict)
+        int s[64];
+        for (int i = 0; i < k; i++) s[i] = i;
+        for (int i = k; i < n_experts; i++) {
+            int mn = 0;
+            for (int j = 1; j < k; j++)
+                if (pe[s[j]] < pe[s[mn]]) mn = j;
+            if (pe[i] > pe[s[mn]]) s[mn] = i;
+        }
+        for (int i = 0; i < k; i++) sel[(size_t)row * k + i] = s[i];
+    }
+}
+int jl_launch_moe_route(jl_ctx *ctx, cudaStream_t s, float *logits, int rows, int n_experts, int k, int32_t *sel) {
+    if (rows <= 0) return JL_OK;
+    if (n_experts < 1 || n_experts > 64 || k < 1 || k > n_experts) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "moe_route: %d experts / top-%d", n_experts, k);
+    moe_route_kernel<<<rows, 32, 0, s>>>(logits, n_experts, k, sel);
+    ctx->launches++;
+    JL_CUDA_CHECK(ctx, cudaGetLastError());
+    return JL_OK;
+}
+
 // ---- softmax (VectorMath.java:69-90), single row, one CTA ---------------------------------------------------------
 __global__ void softmax_kernel(float *x, int offset, int length) {
     __shared__ float red[32];

@@ -86,10 +86,12 @@ __global__ void __launch_bounds__(GEMV_THREADS, MINB) gemv_kernel(const GemvPara
         } else {
             seg_lookup(p, it.r, seg, local);
         }
-        const GemvSeg &sg = p.seg[seg];
+        const void *wb;
+        const float *wsb;
+        gemv_seg_base(p, seg, wb, wsb);
         const size_t grow = (size_t)(p.row0 + local);
-        wrow = (const uint8_t *)sg.w + (grow * (size_t)(p.ldw / 32) + (size_t)(p.w_col_off / 32)) * wbytes_per_blk;
-        srow = sg.ws + grow * (size_t)(p.ldw / 32) + (size_t)(p.w_col_off / 32);
+        wrow = (const uint8_t *)wb + (grow * (size_t)(p.ldw / 32) + (size_t)(p.w_col_off / 32)) * wbytes_per_blk;
+        srow = wsb + grow * (size_t)(p.ldw / 32) + (size_t)(p.w_col_off / 32);
     };
     auto advance = [&](It &it) {
         if (++it.c == nchunks) {
@@ -200,8 +202,11 @@ __global__ void __launch_bounds__(NT, 1) gemv_decode_kernel(const GemvParams p, 
             seg_lookup(p, R0 + it.r, seg, local);
         }
         const size_t blk = (size_t)(p.row0 + local) * row_blocks + col_blocks;
-        wrow = (const uint8_t *)p.seg[seg].w + blk * WB;
-        srow = p.seg[seg].ws + blk;
+        const void *wb;
+        const float *wsb;
+        gemv_seg_base(p, seg, wb, wsb);
+        wrow = (const uint8_t *)wb + blk * WB;
+        srow = wsb + blk;
     };
     auto advance = [&](It &it) {
         if (!LONG || ++it.c == nchunks) {

@@ -61,6 +61,15 @@ struct jl_model {
     bool timing_valid = false;
     int64_t weight_bytes = 0;
     unsigned *fda_done = nullptr;
+    // mixture of experts (MoEBlock.java): router + per-expert w1 / w2 / w3, device pointer tables for the indirect GEMV launches
+    int n_exp = 0, exp_k = 0;
+    std::vector<DevTensor> moe_gate; // [layers]
+    std::vector<DevTensor> moe_w;    // [layers][n_exp][3]
+    std::vector<char> moe_set;       // [layers][1 + n_exp * 3]
+    void **moe_wtab = nullptr;       // device [layers][3][n_exp] weight pointers
+    float **moe_stab = nullptr;      // device [layers][3][n_exp] scale pointers
+    float *moe_logits = nullptr;     // [maxB][n_exp]
+    int32_t *moe_sel = nullptr;      // [maxB][exp_k]
     // persistent decode kernel (jl_pdecode.cu)
     bool pd_ok = false;
     int pd_wdtype = JL_Q4;
@@ -139,6 +148,16 @@ extern "C" int jl_model_create(jl_ctx *ctx, const jl_model_config *cfg, jl_model
     m->kv_heads_local = m->kv_seg / hs;
     m->l.resize((size_t)c.num_layers * 9);
     m->l_set.assign((size_t)c.num_layers * 9, 0);
+    if (c.num_experts > 0) {
+        if (c.num_experts > 64 || c.experts_per_token < 1 || c.experts_per_token > c.num_experts || m->cfg.tp_size > 1)
+            return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "model_create: %d experts / top-%d (max 64 experts, single rank)", c.num_experts,
+                                c.experts_per_token),
+                   delete m, JL_ERR_UNSUPPORTED;
+        m->n_exp = c.num_experts, m->exp_k = c.experts_per_token;
+        m->moe_gate.resize(c.num_layers);
+        m->moe_w.resize((size_t)c.num_layers * m->n_exp * 3);
+        m->moe_set.assign((size_t)c.num_layers * (1 + m->n_exp * 3), 0);
+    }
     m->max_context = c.max_context > 0 && c.max_context < c.context_length ? c.max_context : c.context_length;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
@@ -209,6 +228,34 @@ extern "C" int jl_model_set_tensor(jl_model *m, int layer, int slot, int64_t ten
     return JL_OK;
 }
 
+extern "C" int jl_model_set_expert_tensor(jl_model *m, int layer, int expert, int which, int64_t tensor_id) {
+    if (!m) return JL_ERR_INVALID;
+    jl_ctx *ctx = m->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (m->n_exp <= 0) return jl_set_error(ctx, JL_ERR_INVALID, "model_set_expert_tensor: the model has no experts");
+    if (m->finalized) return jl_set_error(ctx, JL_ERR_INVALID, "model_set_expert_tensor: model already finalized");
+    auto it = ctx->tensors.find(tensor_id);
+    if (it == ctx->tensors.end()) return jl_set_error(ctx, JL_ERR_INVALID, "model_set_expert_tensor: unknown tensor id");
+    if (layer < 0 || layer >= m->cfg.num_layers || expert >= m->n_exp || which < 0 || which > 2)
+        return jl_set_error(ctx, JL_ERR_INVALID, "model_set_expert_tensor: bad layer / expert / slot");
+    DevTensor &t = it->second;
+    const int E = m->cfg.embedding_length, H = m->cfg.hidden_length;
+    const int64_t rows = expert < 0 ? m->n_exp : (which == 1 ? E : H), cols = expert < 0 ? E : (which == 1 ? H : E);
+    if (t.rows != rows || t.cols != cols)
+        return jl_set_error(ctx, JL_ERR_INVALID, "model_set_expert_tensor: expects [%lld,%lld], got [%lld,%lld]", (long long)rows, (long long)cols,
+                            (long long)t.rows, (long long)t.cols);
+    t.refs++;
+    m->bound_ids.push_back(t.id);
+    if (expert < 0) {
+        m->moe_gate[layer] = t;
+        m->moe_set[(size_t)layer * (1 + m->n_exp * 3)] = 1;
+    } else {
+        m->moe_w[((size_t)layer * m->n_exp + expert) * 3 + which] = t;
+        m->moe_set[(size_t)layer * (1 + m->n_exp * 3) + 1 + expert * 3 + which] = 1;
+    }
+    return JL_OK;
+}
+
 static int dev_alloc(jl_ctx *ctx, void **p, size_t bytes) {
     if (cudaMalloc(p, bytes ? bytes : 16) != cudaSuccess) {
         cudaGetLastError();
@@ -225,8 +272,14 @@ extern "C" int jl_model_finalize(jl_model *m) {
     JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
     for (int i = 0; i < 2; i++)
         if (!m->g_set[i]) return jl_set_error(ctx, JL_ERR_INVALID, "model_finalize: global tensor %d missing", i);
-    for (size_t i = 0; i < m->l_set.size(); i++)
-        if (!m->l_set[i]) return jl_set_error(ctx, JL_ERR_INVALID, "model_finalize: layer %zu slot %zu missing", i / 9, i % 9);
+    for (size_t i = 0; i < m->l_set.size(); i++) {
+        const size_t slot = i % 9;
+        if (m->n_exp > 0 && (slot == JL_L_GATE || slot == JL_L_DOWN || slot == JL_L_UP)) continue; // experts instead of a dense MLP
+        if (!m->l_set[i]) return jl_set_error(ctx, JL_ERR_INVALID, "model_finalize: layer %zu slot %zu missing", i / 9, slot);
+    }
+    for (size_t i = 0; i < m->moe_set.size(); i++)
+        if (!m->moe_set[i])
+            return jl_set_error(ctx, JL_ERR_INVALID, "model_finalize: layer %zu expert tensor %zu missing", i / (1 + m->n_exp * 3), i % (1 + m->n_exp * 3));
     // the fused QKV and gate+up launches decode all their segments with one weight dtype: a checkpoint that mixes
     // precisions inside a fused group (e.g. Q in Q4, K/V left in BF16) must be rejected, not mis-read
     for (int L = 0; L < c.num_layers; L++) {
@@ -234,7 +287,7 @@ extern "C" int jl_model_finalize(jl_model *m) {
         if (lw[JL_L_K].dtype != lw[JL_L_Q].dtype || lw[JL_L_V].dtype != lw[JL_L_Q].dtype)
             return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "model_finalize: layer %d q/k/v weights must share one dtype (got %d/%d/%d)", L,
                                 lw[JL_L_Q].dtype, lw[JL_L_K].dtype, lw[JL_L_V].dtype);
-        if (lw[JL_L_UP].dtype != lw[JL_L_GATE].dtype)
+        if (m->n_exp == 0 && lw[JL_L_UP].dtype != lw[JL_L_GATE].dtype)
             return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "model_finalize: layer %d gate/up weights must share one dtype (got %d/%d)", L,
                                 lw[JL_L_GATE].dtype, lw[JL_L_UP].dtype);
     }
@@ -276,6 +329,27 @@ extern "C" int jl_model_finalize(jl_model *m) {
     M_CHECK(dev_alloc(ctx, (void **)&m->v, B * m->kv_seg * 4));
     M_CHECK(dev_alloc(ctx, (void **)&m->att, B * m->attn_seg * 4));
     M_CHECK(dev_alloc(ctx, (void **)&m->hbuf, B * m->h_seg * 4));
+    if (m->n_exp > 0) {
+        M_CHECK(dev_alloc(ctx, (void **)&m->moe_logits, B * m->n_exp * 4));
+        M_CHECK(dev_alloc(ctx, (void **)&m->moe_sel, B * m->exp_k * 4));
+        const size_t ne = (size_t)c.num_layers * 3 * m->n_exp;
+        std::vector<void *> wt(ne);
+        std::vector<float *> st(ne);
+        int wd0 = m->moe_w[0].dtype;
+        for (int L = 0; L < c.num_layers; L++)
+            for (int w = 0; w < 3; w++)
+                for (int e = 0; e < m->n_exp; e++) {
+                    const DevTensor &t = m->moe_w[((size_t)L * m->n_exp + e) * 3 + w];
+                    if (t.dtype != wd0 || (wd0 != JL_Q4 && wd0 != JL_I8))
+                        return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "model_finalize: expert weights must share one quantised dtype (Q4 or I8)");
+                    wt[((size_t)L * 3 + w) * m->n_exp + e] = t.data;
+                    st[((size_t)L * 3 + w) * m->n_exp + e] = t.scales;
+                }
+        M_CHECK(dev_alloc(ctx, (void **)&m->moe_wtab, ne * sizeof(void *)));
+        M_CHECK(dev_alloc(ctx, (void **)&m->moe_stab, ne * sizeof(float *)));
+        JL_CUDA_CHECK(ctx, cudaMemcpy(m->moe_wtab, wt.data(), ne * sizeof(void *), cudaMemcpyHostToDevice));
+        JL_CUDA_CHECK(ctx, cudaMemcpy(m->moe_stab, st.data(), ne * sizeof(float *), cudaMemcpyHostToDevice));
+    }
     M_CHECK(dev_alloc(ctx, (void **)&m->partial, B * E * 4));
     if (c.prefill_tensor_core) {
         size_t kmax = E > m->h_seg ? E : m->h_seg;
@@ -283,7 +357,7 @@ extern "C" int jl_model_finalize(jl_model *m) {
         M_CHECK(dev_alloc(ctx, (void **)&m->ln, B * E * 4));
         M_CHECK(dev_alloc(ctx, (void **)&m->hbuf2, B * m->h_seg * 4));
         M_CHECK(dev_alloc(ctx, (void **)&m->abf, B * kmax * 2));
-        bool ok = c.tp_size == 1 && (E % 128) == 0 && (m->h_seg % 128) == 0 && (m->attn_seg % 128) == 0 && (m->kv_seg % 128) == 0;
+        bool ok = m->n_exp == 0 && c.tp_size == 1 && (E % 128) == 0 && (m->h_seg % 128) == 0 && (m->attn_seg % 128) == 0 && (m->kv_seg % 128) == 0;
         for (int L = 0; L < c.num_layers && ok; L++)
             for (int sl : {JL_L_Q, JL_L_K, JL_L_V, JL_L_O, JL_L_GATE, JL_L_DOWN, JL_L_UP}) ok = ok && m->l[(size_t)L * 9 + sl].dtype == JL_Q4;
         m->tc_ok = ok;
@@ -308,14 +382,20 @@ extern "C" int jl_model_finalize(jl_model *m) {
     auto tb = [](const DevTensor &t) { return (int64_t)t.bytes; };
     int64_t wb = 0;
     for (int L = 0; L < c.num_layers; L++)
-        for (int s : {JL_L_Q, JL_L_K, JL_L_V, JL_L_O, JL_L_GATE, JL_L_DOWN, JL_L_UP}) wb += tb(m->l[(size_t)L * 9 + s]);
+        for (int s : {JL_L_Q, JL_L_K, JL_L_V, JL_L_O, JL_L_GATE, JL_L_DOWN, JL_L_UP})
+            if (m->l_set[(size_t)L * 9 + s]) wb += tb(m->l[(size_t)L * 9 + s]);
+    // mixture of experts: the router plus the experts_per_token selected experts are streamed per token
+    for (int L = 0; L < c.num_layers && m->n_exp > 0; L++) {
+        wb += tb(m->moe_gate[L]);
+        for (int w = 0; w < 3; w++) wb += (int64_t)m->exp_k * tb(m->moe_w[((size_t)L * m->n_exp) * 3 + w]);
+    }
     wb += tb(m->g_set[JL_T_LM_HEAD] ? m->g[JL_T_LM_HEAD] : m->g[JL_T_EMBED]);
     m->weight_bytes = wb;
     // ---- persistent decode kernel eligibility: Q8 activations, every linear weight (and the lm_head) in ONE quantised dtype ----
     {
         const DevTensor &head = m->g_set[JL_T_LM_HEAD] ? m->g[JL_T_LM_HEAD] : m->g[JL_T_EMBED];
         const int wd = m->l[JL_L_Q].dtype;
-        bool ok = c.working_qtype == JL_I8 && (wd == JL_Q4 || wd == JL_I8) && head.dtype == wd;
+        bool ok = m->n_exp == 0 && c.working_qtype == JL_I8 && (wd == JL_Q4 || wd == JL_I8) && head.dtype == wd;
         for (int L = 0; L < c.num_layers && ok; L++)
             for (int sl : {JL_L_Q, JL_L_K, JL_L_V, JL_L_O, JL_L_GATE, JL_L_DOWN, JL_L_UP}) ok = ok && m->l[(size_t)L * 9 + sl].dtype == wd;
         // lm_head rows of this rank (vocabulary-sharded under tensor parallelism: SURVEY 8e; the reference computes the
@@ -443,7 +523,7 @@ extern "C" int jl_model_free(jl_model *m) {
         if (p) cudaFree(p);
     void *bufs[] = {m->ln, m->hbuf2, m->abf, m->rope, m->page_table_dev, m->x, m->xb, m->q, m->k, m->v, m->att, m->hbuf, m->partial, m->logits,
                     m->last_hidden, m->attn_ws, m->d_tokens, m->d_positions, m->d_sessions, m->d_next, m->d_hist, m->d_counter,
-                    m->argmax_scratch, m->fda_done, m->pd_sync, m->pd_slots, m->pd_att_done, m->pd_trace, m->ll_o, m->ll_d, m->ll_a};
+                    m->argmax_scratch, m->fda_done, m->moe_wtab, m->moe_stab, m->moe_logits, m->moe_sel, m->pd_sync, m->pd_slots, m->pd_att_done, m->pd_trace, m->ll_o, m->ll_d, m->ll_a};
     for (void *p : bufs)
         if (p) cudaFree(p);
     if (m->h_pinned) cudaFreeHost(m->h_pinned);
@@ -619,6 +699,58 @@ static int forward_rows(jl_model *m, int M, int max_pos, int splits, bool timed,
                 JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->xb, m->partial, (size_t)M * E * 4, cudaMemcpyDeviceToDevice, m->stream));
                 M_CHECK(jl_launch_accumulate(ctx, m->stream, m->xb, M, E, JL_F32, m->x, nullptr, M, E, 0, E));
             }
+        }
+        if (m->n_exp > 0) {
+            // ---- mixture of experts (MoEBlock.java:73-149), one row at a time: router GEMV -> softmax + top-k on the device ->
+            // per selected expert gate/up (SiLU*up fused) and down_proj through the expert pointer tables; the expert results
+            // are summed UNWEIGHTED in selection order (:139-143), then the residual is added (TransformerBlock.java:203).
+            // Row b of the result is the sum over row b's experts (the reference's copy of expert 0's result into row 0 for
+            // every batch row, MoEBlock.java:141, is a bug we do not reproduce; with one row per call they coincide).
+            const int NE = m->n_exp, KE = m->exp_k, H = m->h_seg;
+            void **wt = m->moe_wtab + (size_t)L * 3 * NE;
+            float **st = m->moe_stab + (size_t)L * 3 * NE;
+            const bool aq = act_q(m->moe_w[(size_t)L * NE * 3]);
+            for (int b = 0; b < M; b++) {
+                {
+                    GemvParams p = {};
+                    p.nseg = 1;
+                    set_w(p, 0, m->moe_gate[L], m->moe_logits + (size_t)b * NE, NE);
+                    p.w_dtype = m->moe_gate[L].dtype, p.ldw = E, p.K = E;
+                    p.a = m->xb + (size_t)b * E, p.lda = E;
+                    p.norm_w = lw[JL_L_FFN_NORM].data, p.norm_w_dtype = lw[JL_L_FFN_NORM].dtype, p.norm_eps = c.layer_norm_eps, p.norm_E = E;
+                    p.total_rows = NE;
+                    M_CHECK(run_gemm(m, p, act_q(m->moe_gate[L]) ? PRO_RMSNORM_QUANT : PRO_RMSNORM_F32, EPI_STORE, 1, (size_t)E * 4, false));
+                }
+                M_CHECK(jl_launch_moe_route(ctx, m->stream, m->moe_logits + (size_t)b * NE, 1, NE, KE, m->moe_sel + (size_t)b * KE));
+                for (int i = 0; i < KE; i++) {
+                    const DevTensor &proto = m->moe_w[(size_t)L * NE * 3]; // shapes / dtype of every expert
+                    GemvParams p = {};
+                    p.nseg = 2;
+                    set_w(p, 0, proto, m->hbuf, H);
+                    set_w(p, 1, proto, m->hbuf, H);
+                    p.sel = m->moe_sel + (size_t)b * KE + i;
+                    p.w_tab[0] = (const void *const *)(wt + 0 * NE), p.ws_tab[0] = (const float *const *)(st + 0 * NE); // w1
+                    p.w_tab[1] = (const void *const *)(wt + 2 * NE), p.ws_tab[1] = (const float *const *)(st + 2 * NE); // w3
+                    p.w_dtype = proto.dtype, p.ldw = E, p.K = E;
+                    p.a = m->xb + (size_t)b * E, p.lda = E;
+                    p.norm_w = lw[JL_L_FFN_NORM].data, p.norm_w_dtype = lw[JL_L_FFN_NORM].dtype, p.norm_eps = c.layer_norm_eps, p.norm_E = E;
+                    p.total_rows = H;
+                    M_CHECK(run_gemm(m, p, aq ? PRO_RMSNORM_QUANT : PRO_RMSNORM_F32, EPI_SILU_MUL, 1, (size_t)E * 4, false));
+                    GemvParams d = {};
+                    d.nseg = 1;
+                    const DevTensor &dproto = m->moe_w[(size_t)L * NE * 3 + 1];
+                    set_w(d, 0, dproto, m->x + (size_t)b * E, E);
+                    d.sel = p.sel;
+                    d.w_tab[0] = (const void *const *)(wt + 1 * NE), d.ws_tab[0] = (const float *const *)(st + 1 * NE); // w2
+                    d.w_dtype = dproto.dtype, d.ldw = H, d.K = H;
+                    d.a = m->hbuf, d.lda = H;
+                    d.residual = m->x + (size_t)b * E, d.res_ld = E; // expert i > 0 accumulates onto the sum so far
+                    d.total_rows = E;
+                    M_CHECK(run_gemm(m, d, aq ? PRO_F32_QUANT : PRO_F32, i == 0 ? EPI_STORE : EPI_ADD_RESIDUAL, 1, (size_t)H * 4, false));
+                }
+            }
+            M_CHECK(jl_launch_accumulate(ctx, m->stream, m->x, M, E, JL_F32, m->xb, nullptr, M, E, 0, E)); // + residual
+            continue;
         }
         // ---- pre-FF norm + quantise + gate/up + SiLU*up (TransformerBlock.java:187-196, MLPBlock.java:117-141) ----
         {

@@ -61,7 +61,8 @@ class LlamaModel:
             num_kv_heads=cfg["kv_heads"], num_layers=cfg["layers"], vocab_size=cfg["vocab"], head_size=cfg["E"] // cfg["heads"],
             layer_norm_eps=cfg["eps"], rope_theta=cfg["rope_theta"], rope_scaling=cfg.get("rope_scale", 1.0),
             working_qtype=working_qtype, kv_dtype=kv_dtype, max_batch=max_batch, max_sessions=max_sessions,
-            max_context=max_context, tp_rank=tp_rank, tp_size=tp_size, prefill_tensor_core=prefill_tensor_core, flags=flags)
+            max_context=max_context, tp_rank=tp_rank, tp_size=tp_size, prefill_tensor_core=prefill_tensor_core, flags=flags,
+            num_experts=cfg.get("experts", 0), experts_per_token=cfg.get("experts_per_token", 0))
         h = C.c_void_p()
         ctx.check(self.lib.jl_model_create(ctx.h, C.byref(mc), C.byref(h)))
         self.h = h
@@ -138,6 +139,16 @@ class LlamaModel:
             ctx.check(self.lib.jl_model_set_tensor(self.h, layer, slot, tid))
             return True
 
+        def put_expert(layer, expert, which, name):
+            dt, data, scales = get(name)
+            rows = data.shape[0]
+            cols = data.shape[1] * (2 if dt == Q4 else 1)
+            tid = self.lib.jl_register_tensor(ctx.h, dt, rows, cols, ptr(data), ptr(scales))
+            if tid < 0:
+                raise native.JlamaNativeError(-1, self.lib.jl_last_error(ctx.h).decode())
+            self._ids.append(tid)
+            ctx.check(self.lib.jl_model_set_expert_tensor(self.h, layer, expert, which, tid))
+
         sharded = tp_size > 1
         put(-1, native.T_EMBED, "model.embed_tokens.weight")
         put(-1, native.T_OUT_NORM, "model.norm.weight")
@@ -150,6 +161,12 @@ class LlamaModel:
             put(i, native.L_V, b + "self_attn.v_proj.weight", "rows_kv" if sharded else None)
             put(i, native.L_O, b + "self_attn.o_proj.weight", "cols_attn" if sharded else None)
             put(i, native.L_FFN_NORM, b + "post_attention_layernorm.weight")
+            if cfg.get("experts"):  # MixtralModel.java:88-105
+                put_expert(i, -1, 0, b + "block_sparse_moe.gate.weight")
+                for e in range(cfg["experts"]):
+                    for which, nm in ((0, "w1"), (1, "w2"), (2, "w3")):
+                        put_expert(i, e, which, b + "block_sparse_moe.experts.%d.%s.weight" % (e, nm))
+                continue
             put(i, native.L_GATE, b + "mlp.gate_proj.weight", "rows_hidden" if sharded else None)
             put(i, native.L_DOWN, b + "mlp.down_proj.weight", "cols_hidden" if sharded else None)
             put(i, native.L_UP, b + "mlp.up_proj.weight", "rows_hidden" if sharded else None)

@@ -35,7 +35,7 @@ class ModelConfig(C.Structure):
         ("head_size", C.c_int), ("layer_norm_eps", C.c_float), ("rope_theta", C.c_double), ("rope_scaling", C.c_double),
         ("working_qtype", C.c_int), ("kv_dtype", C.c_int), ("max_batch", C.c_int), ("max_sessions", C.c_int),
         ("max_context", C.c_int), ("tp_rank", C.c_int), ("tp_size", C.c_int), ("prefill_tensor_core", C.c_int),
-        ("flags", C.c_int),
+        ("flags", C.c_int), ("num_experts", C.c_int), ("experts_per_token", C.c_int),
     ]
 
 
@@ -99,6 +99,7 @@ SIGNATURES = {
     "jl_kv_page_geometry": (_i, [_i, _i, _i, _i, _i64, C.POINTER(_i), C.POINTER(_i)]),
     "jl_model_create": (_i, [_vp, C.POINTER(ModelConfig), C.POINTER(_vp)]),
     "jl_model_set_tensor": (_i, [_vp, _i, _i, _i64]),
+    "jl_model_set_expert_tensor": (_i, [_vp, _i, _i, _i, _i64]),
     "jl_model_finalize": (_i, [_vp]),
     "jl_model_free": (_i, [_vp]),
     "jl_model_reset_session": (_i, [_vp, _i]),

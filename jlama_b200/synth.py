@@ -26,11 +26,16 @@ CONFIGS = {
     "small-hs128": dict(ctx=512, E=1024, H=2048, heads=8, kv_heads=2, layers=2, vocab=1024, eps=1e-5, rope_theta=500000.0),
     # 8 KV heads so that the jlama-net model-shard split reaches 8 ranks (JlamaService.java:65-68 caps shards at KV heads)
     "llama-tp8-test": dict(ctx=512, E=1024, H=3584, heads=16, kv_heads=8, layers=3, vocab=4096, eps=1e-5, rope_theta=500000.0),
+    # mixture of experts (Mixtral layout: 8 experts, top-2) at test size
+    "tiny-mixtral": dict(ctx=256, E=256, H=512, heads=8, kv_heads=4, layers=2, vocab=512, eps=1e-5, rope_theta=10000.0, experts=8, experts_per_token=2),
+    "small-mixtral": dict(ctx=512, E=1024, H=2048, heads=8, kv_heads=2, layers=3, vocab=1024, eps=1e-5, rope_theta=1000000.0, experts=4, experts_per_token=2),
     # BASELINE.json configs (public HF config.json dims)
     "llama-3.2-1b": dict(ctx=131072, E=2048, H=8192, heads=32, kv_heads=8, layers=16, vocab=128256, eps=1e-5,
                          rope_theta=500000.0, tied=True),
     "llama-3-8b": dict(ctx=8192, E=4096, H=14336, heads=32, kv_heads=8, layers=32, vocab=128256, eps=1e-5,
                        rope_theta=500000.0),
+    "mixtral-8x7b": dict(ctx=32768, E=4096, H=14336, heads=32, kv_heads=8, layers=32, vocab=32000, eps=1e-5, rope_theta=1000000.0,
+                         experts=8, experts_per_token=2),
 }
 
 SEED0 = 0x4A4C414D41  # "JLAMA"
@@ -96,10 +101,18 @@ def tensor_specs(cfg):
             (b + "self_attn.v_proj.weight", kvl, E, "linear"),
             (b + "self_attn.o_proj.weight", E, E, "linear"),
             (b + "post_attention_layernorm.weight", 1, E, "norm"),
-            (b + "mlp.gate_proj.weight", H, E, "linear"),
-            (b + "mlp.down_proj.weight", E, H, "linear"),
-            (b + "mlp.up_proj.weight", H, E, "linear"),
         ]
+        if cfg.get("experts"):  # MixtralModel.java:88-105
+            specs.append((b + "block_sparse_moe.gate.weight", cfg["experts"], E, "linear"))
+            for e in range(cfg["experts"]):
+                p = b + "block_sparse_moe.experts.%d." % e
+                specs += [(p + "w1.weight", H, E, "linear"), (p + "w2.weight", E, H, "linear"), (p + "w3.weight", H, E, "linear")]
+        else:
+            specs += [
+                (b + "mlp.gate_proj.weight", H, E, "linear"),
+                (b + "mlp.down_proj.weight", E, H, "linear"),
+                (b + "mlp.up_proj.weight", H, E, "linear"),
+            ]
     specs.append(("model.norm.weight", 1, E, "norm"))
     if not cfg.get("tied"):
         specs.append(("lm_head.weight", V, E, "head"))
@@ -125,7 +138,7 @@ def make_one(cfg, name, rows, cols, kind, wdtype=Q4, mode="quantize", embed_dtyp
     # synthetic network is residual-dominated and well-conditioned like a trained one; with every matrix at
     # std 0.02 a random transformer amplifies 1e-7 summation-order differences into O(1) logit changes.
     std = 0.02
-    if name.endswith("o_proj.weight") or name.endswith("down_proj.weight"):
+    if name.endswith("o_proj.weight") or name.endswith("down_proj.weight") or name.endswith(".w2.weight"):
         std = 0.02 / float(np.sqrt(2.0 * cfg["layers"]))
     return make_tensor(seed, rows, cols, wdtype, mode, std=std, q4_fn=q4_fn)
 
@@ -146,7 +159,10 @@ def linear_weight_count(cfg):
     E, H, V = cfg["E"], cfg["H"], cfg["vocab"]
     hs = E // cfg["heads"]
     kvl = cfg["kv_heads"] * hs
-    per_layer = E * E * 2 + kvl * E * 2 + H * E * 3
+    if cfg.get("experts"):  # per token: attention + router + the selected experts
+        per_layer = E * E * 2 + kvl * E * 2 + cfg["experts"] * E + cfg["experts_per_token"] * H * E * 3
+    else:
+        per_layer = E * E * 2 + kvl * E * 2 + H * E * 3
     return per_layer * cfg["layers"] + V * E
 
 

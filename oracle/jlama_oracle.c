@@ -593,6 +593,10 @@ typedef struct {
     float **pages; /* [n_layer_pages * n_ctx_pages] of [lpp,2,cpp,kv_len] f32, lazily calloc'd */
     /* tensor-parallel simulation: numModelShards partial sums reduced in rank order */
     int tp;
+    /* mixture of experts (model/MoEBlock.java, model/mixtral/MixtralModel.java:63-120); n_experts == 0: dense MLP */
+    int n_experts, n_experts_per_tok;
+    jo_tensor *moe_gate; /* [layers] router weight [n_experts, E] */
+    jo_tensor *moe_w;    /* [layers][n_experts][3]: w1 (gate_proj), w2 (down_proj), w3 (up_proj) */
 } jo_model;
 
 jo_model *jo_model_create(int ctx, int E, int H, int heads, int kv_heads, int layers, int vocab, float eps,
@@ -619,6 +623,20 @@ jo_model *jo_model_create(int ctx, int E, int H, int heads, int kv_heads, int la
 }
 
 void jo_model_set_tp(jo_model *m, int tp) { m->tp = tp; }
+void jo_model_set_moe(jo_model *m, int n_experts, int n_experts_per_tok) {
+    m->n_experts = n_experts;
+    m->n_experts_per_tok = n_experts_per_tok;
+    free(m->moe_gate);
+    free(m->moe_w);
+    m->moe_gate = (jo_tensor *)calloc((size_t)m->layers, sizeof(jo_tensor));
+    m->moe_w = (jo_tensor *)calloc((size_t)m->layers * n_experts * 3, sizeof(jo_tensor));
+}
+/* expert < 0: the router ("block_sparse_moe.gate.weight"); which: 0 = w1, 1 = w2, 2 = w3 */
+void jo_model_set_expert(jo_model *m, int layer, int expert, int which, int dtype, int64_t rows, int64_t cols, const void *data,
+                         const float *scales) {
+    jo_tensor *t = expert < 0 ? &m->moe_gate[layer] : &m->moe_w[((size_t)layer * m->n_experts + expert) * 3 + which];
+    t->dtype = dtype; t->rows = rows; t->cols = cols; t->data = data; t->scales = scales;
+}
 void jo_model_kv_geometry(jo_model *m, int *lpp, int *cpp) { *lpp = m->layers_per_page; *cpp = m->ctx_per_page; }
 
 void jo_model_reset_kv(jo_model *m) {
@@ -630,7 +648,7 @@ void jo_model_reset_kv(jo_model *m) {
 
 void jo_model_free(jo_model *m) {
     jo_model_reset_kv(m);
-    free(m->pages); free(m->rope); free(m->l); free(m);
+    free(m->pages); free(m->rope); free(m->l); free(m->moe_gate); free(m->moe_w); free(m);
 }
 
 /* layer < 0 -> global tensor `kind`; data is NOT copied */
@@ -766,6 +784,45 @@ static void forward_rows(jo_model *m, float *x, int M, int startPos) {
         for (int64_t i = 0; i < (int64_t)M * E; i++) res[i] = res[i] + x[i];
         /* pre-FF norm, MLP (MLPBlock.java:106-166) */
         jo_rmsnorm(res, M, E, &lw[L_FFN_NORM], 0.0f, m->eps, E, 0, E, ln);
+        if (m->n_experts > 0) {
+            /* MoEBlock.forward (MoEBlock.java:73-149), one row at a time.  The input is the maybeQuantize'd pre-FF norm
+             * (TransformerBlock.java:192-196), so the router dot products and the expert GEMVs are Q8 x Q4 when the model is.
+             * Quirk NOT reproduced: for expert 0 the reference copies the expert result into row 0 of `result` whatever the
+             * batch row (MoEBlock.java:139-143 copyFrom(moeResult, 0, 0, E)); with one row per call (decode, or
+             * jlama.max_batch_size = 1) that is row b, which is what is computed here for every row. */
+            const int NE = m->n_experts, KE = m->n_experts_per_tok;
+            float er[64];
+            int sel[64];
+            float *moe = (float *)malloc(sizeof(float) * E);
+            for (int b = 0; b < M; b++) {
+                const float *lnb = ln + (size_t)b * E;
+                gemm_act(m, er, NE, lnb, 1, E, &m->moe_gate[L], 0, E, 0, NE, qb, sb); /* :82-88 dotProduct per expert */
+                jo_softmax(er, 0, NE);                                                  /* :91 */
+                for (int i = 0; i < KE; i++) sel[i] = i;                                /* topk :151-168: replace the minimum */
+                for (int i = KE; i < NE; i++) {
+                    int mn = 0;
+                    for (int j = 1; j < KE; j++)
+                        if (er[sel[j]] < er[sel[mn]]) mn = j;
+                    if (er[i] > er[sel[mn]]) sel[mn] = i;
+                }
+                float *xrow = x + (size_t)b * E;
+                for (int i = 0; i < KE; i++) {
+                    const jo_tensor *ew = &m->moe_w[((size_t)L * NE + sel[i]) * 3];
+                    gemm_act(m, buf, H, lnb, 1, E, &ew[0], 0, E, 0, H, qb, sb);  /* w1 */
+                    gemm_act(m, buf2, H, lnb, 1, E, &ew[2], 0, E, 0, H, qb, sb); /* w3 */
+                    for (int j = 0; j < H; j++) buf[j] = jo_silu(buf[j]) * buf2[j]; /* :118-125 */
+                    /* w1/w3 are row-sharded and the [1,H] buffer is reduced before the un-sharded w2 (:127-134): disjoint
+                     * segments, so sharding does not change the arithmetic */
+                    gemm_act(m, moe, E, buf, 1, H, &ew[1], 0, H, 0, E, qb, sb);
+                    if (i == 0) memcpy(xrow, moe, sizeof(float) * E);
+                    else
+                        for (int j = 0; j < E; j++) xrow[j] = xrow[j] + moe[j]; /* unweighted sum :139-143 */
+                }
+            }
+            free(moe);
+            for (int64_t i = 0; i < (int64_t)M * E; i++) x[i] = x[i] + res[i]; /* TransformerBlock.java:203 */
+            continue;
+        }
         gemm_act(m, buf, H, ln, M, E, &lw[L_GATE], 0, E, 0, H, qb, sb);
         gemm_act(m, buf2, H, ln, M, E, &lw[L_UP], 0, E, 0, H, qb, sb);
 #pragma omp parallel for schedule(static)

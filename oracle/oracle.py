@@ -84,6 +84,8 @@ def lib():
         L.jo_model_free.argtypes = [C.c_void_p]
         L.jo_model_reset_kv.argtypes = [C.c_void_p]
         L.jo_model_set_tp.argtypes = [C.c_void_p, C.c_int]
+        L.jo_model_set_moe.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.jo_model_set_expert.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
         L.jo_model_kv_geometry.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.jo_model_kv_row.restype = C.POINTER(C.c_float)
         L.jo_model_kv_row.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -390,11 +392,26 @@ class OracleLlama:
             cols = data.shape[1] * (2 if dt == Q4 else 1)
             L.jo_model_set_tensor(self.h, layer, kind, dt, C.c_int64(rows), C.c_int64(cols), _p(data), _p(scales))
 
+        n_exp = cfg.get("experts", 0)
+        if n_exp:
+            L.jo_model_set_moe(self.h, n_exp, cfg["experts_per_token"])
+
+        def put_expert(layer, expert, which, name):
+            dt, data, scales = weights[name]
+            rows = data.shape[0]
+            cols = data.shape[1] * (2 if dt == Q4 else 1)
+            L.jo_model_set_expert(self.h, layer, expert, which, dt, C.c_int64(rows), C.c_int64(cols), _p(data), _p(scales))
+
         put(-1, T_EMBED, "model.embed_tokens.weight")
         put(-1, T_OUT_NORM, "model.norm.weight")
         put(-1, T_LM_HEAD, "lm_head.weight")
         for i in range(cfg["layers"]):
             b = "model.layers.%d." % i
+            if n_exp:  # MixtralModel.java:88-105 tensor names
+                put_expert(i, -1, 0, b + "block_sparse_moe.gate.weight")
+                for e in range(n_exp):
+                    for which, nm in ((0, "w1"), (1, "w2"), (2, "w3")):
+                        put_expert(i, e, which, b + "block_sparse_moe.experts.%d.%s.weight" % (e, nm))
             put(i, L_ATTN_NORM, b + "input_layernorm.weight")
             put(i, L_Q, b + "self_attn.q_proj.weight")
             put(i, L_K, b + "self_attn.k_proj.weight")
