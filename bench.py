@@ -157,6 +157,58 @@ def gpu_q4_quantizer(ctx):
     return q4
 
 
+def config3_workload(ctx, cfg, peak, sessions=8, prompt_tokens=2048, decode_tokens=128):
+    """BASELINE config 3: Llama-3-8B Q8_0 (int8 weights + one f32 scale per 32-element block, Q8ByteBufferTensor.java:68-90),
+    `sessions` concurrent sessions sharing the weights (the reference's batch: KvBufferCache.java:58-60), prefill 2048 /
+    decode 128 each.  Weights: synthetic int8 bytes + scales ("direct").  Everything is driven through the host-buffer
+    C ABI (jl_model_batch_forward / jl_model_decode), so both numbers are end-to-end figures."""
+    from jlama_b200 import native, synth
+    from jlama_b200.model import LlamaModel
+    t0 = time.time()
+    w8 = synth.make_weights(cfg, wdtype=native.I8, mode="direct")
+    log("[bench] config 3: synthetic Q8_0 checkpoint generated in %.1fs" % (time.time() - t0))
+    prompt_tokens = min(prompt_tokens, cfg["ctx"] - decode_tokens - 8)
+    m = LlamaModel(ctx, cfg, w8, max_context=prompt_tokens + decode_tokens + 8, max_sessions=sessions)
+    wbytes = m.weight_bytes()
+    prompts = [synth.random_prompt(cfg, prompt_tokens, seed=500 + s) for s in range(sessions)]
+    m.batch_forward(prompts[0][:64], 0, session=0)  # warm-up
+    m.reset_session(0)
+    ctx.sync()
+    t0 = time.perf_counter()
+    firsts = []
+    for s in range(sessions):
+        m.batch_forward(prompts[s], 0, session=s)
+        firsts.append(m.sample(session=s, want_logits=False)[0])
+    ctx.sync()
+    prefill_s = time.perf_counter() - t0
+    toks = np.array(firsts, dtype=np.int32)
+    pos = np.full(sessions, prompt_tokens, dtype=np.int32)
+    for _ in range(4):  # warm-up (captures the batch graph)
+        toks, _ = m.decode(toks, pos)
+        pos += 1
+    ctx.sync()
+    l0 = ctx.kernel_launches()
+    t0 = time.perf_counter()
+    n = decode_tokens - 4
+    for _ in range(n):
+        toks, _ = m.decode(toks, pos)
+        pos += 1
+    ctx.sync()
+    dt = time.perf_counter() - t0
+    launches = ctx.kernel_launches() - l0
+    hs = cfg["E"] // cfg["heads"]
+    kv_bytes = sessions * cfg["layers"] * 2 * cfg["kv_heads"] * hs * 4 * (prompt_tokens + 4 + n / 2.0 + 1)
+    step = dt / n
+    out = {"workload": "%s Q8_0 (int8 weights + f32 block scales, Q8 activations, F32 KV), %d sessions, prefill %d / decode %d, direct synthetic weights"
+                       % (cfg["name"], sessions, prompt_tokens, decode_tokens),
+           "prefill_tokens_per_s": sessions * prompt_tokens / prefill_s, "decode_tokens_per_s": sessions / step, "decode_ms_per_step": 1e3 * step,
+           "bytes_per_step": {"weights": wbytes, "kv": kv_bytes}, "frac_of_hbm_peak": (wbytes + kv_bytes) / 1e9 / step / peak,
+           "launches_per_step": launches / n, "decode_mode": m.decode_mode(sessions),
+           "timing": "host clock around the host-buffer C-ABI calls (tokens H2D, sampled tokens D2H every step)"}
+    m.close()
+    return out
+
+
 def first_divergence(a, b):
     for i, (x, y) in enumerate(zip(a, b)):
         if int(x) != int(y):
@@ -250,6 +302,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity-port-tokens", type=int, default=0, help="tokens also checked against the plain-C oracle port (slow; off by default)")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-config3", action="store_true", help="skip the BASELINE config-3 measurement (8B Q8_0, 8 sessions, prefill 2048 / decode 128)")
     ap.add_argument("--no-persistent", action="store_true", help="decode through the CUDA graph of per-op kernels instead of the persistent kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -414,6 +467,11 @@ def main():
             "position": ptoks + 8, "tokens_per_s": 1.0 / lstep, "ms_per_step": 1e3 * lstep, "kv_bytes_per_token": kv_bytes,
             "frac_of_hbm_peak_weights_plus_kv": (wbytes + kv_bytes) / 1e9 / lstep / peak}
         pm.close()
+        if not args.no_config3 and cfg["name"].startswith("llama-3-8b"):
+            try:
+                result["config"]["config3_q8_batch8"] = config3_workload(ctx, cfg, peak)
+            except Exception as e:  # noqa: BLE001 -- a secondary measurement must never break the bench line
+                log("[bench] config 3 skipped: %r" % (e,))
         model = LlamaModel(ctx, cfg, weights, max_context=min(cfg["ctx"], max(512, n_total)))
 
     # ---- cpu_baseline + in-run parity ----------------------------------------------------------------------------------

@@ -139,7 +139,10 @@ __device__ __forceinline__ void gemv_seg_base(const GemvParams &p, int seg, cons
 
 // Launch on `stream`.  use_pdl: launch with the programmatic-stream-serialization attribute.
 int jl_launch_gemv(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int prologue, int epilogue, bool use_pdl);
-int jl_gemv_max_m(int w_dtype, int prologue, int K); // largest M chunk (1/2/4/8) that fits shared memory, 0 if none
+int jl_gemv_max_m(int w_dtype, int prologue, int K);
+// batched decode (2..8 rows): integer block products on the tensor cores (jl_gemm8.cu)
+bool jl_gemm8_supported(const GemvParams &p, int prologue, int epilogue);
+int jl_launch_gemm8(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int prologue, int epilogue); // largest M chunk (1/2/4/8) that fits shared memory, 0 if none
 
 // ---------------------------------------------------------------------------------------------
 // Element-wise / normalisation / sampling kernels (jl_elementwise.cu)
@@ -212,6 +215,9 @@ struct AttnParams {
 int jl_launch_rope_kv_append(jl_ctx *ctx, cudaStream_t s, const AttnParams &p, float *q_inplace, bool use_pdl);
 // Causal attention of each row against positions [0, pos] of its session (CausalSelfAttention.java:314-356).
 int jl_launch_paged_attention(jl_ctx *ctx, cudaStream_t s, const AttnParams &p, int max_pos, bool use_pdl);
+// tiled prefill attention for one session's chunk of consecutive positions (jl_attn_prefill.cu)
+bool jl_prefill_attention_supported(const AttnParams &p);
+int jl_launch_prefill_attention(jl_ctx *ctx, cudaStream_t s, const AttnParams &p, int session, int pos0);
 // Decode steps (every row a different session): RoPE + KV append + attention fused in one kernel; q/k/v are the raw
 // projections.  done_cnt: [rows * kv_heads] zero-initialised split-arrival counters (self-resetting).
 int jl_launch_fused_decode_attention(jl_ctx *ctx, cudaStream_t s, const AttnParams &p, unsigned *done_cnt, bool use_pdl);

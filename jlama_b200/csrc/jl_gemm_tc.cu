@@ -9,18 +9,23 @@
 //     tokens), so the instruction's M is always full and D comes out as [weight row][token];
 //   * per-block dequantisation (nibble - 8) * f32 scale -> BF16 is fused into the shared-memory fill of the
 //     weight tile: eight producer warps read the packed Q4 blocks with 128-bit loads straight from HBM/L2
-//     and write the 128-byte-swizzled K-major tile the tensor core consumes; the activation tile (already BF16
-//     in HBM) is copied into the same swizzled layout;
-//   * 4-stage mbarrier pipeline: producers -> full[s] -> MMA warp -> tcgen05.commit -> empty[s];
+//     and write the 128-byte-swizzled K-major tile the tensor core consumes; their packed blocks are requested three
+//     pipeline stages ahead (registers), so the dequantisation never waits for HBM/L2;
+//   * the activation tile (already BF16 in HBM) arrives by TMA: one thread of a tenth warp issues
+//     cp.async.bulk.tensor.2d with a SWIZZLE_128B tensor map ([T, lda] BF16, box 64 x BN) that completes on the stage's
+//     full barrier (expect_tx); rows past T are zero-filled by the copy engine;
+//   * 4-stage mbarrier pipeline: producers + TMA -> full[s] -> MMA warp -> tcgen05.commit -> empty[s];
 //   * epilogue: tcgen05.ld (32 lanes x 16 columns per warp) -> optional residual add -> coalesced f32 stores.
 //
 // Numerics: operands are rounded to BF16 (8-bit mantissa), accumulation is F32.  This is the "F32/BF16 x Q4"
 // flavour of the reference (tolerance class 1e-2 rel on logits); the exact-integer Q8 x Q4 arithmetic stays
 // available through the GEMV path (jl_model: prefill_tensor_core = 0).
 #include "jl_common.cuh"
+#include <cuda.h> // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
 
 #define TC_PWARPS 8                      // producer / epilogue warps
-#define TC_THREADS (TC_PWARPS * 32 + 32) // + warp 8: TMEM allocator and MMA issuer
+#define TC_THREADS (TC_PWARPS * 32 + 64) // + warp 8: TMEM allocator and MMA issuer, warp 9: TMA issuer
+#define TC_PF 3                          // weight blocks requested this many stages ahead
 #define TC_BM 128                        // weight rows per CTA (UMMA M)
 #define TC_BK 64                         // K per pipeline stage: 64 bf16 = one 128-byte swizzle atom
 #define TC_STAGES 4
@@ -81,7 +86,7 @@ struct TcParams {
 
 // BN = tokens per CTA (UMMA N): 128, or 256 to amortise the weight dequantisation over twice the tokens
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_q4_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_q4_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap amap) {
     constexpr int ATILE = BN * TC_BK * 2;
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     unsigned char *wtile = tc_smem;                                // [STAGES][16 KB] weight tiles (UMMA A)
@@ -114,29 +119,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_q4_tc_kernel(const TcParam
 
     if (warp < TC_PWARPS) {
         // ===== producers.  Weight tile: thread (r = tid & 127, half = tid >> 7) dequantises one 32-element block of
-        // row r (four 16-byte chunks).  Token tile: 256 threads copy BN rows of 128 bytes.  Chunks are XOR-swizzled
-        // by (row & 7) -- the SWIZZLE_128B K-major layout the tensor core reads. =====
+        // row r (four 16-byte chunks), XOR-swizzled by (row & 7) -- the SWIZZLE_128B K-major layout the tensor core
+        // reads (and the layout TMA writes for the token tile). =====
         const int r = tid & 127, half = tid >> 7;
         const size_t wrow = (size_t)(n0 + r);
         const uint8_t *wq = p.w + wrow * (size_t)(p.ldw / 2) + p.w_col_off / 2 + half * 16;
         const float *wsc = p.ws + wrow * (size_t)(p.ldw / 32) + p.w_col_off / 32 + half;
-        // token tile mapping: BN == 256: thread t copies row t (8 chunks); BN == 128: row r, chunks half*4 .. half*4+3
-        constexpr int ACH = BN == 256 ? 8 : 4;
-        const int arow_i = BN == 256 ? tid : r;
-        const int ach0 = BN == 256 ? 0 : half * 4;
-        const bool tok_ok = (t0 + arow_i) < p.T;
-        const uint16_t *arow = p.a + (size_t)(tok_ok ? t0 + arow_i : 0) * p.lda + ach0 * 8;
+        uint4 qn[TC_PF];
+        float scn[TC_PF];
+#pragma unroll
+        for (int i = 0; i < TC_PF; i++) {
+            const int kk = i < nk ? i : nk - 1;
+            qn[i] = ldg_nc_u4(wq + (size_t)kk * 32);
+            scn[i] = ldg_nc_f32(wsc + kk * 2);
+        }
         for (int kc = 0; kc < nk; kc++) {
             const int s = kc % TC_STAGES, use = kc / TC_STAGES;
-            // issue the global loads first, then wait for the slot
-            const uint4 q = ldg_nc_u4(wq + (size_t)kc * 32);
-            const float sc = ldg_nc_f32(wsc + kc * 2);
-            uint4 av[ACH];
+            const uint4 q = qn[0];
+            const float sc = scn[0];
 #pragma unroll
-            for (int c = 0; c < ACH; c++) av[c] = tok_ok ? *(const uint4 *)(arow + (size_t)kc * TC_BK + c * 8) : make_uint4(0, 0, 0, 0);
+            for (int i = 0; i + 1 < TC_PF; i++) qn[i] = qn[i + 1], scn[i] = scn[i + 1];
+            {
+                const int kk = kc + TC_PF < nk ? kc + TC_PF : nk - 1;
+                qn[TC_PF - 1] = ldg_nc_u4(wq + (size_t)kk * 32);
+                scn[TC_PF - 1] = ldg_nc_f32(wsc + kk * 2);
+            }
             tc_mbar_wait(&empty[s], (use & 1) ^ 1);
             unsigned char *wdst = wtile + (size_t)s * TC_WTILE_BYTES + (size_t)r * 128;
-            unsigned char *adst = atile + (size_t)s * ATILE + (size_t)arow_i * 128;
             // block = 16 bytes: element j = low nibble of byte j, element j+16 = high nibble of byte j.
             // nibble -> float through the 2^23 magic number (PRMT + FADD), * scale, round once to BF16.
             const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
@@ -160,8 +169,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_q4_tc_kernel(const TcParam
                 o.w = pack_bf16x2(src[6], src[7]);
                 *(uint4 *)(wdst + (((half * 4 + c) ^ (r & 7)) * 16)) = o;
             }
-#pragma unroll
-            for (int c = 0; c < ACH; c++) *(uint4 *)(adst + (((ach0 + c) ^ (arow_i & 7)) * 16)) = av[c];
             // make the generic-proxy writes visible to the tensor core (async proxy), then signal
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
@@ -194,8 +201,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_q4_tc_kernel(const TcParam
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else if (warp == TC_PWARPS + 1) {
+        // ===== TMA issuer: the BN x 64 BF16 token tile of every K stage, as far ahead as the ring allows =====
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&amap) : "memory");
+            for (int kc = 0; kc < nk; kc++) {
+                const int s = kc % TC_STAGES, use = kc / TC_STAGES;
+                tc_mbar_wait(&empty[s], (use & 1) ^ 1);
+                asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(&full[s])), "r"((uint32_t)ATILE) : "memory");
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             ::"r"(tc_smem_u32(atile + (size_t)s * ATILE)), "l"((uint64_t)&amap), "r"(kc * TC_BK), "r"(t0), "r"(tc_smem_u32(&full[s]))
+                             : "memory");
+            }
+        }
     } else {
-        // ===== MMA issuer (one elected lane of the last warp) =====
+        // ===== MMA issuer (one elected lane of warp 8) =====
         const uint32_t idesc = tc_instr_desc<BN>();
         for (int kc = 0; kc < nk; kc++) {
             const int s = kc % TC_STAGES, use = kc / TC_STAGES;
@@ -232,13 +252,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_q4_tc_kernel(const TcParam
     }
 }
 
+typedef CUresult (*tc_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tc_encode_fn tc_encoder() {
+    static tc_encode_fn fn = nullptr;
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            fn = (tc_encode_fn)sym;
+    }
+    return fn;
+}
+
 template <int BN>
 static int launch_tc(jl_ctx *ctx, cudaStream_t stream, const TcParams &p) {
     const size_t smem = (size_t)TC_STAGES * (TC_WTILE_BYTES + (size_t)BN * TC_BK * 2) + 1024;
     static size_t configured[JL_MAX_DEVICES] = {};
     JL_CUDA_CHECK(ctx, jl_ensure_dyn_smem(gemm_q4_tc_kernel<BN>, ctx->device, smem, configured));
+    // tensor map of the BF16 activations [T rows, K cols] (row pitch lda): box = 64 columns (one 128-byte swizzle atom) x BN rows
+    tc_encode_fn enc = tc_encoder();
+    if (!enc) return jl_set_error(ctx, JL_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled is not available");
+    CUtensorMap amap;
+    const cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.T};
+    const cuuint64_t strides[1] = {(cuuint64_t)p.lda * 2};
+    const cuuint32_t box[2] = {TC_BK, (cuuint32_t)BN};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult cr = enc(&amap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)p.a, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return jl_set_error(ctx, JL_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
     dim3 grid(p.N / TC_BM, (p.T + BN - 1) / BN);
-    gemm_q4_tc_kernel<BN><<<grid, TC_THREADS, smem, stream>>>(p);
+    gemm_q4_tc_kernel<BN><<<grid, TC_THREADS, smem, stream>>>(p, amap);
     ctx->launches++;
     JL_CUDA_CHECK(ctx, cudaGetLastError());
     return JL_OK;
@@ -248,7 +292,7 @@ static int launch_tc(jl_ctx *ctx, cudaStream_t stream, const TcParams &p) {
 int jl_launch_gemm_tc(jl_ctx *ctx, cudaStream_t stream, const uint16_t *a_bf16, int lda, int T, const DevTensor &W, int n_rows,
                       int w_col_off, int K, float *out, int ldc, int out_col_off, const float *residual, int res_ld) {
     if (W.dtype != JL_Q4) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "gemm_tc: weights must be Q4");
-    if ((K % TC_BK) || (n_rows % TC_BM) || (w_col_off % TC_BK) || T <= 0 || (lda % 8))
+    if ((K % TC_BK) || (n_rows % TC_BM) || (w_col_off % TC_BK) || T <= 0 || (lda % 8) || ((uintptr_t)a_bf16 % 16))
         return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "gemm_tc: needs K %% 64 == 0 and N %% 128 == 0 (K=%d N=%d)", K, n_rows);
     TcParams p;
     p.a = a_bf16, p.lda = lda, p.T = T;

@@ -571,6 +571,7 @@ int jl_launch_gemv(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p_in, int
     if (p.M < 1 || p.M > GEMV_MAX_M) return jl_set_error(ctx, JL_ERR_INVALID, "gemv: M=%d out of range", p.M);
     if (p.K <= 0 || p.total_rows <= 0) return jl_set_error(ctx, JL_ERR_INVALID, "gemv: empty problem");
     const bool quant_w = (p.w_dtype == JL_Q4 || p.w_dtype == JL_I8);
+    if (!p.sel && jl_gemm8_supported(p, prologue, epilogue)) return jl_launch_gemm8(ctx, stream, p, prologue, epilogue);
     const int rows = p.total_rows;
     const int grid = generic_grid(ctx, rows, 3);
 

@@ -798,7 +798,7 @@ static int forward_rows(jl_model *m, int M, int max_pos, int splits, bool timed,
 
 // Prefill chunk on the tensor cores: the same op sequence as forward_rows with every weight GEMM on tcgen05
 // (BF16 operands, F32 accumulate; jl_gemm_tc.cu).  Norms, RoPE, attention, SiLU stay f32.
-static int forward_rows_tc(jl_model *m, int M, int max_pos, int splits) {
+static int forward_rows_tc(jl_model *m, int M, int max_pos, int splits, int session, int pos0) {
     jl_ctx *ctx = m->ctx;
     const jl_model_config &c = m->cfg;
     const int E = c.embedding_length, hs = c.head_size, H = m->h_seg;
@@ -818,7 +818,9 @@ static int forward_rows_tc(jl_model *m, int M, int max_pos, int splits) {
         ap.rows = M, ap.sessions = m->d_sessions, ap.positions = m->d_positions;
         ap.scale = (float)(1.0 / sqrt((double)hs)), ap.ws = m->attn_ws, ap.splits = splits;
         M_CHECK(jl_launch_rope_kv_append(ctx, m->stream, ap, m->q, false));
-        M_CHECK(jl_launch_paged_attention(ctx, m->stream, ap, max_pos, false));
+        // rows = consecutive positions pos0.. of one session: tiled tensor-core attention (jl_attn_prefill.cu)
+        if (jl_prefill_attention_supported(ap)) M_CHECK(jl_launch_prefill_attention(ctx, m->stream, ap, session, pos0));
+        else M_CHECK(jl_launch_paged_attention(ctx, m->stream, ap, max_pos, false));
         M_CHECK(jl_launch_quantize_bf16(ctx, m->stream, m->att, M, m->attn_seg, 0, m->attn_seg, m->abf));
         M_CHECK(jl_launch_gemm_tc(ctx, m->stream, m->abf, m->attn_seg, M, lw[JL_L_O], E, 0, m->attn_seg, m->xb, E, 0, m->x, E));
         M_CHECK(jl_launch_rmsnorm(ctx, m->stream, m->xb, M, E, lw[JL_L_FFN_NORM].dtype, lw[JL_L_FFN_NORM].data, 0.0f, c.layer_norm_eps, E, 0, E,
@@ -891,7 +893,7 @@ extern "C" int jl_model_batch_forward(jl_model *m, int session, const int32_t *t
         JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_positions, hp + m->maxB, (size_t)cnt * 4, cudaMemcpyHostToDevice, m->stream));
         JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_sessions, hp + 2 * m->maxB, (size_t)cnt * 4, cudaMemcpyHostToDevice, m->stream));
         const int max_pos = start_pos + i + cnt - 1;
-        if (m->tc_ok && cnt >= 16) M_CHECK(forward_rows_tc(m, cnt, max_pos, pick_splits(m, max_pos, cnt)));
+        if (m->tc_ok && cnt >= 16) M_CHECK(forward_rows_tc(m, cnt, max_pos, pick_splits(m, max_pos, cnt), session, start_pos + i));
         else M_CHECK(forward_rows(m, cnt, max_pos, pick_splits(m, max_pos, cnt), false));
         // keep the last row for sample()
         JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->last_hidden + (size_t)session * E, m->x + (size_t)(cnt - 1) * E, (size_t)E * 4,

@@ -205,28 +205,48 @@ def test_persistent_kernel_long_context_splits(cuda_ctx, oracle):
     om.close()
 
 
-def test_concurrent_sessions_batch_decode(cuda_ctx, oracle):
+@pytest.mark.parametrize("name,wdt,nsess", [("tiny", "Q4", 4), ("small", "Q4", 8), ("small", "I8", 8), ("small-hs128", "Q4", 5)])
+def test_concurrent_sessions_batch_decode(cuda_ctx, oracle, name, wdt, nsess):
     """The reference's notion of batch = N concurrent sessions sharing the weights (KvBufferCache.java:58-60);
-    a batched decode step must equal each session decoded alone."""
-    from jlama_b200 import synth
-    cfg, w, gm, om = _models(cuda_ctx, oracle, "tiny", max_sessions=4)
-    prompts = [synth.random_prompt(cfg, 5 + 3 * s, seed=100 + s) for s in range(4)]
-    firsts = []
+    a batched decode step must equal each session decoded alone.  The "small" shapes take the 2..8-row int8
+    tensor-core kernel (jl_gemm8.cu); "tiny" (K = 256) stays on the dp4a kernel."""
+    from jlama_b200 import synth, native
+    cfg, w, gm, om = _models(cuda_ctx, oracle, name, wdtype=getattr(native, wdt), max_sessions=nsess)
+    prompts = [synth.random_prompt(cfg, 5 + 3 * s, seed=100 + s) for s in range(nsess)]
+    firsts, glog = [], [[] for _ in range(nsess)]
     for s, p in enumerate(prompts):
         gm.reset_session(s)
         gm.batch_forward(p, 0, session=s)
-        firsts.append(gm.sample(session=s)[0])
+        tok, lg = gm.sample(session=s)
+        firsts.append(tok)
+        glog[s].append(lg)
     toks = np.array(firsts, dtype=np.int32)
     pos = np.array([len(p) for p in prompts], dtype=np.int32)
     hist = [toks.copy()]
     for _ in range(5):
-        toks, _ = gm.decode(toks, pos)
+        toks, lg = gm.decode(toks, pos, want_logits=True)
         pos += 1
         hist.append(toks.copy())
-    hist = np.array(hist)  # [6, 4]
+        for s in range(nsess):
+            glog[s].append(lg[s])
+    hist = np.array(hist)  # [6, nsess]
+    exact = 0
     for s, p in enumerate(prompts):
-        ot, _ = om.generate(p, 6, want_logits=False)
-        assert list(hist[:, s]) == list(ot), s
+        ot, ol = om.generate(p, 6, want_logits=True)
+        for i in range(6):
+            # logits agree to summation-order level at every step the two sides saw the same inputs
+            # (Q4: the oracle runs the same integer block arithmetic; I8 weights: the oracle is a float dot over dequantised
+            # values, so single int8 activations flip at rounding boundaries -- see tests/test_gpu_layer8b.py)
+            err = np.abs(glog[s][i] - ol[i]).max()
+            assert err <= (2e-3 if wdt == "Q4" else 1e-2) * np.abs(ol[i]).max(), (s, i, err)
+            if hist[i, s] != ot[i]:
+                # a different token is only acceptable on a near tie of the oracle's own top two logits
+                top = np.sort(ol[i])[-2:]
+                assert top[1] - top[0] <= 4 * err, (s, i, float(top[1] - top[0]), float(err))
+                break
+        else:
+            exact += 1
+    assert exact >= nsess - 1  # near ties are rare
     gm.close()
     om.close()
 
@@ -283,6 +303,32 @@ def test_tensor_core_prefill_matches_oracle(cuda_ctx, oracle):
     gm.close()
     ref.close()
     om.close()
+
+
+@pytest.mark.parametrize("name,kvdt,max_batch,n", [("small", "F32", 64, 150), ("small-hs128", "BF16", 48, 130), ("tiny-mha", "F32", 32, 100),
+                                                   ("small-hs128", "F32", 256, 203)])
+def test_tiled_prefill_attention_chunks(cuda_ctx, oracle, name, kvdt, max_batch, n):
+    """The tensor-core prefill path in several chunks (pos0 > 0, ragged last 16-row block, GQA groups 4 / 1, head sizes 64 / 128,
+    F32 and BF16 KV pages): logits after the prompt within the BF16 tolerance of the exact per-position path, and the
+    integer-path decode that follows reads the same KV pages."""
+    from jlama_b200 import native, synth
+    from jlama_b200.model import LlamaModel
+    cfg = synth.get_config(name)
+    w = synth.make_weights(cfg)
+    kv = getattr(native, kvdt)
+    gm = LlamaModel(cuda_ctx, cfg, w, prefill_tensor_core=1, max_batch=max_batch, kv_dtype=kv)
+    ref = LlamaModel(cuda_ctx, cfg, w, kv_dtype=kv, working_qtype=native.F32)
+    prompt = synth.random_prompt(cfg, n)
+    gt, gl = gm.generate(prompt, 3, want_logits=True)
+    rt, rl = ref.generate(prompt, 3, want_logits=True)
+    assert _rel(gl[0], rl[0]) <= 1e-2
+    # K/V rows of the last layer written by the chunked prefill (inputs of every later attention)
+    for pos in (0, n // 2, n - 1):
+        for which in (0, 1):
+            a, b = gm.read_kv(cfg["layers"] - 1, pos, which), ref.read_kv(cfg["layers"] - 1, pos, which)
+            assert np.abs(a - b).max() <= 3e-2 * max(np.abs(b).max(), 1e-3), (pos, which)
+    gm.close()
+    ref.close()
 
 
 @pytest.mark.parametrize("name,act_q8", [("tiny-mixtral", True), ("small-mixtral", True), ("tiny-mixtral", False)])

@@ -18,6 +18,7 @@ SHAPES = [("qkv 8B", 6144, 4096), ("o 8B", 4096, 4096), ("gate 8B", 14336, 4096)
 
 
 def main():
+    batch = "--batch" in sys.argv  # M = 1, 2, 4, 8 without PDL: the 2..8-row tensor-core kernel (jl_gemm8.cu) against M = 1
     quick = "--quick" in sys.argv  # M=1, no PDL, 8B shapes only: for comparing JL_GEMV_CFG / JL_GEMV_AHEAD variants
     tag = "quick"
     peak = 6563.9
@@ -34,13 +35,13 @@ def main():
         s = ((0.5 + rng.random((n * reps, k // 32))) * 0.004).astype(np.float32)
         tid = ctx.lib.jl_register_tensor(ctx.h, native.Q4, n * reps, k, native.ptr(q), native.ptr(s))
         assert tid > 0
-        for m in ((1,) if quick else (1, 4)):
+        for m in ((1,) if quick else ((1, 2, 4, 8) if batch else (1, 4))):
             for mode, mname in ((0, "q8"), (1, "norm+q8"), (2, "f32")):
                 if mode == 2 and m * k * 4 > 190 * 1024:
                     continue
                 if quick and mode == 2 and n < 100000:
                     continue
-                for pdl in ((0,) if quick else (0, 1)):
+                for pdl in ((0,) if quick or batch else (0, 1)):
                     us = C.c_double()
                     ctx.check(ctx.lib.jl_debug_gemv_bench(ctx.h, tid, n, m, mode, 200, pdl, C.byref(us)))
                     gbs = n * k * 0.625 / 1e9 / (us.value * 1e-6)
