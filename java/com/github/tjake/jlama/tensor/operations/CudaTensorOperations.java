@@ -104,8 +104,10 @@ public final class CudaTensorOperations implements TensorOperations {
     @Override public void registerModelTensor(AbstractTensor t) {
         registered.computeIfAbsent(t.getUid(), k -> {
             try {
-                long id = (long) jl_register_tensor.invokeExact(ctx, code(t.dType()), (long) t.shape().first(), (long) t.shape().last(),
-                                                               t.getMemorySegment(), scales(t));
+                // a sparse (row- or column-sliced) weight owns only its slice: register the stored extent
+                // (TensorShape.java:119-133), offsets are rebased per call below
+                long id = (long) jl_register_tensor.invokeExact(ctx, code(t.dType()), (long) t.shape().sparseRowLength(),
+                                                               (long) t.shape().sparseColumnLength(), t.getMemorySegment(), scales(t));
                 if (id < 0) throw new OutOfMemoryError("jl_register_tensor"); // no CPU delegate: fail loudly
                 return id;
             } catch (Error | RuntimeException e) { throw e; } catch (Throwable e) { throw new RuntimeException(e); }
@@ -121,14 +123,21 @@ public final class CudaTensorOperations implements TensorOperations {
             Long id = registered.get(b.getUid());
             int rc;
             if (id == null && (b.dType() == DType.Q4 || b.dType() == DType.I8)) { registerModelTensor(b); id = registered.get(b.getUid()); }
+            // Offsets rebased onto the stored (sparse) extents exactly like NativeSimdTensorOperations.java:96-107:
+            //   aOffset = at.getOffset(0, aColumnOffset), bOffset = bt.getOffset(bt.sparseRowOffset, bColumnOffset),
+            //   rOffset = result.sparseColumnOffset - bt.sparseRowOffset - rRowOffset, adjBRowOffset = bRowOffset - bt.sparseRowOffset
+            final int aOff = a.getOffset(0, aColumnOffset);
+            final int bOff = bColumnOffset - b.shape().sparseColumnOffset();
+            final int rOff = result.shape().sparseColumnOffset() - b.shape().sparseRowOffset() - rRowOffset;
+            final int bRow = bRowOffset - b.shape().sparseRowOffset();
             if (id != null) {
-                rc = (int) jl_gemm.invokeExact(ctx, code(a.dType()), a.getMemorySegment(), scales(a), aColumnOffset, a.getStride(),
-                                               (long) id, bColumnOffset, result.getMemorySegment(), -rRowOffset, a.shape().first(),
-                                               bRowOffset, rowChunkSize, columnLimit, result.getStride());
+                rc = (int) jl_gemm.invokeExact(ctx, code(a.dType()), a.getMemorySegment(), scales(a), aOff, a.getStride(),
+                                               (long) id, bOff, result.getMemorySegment(), rOff, a.shape().first(),
+                                               bRow, rowChunkSize, columnLimit, result.getStride());
             } else {
-                rc = (int) jl_gemm_host.invokeExact(ctx, code(a.dType()), a.getMemorySegment(), aColumnOffset, a.getStride(),
-                                                    code(b.dType()), b.getMemorySegment(), bColumnOffset, b.getStride(),
-                                                    result.getMemorySegment(), -rRowOffset, a.shape().first(), bRowOffset,
+                rc = (int) jl_gemm_host.invokeExact(ctx, code(a.dType()), a.getMemorySegment(), aOff, a.getStride(),
+                                                    code(b.dType()), b.getMemorySegment(), bOff, b.getStride(),
+                                                    result.getMemorySegment(), rOff, a.shape().first(), bRow,
                                                     rowChunkSize, columnLimit, result.getStride());
             }
             check(rc);

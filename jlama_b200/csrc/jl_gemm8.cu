@@ -363,9 +363,15 @@ static int g8_stages(const GemvParams &p) {
 }
 static size_t g8_smem(const GemvParams &p) { return g8_act_smem(p) + G8_RED_BYTES + (size_t)g8_stages(p) * G8_WARPS * G8_STAGE; }
 // warps of a CTA sharing one strip: the largest of 8, 4, 2, 1 that divides the chunk count of a row
-static int g8_ksplit(const GemvParams &p) {
+// Measured at the 8B shapes (gpurun_out/r2_gemv_batch.txt): the split pays while a round's strips do not fill the warps of the
+// chip (o_proj 18.4 -> 14.4 us, down 53 -> 36 us) and costs a little once they do (lm_head 114 -> 129 us): split only as far as
+// needed to give every warp work.
+static int g8_ksplit(const GemvParams &p, int sm_count) {
     const int nch = (p.K / 32) / (p.w_dtype == JL_Q4 ? 8 : 4);
-    for (int s = G8_WARPS; s > 1; s >>= 1)
+    const int strips = (p.total_rows + 15) / 16;
+    int want = 1;
+    while (want < G8_WARPS && strips * want < sm_count * G8_WARPS) want <<= 1;
+    for (int s = want; s > 1; s >>= 1)
         if (nch % s == 0) return s;
     return 1;
 }
@@ -394,7 +400,7 @@ static int launch_g8(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p) {
     static size_t configured[JL_MAX_DEVICES] = {};
     JL_CUDA_CHECK(ctx, jl_ensure_dyn_smem(kern, ctx->device, smem, configured));
     const int strips = (p.total_rows + 15) / 16;
-    const int ksplit = g8_ksplit(p), spr = G8_WARPS / ksplit;
+    const int ksplit = g8_ksplit(p, ctx->sm_count), spr = G8_WARPS / ksplit;
     int grid = ctx->sm_count; // one CTA per SM; a CTA takes 8 / ksplit strips per round
     if (grid > (strips + spr - 1) / spr) grid = (strips + spr - 1) / spr;
     JL_CUDA_CHECK(ctx, jl_launch_kernel(kern, dim3(grid), dim3(G8_THREADS), smem, stream, false, p, nst, ksplit));

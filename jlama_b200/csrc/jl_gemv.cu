@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, MINB) gemv_kernel(const GemvPara
     const int wbytes_per_blk = (WDT == JL_Q4) ? 16 : 32;
     ktrace_begin(p.trace, 0x100u | (unsigned)EPI | ((unsigned long long)prologue << 4) | ((unsigned long long)p.total_rows << 16) |
                               ((unsigned long long)p.K << 40));
+    if (gemv_absent<EPI>(p)) return; // expert held by another rank
 
     // balanced static partition of output rows over all warps of the grid
     const long long gw = (long long)blockIdx.x * GEMV_WARPS + warp;
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(NT, 1) gemv_decode_kernel(const GemvParams p, 
     const int nchunks = LONG ? (nblk + 32 * CH - 1) / (32 * CH) : 1;
     ktrace_begin(p.trace, 0x100u | (unsigned)EPI | ((unsigned long long)PRO << 4) | ((unsigned long long)p.total_rows << 16) |
                               ((unsigned long long)p.K << 40));
+    if (gemv_absent<EPI>(p)) return; // expert held by another rank
 
     // rows of this CTA, items of this warp
     const int R0 = (int)(((long long)p.total_rows * blockIdx.x) / gridDim.x);

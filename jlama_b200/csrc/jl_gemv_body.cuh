@@ -28,6 +28,25 @@ __device__ __forceinline__ void seg_lookup(const GemvParams &p, int row, int &se
     }
 }
 
+// Expert-parallel mixture of experts: the expert this launch was routed to lives on another rank (null entry in the pointer
+// table).  The launch then contributes nothing: outputs are zero (store, SiLU*up) or the running sum passed through (add).
+template <int EPI>
+__device__ __forceinline__ bool gemv_absent(const GemvParams &p) {
+    if (!p.sel) return false;
+    if (p.w_tab[0][__ldg(p.sel)] != nullptr) return false;
+    const long long total = (long long)p.M * p.total_rows;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(i / p.total_rows), rr = (int)(i - (long long)m * p.total_rows);
+        int seg = 0, local = rr;
+        if (EPI != EPI_SILU_MUL) seg_lookup(p, rr, seg, local);
+        const GemvSeg &sg = p.seg[seg];
+        float v = 0.0f;
+        if (EPI == EPI_ADD_RESIDUAL) v = p.residual[(size_t)m * p.res_ld + (p.row0 + local)];
+        sg.out[(size_t)m * sg.out_ld + p.row0 + local + sg.out_off] = v;
+    }
+    return true;
+}
+
 template <int WDT, int CH>
 __device__ __forceinline__ void load_chunk(WBuf<WDT, CH> &b, const uint8_t *wrow, const float *srow, int blk0, int nblk,
                                            int lane, unsigned long long pol) {

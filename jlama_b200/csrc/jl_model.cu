@@ -149,7 +149,7 @@ extern "C" int jl_model_create(jl_ctx *ctx, const jl_model_config *cfg, jl_model
     m->l.resize((size_t)c.num_layers * 9);
     m->l_set.assign((size_t)c.num_layers * 9, 0);
     if (c.num_experts > 0) {
-        if (c.num_experts > 64 || c.experts_per_token < 1 || c.experts_per_token > c.num_experts || m->cfg.tp_size > 1)
+        if (c.num_experts > 64 || c.experts_per_token < 1 || c.experts_per_token > c.num_experts || (c.num_experts % m->cfg.tp_size))
             return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "model_create: %d experts / top-%d (max 64 experts, single rank)", c.num_experts,
                                 c.experts_per_token),
                    delete m, JL_ERR_UNSUPPORTED;
@@ -277,9 +277,14 @@ extern "C" int jl_model_finalize(jl_model *m) {
         if (m->n_exp > 0 && (slot == JL_L_GATE || slot == JL_L_DOWN || slot == JL_L_UP)) continue; // experts instead of a dense MLP
         if (!m->l_set[i]) return jl_set_error(ctx, JL_ERR_INVALID, "model_finalize: layer %zu slot %zu missing", i / 9, slot);
     }
-    for (size_t i = 0; i < m->moe_set.size(); i++)
-        if (!m->moe_set[i])
-            return jl_set_error(ctx, JL_ERR_INVALID, "model_finalize: layer %zu expert tensor %zu missing", i / (1 + m->n_exp * 3), i % (1 + m->n_exp * 3));
+    // expert parallelism (BASELINE config 5: "expert FFN GEMMs sharded one-per-GPU"): rank r holds the experts e with
+    // e % tp_size == r (whole, not row-split); the router is replicated.  Tensors of other ranks' experts stay unset.
+    for (size_t i = 0; i < m->moe_set.size(); i++) {
+        const size_t per = 1 + (size_t)m->n_exp * 3, slot = i % per;
+        const bool mine = slot == 0 || (int)((slot - 1) / 3) % c.tp_size == c.tp_rank;
+        if (mine && !m->moe_set[i]) return jl_set_error(ctx, JL_ERR_INVALID, "model_finalize: layer %zu expert tensor %zu missing", i / per, slot);
+        if (!mine && m->moe_set[i]) return jl_set_error(ctx, JL_ERR_INVALID, "model_finalize: layer %zu expert tensor %zu belongs to another rank", i / per, slot);
+    }
     // the fused QKV and gate+up launches decode all their segments with one weight dtype: a checkpoint that mixes
     // precisions inside a fused group (e.g. Q in Q4, K/V left in BF16) must be rejected, not mis-read
     for (int L = 0; L < c.num_layers; L++) {
@@ -328,18 +333,24 @@ extern "C" int jl_model_finalize(jl_model *m) {
     M_CHECK(dev_alloc(ctx, (void **)&m->k, B * m->kv_seg * 4));
     M_CHECK(dev_alloc(ctx, (void **)&m->v, B * m->kv_seg * 4));
     M_CHECK(dev_alloc(ctx, (void **)&m->att, B * m->attn_seg * 4));
-    M_CHECK(dev_alloc(ctx, (void **)&m->hbuf, B * m->h_seg * 4));
+    // experts are held whole (expert parallelism), so their hidden activations need the full hidden length
+    M_CHECK(dev_alloc(ctx, (void **)&m->hbuf, B * (size_t)(m->n_exp > 0 ? c.hidden_length : m->h_seg) * 4));
     if (m->n_exp > 0) {
         M_CHECK(dev_alloc(ctx, (void **)&m->moe_logits, B * m->n_exp * 4));
         M_CHECK(dev_alloc(ctx, (void **)&m->moe_sel, B * m->exp_k * 4));
         const size_t ne = (size_t)c.num_layers * 3 * m->n_exp;
         std::vector<void *> wt(ne);
         std::vector<float *> st(ne);
-        int wd0 = m->moe_w[0].dtype;
+        int wd0 = m->moe_w[(size_t)c.tp_rank * 3].dtype; // expert tp_rank is the first one this rank holds
         for (int L = 0; L < c.num_layers; L++)
             for (int w = 0; w < 3; w++)
                 for (int e = 0; e < m->n_exp; e++) {
                     const DevTensor &t = m->moe_w[((size_t)L * m->n_exp + e) * 3 + w];
+                    if (e % c.tp_size != c.tp_rank) { // another rank's expert: null table entries, the GEMV contributes nothing
+                        wt[((size_t)L * 3 + w) * m->n_exp + e] = nullptr;
+                        st[((size_t)L * 3 + w) * m->n_exp + e] = nullptr;
+                        continue;
+                    }
                     if (t.dtype != wd0 || (wd0 != JL_Q4 && wd0 != JL_I8))
                         return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "model_finalize: expert weights must share one quantised dtype (Q4 or I8)");
                     wt[((size_t)L * 3 + w) * m->n_exp + e] = t.data;
@@ -387,7 +398,8 @@ extern "C" int jl_model_finalize(jl_model *m) {
     // mixture of experts: the router plus the experts_per_token selected experts are streamed per token
     for (int L = 0; L < c.num_layers && m->n_exp > 0; L++) {
         wb += tb(m->moe_gate[L]);
-        for (int w = 0; w < 3; w++) wb += (int64_t)m->exp_k * tb(m->moe_w[((size_t)L * m->n_exp) * 3 + w]);
+        // expert parallel: on average experts_per_token / tp_size of them live on this rank
+        for (int w = 0; w < 3; w++) wb += (int64_t)m->exp_k * tb(m->moe_w[((size_t)L * m->n_exp + c.tp_rank) * 3 + w]) / c.tp_size;
     }
     wb += tb(m->g_set[JL_T_LM_HEAD] ? m->g[JL_T_LM_HEAD] : m->g[JL_T_EMBED]);
     m->weight_bytes = wb;
@@ -706,10 +718,14 @@ static int forward_rows(jl_model *m, int M, int max_pos, int splits, bool timed,
             // are summed UNWEIGHTED in selection order (:139-143), then the residual is added (TransformerBlock.java:203).
             // Row b of the result is the sum over row b's experts (the reference's copy of expert 0's result into row 0 for
             // every batch row, MoEBlock.java:141, is a bug we do not reproduce; with one row per call they coincide).
-            const int NE = m->n_exp, KE = m->exp_k, H = m->h_seg;
+            // Expert parallel (tp_size > 1): every rank routes identically (replicated router), a selected expert held by another
+            // rank has a null table entry and its launches only write zeros / pass the running sum through (gemv_absent); the
+            // per-rank sums then meet in one all-reduce.  With two experts per token that sum is exact in any order.
+            const int NE = m->n_exp, KE = m->exp_k, H = c.hidden_length;
             void **wt = m->moe_wtab + (size_t)L * 3 * NE;
             float **st = m->moe_stab + (size_t)L * 3 * NE;
-            const bool aq = act_q(m->moe_w[(size_t)L * NE * 3]);
+            const size_t own = ((size_t)L * NE + c.tp_rank) * 3; // first expert held by this rank: shapes / dtype of every expert
+            const bool aq = act_q(m->moe_w[own]);
             for (int b = 0; b < M; b++) {
                 {
                     GemvParams p = {};
@@ -719,11 +735,11 @@ static int forward_rows(jl_model *m, int M, int max_pos, int splits, bool timed,
                     p.a = m->xb + (size_t)b * E, p.lda = E;
                     p.norm_w = lw[JL_L_FFN_NORM].data, p.norm_w_dtype = lw[JL_L_FFN_NORM].dtype, p.norm_eps = c.layer_norm_eps, p.norm_E = E;
                     p.total_rows = NE;
-                    M_CHECK(run_gemm(m, p, act_q(m->moe_gate[L]) ? PRO_RMSNORM_QUANT : PRO_RMSNORM_F32, EPI_STORE, 1, (size_t)E * 4, false));
+                    M_CHECK(run_gemm(m, p, act_q(m->moe_gate[L]) ? PRO_RMSNORM_QUANT : PRO_RMSNORM_F32, EPI_STORE, 1, (size_t)E * 4, false, false));
                 }
                 M_CHECK(jl_launch_moe_route(ctx, m->stream, m->moe_logits + (size_t)b * NE, 1, NE, KE, m->moe_sel + (size_t)b * KE));
                 for (int i = 0; i < KE; i++) {
-                    const DevTensor &proto = m->moe_w[(size_t)L * NE * 3]; // shapes / dtype of every expert
+                    const DevTensor &proto = m->moe_w[own];
                     GemvParams p = {};
                     p.nseg = 2;
                     set_w(p, 0, proto, m->hbuf, H);
@@ -735,10 +751,11 @@ static int forward_rows(jl_model *m, int M, int max_pos, int splits, bool timed,
                     p.a = m->xb + (size_t)b * E, p.lda = E;
                     p.norm_w = lw[JL_L_FFN_NORM].data, p.norm_w_dtype = lw[JL_L_FFN_NORM].dtype, p.norm_eps = c.layer_norm_eps, p.norm_E = E;
                     p.total_rows = H;
-                    M_CHECK(run_gemm(m, p, aq ? PRO_RMSNORM_QUANT : PRO_RMSNORM_F32, EPI_SILU_MUL, 1, (size_t)E * 4, false));
+                    // (no programmatic early launch: the selection is read before any dependency wait)
+                    M_CHECK(run_gemm(m, p, aq ? PRO_RMSNORM_QUANT : PRO_RMSNORM_F32, EPI_SILU_MUL, 1, (size_t)E * 4, false, false));
                     GemvParams d = {};
                     d.nseg = 1;
-                    const DevTensor &dproto = m->moe_w[(size_t)L * NE * 3 + 1];
+                    const DevTensor &dproto = m->moe_w[own + 1];
                     set_w(d, 0, dproto, m->x + (size_t)b * E, E);
                     d.sel = p.sel;
                     d.w_tab[0] = (const void *const *)(wt + 1 * NE), d.ws_tab[0] = (const float *const *)(st + 1 * NE); // w2
@@ -746,9 +763,10 @@ static int forward_rows(jl_model *m, int M, int max_pos, int splits, bool timed,
                     d.a = m->hbuf, d.lda = H;
                     d.residual = m->x + (size_t)b * E, d.res_ld = E; // expert i > 0 accumulates onto the sum so far
                     d.total_rows = E;
-                    M_CHECK(run_gemm(m, d, aq ? PRO_F32_QUANT : PRO_F32, i == 0 ? EPI_STORE : EPI_ADD_RESIDUAL, 1, (size_t)H * 4, false));
+                    M_CHECK(run_gemm(m, d, aq ? PRO_F32_QUANT : PRO_F32, i == 0 ? EPI_STORE : EPI_ADD_RESIDUAL, 1, (size_t)H * 4, false, false));
                 }
             }
+            if (c.tp_size > 1) M_CHECK(jl_comm_allreduce_dev(ctx, m->stream, m->x, (size_t)M * E));
             M_CHECK(jl_launch_accumulate(ctx, m->stream, m->x, M, E, JL_F32, m->xb, nullptr, M, E, 0, E)); // + residual
             continue;
         }

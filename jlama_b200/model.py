@@ -164,6 +164,8 @@ class LlamaModel:
             if cfg.get("experts"):  # MixtralModel.java:88-105
                 put_expert(i, -1, 0, b + "block_sparse_moe.gate.weight")
                 for e in range(cfg["experts"]):
+                    if e % tp_size != self.dctx.model_shard:
+                        continue  # expert parallelism: expert e lives (whole) on rank e % tp_size
                     for which, nm in ((0, "w1"), (1, "w2"), (2, "w3")):
                         put_expert(i, e, which, b + "block_sparse_moe.experts.%d.%s.weight" % (e, nm))
                 continue

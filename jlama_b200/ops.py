@@ -68,21 +68,34 @@ class CudaTensorOperations:
         if not (r_row_offset == 0 or r_row_offset >= b_row_offset):
             raise ValueError("Result offset must be >= b row offset")  # :108
         h = self.ctx.h
+        # sparse operands store a slice of their logical shape: rebase every offset onto the stored extent exactly like
+        # NativeSimdTensorOperations.java:96-107 (aOffset = at.getOffset(0, aColumnOffset), bOffset relative to b's stored
+        # columns, rOffset = result.sparseColumnOffset - b.sparseRowOffset - rRowOffset, adjBRowOffset = bRowOffset - b.sparseRowOffset)
+        if a.is_sparse() or b.is_sparse() or result.is_sparse():
+            r_off = result.sparse_col_off - b.sparse_row_off - r_row_offset
+            return self._batch_dot_product_raw(result, a, b, a_column_offset - a.sparse_col_off, b_column_offset - b.sparse_col_off,
+                                               column_limit, r_off, b_row_offset - b.sparse_row_off, row_chunk_size)
+        return self._batch_dot_product_raw(result, a, b, a_column_offset, b_column_offset, column_limit, -r_row_offset, b_row_offset,
+                                           row_chunk_size)
+
+    def _batch_dot_product_raw(self, result, a, b, a_column_offset, b_column_offset, column_limit, roffset, b_row_offset, row_chunk_size):
+        """offsets relative to the STORED buffers; `roffset` is subtracted from the output column index (vector_simd.c:344)"""
+        h = self.ctx.h
         if b.uid in self._registered:
             rc = self.lib.jl_gemm(h, a.dtype, ptr(a.data), ptr(a.scales), a_column_offset, a.cols,
-                                  self._registered[b.uid], b_column_offset, ptr(result.data), -r_row_offset,
+                                  self._registered[b.uid], b_column_offset, ptr(result.data), roffset,
                                   a.rows, b_row_offset, row_chunk_size, column_limit, result.cols)
         else:
             if b.dtype in (Q4, I8):
                 # unregistered quantised B: register on the fly (the reference would take its CPU delegate,
                 # NativeGPUTensorOperations.java:321-334; there is none here)
                 self.register_model_tensor(b)
-                return self.batch_dot_product(result, a, b, a_column_offset, b_column_offset, column_limit,
-                                              r_row_offset, b_row_offset, row_chunk_size)
+                return self._batch_dot_product_raw(result, a, b, a_column_offset, b_column_offset, column_limit,
+                                                   roffset, b_row_offset, row_chunk_size)
             if a.dtype == I8:
                 raise native.UnsupportedOperation(native.JL_ERR_UNSUPPORTED, "I8 x %d" % b.dtype)
             rc = self.lib.jl_gemm_host(h, a.dtype, ptr(a.data), a_column_offset, a.cols, b.dtype, ptr(b.data),
-                                       b_column_offset, b.cols, ptr(result.data), -r_row_offset, a.rows, b_row_offset,
+                                       b_column_offset, b.cols, ptr(result.data), roffset, a.rows, b_row_offset,
                                        row_chunk_size, column_limit, result.cols)
         self.ctx.check(rc)
 

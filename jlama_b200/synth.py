@@ -28,6 +28,7 @@ CONFIGS = {
     "llama-tp8-test": dict(ctx=512, E=1024, H=3584, heads=16, kv_heads=8, layers=3, vocab=4096, eps=1e-5, rope_theta=500000.0),
     # mixture of experts (Mixtral layout: 8 experts, top-2) at test size
     "tiny-mixtral": dict(ctx=256, E=256, H=512, heads=8, kv_heads=4, layers=2, vocab=512, eps=1e-5, rope_theta=10000.0, experts=8, experts_per_token=2),
+    "mixtral-tp8-test": dict(ctx=256, E=1024, H=1024, heads=16, kv_heads=8, layers=2, vocab=1024, eps=1e-5, rope_theta=1000000.0, experts=8, experts_per_token=2),
     "small-mixtral": dict(ctx=512, E=1024, H=2048, heads=8, kv_heads=2, layers=3, vocab=1024, eps=1e-5, rope_theta=1000000.0, experts=4, experts_per_token=2),
     # BASELINE.json configs (public HF config.json dims)
     "llama-3.2-1b": dict(ctx=131072, E=2048, H=8192, heads=32, kv_heads=8, layers=16, vocab=128256, eps=1e-5,
@@ -152,6 +153,17 @@ def make_weights(cfg, wdtype=Q4, mode="quantize", embed_dtype=None, threads=None
     with ThreadPoolExecutor(max_workers=threads) as ex:
         vals = list(ex.map(lambda sp: make_one(cfg, sp[0], sp[1], sp[2], sp[3], wdtype, mode, embed_dtype, q4_fn), specs))
     return {sp[0]: v for sp, v in zip(specs, vals)}
+
+
+def lazy_weights(cfg, wdtype=Q4, mode="quantize", embed_dtype=None, q4_fn=None):
+    """get(name) -> tensor generated on demand (same seeds and bytes as make_weights).  A rank of a tensor- / expert-parallel job
+    only asks for what it holds, so a Mixtral-8x7B shard never materialises the other ranks' 29 GB."""
+    specs = {sp[0]: sp for sp in tensor_specs(cfg)}
+
+    def get(name):
+        sp = specs.get(name)
+        return None if sp is None else make_one(cfg, sp[0], sp[1], sp[2], sp[3], wdtype, mode, embed_dtype, q4_fn)
+    return get
 
 
 def linear_weight_count(cfg):

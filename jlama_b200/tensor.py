@@ -130,6 +130,53 @@ class AbstractTensor:
     def shape(self):
         return (self.rows, self.cols)
 
+    # ---- sparse shapes (core/tensor/TensorShape.java:37-44,94-133): a tensor may STORE only a column range
+    # [sparse_col_off, sparse_col_off + cols) or a row range [sparse_row_off, sparse_row_off + rows) of its logical
+    # shape; callers keep using logical indices and every operator rebases them (NativeSimdTensorOperations.java:96-107)
+    sparse_col_off = 0
+    sparse_row_off = 0
+    logical_shape = None
+
+    def is_sparse(self):
+        return self.logical_shape is not None
+
+    def get_offset(self, row, col):
+        """TensorShape.getOffset(row, col) (:94-99): element offset inside the stored buffer."""
+        return self.cols * (row - self.sparse_row_off) + col - self.sparse_col_off
+
+    def _column_slice(self, offset, length):
+        raise NotImplementedError
+
+    def sparsify(self, offset, length):
+        """AbstractTensor.sparsify (core/tensor/AbstractTensor.java:151-172): copy of the column range, logical indices kept."""
+        if self.is_sparse() or length == self.cols:
+            return self
+        t = self._column_slice(offset, length)
+        t.sparse_col_off, t.logical_shape = offset, (self.rows, self.cols)
+        return t
+
+    def sparsify_rows(self, offset, length):
+        """TensorShape.sparseRow (:41-44): the row-range counterpart (jlama-net's row split of a weight)."""
+        if self.is_sparse() or length == self.rows:
+            return self
+        t = self._row_slice(offset, length)
+        t.sparse_row_off, t.logical_shape = offset, (self.rows, self.cols)
+        return t
+
+    def _row_slice(self, offset, length):
+        t = self._column_slice(0, self.cols)
+        t.data = np.ascontiguousarray(t.data[offset:offset + length])
+        if t.scales is not None:
+            t.scales = np.ascontiguousarray(t.scales[offset:offset + length])
+        return t
+
+    def get(self, row, col):
+        """AbstractTensor.get with logical indices; outside the stored range it raises (TestParser.testSparsify)."""
+        r, c = row - self.sparse_row_off, col - self.sparse_col_off
+        if not (0 <= r < self.rows and 0 <= c < self.cols):
+            raise IndexError("(%d, %d) is outside the stored range of this sparse tensor" % (row, col))
+        return float(self.to_float()[r, c])
+
     def to_float(self):
         raise NotImplementedError
 
@@ -158,6 +205,9 @@ class FloatBufferTensor(AbstractTensor):
     def to_float(self):
         return self.data
 
+    def _column_slice(self, offset, length):
+        return FloatBufferTensor(self.data[:, offset:offset + length].copy())
+
 
 class BFloat16BufferTensor(AbstractTensor):
     dtype = BF16
@@ -172,6 +222,9 @@ class BFloat16BufferTensor(AbstractTensor):
     def to_float(self):
         return bfloat16_to_float32(self.data)
 
+    def _column_slice(self, offset, length):
+        return BFloat16BufferTensor(self.data[:, offset:offset + length].copy())
+
 
 class Q8ByteBufferTensor(AbstractTensor):
     dtype = I8
@@ -185,6 +238,10 @@ class Q8ByteBufferTensor(AbstractTensor):
 
     def to_float(self):
         return (self.data.astype(np.float32).reshape(self.rows, -1, BLOCK) * self.scales[..., None]).reshape(self.rows, -1)
+
+    def _column_slice(self, offset, length):
+        assert offset % BLOCK == 0 and length % BLOCK == 0
+        return Q8ByteBufferTensor(self.data[:, offset:offset + length].copy(), self.scales[:, offset // BLOCK:(offset + length) // BLOCK].copy())
 
 
 class Q4ByteBufferTensor(AbstractTensor):
@@ -203,3 +260,7 @@ class Q4ByteBufferTensor(AbstractTensor):
 
     def to_float(self):
         return dequantize_q4(self.data, self.scales)
+
+    def _column_slice(self, offset, length):
+        assert offset % BLOCK == 0 and length % BLOCK == 0
+        return Q4ByteBufferTensor(self.data[:, offset // 2:(offset + length) // 2].copy(), self.scales[:, offset // BLOCK:(offset + length) // BLOCK].copy())

@@ -104,6 +104,32 @@ def test_result_offset_and_row_chunks(cuda_ops, oracle):
     assert np.array_equal(c2.data[:, 32:], c1.data[:, 32:ROWS])
 
 
+@pytest.mark.parametrize("bkind", ["Q4", "I8W", "F32"])
+def test_sparse_operands_rebase_offsets(cuda_ops, oracle, bkind):
+    """Sparse (column- / row-sliced) operands behind the same logical call (TensorShape.java:94-133,
+    NativeSimdTensorOperations.java:96-107): the row split of jlama-net hands the operators exactly these shapes."""
+    from jlama_b200 import tensor as T
+    rng = np.random.default_rng(77)
+    M, K, N = 3, 256, 64
+    a, ao = _tensors(T, oracle, "F32", _mk(rng, M, K))
+    b, bo = _tensors(T, oracle, bkind, _mk(rng, N, K, 0.0, 1.0))
+    ref = oracle.batch_dot(ao, bo, 64, 64, 128, 0, 0, N)  # dense: columns [64, 192) of both operands
+    # column-sparse a and b, logical offsets unchanged
+    c = T.FloatBufferTensor(np.zeros((M, N), dtype=np.float32))
+    cuda_ops.batch_dot_product(c, a.sparsify(64, 128), b.sparsify(64, 128), 64, 64, 128)
+    assert np.abs(c.data - ref).max() <= 2e-5 * np.abs(ref).max()
+    # row-sparse b (rows [16, 48) stored), dense result: logical rows land at their logical columns
+    full = oracle.batch_dot(ao, bo, 0, 0, K, 0, 0, N)
+    c = T.FloatBufferTensor(np.zeros((M, N), dtype=np.float32))
+    cuda_ops.batch_dot_product(c, a, b.sparsify_rows(16, 32), 0, 0, K, 0, 16, 32)
+    assert np.abs(c.data[:, 16:48] - full[:, 16:48]).max() <= 2e-5 * np.abs(full).max()
+    assert not c.data[:, :16].any() and not c.data[:, 48:].any()
+    # ... and a column-sparse result that stores only those 32 columns
+    cs = T.FloatBufferTensor(np.zeros((M, N), dtype=np.float32)).sparsify(16, 32)
+    cuda_ops.batch_dot_product(cs, a, b.sparsify_rows(16, 32), 0, 0, K, 0, 16, 32)
+    assert np.abs(cs.data - full[:, 16:48]).max() <= 2e-5 * np.abs(full).max()
+
+
 def test_dot_product_batch_chunk(cuda_ops, oracle):
     # testBatchChunked (:492-513)
     from jlama_b200 import tensor as T

@@ -21,7 +21,9 @@ def _gpus():
         return 0
 
 
-@pytest.mark.parametrize("world,cfg", [(2, "small"), (2, "small-hs128"), (4, "tiny"), (8, "llama-tp8-test")])
+@pytest.mark.parametrize("world,cfg", [(2, "small"), (2, "small-hs128"), (4, "tiny"), (8, "llama-tp8-test"),
+                                       # expert parallel Mixtral (BASELINE config 5): attention row-split, experts whole, one all-reduce
+                                       (2, "small-mixtral"), (4, "tiny-mixtral"), (8, "mixtral-tp8-test")])
 def test_tp_generate_matches_oracle(world, cfg):
     if _gpus() < world:
         pytest.skip("needs %d GPUs" % world)

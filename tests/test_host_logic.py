@@ -117,3 +117,27 @@ def test_tensor_parallel_slicing_reassembles(oracle):
         dt, q, s = _slice_rows(t, d.kvSegmentStart, d.kvSegmentLength)
         parts.append(oracle.dequantize_q4(q, s))
     assert np.array_equal(np.concatenate(parts, axis=0), full)
+
+
+def test_sparsify_keeps_logical_indices():
+    """Port of TestParser.testSparsify (jlama-tests/.../safetensors/TestParser.java:137-170): a column-sparse copy answers the
+    logical indices of its range and refuses everything else; TensorShape.getOffset (:94-99) for the stored buffer."""
+    from jlama_b200 import tensor as T
+    dim = 96
+    b = T.FloatBufferTensor(np.arange(dim * dim, dtype=np.float32).reshape(dim, dim))
+    bt = b.sparsify(32, 20)
+    assert b.data.size == dim * dim and bt.data.size == dim * 20 and bt.is_sparse()
+    for row in (0, 5, dim - 1):
+        for col in range(dim):
+            if 32 <= col < 52:
+                assert bt.get(row, col) == row * dim + col
+                assert bt.data.reshape(-1)[bt.get_offset(row, col)] == row * dim + col
+            else:
+                with pytest.raises(IndexError):
+                    bt.get(row, col)
+    assert b.sparsify(0, dim) is b and bt.sparsify(0, 4) is bt  # AbstractTensor.java:152-154
+    br = b.sparsify_rows(10, 7)
+    assert br.get(12, 3) == 12 * dim + 3 and br.get_offset(12, 3) == 2 * dim + 3
+    q = T.Q4ByteBufferTensor.from_float(np.random.default_rng(0).standard_normal((8, 128)).astype(np.float32))
+    qs = q.sparsify(64, 32)
+    assert qs.cols == 32 and np.array_equal(qs.to_float(), q.to_float()[:, 64:96])

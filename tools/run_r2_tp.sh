@@ -1,12 +1,13 @@
 #!/bin/bash
-# tensor-parallel bring-up on N GPUs of one box: parity tests (torchrun inside pytest), then bench at 2 ranks
+# tensor- / expert-parallel run on N GPUs of one box (N = $1): the world-size-N parity tests (torchrun inside pytest), the bench at
+# N ranks, and at N = 8 the Mixtral-8x7B expert-parallel line
 mkdir -p gpurun_out
-nvidia-smi -L | head -8
-timeout 1200 python -m pytest tests/test_gpu_tp.py -m gpu -q -s > gpurun_out/r2_pytest_tp.txt 2>&1
-echo "pytest tp rc=$?"
-grep -E "tp=|passed|failed|skipped|Error|error" gpurun_out/r2_pytest_tp.txt | tail -20
 N=${1:-2}
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 64 --warmup 8 > gpurun_out/r2_bench_tp$N.json 2> gpurun_out/r2_bench_tp$N.err
+nvidia-smi -L | head -8
+timeout 1200 python -m pytest tests/test_gpu_tp.py -m gpu -q -s --timeout 600 -k "[$N-" > gpurun_out/r2_pytest_tp$N.txt 2>&1
+echo "pytest tp rc=$?"
+grep -E "tp=|passed|failed|skipped|Error|error" gpurun_out/r2_pytest_tp$N.txt | tail -20
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29511 + N)) bench.py --gpus $N --steps 128 --warmup 16 > gpurun_out/r2_bench_tp$N.json 2> gpurun_out/r2_bench_tp$N.err
 echo "bench tp$N rc=$?"
 python - <<PY
 import json
@@ -16,4 +17,10 @@ try:
 except Exception as e:
     print('bench parse failed', e)
 PY
-tail -6 gpurun_out/r2_bench_tp$N.err
+tail -3 gpurun_out/r2_bench_tp$N.err
+if [ $N -eq 8 ]; then
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --model mixtral-8x7b --weights direct --steps 64 --warmup 8 > gpurun_out/r2_bench_mixtral_tp$N.json 2> gpurun_out/r2_bench_mixtral_tp$N.err
+  echo "bench mixtral tp$N rc=$?"
+  cat gpurun_out/r2_bench_mixtral_tp$N.json | cut -c1-1500
+  tail -4 gpurun_out/r2_bench_mixtral_tp$N.err
+fi
