@@ -122,15 +122,15 @@ def measured_peaks():
 
 
 def measured_traffic(cfg):
-    """DRAM bytes of one token's quantised GEMV launches from the committed ncu capture (profiles/), or None."""
-    p = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    """DRAM bytes (read + written) of one decode step from the committed ncu capture of the persistent decode kernel
+    (profiles/r2_ncu_traffic.json: `ncu --set full`, one launch = one token), or None for another model."""
+    p = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
     if not os.path.exists(p):
         return None
     d = json.load(open(p))
     if d.get("model") != cfg["name"]:
         return None
-    per = d["per_launch_bytes"]
-    return d["layers"] * (per["qkv"] + per["o_proj"] + per["gate_up"] + per["down"]) + d["algorithmic_bytes"]["lm_head"]
+    return int(d["per_token_bytes"])
 
 
 def make_model_weights(cfg, mode, q4_fn=None):
@@ -209,12 +209,8 @@ def config3_workload(ctx, cfg, peak, sessions=8, prompt_tokens=2048, decode_toke
     return out
 
 
-def teacher_forced_parity(model, prompt, ref_tokens, ref_logits):
-    """Feed the GPU the REFERENCE's tokens, so that every step compares the two sides on identical inputs (a free-running
-    comparison stops being meaningful at the first divergent token).  Where the arg-max differs, `reference_gap_rel` says how
-    much the reference itself prefers its token over the GPU's (relative to the largest |logit|): on the synthetic random-weight
-    network many steps are near ties -- the reference's AVX-512 kernels and the plain-C port of the same arithmetic pick
-    different tokens at step 0 of the bench prompt (tools/parity_margin.py, profiles/r2_parity_margin.txt)."""
+def teacher_forced_logits(model, prompt, ref_tokens):
+    """Feed the GPU the REFERENCE's tokens (every rank of a tensor-parallel job runs this with the same tokens): logits per step."""
     n = len(ref_tokens)
     model.reset_session(0)
     model.batch_forward(prompt, 0)
@@ -223,6 +219,16 @@ def teacher_forced_parity(model, prompt, ref_tokens, ref_logits):
     for i in range(1, n):
         _, lg = model.decode(np.array([ref_tokens[i - 1]], dtype=np.int32), np.array([len(prompt) + i - 1], dtype=np.int32), want_logits=True)
         logits.append(lg[0])
+    return logits
+
+
+def teacher_forced_parity(logits, ref_logits):
+    """Every step compares the two sides on identical inputs (a free-running comparison stops being meaningful at the first
+    divergent token).  Where the arg-max differs, `reference_gap_rel` says how much the reference itself prefers its token over
+    the GPU's (relative to the largest |logit|): on the synthetic random-weight network many steps are near ties -- the
+    reference's AVX-512 kernels and the plain-C port of the same arithmetic pick different tokens at step 0 of the bench prompt
+    (tools/parity_margin.py, profiles/r2_parity_margin.txt)."""
+    n = len(ref_logits)
     rels, agree, dis = [], 0, []
     for i in range(n):
         rl = np.asarray(ref_logits[i])
@@ -538,8 +544,15 @@ def main():
                          decode_s=time.time() - t0, threads=o.num_threads())
         barrier()
         gt, gl = model.generate(cp, n_cpu, want_logits=True)
-        tf = teacher_forced_parity(model, cp, r["tokens"], r["logits"]) if world == 1 else None
+        ref_tokens = [int(t) for t in r["tokens"]] if rank == 0 else [0] * n_cpu
+        if dist is not None:  # every rank replays the reference's tokens
+            import torch
+            tt = torch.tensor(ref_tokens, dtype=torch.int64, device="cuda")
+            dist.broadcast(tt, 0)
+            ref_tokens = [int(x) for x in tt.cpu().tolist()]
+        tf_logits = teacher_forced_logits(model, cp, ref_tokens)
         if rank == 0:
+            tf = teacher_forced_parity(tf_logits, r["logits"])
             div = first_divergence(gt, r["tokens"])
             upto = n_cpu if div is None else div + 1
             rel = max(float(np.abs(gl[i] - r["logits"][i]).max() / np.abs(r["logits"][i]).max()) for i in range(upto))

@@ -252,6 +252,11 @@ int jl_model_decode_resident(jl_model *m, int session, int32_t first_token, int 
                              int32_t *out_tokens);
 /* test hooks: copy a K/V row (f32) or the hidden rows of the last batch_forward chunk to HOST */
 int jl_model_read_kv(jl_model *m, int session, int layer, int position, int which /*0=K,1=V*/, float *out);
+/* KvBufferCache.KvBufferPage persistence (core/tensor/KvBufferCache.java:121-176): write / read the allocated KV pages of a session
+ * as  <dir>/<session_name>-L<layerPage>C<contextPage>.page  (raw little-endian page bytes, the reference's file naming and layout).
+ * Return the number of pages written / read (>= 0) or a JL_ERR_*.  After a load the caller continues at the position it saved. */
+int jl_model_kv_save(jl_model *m, int session, const char *dir, const char *session_name);
+int jl_model_kv_load(jl_model *m, int session, const char *dir, const char *session_name);
 int jl_model_read_hidden(jl_model *m, int session, float *out /* [embedding_length] last row */);
 /* test hook: copy `n` floats of an internal activation buffer of the LAST forward/decode call to HOST (row 0 first).
  * which: 0 = x (hidden after the last layer), 1 = xb (after attention + residual), 2 = q, 3 = k, 4 = v (raw projections),

@@ -40,12 +40,11 @@ __device__ __forceinline__ void pa_ldsm4t(uint32_t (&r)[4], uint32_t addr) {
                  : "r"(addr));
 }
 
-// K row of `pos` in the page of (session, layer); the V row is `v_off` bytes further (same page, which = 1)
-__device__ __forceinline__ const char *pa_k_row(const KvLayout &kv, int session, int layer, int pos, int esz) {
-    const int lp = layer / kv.layers_per_page, rl = layer % kv.layers_per_page;
-    const int cp = pos / kv.ctx_per_page, rc = pos % kv.ctx_per_page;
-    const char *base = (const char *)kv.page_table[((size_t)session * kv.n_layer_pages + lp) * kv.n_ctx_pages + cp];
-    return base + (((size_t)rl * 2) * kv.ctx_per_page + rc) * kv.kv_len * esz;
+// base of the context page `cp` of (session, layer); K row rc of the layer is at ((rl*2)*ctx_per_page + rc)*kv_len elements,
+// the V row `v_off` bytes further (same page, which = 1)
+__device__ __forceinline__ const char *pa_page(const KvLayout &kv, int session, int layer, int cp) {
+    const int lp = layer / kv.layers_per_page;
+    return (const char *)kv.page_table[((size_t)session * kv.n_layer_pages + lp) * kv.n_ctx_pages + cp];
 }
 
 template <int HS, int KVDT, int NW>
@@ -103,16 +102,36 @@ __global__ void __launch_bounds__(NW * 32) prefill_attention_kernel(const AttnPa
     const int lm = lane >> 3, lr = lane & 7; // ldmatrix: matrix index and row supplied by this lane
     const int srow = tid / C4, sc4 = tid % C4;
 
+    // A 64-position tile touches at most two context pages; their bases are looked up one tile ahead, so that the row loads of a
+    // tile do not wait for a page-table load first.
+    const int cpp = p.kv.ctx_per_page;
+    const size_t layer_off = ((size_t)(p.layer % p.kv.layers_per_page) * 2) * cpp * p.kv.kv_len * esz + ((size_t)kvh * HS + sc4 * 4) * esz;
+    const size_t row_bytes = (size_t)p.kv.kv_len * esz;
+    const char *nb0 = pa_page(p.kv, session, p.layer, 0), *nb1 = nb0;
+    {
+        const int c1 = min(PA_KT - 1, last_key) / cpp;
+        if (c1 != 0) nb1 = pa_page(p.kv, session, p.layer, c1);
+    }
     for (int tile = 0; tile < ntiles; tile++) {
         const int t0 = tile * PA_KT;
+        const char *b0 = nb0, *b1 = nb1;
+        const int cp0 = t0 / cpp;
+        if (tile + 1 < ntiles) { // next tile's pages
+            const int n0 = (t0 + PA_KT) / cpp, n1 = min(t0 + 2 * PA_KT - 1, last_key) / cpp;
+            nb0 = n0 == cp0 ? b0 : pa_page(p.kv, session, p.layer, n0);
+            nb1 = n1 == n0 ? nb0 : pa_page(p.kv, session, p.layer, n1);
+        }
         __syncthreads(); // the previous tile's fragments have been consumed
         // ---- stage K and V [64][HS] as BF16 ------------------------------------------------------------------
-#pragma unroll 4
+#pragma unroll 8
         for (int r = srow; r < PA_KT; r += RPP) {
             const int pos = t0 + r;
             uint2 kq = make_uint2(0u, 0u), vq = kq;
             if (pos <= last_key) {
-                const char *kr = pa_k_row(p.kv, session, p.layer, pos, esz) + ((size_t)kvh * HS + sc4 * 4) * esz;
+                const int cp = pos / cpp;
+                // (pages shorter than a tile -- never produced by the geometry solver for real models -- are looked up per row)
+                const char *pg = cpp >= PA_KT ? (cp == cp0 ? b0 : b1) : pa_page(p.kv, session, p.layer, cp);
+                const char *kr = pg + layer_off + (size_t)(pos - cp * cpp) * row_bytes;
                 if (KVDT == JL_F32) {
                     const float4 kf = __ldg((const float4 *)kr), vf = __ldg((const float4 *)(kr + v_off));
                     kq = make_uint2(pa_pack(kf.x, kf.y), pa_pack(kf.z, kf.w));

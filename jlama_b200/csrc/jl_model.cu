@@ -6,6 +6,7 @@
 // never leave HBM, KV lives in device pages shaped like KvBufferCache's, and the per-token decode
 // step is captured once into a CUDA graph with programmatic dependent launch between kernels.
 #include "jl_common.cuh"
+#include <string>
 #include "jl_pdecode.cuh"
 
 #include <chrono>
@@ -1296,6 +1297,58 @@ extern "C" int jl_model_generate(jl_model *m, int session, const int32_t *prompt
         timings_ms[1] = std::chrono::duration<double, std::milli>(t2 - t1).count();
     }
     return JL_OK;
+}
+
+// ---- KV persistence (KvBufferCache.KvBufferPage, core/tensor/KvBufferCache.java:121-176): the reference backs every page of a
+// non-ephemeral session with the file  <workingDirectory>/<session>-L<layerPage>C<contextPage>.page  holding the raw little-endian
+// page ([layersPerPage][2][contextPerPage][kvLength] of the working KV dtype).  Here pages live in HBM; save writes the allocated
+// pages of a session in exactly that naming and byte layout, load maps such files back (allocating the pages) so a session can be
+// resumed by this library or by the reference.  Returns the number of pages written / read, or a negative status.
+extern "C" int jl_model_kv_save(jl_model *m, int session, const char *dir, const char *session_name) {
+    if (!m || !m->finalized || !dir || !session_name || session < 0 || session >= m->cfg.max_sessions) return JL_ERR_INVALID;
+    jl_ctx *ctx = m->ctx;
+    JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    JL_CUDA_CHECK(ctx, cudaStreamSynchronize(m->stream));
+    std::vector<char> host(m->page_bytes);
+    int n = 0;
+    for (int lp = 0; lp < m->kv.n_layer_pages; lp++)
+        for (int cp = 0; cp < m->kv.n_ctx_pages; cp++) {
+            const void *page = m->page_table_host[((size_t)session * m->kv.n_layer_pages + lp) * m->kv.n_ctx_pages + cp];
+            if (!page) continue;
+            JL_CUDA_CHECK(ctx, cudaMemcpy(host.data(), page, m->page_bytes, cudaMemcpyDeviceToHost));
+            const std::string path = std::string(dir) + "/" + session_name + "-L" + std::to_string(lp) + "C" + std::to_string(cp) + ".page";
+            FILE *f = fopen(path.c_str(), "wb");
+            if (!f) return jl_set_error(ctx, JL_ERR_INVALID, "kv_save: cannot open %s", path.c_str());
+            const size_t w = fwrite(host.data(), 1, m->page_bytes, f);
+            if (fclose(f) != 0 || w != m->page_bytes) return jl_set_error(ctx, JL_ERR_INVALID, "kv_save: short write to %s", path.c_str());
+            n++;
+        }
+    return n;
+}
+
+extern "C" int jl_model_kv_load(jl_model *m, int session, const char *dir, const char *session_name) {
+    if (!m || !m->finalized || !dir || !session_name || session < 0 || session >= m->cfg.max_sessions) return JL_ERR_INVALID;
+    jl_ctx *ctx = m->ctx;
+    JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    std::vector<char> host(m->page_bytes);
+    int n = 0;
+    for (int cp = 0; cp < m->kv.n_ctx_pages; cp++)
+        for (int lp = 0; lp < m->kv.n_layer_pages; lp++) {
+            const std::string path = std::string(dir) + "/" + session_name + "-L" + std::to_string(lp) + "C" + std::to_string(cp) + ".page";
+            FILE *f = fopen(path.c_str(), "rb");
+            if (!f) continue;
+            const size_t r = fread(host.data(), 1, m->page_bytes, f);
+            const bool more = fgetc(f) != EOF;
+            fclose(f);
+            // KvBufferPage re-sizes a file of the wrong length (:148); a page of another geometry cannot be this session's
+            if (r != m->page_bytes || more)
+                return jl_set_error(ctx, JL_ERR_INVALID, "kv_load: %s is not a %zu-byte page of this model's geometry", path.c_str(), m->page_bytes);
+            M_CHECK(ensure_pages(m, session, cp * m->kv.ctx_per_page, cp * m->kv.ctx_per_page)); // allocates every layer page of cp
+            void *page = m->page_table_host[((size_t)session * m->kv.n_layer_pages + lp) * m->kv.n_ctx_pages + cp];
+            JL_CUDA_CHECK(ctx, cudaMemcpy(page, host.data(), m->page_bytes, cudaMemcpyHostToDevice));
+            n++;
+        }
+    return n;
 }
 
 extern "C" int jl_model_read_kv(jl_model *m, int session, int layer, int position, int which, float *out) {

@@ -213,6 +213,19 @@ class LlamaModel:
         self.last_timings_ms = (tm[0], tm[1])
         return out, logits
 
+    def kv_save(self, directory, session_name, session=0):
+        """KvBufferCache.KvBufferPage persistence: <directory>/<session_name>-L<l>C<c>.page files; returns the page count."""
+        n = self.lib.jl_model_kv_save(self.h, session, str(directory).encode(), str(session_name).encode())
+        if n < 0:
+            self.ctx.check(n)
+        return n
+
+    def kv_load(self, directory, session_name, session=0):
+        n = self.lib.jl_model_kv_load(self.h, session, str(directory).encode(), str(session_name).encode())
+        if n < 0:
+            self.ctx.check(n)
+        return n
+
     def read_kv(self, layer, position, which, session=0):
         out = np.empty(self.dctx.kvSegmentLength, dtype=np.float32)
         self.ctx.check(self.lib.jl_model_read_kv(self.h, session, layer, position, which, ptr(out)))

@@ -109,6 +109,8 @@ SIGNATURES = {
     "jl_model_generate": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "jl_model_decode_resident": (_i, [_vp, _i, C.c_int32, _i, _i, _vp]),
     "jl_model_read_kv": (_i, [_vp, _i, _i, _i, _i, _vp]),
+    "jl_model_kv_save": (_i, [_vp, _i, C.c_char_p, C.c_char_p]),
+    "jl_model_kv_load": (_i, [_vp, _i, C.c_char_p, C.c_char_p]),
     "jl_model_read_hidden": (_i, [_vp, _i, _vp]),
     "jl_model_debug_read": (_i, [_vp, _i, _vp, _i64]),
     "jl_model_decode_mode": (_i, [_vp, _i]),

@@ -251,6 +251,41 @@ def test_concurrent_sessions_batch_decode(cuda_ctx, oracle, name, wdt, nsess):
     om.close()
 
 
+def test_kv_pages_persist_and_resume(cuda_ctx, oracle, tmp_path):
+    """KvBufferCache.KvBufferPage (core/tensor/KvBufferCache.java:121-176): a session's pages written as
+    <session>-L<l>C<c>.page files (raw page bytes) and mapped back into a fresh model continue the generation token for token."""
+    from jlama_b200 import synth
+    cfg, w, gm, om = _models(cuda_ctx, oracle, "small")
+    prompt = synth.random_prompt(cfg, 23)
+    ot, _ = om.generate(prompt, 10, want_logits=False)
+    gm.batch_forward(prompt, 0)
+    first, _ = gm.sample(want_logits=False)
+    toks = [first]
+    for i in range(4):
+        nxt, _ = gm.decode([toks[-1]], [len(prompt) + i])
+        toks.append(int(nxt[0]))
+    assert toks == list(ot[:5])
+    n = gm.kv_save(tmp_path, "6f1c6b7e-test")
+    files = sorted(f.name for f in tmp_path.iterdir())
+    assert n == len(files) >= 1 and all(f.startswith("6f1c6b7e-test-L") and f.endswith(".page") for f in files)
+    page_bytes = {f.stat().st_size for f in tmp_path.iterdir()}
+    assert len(page_bytes) == 1  # every page has the page geometry's size
+    # the K row of position 3, layer 1 sits where KvBufferCache puts it: [layer % layersPerPage][0][position % contextPerPage][:]
+    gm.close()
+    from jlama_b200.model import LlamaModel
+    g2 = LlamaModel(cuda_ctx, cfg, w)
+    assert g2.kv_load(tmp_path, "6f1c6b7e-test") == n
+    for i in range(4, 9):
+        nxt, _ = g2.decode([toks[-1]], [len(prompt) + i])
+        toks.append(int(nxt[0]))
+    assert toks == list(ot)
+    (tmp_path / "6f1c6b7e-test-L0C0.page").write_bytes(b"short")
+    with pytest.raises(Exception):
+        g2.kv_load(tmp_path, "6f1c6b7e-test")
+    g2.close()
+    om.close()
+
+
 def test_temperature_sampling_follows_reference_prefix_rule(cuda_ctx, oracle):
     from jlama_b200 import synth
     cfg, w, gm, om = _models(cuda_ctx, oracle, "tiny")
