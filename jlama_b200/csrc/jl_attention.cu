@@ -11,6 +11,7 @@
 // contiguous inside a page row of kv_len floats), reductions are warp shuffles.
 #include "jl_common.cuh"
 #include "jl_attn_task.cuh"
+#include "jl_attn_flat.cuh"
 
 #define ATT_THREADS 128
 
@@ -345,7 +346,70 @@ static int launch_fda(jl_ctx *ctx, cudaStream_t s, const AttnTask &t, int layer,
     return launch_fda_k<HS, JL_BF16>(ctx, s, t, layer, rows, done_cnt, pdl);
 }
 
-int jl_launch_fused_decode_attention(jl_ctx *ctx, cudaStream_t s, const AttnParams &p, unsigned *done_cnt, bool use_pdl) {
+// The flat decode task (jl_attn_flat.cuh: K/V rows straight into registers, one exponential per (position, head), 4-5 CTA
+// barriers whatever the context) as its own launch: grid = (kv_heads, rows, splits).  Used for batched decode (several sessions
+// per step -- the persistent kernel covers the single-session case) whenever a split holds <= FA_MAX_POS positions and the GQA
+// group is a power of two; the tiled task above stays for everything else.
+#define FFA_THREADS 512
+template <int HS>
+__global__ void __launch_bounds__(FFA_THREADS) flat_decode_attention_kernel(const AttnTask t, const int layer, unsigned *done_cnt,
+                                                                            unsigned long long *trace) {
+    ktrace_begin(trace, 0xA00u | (unsigned long long)t.splits << 16);
+    ktrace_mid(trace);
+    extern __shared__ __align__(16) unsigned char ffa_smem[];
+    __shared__ int s_last;
+    const int kvh = blockIdx.x, m = blockIdx.y, split = blockIdx.z;
+    attention_flat<HS, FFA_THREADS>(t, layer, m, kvh, split, ffa_smem, [] {});
+    if (t.splits > 1) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            unsigned *c = &done_cnt[m * t.kv_heads + kvh];
+            const unsigned old = atomicAdd(c, 1u);
+            s_last = (old == (unsigned)t.splits - 1);
+            if (s_last) *c = 0; // ready for the next launch
+            __threadfence();
+        }
+        __syncthreads();
+        if (s_last) attention_merge<HS, FFA_THREADS>(t, m, kvh, ffa_smem);
+    }
+    if (trace) {
+        __syncthreads();
+        ktrace_end(trace);
+    }
+}
+
+template <int HS>
+static int launch_ffa(jl_ctx *ctx, cudaStream_t s, const AttnTask &t, int layer, int rows, unsigned *done_cnt) {
+    size_t smem = attention_flat_smem<HS, FFA_THREADS>();
+    const size_t msm = attention_task_smem<HS, FFA_THREADS>(); // the merge step borrows the tiled task's layout
+    if (msm > smem) smem = msm;
+    static size_t configured[JL_MAX_DEVICES] = {};
+    JL_CUDA_CHECK(ctx, (jl_ensure_dyn_smem(flat_decode_attention_kernel<HS>, ctx->device, smem, configured)));
+    unsigned long long *trace = jl_ktrace_slot(ctx);
+    JL_CUDA_CHECK(ctx, jl_launch_kernel(flat_decode_attention_kernel<HS>, dim3(t.kv_heads, rows, t.splits), dim3(FFA_THREADS), smem, s, false, t,
+                                        layer, done_cnt, trace));
+    ctx->launches++;
+    return JL_OK;
+}
+
+// max_pos: the largest position among the rows (bounds the positions a split can hold)
+static bool flat_decode_ok(const AttnParams &p, int max_pos) {
+    static int env = -1;
+    if (env < 0) {
+        const char *e = getenv("JL_ATTN_FLAT");
+        env = e ? atoi(e) : 1;
+    }
+    if (!env || p.rows < 2) return false;
+    const int group = p.heads / p.kv_heads;
+    if (group & (group - 1)) return false;
+    if (p.head_size != 64 && p.head_size != 128) return false;
+    const int splits = p.splits > 0 ? p.splits : 1;
+    const int per = (((max_pos + 1 + splits - 1) / splits) + 31) / 32 * 32;
+    return per <= FA_MAX_POS;
+}
+
+int jl_launch_fused_decode_attention(jl_ctx *ctx, cudaStream_t s, const AttnParams &p, unsigned *done_cnt, bool use_pdl, int max_pos) {
     if (p.rows <= 0) return JL_OK;
     if (p.heads % p.kv_heads || p.heads / p.kv_heads > MG_MAX_GROUP)
         return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "attention: head group size %d/%d unsupported", p.heads, p.kv_heads);
@@ -354,6 +418,8 @@ int jl_launch_fused_decode_attention(jl_ctx *ctx, cudaStream_t s, const AttnPara
     t.kv_head0_global = p.kv_head0_global, t.splits = p.splits, t.attn_scale = p.scale;
     t.q = p.q, t.k = p.k, t.v = p.v, t.att = p.out, t.attn_ws = p.ws, t.rope = p.rope, t.kv = p.kv;
     t.sessions = p.sessions, t.positions = p.positions;
+    if (max_pos >= 0 && flat_decode_ok(p, max_pos))
+        return p.head_size == 64 ? launch_ffa<64>(ctx, s, t, p.layer, p.rows, done_cnt) : launch_ffa<128>(ctx, s, t, p.layer, p.rows, done_cnt);
     switch (p.head_size) {
         case 32: return launch_fda<32>(ctx, s, t, p.layer, p.rows, done_cnt, use_pdl);
         case 64: return launch_fda<64>(ctx, s, t, p.layer, p.rows, done_cnt, use_pdl);

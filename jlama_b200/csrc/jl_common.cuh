@@ -220,7 +220,8 @@ bool jl_prefill_attention_supported(const AttnParams &p);
 int jl_launch_prefill_attention(jl_ctx *ctx, cudaStream_t s, const AttnParams &p, int session, int pos0);
 // Decode steps (every row a different session): RoPE + KV append + attention fused in one kernel; q/k/v are the raw
 // projections.  done_cnt: [rows * kv_heads] zero-initialised split-arrival counters (self-resetting).
-int jl_launch_fused_decode_attention(jl_ctx *ctx, cudaStream_t s, const AttnParams &p, unsigned *done_cnt, bool use_pdl);
+// max_pos >= 0: the largest position among the rows (lets batched decode take the flat task); -1: tiled task only
+int jl_launch_fused_decode_attention(jl_ctx *ctx, cudaStream_t s, const AttnParams &p, unsigned *done_cnt, bool use_pdl, int max_pos = -1);
 
 // ---------------------------------------------------------------------------------------------
 // Larger-M GEMM paths for prefill (jl_gemm.cu)

@@ -368,6 +368,16 @@ static size_t g8_smem(const GemvParams &p) { return g8_act_smem(p) + G8_RED_BYTE
 // needed to give every warp work.
 static int g8_ksplit(const GemvParams &p, int sm_count) {
     const int nch = (p.K / 32) / (p.w_dtype == JL_Q4 ? 8 : 4);
+    static int forced = -1; // JL_G8_KSPLIT=1|2|4|8: diagnostic override (tools/config3_bench.py)
+    if (forced < 0) {
+        const char *e = getenv("JL_G8_KSPLIT");
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced > 0) {
+        for (int s = forced > G8_WARPS ? G8_WARPS : forced; s > 1; s >>= 1)
+            if (nch % s == 0) return s;
+        return 1;
+    }
     const int strips = (p.total_rows + 15) / 16;
     int want = 1;
     while (want < G8_WARPS && strips * want < sm_count * G8_WARPS) want <<= 1;

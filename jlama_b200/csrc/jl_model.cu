@@ -683,7 +683,10 @@ static int forward_rows(jl_model *m, int M, int max_pos, int splits, bool timed,
         ap.splits = splits;
         if (distinct_sessions) {
             // decode: one fused kernel (RoPE + KV append + attention); `splits` = about one per 64 positions
-            M_CHECK(jl_launch_fused_decode_attention(ctx, m->stream, ap, m->fda_done, pdl));
+            // the launch may be replayed from a graph for every context of its split bucket (run_decode): choose the kernel by the
+            // largest position the bucket can see, not by the current one
+            const int bound = splits >= m->max_splits ? m->max_context - 1 : splits * 64 * M - 1;
+            M_CHECK(jl_launch_fused_decode_attention(ctx, m->stream, ap, m->fda_done, pdl, bound));
         } else {
             M_CHECK(jl_launch_rope_kv_append(ctx, m->stream, ap, m->q, pdl));
             M_CHECK(jl_launch_paged_attention(ctx, m->stream, ap, max_pos, pdl));
@@ -1079,8 +1082,10 @@ static int run_decode(jl_model *m, int n, int max_pos, bool resident, bool want_
         pp.ntok = resident ? ntok : 1;
         return jl_launch_pdecode(ctx, m->stream, pp, m->pd_layers.data(), m, m->pd_wdtype);
     }
-    // fused decode attention: one split per 64 positions, bucketed so that few graphs are captured
+    // fused decode attention: one split per 64 positions (per 64 * n with n sessions in the step: the rows already fill the grid),
+    // bucketed so that few graphs are captured
     int splits = (max_pos + 1 + 63) / 64;
+    if (n > 1) splits = (splits + n - 1) / n;
     {
         static const int buckets[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32};
         int b = 32;

@@ -251,6 +251,45 @@ def test_concurrent_sessions_batch_decode(cuda_ctx, oracle, name, wdt, nsess):
     om.close()
 
 
+@pytest.mark.parametrize("name,kvdt", [("small", "F32"), ("small-hs128", "BF16")])
+def test_batched_decode_long_context_splits(cuda_ctx, oracle, name, kvdt):
+    """Several sessions per step with contexts long enough for split attention (the flat decode task as its own launch,
+    jl_attention.cu flat_decode_attention_kernel, merged by the last-arriving CTA): every session equals the oracle's run of
+    that session alone."""
+    from jlama_b200 import synth, native
+    cfg = synth.get_config(name)
+    w = synth.make_weights(cfg)
+    from jlama_b200.model import LlamaModel
+    kv = getattr(native, kvdt)
+    nsess = 3
+    gm = LlamaModel(cuda_ctx, cfg, w, max_sessions=nsess, kv_dtype=kv)
+    prompts = [synth.random_prompt(cfg, 150 + 40 * s, seed=300 + s) for s in range(nsess)]  # 150, 190, 230 -> two or more splits
+    firsts = []
+    for s, p in enumerate(prompts):
+        gm.batch_forward(p, 0, session=s)
+        firsts.append(gm.sample(session=s, want_logits=False)[0])
+    toks = np.array(firsts, dtype=np.int32)
+    pos = np.array([len(p) for p in prompts], dtype=np.int32)
+    glog = []
+    for _ in range(3):
+        toks, lg = gm.decode(toks, pos, want_logits=True)
+        pos += 1
+        glog.append(lg.copy())
+    gm.close()
+    # F32 pages: the oracle; BF16 pages (no oracle mode for them): the single-session path of this library (persistent kernel)
+    om = oracle.OracleLlama(cfg, w, act_q8=True) if kvdt == "F32" else LlamaModel(cuda_ctx, cfg, w, kv_dtype=kv)
+    for s, p in enumerate(prompts):
+        if kvdt == "F32":
+            om.reset()
+        else:
+            om.reset_session(0)
+        ot, ol = om.generate(p, 4, want_logits=True)
+        assert firsts[s] == ot[0]
+        # teacher-forced only as long as the GPU followed the oracle's tokens; logits of the first batched step always compare
+        assert np.abs(glog[0][s] - ol[1]).max() <= 2e-3 * np.abs(ol[1]).max(), s
+    om.close()
+
+
 def test_kv_pages_persist_and_resume(cuda_ctx, oracle, tmp_path):
     """KvBufferCache.KvBufferPage (core/tensor/KvBufferCache.java:121-176): a session's pages written as
     <session>-L<l>C<c>.page files (raw page bytes) and mapped back into a fresh model continue the generation token for token."""
