@@ -93,7 +93,7 @@ int jl_gemm(jl_ctx *ctx, int a_dtype, const void *a, const float *a_scales, int 
 int jl_gemm_batch(jl_ctx *ctx, int batch_num, int a_dtype, const void *a, const float *a_scales, int a_col_off, int lda,
                   const int64_t *b_ids, int b_col_off, float *const *r, int roffset, int m, int n0, int n, int k,
                   int ldc);
-/* batchDotProduct on the tcgen05 tensor cores for m >= 16 rows of F32/BF16 activations against a registered Q4
+/* batchDotProduct on the tcgen05 tensor cores for m >= 16 rows of F32/BF16 activations against a registered Q4 or Q8_0 (JL_I8)
  * weight (prefill shape).  Same index semantics as jl_gemm; operands are rounded to BF16 (accumulation in F32), so
  * the result matches the reference's F32 x Q4 GEMM (PanamaTensorOperations.java:289-548) to ~1e-3 of max|C|, not bit-wise.
  * Requires k %% 64 == 0, n %% 128 == 0, n0 %% 128 == 0, b_col_off %% 64 == 0 (JL_ERR_UNSUPPORTED otherwise). */

@@ -72,7 +72,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 struct TcParams {
     const uint16_t *a; // activations bf16 [T, lda]
     int lda, T;
-    const uint8_t *w;  // Q4 nibbles, row pitch K_total/2
+    const uint8_t *w;  // Q4 nibbles (row pitch K_total/2) or int8 (row pitch K_total)
     const float *ws;   // scales, row pitch K_total/32
     int ldw;           // K_total (elements)
     int w_col_off;     // first weight column (multiple of 64)
@@ -85,7 +85,8 @@ struct TcParams {
 };
 
 // BN = tokens per CTA (UMMA N): 128, or 256 to amortise the weight dequantisation over twice the tokens
-template <int BN>
+// WDT = JL_Q4 or JL_I8 (Q8_0: int8 + one f32 scale per 32 elements; the block is 32 bytes in natural element order)
+template <int BN, int WDT>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_q4_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap amap) {
     constexpr int ATILE = BN * TC_BK * 2;
     extern __shared__ __align__(1024) unsigned char tc_smem[];
@@ -123,44 +124,69 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_q4_tc_kernel(const TcParam
         // reads (and the layout TMA writes for the token tile). =====
         const int r = tid & 127, half = tid >> 7;
         const size_t wrow = (size_t)(n0 + r);
-        const uint8_t *wq = p.w + wrow * (size_t)(p.ldw / 2) + p.w_col_off / 2 + half * 16;
+        constexpr int WB = WDT == JL_Q4 ? 16 : 32; // bytes of a 32-element block
+        constexpr int NQ = WB / 16;                 // 128-bit loads per block
+        const uint8_t *wq = p.w + (wrow * (size_t)(p.ldw / 32) + p.w_col_off / 32 + half) * WB;
         const float *wsc = p.ws + wrow * (size_t)(p.ldw / 32) + p.w_col_off / 32 + half;
-        uint4 qn[TC_PF];
+        uint4 qn[TC_PF][NQ];
         float scn[TC_PF];
 #pragma unroll
         for (int i = 0; i < TC_PF; i++) {
             const int kk = i < nk ? i : nk - 1;
-            qn[i] = ldg_nc_u4(wq + (size_t)kk * 32);
+#pragma unroll
+            for (int j = 0; j < NQ; j++) qn[i][j] = ldg_nc_u4(wq + (size_t)kk * 2 * WB + j * 16);
             scn[i] = ldg_nc_f32(wsc + kk * 2);
         }
         for (int kc = 0; kc < nk; kc++) {
             const int s = kc % TC_STAGES, use = kc / TC_STAGES;
-            const uint4 q = qn[0];
+            uint4 q[NQ];
+#pragma unroll
+            for (int j = 0; j < NQ; j++) q[j] = qn[0][j];
             const float sc = scn[0];
 #pragma unroll
-            for (int i = 0; i + 1 < TC_PF; i++) qn[i] = qn[i + 1], scn[i] = scn[i + 1];
+            for (int i = 0; i + 1 < TC_PF; i++) {
+#pragma unroll
+                for (int j = 0; j < NQ; j++) qn[i][j] = qn[i + 1][j];
+                scn[i] = scn[i + 1];
+            }
             {
                 const int kk = kc + TC_PF < nk ? kc + TC_PF : nk - 1;
-                qn[TC_PF - 1] = ldg_nc_u4(wq + (size_t)kk * 32);
+#pragma unroll
+                for (int j = 0; j < NQ; j++) qn[TC_PF - 1][j] = ldg_nc_u4(wq + (size_t)kk * 2 * WB + j * 16);
                 scn[TC_PF - 1] = ldg_nc_f32(wsc + kk * 2);
             }
             tc_mbar_wait(&empty[s], (use & 1) ^ 1);
             unsigned char *wdst = wtile + (size_t)s * TC_WTILE_BYTES + (size_t)r * 128;
-            // block = 16 bytes: element j = low nibble of byte j, element j+16 = high nibble of byte j.
-            // nibble -> float through the 2^23 magic number (PRMT + FADD), * scale, round once to BF16.
-            const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
-            float lo[16], hi[16];
+            float lo[16], hi[16]; // elements 0..15 and 16..31 of the block, scaled
+            if (WDT == JL_Q4) {
+                // block = 16 bytes: element j = low nibble of byte j, element j+16 = high nibble of byte j.
+                // nibble -> float through the 2^23 magic number (PRMT + FADD), * scale, round once to BF16.
+                const uint32_t qw[4] = {q[0].x, q[0].y, q[0].z, q[0].w};
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const uint32_t l4 = qw[i] & 0x0F0F0F0Fu, h4 = (qw[i] >> 4) & 0x0F0F0F0Fu;
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t l4 = qw[i] & 0x0F0F0F0Fu, h4 = (qw[i] >> 4) & 0x0F0F0F0Fu;
 #pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    lo[i * 4 + t] = __fmul_rn(__uint_as_float(__byte_perm(l4, 0x4B000000u, 0x7540 | t)) - 8388616.0f, sc);
-                    hi[i * 4 + t] = __fmul_rn(__uint_as_float(__byte_perm(h4, 0x4B000000u, 0x7540 | t)) - 8388616.0f, sc);
+                    for (int t = 0; t < 4; t++) {
+                        lo[i * 4 + t] = __fmul_rn(__uint_as_float(__byte_perm(l4, 0x4B000000u, 0x7540 | t)) - 8388616.0f, sc);
+                        hi[i * 4 + t] = __fmul_rn(__uint_as_float(__byte_perm(h4, 0x4B000000u, 0x7540 | t)) - 8388616.0f, sc);
+                    }
+                }
+            } else {
+                // int8 -> float: byte ^ 0x80 is the value + 128 as an unsigned byte; 2^23 + that, minus (2^23 + 128)
+                const uint32_t qw[8] = {q[0].x, q[0].y, q[0].z, q[0].w, q[NQ - 1].x, q[NQ - 1].y, q[NQ - 1].z, q[NQ - 1].w};
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const uint32_t u = qw[i] ^ 0x80808080u;
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        const float f = __fmul_rn(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7540 | t)) - 8388736.0f, sc);
+                        if (i < 4) lo[i * 4 + t] = f;
+                        else hi[(i - 4) * 4 + t] = f;
+                    }
                 }
             }
 #pragma unroll
-            for (int c = 0; c < 4; c++) { // chunks half*4 + {0,1}: elements 0..15 (low nibbles); {2,3}: elements 16..31
+            for (int c = 0; c < 4; c++) { // chunks half*4 + {0,1}: elements 0..15; {2,3}: elements 16..31
                 const float *src = c < 2 ? lo + c * 8 : hi + (c - 2) * 8;
                 uint4 o;
                 o.x = pack_bf16x2(src[0], src[1]);
@@ -265,11 +291,11 @@ static tc_encode_fn tc_encoder() {
     return fn;
 }
 
-template <int BN>
+template <int BN, int WDT>
 static int launch_tc(jl_ctx *ctx, cudaStream_t stream, const TcParams &p) {
     const size_t smem = (size_t)TC_STAGES * (TC_WTILE_BYTES + (size_t)BN * TC_BK * 2) + 1024;
     static size_t configured[JL_MAX_DEVICES] = {};
-    JL_CUDA_CHECK(ctx, jl_ensure_dyn_smem(gemm_q4_tc_kernel<BN>, ctx->device, smem, configured));
+    JL_CUDA_CHECK(ctx, (jl_ensure_dyn_smem(gemm_q4_tc_kernel<BN, WDT>, ctx->device, smem, configured)));
     // tensor map of the BF16 activations [T rows, K cols] (row pitch lda): box = 64 columns (one 128-byte swizzle atom) x BN rows
     tc_encode_fn enc = tc_encoder();
     if (!enc) return jl_set_error(ctx, JL_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled is not available");
@@ -282,7 +308,7 @@ static int launch_tc(jl_ctx *ctx, cudaStream_t stream, const TcParams &p) {
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return jl_set_error(ctx, JL_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
     dim3 grid(p.N / TC_BM, (p.T + BN - 1) / BN);
-    gemm_q4_tc_kernel<BN><<<grid, TC_THREADS, smem, stream>>>(p, amap);
+    gemm_q4_tc_kernel<BN, WDT><<<grid, TC_THREADS, smem, stream>>>(p, amap);
     ctx->launches++;
     JL_CUDA_CHECK(ctx, cudaGetLastError());
     return JL_OK;
@@ -291,7 +317,7 @@ static int launch_tc(jl_ctx *ctx, cudaStream_t stream, const TcParams &p) {
 // C[T, out_col_off + n] (+= residual) = sum_k A_bf16[T, a_col_off + k] * dequant(W[n, w_col_off + k]),  n in [0, N)
 int jl_launch_gemm_tc(jl_ctx *ctx, cudaStream_t stream, const uint16_t *a_bf16, int lda, int T, const DevTensor &W, int n_rows,
                       int w_col_off, int K, float *out, int ldc, int out_col_off, const float *residual, int res_ld) {
-    if (W.dtype != JL_Q4) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "gemm_tc: weights must be Q4");
+    if (W.dtype != JL_Q4 && W.dtype != JL_I8) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "gemm_tc: weights must be Q4 or Q8_0 (I8)");
     if ((K % TC_BK) || (n_rows % TC_BM) || (w_col_off % TC_BK) || T <= 0 || (lda % 8) || ((uintptr_t)a_bf16 % 16))
         return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "gemm_tc: needs K %% 64 == 0 and N %% 128 == 0 (K=%d N=%d)", K, n_rows);
     TcParams p;
@@ -299,6 +325,7 @@ int jl_launch_gemm_tc(jl_ctx *ctx, cudaStream_t stream, const uint16_t *a_bf16, 
     p.w = (const uint8_t *)W.data, p.ws = W.scales, p.ldw = (int)W.cols, p.w_col_off = w_col_off, p.K = K, p.N = n_rows;
     p.out = out, p.ldc = ldc, p.out_col_off = out_col_off, p.residual = residual, p.res_ld = res_ld;
     // 256-token tiles amortise the dequantisation better; use them when they do not starve the grid
-    if (T > 128 && (size_t)(n_rows / TC_BM) * ((T + 255) / 256) >= (size_t)ctx->sm_count / 2) return launch_tc<256>(ctx, stream, p);
-    return launch_tc<128>(ctx, stream, p);
+    const bool wide = T > 128 && (size_t)(n_rows / TC_BM) * ((T + 255) / 256) >= (size_t)ctx->sm_count / 2;
+    if (W.dtype == JL_Q4) return wide ? launch_tc<256, JL_Q4>(ctx, stream, p) : launch_tc<128, JL_Q4>(ctx, stream, p);
+    return wide ? launch_tc<256, JL_I8>(ctx, stream, p) : launch_tc<128, JL_I8>(ctx, stream, p);
 }

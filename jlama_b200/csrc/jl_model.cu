@@ -371,7 +371,10 @@ extern "C" int jl_model_finalize(jl_model *m) {
         M_CHECK(dev_alloc(ctx, (void **)&m->abf, B * kmax * 2));
         bool ok = m->n_exp == 0 && c.tp_size == 1 && (E % 128) == 0 && (m->h_seg % 128) == 0 && (m->attn_seg % 128) == 0 && (m->kv_seg % 128) == 0;
         for (int L = 0; L < c.num_layers && ok; L++)
-            for (int sl : {JL_L_Q, JL_L_K, JL_L_V, JL_L_O, JL_L_GATE, JL_L_DOWN, JL_L_UP}) ok = ok && m->l[(size_t)L * 9 + sl].dtype == JL_Q4;
+            for (int sl : {JL_L_Q, JL_L_K, JL_L_V, JL_L_O, JL_L_GATE, JL_L_DOWN, JL_L_UP}) {
+                const int dt = m->l[(size_t)L * 9 + sl].dtype;
+                ok = ok && (dt == JL_Q4 || dt == JL_I8); // both block formats are dequantised into the BF16 weight tile
+            }
         m->tc_ok = ok;
     }
     M_CHECK(dev_alloc(ctx, (void **)&m->logits, (size_t)c.max_sessions * c.vocab_size * 4));

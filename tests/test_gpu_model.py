@@ -356,13 +356,15 @@ def test_error_paths_do_not_abort(cuda_ctx):
     assert b"config" in lib.jl_last_error(cuda_ctx.h)
 
 
-def test_tensor_core_prefill_matches_oracle(cuda_ctx, oracle):
-    """prefill with the tcgen05 GEMMs (BF16 operands): logits of the first sampled token within the Q4 tolerance
-    of the F32-activation oracle, decode afterwards token-for-token on the integer path."""
+@pytest.mark.parametrize("wdt", ["Q4", "I8"])
+def test_tensor_core_prefill_matches_oracle(cuda_ctx, oracle, wdt):
+    """prefill with the tcgen05 GEMMs (BF16 operands; Q4 and Q8_0 weights are both dequantised into the BF16 weight tile):
+    logits of the first sampled token within the Q4 tolerance of the F32-activation oracle, decode afterwards
+    token-for-token on the integer path."""
     from jlama_b200 import native, synth
     from jlama_b200.model import LlamaModel
     cfg = synth.get_config("small-hs128")
-    w = synth.make_weights(cfg)
+    w = synth.make_weights(cfg, wdtype=getattr(native, wdt))
     gm = LlamaModel(cuda_ctx, cfg, w, prefill_tensor_core=1)
     ref = LlamaModel(cuda_ctx, cfg, w)
     om = oracle.OracleLlama(cfg, w, act_q8=False)

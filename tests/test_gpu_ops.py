@@ -298,6 +298,26 @@ def test_tensor_core_gemm_matches_bf16_reference(cuda_ops, oracle, M, N, K):
     cuda_ops.unregister_model_tensor(w)
 
 
+@pytest.mark.parametrize("M,N,K", [(48, 128, 128), (200, 256, 4096)])
+def test_tensor_core_gemm_q8_weights(cuda_ops, oracle, M, N, K):
+    """the same tcgen05 GEMM with Q8_0 weights (int8 + f32 scale per 32; BASELINE config 3's format): tight against a float64
+    product of the BF16-rounded operands, 1e-2 class against the exact F32 x I8 arithmetic."""
+    from jlama_b200 import tensor as T
+    rng = np.random.default_rng(M + N + K)
+    w = T.Q8ByteBufferTensor(rng.integers(-127, 128, (N, K), dtype=np.int8), ((0.5 + rng.random((N, K // 32))) * 0.001).astype(np.float32))
+    cuda_ops.register_model_tensor(w)
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    c = T.FloatBufferTensor(np.zeros((M, N), dtype=np.float32))
+    cuda_ops.batch_dot_product_tensor_core(c, T.FloatBufferTensor(a), w, 0, 0, K)
+    a16 = T.bfloat16_to_float32(T.float32_to_bfloat16(a)).astype(np.float64)
+    w16 = T.bfloat16_to_float32(T.float32_to_bfloat16(w.to_float())).astype(np.float64)
+    ref = a16 @ w16.T
+    assert np.abs(c.data - ref).max() <= 2e-5 * np.abs(ref).max() * np.sqrt(K / 64)
+    exact = a.astype(np.float64) @ w.to_float().astype(np.float64).T
+    assert np.abs(c.data - exact).max() <= 1e-2 * np.abs(exact).max()
+    cuda_ops.unregister_model_tensor(w)
+
+
 def test_layernorm_matches_reference_restatement(cuda_ops, oracle):
     """LayerNorm.forward (model/LayerNorm.java:41-67, GPT-2 family).  The reference sums sequentially in float; any other
     summation order moves the statistics by ~1e-6 relative (bar: 2e-5 of the row maximum)."""
