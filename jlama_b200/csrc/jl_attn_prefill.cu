@@ -19,6 +19,7 @@
 // the per-position F32 kernel of jl_attention.cu.
 #include "jl_common.cuh"
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 #define PA_KT 64 // key positions per tile
 
@@ -232,8 +233,12 @@ bool jl_prefill_attention_supported(const AttnParams &p) {
 template <int HS, int KVDT>
 static int launch_pa(jl_ctx *ctx, cudaStream_t s, const AttnParams &p, int session, int pos0) {
     const int group = p.heads / p.kv_heads;
-    if (group == 8) {
-        const int rows_per_cta = 16;
+    // 8 warps (32 rows x group 4, or 16 rows x group 8) when there are enough rows to fill the chip: a staged K/V tile then
+    // serves twice the MMA work, and the staging round trip is what the kernel waits for (ncu: tensor pipe 9 % active)
+    const char *force = getenv("JL_PA_WARPS"); // tests: "8" / "4" pin the CTA shape regardless of the row count
+    const bool big = force ? atoi(force) == 8 : p.rows * p.kv_heads >= 32 * 2 * ctx->sm_count;
+    if (group == 8 || big) {
+        const int rows_per_cta = 16 * (8 / group);
         JL_CUDA_CHECK(ctx, jl_launch_kernel(prefill_attention_kernel<HS, KVDT, 8>, dim3((p.rows + rows_per_cta - 1) / rows_per_cta, p.kv_heads),
                                             dim3(256), 0, s, false, p, session, pos0, group));
     } else {

@@ -171,6 +171,10 @@ int jl_launch_activation(jl_ctx *ctx, cudaStream_t s, int type, float *x, int ro
 int jl_launch_moe_route(jl_ctx *ctx, cudaStream_t s, float *logits, int rows, int n_experts, int k, int32_t *sel);
 int jl_launch_softmax(jl_ctx *ctx, cudaStream_t s, float *x, int offset, int length);
 int jl_launch_silu_mul(jl_ctx *ctx, cudaStream_t s, float *gate, const float *up, int rows, int ld, int offset, int length);
+// fused producers of the BF16 operand of the tensor-core prefill GEMMs
+int jl_launch_rmsnorm_bf16(jl_ctx *ctx, cudaStream_t s, const float *x, int rows, int ldx, int w_dtype, const void *w, float adj, float eps,
+                           int E, uint16_t *out, int ldo);
+int jl_launch_silu_mul_bf16(jl_ctx *ctx, cudaStream_t s, const float *gate, const float *up, int rows, int ld, int length, uint16_t *out, int ldo);
 // embedding rows -> f32 hidden (LlamaModel.java:68-100); tokens on device
 int jl_launch_embed(jl_ctx *ctx, cudaStream_t s, const DevTensor &wte, const int32_t *tokens, int n, float *out, int E);
 // argmax with strict '>' (lowest index wins; AbstractModel.java:455-469): two-stage

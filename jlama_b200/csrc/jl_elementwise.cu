@@ -141,6 +141,69 @@ int jl_launch_quantize_bf16(jl_ctx *ctx, cudaStream_t s, const float *x, int row
     return JL_OK;
 }
 
+// ---- fused producers of the BF16 activation operand of the tensor-core prefill GEMMs (jl_model.cu forward_rows_tc) ----------
+// RMSNorm (RMSNorm.java:34-56, double sum like rmsnorm_kernel) rounded straight to BF16: no f32 round trip through HBM.
+__global__ void rmsnorm_bf16_kernel(const float *x, int ldx, int w_dtype, const void *w, float adj, float eps, int E, uint16_t *out, int ldo) {
+    const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ double red[8];
+    __shared__ float rs_sh;
+    const float *xr = x + (size_t)r * ldx;
+    double ss = 0.0;
+    for (int i = tid; i < E; i += blockDim.x) {
+        const float v = xr[i];
+        ss += (double)__fmul_rn(v, v);
+    }
+    ss = warp_sum_d(ss);
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += red[i];
+        t /= (double)E;
+        t += (double)eps;
+        rs_sh = (float)(1.0 / sqrt(t));
+    }
+    __syncthreads();
+    const float rsf = rs_sh;
+    for (int i = tid; i < E; i += blockDim.x) {
+        const float wv = w_dtype == JL_BF16 ? bf16_bits_to_f32(((const uint16_t *)w)[i]) : ((const float *)w)[i];
+        out[(size_t)r * ldo + i] = f32_to_bf16_ref(__fmul_rn(__fadd_rn(adj, wv), __fmul_rn(rsf, xr[i])));
+    }
+}
+int jl_launch_rmsnorm_bf16(jl_ctx *ctx, cudaStream_t s, const float *x, int rows, int ldx, int w_dtype, const void *w, float adj, float eps,
+                           int E, uint16_t *out, int ldo) {
+    if (rows <= 0 || E <= 0) return JL_OK;
+    rmsnorm_bf16_kernel<<<rows, 256, 0, s>>>(x, ldx, w_dtype, w, adj, eps, E, out, ldo);
+    ctx->launches++;
+    JL_CUDA_CHECK(ctx, cudaGetLastError());
+    return JL_OK;
+}
+// silu(gate) * up (MLPBlock.java:117-141) rounded straight to BF16.  The operand is BF16 anyway (tolerance class of the
+// tensor-core path), so the sigmoid uses the f32 exponential instead of the reference's double one.
+__global__ void silu_mul_bf16_kernel(const float *gate, const float *up, int ld, int length, uint16_t *out, int ldo) {
+    const int r = blockIdx.y;
+    const float4 *g4 = (const float4 *)(gate + (size_t)r * ld), *u4 = (const float4 *)(up + (size_t)r * ld);
+    uint2 *o2 = (uint2 *)(out + (size_t)r * ldo);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < length / 4; i += gridDim.x * blockDim.x) {
+        const float4 g = g4[i], u = u4[i];
+        float v[4] = {g.x, g.y, g.z, g.w};
+        const float w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = __fmul_rn(__fdividef(v[k], 1.0f + __expf(-v[k])), w[k]);
+        o2[i] = make_uint2((uint32_t)f32_to_bf16_ref(v[0]) | ((uint32_t)f32_to_bf16_ref(v[1]) << 16),
+                           (uint32_t)f32_to_bf16_ref(v[2]) | ((uint32_t)f32_to_bf16_ref(v[3]) << 16));
+    }
+}
+int jl_launch_silu_mul_bf16(jl_ctx *ctx, cudaStream_t s, const float *gate, const float *up, int rows, int ld, int length, uint16_t *out, int ldo) {
+    if (length <= 0 || rows <= 0) return JL_OK;
+    if ((length % 4) || (ld % 4) || (ldo % 4)) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "silu_mul_bf16: lengths must be multiples of 4");
+    dim3 grid((length / 4 + 255) / 256 > 64 ? 64 : (length / 4 + 255) / 256, rows);
+    silu_mul_bf16_kernel<<<grid, 256, 0, s>>>(gate, up, ld, length, out, ldo);
+    ctx->launches++;
+    JL_CUDA_CHECK(ctx, cudaGetLastError());
+    return JL_OK;
+}
+
 // ---- Q4 weight quantiser (Q4ByteBufferTensor.java:66-120): one warp per block, byte-identical output --------
 __global__ void quantize_q4w_kernel(const float *x, long long rows, long long cols, uint8_t *q, float *scales) {
     const int lane = threadIdx.x & 31;

@@ -830,9 +830,8 @@ static int forward_rows_tc(jl_model *m, int M, int max_pos, int splits, int sess
     M_CHECK(jl_launch_embed(ctx, m->stream, m->g[JL_T_EMBED], m->d_tokens, M, m->x, E));
     for (int L = 0; L < c.num_layers; L++) {
         const DevTensor *lw = &m->l[(size_t)L * 9];
-        M_CHECK(jl_launch_rmsnorm(ctx, m->stream, m->x, M, E, lw[JL_L_ATTN_NORM].dtype, lw[JL_L_ATTN_NORM].data, 0.0f, c.layer_norm_eps, E, 0,
-                                  E, m->ln));
-        M_CHECK(jl_launch_quantize_bf16(ctx, m->stream, m->ln, M, E, 0, E, m->abf));
+        M_CHECK(jl_launch_rmsnorm_bf16(ctx, m->stream, m->x, M, E, lw[JL_L_ATTN_NORM].dtype, lw[JL_L_ATTN_NORM].data, 0.0f, c.layer_norm_eps, E,
+                                       m->abf, E));
         M_CHECK(jl_launch_gemm_tc(ctx, m->stream, m->abf, E, M, lw[JL_L_Q], m->attn_seg, 0, E, m->q, m->attn_seg, 0, nullptr, 0));
         M_CHECK(jl_launch_gemm_tc(ctx, m->stream, m->abf, E, M, lw[JL_L_K], m->kv_seg, 0, E, m->k, m->kv_seg, 0, nullptr, 0));
         M_CHECK(jl_launch_gemm_tc(ctx, m->stream, m->abf, E, M, lw[JL_L_V], m->kv_seg, 0, E, m->v, m->kv_seg, 0, nullptr, 0));
@@ -848,13 +847,11 @@ static int forward_rows_tc(jl_model *m, int M, int max_pos, int splits, int sess
         else M_CHECK(jl_launch_paged_attention(ctx, m->stream, ap, max_pos, false));
         M_CHECK(jl_launch_quantize_bf16(ctx, m->stream, m->att, M, m->attn_seg, 0, m->attn_seg, m->abf));
         M_CHECK(jl_launch_gemm_tc(ctx, m->stream, m->abf, m->attn_seg, M, lw[JL_L_O], E, 0, m->attn_seg, m->xb, E, 0, m->x, E));
-        M_CHECK(jl_launch_rmsnorm(ctx, m->stream, m->xb, M, E, lw[JL_L_FFN_NORM].dtype, lw[JL_L_FFN_NORM].data, 0.0f, c.layer_norm_eps, E, 0, E,
-                                  m->ln));
-        M_CHECK(jl_launch_quantize_bf16(ctx, m->stream, m->ln, M, E, 0, E, m->abf));
+        M_CHECK(jl_launch_rmsnorm_bf16(ctx, m->stream, m->xb, M, E, lw[JL_L_FFN_NORM].dtype, lw[JL_L_FFN_NORM].data, 0.0f, c.layer_norm_eps, E,
+                                       m->abf, E));
         M_CHECK(jl_launch_gemm_tc(ctx, m->stream, m->abf, E, M, lw[JL_L_GATE], H, 0, E, m->hbuf, H, 0, nullptr, 0));
         M_CHECK(jl_launch_gemm_tc(ctx, m->stream, m->abf, E, M, lw[JL_L_UP], H, 0, E, m->hbuf2, H, 0, nullptr, 0));
-        M_CHECK(jl_launch_silu_mul(ctx, m->stream, m->hbuf, m->hbuf2, M, H, 0, H));
-        M_CHECK(jl_launch_quantize_bf16(ctx, m->stream, m->hbuf, M, H, 0, H, m->abf));
+        M_CHECK(jl_launch_silu_mul_bf16(ctx, m->stream, m->hbuf, m->hbuf2, M, H, H, m->abf, H));
         M_CHECK(jl_launch_gemm_tc(ctx, m->stream, m->abf, H, M, lw[JL_L_DOWN], E, 0, H, m->x, E, 0, m->xb, E));
     }
     return JL_OK;

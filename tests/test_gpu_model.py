@@ -395,7 +395,16 @@ def test_tiled_prefill_attention_chunks(cuda_ctx, oracle, name, kvdt, max_batch,
     gm = LlamaModel(cuda_ctx, cfg, w, prefill_tensor_core=1, max_batch=max_batch, kv_dtype=kv)
     ref = LlamaModel(cuda_ctx, cfg, w, kv_dtype=kv, working_qtype=native.F32)
     prompt = synth.random_prompt(cfg, n)
+    if max_batch == 256:  # also pin the 8-warp CTA shape (32 rows x GQA group) that large prompts select by themselves
+        import os
+        os.environ["JL_PA_WARPS"] = "8"
+        try:
+            g8t, g8l = gm.generate(prompt, 1, want_logits=True)
+        finally:
+            del os.environ["JL_PA_WARPS"]
     gt, gl = gm.generate(prompt, 3, want_logits=True)
+    if max_batch == 256:
+        assert _rel(g8l[0], gl[0]) <= 1e-5 and g8t[0] == gt[0]  # same tiles, same arithmetic, another CTA shape
     rt, rl = ref.generate(prompt, 3, want_logits=True)
     assert _rel(gl[0], rl[0]) <= 1e-2
     # K/V rows of the last layer written by the chunked prefill (inputs of every later attention)
