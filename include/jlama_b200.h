@@ -195,7 +195,28 @@ typedef struct {
     int flags;           /* JL_MODEL_* */
     int num_experts;       /* 0 = dense MLP; > 0: Mixtral-style mixture of experts (core/model/MoEBlock.java) */
     int experts_per_token; /* top-k (MixtralConfig numberOfExpertsPerToken) */
+    int arch;              /* JL_ARCH_LLAMA (Llama / Mixtral blocks) or JL_ARCH_GPT2 (core/model/gpt2/GPT2Model.java) */
 } jl_model_config;
+
+#define JL_ARCH_LLAMA 0
+/* GPT-2 blocks: learned position embeddings (wte + wpe, GPT2Model.java:54-69), LayerNorm with bias (LayerNorm.java:41-67), biased
+ * q/k/v/o and MLP projections (CausalSelfAttention.java:184-192,380; MLPBlock.java:126-128,160), GELU, no RoPE, lm_head tied to wte.
+ * Slots: JL_T_EMBED = wte, JL_T_OUT_NORM = ln_f.weight; JL_L_ATTN_NORM / JL_L_FFN_NORM = ln_1 / ln_2 weights, JL_L_Q/K/V = the three
+ * row blocks of c_attn.weight^T, JL_L_O = attn c_proj^T, JL_L_GATE = c_fc^T, JL_L_DOWN = mlp c_proj^T (JL_L_UP stays empty);
+ * biases and wpe through jl_model_set_aux_tensor.  Single rank, dense (non-MoE). */
+#define JL_ARCH_GPT2 1
+/* jl_model_set_aux_tensor `which`: layer < 0 */
+#define JL_AUX_POS_EMBED 0     /* wpe.weight [context_length, E] */
+#define JL_AUX_OUT_NORM_BIAS 1 /* ln_f.bias [1, E] */
+/* layer >= 0 */
+#define JL_AUX_ATTN_NORM_BIAS 0 /* ln_1.bias */
+#define JL_AUX_Q_BIAS 1         /* c_attn.bias split in three (GPT2Model.java:79) */
+#define JL_AUX_K_BIAS 2
+#define JL_AUX_V_BIAS 3
+#define JL_AUX_O_BIAS 4         /* attn.c_proj.bias */
+#define JL_AUX_FFN_NORM_BIAS 5  /* ln_2.bias */
+#define JL_AUX_FC_BIAS 6        /* mlp.c_fc.bias [1, H] */
+#define JL_AUX_PROJ_BIAS 7      /* mlp.c_proj.bias */
 
 #define JL_MODEL_NO_GRAPH 1 /* launch decode kernels eagerly instead of through a CUDA graph */
 #define JL_MODEL_NO_PDL 2   /* (default) no programmatic dependent launch between the decode kernels */
@@ -225,6 +246,8 @@ int jl_model_set_tensor(jl_model *m, int layer, int slot, int64_t tensor_id);
  * ("block_sparse_moe.gate.weight" [num_experts, E]); otherwise which = 0 w1 (gate_proj [H, E]), 1 w2 (down_proj [E, H]),
  * 2 w3 (up_proj [H, E]) of that expert.  The dense JL_L_GATE / JL_L_UP / JL_L_DOWN slots stay empty for MoE models. */
 int jl_model_set_expert_tensor(jl_model *m, int layer, int expert, int which, int64_t tensor_id);
+/* GPT-2 family: bias vectors ([1, n] F32/BF16) and the position-embedding table, see JL_AUX_* */
+int jl_model_set_aux_tensor(jl_model *m, int layer, int which, int64_t tensor_id);
 /* allocate scratch + KV page pool, build RoPE table, capture graphs */
 int jl_model_finalize(jl_model *m);
 int jl_model_free(jl_model *m);

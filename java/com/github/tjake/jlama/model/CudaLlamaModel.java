@@ -40,7 +40,7 @@ public final class CudaLlamaModel implements AutoCloseable {
         JAVA_INT.withName("working_qtype"), JAVA_INT.withName("kv_dtype"), JAVA_INT.withName("max_batch"),
         JAVA_INT.withName("max_sessions"), JAVA_INT.withName("max_context"), JAVA_INT.withName("tp_rank"), JAVA_INT.withName("tp_size"),
         JAVA_INT.withName("prefill_tensor_core"), JAVA_INT.withName("flags"), JAVA_INT.withName("num_experts"),
-        JAVA_INT.withName("experts_per_token"), MemoryLayout.paddingLayout(4));
+        JAVA_INT.withName("experts_per_token"), JAVA_INT.withName("arch") /* 0 = Llama / Mixtral blocks, 1 = GPT-2 blocks */);
 
     private static final Linker LINKER = Linker.nativeLinker();
     private static final SymbolLookup LIB;

@@ -177,6 +177,7 @@ int jl_launch_rmsnorm_bf16(jl_ctx *ctx, cudaStream_t s, const float *x, int rows
 int jl_launch_silu_mul_bf16(jl_ctx *ctx, cudaStream_t s, const float *gate, const float *up, int rows, int ld, int length, uint16_t *out, int ldo);
 // embedding rows -> f32 hidden (LlamaModel.java:68-100); tokens on device
 int jl_launch_embed(jl_ctx *ctx, cudaStream_t s, const DevTensor &wte, const int32_t *tokens, int n, float *out, int E);
+int jl_launch_pos_embed_add(jl_ctx *ctx, cudaStream_t s, float *x, int rows, int E, const DevTensor &wpe, const int32_t *positions);
 // argmax with strict '>' (lowest index wins; AbstractModel.java:455-469): two-stage
 int jl_launch_argmax(jl_ctx *ctx, cudaStream_t s, const float *logits, int rows, int vocab, int ld, int32_t *out_tokens,
                      void *scratch);

@@ -488,6 +488,24 @@ int jl_launch_silu_mul(jl_ctx *ctx, cudaStream_t s, float *gate, const float *up
     return JL_OK;
 }
 
+// ---- learned position embeddings (GPT2Model.java:54-69): x[r, :] = wte row (already there) + wpe[position[r], :] ----------------
+__global__ void pos_embed_add_kernel(float *x, int E, int dtype, const void *wpe, const int32_t *positions) {
+    const int r = blockIdx.y;
+    const size_t pos = (size_t)positions[r];
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < E; c += gridDim.x * blockDim.x) {
+        const float v = dtype == JL_BF16 ? bf16_bits_to_f32(((const uint16_t *)wpe)[pos * E + c]) : ((const float *)wpe)[pos * E + c];
+        x[(size_t)r * E + c] = __fadd_rn(x[(size_t)r * E + c], v);
+    }
+}
+int jl_launch_pos_embed_add(jl_ctx *ctx, cudaStream_t s, float *x, int rows, int E, const DevTensor &wpe, const int32_t *positions) {
+    if (rows <= 0) return JL_OK;
+    dim3 grid((E + 255) / 256, rows);
+    pos_embed_add_kernel<<<grid, 256, 0, s>>>(x, E, wpe.dtype, wpe.data, positions);
+    ctx->launches++;
+    JL_CUDA_CHECK(ctx, cudaGetLastError());
+    return JL_OK;
+}
+
 // ---- embedding rows -> f32 (LlamaModel.java:68-100; Q4 rows are consumed through get(), Q4ByteBufferTensor.java:179-197)
 __global__ void embed_kernel(int dtype, const void *w, const float *scales, const int32_t *tokens, float *out, int E) {
     pdl_launch_dependents();

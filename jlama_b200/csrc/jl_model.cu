@@ -63,6 +63,11 @@ struct jl_model {
     int64_t weight_bytes = 0;
     unsigned *fda_done = nullptr;
     // mixture of experts (MoEBlock.java): router + per-expert w1 / w2 / w3, device pointer tables for the indirect GEMV launches
+    // GPT-2 family (cfg.arch == JL_ARCH_GPT2): biases per layer [layers][8], wpe and ln_f.bias
+    std::vector<DevTensor> aux;
+    std::vector<char> aux_set;
+    DevTensor gaux[2];
+    bool gaux_set[2] = {false, false};
     int n_exp = 0, exp_k = 0;
     std::vector<DevTensor> moe_gate; // [layers]
     std::vector<DevTensor> moe_w;    // [layers][n_exp][3]
@@ -149,6 +154,13 @@ extern "C" int jl_model_create(jl_ctx *ctx, const jl_model_config *cfg, jl_model
     m->kv_heads_local = m->kv_seg / hs;
     m->l.resize((size_t)c.num_layers * 9);
     m->l_set.assign((size_t)c.num_layers * 9, 0);
+    if (c.arch == JL_ARCH_GPT2) {
+        if (m->cfg.tp_size != 1 || c.num_experts > 0 || c.num_heads != c.num_kv_heads)
+            return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "model_create: GPT-2 blocks are single-rank, dense, multi-head"), delete m, JL_ERR_UNSUPPORTED;
+        m->aux.resize((size_t)c.num_layers * 8);
+        m->aux_set.assign((size_t)c.num_layers * 8, 0);
+    } else if (c.arch != JL_ARCH_LLAMA)
+        return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "model_create: unknown arch %d", c.arch), delete m, JL_ERR_UNSUPPORTED;
     if (c.num_experts > 0) {
         if (c.num_experts > 64 || c.experts_per_token < 1 || c.experts_per_token > c.num_experts || (c.num_experts % m->cfg.tp_size))
             return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "model_create: %d experts / top-%d (max 64 experts, single rank)", c.num_experts,
@@ -257,6 +269,38 @@ extern "C" int jl_model_set_expert_tensor(jl_model *m, int layer, int expert, in
     return JL_OK;
 }
 
+extern "C" int jl_model_set_aux_tensor(jl_model *m, int layer, int which, int64_t tensor_id) {
+    if (!m) return JL_ERR_INVALID;
+    jl_ctx *ctx = m->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const jl_model_config &c = m->cfg;
+    if (c.arch != JL_ARCH_GPT2) return jl_set_error(ctx, JL_ERR_INVALID, "model_set_aux_tensor: only GPT-2 models take bias / position tensors");
+    if (m->finalized) return jl_set_error(ctx, JL_ERR_INVALID, "model_set_aux_tensor: model already finalized");
+    auto it = ctx->tensors.find(tensor_id);
+    if (it == ctx->tensors.end()) return jl_set_error(ctx, JL_ERR_INVALID, "model_set_aux_tensor: unknown tensor id");
+    DevTensor &t = it->second;
+    if (t.dtype != JL_F32 && t.dtype != JL_BF16) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "model_set_aux_tensor: F32 / BF16 only");
+    const int E = c.embedding_length;
+    int64_t rows = 1, cols = E;
+    if (layer < 0) {
+        if (which != JL_AUX_POS_EMBED && which != JL_AUX_OUT_NORM_BIAS) return jl_set_error(ctx, JL_ERR_INVALID, "model_set_aux_tensor: bad global slot");
+        if (which == JL_AUX_POS_EMBED) rows = c.context_length;
+    } else {
+        if (layer >= c.num_layers || which < 0 || which > 7) return jl_set_error(ctx, JL_ERR_INVALID, "model_set_aux_tensor: bad layer slot");
+        if (which == JL_AUX_K_BIAS || which == JL_AUX_V_BIAS) cols = m->kv_seg;
+        else if (which == JL_AUX_Q_BIAS) cols = m->attn_seg;
+        else if (which == JL_AUX_FC_BIAS) cols = m->h_seg;
+    }
+    if (t.rows != rows || t.cols != cols)
+        return jl_set_error(ctx, JL_ERR_INVALID, "model_set_aux_tensor: layer %d slot %d expects [%lld,%lld], got [%lld,%lld]", layer, which,
+                            (long long)rows, (long long)cols, (long long)t.rows, (long long)t.cols);
+    t.refs++;
+    m->bound_ids.push_back(t.id);
+    if (layer < 0) m->gaux[which] = t, m->gaux_set[which] = true;
+    else m->aux[(size_t)layer * 8 + which] = t, m->aux_set[(size_t)layer * 8 + which] = 1;
+    return JL_OK;
+}
+
 static int dev_alloc(jl_ctx *ctx, void **p, size_t bytes) {
     if (cudaMalloc(p, bytes ? bytes : 16) != cudaSuccess) {
         cudaGetLastError();
@@ -276,6 +320,7 @@ extern "C" int jl_model_finalize(jl_model *m) {
     for (size_t i = 0; i < m->l_set.size(); i++) {
         const size_t slot = i % 9;
         if (m->n_exp > 0 && (slot == JL_L_GATE || slot == JL_L_DOWN || slot == JL_L_UP)) continue; // experts instead of a dense MLP
+        if (c.arch == JL_ARCH_GPT2 && slot == JL_L_UP) continue;                                      // c_fc -> GELU -> c_proj: no up projection
         if (!m->l_set[i]) return jl_set_error(ctx, JL_ERR_INVALID, "model_finalize: layer %zu slot %zu missing", i / 9, slot);
     }
     // expert parallelism (BASELINE config 5: "expert FFN GEMMs sharded one-per-GPU"): rank r holds the experts e with
@@ -293,9 +338,14 @@ extern "C" int jl_model_finalize(jl_model *m) {
         if (lw[JL_L_K].dtype != lw[JL_L_Q].dtype || lw[JL_L_V].dtype != lw[JL_L_Q].dtype)
             return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "model_finalize: layer %d q/k/v weights must share one dtype (got %d/%d/%d)", L,
                                 lw[JL_L_Q].dtype, lw[JL_L_K].dtype, lw[JL_L_V].dtype);
-        if (m->n_exp == 0 && lw[JL_L_UP].dtype != lw[JL_L_GATE].dtype)
+        if (m->n_exp == 0 && c.arch != JL_ARCH_GPT2 && lw[JL_L_UP].dtype != lw[JL_L_GATE].dtype)
             return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "model_finalize: layer %d gate/up weights must share one dtype (got %d/%d)", L,
                                 lw[JL_L_GATE].dtype, lw[JL_L_UP].dtype);
+    }
+    if (c.arch == JL_ARCH_GPT2) {
+        for (size_t i = 0; i < m->aux_set.size(); i++)
+            if (!m->aux_set[i]) return jl_set_error(ctx, JL_ERR_INVALID, "model_finalize: layer %zu bias slot %zu missing", i / 8, i % 8);
+        if (!m->gaux_set[0] || !m->gaux_set[1]) return jl_set_error(ctx, JL_ERR_INVALID, "model_finalize: wpe / ln_f.bias missing");
     }
     const int E = c.embedding_length, hs = c.head_size;
     JL_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
@@ -304,7 +354,9 @@ extern "C" int jl_model_finalize(jl_model *m) {
     {
         const int positions = c.context_length + 2 * c.num_kv_heads;
         std::vector<float> tbl((size_t)positions * (hs / 2) * 2);
-        jl_precompute_freqs_cis(hs, positions, c.rope_theta, c.rope_scaling, tbl.data());
+        if (c.arch == JL_ARCH_GPT2) // no rotary embedding: the identity rotation (cos 1, sin 0) leaves q and k bit for bit
+            for (size_t i = 0; i < tbl.size(); i += 2) tbl[i] = 1.0f, tbl[i + 1] = 0.0f;
+        else jl_precompute_freqs_cis(hs, positions, c.rope_theta, c.rope_scaling, tbl.data());
         M_CHECK(dev_alloc(ctx, (void **)&m->rope, tbl.size() * 4));
         JL_CUDA_CHECK(ctx, cudaMemcpy(m->rope, tbl.data(), tbl.size() * 4, cudaMemcpyHostToDevice));
     }
@@ -363,13 +415,15 @@ extern "C" int jl_model_finalize(jl_model *m) {
         JL_CUDA_CHECK(ctx, cudaMemcpy(m->moe_stab, st.data(), ne * sizeof(float *), cudaMemcpyHostToDevice));
     }
     M_CHECK(dev_alloc(ctx, (void **)&m->partial, B * E * 4));
-    if (c.prefill_tensor_core) {
+    if (c.arch == JL_ARCH_GPT2) M_CHECK(dev_alloc(ctx, (void **)&m->ln, B * E * 4)); // LayerNorm output (its own tensor in the reference too)
+    if (c.prefill_tensor_core && c.arch == JL_ARCH_LLAMA) {
         size_t kmax = E > m->h_seg ? E : m->h_seg;
         if ((size_t)m->attn_seg > kmax) kmax = m->attn_seg;
         M_CHECK(dev_alloc(ctx, (void **)&m->ln, B * E * 4));
         M_CHECK(dev_alloc(ctx, (void **)&m->hbuf2, B * m->h_seg * 4));
         M_CHECK(dev_alloc(ctx, (void **)&m->abf, B * kmax * 2));
-        bool ok = m->n_exp == 0 && c.tp_size == 1 && (E % 128) == 0 && (m->h_seg % 128) == 0 && (m->attn_seg % 128) == 0 && (m->kv_seg % 128) == 0;
+        bool ok = m->n_exp == 0 && c.arch == JL_ARCH_LLAMA && c.tp_size == 1 && (E % 128) == 0 && (m->h_seg % 128) == 0 && (m->attn_seg % 128) == 0 &&
+                  (m->kv_seg % 128) == 0;
         for (int L = 0; L < c.num_layers && ok; L++)
             for (int sl : {JL_L_Q, JL_L_K, JL_L_V, JL_L_O, JL_L_GATE, JL_L_DOWN, JL_L_UP}) {
                 const int dt = m->l[(size_t)L * 9 + sl].dtype;
@@ -411,7 +465,7 @@ extern "C" int jl_model_finalize(jl_model *m) {
     {
         const DevTensor &head = m->g_set[JL_T_LM_HEAD] ? m->g[JL_T_LM_HEAD] : m->g[JL_T_EMBED];
         const int wd = m->l[JL_L_Q].dtype;
-        bool ok = m->n_exp == 0 && c.working_qtype == JL_I8 && (wd == JL_Q4 || wd == JL_I8) && head.dtype == wd;
+        bool ok = m->n_exp == 0 && c.arch == JL_ARCH_LLAMA && c.working_qtype == JL_I8 && (wd == JL_Q4 || wd == JL_I8) && head.dtype == wd;
         for (int L = 0; L < c.num_layers && ok; L++)
             for (int sl : {JL_L_Q, JL_L_K, JL_L_V, JL_L_O, JL_L_GATE, JL_L_DOWN, JL_L_UP}) ok = ok && m->l[(size_t)L * 9 + sl].dtype == wd;
         // lm_head rows of this rank (vocabulary-sharded under tensor parallelism: SURVEY 8e; the reference computes the
@@ -630,7 +684,10 @@ static void set_w(GemvParams &p, int seg, const DevTensor &t, float *out, int ou
 }
 
 // AbstractModel.forward (:314-329) over M rows whose tokens/positions/sessions are already on the device.
+static int forward_rows_gpt2(jl_model *m, int M, int max_pos, int splits, bool distinct_sessions);
+
 static int forward_rows(jl_model *m, int M, int max_pos, int splits, bool timed, bool distinct_sessions = false) {
+    if (m->cfg.arch == JL_ARCH_GPT2) return forward_rows_gpt2(m, M, max_pos, splits, distinct_sessions);
     jl_ctx *ctx = m->ctx;
     const jl_model_config &c = m->cfg;
     const int E = c.embedding_length, hs = c.head_size;
@@ -857,6 +914,86 @@ static int forward_rows_tc(jl_model *m, int M, int max_pos, int splits, int sess
     return JL_OK;
 }
 
+// GPT-2 blocks (core/model/gpt2/GPT2Model.java:54-129) on the same per-op kernels: x = wte[token] + wpe[position]; per layer
+//   ln1 = LayerNorm(x) -> q,k,v = ln1 . W^T + bias -> attention (no rotary: identity table) -> xb = (att . Wo^T + bo) + x
+//   ln2 = LayerNorm(xb) -> h = gelu(ln2 . Wfc^T + bfc) -> x = (h . Wproj^T + bproj) + xb
+// in the order TransformerBlock.forward / CausalSelfAttention.forward / MLPBlock.forward apply them (bias after the reducer,
+// residual last: CausalSelfAttention.java:363-380, MLPBlock.java:126-160, TransformerBlock.java:185,203).
+static int forward_rows_gpt2(jl_model *m, int M, int max_pos, int splits, bool distinct_sessions) {
+    jl_ctx *ctx = m->ctx;
+    const jl_model_config &c = m->cfg;
+    const int E = c.embedding_length, hs = c.head_size, H = m->h_seg;
+    const bool q8 = c.working_qtype == JL_I8;
+    auto act_q = [&](const DevTensor &w) { return q8 && (w.dtype == JL_Q4 || w.dtype == JL_I8); };
+    auto bias = [&](float *a, int lda, const DevTensor &b, int n) {
+        return jl_launch_accumulate(ctx, m->stream, a, M, lda, b.dtype, b.data, nullptr, 1, (int)b.cols, 0, n);
+    };
+    M_CHECK(jl_launch_embed(ctx, m->stream, m->g[JL_T_EMBED], m->d_tokens, M, m->x, E));
+    M_CHECK(jl_launch_pos_embed_add(ctx, m->stream, m->x, M, E, m->gaux[JL_AUX_POS_EMBED], m->d_positions));
+    for (int L = 0; L < c.num_layers; L++) {
+        const DevTensor *lw = &m->l[(size_t)L * 9];
+        const DevTensor *ax = &m->aux[(size_t)L * 8];
+        M_CHECK(jl_launch_layernorm(ctx, m->stream, m->x, M, E, lw[JL_L_ATTN_NORM].dtype, lw[JL_L_ATTN_NORM].data, ax[JL_AUX_ATTN_NORM_BIAS].dtype,
+                                    ax[JL_AUX_ATTN_NORM_BIAS].data, c.layer_norm_eps, E, 0, E, m->ln));
+        {
+            GemvParams p = {};
+            p.nseg = 3;
+            set_w(p, 0, lw[JL_L_Q], m->q, m->attn_seg);
+            set_w(p, 1, lw[JL_L_K], m->k, m->kv_seg);
+            set_w(p, 2, lw[JL_L_V], m->v, m->kv_seg);
+            p.w_dtype = lw[JL_L_Q].dtype, p.ldw = E, p.K = E, p.a = m->ln, p.lda = E;
+            p.total_rows = m->attn_seg + 2 * m->kv_seg;
+            M_CHECK(run_gemm(m, p, act_q(lw[JL_L_Q]) ? PRO_F32_QUANT : PRO_F32, EPI_STORE, M, (size_t)E * 4, false, false));
+        }
+        M_CHECK(bias(m->q, m->attn_seg, ax[JL_AUX_Q_BIAS], m->attn_seg));
+        M_CHECK(bias(m->k, m->kv_seg, ax[JL_AUX_K_BIAS], m->kv_seg));
+        M_CHECK(bias(m->v, m->kv_seg, ax[JL_AUX_V_BIAS], m->kv_seg));
+        AttnParams ap = {};
+        ap.kv = m->kv, ap.layer = L, ap.heads = m->heads_local, ap.kv_heads = m->kv_heads_local, ap.head_size = hs;
+        ap.head0_global = m->d.headStart, ap.kv_head0_global = m->d.groupHeadStart;
+        ap.q = m->q, ap.k = m->k, ap.v = m->v, ap.q_ld = m->attn_seg, ap.kv_ld = m->kv_seg, ap.out = m->att, ap.rope = m->rope;
+        ap.rows = M, ap.sessions = m->d_sessions, ap.positions = m->d_positions;
+        ap.scale = (float)(1.0 / sqrt((double)hs)), ap.ws = m->attn_ws, ap.splits = splits;
+        if (distinct_sessions) {
+            const int bound = splits >= m->max_splits ? m->max_context - 1 : splits * 64 * M - 1;
+            M_CHECK(jl_launch_fused_decode_attention(ctx, m->stream, ap, m->fda_done, false, bound));
+        } else {
+            M_CHECK(jl_launch_rope_kv_append(ctx, m->stream, ap, m->q, false));
+            M_CHECK(jl_launch_paged_attention(ctx, m->stream, ap, max_pos, false));
+        }
+        {
+            GemvParams p = {};
+            p.nseg = 1;
+            set_w(p, 0, lw[JL_L_O], m->xb, E);
+            p.w_dtype = lw[JL_L_O].dtype, p.ldw = m->attn_seg, p.K = m->attn_seg, p.a = m->att, p.lda = m->attn_seg, p.total_rows = E;
+            M_CHECK(run_gemm(m, p, act_q(lw[JL_L_O]) ? PRO_F32_QUANT : PRO_F32, EPI_STORE, M, (size_t)m->attn_seg * 4, false, false));
+        }
+        M_CHECK(bias(m->xb, E, ax[JL_AUX_O_BIAS], E));
+        M_CHECK(jl_launch_accumulate(ctx, m->stream, m->xb, M, E, JL_F32, m->x, nullptr, M, E, 0, E)); // + residual
+        M_CHECK(jl_launch_layernorm(ctx, m->stream, m->xb, M, E, lw[JL_L_FFN_NORM].dtype, lw[JL_L_FFN_NORM].data, ax[JL_AUX_FFN_NORM_BIAS].dtype,
+                                    ax[JL_AUX_FFN_NORM_BIAS].data, c.layer_norm_eps, E, 0, E, m->ln));
+        {
+            GemvParams p = {};
+            p.nseg = 1;
+            set_w(p, 0, lw[JL_L_GATE], m->hbuf, H);
+            p.w_dtype = lw[JL_L_GATE].dtype, p.ldw = E, p.K = E, p.a = m->ln, p.lda = E, p.total_rows = H;
+            M_CHECK(run_gemm(m, p, act_q(lw[JL_L_GATE]) ? PRO_F32_QUANT : PRO_F32, EPI_STORE, M, (size_t)E * 4, false, false));
+        }
+        M_CHECK(bias(m->hbuf, H, ax[JL_AUX_FC_BIAS], H));
+        M_CHECK(jl_launch_activation(ctx, m->stream, JL_ACT_GELU, m->hbuf, M, H, 0, H));
+        {
+            GemvParams p = {};
+            p.nseg = 1;
+            set_w(p, 0, lw[JL_L_DOWN], m->x, E);
+            p.w_dtype = lw[JL_L_DOWN].dtype, p.ldw = H, p.K = H, p.a = m->hbuf, p.lda = H, p.total_rows = E;
+            M_CHECK(run_gemm(m, p, act_q(lw[JL_L_DOWN]) ? PRO_F32_QUANT : PRO_F32, EPI_STORE, M, (size_t)H * 4, false, false));
+        }
+        M_CHECK(bias(m->x, E, ax[JL_AUX_PROJ_BIAS], E));
+        M_CHECK(jl_launch_accumulate(ctx, m->stream, m->x, M, E, JL_F32, m->xb, nullptr, M, E, 0, E)); // + residual
+    }
+    return JL_OK;
+}
+
 // AbstractModel.sample (:443-473) for `n` hidden rows [n, E] -> logits [n, vocab] -> argmax tokens
 static int sample_rows(jl_model *m, const float *hidden, int n, bool timed) {
     jl_ctx *ctx = m->ctx;
@@ -871,6 +1008,15 @@ static int sample_rows(jl_model *m, const float *hidden, int n, bool timed) {
     p.K = E;
     p.a = hidden;
     p.lda = E;
+    if (c.arch == JL_ARCH_GPT2) { // ln_f is a LayerNorm with bias (GPT2Model.java:112-128), the logits weights are wte
+        M_CHECK(jl_launch_layernorm(ctx, m->stream, hidden, n, E, m->g[JL_T_OUT_NORM].dtype, m->g[JL_T_OUT_NORM].data, m->gaux[JL_AUX_OUT_NORM_BIAS].dtype,
+                                    m->gaux[JL_AUX_OUT_NORM_BIAS].data, c.layer_norm_eps, E, 0, E, m->ln));
+        p.a = m->ln;
+        p.total_rows = c.vocab_size;
+        M_CHECK(run_gemm(m, p, PRO_F32, EPI_STORE, n, (size_t)E * 4, timed));
+        M_CHECK(jl_launch_argmax(ctx, m->stream, m->logits, n, c.vocab_size, c.vocab_size, m->d_next, m->argmax_scratch));
+        return JL_OK;
+    }
     p.norm_w = m->g[JL_T_OUT_NORM].data;
     p.norm_w_dtype = m->g[JL_T_OUT_NORM].dtype;
     p.norm_eps = c.layer_norm_eps;

@@ -260,3 +260,70 @@ class LlamaModel:
             for tid in self._ids:
                 self.lib.jl_unregister_tensor(self.ctx.h, tid)
             self._ids = []
+
+
+class GPT2Model(LlamaModel):
+    """core/model/gpt2/GPT2Model.java:54-129 behind the same C ABI (jl_model_config.arch = JL_ARCH_GPT2): wte + wpe embeddings, LayerNorm
+    with bias, biased projections, GELU MLP, no rotary embedding, logits over wte.  `weights` holds the checkpoint in its file layout
+    (Hugging Face Conv1D: c_attn / c_fc / c_proj weights are [in, out]); like the reference's loader this class transposes them and
+    splits c_attn into q, k, v (GPT2Model.java:79-80).  BASELINE config 1 (GPT-2-small F32)."""
+
+    def __init__(self, ctx, cfg, weights, working_qtype=native.F32, kv_dtype=F32, max_batch=256, max_sessions=1, max_context=0, flags=0):
+        self.ctx, self.cfg, self.lib = ctx, cfg, ctx.lib
+        self.dctx = DistributedContext(cfg, 0, 1)
+        mc = native.ModelConfig(
+            context_length=cfg["ctx"], embedding_length=cfg["E"], hidden_length=cfg["H"], num_heads=cfg["heads"], num_kv_heads=cfg["heads"],
+            num_layers=cfg["layers"], vocab_size=cfg["vocab"], head_size=cfg["E"] // cfg["heads"], layer_norm_eps=cfg["eps"], rope_theta=10000.0,
+            rope_scaling=1.0, working_qtype=working_qtype, kv_dtype=kv_dtype, max_batch=max_batch, max_sessions=max_sessions,
+            max_context=max_context, tp_rank=0, tp_size=1, prefill_tensor_core=0, flags=flags, num_experts=0, experts_per_token=0,
+            arch=native.ARCH_GPT2)
+        h = C.c_void_p()
+        ctx.check(self.lib.jl_model_create(ctx.h, C.byref(mc), C.byref(h)))
+        self.h = h
+        self._ids = []
+        self.max_sessions = max_sessions
+        try:
+            self._load_gpt2(ctx, cfg, weights)
+        except Exception:
+            self.close()
+            raise
+
+    def _load_gpt2(self, ctx, cfg, weights):
+        get = weights if callable(weights) else weights.get
+        E = cfg["E"]
+
+        def reg(a):
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            a = a.reshape(1, -1) if a.ndim == 1 else a
+            tid = self.lib.jl_register_tensor(ctx.h, F32, a.shape[0], a.shape[1], ptr(a), None)
+            if tid < 0:
+                raise native.JlamaNativeError(-1, self.lib.jl_last_error(ctx.h).decode())
+            self._ids.append(tid)
+            return tid
+
+        def w(name):
+            return get(name)[1]  # (dtype, data, scales)
+
+        ctx.check(self.lib.jl_model_set_tensor(self.h, -1, native.T_EMBED, reg(w("wte.weight"))))
+        ctx.check(self.lib.jl_model_set_aux_tensor(self.h, -1, native.AUX_POS_EMBED, reg(w("wpe.weight"))))
+        ctx.check(self.lib.jl_model_set_tensor(self.h, -1, native.T_OUT_NORM, reg(w("ln_f.weight"))))
+        ctx.check(self.lib.jl_model_set_aux_tensor(self.h, -1, native.AUX_OUT_NORM_BIAS, reg(w("ln_f.bias"))))
+        for i in range(cfg["layers"]):
+            b = "h.%d." % i
+            st, sa = (lambda slot, a: ctx.check(self.lib.jl_model_set_tensor(self.h, i, slot, reg(a)))), \
+                     (lambda slot, a: ctx.check(self.lib.jl_model_set_aux_tensor(self.h, i, slot, reg(a))))
+            st(native.L_ATTN_NORM, w(b + "ln_1.weight"))
+            sa(native.AUX_ATTN_NORM_BIAS, w(b + "ln_1.bias"))
+            wq, wk, wv = np.split(w(b + "attn.c_attn.weight").T, 3, axis=0)  # .transpose().split(3, 0)
+            bq, bk, bv = np.split(w(b + "attn.c_attn.bias").reshape(-1), 3)    # .split(3, 1)
+            st(native.L_Q, wq), st(native.L_K, wk), st(native.L_V, wv)
+            sa(native.AUX_Q_BIAS, bq), sa(native.AUX_K_BIAS, bk), sa(native.AUX_V_BIAS, bv)
+            st(native.L_O, w(b + "attn.c_proj.weight").T)
+            sa(native.AUX_O_BIAS, w(b + "attn.c_proj.bias"))
+            st(native.L_FFN_NORM, w(b + "ln_2.weight"))
+            sa(native.AUX_FFN_NORM_BIAS, w(b + "ln_2.bias"))
+            st(native.L_GATE, w(b + "mlp.c_fc.weight").T)
+            sa(native.AUX_FC_BIAS, w(b + "mlp.c_fc.bias"))
+            st(native.L_DOWN, w(b + "mlp.c_proj.weight").T)
+            sa(native.AUX_PROJ_BIAS, w(b + "mlp.c_proj.bias"))
+        ctx.check(self.lib.jl_model_finalize(self.h))

@@ -35,7 +35,7 @@ class ModelConfig(C.Structure):
         ("head_size", C.c_int), ("layer_norm_eps", C.c_float), ("rope_theta", C.c_double), ("rope_scaling", C.c_double),
         ("working_qtype", C.c_int), ("kv_dtype", C.c_int), ("max_batch", C.c_int), ("max_sessions", C.c_int),
         ("max_context", C.c_int), ("tp_rank", C.c_int), ("tp_size", C.c_int), ("prefill_tensor_core", C.c_int),
-        ("flags", C.c_int), ("num_experts", C.c_int), ("experts_per_token", C.c_int),
+        ("flags", C.c_int), ("num_experts", C.c_int), ("experts_per_token", C.c_int), ("arch", C.c_int),
     ]
 
 
@@ -100,6 +100,7 @@ SIGNATURES = {
     "jl_model_create": (_i, [_vp, C.POINTER(ModelConfig), C.POINTER(_vp)]),
     "jl_model_set_tensor": (_i, [_vp, _i, _i, _i64]),
     "jl_model_set_expert_tensor": (_i, [_vp, _i, _i, _i, _i64]),
+    "jl_model_set_aux_tensor": (_i, [_vp, _i, _i, _i64]),
     "jl_model_finalize": (_i, [_vp]),
     "jl_model_free": (_i, [_vp]),
     "jl_model_reset_session": (_i, [_vp, _i]),
@@ -193,3 +194,8 @@ class Context:
 
     def __exit__(self, *a):
         self.close()
+
+# jl_model_config.arch and the GPT-2 auxiliary slots (include/jlama_b200.h JL_ARCH_*, JL_AUX_*)
+ARCH_LLAMA, ARCH_GPT2 = 0, 1
+AUX_POS_EMBED, AUX_OUT_NORM_BIAS = 0, 1
+AUX_ATTN_NORM_BIAS, AUX_Q_BIAS, AUX_K_BIAS, AUX_V_BIAS, AUX_O_BIAS, AUX_FFN_NORM_BIAS, AUX_FC_BIAS, AUX_PROJ_BIAS = range(8)

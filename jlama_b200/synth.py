@@ -180,3 +180,40 @@ def linear_weight_count(cfg):
 
 def random_prompt(cfg, n, seed=1234):
     return np.random.default_rng(seed).integers(0, cfg["vocab"], size=n, dtype=np.int32)
+
+
+# ---- GPT-2 family (BASELINE config 1: "GPT-2-small F32") ------------------------------------------------------------------------
+GPT2_CONFIGS = {
+    "gpt2-tiny": dict(ctx=64, E=128, H=512, heads=4, layers=2, vocab=256, eps=1e-5),
+    "gpt2-small": dict(ctx=1024, E=768, H=3072, heads=12, layers=12, vocab=50257, eps=1e-5),  # gpt2 (124M) dims
+}
+
+
+def get_gpt2_config(name):
+    cfg = dict(GPT2_CONFIGS[name])
+    cfg["name"], cfg["kv_heads"] = name, cfg["heads"]
+    return cfg
+
+
+def make_gpt2_weights(cfg):
+    """Synthetic F32 GPT-2 checkpoint in the file layout the reference loads (GPT2Model.java:54-129): Conv1D weights are [in, out]."""
+    E, H, V, L = cfg["E"], cfg["H"], cfg["vocab"], cfg["layers"]
+    out = {}
+
+    def t(name, shape, std, mean=0.0):
+        rng = np.random.default_rng(tensor_seed(cfg, name))
+        out[name] = (F32, (mean + std * rng.standard_normal(shape, dtype=np.float32)).astype(np.float32), None)
+
+    t("wte.weight", (V, E), 0.5)
+    t("wpe.weight", (cfg["ctx"], E), 0.1)
+    res = 0.02 / float(np.sqrt(2.0 * L))
+    for i in range(L):
+        b = "h.%d." % i
+        t(b + "ln_1.weight", (E,), 0.1, 1.0), t(b + "ln_1.bias", (E,), 0.05)
+        t(b + "attn.c_attn.weight", (E, 3 * E), 0.02), t(b + "attn.c_attn.bias", (3 * E,), 0.01)
+        t(b + "attn.c_proj.weight", (E, E), res), t(b + "attn.c_proj.bias", (E,), 0.01)
+        t(b + "ln_2.weight", (E,), 0.1, 1.0), t(b + "ln_2.bias", (E,), 0.05)
+        t(b + "mlp.c_fc.weight", (E, H), 0.02), t(b + "mlp.c_fc.bias", (H,), 0.01)
+        t(b + "mlp.c_proj.weight", (H, E), res), t(b + "mlp.c_proj.bias", (E,), 0.01)
+    t("ln_f.weight", (E,), 0.1, 1.0), t("ln_f.bias", (E,), 0.05)
+    return out

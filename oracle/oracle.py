@@ -472,3 +472,89 @@ def num_threads():
 
 def set_num_threads(n):
     lib().jo_set_num_threads(int(n))
+
+
+class OracleGPT2:
+    """core/model/gpt2/GPT2Model.java:54-129 restated for F32 checkpoints (test infrastructure): embedding wte + wpe (:54-69); per layer
+    LayerNorm (model/LayerNorm.java:41-67, the C restatement) -> q/k/v = ln . W^T + bias (CausalSelfAttention.java:161-192) ->
+    attention without rotary embedding (:199-356: scores * 1/sqrt(headSize), VectorMath.softMax, P.V) -> (att . Wo^T + bias) + x
+    (:363-380, TransformerBlock.java:185) -> LayerNorm -> gelu(ln . Wfc^T + bias) (MLPBlock.java:117-141, ActivationFunction.java:29-37)
+    -> (h . Wproj^T + bias) + xb (:144-160, TransformerBlock.java:203); logits = ln_f(x) . wte^T (:112-128).  Dot products are numpy
+    float32 (another summation order than any reference kernel: 1e-6 class, the F32 tolerance is 1e-3)."""
+
+    def __init__(self, cfg, weights):
+        self.cfg = cfg
+        g = lambda n: np.asarray(weights[n][1], dtype=np.float32)  # noqa: E731
+        self.wte, self.wpe = g("wte.weight"), g("wpe.weight")
+        self.lnf = (OTensor(F32, g("ln_f.weight").reshape(1, -1)), OTensor(F32, g("ln_f.bias").reshape(1, -1)))
+        self.layers = []
+        for i in range(cfg["layers"]):
+            b = "h.%d." % i
+            wq, wk, wv = np.split(np.ascontiguousarray(g(b + "attn.c_attn.weight").T), 3, axis=0)
+            bq, bk, bv = np.split(g(b + "attn.c_attn.bias").reshape(-1), 3)
+            self.layers.append(dict(
+                ln1=(OTensor(F32, g(b + "ln_1.weight").reshape(1, -1)), OTensor(F32, g(b + "ln_1.bias").reshape(1, -1))),
+                ln2=(OTensor(F32, g(b + "ln_2.weight").reshape(1, -1)), OTensor(F32, g(b + "ln_2.bias").reshape(1, -1))),
+                wq=wq, wk=wk, wv=wv, bq=bq, bk=bk, bv=bv,
+                wo=np.ascontiguousarray(g(b + "attn.c_proj.weight").T), bo=g(b + "attn.c_proj.bias").reshape(-1),
+                wfc=np.ascontiguousarray(g(b + "mlp.c_fc.weight").T), bfc=g(b + "mlp.c_fc.bias").reshape(-1),
+                wpr=np.ascontiguousarray(g(b + "mlp.c_proj.weight").T), bpr=g(b + "mlp.c_proj.bias").reshape(-1)))
+        self.reset()
+
+    def reset(self):
+        self.k = [[] for _ in self.layers]
+        self.v = [[] for _ in self.layers]
+
+    @staticmethod
+    def _gelu(x):
+        xd = x.astype(np.float64)
+        return (0.5 * xd * (1.0 + np.tanh(np.sqrt(2.0 / np.pi) * (xd + 0.044715 * xd ** 3)))).astype(np.float32)
+
+    def forward(self, token, pos):
+        c = self.cfg
+        E, nh = c["E"], c["heads"]
+        hs = E // nh
+        scale = np.float32(1.0 / np.sqrt(float(hs)))
+        x = (self.wte[token] + self.wpe[pos]).astype(np.float32)
+        for li, L in enumerate(self.layers):
+            ln = layernorm(x[None, :], L["ln1"][0], L["ln1"][1], c["eps"])[0]
+            q = (L["wq"] @ ln + L["bq"]).astype(np.float32)
+            self.k[li].append((L["wk"] @ ln + L["bk"]).astype(np.float32))
+            self.v[li].append((L["wv"] @ ln + L["bv"]).astype(np.float32))
+            K, V = np.stack(self.k[li]), np.stack(self.v[li])
+            att = np.empty(E, dtype=np.float32)
+            for h in range(nh):
+                sl = slice(h * hs, (h + 1) * hs)
+                s = ((K[:, sl] @ q[sl]).astype(np.float32) * scale).astype(np.float32)
+                s = np.ascontiguousarray(s)
+                softmax(s, 0, len(s))
+                att[sl] = (s @ V[:, sl]).astype(np.float32)
+            xb = ((L["wo"] @ att + L["bo"]).astype(np.float32) + x).astype(np.float32)
+            ln2 = layernorm(xb[None, :], L["ln2"][0], L["ln2"][1], c["eps"])[0]
+            hdn = self._gelu((L["wfc"] @ ln2 + L["bfc"]).astype(np.float32))
+            x = ((L["wpr"] @ hdn + L["bpr"]).astype(np.float32) + xb).astype(np.float32)
+        return x
+
+    def logits(self, x):
+        ln = layernorm(x[None, :], self.lnf[0], self.lnf[1], self.cfg["eps"])[0]
+        return (self.wte @ ln).astype(np.float32)
+
+    def generate(self, prompt, n_new):
+        """greedy; returns (tokens, logits per step)"""
+        self.reset()
+        x = None
+        for p, tok in enumerate(prompt):
+            x = self.forward(int(tok), p)
+        toks, lgs = [], []
+        pos = len(prompt)
+        for _ in range(n_new):
+            lg = self.logits(x)
+            tok = int(np.argmax(lg))  # first maximum, like AbstractModel.sample's strict '>' scan
+            toks.append(tok)
+            lgs.append(lg)
+            x = self.forward(tok, pos)
+            pos += 1
+        return toks, lgs
+
+    def close(self):
+        pass
