@@ -52,14 +52,6 @@ def main():
     mean = seg[1:].mean(axis=0) if L > 1 else seg[0]
     out = {"model": a.model, "position": a.prompt + a.steps - 1, "token_us": (end - t0) / 1e3, "event_ms_per_token": tot_ms / a.steps,
            "layer_us": float(mean.sum()), "lm_head_us": (end - lm0) / 1e3, "phases_us": {k: float(v) for k, v in zip(names, mean)}}
-    dbg = t[16 + L * 8:16 + L * 16].reshape(L, 8)
-    if dbg[1:, 0].all():
-        # ring-phase internals of CTA 0 (gate+up: slots 0-2, qkv: slots 4-6): after prologue, after its last chunk, after the CTA barrier
-        gu0 = per[1:, 5]
-        out["ring_debug_us"] = {"gu prologue": float((dbg[1:, 0] - gu0).mean() / 1e3), "gu chunks (thread 0)": float((dbg[1:, 1] - dbg[1:, 0]).mean() / 1e3),
-                                "gu cta barrier": float((dbg[1:, 2] - dbg[1:, 1]).mean() / 1e3), "gu rows+arrive": float((per[1:, 6] - dbg[1:, 2]).mean() / 1e3),
-                                "qkv prologue": float((dbg[1:, 4] - per[1:, 0]).mean() / 1e3), "qkv chunks (thread 0)": float((dbg[1:, 5] - dbg[1:, 4]).mean() / 1e3),
-                                "qkv cta barrier": float((dbg[1:, 6] - dbg[1:, 5]).mean() / 1e3), "qkv rows+arrive": float((per[1:, 1] - dbg[1:, 6]).mean() / 1e3)}
     if a.json:
         print(json.dumps(out), flush=True)
     else:
@@ -67,8 +59,6 @@ def main():
             a.model, out["position"], out["token_us"], out["event_ms_per_token"], out["layer_us"], out["lm_head_us"]))
         for k, v in zip(names, mean):
             print("  %-12s %7.2f us" % (k, v))
-        for k, v in out.get("ring_debug_us", {}).items():
-            print("  [ring] %-24s %7.2f us" % (k, v))
     m.close()
     ctx.close()
 
