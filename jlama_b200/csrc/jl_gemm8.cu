@@ -16,8 +16,7 @@
 // rows; epilogues: store, residual add, SiLU(gate) * up.
 #include "jl_common.cuh"
 
-#define G8_THREADS 256
-#define G8_WARPS 8
+#define G8_MAX_WARPS 16
 #define G8_PAD 16        // bytes added to a session's activation row in shared memory: makes the fragment loads bank-conflict free
 #define G8_CHUNK 128     // weight bytes of one row in one pipeline stage (8 Q4 blocks / 4 I8 blocks)
 #define G8_ROWB 144      // staged row stride: 128 + 16 (lane (g, t) reads word g*36 + 4u + t: 32 distinct banks)
@@ -80,8 +79,12 @@ __device__ __forceinline__ void g8_strip_base(const GemvParams &p, int strip, in
 // shared memory left beside the activations -- about 2 KB x (nst - 1) in flight per warp, ~10 MB on the chip, which is what the
 // HBM latency x bandwidth product asks for.  A warp walks a flat list of (strip, tensor, chunk) tasks, so its pipeline never drains
 // between strips, and the first stages are issued BEFORE the activation prologue so that the prologue hides their latency.
-template <int WDT, int EPI, int PRO>
-__global__ void __launch_bounds__(G8_THREADS, 1) gemm8_kernel(const GemvParams p, const int nst, const int ksplit) {
+// NWARP = 8 or 16 warps per CTA (one CTA per SM): 16 when the shared memory left beside the activations still gives every warp a
+// 3-stage pipeline (K <= 8192) -- the main loop is a chain of shared-memory -> MMA -> FMA steps and 8 warps leave the issue slots
+// 60 % idle (ncu: issue active 40 %, occupancy 12.5 %)
+template <int WDT, int EPI, int PRO, int NWARP>
+__global__ void __launch_bounds__(NWARP * 32, 1) gemm8_kernel(const GemvParams p, const int nst, const int ksplit) {
+    constexpr int G8_THREADS = NWARP * 32, G8_WARPS = NWARP;
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr bool NORM = PRO == PRO_RMSNORM_QUANT;
     constexpr int NW = EPI == EPI_SILU_MUL ? 2 : 1;
@@ -354,19 +357,29 @@ __global__ void __launch_bounds__(G8_THREADS, 1) gemm8_kernel(const GemvParams p
 }
 
 static size_t g8_act_smem(const GemvParams &p) { return (size_t)8 * (p.K + G8_PAD) + (size_t)8 * (p.K / 32 + 1) * 8; }
-#define G8_RED_BYTES (2 * G8_WARPS * 2 * 128 * 4) // partial sums of the K split: [2 buffers][8 warps][2 tensors][4 x 32 lanes] f32
-static int g8_stages(const GemvParams &p) {
-    const size_t act = g8_act_smem(p) + G8_RED_BYTES;
+static size_t g8_red_bytes(int nwarp) { return (size_t)2 * nwarp * 2 * 128 * 4; } // partial sums of the K split: [2 buffers][warps][2 tensors][4 x 32 lanes] f32
+static int g8_stages(const GemvParams &p, int nwarp) {
+    const size_t act = g8_act_smem(p) + g8_red_bytes(nwarp);
     if (act + 2048 >= G8_SMEM_LIMIT) return 0;
-    int n = (int)((G8_SMEM_LIMIT - 2048 - act) / ((size_t)G8_WARPS * G8_STAGE));
+    int n = (int)((G8_SMEM_LIMIT - 2048 - act) / ((size_t)nwarp * G8_STAGE));
     return n > G8_MAX_STAGES ? G8_MAX_STAGES : n;
 }
-static size_t g8_smem(const GemvParams &p) { return g8_act_smem(p) + G8_RED_BYTES + (size_t)g8_stages(p) * G8_WARPS * G8_STAGE; }
+static size_t g8_smem(const GemvParams &p, int nwarp) { return g8_act_smem(p) + g8_red_bytes(nwarp) + (size_t)g8_stages(p, nwarp) * nwarp * G8_STAGE; }
+// warps per CTA: 16 while every warp still gets a 3-stage pipeline
+static int g8_warps(const GemvParams &p) {
+    static int forced = -1; // JL_G8_WARPS=8|16: diagnostic override
+    if (forced < 0) {
+        const char *e = getenv("JL_G8_WARPS");
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced == 8) return 8;
+    return g8_stages(p, 16) >= 3 ? 16 : 8;
+}
 // warps of a CTA sharing one strip: the largest of 8, 4, 2, 1 that divides the chunk count of a row
 // Measured at the 8B shapes (gpurun_out/r2_gemv_batch.txt): the split pays while a round's strips do not fill the warps of the
 // chip (o_proj 18.4 -> 14.4 us, down 53 -> 36 us) and costs a little once they do (lm_head 114 -> 129 us): split only as far as
 // needed to give every warp work.
-static int g8_ksplit(const GemvParams &p, int sm_count) {
+static int g8_ksplit(const GemvParams &p, int sm_count, int nwarp) {
     const int nch = (p.K / 32) / (p.w_dtype == JL_Q4 ? 8 : 4);
     static int forced = -1; // JL_G8_KSPLIT=1|2|4|8: diagnostic override (tools/config3_bench.py)
     if (forced < 0) {
@@ -374,13 +387,13 @@ static int g8_ksplit(const GemvParams &p, int sm_count) {
         forced = e ? atoi(e) : 0;
     }
     if (forced > 0) {
-        for (int s = forced > G8_WARPS ? G8_WARPS : forced; s > 1; s >>= 1)
+        for (int s = forced > nwarp ? nwarp : forced; s > 1; s >>= 1)
             if (nch % s == 0) return s;
         return 1;
     }
     const int strips = (p.total_rows + 15) / 16;
     int want = 1;
-    while (want < G8_WARPS && strips * want < sm_count * G8_WARPS) want <<= 1;
+    while (want < nwarp && strips * want < sm_count * nwarp) want <<= 1;
     for (int s = want; s > 1; s >>= 1)
         if (nch % s == 0) return s;
     return 1;
@@ -399,23 +412,27 @@ bool jl_gemm8_supported(const GemvParams &p, int prologue, int epilogue) {
     if (epilogue != EPI_SILU_MUL)
         for (int i = 0; i + 1 < p.nseg; i++)
             if (p.seg[i].rows % 16) return false; // a strip must not straddle two weight tensors
-    return g8_stages(p) >= 2;
+    return g8_stages(p, 8) >= 2;
 }
 
-template <int WDT, int EPI, int PRO>
-static int launch_g8(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p) {
-    auto kern = gemm8_kernel<WDT, EPI, PRO>;
-    const size_t smem = g8_smem(p);
-    const int nst = g8_stages(p);
+template <int WDT, int EPI, int PRO, int NWARP>
+static int launch_g8w(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p) {
+    auto kern = gemm8_kernel<WDT, EPI, PRO, NWARP>;
+    const size_t smem = g8_smem(p, NWARP);
+    const int nst = g8_stages(p, NWARP);
     static size_t configured[JL_MAX_DEVICES] = {};
     JL_CUDA_CHECK(ctx, jl_ensure_dyn_smem(kern, ctx->device, smem, configured));
     const int strips = (p.total_rows + 15) / 16;
-    const int ksplit = g8_ksplit(p, ctx->sm_count), spr = G8_WARPS / ksplit;
-    int grid = ctx->sm_count; // one CTA per SM; a CTA takes 8 / ksplit strips per round
+    const int ksplit = g8_ksplit(p, ctx->sm_count, NWARP), spr = NWARP / ksplit;
+    int grid = ctx->sm_count; // one CTA per SM; a CTA takes NWARP / ksplit strips per round
     if (grid > (strips + spr - 1) / spr) grid = (strips + spr - 1) / spr;
-    JL_CUDA_CHECK(ctx, jl_launch_kernel(kern, dim3(grid), dim3(G8_THREADS), smem, stream, false, p, nst, ksplit));
+    JL_CUDA_CHECK(ctx, jl_launch_kernel(kern, dim3(grid), dim3(NWARP * 32), smem, stream, false, p, nst, ksplit));
     ctx->launches++;
     return JL_OK;
+}
+template <int WDT, int EPI, int PRO>
+static int launch_g8(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p) {
+    return g8_warps(p) == 16 ? launch_g8w<WDT, EPI, PRO, 16>(ctx, stream, p) : launch_g8w<WDT, EPI, PRO, 8>(ctx, stream, p);
 }
 template <int WDT, int EPI>
 static int launch_g8_p(jl_ctx *ctx, cudaStream_t stream, const GemvParams &p, int prologue) {
