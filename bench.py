@@ -193,8 +193,11 @@ def config3_workload(ctx, cfg, peak, sessions=8, prompt_tokens=2048, decode_toke
     l0 = ctx.kernel_launches()
     t0 = time.perf_counter()
     n = decode_tokens - 4
+    per_step = []
     for _ in range(n):
-        toks, _ = m.decode(toks, pos)
+        ts = time.perf_counter()
+        toks, _ = m.decode(toks, pos)  # returns after the sampled tokens are back on the host
+        per_step.append(time.perf_counter() - ts)
         pos += 1
     ctx.sync()
     dt = time.perf_counter() - t0
@@ -205,7 +208,7 @@ def config3_workload(ctx, cfg, peak, sessions=8, prompt_tokens=2048, decode_toke
     out = {"workload": "%s Q8_0 (int8 weights + f32 block scales, Q8 activations, F32 KV), %d sessions, prefill %d / decode %d, direct synthetic weights"
                        % (cfg["name"], sessions, prompt_tokens, decode_tokens),
            "prefill_tokens_per_s": sessions * prompt_tokens / prefill_s, "prefill_path": "tcgen05 BF16 GEMM + tiled tensor-core attention, one 2048-token chunk per session",
-           "decode_tokens_per_s": sessions / step, "decode_ms_per_step": 1e3 * step,
+           "decode_tokens_per_s": sessions / step, "decode_ms_per_step": 1e3 * step, "decode_ms_per_step_median": 1e3 * float(np.median(per_step)),
            "bytes_per_step": {"weights": wbytes, "kv": kv_bytes}, "frac_of_hbm_peak": (wbytes + kv_bytes) / 1e9 / step / peak,
            "launches_per_step": launches / n, "decode_mode": m.decode_mode(sessions),
            "timing": "host clock around the host-buffer C-ABI calls (tokens H2D, sampled tokens D2H every step)"}
