@@ -237,6 +237,8 @@ typedef struct {
 #define JL_L_DOWN 7
 #define JL_L_UP 8
 
+/* sizeof(jl_model_config) of this build: bindings that mirror the struct by hand (ctypes, FFM StructLayout) compare it with theirs */
+int jl_model_config_size(void);
 int jl_model_create(jl_ctx *ctx, const jl_model_config *cfg, jl_model **out);
 /* layer < 0: global slot (JL_T_*); else per-layer slot (JL_L_*).  The tensor must already hold this
  * rank's shard (rows for q/k/v/gate/up, columns for o/down: LlamaModel.java:120-133,

@@ -120,6 +120,8 @@ static bool use_pd(const jl_model *m) {
     return m->pd_ok && env == 1 && !(m->cfg.flags & (JL_MODEL_NO_PERSISTENT | JL_MODEL_NO_GRAPH));
 }
 
+extern "C" int jl_model_config_size(void) { return (int)sizeof(jl_model_config); }
+
 extern "C" int jl_model_create(jl_ctx *ctx, const jl_model_config *cfg, jl_model **out) {
     if (!ctx || !cfg || !out) return JL_ERR_INVALID;
     *out = nullptr;

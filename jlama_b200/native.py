@@ -99,6 +99,7 @@ SIGNATURES = {
     "jl_kv_page_geometry": (_i, [_i, _i, _i, _i, _i64, C.POINTER(_i), C.POINTER(_i)]),
     "jl_model_create": (_i, [_vp, C.POINTER(ModelConfig), C.POINTER(_vp)]),
     "jl_model_set_tensor": (_i, [_vp, _i, _i, _i64]),
+    "jl_model_config_size": (_i, []),
     "jl_model_set_expert_tensor": (_i, [_vp, _i, _i, _i, _i64]),
     "jl_model_set_aux_tensor": (_i, [_vp, _i, _i, _i64]),
     "jl_model_finalize": (_i, [_vp]),

@@ -141,3 +141,11 @@ def test_sparsify_keeps_logical_indices():
     q = T.Q4ByteBufferTensor.from_float(np.random.default_rng(0).standard_normal((8, 128)).astype(np.float32))
     qs = q.sparsify(64, 32)
     assert qs.cols == 32 and np.array_equal(qs.to_float(), q.to_float()[:, 64:96])
+
+
+def test_model_config_mirror_matches_the_c_struct(lib):
+    """the ctypes mirror of jl_model_config (and the FFM StructLayout in java/.../CudaLlamaModel.java, 104 bytes) must not drift"""
+    import ctypes as C
+    from jlama_b200 import native
+    assert lib.jl_model_config_size() == C.sizeof(native.ModelConfig) == 104
+    assert native.ModelConfig.arch.offset == 100 and native.ModelConfig.rope_theta.offset == 40

@@ -185,3 +185,43 @@ def test_oracle_model_generate_is_deterministic_and_causal(oracle):
     assert np.abs(l3 - l1).max() <= 1e-3 * np.abs(l1).max()
     m.close()
     m2.close()
+
+
+def test_gpt2_restatement_is_self_consistent(oracle):
+    """oracle.OracleGPT2 (GPT2Model.java:54-129 restated, incremental K/V) against a from-scratch float64 evaluation of the same network
+    over the whole sequence (full causal attention matrix): pins the bookkeeping of the restatement (cache, splits of c_attn, biases,
+    residual order); the reference holds no golden vectors for GPT-2 without a checkpoint (TestModels needs downloaded weights)."""
+    from jlama_b200 import synth
+    cfg = synth.get_gpt2_config("gpt2-tiny")
+    w = synth.make_gpt2_weights(cfg)
+    g = lambda n: np.asarray(w[n][1], dtype=np.float64)  # noqa: E731
+    toks = synth.random_prompt(cfg, 11)
+    E, nh, eps = cfg["E"], cfg["heads"], cfg["eps"]
+    hs = E // nh
+
+    def ln(x, wn, bn):
+        mu = x.mean(-1, keepdims=True)
+        var = (x * x).mean(-1, keepdims=True) - mu * mu
+        return (x - mu) / np.sqrt(var + eps) * g(wn) + g(bn)
+
+    x = g("wte.weight")[np.asarray(toks)] + g("wpe.weight")[:len(toks)]
+    mask = np.triu(np.full((len(toks), len(toks)), -np.inf), 1)
+    for i in range(cfg["layers"]):
+        b = "h.%d." % i
+        qkv = ln(x, b + "ln_1.weight", b + "ln_1.bias") @ g(b + "attn.c_attn.weight") + g(b + "attn.c_attn.bias")
+        q, k, v = np.split(qkv, 3, axis=1)
+        att = np.empty_like(q)
+        for h in range(nh):
+            sl = slice(h * hs, (h + 1) * hs)
+            s = q[:, sl] @ k[:, sl].T / np.sqrt(hs) + mask
+            p = np.exp(s - s.max(-1, keepdims=True))
+            att[:, sl] = (p / p.sum(-1, keepdims=True)) @ v[:, sl]
+        xb = att @ g(b + "attn.c_proj.weight") + g(b + "attn.c_proj.bias") + x
+        hfc = ln(xb, b + "ln_2.weight", b + "ln_2.bias") @ g(b + "mlp.c_fc.weight") + g(b + "mlp.c_fc.bias")
+        hfc = 0.5 * hfc * (1 + np.tanh(np.sqrt(2 / np.pi) * (hfc + 0.044715 * hfc ** 3)))
+        x = hfc @ g(b + "mlp.c_proj.weight") + g(b + "mlp.c_proj.bias") + xb
+    ref_logits = ln(x[-1:], "ln_f.weight", "ln_f.bias")[0] @ g("wte.weight").T
+    om = oracle.OracleGPT2(cfg, w)
+    ot, ol = om.generate(toks, 1)
+    assert np.abs(ol[0] - ref_logits).max() <= 2e-5 * np.abs(ref_logits).max()
+    assert ot[0] == int(np.argmax(ref_logits))
