@@ -331,6 +331,71 @@ int jl_model_load_safetensors(jl_model *m, jl_ctx *ctx, jl_st *st, int64_t *ids_
 /* this model's DistributedContext and shard count */
 int jl_model_tp_layout(jl_model *m, jl_dctx *out, int *tp_size);
 
+/* ---- concurrent sessions: request queue + iteration-level batching (csrc/jl_sched.cu) ------------------------------------
+ * The reference runs one thread per request, each calling AbstractModel.generate (core/model/AbstractModel.java:516-646) on its own
+ * KvBuffer (core/tensor/KvBufferCache.java:58-60; jlama-net/.../openai/OpenAIChatService.java:64-74,107-160).  Here requests queue in
+ * front of the batched decode step: every jl_sched_step admits queued requests into free session slots (FIFO), forwards prompt chunks,
+ * runs ONE decode step for all generating requests (rows of different lengths side by side, at most the model's rows-per-call per
+ * backend call) and retires finished requests so that their slots are reused by the next step.  Greedy (temperature 0) like
+ * jl_model_decode.  Under tensor parallelism every rank runs the same scheduler on the same request stream (it is deterministic).
+ * Free the scheduler before its model. */
+typedef struct jl_sched jl_sched;
+/* request states */
+#define JL_SCHED_QUEUED 0
+#define JL_SCHED_PREFILL 1
+#define JL_SCHED_DECODING 2
+#define JL_SCHED_FINISHED 3
+#define JL_SCHED_FAILED 4
+/* Generator.FinishReason (core/model/functions/Generator.java) + the scheduler's own exits */
+#define JL_FINISH_NONE 0
+#define JL_FINISH_MAX_TOKENS 1 /* max_new tokens produced, or the reserved context is full (generate :538,:590) */
+#define JL_FINISH_STOP_TOKEN 2 /* c.eosTokens.contains(next) (:604-608) */
+#define JL_FINISH_CANCELLED 3
+#define JL_FINISH_ERROR 4      /* a backend call failed for this request; jl_sched_last_error */
+/* submit flags */
+#define JL_SCHED_KEEP_SESSION 1 /* keep the session slot and its KV after the request finishes, for a continuation (the reference's
+                                   session header: the next generate() on that UUID starts at kvmem.getCurrentContextPosition(), :533) */
+/* the four model calls the policy is written against; all return JL_OK or a JL_ERR_* */
+typedef struct {
+    int (*reset_session)(void *user, int session);                                                   /* jl_model_reset_session */
+    int (*batch_forward)(void *user, int session, const int32_t *tokens, int n, int start_pos);       /* jl_model_batch_forward */
+    int (*sample)(void *user, int session, int32_t *token_out);                                       /* jl_model_sample, temperature 0 */
+    int (*decode)(void *user, int n, const int32_t *sessions, const int32_t *tokens, const int32_t *positions,
+                  int32_t *next_tokens);                                                              /* jl_model_decode */
+} jl_sched_backend;
+typedef struct {
+    int admitted, prefill_tokens, decode_rows, decode_calls, finished; /* what this step (or run) did */
+    int active, queued;                                                 /* afterwards */
+} jl_sched_stats;
+typedef struct {
+    int state, finish_reason, session, start_pos, n_prompt, n_prefilled, n_generated, next_position;
+    int64_t submit_step, first_token_step, finish_step; /* scheduler step counters: queueing delay and time to first token in steps */
+} jl_sched_request_info_t;
+/* max_active: session slots to use (<= the model's max_sessions; 0 = all).  prefill_tokens_per_step: prompt tokens forwarded per step over
+ * all admitted requests (chunked prefill, bounds the latency a long prompt adds to the running requests' decode steps); 0 = no bound. */
+int jl_sched_create(jl_model *m, int max_active, int prefill_tokens_per_step, jl_sched **out);
+/* the same policy over caller-supplied model calls (CPU tests drive it with the oracle; a host with its own model object plugs in here) */
+int jl_sched_create_backend(const jl_sched_backend *be, void *user, int n_sessions, int max_rows_per_decode, int max_context,
+                            int prefill_tokens_per_step, jl_sched **out);
+int jl_sched_free(jl_sched *s);
+const char *jl_sched_last_error(jl_sched *s);
+/* Queue a request: prompt token ids, at most max_new generated tokens (the first is sampled from the prompt's last row and, like the
+ * reference's, not stop-checked), optional stop tokens.  continue_request >= 0: a finished JL_SCHED_KEEP_SESSION request whose session
+ * this request appends to.  Returns the request id (> 0) or -1.  Callable from any thread, also while a step runs. */
+int64_t jl_sched_submit(jl_sched *s, const int32_t *prompt, int n_prompt, int max_new, const int32_t *stop_tokens, int n_stop, int flags,
+                        int64_t continue_request);
+int jl_sched_cancel(jl_sched *s, int64_t request); /* takes effect at the next step boundary */
+/* one scheduling iteration; returns the first backend error of the step (the affected requests are JL_SCHED_FAILED, the others go on) */
+int jl_sched_step(jl_sched *s, jl_sched_stats *stats /* nullable */);
+/* step until nothing is queued or running (max_steps <= 0: no limit); totals are summed over the steps */
+int jl_sched_run(jl_sched *s, int max_steps, jl_sched_stats *totals /* nullable */);
+/* tokens generated so far (streaming read), state and finish reason; copies min(cap, n) tokens, *n_tokens = n */
+int jl_sched_result(jl_sched *s, int64_t request, int32_t *tokens, int cap, int *n_tokens, int *state, int *finish_reason);
+int jl_sched_request_info(jl_sched *s, int64_t request, jl_sched_request_info_t *info);
+/* forget a finished / failed request; frees the session slot it kept */
+int jl_sched_release(jl_sched *s, int64_t request);
+int jl_sched_counts(jl_sched *s, int *queued, int *active, int *free_slots);
+
 /* ---- jlama-net replacement: NCCL over NVLink instead of gRPC -------------------------------
  * JlamaService.combine (jlama-net/src/main/java/com/github/tjake/jlama/net/grpc/JlamaService.java:300-359)
  * == all-reduce SUM of [M,E] f32.  One process per GPU; rank 0 creates the id, the launcher

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libjlama_b200.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["jl_runtime.cu", "jl_gemv.cu", "jl_gemm_tc.cu", "jl_elementwise.cu", "jl_attention.cu", "jl_model.cu", "jl_comm.cu", "jl_pdecode.cu", "jl_safetensors.cu", "jl_gemm8.cu", "jl_attn_prefill.cu"]
+SOURCES = ["jl_runtime.cu", "jl_gemv.cu", "jl_gemm_tc.cu", "jl_elementwise.cu", "jl_attention.cu", "jl_model.cu", "jl_comm.cu", "jl_pdecode.cu", "jl_safetensors.cu", "jl_gemm8.cu", "jl_attn_prefill.cu", "jl_sched.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr"]

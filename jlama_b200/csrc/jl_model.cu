@@ -21,6 +21,9 @@ int jl_comm_allgather_dev(jl_ctx *ctx, cudaStream_t stream, const void *send, vo
 
 struct jl_model {
     jl_ctx *ctx = nullptr;
+    // serialises the entry points that use the model stream and its staging buffers: the reference calls generate() from one thread per
+    // request (OpenAIChatService.java:107-160); recursive because generate() is built from the other entry points
+    std::recursive_mutex mu;
     jl_model_config cfg;
     jl_dctx d;
     cudaStream_t stream = nullptr;
@@ -561,6 +564,14 @@ extern "C" int jl_model_finalize(jl_model *m) {
 
 extern "C" int64_t jl_model_weight_bytes(jl_model *m) { return m ? m->weight_bytes : -1; }
 
+// limits the session scheduler (jl_sched.cu) plans against: {max_sessions, reserved context, max_batch, rows per decode call}
+void jl_model_limits(jl_model *m, int out[4]) {
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if (!m || !m->finalized) return;
+    out[0] = m->cfg.max_sessions, out[1] = m->max_context, out[2] = m->cfg.max_batch;
+    out[3] = m->cfg.max_sessions < GEMV_MAX_M ? m->cfg.max_sessions : GEMV_MAX_M;
+}
+
 // The timeline buffer was replaced (jl_debug_ktrace): drop every captured decode graph, they are re-captured on demand.
 void jl_models_invalidate_graphs(jl_ctx *ctx) {
     for (jl_model *m : ctx->models) {
@@ -609,6 +620,7 @@ extern "C" int jl_model_free(jl_model *m) {
 
 extern "C" int jl_model_reset_session(jl_model *m, int session) {
     if (!m || !m->finalized || session < 0 || session >= m->cfg.max_sessions) return JL_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> model_lock(m->mu);
     jl_ctx *ctx = m->ctx;
     JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
     JL_CUDA_CHECK(ctx, cudaStreamSynchronize(m->stream));
@@ -1047,6 +1059,7 @@ static int pick_splits(const jl_model *m, int max_pos, int rows) {
 extern "C" int jl_model_batch_forward(jl_model *m, int session, const int32_t *tokens, int n, int start_pos) {
     if (!m || !m->finalized || !tokens || n <= 0 || session < 0 || session >= m->cfg.max_sessions || start_pos < 0)
         return JL_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> model_lock(m->mu);
     jl_ctx *ctx = m->ctx;
     JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
     const int E = m->cfg.embedding_length;
@@ -1079,6 +1092,7 @@ __global__ void __launch_bounds__(256) softmax_sample_kernel(float *logits, int 
 extern "C" int jl_model_sample(jl_model *m, int session, float temperature, float uniform, int32_t *token_out,
                                float *logits_out) {
     if (!m || !m->finalized || !token_out || session < 0 || session >= m->cfg.max_sessions) return JL_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> model_lock(m->mu);
     jl_ctx *ctx = m->ctx;
     JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
     const int E = m->cfg.embedding_length, V = m->cfg.vocab_size;
@@ -1295,6 +1309,7 @@ extern "C" int jl_model_decode(jl_model *m, int n, const int32_t *sessions, cons
     if (!m || !m->finalized || n <= 0 || n > m->cfg.max_sessions || n > GEMV_MAX_M || !sessions || !tokens || !positions ||
         !next_tokens)
         return m ? jl_set_error(m->ctx, JL_ERR_INVALID, "decode: bad arguments (n=%d, max %d)", n, GEMV_MAX_M) : JL_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> model_lock(m->mu);
     jl_ctx *ctx = m->ctx;
     JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
     int max_pos = 0;
@@ -1302,6 +1317,8 @@ extern "C" int jl_model_decode(jl_model *m, int n, const int32_t *sessions, cons
     for (int i = 0; i < n; i++) {
         if (sessions[i] < 0 || sessions[i] >= m->cfg.max_sessions || positions[i] < 0)
             return jl_set_error(ctx, JL_ERR_INVALID, "decode: bad session/position");
+        for (int j = 0; j < i; j++) // two rows of one session would append to and read the same KV positions concurrently
+            if (sessions[j] == sessions[i]) return jl_set_error(ctx, JL_ERR_INVALID, "decode: session %d appears twice in one step", sessions[i]);
         M_CHECK(ensure_pages(m, sessions[i], positions[i], positions[i]));
         if (positions[i] > max_pos) max_pos = positions[i];
         hp[i] = tokens[i];
@@ -1355,6 +1372,7 @@ extern "C" int jl_model_decode_resident(jl_model *m, int session, int32_t first_
                                         int32_t *out_tokens) {
     if (!m || !m->finalized || session < 0 || session >= m->cfg.max_sessions || n_new <= 0 || !out_tokens || start_pos < 0)
         return JL_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> model_lock(m->mu);
     jl_ctx *ctx = m->ctx;
     if (n_new > m->hist_cap) return jl_set_error(ctx, JL_ERR_INVALID, "decode_resident: n_new too large");
     JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
@@ -1403,6 +1421,7 @@ extern "C" int jl_model_decode_resident(jl_model *m, int session, int32_t first_
 // met, 4 o_proj done, 5 gate/up dependency met, 6 gate/up done, 7 down dependency met; then lm_head dependency met, token published.
 extern "C" int jl_model_debug_trace(jl_model *m, uint64_t *out, int64_t out_words) {
     if (!m || !m->finalized || !out) return JL_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> model_lock(m->mu);
     jl_ctx *ctx = m->ctx;
     if (!m->pd_trace) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "phase tracing is off (set JL_PD_TRACE=1 before creating the model)");
     const size_t words = (size_t)m->cfg.num_layers * 16 + 32;
@@ -1429,6 +1448,7 @@ extern "C" int jl_model_last_timing(jl_model *m, double *total_ms, double *gemv_
 extern "C" int jl_model_generate(jl_model *m, int session, const int32_t *prompt, int n_prompt, int n_new, int32_t *out_tokens,
                                  float *logits_out, double *timings_ms) {
     if (!m || !m->finalized || !prompt || n_prompt <= 0 || n_new <= 0 || !out_tokens) return JL_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> model_lock(m->mu);
     const int V = m->cfg.vocab_size;
     auto t0 = std::chrono::steady_clock::now();
     M_CHECK(jl_model_reset_session(m, session));
@@ -1459,6 +1479,7 @@ extern "C" int jl_model_generate(jl_model *m, int session, const int32_t *prompt
 // resumed by this library or by the reference.  Returns the number of pages written / read, or a negative status.
 extern "C" int jl_model_kv_save(jl_model *m, int session, const char *dir, const char *session_name) {
     if (!m || !m->finalized || !dir || !session_name || session < 0 || session >= m->cfg.max_sessions) return JL_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> model_lock(m->mu);
     jl_ctx *ctx = m->ctx;
     JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
     JL_CUDA_CHECK(ctx, cudaStreamSynchronize(m->stream));
@@ -1481,6 +1502,7 @@ extern "C" int jl_model_kv_save(jl_model *m, int session, const char *dir, const
 
 extern "C" int jl_model_kv_load(jl_model *m, int session, const char *dir, const char *session_name) {
     if (!m || !m->finalized || !dir || !session_name || session < 0 || session >= m->cfg.max_sessions) return JL_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> model_lock(m->mu);
     jl_ctx *ctx = m->ctx;
     JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
     std::vector<char> host(m->page_bytes);
@@ -1508,6 +1530,7 @@ extern "C" int jl_model_read_kv(jl_model *m, int session, int layer, int positio
     if (!m || !m->finalized || !out || session < 0 || session >= m->cfg.max_sessions || layer < 0 ||
         layer >= m->cfg.num_layers || position < 0 || position >= m->max_context || (which != 0 && which != 1))
         return JL_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> model_lock(m->mu);
     jl_ctx *ctx = m->ctx;
     JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
     const KvLayout &kv = m->kv;
@@ -1540,6 +1563,7 @@ extern "C" int jl_model_tp_layout(jl_model *m, jl_dctx *out, int *tp_size) {
 
 extern "C" int jl_model_debug_read(jl_model *m, int which, float *out, int64_t n) {
     if (!m || !m->finalized || !out || n <= 0) return JL_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> model_lock(m->mu);
     jl_ctx *ctx = m->ctx;
     JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
     const float *src[8] = {m->x, m->xb, m->q, m->k, m->v, m->att, m->hbuf, m->logits};
@@ -1554,6 +1578,7 @@ extern "C" int jl_model_debug_read(jl_model *m, int which, float *out, int64_t n
 
 extern "C" int jl_model_read_hidden(jl_model *m, int session, float *out) {
     if (!m || !m->finalized || !out || session < 0 || session >= m->cfg.max_sessions) return JL_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> model_lock(m->mu);
     jl_ctx *ctx = m->ctx;
     JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
     JL_CUDA_CHECK(ctx, cudaStreamSynchronize(m->stream));

@@ -46,6 +46,32 @@ class Dctx(C.Structure):
         "groupHeadStart", "groupHeadEnd", "numberOfLayers", "layerStart", "layerEnd")]
 
 
+class SchedStats(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("admitted", "prefill_tokens", "decode_rows", "decode_calls", "finished", "active", "queued")]
+
+
+class SchedRequestInfo(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("state", "finish_reason", "session", "start_pos", "n_prompt", "n_prefilled", "n_generated",
+                                        "next_position")] + [(n, C.c_int64) for n in ("submit_step", "first_token_step", "finish_step")]
+
+
+# jl_sched_backend: the four model calls the scheduler policy is written against
+SCHED_RESET_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int)
+SCHED_FORWARD_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_int)
+SCHED_SAMPLE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int32))
+SCHED_DECODE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                              C.POINTER(C.c_int32))
+
+
+class SchedBackend(C.Structure):
+    _fields_ = [("reset_session", SCHED_RESET_FN), ("batch_forward", SCHED_FORWARD_FN), ("sample", SCHED_SAMPLE_FN),
+                ("decode", SCHED_DECODE_FN)]
+
+
+SCHED_QUEUED, SCHED_PREFILL, SCHED_DECODING, SCHED_FINISHED, SCHED_FAILED = range(5)
+FINISH_NONE, FINISH_MAX_TOKENS, FINISH_STOP_TOKEN, FINISH_CANCELLED, FINISH_ERROR = range(5)
+SCHED_KEEP_SESSION = 1
+
 # every symbol include/jlama_b200.h declares: (restype, argtypes)
 _vp, _i, _i64, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 SIGNATURES = {
@@ -119,6 +145,18 @@ SIGNATURES = {
     "jl_model_debug_trace": (_i, [_vp, _vp, _i64]),
     "jl_model_weight_bytes": (_i64, [_vp]),
     "jl_model_last_timing": (_i, [_vp, C.POINTER(_d), C.POINTER(_d)]),
+    "jl_sched_create": (_i, [_vp, _i, _i, C.POINTER(_vp)]),
+    "jl_sched_create_backend": (_i, [C.POINTER(SchedBackend), _vp, _i, _i, _i, _i, C.POINTER(_vp)]),
+    "jl_sched_free": (_i, [_vp]),
+    "jl_sched_last_error": (C.c_char_p, [_vp]),
+    "jl_sched_submit": (_i64, [_vp, _vp, _i, _i, _vp, _i, _i, _i64]),
+    "jl_sched_cancel": (_i, [_vp, _i64]),
+    "jl_sched_step": (_i, [_vp, C.POINTER(SchedStats)]),
+    "jl_sched_run": (_i, [_vp, _i, C.POINTER(SchedStats)]),
+    "jl_sched_result": (_i, [_vp, _i64, _vp, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "jl_sched_request_info": (_i, [_vp, _i64, C.POINTER(SchedRequestInfo)]),
+    "jl_sched_release": (_i, [_vp, _i64]),
+    "jl_sched_counts": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "jl_comm_unique_id": (_i, [_vp, _vp]),
     "jl_comm_init": (_i, [_vp, _vp, _i, _i]),
     "jl_comm_allreduce_f32": (_i, [_vp, _vp, _i64]),

@@ -1,0 +1,143 @@
+"""Concurrent sessions on the GPU: the request scheduler (csrc/jl_sched.cu) over the batched decode step, and generate() called from
+several threads (the reference's concurrency model: one thread per request, KvBufferCache.java:58-60, OpenAIChatService.java:107-160).
+Every request must come out as AbstractModel.generate() produces it on its own -- checked against the CPU oracle, request by request.
+tests/test_scheduler.py runs the same policy code on CPU."""
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_against_oracle(om, results, near_tie=1e-2):
+    """token for token; a different token is only acceptable where the oracle's own top two logits are a near tie"""
+    exact = 0
+    for prompt, n_new, toks in results:
+        ot, ol = om.generate(prompt, n_new)
+        assert len(toks) == len(ot)
+        for i in range(len(ot)):
+            if toks[i] != ot[i]:
+                top = np.sort(ol[i])[-2:]
+                assert top[1] - top[0] <= near_tie * np.abs(ol[i]).max(), (i, int(toks[i]), int(ot[i]), float(top[1] - top[0]))
+                break
+        else:
+            exact += 1
+    assert exact >= len(results) - 1  # near ties are rare
+    return exact
+
+
+@pytest.mark.parametrize("name,act_q8,slots,budget", [("small", True, 4, 24), ("tiny", True, 3, 0), ("small", True, 1, 0)])
+def test_scheduler_batches_requests_like_sequential_generate(cuda_ctx, oracle, name, act_q8, slots, budget):
+    from jlama_b200 import native, synth
+    from jlama_b200.model import LlamaModel
+    from jlama_b200.scheduler import SessionScheduler
+    cfg = synth.get_config(name)
+    w = synth.make_weights(cfg)
+    gm = LlamaModel(cuda_ctx, cfg, w, working_qtype=native.I8 if act_q8 else native.F32, max_sessions=slots)
+    om = oracle.OracleLlama(cfg, w, act_q8=act_q8)
+    n_req = 9 if slots > 1 else 3
+    work = [(synth.random_prompt(cfg, 5 + 4 * i, seed=500 + i), 3 + (5 * i) % 12) for i in range(n_req)]
+    with SessionScheduler(gm, prefill_tokens_per_step=budget) as sched:
+        ids = [sched.submit(p, n) for p, n in work]
+        max_active, rows_seen = 0, set()
+        while True:
+            st = sched.step()
+            max_active = max(max_active, st.active)
+            rows_seen.add(st.decode_rows)
+            assert st.active <= slots and st.decode_rows <= slots
+            if budget:
+                assert st.prefill_tokens <= budget
+            if st.active == 0 and st.queued == 0:
+                break
+        assert max_active == slots
+        if slots > 1:
+            assert max(rows_seen) > 1  # requests really shared decode steps
+        results = []
+        sessions = set()
+        for rid, (p, n) in zip(ids, work):
+            toks, state, reason = sched.result(rid)
+            assert state == native.SCHED_FINISHED and reason == native.FINISH_MAX_TOKENS and len(toks) == n
+            sessions.add(sched.info(rid).session)
+            results.append((p, n, toks))
+        assert len(sessions) == slots  # all slots used, and reused: n_req > slots
+        assert sched.counts() == (0, 0, slots)
+    _check_against_oracle(om, results)
+    gm.close()
+    om.close()
+
+
+def test_scheduler_stop_tokens_and_kept_sessions(cuda_ctx, oracle):
+    from jlama_b200 import native, synth
+    from jlama_b200.model import LlamaModel
+    from jlama_b200.scheduler import SessionScheduler
+    cfg = synth.get_config("small")
+    w = synth.make_weights(cfg)
+    gm = LlamaModel(cuda_ctx, cfg, w, max_sessions=2)
+    om = oracle.OracleLlama(cfg, w, act_q8=True)
+    p1 = synth.random_prompt(cfg, 11, seed=41)
+    with SessionScheduler(gm) as sched:
+        b = sched.submit(p1, 10, keep_session=True)
+        sched.run()
+        tb, _, rb = sched.result(b)
+        assert len(tb) == 10 and rb == native.FINISH_MAX_TOKENS
+        # the same request again, alone like the first (same kernels, same inputs: bit-identical), now with a stop token
+        stop = int(tb[4])
+        hit = next(i for i in range(1, 10) if tb[i] == stop)  # the token sampled from the prompt is not stop-checked (:576-589)
+        a = sched.submit(p1, 10, stop=[stop])
+        sched.run()
+        ta, _, ra = sched.result(a)
+        assert ta.tolist() == tb[:hit + 1].tolist() and ra == native.FINISH_STOP_TOKEN
+        # a second turn on the kept session appends to its KV (AbstractModel.java:533): the same tokens as one generate() over
+        # prompt + the first turn's forwarded tokens + the new prompt
+        p2 = synth.random_prompt(cfg, 5, seed=42)
+        c = sched.submit(p2, 5, continue_request=b)
+        sched.run()
+        tc, _, _ = sched.result(c)
+        assert sched.info(c).start_pos == len(p1) + 9 and sched.info(c).session == 0
+        joined = np.concatenate([p1, tb[:9], p2]).astype(np.int32)
+    # the oracle forwards the joined prompt in one batch; the GPU did it in two turns with decode steps in between: same KV, same tokens
+    _check_against_oracle(om, [(p1, 10, tb), (joined, 5, tc)])
+    gm.close()
+    om.close()
+
+
+def test_generate_from_two_threads_on_two_sessions(cuda_ctx, oracle):
+    """The reference's concurrency model: request threads call generate() on one model, each with its own session; the entry points
+    of a jl_model serialise on the model's lock (they share the stream and the staging buffers)."""
+    from jlama_b200 import synth
+    from jlama_b200.model import LlamaModel
+    cfg = synth.get_config("small")
+    w = synth.make_weights(cfg)
+    gm = LlamaModel(cuda_ctx, cfg, w, max_sessions=2)
+    om = oracle.OracleLlama(cfg, w, act_q8=True)
+    prompts = [synth.random_prompt(cfg, 13, seed=61), synth.random_prompt(cfg, 21, seed=62)]
+    outs, errs = [None, None], []
+
+    def worker(i):
+        try:
+            for _ in range(3):
+                outs[i] = gm.generate(prompts[i], 12, session=i)[0]
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    _check_against_oracle(om, [(prompts[i], 12, outs[i]) for i in range(2)])
+    gm.close()
+    om.close()
+
+
+def test_decode_rejects_a_session_twice_in_one_step(cuda_ctx):
+    from jlama_b200 import native, synth
+    from jlama_b200.model import LlamaModel
+    cfg = synth.get_config("tiny")
+    gm = LlamaModel(cuda_ctx, cfg, synth.make_weights(cfg), max_sessions=2)
+    gm.batch_forward(synth.random_prompt(cfg, 4), 0, session=0)
+    with pytest.raises(native.JlamaNativeError):
+        gm.decode([1, 2], [4, 4], sessions=[0, 0])
+    gm.close()

@@ -1,0 +1,336 @@
+"""The concurrent-session scheduler (csrc/jl_sched.cu) on CPU: the native policy code runs over Python backends.
+
+1. a toy deterministic "model" that checks the protocol (KV positions appended in order, distinct sessions per step, rows per call,
+   reset before reuse) while the scheduler batches requests of different lengths;
+2. the CPU oracle (one OracleLlama per session slot) as the device: continuous batching must produce exactly the tokens of
+   AbstractModel.generate() run request by request (core/model/AbstractModel.java:516-646).
+"""
+import threading
+
+import numpy as np
+import pytest
+
+from jlama_b200 import native, synth
+from jlama_b200.scheduler import SessionScheduler
+
+VOCAB = 97
+
+
+def _toy_next(history):
+    h = 1469598103934665603
+    for t in history:
+        h = ((h ^ (int(t) + 1)) * 1099511628211) % (1 << 64)
+    return int(h % VOCAB)
+
+
+def _toy_generate(prompt, n_new, stop=(), context=1 << 30, start_hist=()):
+    """What one request must produce: the reference's loop (first token not stop-checked, :576-608)."""
+    hist = list(start_hist) + [int(t) for t in prompt]
+    out = [_toy_next(hist)]
+    while len(out) < n_new and len(hist) < context:
+        hist.append(out[-1])
+        out.append(_toy_next(hist))
+        if out[-1] in stop:
+            break
+    return out, hist
+
+
+class ToyBackend:
+    """Sessions are token histories (the KV analogue); every call asserts the protocol the GPU model relies on."""
+
+    def __init__(self, n_sessions, max_rows, fail_session=None):
+        self.hist = [None] * n_sessions
+        self.max_rows = max_rows
+        self.calls = []
+        self.fail_session = fail_session
+        self.busy = set()
+
+    def reset_session(self, s):
+        self.hist[s] = []
+        self.calls.append(("reset", s))
+
+    def batch_forward(self, s, tokens, start_pos):
+        assert self.hist[s] is not None, "forward on a session that was never reset"
+        assert start_pos == len(self.hist[s]), (start_pos, len(self.hist[s]))
+        if s == self.fail_session:
+            raise RuntimeError("injected failure")
+        self.hist[s].extend(int(t) for t in tokens)
+        self.calls.append(("forward", s, len(tokens), start_pos))
+
+    def sample(self, s):
+        self.calls.append(("sample", s))
+        return _toy_next(self.hist[s])
+
+    def decode(self, sessions, tokens, positions):
+        assert 1 <= len(sessions) <= self.max_rows
+        assert len(set(sessions.tolist())) == len(sessions), "a session twice in one step"
+        out = []
+        for s, t, p in zip(sessions.tolist(), tokens.tolist(), positions.tolist()):
+            assert p == len(self.hist[s]), (s, p, len(self.hist[s]))
+            self.hist[s].append(t)
+            out.append(_toy_next(self.hist[s]))
+        self.calls.append(("decode", tuple(sessions.tolist())))
+        return out
+
+
+def _toy_sched(n_sessions=4, max_rows=3, max_context=4096, budget=0, **kw):
+    be = ToyBackend(n_sessions, max_rows, **kw)
+    s = SessionScheduler.over_backend(be.reset_session, be.batch_forward, be.sample, be.decode, n_sessions, max_rows, max_context, budget)
+    return be, s
+
+
+def test_continuous_batching_reproduces_sequential_generation_and_reuses_slots():
+    rng = np.random.default_rng(7)
+    be, s = _toy_sched(n_sessions=4, max_rows=3)
+    reqs = []
+    for i in range(23):
+        prompt = rng.integers(0, VOCAB, size=int(rng.integers(1, 40)))
+        n_new = int(rng.integers(1, 30))
+        reqs.append((s.submit(prompt, n_new), prompt, n_new))
+    max_active = 0
+    steps = 0
+    while True:
+        st = s.step()
+        steps += 1
+        max_active = max(max_active, st.active)
+        assert st.active <= 4 and st.decode_rows <= 4 and st.decode_calls <= 2  # 4 slots, 3 rows per call
+        if st.active == 0 and st.queued == 0:
+            break
+        assert steps < 1000
+    assert max_active == 4
+    sessions_used = {}
+    first_steps = []
+    for rid, prompt, n_new in reqs:
+        toks, state, reason = s.result(rid)
+        want, _ = _toy_generate(prompt, n_new)
+        assert state == native.SCHED_FINISHED and reason == native.FINISH_MAX_TOKENS
+        assert toks.tolist() == want
+        inf = s.info(rid)
+        sessions_used.setdefault(inf.session, []).append(rid)
+        first_steps.append(inf.first_token_step)
+        assert inf.n_prefilled == len(prompt) and inf.n_generated == n_new
+    assert first_steps == sorted(first_steps)  # FIFO admission
+    assert max(len(v) for v in sessions_used.values()) >= 4  # 23 requests over 4 slots: slots are reused...
+    resets = [c for c in be.calls if c[0] == "reset"]
+    assert len(resets) == 23  # ...and zeroed before every reuse
+    # steps with several generating requests share one decode call
+    assert any(c[0] == "decode" and len(c[1]) == 3 for c in be.calls)
+    q, a, f = s.counts()
+    assert (q, a, f) == (0, 0, 4)
+    s.close()
+
+
+def test_stop_tokens_follow_the_reference_loop():
+    be, s = _toy_sched()
+    prompt = [3, 1, 4, 1, 5]
+    free, _ = _toy_generate(prompt, 40)
+    stop = free[7]
+    first_hit = next(i for i in range(1, 40) if free[i] == stop)  # the token sampled from the prompt is not stop-checked
+    rid = s.submit(prompt, 40, stop=[stop, 1000])
+    # a stop token equal to the very first sampled token must not stop the request (AbstractModel.java:576-589)
+    rid2 = s.submit(prompt, 5, stop=[free[0]])
+    s.run()
+    toks, state, reason = s.result(rid)
+    assert toks.tolist() == free[:first_hit + 1] and reason == native.FINISH_STOP_TOKEN
+    toks2, _, reason2 = s.result(rid2)
+    want2, _ = _toy_generate(prompt, 5, stop=[free[0]])
+    assert toks2.tolist() == want2 and toks2[0] == free[0]
+    assert len(toks2) == 5 or reason2 == native.FINISH_STOP_TOKEN
+    s.close()
+
+
+def test_context_limit_and_argument_checks():
+    be, s = _toy_sched(max_context=16)
+    with pytest.raises(native.JlamaNativeError):
+        s.submit(list(range(16)), 4)  # Preconditions :530 -- no room for a generated token
+    with pytest.raises(native.JlamaNativeError):
+        s.submit([], 4)
+    with pytest.raises(native.JlamaNativeError):
+        s.submit([1, 2], 0)
+    rid = s.submit(list(range(10)), 100)
+    s.run()
+    toks, state, reason = s.result(rid)
+    want, hist = _toy_generate(list(range(10)), 100, context=16)
+    assert toks.tolist() == want and reason == native.FINISH_MAX_TOKENS and len(hist) == 16  # positions 0..15 written, none beyond
+    assert s.info(rid).next_position == 16
+    with pytest.raises(native.JlamaNativeError):
+        s.result(12345)
+    s.close()
+
+
+def test_chunked_prefill_budget_interleaves_decode_steps():
+    be, s = _toy_sched(n_sessions=2, max_rows=2, budget=8)
+    short = s.submit([5, 6, 7], 12)
+    s.step()  # the short request is generating before the long prompt arrives
+    long_prompt = list(range(1, 31))
+    long = s.submit(long_prompt, 3)
+    per_step = []
+    while True:
+        st = s.step()
+        per_step.append((st.prefill_tokens, st.decode_rows))
+        if st.active == 0 and st.queued == 0:
+            break
+    assert all(p <= 8 for p, _ in per_step)
+    assert [p for p, _ in per_step[:4]] == [8, 8, 8, 6]
+    assert all(d >= 1 for _, d in per_step[:4])  # the running request keeps decoding while the long prompt is forwarded in chunks
+    fw = [c for c in be.calls if c[0] == "forward" and c[2] != 3]
+    assert [(c[2], c[3]) for c in fw] == [(8, 0), (8, 8), (8, 16), (6, 24)]
+    assert s.result(long)[0].tolist() == _toy_generate(long_prompt, 3)[0]
+    assert s.result(short)[0].tolist() == _toy_generate([5, 6, 7], 12)[0]
+    s.close()
+
+
+def test_cancel_queued_and_running_requests():
+    be, s = _toy_sched(n_sessions=1, max_rows=1)
+    a = s.submit([1, 2, 3], 50)
+    b = s.submit([4, 5], 50)
+    c = s.submit([6], 4)
+    s.step()
+    s.step()
+    s.cancel(b)  # still queued
+    s.cancel(a)  # running
+    s.run()
+    ta, sa, ra = s.result(a)
+    assert ra == native.FINISH_CANCELLED and 1 <= len(ta) < 50
+    assert ta.tolist() == _toy_generate([1, 2, 3], 50)[0][:len(ta)]
+    tb, sb, rb = s.result(b)
+    assert rb == native.FINISH_CANCELLED and len(tb) == 0 and s.info(b).session == -1
+    assert s.result(c)[0].tolist() == _toy_generate([6], 4)[0]
+    with pytest.raises(native.JlamaNativeError):
+        s.cancel(999)
+    s.close()
+
+
+def test_kept_sessions_continue_at_their_context_position():
+    be, s = _toy_sched(n_sessions=2, max_rows=2)
+    a = s.submit([9, 8, 7], 5, keep_session=True)
+    s.run()
+    ta, _, _ = s.result(a)
+    want_a, hist_a = _toy_generate([9, 8, 7], 5)
+    assert ta.tolist() == want_a
+    assert s.counts() == (0, 0, 1)  # the finished request still holds its slot
+    ia = s.info(a)
+    assert ia.next_position == len(hist_a) == 3 + 4
+    # follow-up turn: appended to the same KV at the session's position (AbstractModel.java:533); the last sampled token of the first
+    # turn was never forwarded, exactly like the reference
+    b = s.submit([11, 12], 6, continue_request=a)
+    with pytest.raises(native.JlamaNativeError):
+        s.submit([1], 2, continue_request=a)  # one continuation per kept session
+    with pytest.raises(native.JlamaNativeError):
+        s.release(a)  # its continuation is queued
+    other = s.submit([1, 2, 3, 4], 3)
+    s.run()
+    want_b, _ = _toy_generate([11, 12], 6, start_hist=hist_a)
+    assert s.result(b)[0].tolist() == want_b
+    ib = s.info(b)
+    assert ib.session == ia.session and ib.start_pos == ia.next_position
+    assert [c for c in be.calls if c[0] == "reset"].count(("reset", ia.session)) == 1  # the continuation did not zero the session
+    assert s.result(other)[0].tolist() == _toy_generate([1, 2, 3, 4], 3)[0]
+    assert s.counts() == (0, 0, 2)  # b did not ask to keep the session
+    with pytest.raises(native.JlamaNativeError):
+        s.submit([1], 2, continue_request=b)
+    s.release(a)
+    s.release(b)
+    with pytest.raises(native.JlamaNativeError):
+        s.result(a)
+    s.close()
+
+
+def test_run_reports_a_queue_that_can_never_be_admitted():
+    be, s = _toy_sched(n_sessions=1, max_rows=1)
+    a = s.submit([1, 2], 2, keep_session=True)
+    s.run()
+    b = s.submit([3], 2)
+    with pytest.raises(native.JlamaNativeError):
+        s.run()  # the only slot is held by a's kept session
+    assert s.result(b)[1] == native.SCHED_QUEUED
+    s.release(a)
+    s.run()
+    assert s.result(b)[0].tolist() == _toy_generate([3], 2)[0]
+    s.close()
+
+
+def test_a_failing_backend_call_fails_only_its_request():
+    be, s = _toy_sched(n_sessions=3, max_rows=3, fail_session=1)
+    ids = [s.submit([i + 1, i + 2], 4) for i in range(5)]
+    st = s.run(check=False)
+    states = [s.result(r)[1] for r in ids]
+    reasons = [s.result(r)[2] for r in ids]
+    failed = [i for i, x in enumerate(states) if x == native.SCHED_FAILED]
+    assert failed and all(s.info(ids[i]).session == 1 for i in failed) and all(reasons[i] == native.FINISH_ERROR for i in failed)
+    for i, r in enumerate(ids):
+        if i not in failed:
+            assert s.result(r)[0].tolist() == _toy_generate([i + 1, i + 2], 4)[0]
+    assert len(failed) + sum(x == native.SCHED_FINISHED for x in states) == 5
+    assert s.backend_errors and "injected" in str(s.backend_errors[0])
+    assert s.counts() == (0, 0, 3)  # failed requests do not leak their slot
+    s.close()
+
+
+def test_submit_from_other_threads_while_stepping():
+    be, s = _toy_sched(n_sessions=4, max_rows=4)
+    rng = np.random.default_rng(3)
+    work = [(rng.integers(0, VOCAB, size=int(rng.integers(1, 20))), int(rng.integers(1, 20))) for _ in range(40)]
+    ids = [None] * len(work)
+
+    def producer(lo, hi):
+        for i in range(lo, hi):
+            ids[i] = s.submit(work[i][0], work[i][1])
+
+    threads = [threading.Thread(target=producer, args=(i * 10, i * 10 + 10)) for i in range(4)]
+    for t in threads:
+        t.start()
+    done = False
+    while not done:
+        st = s.step()
+        alive = any(t.is_alive() for t in threads)
+        done = not alive and st.active == 0 and st.queued == 0
+    for t in threads:
+        t.join()
+    s.run()
+    for rid, (prompt, n_new) in zip(ids, work):
+        toks, state, _ = s.result(rid)
+        assert state == native.SCHED_FINISHED and toks.tolist() == _toy_generate(prompt, n_new)[0]
+    s.close()
+
+
+def test_oracle_as_the_device_matches_generate_request_by_request(oracle):
+    """The same native scheduler, with the CPU restatement of the model in place of the GPU: one OracleLlama per session slot.
+    Every request must come out token for token as AbstractModel.generate() produces it on its own."""
+    cfg = synth.get_config("tiny")
+    w = synth.make_weights(cfg)
+    n_slots = 3
+    slots = [oracle.OracleLlama(cfg, w, act_q8=True) for _ in range(n_slots)]
+    hidden = [None] * n_slots
+
+    def reset(s):
+        slots[s].reset()
+
+    def forward(s, tokens, start_pos):
+        hidden[s] = slots[s].batch_forward(tokens, start_pos)
+
+    def sample(s):
+        return slots[s].sample(hidden[s])[0]
+
+    def decode(sessions, tokens, positions):
+        out = []
+        for s, t, p in zip(sessions.tolist(), tokens.tolist(), positions.tolist()):
+            out.append(slots[s].sample(slots[s].batch_forward([t], p))[0])
+        return out
+
+    sched = SessionScheduler.over_backend(reset, forward, sample, decode, n_slots, 2, cfg["ctx"], prefill_tokens_per_step=16)
+    reqs = []
+    for i in range(7):
+        prompt = synth.random_prompt(cfg, 4 + 5 * i, seed=300 + i)
+        n_new = 3 + (i * 2) % 7
+        reqs.append((sched.submit(prompt, n_new), prompt, n_new))
+    sched.run()
+    ref = oracle.OracleLlama(cfg, w, act_q8=True)
+    for rid, prompt, n_new in reqs:
+        toks, state, reason = sched.result(rid)
+        want, _ = ref.generate(prompt, n_new)
+        assert state == native.SCHED_FINISHED and toks.tolist() == list(want), (rid, toks.tolist(), list(want))
+    sched.close()
+    ref.close()
+    for o in slots:
+        o.close()
