@@ -564,6 +564,8 @@ extern "C" int jl_model_finalize(jl_model *m) {
 
 extern "C" int64_t jl_model_weight_bytes(jl_model *m) { return m ? m->weight_bytes : -1; }
 
+int jl_model_num_experts(jl_model *m) { return m ? m->n_exp : 0; } // jl_model_load_safetensors
+
 // limits the session scheduler (jl_sched.cu) plans against: {max_sessions, reserved context, max_batch, rows per decode call}
 void jl_model_limits(jl_model *m, int out[4]) {
     out[0] = out[1] = out[2] = out[3] = 0;

@@ -256,20 +256,37 @@ static int st_map_file(jl_st *st, const std::string &path) {
             continue;
         }
         const JVal *dt = kv.second.get("dtype"), *sh = kv.second.get("shape"), *off = kv.second.get("data_offsets");
-        if (!dt || !sh || !off || off->arr.size() != 2 || sh->arr.size() > 4) {
+        auto bad = [&](const std::string &why) {
             munmap(m, f.size), close(f.fd);
-            return st_fail(path + ": malformed tensor entry " + kv.first);
-        }
+            return st_fail(path + ": " + why + " (tensor " + kv.first + ")");
+        };
+        if (kv.second.kind != JVal::OBJ || !dt || dt->kind != JVal::STR || !sh || sh->kind != JVal::ARR || !off || off->kind != JVal::ARR ||
+            off->arr.size() != 2 || sh->arr.size() > 4)
+            return bad("malformed tensor entry");
         StTensor t;
         t.name = kv.first;
         t.dtype = dtype_from_string(dt->str);
         t.ndim = (int)sh->arr.size();
-        for (int i = 0; i < t.ndim; i++) t.shape[i] = sh->arr[i].inum;
+        // everything below is read through these numbers: they must be non-negative integers, the byte range must lie inside the
+        // file's data section and, for the dtypes this library reads, hold exactly the elements the shape promises
+        uint64_t elems = 1;
+        for (int i = 0; i < t.ndim; i++) {
+            const JVal &dv = sh->arr[(size_t)i];
+            if (dv.kind != JVal::NUM || !dv.is_int || dv.inum < 0) return bad("shape entries must be non-negative integers");
+            t.shape[i] = dv.inum;
+            if (dv.inum != 0 && elems > (1ULL << 62) / (uint64_t)dv.inum) return bad("shape overflows");
+            elems *= (uint64_t)dv.inum;
+        }
+        for (int i = 0; i < 2; i++)
+            if (off->arr[(size_t)i].kind != JVal::NUM || !off->arr[(size_t)i].is_int || off->arr[(size_t)i].inum < 0)
+                return bad("data_offsets must be non-negative integers");
         t.file = fi;
         t.off0 = (uint64_t)off->arr[0].inum, t.off1 = (uint64_t)off->arr[1].inum;
-        if (t.off1 < t.off0 || f.data0 + t.off1 > f.size) {
-            munmap(m, f.size), close(f.fd);
-            return st_fail(path + ": data_offsets of " + kv.first + " exceed the file");
+        if (t.off1 < t.off0 || t.off1 > f.size - f.data0) return bad("data_offsets exceed the file");
+        if (t.dtype >= 0) {
+            if (t.dtype == JL_Q4 && (elems & 1)) return bad("Q4 tensor with an odd element count");
+            const uint64_t want = t.dtype == JL_F32 ? elems * 4 : (t.dtype == JL_Q4 ? elems / 2 : (t.dtype == JL_I8 ? elems : elems * 2));
+            if (want != t.off1 - t.off0) return bad("byte range does not match dtype and shape");
         }
         st->tensors.push_back(t);
     }
@@ -327,8 +344,14 @@ extern "C" int jl_st_open(const char *path, jl_st **out) {
             std::vector<std::string> shards;
             for (auto &kv : wm->obj)
                 if (kv.second.kind == JVal::STR && std::find(shards.begin(), shards.end(), kv.second.str) == shards.end()) shards.push_back(kv.second.str);
-            for (auto &s : shards)
+            for (auto &s : shards) {
+                // shard files live next to the index (SafeTensorIndex.java:59-70): no absolute paths, no way out of the directory
+                if (s.empty() || s[0] == '/' || s.find("..") != std::string::npos) {
+                    rc = st_fail(idx + ": bad shard file name " + s);
+                    break;
+                }
                 if ((rc = st_map_file(st.get(), p + "/" + s)) != JL_OK) break;
+            }
         } else if (file_exists(single)) {
             rc = st_map_file(st.get(), single);
         } else {
@@ -601,6 +624,9 @@ extern "C" int jl_config_from_json(const char *config_json_path, jl_model_config
             const JVal *ty = rs->get("rope_type"), *fa = rs->get("factor");
             if (ty && ty->kind == JVal::STR && ty->str == "linear" && fa && fa->kind == JVal::NUM) cfg->rope_scaling = fa->num;
         }
+    // MixtralConfig (core/model/mixtral/MixtralConfig.java): num_local_experts / num_experts_per_tok
+    cfg->num_experts = (int)geti("num_local_experts", 0);
+    cfg->experts_per_token = cfg->num_experts > 0 ? (int)geti("num_experts_per_tok", 2) : 0;
     cfg->working_qtype = JL_I8;
     cfg->kv_dtype = JL_F32;
     cfg->tp_size = 1;
@@ -620,16 +646,23 @@ static int register_slice(jl_ctx *ctx, jl_st *st, const char *name, int64_t row0
     const int i = jl_st_find(st, name);
     if (i < 0) return jl_set_error(ctx, JL_ERR_INVALID, "checkpoint has no tensor %s", name);
     const StTensor &t = st->tensors[i];
+    if (t.dtype < 0) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "%s: dtype not readable by this library", name);
+    if (t.ndim != 1 && t.ndim != 2) return jl_set_error(ctx, JL_ERR_INVALID, "%s: %d-dimensional tensor where a matrix or vector is expected", name, t.ndim);
     const int64_t R = t.ndim == 2 ? t.shape[0] : 1, Cc = t.ndim == 2 ? t.shape[1] : t.shape[0];
     if (rows < 0) row0 = 0, rows = R;
     if (cols < 0) col0 = 0, cols = Cc;
-    if (row0 + rows > R || col0 + cols > Cc) return jl_set_error(ctx, JL_ERR_INVALID, "%s: slice out of range", name);
+    if (row0 < 0 || col0 < 0 || rows <= 0 || cols <= 0 || row0 + rows > R || col0 + cols > Cc)
+        return jl_set_error(ctx, JL_ERR_INVALID, "%s: slice out of range", name);
     const uint8_t *src = (const uint8_t *)jl_st_data(st, i);
     const float *qb = nullptr;
     int dt = t.dtype;
     if (dt == JL_Q4 || dt == JL_I8) {
         const int j = jl_st_find(st, (std::string(name) + ".qb").c_str());
         if (j < 0) return jl_set_error(ctx, JL_ERR_INVALID, "%s: quantised tensor without %s.qb", name, name);
+        // the scales are read as f32 [R, Cc/32] (SafeTensorSupport.java:264-267): check that the sibling really is that
+        const StTensor &q = st->tensors[j];
+        if ((Cc % 32) || q.dtype != JL_F32 || q.ndim != 2 || q.shape[0] != R || q.shape[1] != Cc / 32)
+            return jl_set_error(ctx, JL_ERR_INVALID, "%s.qb: expected F32 block scales of shape [%lld, %lld]", name, (long long)R, (long long)(Cc / 32));
         qb = (const float *)jl_st_data(st, j);
         if ((col0 % 32) || (cols % 32)) return jl_set_error(ctx, JL_ERR_INVALID, "%s: column shard must be a multiple of 32", name);
     }
@@ -663,6 +696,7 @@ static int register_slice(jl_ctx *ctx, jl_st *st, const char *name, int64_t row0
 }
 
 extern "C" int jl_model_tp_layout(jl_model *m, jl_dctx *out, int *tp_size); // jl_model.cu
+int jl_model_num_experts(jl_model *m);                                          // jl_model.cu
 
 // Registers this rank's shard of every tensor and binds it (the C++ twin of jlama_b200/model.py LlamaModel.__init__).
 // ids_out (nullable, capacity ids_cap): the registered tensor ids, for jl_unregister_tensor after jl_model_free.
@@ -685,7 +719,17 @@ extern "C" int jl_model_load_safetensors(jl_model *m, jl_ctx *ctx, jl_st *st, in
         n++;
         return jl_model_set_tensor(m, layer, slot, id);
     };
+    auto put_expert = [&](int layer, int expert, int which, const std::string &name) -> int {
+        int64_t id = -1;
+        int rc = register_slice(ctx, st, name.c_str(), 0, -1, 0, -1, &id);
+        if (rc != JL_OK) return rc;
+        if (ids_out && n < ids_cap) ids_out[n] = id;
+        n++;
+        return jl_model_set_expert_tensor(m, layer, expert, which, id);
+    };
     const bool sh = tp > 1;
+    const int rank = sh && d.attentionSegmentLength > 0 ? d.attentionSegmentStart / d.attentionSegmentLength : 0;
+    const int n_experts = jl_model_num_experts(m);
     int rc = put(-1, JL_T_EMBED, "model.embed_tokens.weight", 0, -1, 0, -1, false);
     if (rc == JL_OK) rc = put(-1, JL_T_OUT_NORM, "model.norm.weight", 0, -1, 0, -1, false);
     if (rc == JL_OK) rc = put(-1, JL_T_LM_HEAD, "lm_head.weight", 0, -1, 0, -1, true); // tied embeddings: absent (LlamaModel.java:152-156)
@@ -700,6 +744,19 @@ extern "C" int jl_model_load_safetensors(jl_model *m, jl_ctx *ctx, jl_st *st, in
         if (rc == JL_OK) rc = put(L, JL_L_V, b + "self_attn.v_proj.weight", kr0, kr, 0, -1, false);
         if (rc == JL_OK) rc = put(L, JL_L_O, b + "self_attn.o_proj.weight", 0, -1, ar0, ar, false);
         if (rc == JL_OK) rc = put(L, JL_L_FFN_NORM, b + "post_attention_layernorm.weight", 0, -1, 0, -1, false);
+        if (rc == JL_OK && n_experts > 0) {
+            // MixtralModel.java:88-105: router + w1 (gate) / w2 (down) / w3 (up) per expert.  Expert parallelism as in model.py:
+            // expert e lives whole on rank e % tp, the router is replicated.
+            rc = put_expert(L, -1, 0, b + "block_sparse_moe.gate.weight");
+            for (int e = 0; e < n_experts && rc == JL_OK; e++) {
+                if (e % tp != rank) continue;
+                const std::string eb = b + "block_sparse_moe.experts." + std::to_string(e) + ".";
+                rc = put_expert(L, e, 0, eb + "w1.weight");
+                if (rc == JL_OK) rc = put_expert(L, e, 1, eb + "w2.weight");
+                if (rc == JL_OK) rc = put_expert(L, e, 2, eb + "w3.weight");
+            }
+            continue;
+        }
         if (rc == JL_OK) rc = put(L, JL_L_GATE, b + "mlp.gate_proj.weight", hr0, hr, 0, -1, false);
         if (rc == JL_OK) rc = put(L, JL_L_DOWN, b + "mlp.down_proj.weight", 0, -1, hr0, hr, false);
         if (rc == JL_OK) rc = put(L, JL_L_UP, b + "mlp.up_proj.weight", hr0, hr, 0, -1, false);

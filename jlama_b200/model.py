@@ -88,6 +88,8 @@ class LlamaModel:
         self.ctx, self.lib = ctx, ctx.lib
         self.cfg = dict(ctx=mc.context_length, E=mc.embedding_length, H=mc.hidden_length, heads=mc.num_heads, kv_heads=mc.num_kv_heads,
                         layers=mc.num_layers, vocab=mc.vocab_size, eps=mc.layer_norm_eps, rope_theta=mc.rope_theta, name=os.path.basename(path))
+        if mc.num_experts:
+            self.cfg.update(experts=mc.num_experts, experts_per_token=mc.experts_per_token)
         self.dctx = DistributedContext(self.cfg, tp_rank, tp_size)
         self.max_sessions = max_sessions
         self._ids = []
@@ -96,7 +98,7 @@ class LlamaModel:
         self.h = h
         try:
             with sio.SafeTensors(path) as st:
-                cap = 16 * mc.num_layers + 8
+                cap = (16 + 3 * mc.num_experts) * mc.num_layers + 8
                 ids = (C.c_int64 * cap)()
                 n = C.c_int()
                 rc = self.lib.jl_model_load_safetensors(self.h, ctx.h, st.h, ids, cap, C.byref(n))

@@ -127,6 +127,9 @@ def save_checkpoint(dirpath, weights, config=None):
               "num_attention_heads": config["heads"], "num_key_value_heads": config["kv_heads"], "num_hidden_layers": config["layers"],
               "vocab_size": config["vocab"], "max_position_embeddings": config["ctx"], "rms_norm_eps": config["eps"],
               "rope_theta": config["rope_theta"], "tie_word_embeddings": bool(config.get("tied"))}
+        if config.get("experts"):  # MixtralConfig.java: num_local_experts / num_experts_per_tok
+            hf.update({"architectures": ["MixtralForCausalLM"], "num_local_experts": config["experts"],
+                       "num_experts_per_tok": config["experts_per_token"]})
         with open(os.path.join(dirpath, "config.json"), "w") as f:
             json.dump(hf, f)
 

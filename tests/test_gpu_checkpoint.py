@@ -58,3 +58,23 @@ def test_checkpoint_directory_loads_and_generates_like_in_memory_weights(cuda_ct
     assert list(ta) == list(ot)
     a.close()
     b.close()
+
+
+def test_mixtral_checkpoint_directory_loads_like_in_memory_weights(cuda_ctx, oracle, tmp_path):
+    """MixtralModel.java:88-105 tensor names (block_sparse_moe.gate / experts.<e>.w1|w2|w3) and MixtralConfig's num_local_experts /
+    num_experts_per_tok read behind the C ABI: same registrations as the in-memory path, so the generations are bit-identical."""
+    from jlama_b200 import synth
+    from jlama_b200 import safetensors_io as sio
+    from jlama_b200.model import LlamaModel
+    cfg = synth.get_config("tiny-mixtral")
+    w = synth.make_weights(cfg)
+    sio.save_checkpoint(str(tmp_path / "mx"), w, cfg)
+    a = LlamaModel.from_checkpoint(cuda_ctx, str(tmp_path / "mx"))
+    assert a.cfg["experts"] == 8 and a.cfg["experts_per_token"] == 2
+    b = LlamaModel(cuda_ctx, cfg, w)
+    prompt = synth.random_prompt(cfg, 9)
+    ta, la = a.generate(prompt, 8, want_logits=True)
+    tb, lb = b.generate(prompt, 8, want_logits=True)
+    assert list(ta) == list(tb) and np.array_equal(la, lb)
+    a.close()
+    b.close()

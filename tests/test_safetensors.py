@@ -93,3 +93,107 @@ def test_index_json_shards_and_i8(tmp_path):
         assert st.metadata("format") == "pt"
     with pytest.raises(sio.SafeTensorsError):
         sio.SafeTensors(str(tmp_path / "missing-dir-or-file"))
+
+
+def _file(tmp_path, name, header, data=b""):
+    h = header if isinstance(header, bytes) else json.dumps(header).encode()
+    p = tmp_path / name
+    p.write_bytes(struct.pack("<q", len(h)) + h + data)
+    return str(p)
+
+
+@pytest.mark.parametrize("entry,why", [
+    ({"dtype": "F32", "shape": [4, 4], "data_offsets": [0, 16]}, "does not match"),        # 64 bytes promised, 16 present
+    ({"dtype": "Q4", "shape": [2, 64], "data_offsets": [0, 16]}, "does not match"),        # Q4 is N*K/2 = 64 bytes
+    ({"dtype": "F32", "shape": [-1, 4], "data_offsets": [0, 16]}, "non-negative"),
+    ({"dtype": "F32", "shape": [2, 2.5], "data_offsets": [0, 16]}, "non-negative"),
+    ({"dtype": "F32", "shape": [4], "data_offsets": [-16, 0]}, "non-negative"),            # would point before the data section
+    ({"dtype": "F32", "shape": [4], "data_offsets": [16, 0]}, "exceed"),
+    ({"dtype": "F32", "shape": [4], "data_offsets": [0, 1 << 40]}, "exceed"),
+    ({"dtype": "F32", "shape": [1 << 40, 1 << 40], "data_offsets": [0, 16]}, "overflow"),
+    ({"dtype": "F32", "shape": [1, 1, 1, 1, 4], "data_offsets": [0, 16]}, "malformed"),
+    ({"dtype": 7, "shape": [4], "data_offsets": [0, 16]}, "malformed"),
+    ({"dtype": "F32", "shape": "4", "data_offsets": [0, 16]}, "malformed"),
+    ({"dtype": "F32", "shape": [4], "data_offsets": [0]}, "malformed"),
+    ("F32", "malformed"),
+])
+def test_header_entries_are_validated_before_anything_reads_through_them(tmp_path, entry, why):
+    """Every later read (jl_st_data, the loader's row slices, the quantiser) trusts shape, dtype and data_offsets: a header whose
+    numbers do not describe bytes that exist in the file is rejected when it is opened."""
+    with pytest.raises(sio.SafeTensorsError, match=why):
+        sio.SafeTensors(_file(tmp_path, "bad.safetensors", {"t": entry}, b"\0" * 16))
+
+
+def test_unknown_dtypes_are_listed_but_not_interpreted(tmp_path):
+    p = _file(tmp_path, "u.safetensors", {"x": {"dtype": "F8_E4M3", "shape": [3], "data_offsets": [0, 3]},
+                                          "y": {"dtype": "F16", "shape": [2], "data_offsets": [3, 7]}}, b"abc" + b"\0" * 4)
+    with sio.SafeTensors(p) as st:
+        assert st.info("x")["dtype_code"] == -1 and st.info("x")["nbytes"] == 3
+        assert st.info("y")["dtype"] == "F16"
+        assert st.majority_dtype() == native.F32  # F16 counts as F32 (Weights.java:49-66)
+
+
+def test_index_json_cannot_name_files_outside_the_checkpoint_directory(tmp_path):
+    d = tmp_path / "m"
+    d.mkdir()
+    sio.write_safetensors(str(tmp_path / "outside.safetensors"), {"a": (native.F32, np.zeros((1, 4), np.float32), None)})
+    for shard in ("../outside.safetensors", str(tmp_path / "outside.safetensors"), ""):
+        (d / "model.safetensors.index.json").write_text(json.dumps({"weight_map": {"a": shard}}))
+        with pytest.raises(sio.SafeTensorsError, match="shard"):
+            sio.SafeTensors(str(d))
+
+
+def test_mutated_headers_never_crash_the_reader(tmp_path):
+    """Byte-level mutations of a valid header: the reader either rejects the file or returns tensors whose bytes are all
+    inside the mapping (every byte of every listed tensor is touched)."""
+    rng = np.random.default_rng(11)
+    good = {"a": {"dtype": "F32", "shape": [2, 8], "data_offsets": [0, 64]},
+            "w": {"dtype": "Q4", "shape": [2, 64], "data_offsets": [64, 128]},
+            "w.qb": {"dtype": "F32", "shape": [2, 2], "data_offsets": [128, 144]},
+            "__metadata__": {"k": "vé\\n"}}
+    base = json.dumps(good).encode()
+    data = bytes(range(144))
+    opened = 0
+    for it in range(400):
+        h = bytearray(base)
+        for _ in range(int(rng.integers(1, 4))):
+            kind = int(rng.integers(0, 4))
+            pos = int(rng.integers(0, len(h)))
+            if kind == 0:
+                h[pos] = int(rng.integers(0, 256))
+            elif kind == 1:
+                del h[pos:pos + int(rng.integers(1, 6))]
+            elif kind == 2:
+                h[pos:pos] = bytes(rng.integers(32, 127, size=int(rng.integers(1, 6)), dtype=np.uint8))
+            else:
+                tok = [b"-1", b"99999999999999999999", b"1e309", b"[", b"{", b"\\u12", b"\"", b"null", b"9223372036854775807"][int(rng.integers(0, 9))]
+                h[pos:pos] = tok
+        p = _file(tmp_path, "m.safetensors", bytes(h), data)
+        try:
+            st = sio.SafeTensors(p)
+        except (sio.SafeTensorsError, UnicodeDecodeError):
+            continue
+        opened += 1
+        for name in st.names():
+            inf = st.info(name)
+            i = st._index[name][0]
+            if inf["nbytes"]:
+                ptr = st.lib.jl_st_data(st.h, i)
+                raw = np.ctypeslib.as_array(__import__("ctypes").cast(ptr, __import__("ctypes").POINTER(__import__("ctypes").c_uint8)), shape=(inf["nbytes"],))
+                assert int(raw.astype(np.uint64).sum()) >= 0
+        st.close()
+    assert opened > 0  # some mutations only touch names / metadata and must still load
+
+
+def test_config_json_mixtral_fields(tmp_path):
+    cfg = synth.get_config("tiny-mixtral")
+    sio.save_checkpoint(str(tmp_path / "mx"), {}, cfg)
+    mc = sio.config_from_json(str(tmp_path / "mx" / "config.json"))
+    assert (mc.num_experts, mc.experts_per_token) == (8, 2) and mc.num_layers == cfg["layers"]
+    dense = synth.get_config("tiny")
+    sio.save_checkpoint(str(tmp_path / "d"), {}, dense)
+    mc = sio.config_from_json(str(tmp_path / "d" / "config.json"))
+    assert (mc.num_experts, mc.experts_per_token) == (0, 0)
+    (tmp_path / "broken.json").write_text("{\"hidden_size\": 12")
+    with pytest.raises(sio.SafeTensorsError):
+        sio.config_from_json(str(tmp_path / "broken.json"))
