@@ -214,6 +214,9 @@ public final class CudaLlamaModel implements AutoCloseable {
         } catch (RuntimeException | Error e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); }
     }
 
+    /** jl_model* for the classes of this package that take the model as an argument (CudaSessionScheduler). */
+    MemorySegment handle() { return model; }
+
     public void resetSession(int session) {
         try { check((int) jl_model_reset_session.invokeExact(model, session), ctx); }
         catch (RuntimeException | Error e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); }

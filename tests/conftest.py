@@ -10,6 +10,15 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    config.addinivalue_line("markers", "late: run after every other test (see pytest_collection_modifyitems)")
+
+
+def pytest_collection_modifyitems(config, items):
+    """GPU tests written after this round's GPU budget was spent have not run on a B200 yet.  They are marked `late` and ordered
+    behind everything else, so that under `-x` a surprise in one of them cannot hide the tests that are known to pass."""
+    late = [it for it in items if it.get_closest_marker("late")]
+    if late:
+        items[:] = [it for it in items if not it.get_closest_marker("late")] + late
 
 
 @pytest.fixture(scope="session")
