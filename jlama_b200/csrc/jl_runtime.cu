@@ -316,6 +316,7 @@ extern "C" int jl_gemm_host(jl_ctx *ctx, int a_dtype, const void *a, int a_col_o
     JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
     if (b_dtype != JL_F32 && b_dtype != JL_BF16) return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "gemm_host: B must be F32/BF16");
     if (!b || n <= 0) return n <= 0 ? JL_OK : jl_set_error(ctx, JL_ERR_INVALID, "gemm_host: null B");
+    if (n0 < 0 || ldb <= 0) return jl_set_error(ctx, JL_ERR_INVALID, "gemm_host: negative row offset / row stride");
     const size_t esz = b_dtype == JL_F32 ? 4 : 2;
     // upload only the rows used
     DevTensor B;
@@ -339,8 +340,9 @@ extern "C" int jl_gemm_host(jl_ctx *ctx, int a_dtype, const void *a, int a_col_o
 extern "C" int jl_accumulate(jl_ctx *ctx, float *a, int a_rows, int lda, int b_dtype, const void *b, const float *b_scales,
                              int b_rows, int ldb, int offset, int length) {
     HOST_OP_PROLOGUE();
-    if (!a || !b || offset < 0 || offset + length > lda || offset + length > ldb)
+    if (!a || !b || a_rows < 0 || length < 0 || offset < 0 || (int64_t)offset + length > lda || (int64_t)offset + length > ldb)
         return jl_set_error(ctx, JL_ERR_INVALID, "accumulate: bad arguments");
+    if (a_rows == 0 || length == 0) return JL_OK;
     if (b_rows != 1 && b_rows != a_rows) return jl_set_error(ctx, JL_ERR_INVALID, "accumulate: b must have 1 or a_rows rows");
     if (b_dtype != JL_F32 && b_dtype != JL_BF16 && b_dtype != JL_Q4)
         return jl_set_error(ctx, JL_ERR_UNSUPPORTED, "accumulate: b dtype %d", b_dtype);
@@ -367,8 +369,10 @@ extern "C" int jl_accumulate(jl_ctx *ctx, float *a, int a_rows, int lda, int b_d
 extern "C" int jl_maccumulate(jl_ctx *ctx, float *a, int a_rows, int lda, const float *b, int b_rows, int ldb, int offset,
                               int length) {
     HOST_OP_PROLOGUE();
-    if (!a || !b || offset < 0 || offset + length > lda || offset + length > ldb || (b_rows != 1 && b_rows != a_rows))
+    if (!a || !b || a_rows < 0 || length < 0 || offset < 0 || (int64_t)offset + length > lda || (int64_t)offset + length > ldb ||
+        (b_rows != 1 && b_rows != a_rows))
         return jl_set_error(ctx, JL_ERR_INVALID, "maccumulate: bad arguments");
+    if (a_rows == 0 || length == 0) return JL_OK;
     const size_t ab = (size_t)a_rows * lda * 4, bb = (size_t)b_rows * ldb * 4;
     float *da = (float *)jl_scratch(ctx, 0, ab), *db = (float *)jl_scratch(ctx, 1, bb);
     if (!da || !db) return JL_ERR_OOM;
@@ -383,7 +387,8 @@ extern "C" int jl_maccumulate(jl_ctx *ctx, float *a, int a_rows, int lda, const 
 
 extern "C" int jl_scale(jl_ctx *ctx, float factor, float *x, int rows, int ldx, int offset, int length) {
     HOST_OP_PROLOGUE();
-    if (!x || offset < 0 || offset + length > ldx) return jl_set_error(ctx, JL_ERR_INVALID, "scale: bad arguments");
+    if (!x || rows < 0 || length < 0 || offset < 0 || (int64_t)offset + length > ldx) return jl_set_error(ctx, JL_ERR_INVALID, "scale: bad arguments");
+    if (rows == 0 || length == 0) return JL_OK;
     const size_t xb = (size_t)rows * ldx * 4;
     float *dx = (float *)jl_scratch(ctx, 0, xb);
     if (!dx) return JL_ERR_OOM;
@@ -398,7 +403,8 @@ extern "C" int jl_scale(jl_ctx *ctx, float factor, float *x, int rows, int ldx, 
 extern "C" int jl_saxpy_batch(jl_ctx *ctx, const float *alpha, const float *x, int ldx, float *y, int xoffset, int yoffset,
                               int limit, int a_offset, int x_row_offset, int batch) {
     HOST_OP_PROLOGUE();
-    if (!alpha || !x || !y || limit < 0 || batch < 0 || xoffset < 0 || xoffset + limit > ldx)
+    if (!alpha || !x || !y || limit < 0 || batch < 0 || xoffset < 0 || yoffset < 0 || a_offset < 0 || x_row_offset < 0 ||
+        (int64_t)xoffset + limit > ldx)
         return jl_set_error(ctx, JL_ERR_INVALID, "saxpy: bad arguments");
     if (limit == 0 || batch == 0) return JL_OK;
     float *da = (float *)jl_scratch(ctx, 0, (size_t)batch * 4);
@@ -425,8 +431,9 @@ extern "C" int jl_saxpy(jl_ctx *ctx, float alpha, const float *x, float *y, int 
 extern "C" int jl_quantize_q8(jl_ctx *ctx, const float *x, int rows, int ldx, int offset, int length, int8_t *q,
                               float *scales) {
     HOST_OP_PROLOGUE();
-    if (!x || !q || !scales || offset < 0 || offset + length > ldx)
+    if (!x || !q || !scales || rows < 0 || length < 0 || offset < 0 || (int64_t)offset + length > ldx)
         return jl_set_error(ctx, JL_ERR_INVALID, "quantize_q8: bad arguments");
+    if (rows == 0) return JL_OK;
     const size_t xb = (size_t)rows * ldx * 4, qb = (size_t)rows * ldx, sb = (size_t)rows * (ldx / 32) * 4;
     float *dx = (float *)jl_scratch(ctx, 0, xb);
     int8_t *dq = (int8_t *)jl_scratch(ctx, 1, qb);
@@ -445,7 +452,9 @@ extern "C" int jl_quantize_q8(jl_ctx *ctx, const float *x, int rows, int ldx, in
 
 extern "C" int jl_quantize_bf16(jl_ctx *ctx, const float *x, int rows, int ldx, int offset, int length, uint16_t *out) {
     HOST_OP_PROLOGUE();
-    if (!x || !out || offset < 0 || offset + length > ldx) return jl_set_error(ctx, JL_ERR_INVALID, "quantize_bf16: bad arguments");
+    if (!x || !out || rows < 0 || length < 0 || offset < 0 || (int64_t)offset + length > ldx)
+        return jl_set_error(ctx, JL_ERR_INVALID, "quantize_bf16: bad arguments");
+    if (rows == 0) return JL_OK;
     const size_t xb = (size_t)rows * ldx * 4, ob = (size_t)rows * ldx * 2;
     float *dx = (float *)jl_scratch(ctx, 0, xb);
     uint16_t *dout = (uint16_t *)jl_scratch(ctx, 1, ob);
@@ -461,7 +470,8 @@ extern "C" int jl_quantize_bf16(jl_ctx *ctx, const float *x, int rows, int ldx, 
 
 extern "C" int jl_quantize_q4_weights(jl_ctx *ctx, const float *x, int64_t rows, int64_t cols, uint8_t *q, float *scales) {
     HOST_OP_PROLOGUE();
-    if (!x || !q || !scales || rows <= 0 || cols <= 0) return jl_set_error(ctx, JL_ERR_INVALID, "quantize_q4: bad arguments");
+    if (!x || !q || !scales || rows <= 0 || cols <= 0 || (cols % 32))
+        return jl_set_error(ctx, JL_ERR_INVALID, "quantize_q4: bad arguments (cols must be a multiple of the 32-element block)");
     const size_t xb = (size_t)rows * cols * 4, qb = (size_t)rows * cols / 2, sb = (size_t)rows * (cols / 32) * 4;
     float *dx = (float *)jl_scratch(ctx, 0, xb);
     uint8_t *dq = (uint8_t *)jl_scratch(ctx, 1, qb);
@@ -479,9 +489,10 @@ extern "C" int jl_quantize_q4_weights(jl_ctx *ctx, const float *x, int64_t rows,
 extern "C" int jl_layernorm(jl_ctx *ctx, const float *x, int rows, int ldx, int w_dtype, const void *w, int b_dtype, const void *bias, float eps,
                             int embedding_length, int offset, int length, float *out) {
     HOST_OP_PROLOGUE();
-    if (!x || !w || !bias || !out || offset < 0 || offset + length > ldx || (w_dtype != JL_F32 && w_dtype != JL_BF16) ||
-        (b_dtype != JL_F32 && b_dtype != JL_BF16))
+    if (!x || !w || !bias || !out || rows < 0 || length < 0 || offset < 0 || (int64_t)offset + length > ldx ||
+        (w_dtype != JL_F32 && w_dtype != JL_BF16) || (b_dtype != JL_F32 && b_dtype != JL_BF16))
         return jl_set_error(ctx, JL_ERR_INVALID, "layernorm: bad arguments");
+    if (rows == 0 || length == 0) return JL_OK;
     const size_t xb = (size_t)rows * ldx * 4, n = (size_t)(offset + length);
     const size_t wb = n * (w_dtype == JL_F32 ? 4 : 2), bb = n * (b_dtype == JL_F32 ? 4 : 2);
     float *dx = (float *)jl_scratch(ctx, 0, xb);
@@ -502,7 +513,9 @@ extern "C" int jl_layernorm(jl_ctx *ctx, const float *x, int rows, int ldx, int 
 
 extern "C" int jl_activation(jl_ctx *ctx, int type, float *x, int rows, int ld, int offset, int length) {
     HOST_OP_PROLOGUE();
-    if (!x || type < 0 || type > 2 || offset < 0 || offset + length > ld) return jl_set_error(ctx, JL_ERR_INVALID, "activation: bad arguments");
+    if (!x || type < 0 || type > 2 || rows < 0 || length < 0 || offset < 0 || (int64_t)offset + length > ld)
+        return jl_set_error(ctx, JL_ERR_INVALID, "activation: bad arguments");
+    if (rows == 0 || length == 0) return JL_OK;
     const size_t xb = (size_t)rows * ld * 4;
     float *dx = (float *)jl_scratch(ctx, 0, xb);
     if (!dx) return JL_ERR_OOM;
@@ -516,7 +529,8 @@ extern "C" int jl_activation(jl_ctx *ctx, int type, float *x, int rows, int ld, 
 
 extern "C" int jl_quantize_q8_weights(jl_ctx *ctx, const float *x, int64_t rows, int64_t cols, int8_t *q, float *scales) {
     HOST_OP_PROLOGUE();
-    if (!x || !q || !scales || rows <= 0 || cols <= 0) return jl_set_error(ctx, JL_ERR_INVALID, "quantize_q8_weights: bad arguments");
+    if (!x || !q || !scales || rows <= 0 || cols <= 0 || (cols % 32))
+        return jl_set_error(ctx, JL_ERR_INVALID, "quantize_q8_weights: bad arguments (cols must be a multiple of the 32-element block)");
     const size_t xb = (size_t)rows * cols * 4, qb = (size_t)rows * cols, sb = (size_t)rows * (cols / 32) * 4;
     float *dx = (float *)jl_scratch(ctx, 0, xb);
     int8_t *dq = (int8_t *)jl_scratch(ctx, 1, qb);
@@ -534,8 +548,9 @@ extern "C" int jl_quantize_q8_weights(jl_ctx *ctx, const float *x, int64_t rows,
 extern "C" int jl_rmsnorm(jl_ctx *ctx, const float *x, int rows, int ldx, int w_dtype, const void *w, float weight_adjustment,
                           float eps, int embedding_length, int offset, int length, float *out) {
     HOST_OP_PROLOGUE();
-    if (!x || !w || !out || offset < 0 || offset + length > ldx || (w_dtype != JL_F32 && w_dtype != JL_BF16))
+    if (!x || !w || !out || rows < 0 || length < 0 || offset < 0 || (int64_t)offset + length > ldx || (w_dtype != JL_F32 && w_dtype != JL_BF16))
         return jl_set_error(ctx, JL_ERR_INVALID, "rmsnorm: bad arguments");
+    if (rows == 0) return JL_OK;
     const size_t xb = (size_t)rows * ldx * 4, wb = (size_t)(offset + length) * (w_dtype == JL_F32 ? 4 : 2);
     float *dx = (float *)jl_scratch(ctx, 0, xb);
     void *dw = jl_scratch(ctx, 1, wb);
@@ -568,7 +583,9 @@ extern "C" int jl_softmax(jl_ctx *ctx, float *x, int offset, int length) {
 
 extern "C" int jl_silu_mul(jl_ctx *ctx, float *gate, const float *up, int rows, int ld, int offset, int length) {
     HOST_OP_PROLOGUE();
-    if (!gate || !up || offset < 0 || offset + length > ld) return jl_set_error(ctx, JL_ERR_INVALID, "silu_mul: bad arguments");
+    if (!gate || !up || rows < 0 || length < 0 || offset < 0 || (int64_t)offset + length > ld)
+        return jl_set_error(ctx, JL_ERR_INVALID, "silu_mul: bad arguments");
+    if (rows == 0 || length == 0) return JL_OK;
     const size_t b = (size_t)rows * ld * 4;
     float *dg = (float *)jl_scratch(ctx, 0, b), *du = (float *)jl_scratch(ctx, 1, b);
     if (!dg || !du) return JL_ERR_OOM;
