@@ -16,8 +16,9 @@
  *    aborts the process (the reference GPU natives call exit(),
  *    vector_gpu.c:96,116 -- deliberately not reproduced).
  *  - there is no CPU fallback: with no usable sm_100 device jl_init fails.
- *  - thread-safe: calls on one jl_ctx are serialised internally; model calls
- *    run on the model's own stream.
+ *  - thread-safe: calls on one jl_ctx are serialised internally; the entry points
+ *    of one jl_model serialise on the model's own lock and run on its own stream
+ *    (request threads may call jl_model_generate concurrently, one session each).
  *  - dtype codes: Jlama DType (core/safetensors/DType.java) subset.
  */
 #ifndef JLAMA_B200_H
@@ -282,6 +283,14 @@ int jl_model_read_kv(jl_model *m, int session, int layer, int position, int whic
  * Return the number of pages written / read (>= 0) or a JL_ERR_*.  After a load the caller continues at the position it saved. */
 int jl_model_kv_save(jl_model *m, int session, const char *dir, const char *session_name);
 int jl_model_kv_load(jl_model *m, int session, const char *dir, const char *session_name);
+/* Host spill of an idle session (SURVEY 8f.3 "device page pool, host spill/restore"): offload copies the allocated KV pages of `session`
+ * to host memory, frees their HBM and leaves the slot empty; returns a handle (> 0) or a negative JL_ERR_*.  restore zeroes `session`
+ * (any slot), brings the pages of `handle` back and forgets the handle; the caller continues at the position it stopped at.  discard
+ * drops a handle that will not be restored.  kv_pages = allocated pages of a session. */
+int64_t jl_model_kv_offload(jl_model *m, int session);
+int jl_model_kv_restore(jl_model *m, int session, int64_t handle);
+int jl_model_kv_discard(jl_model *m, int64_t handle);
+int jl_model_kv_pages(jl_model *m, int session);
 int jl_model_read_hidden(jl_model *m, int session, float *out /* [embedding_length] last row */);
 /* test hook: copy `n` floats of an internal activation buffer of the LAST forward/decode call to HOST (row 0 first).
  * which: 0 = x (hidden after the last layer), 1 = xb (after attention + residual), 2 = q, 3 = k, 4 = v (raw projections),
@@ -336,7 +345,9 @@ int jl_model_tp_layout(jl_model *m, jl_dctx *out, int *tp_size);
  * KvBuffer (core/tensor/KvBufferCache.java:58-60; jlama-net/.../openai/OpenAIChatService.java:64-74,107-160).  Here requests queue in
  * front of the batched decode step: every jl_sched_step admits queued requests into free session slots (FIFO), forwards prompt chunks,
  * runs ONE decode step for all generating requests (rows of different lengths side by side, at most the model's rows-per-call per
- * backend call) and retires finished requests so that their slots are reused by the next step.  Greedy (temperature 0) like
+ * backend call) and retires finished requests so that their slots are reused by the next step.  When no slot is free, the least
+ * recently finished kept session is spilled to host memory (KvBufferCache's pages are file-backed in the reference, :121-176; here the
+ * idle session's pages leave HBM) and restored into any free slot when its follow-up arrives.  Greedy (temperature 0) like
  * jl_model_decode.  Under tensor parallelism every rank runs the same scheduler on the same request stream (it is deterministic).
  * Free the scheduler before its model. */
 typedef struct jl_sched jl_sched;
@@ -362,13 +373,19 @@ typedef struct {
     int (*sample)(void *user, int session, int32_t *token_out);                                       /* jl_model_sample, temperature 0 */
     int (*decode)(void *user, int n, const int32_t *sessions, const int32_t *tokens, const int32_t *positions,
                   int32_t *next_tokens);                                                              /* jl_model_decode */
+    /* optional, all three or none: host spill of kept sessions (jl_model_kv_offload / kv_restore / kv_discard) */
+    int (*offload)(void *user, int session, int64_t *handle_out);
+    int (*restore)(void *user, int session, int64_t handle);
+    int (*discard)(void *user, int64_t handle);
 } jl_sched_backend;
 typedef struct {
     int admitted, prefill_tokens, decode_rows, decode_calls, finished; /* what this step (or run) did */
     int active, queued;                                                 /* afterwards */
+    int spilled;                                                        /* kept sessions moved to host memory to free their slot */
 } jl_sched_stats;
 typedef struct {
-    int state, finish_reason, session, start_pos, n_prompt, n_prefilled, n_generated, next_position;
+    int state, finish_reason, session /* -1: none, or spilled */, start_pos, n_prompt, n_prefilled, n_generated, next_position;
+    int spilled; /* 1: this finished request's kept KV lives in host memory; its continuation restores it into a free slot */
     int64_t submit_step, first_token_step, finish_step; /* scheduler step counters: queueing delay and time to first token in steps */
 } jl_sched_request_info_t;
 /* max_active: session slots to use (<= the model's max_sessions; 0 = all).  prefill_tokens_per_step: prompt tokens forwarded per step over

@@ -12,6 +12,7 @@
 #include <chrono>
 #include <map>
 #include <math.h>
+#include <new>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -88,6 +89,13 @@ struct jl_model {
     int pd_vocab0 = 0, pd_vocab_rows = 0;
     // tensor-parallel exchange buffers: local allocations + every rank's copy opened through CUDA IPC
     uint4 *ll_o = nullptr, *ll_d = nullptr, *ll_a = nullptr;
+    // sessions spilled to host memory (jl_model_kv_offload): handle -> (layer page, context page, page bytes) per allocated page
+    struct KvSpill {
+        std::vector<std::pair<int, int>> pages;
+        std::vector<char> bytes;
+    };
+    std::map<int64_t, KvSpill> spills;
+    int64_t next_spill = 1;
     uint4 *peer_ll_o[PD_MAX_TP] = {}, *peer_ll_d[PD_MAX_TP] = {}, *peer_ll_a[PD_MAX_TP] = {};
     float *peer_logits[PD_MAX_TP] = {};
     std::vector<void *> ipc_opened;
@@ -1526,6 +1534,85 @@ extern "C" int jl_model_kv_load(jl_model *m, int session, const char *dir, const
             n++;
         }
     return n;
+}
+
+// ---- host spill of an idle session -----------------------------------------------------------------------------------------------
+// The reference's pages are memory-mapped files, so an idle session costs no RAM (KvBufferCache.java:121-176).  Here an idle session
+// would pin HBM; offload moves its pages to host memory and returns the slot to the pool, restore brings them back into any slot.
+static int set_page(jl_model *m, size_t idx, void *p) {
+    jl_ctx *ctx = m->ctx;
+    m->page_table_host[idx] = p;
+    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(&m->page_table_dev[idx], &m->page_table_host[idx], sizeof(void *), cudaMemcpyHostToDevice, m->stream));
+    JL_CUDA_CHECK(ctx, cudaStreamSynchronize(m->stream)); // the staged pointer must outlive the copy
+    return JL_OK;
+}
+
+extern "C" int jl_model_kv_pages(jl_model *m, int session) {
+    if (!m || !m->finalized || session < 0 || session >= m->cfg.max_sessions) return JL_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> model_lock(m->mu);
+    const size_t per = (size_t)m->kv.n_layer_pages * m->kv.n_ctx_pages;
+    int n = 0;
+    for (size_t i = 0; i < per; i++) n += m->page_table_host[(size_t)session * per + i] != nullptr;
+    return n;
+}
+
+extern "C" int64_t jl_model_kv_offload(jl_model *m, int session) {
+    if (!m || !m->finalized || session < 0 || session >= m->cfg.max_sessions) return JL_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> model_lock(m->mu);
+    jl_ctx *ctx = m->ctx;
+    JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    JL_CUDA_CHECK(ctx, cudaStreamSynchronize(m->stream));
+    jl_model::KvSpill sp;
+    for (int lp = 0; lp < m->kv.n_layer_pages; lp++)
+        for (int cp = 0; cp < m->kv.n_ctx_pages; cp++)
+            if (m->page_table_host[((size_t)session * m->kv.n_layer_pages + lp) * m->kv.n_ctx_pages + cp]) sp.pages.emplace_back(lp, cp);
+    try {
+        sp.bytes.resize(sp.pages.size() * m->page_bytes);
+    } catch (const std::bad_alloc &) {
+        return jl_set_error(ctx, JL_ERR_OOM, "kv_offload: out of host memory for %zu pages", sp.pages.size());
+    }
+    // copy everything first, free afterwards: a failure leaves the session as it was
+    for (size_t i = 0; i < sp.pages.size(); i++) {
+        const size_t idx = ((size_t)session * m->kv.n_layer_pages + sp.pages[i].first) * m->kv.n_ctx_pages + sp.pages[i].second;
+        JL_CUDA_CHECK(ctx, cudaMemcpy(sp.bytes.data() + i * m->page_bytes, m->page_table_host[idx], m->page_bytes, cudaMemcpyDeviceToHost));
+    }
+    for (size_t i = 0; i < sp.pages.size(); i++) {
+        const size_t idx = ((size_t)session * m->kv.n_layer_pages + sp.pages[i].first) * m->kv.n_ctx_pages + sp.pages[i].second;
+        void *page = m->page_table_host[idx];
+        M_CHECK(set_page(m, idx, nullptr));
+        cudaFree(page);
+    }
+    const int64_t h = m->next_spill++;
+    m->spills.emplace(h, std::move(sp));
+    return h;
+}
+
+extern "C" int jl_model_kv_restore(jl_model *m, int session, int64_t handle) {
+    if (!m || !m->finalized || session < 0 || session >= m->cfg.max_sessions) return JL_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> model_lock(m->mu);
+    jl_ctx *ctx = m->ctx;
+    auto it = m->spills.find(handle);
+    if (it == m->spills.end()) return jl_set_error(ctx, JL_ERR_INVALID, "kv_restore: unknown spill handle %lld", (long long)handle);
+    JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    M_CHECK(jl_model_reset_session(m, session)); // pages the slot still holds from its previous user start from zero
+    const jl_model::KvSpill &sp = it->second;
+    for (size_t i = 0; i < sp.pages.size(); i++) {
+        const size_t idx = ((size_t)session * m->kv.n_layer_pages + sp.pages[i].first) * m->kv.n_ctx_pages + sp.pages[i].second;
+        if (!m->page_table_host[idx]) {
+            void *p = nullptr;
+            M_CHECK(dev_alloc(ctx, &p, m->page_bytes));
+            M_CHECK(set_page(m, idx, p));
+        }
+        JL_CUDA_CHECK(ctx, cudaMemcpy(m->page_table_host[idx], sp.bytes.data() + i * m->page_bytes, m->page_bytes, cudaMemcpyHostToDevice));
+    }
+    m->spills.erase(it);
+    return JL_OK;
+}
+
+extern "C" int jl_model_kv_discard(jl_model *m, int64_t handle) {
+    if (!m) return JL_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> model_lock(m->mu);
+    return m->spills.erase(handle) ? JL_OK : jl_set_error(m->ctx, JL_ERR_INVALID, "kv_discard: unknown spill handle %lld", (long long)handle);
 }
 
 extern "C" int jl_model_read_kv(jl_model *m, int session, int layer, int position, int which, float *out) {

@@ -16,6 +16,9 @@
 // The scheduler is pure host logic above four backend calls (reset_session / batch_forward / sample / decode).  jl_sched_create
 // binds them to a jl_model; jl_sched_create_backend takes them as function pointers, which is how the CPU tests drive the very same
 // policy code with the oracle as the "device" (tests/test_scheduler.py) and how a host that owns its own model object would plug in.
+// Kept sessions and host spill: a finished JL_SCHED_KEEP_SESSION request holds its slot and KV for a follow-up turn.  When a request
+// finds no free slot and the backend can offload (jl_model_kv_offload), the least recently finished kept session is moved to host
+// memory and its slot is reused; its continuation later restores the pages into whatever slot is free (jl_model_kv_restore).
 // Locking: `step_mu` serialises steps; `mu` guards the request table and is NOT held across backend calls, so submit / result /
 // cancel from other threads never wait for GPU work.
 #include <deque>
@@ -47,9 +50,10 @@ struct Request {
     int prefilled = 0;  // prompt tokens already forwarded
     int forwarded = 0;  // generated tokens already fed back through a decode step
     bool cancel = false;
-    bool need_reset = false; // fresh session: zero its pages before the first prompt chunk
     int64_t parent = -1;     // finished request whose kept session (and KV) this request continues
     int64_t child = -1;      // pending / admitted continuation of this request
+    bool spilling = false;   // chosen as the victim of this step's offload; `spill` is set when the backend call returns
+    int64_t spill = -1;      // backend handle of this finished request's KV after it was offloaded to host memory (session == -1 then)
     std::vector<int32_t> out;
     uint64_t submit_step = 0, first_token_step = 0, finish_step = 0;
     int next_pos() const { return start_pos + (int)prompt.size() + forwarded; } // position the next decode step writes
@@ -70,6 +74,7 @@ struct jl_sched {
     uint64_t step_no = 0;
     std::string last_error;
     jl_sched_stats totals = {};
+    std::vector<int64_t> discards; // spill handles of released requests, dropped by the next step (backend calls never run under `mu`)
 };
 
 static int sched_error(jl_sched *s, int code, const char *fmt, ...) {
@@ -92,11 +97,22 @@ static int mb_decode(void *u, int n, const int32_t *sessions, const int32_t *tok
     return jl_model_decode((jl_model *)u, n, sessions, tokens, positions, next, nullptr);
 }
 
+static int mb_offload(void *u, int session, int64_t *handle) {
+    const int64_t h = jl_model_kv_offload((jl_model *)u, session);
+    if (h < 0) return (int)h;
+    *handle = h;
+    return JL_OK;
+}
+static int mb_restore(void *u, int session, int64_t handle) { return jl_model_kv_restore((jl_model *)u, session, handle); }
+static int mb_discard(void *u, int64_t handle) { return jl_model_kv_discard((jl_model *)u, handle); }
+
 extern "C" int jl_sched_create_backend(const jl_sched_backend *be, void *user, int n_sessions, int max_rows, int max_context,
                                        int prefill_tokens_per_step, jl_sched **out) {
     if (!be || !out || !be->reset_session || !be->batch_forward || !be->sample || !be->decode || n_sessions <= 0 || max_rows <= 0 ||
         max_context <= 1)
         return JL_ERR_INVALID;
+    if ((be->offload != nullptr) != (be->restore != nullptr) || (be->offload != nullptr) != (be->discard != nullptr))
+        return JL_ERR_INVALID; // host spill is all three calls or none
     jl_sched *s = new jl_sched();
     s->be = *be;
     s->user = user;
@@ -115,7 +131,7 @@ extern "C" int jl_sched_create(jl_model *m, int max_active, int prefill_tokens_p
     jl_model_limits(m, lim);
     if (lim[0] <= 0) return JL_ERR_INVALID; // not finalized
     const int n = max_active > 0 && max_active < lim[0] ? max_active : lim[0];
-    static const jl_sched_backend be = {mb_reset, mb_forward, mb_sample, mb_decode};
+    static const jl_sched_backend be = {mb_reset, mb_forward, mb_sample, mb_decode, mb_offload, mb_restore, mb_discard};
     return jl_sched_create_backend(&be, m, n, lim[3], lim[1], prefill_tokens_per_step, out);
 }
 
@@ -141,11 +157,10 @@ extern "C" int64_t jl_sched_submit(jl_sched *s, const int32_t *prompt, int n_pro
         // AbstractModel.generate :533 startPos = kvmem.getCurrentContextPosition(): a follow-up on the same session appends to its KV
         auto it = s->reqs.find(continue_request);
         if (it == s->reqs.end() || it->second.state != JL_SCHED_FINISHED || !(it->second.flags & JL_SCHED_KEEP_SESSION) ||
-            it->second.session < 0)
+            (it->second.session < 0 && it->second.spill < 0 && !it->second.spilling))
             return sched_error(s, -1, "submit: request %lld is not a finished request that kept its session", (long long)continue_request);
         if (it->second.child >= 0)
             return sched_error(s, -1, "submit: request %lld already has a continuation", (long long)continue_request);
-        r.session = it->second.session;
         r.start_pos = it->second.next_pos();
         r.parent = continue_request;
     }
@@ -200,6 +215,7 @@ extern "C" int jl_sched_request_info(jl_sched *s, int64_t request, jl_sched_requ
     info->state = r.state, info->finish_reason = r.reason, info->session = r.session, info->start_pos = r.start_pos;
     info->n_prompt = (int)r.prompt.size(), info->n_prefilled = r.prefilled, info->n_generated = (int)r.out.size();
     info->next_position = r.next_pos();
+    info->spilled = r.spill >= 0 ? 1 : 0;
     info->submit_step = (int64_t)r.submit_step, info->first_token_step = (int64_t)r.first_token_step;
     info->finish_step = (int64_t)r.finish_step;
     return JL_OK;
@@ -225,6 +241,7 @@ extern "C" int jl_sched_release(jl_sched *s, int64_t request) {
         if (pa != s->reqs.end()) pa->second.child = -1;
     }
     if (r.session >= 0 && s->slot_owner[(size_t)r.session] == request) s->slot_owner[(size_t)r.session] = -1;
+    if (r.spill >= 0) s->discards.push_back(r.spill);
     s->reqs.erase(it);
     return JL_OK;
 }
@@ -272,10 +289,16 @@ static void check_done(jl_sched *s, Request &r, bool stop_check) {
 }
 
 namespace {
+struct SlotJob { // what has to happen to a session slot before its new owner's first prompt chunk
+    int64_t victim = -1; // kept request whose KV is offloaded out of the slot first
+    int64_t restore_from = -1; // request whose spilled KV is restored into the slot (continuation of a spilled session)
+    bool reset = false;        // fresh request: zero the slot
+};
 struct PrefillJob {
     int64_t id;
     int session, start, n, pos;
-    bool reset, last;
+    bool last;
+    SlotJob slot;
     std::vector<int32_t> tokens;
 };
 struct Row {
@@ -284,86 +307,139 @@ struct Row {
 };
 } // namespace
 
+// must hold s->mu.  A slot for a request that needs one: a free slot, else (backend permitting) the slot of the kept session that
+// finished longest ago -- sessions whose follow-up is already queued go last.  *victim = the request to offload, or -1.
+static int take_slot(jl_sched *s, int64_t *victim) {
+    *victim = -1;
+    for (int k = 0; k < s->n_sessions; k++)
+        if (s->slot_owner[(size_t)k] < 0) return k;
+    if (!s->be.offload) return -1;
+    int best = -1;
+    for (int k = 0; k < s->n_sessions; k++) {
+        auto it = s->reqs.find(s->slot_owner[(size_t)k]);
+        if (it == s->reqs.end() || it->second.state != JL_SCHED_FINISHED || it->second.session != k) continue; // running, not kept
+        if (best < 0) {
+            best = k;
+            continue;
+        }
+        const Request &a = it->second, &b = s->reqs[s->slot_owner[(size_t)best]];
+        const bool a_waits = a.child >= 0, b_waits = b.child >= 0;
+        if (a_waits != b_waits ? !a_waits : a.finish_step < b.finish_step) best = k;
+    }
+    if (best >= 0) *victim = s->slot_owner[(size_t)best];
+    return best;
+}
+
 extern "C" int jl_sched_step(jl_sched *s, jl_sched_stats *stats) {
     if (!s) return JL_ERR_INVALID;
     std::lock_guard<std::mutex> step_lock(s->step_mu);
     jl_sched_stats st = {};
     int first_error = JL_OK;
     std::vector<PrefillJob> jobs;
+    std::unordered_map<int64_t, SlotJob> slot_jobs; // admitted this step: request id -> slot preparation
+    std::vector<int64_t> discards;
 
     // ---- plan: cancellations, admissions, prompt chunks ----------------------------------------------------------------------
     {
         std::lock_guard<std::mutex> lk(s->mu);
         s->step_no++;
+        discards.swap(s->discards);
         for (size_t i = 0; i < s->active.size();) {
             Request &r = s->reqs[s->active[i]];
             if (r.cancel) finish(s, r, JL_SCHED_FINISHED, JL_FINISH_CANCELLED), st.finished++;
             else i++;
         }
-        // FIFO admission into free session slots.  A continuation returns to the slot its parent kept, so it is admitted even when
-        // every other slot is busy; fresh requests keep their order (the first one that finds no slot blocks the fresh ones behind it).
+        // FIFO admission.  A continuation whose parent still sits in its slot returns to that slot (always possible); every other
+        // request needs a slot from take_slot, and the first one that finds none blocks the slot-seeking requests behind it.
         bool blocked = false;
         for (size_t qi = 0; qi < s->queue.size();) {
             Request &r = s->reqs[s->queue[qi]];
+            auto pa = r.parent >= 0 ? s->reqs.find(r.parent) : s->reqs.end();
             if (r.cancel) {
-                if (r.parent >= 0) {
-                    auto pa = s->reqs.find(r.parent);
-                    if (pa != s->reqs.end()) pa->second.child = -1; // the parent still holds the session and may be continued again
-                    r.session = -1;
-                }
+                if (pa != s->reqs.end()) pa->second.child = -1; // the parent still holds the KV and may be continued again
                 finish(s, r, JL_SCHED_FINISHED, JL_FINISH_CANCELLED), st.finished++;
                 s->queue.erase(s->queue.begin() + (long)qi);
                 continue;
             }
-            if (r.parent >= 0) {
-                s->slot_owner[(size_t)r.session] = r.id; // the parent's slot with its KV; ownership moves to the continuation
-                auto pa = s->reqs.find(r.parent);
-                if (pa != s->reqs.end()) pa->second.session = -1;
+            SlotJob sj;
+            if (pa != s->reqs.end() && pa->second.session >= 0) {
+                r.session = pa->second.session; // the parent's slot with its KV; ownership moves to the continuation
+                pa->second.session = -1;
             } else {
-                int slot = -1;
-                if (!blocked)
-                    for (int k = 0; k < s->n_sessions; k++)
-                        if (s->slot_owner[(size_t)k] < 0) {
-                            slot = k;
-                            break;
-                        }
+                int64_t victim = -1;
+                const int slot = blocked ? -1 : take_slot(s, &victim);
                 if (slot < 0) {
                     blocked = true;
                     qi++;
                     continue;
                 }
-                s->slot_owner[(size_t)slot] = r.id;
+                if (victim >= 0) {
+                    Request &v = s->reqs[victim];
+                    v.session = -1; // its KV leaves the device in this step (spill handle set when the offload returns)
+                    v.spilling = true;
+                    sj.victim = victim;
+                    st.spilled++;
+                }
                 r.session = slot;
-                r.need_reset = true;
+                if (pa != s->reqs.end()) sj.restore_from = r.parent; // continuation of a spilled session
+                else sj.reset = true;
             }
+            s->slot_owner[(size_t)r.session] = r.id;
             r.state = JL_SCHED_PREFILL;
             s->active.push_back(r.id);
             s->queue.erase(s->queue.begin() + (long)qi);
+            slot_jobs[r.id] = sj;
             st.admitted++;
         }
         int budget = s->prefill_budget > 0 ? s->prefill_budget : 0x7fffffff;
         for (int64_t id : s->active) {
             Request &r = s->reqs[id];
-            if (r.state != JL_SCHED_PREFILL || budget <= 0) continue;
+            if (r.state != JL_SCHED_PREFILL) continue;
+            auto sj = slot_jobs.find(id);
+            if (budget <= 0 && sj == slot_jobs.end()) continue;
             const int left = (int)r.prompt.size() - r.prefilled;
-            const int n = left < budget ? left : budget;
+            const int n = left < budget ? left : (budget > 0 ? budget : 0);
             PrefillJob j;
             j.id = id, j.session = r.session, j.start = r.prefilled, j.n = n, j.pos = r.start_pos + r.prefilled;
-            j.reset = r.need_reset;
-            r.need_reset = false;
-            j.last = r.prefilled + n == (int)r.prompt.size();
+            if (sj != slot_jobs.end()) j.slot = sj->second; // the slot is prepared in the admission step even if the budget is spent
+            j.last = n > 0 && r.prefilled + n == (int)r.prompt.size();
             j.tokens.assign(r.prompt.begin() + r.prefilled, r.prompt.begin() + r.prefilled + n);
             jobs.push_back(std::move(j));
             budget -= n;
         }
     }
 
-    // ---- prompt chunks (backend calls, table unlocked) ---------------------------------------------------------------------------
+    // ---- backend calls, table unlocked: dropped spills, slot preparation, prompt chunks ---------------------------------------------
+    for (int64_t h : discards) s->be.discard(s->user, h);
     for (PrefillJob &j : jobs) {
         int rc = JL_OK;
         int32_t tok = 0;
-        if (j.reset) rc = s->be.reset_session(s->user, j.session);
-        if (rc == JL_OK) rc = s->be.batch_forward(s->user, j.session, j.tokens.data(), j.n, j.pos);
+        if (j.slot.victim >= 0) {
+            int64_t handle = -1;
+            const int orc = s->be.offload(s->user, j.session, &handle);
+            std::lock_guard<std::mutex> lk(s->mu);
+            auto v = s->reqs.find(j.slot.victim);
+            if (v != s->reqs.end()) v->second.spilling = false;
+            if (orc == JL_OK && v != s->reqs.end()) v->second.spill = handle;
+            else if (orc == JL_OK) s->discards.push_back(handle); // released meanwhile
+            else {
+                // the KV of the kept session could not be saved: it can no longer be continued; the slot is reused regardless
+                if (v != s->reqs.end()) v->second.flags &= ~JL_SCHED_KEEP_SESSION;
+                if (first_error == JL_OK) first_error = sched_error(s, orc, "offload of kept request %lld failed (%d): its session is dropped", (long long)j.slot.victim, orc);
+            }
+        }
+        if (j.slot.restore_from >= 0) {
+            int64_t handle = -1;
+            {
+                std::lock_guard<std::mutex> lk(s->mu);
+                auto pa = s->reqs.find(j.slot.restore_from);
+                if (pa != s->reqs.end()) handle = pa->second.spill, pa->second.spill = -1;
+            }
+            rc = handle >= 0 ? s->be.restore(s->user, j.session, handle) : JL_ERR_INVALID;
+        } else if (j.slot.reset) {
+            rc = s->be.reset_session(s->user, j.session);
+        }
+        if (rc == JL_OK && j.n > 0) rc = s->be.batch_forward(s->user, j.session, j.tokens.data(), j.n, j.pos);
         if (rc == JL_OK && j.last) rc = s->be.sample(s->user, j.session, &tok);
         std::lock_guard<std::mutex> lk(s->mu);
         Request &r = s->reqs[j.id];
@@ -420,7 +496,7 @@ extern "C" int jl_sched_step(jl_sched *s, jl_sched_stats *stats) {
         st.active = (int)s->active.size();
         st.queued = (int)s->queue.size();
         s->totals.admitted += st.admitted, s->totals.prefill_tokens += st.prefill_tokens, s->totals.decode_rows += st.decode_rows;
-        s->totals.decode_calls += st.decode_calls, s->totals.finished += st.finished;
+        s->totals.decode_calls += st.decode_calls, s->totals.finished += st.finished, s->totals.spilled += st.spilled;
         s->totals.active = st.active, s->totals.queued = st.queued;
     }
     if (stats) *stats = st;
@@ -436,7 +512,7 @@ extern "C" int jl_sched_run(jl_sched *s, int max_steps, jl_sched_stats *totals) 
         const int rc = jl_sched_step(s, &st);
         if (rc != JL_OK && rc_all == JL_OK) rc_all = rc;
         sum.admitted += st.admitted, sum.prefill_tokens += st.prefill_tokens, sum.decode_rows += st.decode_rows;
-        sum.decode_calls += st.decode_calls, sum.finished += st.finished, sum.active = st.active, sum.queued = st.queued;
+        sum.decode_calls += st.decode_calls, sum.finished += st.finished, sum.spilled += st.spilled, sum.active = st.active, sum.queued = st.queued;
         if (st.active == 0 && st.queued == 0) break;
         // nothing admitted, forwarded or decoded although work is queued: every slot is held by a kept session
         if (st.admitted == 0 && st.prefill_tokens == 0 && st.decode_rows == 0 && st.finished == 0) {

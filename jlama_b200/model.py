@@ -228,6 +228,22 @@ class LlamaModel:
             self.ctx.check(n)
         return n
 
+    def kv_offload(self, session=0):
+        """Move the session's KV pages to host memory and free their HBM; returns the handle kv_restore takes."""
+        h = self.lib.jl_model_kv_offload(self.h, session)
+        if h < 0:
+            self.ctx.check(int(h))
+        return h
+
+    def kv_restore(self, handle, session=0):
+        self.ctx.check(self.lib.jl_model_kv_restore(self.h, session, handle))
+
+    def kv_discard(self, handle):
+        self.ctx.check(self.lib.jl_model_kv_discard(self.h, handle))
+
+    def kv_pages(self, session=0):
+        return int(self.lib.jl_model_kv_pages(self.h, session))
+
     def read_kv(self, layer, position, which, session=0):
         out = np.empty(self.dctx.kvSegmentLength, dtype=np.float32)
         self.ctx.check(self.lib.jl_model_read_kv(self.h, session, layer, position, which, ptr(out)))

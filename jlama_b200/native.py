@@ -47,12 +47,13 @@ class Dctx(C.Structure):
 
 
 class SchedStats(C.Structure):
-    _fields_ = [(n, C.c_int) for n in ("admitted", "prefill_tokens", "decode_rows", "decode_calls", "finished", "active", "queued")]
+    _fields_ = [(n, C.c_int) for n in ("admitted", "prefill_tokens", "decode_rows", "decode_calls", "finished", "active", "queued",
+                                        "spilled")]
 
 
 class SchedRequestInfo(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("state", "finish_reason", "session", "start_pos", "n_prompt", "n_prefilled", "n_generated",
-                                        "next_position")] + [(n, C.c_int64) for n in ("submit_step", "first_token_step", "finish_step")]
+                                        "next_position", "spilled")] + [(n, C.c_int64) for n in ("submit_step", "first_token_step", "finish_step")]
 
 
 # jl_sched_backend: the four model calls the scheduler policy is written against
@@ -63,9 +64,14 @@ SCHED_DECODE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int32)
                               C.POINTER(C.c_int32))
 
 
+SCHED_OFFLOAD_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int64))
+SCHED_RESTORE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int64)
+SCHED_DISCARD_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64)
+
+
 class SchedBackend(C.Structure):
     _fields_ = [("reset_session", SCHED_RESET_FN), ("batch_forward", SCHED_FORWARD_FN), ("sample", SCHED_SAMPLE_FN),
-                ("decode", SCHED_DECODE_FN)]
+                ("decode", SCHED_DECODE_FN), ("offload", SCHED_OFFLOAD_FN), ("restore", SCHED_RESTORE_FN), ("discard", SCHED_DISCARD_FN)]
 
 
 SCHED_QUEUED, SCHED_PREFILL, SCHED_DECODING, SCHED_FINISHED, SCHED_FAILED = range(5)
@@ -139,6 +145,10 @@ SIGNATURES = {
     "jl_model_read_kv": (_i, [_vp, _i, _i, _i, _i, _vp]),
     "jl_model_kv_save": (_i, [_vp, _i, C.c_char_p, C.c_char_p]),
     "jl_model_kv_load": (_i, [_vp, _i, C.c_char_p, C.c_char_p]),
+    "jl_model_kv_offload": (_i64, [_vp, _i]),
+    "jl_model_kv_restore": (_i, [_vp, _i, _i64]),
+    "jl_model_kv_discard": (_i, [_vp, _i64]),
+    "jl_model_kv_pages": (_i, [_vp, _i]),
     "jl_model_read_hidden": (_i, [_vp, _i, _vp]),
     "jl_model_debug_read": (_i, [_vp, _i, _vp, _i64]),
     "jl_model_decode_mode": (_i, [_vp, _i]),

@@ -32,10 +32,12 @@ class SessionScheduler:
         self.h = h
 
     @classmethod
-    def over_backend(cls, reset_session, batch_forward, sample, decode, n_sessions, max_rows, max_context, prefill_tokens_per_step=0):
+    def over_backend(cls, reset_session, batch_forward, sample, decode, n_sessions, max_rows, max_context, prefill_tokens_per_step=0,
+                     offload=None, restore=None, discard=None):
         """reset_session(session); batch_forward(session, tokens: np.int32[n], start_pos); sample(session) -> token;
-        decode(sessions, tokens, positions: np.int32[n]) -> next tokens.  A raised exception fails the affected requests
-        (JL_ERR_INVALID), exactly like a backend error code."""
+        decode(sessions, tokens, positions: np.int32[n]) -> next tokens; optionally the host-spill trio offload(session) -> handle,
+        restore(session, handle), discard(handle).  A raised exception fails the affected requests (JL_ERR_INVALID), exactly like a
+        backend error code."""
         self = cls.__new__(cls)
         self.lib = native.load()
         self._model = None
@@ -73,8 +75,25 @@ class SessionScheduler:
                 nxt[i] = int(res[i])
             return native.JL_OK
 
+        @guard
+        def _offload(_u, session, handle_out):
+            handle_out[0] = int(offload(session))
+            return native.JL_OK
+
+        @guard
+        def _restore(_u, session, handle):
+            restore(session, handle)
+            return native.JL_OK
+
+        @guard
+        def _discard(_u, handle):
+            discard(handle)
+            return native.JL_OK
+
         be = native.SchedBackend(native.SCHED_RESET_FN(_reset), native.SCHED_FORWARD_FN(_forward), native.SCHED_SAMPLE_FN(_sample),
                                  native.SCHED_DECODE_FN(_decode))
+        if offload is not None:
+            be.offload, be.restore, be.discard = native.SCHED_OFFLOAD_FN(_offload), native.SCHED_RESTORE_FN(_restore), native.SCHED_DISCARD_FN(_discard)
         self._keep = be  # the C side copies the struct, the CFUNCTYPE objects must outlive it
         h = C.c_void_p()
         rc = self.lib.jl_sched_create_backend(C.byref(be), None, n_sessions, max_rows, max_context, prefill_tokens_per_step, C.byref(h))

@@ -141,3 +141,68 @@ def test_decode_rejects_a_session_twice_in_one_step(cuda_ctx):
     with pytest.raises(native.JlamaNativeError):
         gm.decode([1, 2], [4, 4], sessions=[0, 0])
     gm.close()
+
+
+def test_kv_offload_frees_the_slot_and_restore_resumes_in_another_one(cuda_ctx, oracle):
+    """Host spill: the pages of an idle session leave HBM, the slot serves another request, and the session resumes token
+    for token after its pages come back into a different slot."""
+    from jlama_b200 import native, synth
+    from jlama_b200.model import LlamaModel
+    cfg = synth.get_config("small")
+    w = synth.make_weights(cfg)
+    gm = LlamaModel(cuda_ctx, cfg, w, max_sessions=2)
+    om = oracle.OracleLlama(cfg, w, act_q8=True)
+    prompt = synth.random_prompt(cfg, 23)
+    gm.reset_session(0)
+    gm.batch_forward(prompt, 0, session=0)
+    toks = [gm.sample(session=0, want_logits=False)[0]]
+    for i in range(4):
+        toks.append(int(gm.decode([toks[-1]], [len(prompt) + i], sessions=[0])[0][0]))
+    pages = gm.kv_pages(0)
+    assert pages >= 1
+    k_before = gm.read_kv(1, 5, 0, session=0)
+    h = gm.kv_offload(0)
+    assert h > 0 and gm.kv_pages(0) == 0
+    with pytest.raises(native.JlamaNativeError):
+        gm.read_kv(1, 5, 0, session=0)  # the page is gone from the device
+    # the emptied slot serves somebody else in the meantime
+    other = synth.random_prompt(cfg, 9, seed=77)
+    got_other = gm.generate(other, 6, session=0)[0]
+    gm.kv_restore(h, session=1)
+    assert gm.kv_pages(1) == pages and np.array_equal(gm.read_kv(1, 5, 0, session=1), k_before)
+    with pytest.raises(native.JlamaNativeError):
+        gm.kv_restore(h, session=1)  # a handle restores once
+    for i in range(4, 9):
+        toks.append(int(gm.decode([toks[-1]], [len(prompt) + i], sessions=[1])[0][0]))
+    _check_against_oracle(om, [(prompt, 10, np.array(toks)), (other, 6, got_other)])
+    h2 = gm.kv_offload(1)
+    gm.kv_discard(h2)
+    with pytest.raises(native.JlamaNativeError):
+        gm.kv_discard(h2)
+    gm.close()
+    om.close()
+
+
+def test_scheduler_spills_an_idle_kept_session_and_restores_it_for_its_follow_up(cuda_ctx, oracle):
+    from jlama_b200 import synth
+    from jlama_b200.model import LlamaModel
+    from jlama_b200.scheduler import SessionScheduler
+    cfg = synth.get_config("small")
+    w = synth.make_weights(cfg)
+    gm = LlamaModel(cuda_ctx, cfg, w, max_sessions=1)
+    om = oracle.OracleLlama(cfg, w, act_q8=True)
+    p1, p2, p3 = (synth.random_prompt(cfg, n, seed=s) for n, s in ((12, 81), (7, 82), (4, 83)))
+    with SessionScheduler(gm) as sched:
+        a = sched.submit(p1, 6, keep_session=True)
+        sched.run()
+        b = sched.submit(p2, 5)  # the only slot is held by a's idle session: a goes to host memory
+        st = sched.run()
+        assert st.spilled == 1 and sched.info(a).spilled == 1
+        a2 = sched.submit(p3, 5, continue_request=a)
+        sched.run()
+        ta, tb, ta2 = sched.result(a)[0], sched.result(b)[0], sched.result(a2)[0]
+        assert sched.info(a2).start_pos == len(p1) + 5 and sched.info(a).spilled == 0
+    joined = np.concatenate([p1, ta[:5], p3]).astype(np.int32)
+    _check_against_oracle(om, [(p1, 6, ta), (p2, 5, tb), (joined, 5, ta2)])
+    gm.close()
+    om.close()

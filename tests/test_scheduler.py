@@ -43,7 +43,7 @@ class ToyBackend:
         self.max_rows = max_rows
         self.calls = []
         self.fail_session = fail_session
-        self.busy = set()
+        self.store, self.next_handle, self.fail_offload = {}, 100, False
 
     def reset_session(self, s):
         self.hist[s] = []
@@ -73,9 +73,30 @@ class ToyBackend:
         return out
 
 
-def _toy_sched(n_sessions=4, max_rows=3, max_context=4096, budget=0, **kw):
+    # host spill: the history (the KV analogue) leaves the slot and comes back through a handle
+    def offload(self, s):
+        if self.fail_offload:
+            raise RuntimeError("injected offload failure")
+        assert self.hist[s] is not None
+        self.next_handle += 1
+        self.store[self.next_handle] = self.hist[s]
+        self.hist[s] = None
+        self.calls.append(("offload", s, self.next_handle))
+        return self.next_handle
+
+    def restore(self, s, handle):
+        self.hist[s] = self.store.pop(handle)
+        self.calls.append(("restore", s, handle))
+
+    def discard(self, handle):
+        del self.store[handle]
+        self.calls.append(("discard", handle))
+
+
+def _toy_sched(n_sessions=4, max_rows=3, max_context=4096, budget=0, spill=False, **kw):
     be = ToyBackend(n_sessions, max_rows, **kw)
-    s = SessionScheduler.over_backend(be.reset_session, be.batch_forward, be.sample, be.decode, n_sessions, max_rows, max_context, budget)
+    extra = dict(offload=be.offload, restore=be.restore, discard=be.discard) if spill else {}
+    s = SessionScheduler.over_backend(be.reset_session, be.batch_forward, be.sample, be.decode, n_sessions, max_rows, max_context, budget, **extra)
     return be, s
 
 
@@ -247,6 +268,79 @@ def test_run_reports_a_queue_that_can_never_be_admitted():
     s.release(a)
     s.run()
     assert s.result(b)[0].tolist() == _toy_generate([3], 2)[0]
+    s.close()
+
+
+def test_kept_sessions_spill_to_host_when_slots_run_out_and_come_back_in_any_slot():
+    be, s = _toy_sched(n_sessions=2, max_rows=2, spill=True)
+    a = s.submit([1, 2, 3], 4, keep_session=True)
+    s.run()
+    b = s.submit([4, 5], 6, keep_session=True)
+    s.run()
+    assert s.counts() == (0, 0, 0) and s.info(a).session == 0 and s.info(b).session == 1
+    want_a, hist_a = _toy_generate([1, 2, 3], 4)
+    want_b, hist_b = _toy_generate([4, 5], 6)
+    # both slots are held by idle kept sessions; a fresh request takes the slot of the one that finished first
+    c = s.submit([7, 8, 9, 10], 5)
+    st = s.run()
+    assert st.spilled == 1 and ("offload", 0, 101) in be.calls
+    ia = s.info(a)
+    assert ia.spilled == 1 and ia.session == -1 and s.info(b).spilled == 0 and s.info(c).session == 0
+    assert s.result(c)[0].tolist() == _toy_generate([7, 8, 9, 10], 5)[0]
+    assert be.calls.index(("offload", 0, 101)) < be.calls.index(("reset", 0), 2)  # saved before the slot is zeroed for its new user
+    # a's follow-up turn: restored into the slot c left, at a's context position, history intact
+    a2 = s.submit([20, 21], 3, continue_request=a)
+    s.run()
+    assert ("restore", 0, 101) in be.calls and not be.store
+    assert s.result(a2)[0].tolist() == _toy_generate([20, 21], 3, start_hist=hist_a)[0]
+    assert s.info(a2).start_pos == len(hist_a) and s.info(a).spilled == 0
+    # b's follow-up goes back to b's own slot without any copy
+    n_calls = len(be.calls)
+    b2 = s.submit([30], 2, continue_request=b)
+    s.run()
+    assert s.result(b2)[0].tolist() == _toy_generate([30], 2, start_hist=hist_b)[0] and s.info(b2).session == 1
+    assert not any(c2[0] in ("offload", "restore", "reset") for c2 in be.calls[n_calls:])
+    assert s.result(a)[0].tolist() == want_a and s.result(b)[0].tolist() == want_b
+    s.close()
+
+
+def test_spill_prefers_sessions_without_a_queued_follow_up_and_release_discards_the_host_copy():
+    be, s = _toy_sched(n_sessions=2, max_rows=2, spill=True)
+    a = s.submit([1], 2, keep_session=True)
+    s.run()
+    b = s.submit([2], 2, keep_session=True)
+    s.run()
+    # a fresh request, then a's follow-up: a finished first, but its continuation is queued, so b is the one to go
+    fresh = [s.submit([5], 2)]
+    a2 = s.submit([9], 2, continue_request=a)
+    s.step()
+    assert s.info(b).spilled == 1 and s.info(a).spilled == 0 and s.info(a2).session == 0 and s.info(fresh[0]).session == 1
+    fresh += [s.submit([6], 2), s.submit([7], 2)]
+    s.run()
+    for i, f in enumerate(fresh):
+        assert s.result(f)[0].tolist() == _toy_generate([5 + i], 2)[0]
+    assert s.result(a2)[0].tolist() == _toy_generate([9], 2, start_hist=_toy_generate([1], 2)[1])[0]
+    # b is never continued: releasing it drops the host copy at the next step
+    assert len(be.store) == 1
+    s.release(b)
+    s.step()
+    assert not be.store and be.calls[-1][0] == "discard"
+    s.close()
+
+
+def test_a_failed_offload_drops_the_kept_session_but_not_the_new_request():
+    be, s = _toy_sched(n_sessions=1, max_rows=1, spill=True)
+    a = s.submit([1, 2], 3, keep_session=True)
+    s.run()
+    be.fail_offload = True
+    b = s.submit([3, 4], 3)
+    with pytest.raises(native.JlamaNativeError, match="offload"):
+        s.run()
+    s.run()
+    assert s.result(b)[0].tolist() == _toy_generate([3, 4], 3)[0]  # the slot was reused regardless
+    with pytest.raises(native.JlamaNativeError):
+        s.submit([5], 2, continue_request=a)  # a's KV is gone, it cannot be continued
+    assert s.info(a).spilled == 0 and s.info(a).session == -1
     s.close()
 
 
