@@ -65,10 +65,10 @@ public final class CudaSessionScheduler implements AutoCloseable {
         stepper.start();
     }
 
-    /** The serving loop: step while anything is queued or running, sleep otherwise.  jl_sched_stats = 7 ints. */
+    /** The serving loop: step while anything is queued or running, sleep otherwise.  jl_sched_stats = 8 ints ([5] active, [6] queued). */
     private void loop() {
         try (Arena a = Arena.ofConfined()) {
-            MemorySegment st = a.allocate(JAVA_INT, 7);
+            MemorySegment st = a.allocate(JAVA_INT, 8);
             while (running) {
                 int rc = (int) jl_sched_step.invokeExact(sched, st);   // a failing request is marked FAILED; the others go on
                 boolean idle = st.getAtIndex(JAVA_INT, 5) == 0 && st.getAtIndex(JAVA_INT, 6) == 0;
