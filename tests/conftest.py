@@ -14,8 +14,8 @@ def pytest_configure(config):
 
 
 def pytest_collection_modifyitems(config, items):
-    """GPU tests written after this round's GPU budget was spent have not run on a B200 yet.  They are marked `late` and ordered
-    behind everything else, so that under `-x` a surprise in one of them cannot hide the tests that are known to pass."""
+    """A GPU test that has not run on a B200 yet (written after a round's GPU budget was spent) can be marked `late`: it is ordered
+    behind everything else, so that under `-x` a surprise in it cannot hide the tests that are known to pass.  None is marked now."""
     late = [it for it in items if it.get_closest_marker("late")]
     if late:
         items[:] = [it for it in items if not it.get_closest_marker("late")] + late

@@ -60,7 +60,6 @@ def test_checkpoint_directory_loads_and_generates_like_in_memory_weights(cuda_ct
     b.close()
 
 
-@pytest.mark.late
 def test_mixtral_checkpoint_directory_loads_like_in_memory_weights(cuda_ctx, oracle, tmp_path):
     """MixtralModel.java:88-105 tensor names (block_sparse_moe.gate / experts.<e>.w1|w2|w3) and MixtralConfig's num_local_experts /
     num_experts_per_tok read behind the C ABI: same registrations as the in-memory path, so the generations are bit-identical."""

@@ -7,7 +7,7 @@ import threading
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu, pytest.mark.late]
+pytestmark = pytest.mark.gpu
 
 
 def _check_against_oracle(om, results, near_tie=1e-2):
