@@ -266,6 +266,14 @@ int jl_model_sample(jl_model *m, int session, float temperature, float uniform, 
  * tokens/positions/next_tokens are HOST int32[n]; logits_out HOST [n, vocab] or NULL. */
 int jl_model_decode(jl_model *m, int n, const int32_t *sessions, const int32_t *tokens, const int32_t *positions,
                     int32_t *next_tokens, float *logits_out);
+/* jl_model_decode with per-row sampling: a row whose temperature is not 0 draws its token with AbstractModel.sample's rule (:475-489:
+ * exp((l - max) / T) in double, float running sum against `uniform`) from its logits row; rows at temperature 0 keep the arg-max.
+ * temperatures / uniforms: HOST float[n].  logits_out receives the raw logits. */
+int jl_model_decode_sample(jl_model *m, int n, const int32_t *sessions, const int32_t *tokens, const int32_t *positions,
+                           const float *temperatures, const float *uniforms, int32_t *next_tokens, float *logits_out);
+/* generate() with a temperature: uniforms[i] (HOST float[n_new]) stands for the i-th ThreadLocalRandom.nextFloat() of the loop */
+int jl_model_generate_sample(jl_model *m, int session, const int32_t *prompt, int n_prompt, int n_new, float temperature,
+                             const float *uniforms, int32_t *out_tokens, double *timings_ms);
 /* AbstractModel.generate (:516-646) at temperature 0 over token ids: returns n_new tokens (the first is
  * sampled from the prompt's last row).  timings_ms (nullable double[2]) = {prompt, generate} wall ms like
  * Generator.Response.  logits_out HOST [n_new, vocab] or NULL. */
@@ -345,10 +353,10 @@ int jl_model_tp_layout(jl_model *m, jl_dctx *out, int *tp_size);
  * KvBuffer (core/tensor/KvBufferCache.java:58-60; jlama-net/.../openai/OpenAIChatService.java:64-74,107-160).  Here requests queue in
  * front of the batched decode step: every jl_sched_step admits queued requests into free session slots (FIFO), forwards prompt chunks,
  * runs ONE decode step for all generating requests (rows of different lengths side by side, at most the model's rows-per-call per
- * backend call) and retires finished requests so that their slots are reused by the next step.  When no slot is free, the least
+ * backend call, each row greedy or sampled at its own temperature) and retires finished requests so that their slots are reused by the
+ * next step.  When no slot is free, the least
  * recently finished kept session is spilled to host memory (KvBufferCache's pages are file-backed in the reference, :121-176; here the
- * idle session's pages leave HBM) and restored into any free slot when its follow-up arrives.  Greedy (temperature 0) like
- * jl_model_decode.  Under tensor parallelism every rank runs the same scheduler on the same request stream (it is deterministic).
+ * idle session's pages leave HBM) and restored into any free slot when its follow-up arrives.  Under tensor parallelism every rank runs the same scheduler on the same request stream (it is deterministic).
  * Free the scheduler before its model. */
 typedef struct jl_sched jl_sched;
 /* request states */
@@ -370,9 +378,9 @@ typedef struct jl_sched jl_sched;
 typedef struct {
     int (*reset_session)(void *user, int session);                                                   /* jl_model_reset_session */
     int (*batch_forward)(void *user, int session, const int32_t *tokens, int n, int start_pos);       /* jl_model_batch_forward */
-    int (*sample)(void *user, int session, int32_t *token_out);                                       /* jl_model_sample, temperature 0 */
+    int (*sample)(void *user, int session, float temperature, float uniform, int32_t *token_out);     /* jl_model_sample */
     int (*decode)(void *user, int n, const int32_t *sessions, const int32_t *tokens, const int32_t *positions,
-                  int32_t *next_tokens);                                                              /* jl_model_decode */
+                  const float *temperatures, const float *uniforms, int32_t *next_tokens);            /* jl_model_decode_sample */
     /* optional, all three or none: host spill of kept sessions (jl_model_kv_offload / kv_restore / kv_discard) */
     int (*offload)(void *user, int session, int64_t *handle_out);
     int (*restore)(void *user, int session, int64_t handle);
@@ -398,9 +406,12 @@ int jl_sched_free(jl_sched *s);
 const char *jl_sched_last_error(jl_sched *s);
 /* Queue a request: prompt token ids, at most max_new generated tokens (the first is sampled from the prompt's last row and, like the
  * reference's, not stop-checked), optional stop tokens.  continue_request >= 0: a finished JL_SCHED_KEEP_SESSION request whose session
- * this request appends to.  Returns the request id (> 0) or -1.  Callable from any thread, also while a step runs. */
+ * this request appends to.  temperature 0 = arg-max; otherwise every token is drawn with the reference's rule (AbstractModel.java:475-489)
+ * from a per-request uniform stream seeded with `seed` (the reference draws ThreadLocalRandom.nextFloat(), :576,:594): the k-th token of
+ * a request uses its k-th draw however the steps were batched, so (seed, prompt) reproduces.  Returns the request id (> 0) or -1.
+ * Callable from any thread, also while a step runs. */
 int64_t jl_sched_submit(jl_sched *s, const int32_t *prompt, int n_prompt, int max_new, const int32_t *stop_tokens, int n_stop, int flags,
-                        int64_t continue_request);
+                        int64_t continue_request, float temperature, uint64_t seed);
 int jl_sched_cancel(jl_sched *s, int64_t request); /* takes effect at the next step boundary */
 /* one scheduling iteration; returns the first backend error of the step (the affected requests are JL_SCHED_FAILED, the others go on) */
 int jl_sched_step(jl_sched *s, jl_sched_stats *stats /* nullable */);

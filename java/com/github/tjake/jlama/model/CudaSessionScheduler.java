@@ -38,7 +38,7 @@ public final class CudaSessionScheduler implements AutoCloseable {
     private static final MethodHandle jl_sched_free = h("jl_sched_free", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     private static final MethodHandle jl_sched_last_error = h("jl_sched_last_error", FunctionDescriptor.of(ADDRESS, ADDRESS));
     private static final MethodHandle jl_sched_submit =
-        h("jl_sched_submit", FunctionDescriptor.of(JAVA_LONG, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_LONG));
+        h("jl_sched_submit", FunctionDescriptor.of(JAVA_LONG, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_LONG, JAVA_FLOAT, JAVA_LONG));
     private static final MethodHandle jl_sched_cancel = h("jl_sched_cancel", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG));
     private static final MethodHandle jl_sched_step = h("jl_sched_step", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
     private static final MethodHandle jl_sched_result =
@@ -82,15 +82,18 @@ public final class CudaSessionScheduler implements AutoCloseable {
 
     /**
      * AbstractModel.generate over token ids: blocks until the request finishes, calls onToken for every generated token in order, returns
-     * the FinishReason code.  keepSession = the caller sent a session id and may come back with a follow-up prompt.
+     * the FinishReason code.  keepSession = the caller sent a session id and may come back with a follow-up prompt.  temperature 0 = arg-max;
+     * otherwise every token is drawn with AbstractModel.sample's rule (:475-489) from a stream seeded here (the reference draws
+     * ThreadLocalRandom.current().nextFloat() per token, :576,:594).
      */
-    public int generate(UUID session, int[] promptTokens, int maxNew, int[] eosTokens, boolean keepSession, IntConsumer onToken) {
+    public int generate(UUID session, int[] promptTokens, float temperature, int maxNew, int[] eosTokens, boolean keepSession, IntConsumer onToken) {
         try (Arena a = Arena.ofConfined()) {
             MemorySegment pr = a.allocateFrom(JAVA_INT, promptTokens);
             MemorySegment eos = eosTokens.length == 0 ? MemorySegment.NULL : a.allocateFrom(JAVA_INT, eosTokens);
             Long parent = kept.remove(session);
             long id = (long) jl_sched_submit.invokeExact(sched, pr, promptTokens.length, maxNew, eos, eosTokens.length,
-                                                          keepSession ? KEEP_SESSION : 0, parent == null ? -1L : (long) parent);
+                                                          keepSession ? KEEP_SESSION : 0, parent == null ? -1L : (long) parent,
+                                                          temperature, java.util.concurrent.ThreadLocalRandom.current().nextLong());
             if (id < 0) throw new IllegalArgumentException(((MemorySegment) jl_sched_last_error.invokeExact(sched)).reinterpret(512).getString(0));
             synchronized (tick) { tick.notifyAll(); }
             MemorySegment buf = a.allocate(JAVA_INT, maxNew), n = a.allocate(JAVA_INT), state = a.allocate(JAVA_INT), reason = a.allocate(JAVA_INT);

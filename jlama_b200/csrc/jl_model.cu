@@ -1314,11 +1314,16 @@ static int run_decode(jl_model *m, int n, int max_pos, bool resident, bool want_
     return JL_OK;
 }
 
-extern "C" int jl_model_decode(jl_model *m, int n, const int32_t *sessions, const int32_t *tokens, const int32_t *positions,
-                               int32_t *next_tokens, float *logits_out) {
+// temperatures / uniforms: nullable [n]; a row with temperature != 0 is sampled with the reference's prefix-sum rule
+// (AbstractModel.java:475-489, softmax_sample_kernel) from its logits row instead of taking the arg-max
+static int decode_impl(jl_model *m, int n, const int32_t *sessions, const int32_t *tokens, const int32_t *positions,
+                       const float *temperatures, const float *uniforms, int32_t *next_tokens, float *logits_out) {
     if (!m || !m->finalized || n <= 0 || n > m->cfg.max_sessions || n > GEMV_MAX_M || !sessions || !tokens || !positions ||
         !next_tokens)
         return m ? jl_set_error(m->ctx, JL_ERR_INVALID, "decode: bad arguments (n=%d, max %d)", n, GEMV_MAX_M) : JL_ERR_INVALID;
+    bool sampled = false;
+    for (int i = 0; temperatures && i < n; i++) sampled = sampled || temperatures[i] != 0.0f;
+    if (sampled && !uniforms) return jl_set_error(m->ctx, JL_ERR_INVALID, "decode: temperatures without uniform samples");
     std::lock_guard<std::recursive_mutex> model_lock(m->mu);
     jl_ctx *ctx = m->ctx;
     JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
@@ -1342,11 +1347,18 @@ extern "C" int jl_model_decode(jl_model *m, int n, const int32_t *sessions, cons
     JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_positions, hp + m->maxB, (size_t)n * 4, cudaMemcpyHostToDevice, m->stream));
     JL_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_sessions, hp + 2 * m->maxB, (size_t)n * 4, cudaMemcpyHostToDevice, m->stream));
     auto c1 = std::chrono::steady_clock::now();
-    M_CHECK(run_decode(m, n, max_pos, false, logits_out != nullptr));
+    M_CHECK(run_decode(m, n, max_pos, false, logits_out != nullptr || sampled));
     auto c2 = std::chrono::steady_clock::now();
-    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(hp + 3 * m->maxB, m->d_next, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
-    if (logits_out)
+    if (logits_out) // before the sampling kernels turn the sampled rows into exponentials in place
         JL_CUDA_CHECK(ctx, cudaMemcpyAsync(logits_out, m->logits, (size_t)n * m->cfg.vocab_size * 4, cudaMemcpyDeviceToHost, m->stream));
+    for (int i = 0; sampled && i < n; i++) {
+        if (temperatures[i] == 0.0f) continue; // :471-473 short-circuit: the arg-max of the step stands
+        softmax_sample_kernel<<<1, 256, 0, m->stream>>>(m->logits + (size_t)i * m->cfg.vocab_size, m->cfg.vocab_size, temperatures[i], uniforms[i],
+                                                        m->d_next + i);
+        ctx->launches++;
+        JL_CUDA_CHECK(ctx, cudaGetLastError());
+    }
+    JL_CUDA_CHECK(ctx, cudaMemcpyAsync(hp + 3 * m->maxB, m->d_next, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
     JL_CUDA_CHECK(ctx, cudaEventRecord(m->ev_end, m->stream));
     auto c3 = std::chrono::steady_clock::now();
     JL_CUDA_CHECK(ctx, cudaStreamSynchronize(m->stream));
@@ -1376,6 +1388,16 @@ extern "C" int jl_model_decode(jl_model *m, int n, const int32_t *sessions, cons
         m->last_gemv_ms = g;
     }
     return JL_OK;
+}
+
+extern "C" int jl_model_decode(jl_model *m, int n, const int32_t *sessions, const int32_t *tokens, const int32_t *positions,
+                               int32_t *next_tokens, float *logits_out) {
+    return decode_impl(m, n, sessions, tokens, positions, nullptr, nullptr, next_tokens, logits_out);
+}
+
+extern "C" int jl_model_decode_sample(jl_model *m, int n, const int32_t *sessions, const int32_t *tokens, const int32_t *positions,
+                                      const float *temperatures, const float *uniforms, int32_t *next_tokens, float *logits_out) {
+    return decode_impl(m, n, sessions, tokens, positions, temperatures, uniforms, next_tokens, logits_out);
 }
 
 extern "C" int jl_model_decode_resident(jl_model *m, int session, int32_t first_token, int start_pos, int n_new,
@@ -1471,6 +1493,35 @@ extern "C" int jl_model_generate(jl_model *m, int session, const int32_t *prompt
         const int32_t pos = n_prompt + i - 1;
         int32_t nx = 0;
         M_CHECK(jl_model_decode(m, 1, &session, &next, &pos, &nx, logits_out ? logits_out + (size_t)i * V : nullptr));
+        next = nx;
+        out_tokens[i] = next;
+    }
+    auto t2 = std::chrono::steady_clock::now();
+    if (timings_ms) {
+        timings_ms[0] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        timings_ms[1] = std::chrono::duration<double, std::milli>(t2 - t1).count();
+    }
+    return JL_OK;
+}
+
+// AbstractModel.generate (:516-646) with a temperature: uniforms[i] plays ThreadLocalRandom.current().nextFloat() of the i-th sample()
+// call (:576, :594), so a caller that passes the same stream gets the same tokens.
+extern "C" int jl_model_generate_sample(jl_model *m, int session, const int32_t *prompt, int n_prompt, int n_new, float temperature,
+                                        const float *uniforms, int32_t *out_tokens, double *timings_ms) {
+    if (!m || !m->finalized || !prompt || n_prompt <= 0 || n_new <= 0 || !out_tokens || (temperature != 0.0f && !uniforms)) return JL_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> model_lock(m->mu);
+    auto t0 = std::chrono::steady_clock::now();
+    M_CHECK(jl_model_reset_session(m, session));
+    M_CHECK(jl_model_batch_forward(m, session, prompt, n_prompt, 0));
+    int32_t next = 0;
+    M_CHECK(jl_model_sample(m, session, temperature, temperature != 0.0f ? uniforms[0] : 0.0f, &next, nullptr));
+    auto t1 = std::chrono::steady_clock::now();
+    out_tokens[0] = next;
+    for (int i = 1; i < n_new; i++) {
+        const int32_t pos = n_prompt + i - 1;
+        const float u = temperature != 0.0f ? uniforms[i] : 0.0f;
+        int32_t nx = 0;
+        M_CHECK(decode_impl(m, 1, &session, &next, &pos, &temperature, &u, &nx, nullptr));
         next = nx;
         out_tokens[i] = next;
     }

@@ -43,6 +43,8 @@ struct Request {
     std::vector<int32_t> stop;
     int max_new = 0;
     int flags = 0;
+    float temperature = 0.0f;
+    uint64_t rng = 0; // splitmix64 state: the k-th sampled token of a request uses its k-th draw, however the steps were batched
     int state = JL_SCHED_QUEUED;
     int reason = JL_FINISH_NONE;
     int session = -1;
@@ -87,14 +89,27 @@ static int sched_error(jl_sched *s, int code, const char *fmt, ...) {
     return code;
 }
 
+// ThreadLocalRandom.current().nextFloat() of AbstractModel.generate (:576, :594): 24 random bits / 2^24 in [0, 1), from a per-request
+// splitmix64 stream so that a (seed, prompt) pair reproduces its tokens.
+static float next_uniform(Request &r) {
+    uint64_t z = (r.rng += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+
 // ---- jl_model backend ---------------------------------------------------------------------------------------------------------
 static int mb_reset(void *u, int session) { return jl_model_reset_session((jl_model *)u, session); }
 static int mb_forward(void *u, int session, const int32_t *tokens, int n, int start_pos) {
     return jl_model_batch_forward((jl_model *)u, session, tokens, n, start_pos);
 }
-static int mb_sample(void *u, int session, int32_t *token) { return jl_model_sample((jl_model *)u, session, 0.0f, 0.0f, token, nullptr); }
-static int mb_decode(void *u, int n, const int32_t *sessions, const int32_t *tokens, const int32_t *positions, int32_t *next) {
-    return jl_model_decode((jl_model *)u, n, sessions, tokens, positions, next, nullptr);
+static int mb_sample(void *u, int session, float temperature, float uniform, int32_t *token) {
+    return jl_model_sample((jl_model *)u, session, temperature, uniform, token, nullptr);
+}
+static int mb_decode(void *u, int n, const int32_t *sessions, const int32_t *tokens, const int32_t *positions, const float *temperatures,
+                     const float *uniforms, int32_t *next) {
+    return jl_model_decode_sample((jl_model *)u, n, sessions, tokens, positions, temperatures, uniforms, next, nullptr);
 }
 
 static int mb_offload(void *u, int session, int64_t *handle) {
@@ -147,11 +162,11 @@ extern "C" int jl_sched_free(jl_sched *s) {
 extern "C" const char *jl_sched_last_error(jl_sched *s) { return s ? s->last_error.c_str() : "null scheduler"; }
 
 extern "C" int64_t jl_sched_submit(jl_sched *s, const int32_t *prompt, int n_prompt, int max_new, const int32_t *stop_tokens,
-                                   int n_stop, int flags, int64_t continue_request) {
+                                   int n_stop, int flags, int64_t continue_request, float temperature, uint64_t seed) {
     if (!s) return -1;
     std::lock_guard<std::mutex> lk(s->mu);
-    if (!prompt || n_prompt <= 0 || max_new <= 0 || n_stop < 0 || (n_stop > 0 && !stop_tokens))
-        return sched_error(s, -1, "submit: bad arguments (n_prompt=%d, max_new=%d)", n_prompt, max_new);
+    if (!prompt || n_prompt <= 0 || max_new <= 0 || n_stop < 0 || (n_stop > 0 && !stop_tokens) || !(temperature >= 0.0f))
+        return sched_error(s, -1, "submit: bad arguments (n_prompt=%d, max_new=%d, temperature=%g)", n_prompt, max_new, (double)temperature);
     Request r;
     if (continue_request >= 0) {
         // AbstractModel.generate :533 startPos = kvmem.getCurrentContextPosition(): a follow-up on the same session appends to its KV
@@ -173,6 +188,8 @@ extern "C" int64_t jl_sched_submit(jl_sched *s, const int32_t *prompt, int n_pro
     if (n_stop > 0) r.stop.assign(stop_tokens, stop_tokens + n_stop);
     r.max_new = max_new;
     r.flags = flags;
+    r.temperature = temperature;
+    r.rng = seed;
     r.submit_step = s->step_no;
     r.out.reserve((size_t)(max_new < 4096 ? max_new : 4096));
     const int64_t id = r.id;
@@ -298,12 +315,14 @@ struct PrefillJob {
     int64_t id;
     int session, start, n, pos;
     bool last;
+    float temperature = 0.0f, uniform = 0.0f; // for the token sampled from the prompt's last row
     SlotJob slot;
     std::vector<int32_t> tokens;
 };
 struct Row {
     int64_t id;
     int32_t session, token, position;
+    float temperature, uniform;
 };
 } // namespace
 
@@ -403,6 +422,7 @@ extern "C" int jl_sched_step(jl_sched *s, jl_sched_stats *stats) {
             j.id = id, j.session = r.session, j.start = r.prefilled, j.n = n, j.pos = r.start_pos + r.prefilled;
             if (sj != slot_jobs.end()) j.slot = sj->second; // the slot is prepared in the admission step even if the budget is spent
             j.last = n > 0 && r.prefilled + n == (int)r.prompt.size();
+            if (j.last && r.temperature != 0.0f) j.temperature = r.temperature, j.uniform = next_uniform(r);
             j.tokens.assign(r.prompt.begin() + r.prefilled, r.prompt.begin() + r.prefilled + n);
             jobs.push_back(std::move(j));
             budget -= n;
@@ -440,7 +460,7 @@ extern "C" int jl_sched_step(jl_sched *s, jl_sched_stats *stats) {
             rc = s->be.reset_session(s->user, j.session);
         }
         if (rc == JL_OK && j.n > 0) rc = s->be.batch_forward(s->user, j.session, j.tokens.data(), j.n, j.pos);
-        if (rc == JL_OK && j.last) rc = s->be.sample(s->user, j.session, &tok);
+        if (rc == JL_OK && j.last) rc = s->be.sample(s->user, j.session, j.temperature, j.uniform, &tok);
         std::lock_guard<std::mutex> lk(s->mu);
         Request &r = s->reqs[j.id];
         if (rc != JL_OK) {
@@ -465,15 +485,21 @@ extern "C" int jl_sched_step(jl_sched *s, jl_sched_stats *stats) {
     {
         std::lock_guard<std::mutex> lk(s->mu);
         for (int64_t id : s->active) {
-            const Request &r = s->reqs[id];
-            if (r.state == JL_SCHED_DECODING) rows.push_back(Row{id, r.session, r.out.back(), r.next_pos()});
+            Request &r = s->reqs[id];
+            if (r.state != JL_SCHED_DECODING) continue;
+            const float u = r.temperature != 0.0f ? next_uniform(r) : 0.0f;
+            rows.push_back(Row{id, r.session, r.out.back(), r.next_pos(), r.temperature, u});
         }
     }
     std::vector<int32_t> sess((size_t)s->max_rows), toks((size_t)s->max_rows), pos((size_t)s->max_rows), next((size_t)s->max_rows);
+    std::vector<float> temps((size_t)s->max_rows), unis((size_t)s->max_rows);
     for (size_t g = 0; g < rows.size(); g += (size_t)s->max_rows) {
         const int n = (int)(rows.size() - g < (size_t)s->max_rows ? rows.size() - g : (size_t)s->max_rows);
-        for (int i = 0; i < n; i++) sess[(size_t)i] = rows[g + i].session, toks[(size_t)i] = rows[g + i].token, pos[(size_t)i] = rows[g + i].position;
-        const int rc = s->be.decode(s->user, n, sess.data(), toks.data(), pos.data(), next.data());
+        for (int i = 0; i < n; i++) {
+            const Row &w = rows[g + (size_t)i];
+            sess[(size_t)i] = w.session, toks[(size_t)i] = w.token, pos[(size_t)i] = w.position, temps[(size_t)i] = w.temperature, unis[(size_t)i] = w.uniform;
+        }
+        const int rc = s->be.decode(s->user, n, sess.data(), toks.data(), pos.data(), temps.data(), unis.data(), next.data());
         st.decode_calls++;
         std::lock_guard<std::mutex> lk(s->mu);
         for (int i = 0; i < n; i++) {

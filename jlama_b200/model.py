@@ -191,14 +191,23 @@ class LlamaModel:
                                                 ptr(logits)))
         return tok.value, logits
 
-    def decode(self, tokens, positions, sessions=None, want_logits=False):
+    def decode(self, tokens, positions, sessions=None, want_logits=False, temperatures=None, uniforms=None):
+        """One decode step for n sessions.  temperatures / uniforms (per row): rows with a temperature other than 0 are sampled with
+        AbstractModel.sample's rule (:475-489) from their logits row, the others take the arg-max."""
         tokens = np.ascontiguousarray(tokens, dtype=np.int32)
         positions = np.ascontiguousarray(positions, dtype=np.int32)
         n = len(tokens)
         sessions = np.arange(n, dtype=np.int32) if sessions is None else np.ascontiguousarray(sessions, dtype=np.int32)
         nxt = np.empty(n, dtype=np.int32)
         logits = np.empty((n, self.cfg["vocab"]), dtype=np.float32) if want_logits else None
-        self.ctx.check(self.lib.jl_model_decode(self.h, n, ptr(sessions), ptr(tokens), ptr(positions), ptr(nxt), ptr(logits)))
+        if temperatures is None:
+            self.ctx.check(self.lib.jl_model_decode(self.h, n, ptr(sessions), ptr(tokens), ptr(positions), ptr(nxt), ptr(logits)))
+        else:
+            t = np.ascontiguousarray(temperatures, dtype=np.float32)
+            u = np.ascontiguousarray(uniforms, dtype=np.float32)
+            assert len(t) == n and len(u) == n
+            self.ctx.check(self.lib.jl_model_decode_sample(self.h, n, ptr(sessions), ptr(tokens), ptr(positions), ptr(t), ptr(u), ptr(nxt),
+                                                           ptr(logits)))
         return nxt, logits
 
     def decode_resident(self, first_token, start_pos, n_new, session=0):
@@ -214,6 +223,16 @@ class LlamaModel:
         self.ctx.check(self.lib.jl_model_generate(self.h, session, ptr(prompt), len(prompt), n_new, ptr(out), ptr(logits), tm))
         self.last_timings_ms = (tm[0], tm[1])
         return out, logits
+
+    def generate_sample(self, prompt, n_new, temperature, uniforms, session=0):
+        """AbstractModel.generate with a temperature; uniforms[i] stands for the i-th ThreadLocalRandom.nextFloat() of the loop."""
+        prompt = np.ascontiguousarray(prompt, dtype=np.int32)
+        u = np.ascontiguousarray(uniforms, dtype=np.float32)
+        assert len(u) >= n_new
+        out = np.empty(n_new, dtype=np.int32)
+        self.ctx.check(self.lib.jl_model_generate_sample(self.h, session, ptr(prompt), len(prompt), n_new, C.c_float(temperature), ptr(u),
+                                                         ptr(out), None))
+        return out
 
     def kv_save(self, directory, session_name, session=0):
         """KvBufferCache.KvBufferPage persistence: <directory>/<session_name>-L<l>C<c>.page files; returns the page count."""

@@ -59,9 +59,9 @@ class SchedRequestInfo(C.Structure):
 # jl_sched_backend: the four model calls the scheduler policy is written against
 SCHED_RESET_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int)
 SCHED_FORWARD_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_int)
-SCHED_SAMPLE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int32))
+SCHED_SAMPLE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_int32))
 SCHED_DECODE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
-                              C.POINTER(C.c_int32))
+                              C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32))
 
 
 SCHED_OFFLOAD_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int64))
@@ -141,6 +141,8 @@ SIGNATURES = {
     "jl_model_sample": (_i, [_vp, _i, _f, _f, _vp, _vp]),
     "jl_model_decode": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "jl_model_generate": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
+    "jl_model_decode_sample": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "jl_model_generate_sample": (_i, [_vp, _i, _vp, _i, _i, _f, _vp, _vp, _vp]),
     "jl_model_decode_resident": (_i, [_vp, _i, C.c_int32, _i, _i, _vp]),
     "jl_model_read_kv": (_i, [_vp, _i, _i, _i, _i, _vp]),
     "jl_model_kv_save": (_i, [_vp, _i, C.c_char_p, C.c_char_p]),
@@ -159,7 +161,7 @@ SIGNATURES = {
     "jl_sched_create_backend": (_i, [C.POINTER(SchedBackend), _vp, _i, _i, _i, _i, C.POINTER(_vp)]),
     "jl_sched_free": (_i, [_vp]),
     "jl_sched_last_error": (C.c_char_p, [_vp]),
-    "jl_sched_submit": (_i64, [_vp, _vp, _i, _i, _vp, _i, _i, _i64]),
+    "jl_sched_submit": (_i64, [_vp, _vp, _i, _i, _vp, _i, _i, _i64, _f, C.c_uint64]),
     "jl_sched_cancel": (_i, [_vp, _i64]),
     "jl_sched_step": (_i, [_vp, C.POINTER(SchedStats)]),
     "jl_sched_run": (_i, [_vp, _i, C.POINTER(SchedStats)]),

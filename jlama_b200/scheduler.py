@@ -34,8 +34,8 @@ class SessionScheduler:
     @classmethod
     def over_backend(cls, reset_session, batch_forward, sample, decode, n_sessions, max_rows, max_context, prefill_tokens_per_step=0,
                      offload=None, restore=None, discard=None):
-        """reset_session(session); batch_forward(session, tokens: np.int32[n], start_pos); sample(session) -> token;
-        decode(sessions, tokens, positions: np.int32[n]) -> next tokens; optionally the host-spill trio offload(session) -> handle,
+        """reset_session(session); batch_forward(session, tokens: np.int32[n], start_pos); sample(session, temperature, uniform) -> token;
+        decode(sessions, tokens, positions: np.int32[n], temperatures, uniforms: np.float32[n]) -> next tokens; optionally the host-spill trio offload(session) -> handle,
         restore(session, handle), discard(handle).  A raised exception fails the affected requests (JL_ERR_INVALID), exactly like a
         backend error code."""
         self = cls.__new__(cls)
@@ -63,14 +63,14 @@ class SessionScheduler:
             return native.JL_OK
 
         @guard
-        def _sample(_u, session, out):
-            out[0] = int(sample(session))
+        def _sample(_u, session, temperature, uniform, out):
+            out[0] = int(sample(session, temperature, uniform))
             return native.JL_OK
 
         @guard
-        def _decode(_u, n, sessions, tokens, positions, nxt):
+        def _decode(_u, n, sessions, tokens, positions, temperatures, uniforms, nxt):
             arr = lambda p: np.ctypeslib.as_array(p, shape=(n,)).copy()  # noqa: E731
-            res = decode(arr(sessions), arr(tokens), arr(positions))
+            res = decode(arr(sessions), arr(tokens), arr(positions), arr(temperatures), arr(uniforms))
             for i in range(n):
                 nxt[i] = int(res[i])
             return native.JL_OK
@@ -106,11 +106,13 @@ class SessionScheduler:
         if rc != native.JL_OK:
             raise native.JlamaNativeError(rc, self.lib.jl_sched_last_error(self.h).decode())
 
-    def submit(self, prompt, max_new, stop=(), keep_session=False, continue_request=-1):
+    def submit(self, prompt, max_new, stop=(), keep_session=False, continue_request=-1, temperature=0.0, seed=0):
+        """temperature 0 = arg-max; otherwise tokens are drawn with the reference's rule from a uniform stream seeded with `seed`."""
         prompt = np.ascontiguousarray(prompt, dtype=np.int32)
         stop = np.ascontiguousarray(list(stop), dtype=np.int32)
         rid = self.lib.jl_sched_submit(self.h, native.ptr(prompt), len(prompt), max_new, native.ptr(stop) if len(stop) else None,
-                                       len(stop), native.SCHED_KEEP_SESSION if keep_session else 0, continue_request)
+                                       len(stop), native.SCHED_KEEP_SESSION if keep_session else 0, continue_request,
+                                       C.c_float(temperature), C.c_uint64(seed))
         if rid < 0:
             raise native.JlamaNativeError(native.JL_ERR_INVALID, self.lib.jl_sched_last_error(self.h).decode())
         return rid

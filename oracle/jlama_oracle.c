@@ -874,6 +874,29 @@ int jo_model_sample(jo_model *m, const float *hidden_row, float *logits) {
     return maxi;
 }
 
+/* AbstractModel.sample :475-489, the part after the arg-max when temperature != 0: v = (float) exp((logit - maxv) / temperature)
+ * with maxv a double and FastMath.exp restated by libm (parity unpinned, see the header), `sum` a float accumulated in index order,
+ * then the first index whose float running sum of v / sum reaches uniformSample; vocab - 1 if none does.  `logits` is overwritten with
+ * the exponentials exactly like the reference's logits tensor. */
+int jo_sample_temperature(float *logits, int vocab, float temperature, float uniform) {
+    double maxv = -INFINITY;
+    for (int i = 0; i < vocab; i++)
+        if (logits[i] > maxv) maxv = logits[i];
+    float sum = 0;
+    for (int i = 0; i < vocab; i++) {
+        const float v = (float)exp(((double)logits[i] - maxv) / (double)temperature);
+        sum += v;
+        logits[i] = v;
+    }
+    float acc = 0;
+    for (int i = 0; i < vocab; i++) {
+        const float v = logits[i] / sum;
+        acc += v;
+        if (acc >= uniform) return i;
+    }
+    return vocab - 1;
+}
+
 /* AbstractModel.generate :516-646 at temperature 0 over token ids:
  * prefill prompt, then decode until n_total positions. out_tokens gets the
  * sampled tokens (first = sample after the prompt).  If logits_out != NULL it

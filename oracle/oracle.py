@@ -91,6 +91,7 @@ def lib():
         L.jo_model_kv_row.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.jo_model_batch_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.jo_model_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.jo_sample_temperature.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float]
         L.jo_model_generate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.jo_silu.restype = C.c_float
         L.jo_silu.argtypes = [C.c_float]
@@ -464,6 +465,12 @@ class OracleLlama:
             self.close()
         except Exception:
             pass
+
+
+def sample_temperature(logits, temperature, uniform):
+    """AbstractModel.sample (:475-489) for temperature != 0 on a logits row; returns the drawn token."""
+    work = np.ascontiguousarray(logits, dtype=np.float32).copy()
+    return int(lib().jo_sample_temperature(_p(work), len(work), C.c_float(temperature), C.c_float(uniform)))
 
 
 def num_threads():

@@ -206,3 +206,76 @@ def test_scheduler_spills_an_idle_kept_session_and_restores_it_for_its_follow_up
     _check_against_oracle(om, [(p1, 6, ta), (p2, 5, tb), (joined, 5, ta2)])
     gm.close()
     om.close()
+
+
+# ---- temperature sampling in decode steps: written after the round's last GPU call, not yet run on a B200 -> ordered last (conftest) ----
+def _splitmix_uniforms(seed, n):
+    """the scheduler's per-request stream (csrc/jl_sched.cu next_uniform): splitmix64, top 24 bits / 2^24"""
+    out, x, M = [], seed, (1 << 64) - 1
+    for _ in range(n):
+        x = (x + 0x9E3779B97F4A7C15) & M
+        z = x
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+        z ^= z >> 31
+        out.append(np.float32(z >> 40) * np.float32(1.0 / 16777216.0))
+    return np.array(out, dtype=np.float32)
+
+
+@pytest.mark.late
+def test_decode_sample_draws_rows_with_the_reference_rule(cuda_ctx, oracle):
+    """jl_model_decode_sample: rows with a temperature are drawn by AbstractModel.sample's rule (:475-489) from their own logits row,
+    rows at temperature 0 keep the arg-max; the logits handed back are the raw ones."""
+    from jlama_b200 import synth
+    from jlama_b200.model import LlamaModel
+    cfg = synth.get_config("small")
+    gm = LlamaModel(cuda_ctx, cfg, synth.make_weights(cfg), max_sessions=3)
+    firsts = []
+    prompts = [synth.random_prompt(cfg, 6 + 2 * s, seed=900 + s) for s in range(3)]
+    for s, p in enumerate(prompts):
+        gm.reset_session(s)
+        gm.batch_forward(p, 0, session=s)
+        firsts.append(gm.sample(session=s, want_logits=False)[0])
+    pos = [len(p) for p in prompts]
+    greedy, lg = gm.decode(firsts, pos, want_logits=True)  # re-decoding a position rewrites the same KV row: idempotent
+    T = np.array([0.7, 0.0, 1.3], dtype=np.float32)
+    for us in ((0.0, 0.5, 0.25), (0.9, 0.1, 0.6), (0.4, 0.4, 0.999)):
+        toks, lg2 = gm.decode(firsts, pos, want_logits=True, temperatures=T, uniforms=np.array(us, dtype=np.float32))
+        assert np.abs(lg2 - lg).max() <= 1e-5 * np.abs(lg).max()  # the raw logits, copied out before the rows are exponentiated in place
+        assert toks[1] == greedy[1]
+        for i in (0, 2):
+            expect = oracle.sample_temperature(lg[i], float(T[i]), us[i])
+            e = np.exp((lg[i].astype(np.float64) - lg[i].max()) / float(T[i])).astype(np.float32)
+            cdf = np.cumsum((e / e.sum(dtype=np.float32)).astype(np.float32), dtype=np.float32)
+            # the device sums the exponentials in another order than the reference's sequential loop: a draw that lands within
+            # rounding of a cdf step may pick the neighbour
+            assert toks[i] == expect or abs(int(toks[i]) - expect) <= 1 or abs(cdf[toks[i]] - us[i]) < 1e-4, (i, us, int(toks[i]), expect)
+    # a single sampled row goes through the persistent kernel's logits
+    t1, _ = gm.decode(firsts[:1], pos[:1], sessions=[0], temperatures=[0.7], uniforms=[0.5])
+    e1 = oracle.sample_temperature(lg[0], 0.7, 0.5)
+    assert abs(int(t1[0]) - e1) <= 1
+    gm.close()
+
+
+@pytest.mark.late
+def test_scheduler_sampled_request_equals_generate_sample_with_the_same_stream(cuda_ctx):
+    from jlama_b200 import synth
+    from jlama_b200.model import LlamaModel
+    from jlama_b200.scheduler import SessionScheduler
+    cfg = synth.get_config("small")
+    gm = LlamaModel(cuda_ctx, cfg, synth.make_weights(cfg), max_sessions=1)
+    prompt = synth.random_prompt(cfg, 10, seed=950)
+    with SessionScheduler(gm) as sched:
+        a = sched.submit(prompt, 12, temperature=0.9, seed=1234)
+        sched.run()
+        b = sched.submit(prompt, 12, temperature=0.9, seed=1234)
+        sched.run()
+        c = sched.submit(prompt, 12)
+        sched.run()
+        ta, tb, tc = sched.result(a)[0], sched.result(b)[0], sched.result(c)[0]
+    assert ta.tolist() == tb.tolist()  # (seed, prompt) reproduces
+    # one slot: every step is a one-row decode, the same kernels generate_sample runs -> bit-identical logits, identical draws
+    assert gm.generate_sample(prompt, 12, 0.9, _splitmix_uniforms(1234, 12)).tolist() == ta.tolist()
+    assert gm.generate(prompt, 12)[0].tolist() == tc.tolist()
+    assert ta.tolist() != tc.tolist()  # twelve draws at T = 0.9 do not all land on the arg-max
+    gm.close()

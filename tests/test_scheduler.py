@@ -16,10 +16,12 @@ from jlama_b200.scheduler import SessionScheduler
 VOCAB = 97
 
 
-def _toy_next(history):
+def _toy_next(history, temperature=0.0, uniform=0.0):
     h = 1469598103934665603
     for t in history:
         h = ((h ^ (int(t) + 1)) * 1099511628211) % (1 << 64)
+    if temperature != 0.0:  # a "sampled" token depends on the draw it was given
+        h = (h + int(round(float(uniform) * (1 << 24))) * 2654435761 + int(round(float(temperature) * 1000))) % (1 << 64)
     return int(h % VOCAB)
 
 
@@ -44,6 +46,7 @@ class ToyBackend:
         self.calls = []
         self.fail_session = fail_session
         self.store, self.next_handle, self.fail_offload = {}, 100, False
+        self.draws = []
 
     def reset_session(self, s):
         self.hist[s] = []
@@ -57,18 +60,20 @@ class ToyBackend:
         self.hist[s].extend(int(t) for t in tokens)
         self.calls.append(("forward", s, len(tokens), start_pos))
 
-    def sample(self, s):
+    def sample(self, s, temperature, uniform):
         self.calls.append(("sample", s))
-        return _toy_next(self.hist[s])
+        self.draws.append((s, float(temperature), float(uniform)))
+        return _toy_next(self.hist[s], temperature, uniform)
 
-    def decode(self, sessions, tokens, positions):
+    def decode(self, sessions, tokens, positions, temperatures, uniforms):
         assert 1 <= len(sessions) <= self.max_rows
         assert len(set(sessions.tolist())) == len(sessions), "a session twice in one step"
         out = []
-        for s, t, p in zip(sessions.tolist(), tokens.tolist(), positions.tolist()):
+        for s, t, p, T, u in zip(sessions.tolist(), tokens.tolist(), positions.tolist(), temperatures.tolist(), uniforms.tolist()):
             assert p == len(self.hist[s]), (s, p, len(self.hist[s]))
             self.hist[s].append(t)
-            out.append(_toy_next(self.hist[s]))
+            self.draws.append((s, T, u))
+            out.append(_toy_next(self.hist[s], T, u))
         self.calls.append(("decode", tuple(sessions.tolist())))
         return out
 
@@ -403,14 +408,16 @@ def test_oracle_as_the_device_matches_generate_request_by_request(oracle):
     def forward(s, tokens, start_pos):
         hidden[s] = slots[s].batch_forward(tokens, start_pos)
 
-    def sample(s):
-        return slots[s].sample(hidden[s])[0]
+    def pick(s, hid, T, u):
+        tok, logits = slots[s].sample(hid)
+        return tok if T == 0.0 else oracle.sample_temperature(logits, T, u)
 
-    def decode(sessions, tokens, positions):
-        out = []
-        for s, t, p in zip(sessions.tolist(), tokens.tolist(), positions.tolist()):
-            out.append(slots[s].sample(slots[s].batch_forward([t], p))[0])
-        return out
+    def sample(s, T, u):
+        return pick(s, hidden[s], T, u)
+
+    def decode(sessions, tokens, positions, temperatures, uniforms):
+        return [pick(s, slots[s].batch_forward([t], p), T, u)
+                for s, t, p, T, u in zip(sessions.tolist(), tokens.tolist(), positions.tolist(), temperatures.tolist(), uniforms.tolist())]
 
     sched = SessionScheduler.over_backend(reset, forward, sample, decode, n_slots, 2, cfg["ctx"], prefill_tokens_per_step=16)
     reqs = []
@@ -428,3 +435,68 @@ def test_oracle_as_the_device_matches_generate_request_by_request(oracle):
     ref.close()
     for o in slots:
         o.close()
+
+
+def test_sampled_requests_draw_a_reproducible_uniform_stream_independent_of_batching():
+    """temperature != 0: the k-th token of a request is drawn with the k-th value of its own seeded stream (the reference draws
+    ThreadLocalRandom.nextFloat() per sample() call, AbstractModel.java:576,594), so the tokens do not depend on how many other
+    requests shared its decode steps; greedy requests in the same steps get temperature 0 and are unaffected."""
+    def run(n_sessions, max_rows, budget):
+        be, s = _toy_sched(n_sessions=n_sessions, max_rows=max_rows, budget=budget)
+        ids = [s.submit([3, 4, 5], 9, temperature=0.8, seed=42),
+               s.submit([6, 7], 7),
+               s.submit([3, 4, 5], 9, temperature=0.8, seed=43),
+               s.submit([8, 9, 10, 11, 12], 6, temperature=1.5, seed=42),
+               s.submit([3, 4, 5], 9, temperature=0.8, seed=42)]
+        s.run()
+        out = [s.result(r)[0].tolist() for r in ids]
+        draws = be.draws
+        s.close()
+        return out, draws
+    a, draws = run(5, 5, 0)
+    b, _ = run(2, 1, 3)   # different slot count, one row per decode call, chunked prefill
+    assert a == b
+    assert a[0] == a[4] and a[0] != a[2]            # same seed and prompt reproduce; another seed differs
+    assert a[1] == _toy_generate([6, 7], 7)[0]     # the greedy request is what it would be alone
+    us = [u for (_, T, u) in draws if T != 0.0]
+    assert len(us) == 9 + 9 + 6 + 9 and all(0.0 <= u < 1.0 for u in us) and len(set(us)) == 18  # two distinct seeds, at most 9 draws each
+    assert all(u == 0.0 for (_, T, u) in draws if T == 0.0)
+    # the stream itself: splitmix64 from the seed, top 24 bits / 2^24 (tests/test_gpu_scheduler.py replays it for generate_sample)
+    x, M, want = 42, (1 << 64) - 1, []
+    for _ in range(9):
+        x = (x + 0x9E3779B97F4A7C15) & M
+        z = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & M
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+        want.append(float(np.float32((z ^ (z >> 31)) >> 40) * np.float32(1.0 / 16777216.0)))
+    first = [u for (s_, T, u) in draws if T != 0.0 and s_ == 0][:9]  # request 0 sits in slot 0 when every request has its own slot
+    assert first == want
+    be, s = _toy_sched()
+    with pytest.raises(native.JlamaNativeError):
+        s.submit([1], 2, temperature=-0.5)
+    with pytest.raises(native.JlamaNativeError):
+        s.submit([1], 2, temperature=float("nan"))
+    s.close()
+
+
+def test_oracle_temperature_rule_matches_a_numpy_restatement(oracle):
+    """AbstractModel.sample :475-489 restated twice (C in the oracle, numpy here): float exponentials of (logit - max) / T computed in
+    double, float running sums in index order, first index whose cumulative probability reaches the uniform sample."""
+    rng = np.random.default_rng(5)
+    for V, T in ((17, 0.7), (512, 1.0), (4096, 0.3)):
+        logits = (rng.standard_normal(V) * 3).astype(np.float32)
+        e = np.exp((logits.astype(np.float64) - float(logits.max())) / T).astype(np.float32)
+        total = np.float32(0)
+        for v in e:
+            total = np.float32(total + v)
+        p = (e / total).astype(np.float32)
+        cdf = np.zeros(V, dtype=np.float32)
+        acc = np.float32(0)
+        for i, v in enumerate(p):
+            acc = np.float32(acc + v)
+            cdf[i] = acc
+        for u in (0.0, 1e-6, 0.2, 0.5, 0.77, 0.999, 1.0):
+            hit = np.nonzero(cdf >= np.float32(u))[0]
+            want = int(hit[0]) if len(hit) else V - 1
+            assert oracle.sample_temperature(logits, T, u) == want, (V, T, u)
+    # u above the final cumulative sum (float rounding can leave it below 1): the last index
+    assert oracle.sample_temperature(np.zeros(8, np.float32), 1.0, 1.5) == 7
