@@ -15,7 +15,7 @@ def pytest_configure(config):
 
 def pytest_collection_modifyitems(config, items):
     """A GPU test that has not run on a B200 yet (written after a round's GPU budget was spent) can be marked `late`: it is ordered
-    behind everything else, so that under `-x` a surprise in it cannot hide the tests that are known to pass."""
+    behind everything else, so that under `-x` a surprise in it cannot hide the tests that are known to pass.  None is marked now."""
     late = [it for it in items if it.get_closest_marker("late")]
     if late:
         items[:] = [it for it in items if not it.get_closest_marker("late")] + late

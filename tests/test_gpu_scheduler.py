@@ -208,7 +208,7 @@ def test_scheduler_spills_an_idle_kept_session_and_restores_it_for_its_follow_up
     om.close()
 
 
-# ---- temperature sampling in decode steps: written after the round's last GPU call, not yet run on a B200 -> ordered last (conftest) ----
+# ---- temperature sampling in decode steps ----
 def _splitmix_uniforms(seed, n):
     """the scheduler's per-request stream (csrc/jl_sched.cu next_uniform): splitmix64, top 24 bits / 2^24"""
     out, x, M = [], seed, (1 << 64) - 1
@@ -222,7 +222,6 @@ def _splitmix_uniforms(seed, n):
     return np.array(out, dtype=np.float32)
 
 
-@pytest.mark.late
 def test_decode_sample_draws_rows_with_the_reference_rule(cuda_ctx, oracle):
     """jl_model_decode_sample: rows with a temperature are drawn by AbstractModel.sample's rule (:475-489) from their own logits row,
     rows at temperature 0 keep the arg-max; the logits handed back are the raw ones."""
@@ -257,7 +256,6 @@ def test_decode_sample_draws_rows_with_the_reference_rule(cuda_ctx, oracle):
     gm.close()
 
 
-@pytest.mark.late
 def test_scheduler_sampled_request_equals_generate_sample_with_the_same_stream(cuda_ctx):
     from jlama_b200 import synth
     from jlama_b200.model import LlamaModel
