@@ -66,11 +66,14 @@ extern "C" int jl_comm_unique_id(jl_ctx *ctx, uint8_t *id128) {
     return JL_OK;
 }
 
+extern "C" int jl_comm_destroy(jl_ctx *ctx);
+
 extern "C" int jl_comm_init(jl_ctx *ctx, const uint8_t *id128, int rank, int world) {
     if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return JL_ERR_INVALID;
     int rc = nccl_load(ctx);
     if (rc) return rc;
     JL_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    if (ctx->nccl_comm) jl_comm_destroy(ctx); // a second init replaces the communicator instead of leaking it
     ncclUniqueId id;
     memcpy(id.internal, id128, 128);
     ncclComm_t comm;

@@ -500,3 +500,104 @@ def test_oracle_temperature_rule_matches_a_numpy_restatement(oracle):
             assert oracle.sample_temperature(logits, T, u) == want, (V, T, u)
     # u above the final cumulative sum (float rounding can leave it below 1): the last index
     assert oracle.sample_temperature(np.zeros(8, np.float32), 1.0, 1.5) == 7
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_randomised_serving_scenarios_keep_every_request_on_its_own_trajectory(seed):
+    """Model-based stress test: random submissions (fresh, kept, follow-up turns, sampled), cancellations and releases interleaved with
+    steps, over few slots with host spill.  The toy backend asserts the device protocol on every call; here every request that finished on
+    its own must hold exactly the tokens its history chain dictates, whatever was batched, spilled or restored around it."""
+    rng = np.random.default_rng(1000 + seed)
+    n_slots = int(rng.integers(1, 4))
+    be, s = _toy_sched(n_sessions=n_slots, max_rows=int(rng.integers(1, 4)), budget=int(rng.integers(0, 12)), spill=True, max_context=96)
+    meta = {}      # id -> dict(prompt, max_new, stop, T, seed, parent, keep)
+    open_kept = []  # finished kept requests that may still be continued
+    live = []
+    for _ in range(int(rng.integers(40, 90))):
+        op = rng.random()
+        if op < 0.45:
+            parent = -1
+            if open_kept and rng.random() < 0.5:
+                parent = open_kept.pop(int(rng.integers(0, len(open_kept))))
+            prompt = rng.integers(0, VOCAB, size=int(rng.integers(1, 9))).tolist()
+            m = dict(prompt=prompt, max_new=int(rng.integers(1, 8)), stop=[int(rng.integers(0, VOCAB))] if rng.random() < 0.3 else [],
+                     T=float(rng.choice([0.0, 0.0, 0.7])), seed=int(rng.integers(0, 1 << 30)), parent=parent, keep=bool(rng.random() < 0.5))
+            try:
+                rid = s.submit(prompt, m["max_new"], stop=m["stop"], keep_session=m["keep"], continue_request=parent, temperature=m["T"], seed=m["seed"])
+            except native.JlamaNativeError:
+                continue  # context exhausted for this chain, or the parent's KV was dropped
+            meta[rid] = m
+            live.append(rid)
+        elif op < 0.55 and live:
+            s.cancel(live[int(rng.integers(0, len(live)))])
+        elif op < 0.62 and open_kept:
+            s.release(open_kept.pop(int(rng.integers(0, len(open_kept)))))
+        else:
+            st = s.step(check=False)
+            assert st.active <= n_slots
+        for rid in list(live):
+            _, state, reason = s.result(rid)
+            if state in (native.SCHED_FINISHED, native.SCHED_FAILED):
+                live.remove(rid)
+                if state == native.SCHED_FINISHED and reason != native.FINISH_CANCELLED and meta[rid]["keep"]:
+                    open_kept.append(rid)
+    s.run(check=False)
+    assert not be.__dict__.get("errors") and not s.backend_errors, s.backend_errors
+
+    def history_before(rid):
+        """tokens in the KV when request rid starts: its parent's chain, prompt and forwarded tokens"""
+        m = meta[rid]
+        if m["parent"] < 0:
+            return []
+        p = m["parent"]
+        toks = s_tokens[p]
+        return history_before(p) + meta[p]["prompt"] + toks[:len(toks) - 1]
+
+    s_tokens, s_state = {}, {}
+    for rid in meta:
+        try:
+            t, state, reason = s.result(rid)
+        except native.JlamaNativeError:
+            continue  # released
+        s_tokens[rid], s_state[rid] = t.tolist(), (state, reason)
+    checked = 0
+    for rid, m in meta.items():
+        if rid not in s_tokens or s_state[rid][0] != native.SCHED_FINISHED or s_state[rid][1] == native.FINISH_CANCELLED:
+            continue
+        chain_ok, q = True, m["parent"]
+        while q >= 0:
+            chain_ok = chain_ok and q in s_tokens
+            q = meta[q]["parent"]
+        if not chain_ok:
+            continue  # an ancestor was released: its tokens are no longer readable (the KV chain itself was still intact)
+        hist = history_before(rid) + m["prompt"]
+        # replay the request alone: k-th token with the k-th draw of its stream
+        x, M, out = m["seed"], (1 << 64) - 1, []
+        while True:
+            u = 0.0
+            if m["T"] != 0.0:
+                x = (x + 0x9E3779B97F4A7C15) & M
+                z = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & M
+                z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+                u = float(np.float32((z ^ (z >> 31)) >> 40) * np.float32(1.0 / 16777216.0))
+            out.append(_toy_next(hist, np.float32(m["T"]), u))
+            if (len(out) > 1 and out[-1] in m["stop"]) or len(out) >= m["max_new"] or len(hist) >= 96:
+                break
+            hist = hist + [out[-1]]
+        assert s_tokens[rid] == out, (rid, m, s_tokens[rid], out)
+        checked += 1
+    assert checked >= 5
+    # everything released: no slot, no host copy may be left behind
+    for rid in list(meta):
+        try:
+            s.release(rid)
+        except native.JlamaNativeError:
+            pass
+    for rid in list(meta):  # parents whose continuation was still pending at the first pass
+        try:
+            s.release(rid)
+        except native.JlamaNativeError:
+            pass
+    s.step()
+    assert s.counts() == (0, 0, n_slots) and not be.store
+    s.close()
