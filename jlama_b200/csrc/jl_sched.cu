@@ -155,6 +155,12 @@ extern "C" int jl_sched_free(jl_sched *s) {
     {
         std::lock_guard<std::mutex> a(s->step_mu); // a step in flight finishes first
     }
+    // host copies of spilled sessions nobody will restore any more
+    if (s->be.discard) {
+        for (int64_t h : s->discards) s->be.discard(s->user, h);
+        for (auto &kv : s->reqs)
+            if (kv.second.spill >= 0) s->be.discard(s->user, kv.second.spill);
+    }
     delete s;
     return JL_OK;
 }

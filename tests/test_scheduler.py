@@ -349,6 +349,17 @@ def test_a_failed_offload_drops_the_kept_session_but_not_the_new_request():
     s.close()
 
 
+def test_closing_the_scheduler_drops_the_host_copies_it_still_holds():
+    be, s = _toy_sched(n_sessions=1, max_rows=1, spill=True)
+    a = s.submit([1, 2], 2, keep_session=True)
+    s.run()
+    s.submit([3], 2, keep_session=True)
+    s.run()
+    assert len(be.store) == 1 and s.info(a).spilled == 1
+    s.close()
+    assert not be.store and be.calls[-1][0] == "discard"
+
+
 def test_a_failing_backend_call_fails_only_its_request():
     be, s = _toy_sched(n_sessions=3, max_rows=3, fail_session=1)
     ids = [s.submit([i + 1, i + 2], 4) for i in range(5)]
