@@ -395,6 +395,9 @@ typedef struct {
     int state, finish_reason, session /* -1: none, or spilled */, start_pos, n_prompt, n_prefilled, n_generated, next_position;
     int spilled; /* 1: this finished request's kept KV lives in host memory; its continuation restores it into a free slot */
     int64_t submit_step, first_token_step, finish_step; /* scheduler step counters: queueing delay and time to first token in steps */
+    /* host-clock milliseconds: waiting for a slot; admission -> first token (Generator.Response promptTimeMs, AbstractModel.java:561-568);
+     * first token -> finish (generateTimeMs, :589,:623).  A phase still running is measured up to the call. */
+    double queue_ms, prompt_ms, generate_ms;
 } jl_sched_request_info_t;
 /* max_active: session slots to use (<= the model's max_sessions; 0 = all).  prefill_tokens_per_step: prompt tokens forwarded per step over
  * all admitted requests (chunked prefill, bounds the latency a long prompt adds to the running requests' decode steps); 0 = no bound. */

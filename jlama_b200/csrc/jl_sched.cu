@@ -21,6 +21,7 @@
 // memory and its slot is reused; its continuation later restores the pages into whatever slot is free (jl_model_kv_restore).
 // Locking: `step_mu` serialises steps; `mu` guards the request table and is NOT held across backend calls, so submit / result /
 // cancel from other threads never wait for GPU work.
+#include <chrono>
 #include <deque>
 #include <mutex>
 #include <string>
@@ -58,6 +59,10 @@ struct Request {
     int64_t spill = -1;      // backend handle of this finished request's KV after it was offloaded to host memory (session == -1 then)
     std::vector<int32_t> out;
     uint64_t submit_step = 0, first_token_step = 0, finish_step = 0;
+    // host clock, like Generator.Response's promptTimeMs / generateTimeMs (AbstractModel.java:561-568,589,623): queued -> admitted ->
+    // first token -> finished
+    std::chrono::steady_clock::time_point t_submit, t_admit, t_first, t_finish;
+    bool admitted = false;
     int next_pos() const { return start_pos + (int)prompt.size() + forwarded; } // position the next decode step writes
 };
 
@@ -197,6 +202,7 @@ extern "C" int64_t jl_sched_submit(jl_sched *s, const int32_t *prompt, int n_pro
     r.temperature = temperature;
     r.rng = seed;
     r.submit_step = s->step_no;
+    r.t_submit = r.t_admit = r.t_first = r.t_finish = std::chrono::steady_clock::now();
     r.out.reserve((size_t)(max_new < 4096 ? max_new : 4096));
     const int64_t id = r.id;
     if (r.parent >= 0) s->reqs[r.parent].child = id;
@@ -241,6 +247,17 @@ extern "C" int jl_sched_request_info(jl_sched *s, int64_t request, jl_sched_requ
     info->spilled = r.spill >= 0 ? 1 : 0;
     info->submit_step = (int64_t)r.submit_step, info->first_token_step = (int64_t)r.first_token_step;
     info->finish_step = (int64_t)r.finish_step;
+    // phases that have not ended yet are measured up to now
+    const auto now = std::chrono::steady_clock::now();
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    const bool admitted = r.admitted;
+    const bool has_first = !r.out.empty();
+    const bool done = r.state == JL_SCHED_FINISHED || r.state == JL_SCHED_FAILED;
+    info->queue_ms = ms(r.t_submit, admitted ? r.t_admit : (done ? r.t_finish : now));
+    info->prompt_ms = admitted ? ms(r.t_admit, has_first ? r.t_first : (done ? r.t_finish : now)) : 0.0;
+    info->generate_ms = has_first ? ms(r.t_first, done ? r.t_finish : now) : 0.0;
     return JL_OK;
 }
 
@@ -287,6 +304,7 @@ static void finish(jl_sched *s, Request &r, int state, int reason) {
     r.state = state;
     r.reason = reason;
     r.finish_step = s->step_no;
+    r.t_finish = std::chrono::steady_clock::now();
     for (size_t i = 0; i < s->active.size(); i++)
         if (s->active[i] == r.id) {
             s->active.erase(s->active.begin() + (long)i);
@@ -411,6 +429,8 @@ extern "C" int jl_sched_step(jl_sched *s, jl_sched_stats *stats) {
             }
             s->slot_owner[(size_t)r.session] = r.id;
             r.state = JL_SCHED_PREFILL;
+            r.t_admit = std::chrono::steady_clock::now();
+            r.admitted = true;
             s->active.push_back(r.id);
             s->queue.erase(s->queue.begin() + (long)qi);
             slot_jobs[r.id] = sj;
@@ -479,6 +499,7 @@ extern "C" int jl_sched_step(jl_sched *s, jl_sched_stats *stats) {
         if (j.last) {
             r.out.push_back(tok);
             r.first_token_step = s->step_no;
+            r.t_first = std::chrono::steady_clock::now();
             r.state = JL_SCHED_DECODING;
             // the token sampled from the prompt is not stop-checked by the reference (AbstractModel.java:576-589)
             check_done(s, r, false);

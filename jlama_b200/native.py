@@ -53,7 +53,8 @@ class SchedStats(C.Structure):
 
 class SchedRequestInfo(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("state", "finish_reason", "session", "start_pos", "n_prompt", "n_prefilled", "n_generated",
-                                        "next_position", "spilled")] + [(n, C.c_int64) for n in ("submit_step", "first_token_step", "finish_step")]
+                                        "next_position", "spilled")] + [(n, C.c_int64) for n in ("submit_step", "first_token_step", "finish_step")] + [
+        (n, C.c_double) for n in ("queue_ms", "prompt_ms", "generate_ms")]
 
 
 # jl_sched_backend: the four model calls the scheduler policy is written against

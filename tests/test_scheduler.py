@@ -349,6 +349,30 @@ def test_a_failed_offload_drops_the_kept_session_but_not_the_new_request():
     s.close()
 
 
+def test_request_timings_split_queueing_prompt_and_generation():
+    import time
+    be, s = _toy_sched(n_sessions=1, max_rows=1)
+    a = s.submit([1, 2, 3], 4)
+    b = s.submit([4], 2)
+    c = s.submit([5], 2)
+    s.cancel(c)
+    time.sleep(0.02)
+    assert s.info(a).queue_ms >= 15 and s.info(a).prompt_ms == 0 and s.info(a).generate_ms == 0  # still queued: measured up to now
+    s.step()
+    time.sleep(0.02)
+    ia = s.info(a)
+    assert ia.queue_ms >= 15 and ia.prompt_ms >= 0 and ia.generate_ms >= 15  # first token is out, generation is running
+    s.run()
+    ia, ib, ic = s.info(a), s.info(b), s.info(c)
+    frozen = (ia.queue_ms, ia.prompt_ms, ia.generate_ms)
+    time.sleep(0.01)
+    ia = s.info(a)
+    assert (ia.queue_ms, ia.prompt_ms, ia.generate_ms) == frozen  # finished: the clocks stand
+    assert ib.queue_ms >= ia.queue_ms + ia.prompt_ms  # b waited for a's slot
+    assert ic.prompt_ms == 0 and ic.generate_ms == 0 and ic.queue_ms > 0  # cancelled in the queue
+    s.close()
+
+
 def test_closing_the_scheduler_drops_the_host_copies_it_still_holds():
     be, s = _toy_sched(n_sessions=1, max_rows=1, spill=True)
     a = s.submit([1, 2], 2, keep_session=True)
