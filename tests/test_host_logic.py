@@ -27,6 +27,57 @@ def test_library_exports_every_declared_symbol(lib):
         assert hasattr(lib, name), name
 
 
+def _c_kind(decl):
+    """'const float *x' -> 'ptr', 'int64_t n' -> 'i64', ... for a C parameter or return type"""
+    d = decl.strip()
+    if "*" in d or "[" in d:
+        return "ptr"
+    words = [w for w in re.split(r"\s+", d) if w not in ("const", "unsigned", "struct")]
+    t = words[0]
+    return {"int": "i32", "int32_t": "i32", "int64_t": "i64", "uint64_t": "u64", "float": "f32", "double": "f64", "void": "void"}[t]
+
+
+def _ctypes_kind(t):
+    if t is None:
+        return "void"
+    if t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents") or hasattr(t, "_type_") and isinstance(t._type_, type):
+        return "ptr"
+    return {C.c_int: "i32", C.c_int32: "i32", C.c_int64: "i64", C.c_uint64: "u64", C.c_float: "f32", C.c_double: "f64"}[t]
+
+
+def test_ctypes_signatures_agree_with_the_header_prototypes():
+    """Every prototype of include/jlama_b200.h against the ctypes signature the Python binding declares for it: parameter count and,
+    per parameter and return value, the machine type (pointer / int32 / int64 / uint64 / float / double).  A binding that passes a 32-bit
+    int where the ABI takes int64_t, or forgets a parameter, fails here instead of corrupting an argument at run time."""
+    from jlama_b200 import native
+    hdr = open(os.path.join(ROOT, "include", "jlama_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    hdr = re.sub(r"typedef struct \{.*?\} \w+;", "", hdr, flags=re.S)  # struct bodies (function-pointer members) are not prototypes
+    hdr = re.sub(r"^\s*#.*$", "", hdr, flags=re.M)                      # preprocessor lines
+    protos = re.findall(r"([A-Za-z_][\w\s\*]*?)\b(jl_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr)
+    seen = set()
+    for ret, name, params in protos:
+        res, args = native.SIGNATURES[name]
+        plist = [] if params.strip() in ("", "void") else [p for p in params.split(",")]
+        assert len(plist) == len(args), (name, len(plist), len(args))
+        assert _c_kind(ret + " x") == _ctypes_kind(res), (name, ret)
+        for i, (p, a) in enumerate(zip(plist, args)):
+            assert _c_kind(p) == _ctypes_kind(a), (name, i, p.strip(), a)
+        seen.add(name)
+    assert seen == set(native.SIGNATURES), seen ^ set(native.SIGNATURES)
+    # the structs mirrored by hand: member counts
+    raw = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "jlama_b200.h")).read(), flags=re.S)
+    bodies = {name: body for body, name in re.findall(r"typedef struct \{([^{}]*)\} (\w+);", raw)}
+    for cname, ctype in (("jl_sched_stats", native.SchedStats), ("jl_sched_request_info_t", native.SchedRequestInfo),
+                         ("jl_sched_backend", native.SchedBackend), ("jl_dctx", native.Dctx), ("jl_model_config", native.ModelConfig)):
+        n_members = 0
+        for stmt in bodies[cname].split(";"):
+            stmt = stmt.strip()
+            if stmt:
+                n_members += 1 if "(*" in stmt else len(stmt.split(","))
+        assert n_members == len(ctype._fields_), (cname, n_members, len(ctype._fields_))
+
+
 def test_init_fails_loudly_without_gpu_or_succeeds_on_sm100(lib):
     h = C.c_void_p()
     rc = lib.jl_init(0, C.byref(h), None)
