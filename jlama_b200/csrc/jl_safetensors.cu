@@ -458,9 +458,16 @@ extern "C" int jl_st_write(const char *path, int n, const char *const *names, co
 }
 
 // ---- offline quantiser: SafeTensorSupport.quantizeModel (:215-332) with the block quantisers running on the GPU -----------------
-static void f16_to_f32(const uint16_t *src, float *dst, size_t n) {
+// `src` points into the file mapping: the reference writes the data section right after an unpadded header (SafeTensorSupport.java:306-311),
+// so 2- and 4-byte elements may sit at odd addresses; they are read bytewise.
+static inline uint16_t load_u16(const void *base, size_t i) {
+    uint16_t v;
+    memcpy(&v, (const uint8_t *)base + 2 * i, 2);
+    return v;
+}
+static void f16_to_f32(const void *src, float *dst, size_t n) {
     for (size_t i = 0; i < n; i++) {
-        const uint32_t h = src[i], s = (h & 0x8000u) << 16, e = (h >> 10) & 0x1F, m = h & 0x3FF;
+        const uint32_t h = load_u16(src, i), s = (h & 0x8000u) << 16, e = (h >> 10) & 0x1F, m = h & 0x3FF;
         uint32_t u;
         if (e == 0) {
             if (m == 0) u = s;
@@ -481,12 +488,11 @@ static void tensor_to_f32(const StTensor &t, const void *src, std::vector<float>
     out.resize(n);
     if (t.dtype == JL_F32) memcpy(out.data(), src, n * 4);
     else if (t.dtype == JL_BF16) {
-        const uint16_t *s = (const uint16_t *)src;
         for (size_t i = 0; i < n; i++) {
-            const uint32_t u = (uint32_t)s[i] << 16; // FloatConversions.bFloat16ToFloat32 (:31-33)
+            const uint32_t u = (uint32_t)load_u16(src, i) << 16; // FloatConversions.bFloat16ToFloat32 (:31-33)
             memcpy(&out[i], &u, 4);
         }
-    } else f16_to_f32((const uint16_t *)src, out.data(), n);
+    } else f16_to_f32(src, out.data(), n);
 }
 static std::vector<std::string> split_csv(const char *s) {
     std::vector<std::string> v;
@@ -677,7 +683,7 @@ static int register_slice(jl_ctx *ctx, jl_st *st, const char *name, int64_t row0
     const bool whole_rows = col0 == 0 && cols == Cc;
     HostSlice hs;
     const uint8_t *dptr = src + (size_t)row0 * row_bytes;
-    const float *sptr = qb ? qb + (size_t)row0 * (Cc / 32) : nullptr;
+    const float *sptr = qb ? (const float *)((const uint8_t *)qb + (size_t)row0 * (size_t)(Cc / 32) * 4) : nullptr;
     if (!whole_rows) {
         hs.data.resize((size_t)rows * sl_bytes);
         for (int64_t r = 0; r < rows; r++) memcpy(hs.data.data() + (size_t)r * sl_bytes, src + (size_t)(row0 + r) * row_bytes + c0b, sl_bytes);
@@ -685,7 +691,8 @@ static int register_slice(jl_ctx *ctx, jl_st *st, const char *name, int64_t row0
         if (qb) {
             hs.scales.resize((size_t)rows * (cols / 32));
             for (int64_t r = 0; r < rows; r++)
-                memcpy(hs.scales.data() + (size_t)r * (cols / 32), qb + (size_t)(row0 + r) * (Cc / 32) + col0 / 32, (size_t)(cols / 32) * 4);
+                memcpy(hs.scales.data() + (size_t)r * (cols / 32), (const uint8_t *)qb + ((size_t)(row0 + r) * (size_t)(Cc / 32) + (size_t)(col0 / 32)) * 4,
+                       (size_t)(cols / 32) * 4);
             sptr = hs.scales.data();
         }
     }
