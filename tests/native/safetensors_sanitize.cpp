@@ -2,7 +2,8 @@
 // Built with -fsanitize=address,undefined by tests/test_safetensors_sanitizers.py.
 //   1. a well-formed JQ4 checkpoint (Llama layout and Mixtral layout) written with jl_st_write is loaded through
 //      jl_model_load_safetensors for every rank of tp = 1, 2, 4; the stub jl_register_tensor reads EVERY byte of every slice it is
-//      handed (data and block scales), so a slice that leaves the mapping or the temporary slice buffers is an ASAN report;
+//      handed (data and block scales), so a slice that leaves the mapping or the temporary slice buffers is an ASAN report, and
+//      checksums them against the rows / columns the rank must receive (LlamaModel.java:120-133 row and column splits);
 //   2. thousands of header mutations: jl_st_open either rejects the file or returns tensors whose bytes are all readable, and the
 //      loader either fails cleanly or reads in bounds.
 #include "jl_safetensors.cu"
@@ -28,6 +29,16 @@ struct jl_model {
     long sets;
 };
 int jl_set_error(jl_ctx *, int code, const char *, ...) { return code; }
+struct Registered {
+    int dtype;
+    int64_t rows, cols;
+    uint64_t data_sum, scale_sum;
+};
+static std::vector<Registered> g_registered; // what the loader handed to jl_register_tensor, in order
+static uint64_t fnv(const uint8_t *p, size_t n, uint64_t h = 1469598103934665603ull) {
+    for (size_t i = 0; i < n; i++) h = (h ^ p[i]) * 1099511628211ull;
+    return h;
+}
 static volatile uint64_t g_sink;
 static uint64_t g_bytes_read;
 extern "C" int64_t jl_register_tensor(jl_ctx *, int dtype, int64_t rows, int64_t cols, const void *data, const float *scales) {
@@ -44,6 +55,11 @@ extern "C" int64_t jl_register_tensor(jl_ctx *, int dtype, int64_t rows, int64_t
     }
     g_sink = acc;
     g_bytes_read += row * (size_t)rows;
+    Registered r;
+    r.dtype = dtype, r.rows = rows, r.cols = cols;
+    r.data_sum = fnv(p, row * (size_t)rows);
+    r.scale_sum = (dtype == JL_Q4 || dtype == JL_I8) ? fnv((const uint8_t *)scales, (size_t)rows * (size_t)(cols / 32) * 4) : 0;
+    g_registered.push_back(r);
     static int64_t next = 1;
     return next++;
 }
@@ -113,6 +129,66 @@ static Blob make_checkpoint(bool moe, std::mt19937 &rng) {
     return b;
 }
 
+// what rank `rank` of `tp` must receive for tensor `name`: rows [r0, r0+nr) x columns [c0, c0+nc) of the stored matrix, checksummed the
+// same way (Q4: nibble bytes of the column range + the f32 block scales of that range)
+static Registered expect(const Blob &b, const std::string &name, int64_t r0, int64_t nr, int64_t c0, int64_t nc) {
+    size_t i = 0;
+    while (b.names[i] != name) i++;
+    const int dt = b.dtypes[i];
+    const int64_t R = b.shapes[i * 4], C = b.shapes[i * 4 + 1];
+    if (nr < 0) r0 = 0, nr = R;
+    if (nc < 0) c0 = 0, nc = C;
+    Registered e;
+    e.dtype = dt, e.rows = nr, e.cols = nc, e.scale_sum = 0;
+    const double bpe = dt == JL_F32 ? 4 : (dt == JL_Q4 ? 0.5 : 1);
+    uint64_t h = 1469598103934665603ull;
+    for (int64_t r = r0; r < r0 + nr; r++) h = fnv(b.data[i].data() + (size_t)(r * C * bpe) + (size_t)(c0 * bpe), (size_t)(nc * bpe), h);
+    e.data_sum = h;
+    if (dt == JL_Q4) {
+        const std::vector<uint8_t> &qb = b.data[i + 1]; // "<name>.qb" follows its tensor
+        h = 1469598103934665603ull;
+        for (int64_t r = r0; r < r0 + nr; r++) h = fnv(qb.data() + ((size_t)r * (size_t)(C / 32) + (size_t)(c0 / 32)) * 4, (size_t)(nc / 32) * 4, h);
+        e.scale_sum = h;
+    }
+    return e;
+}
+
+// the order and the slices of LlamaModel.loadInputWeights / loadTransformerBlockWeights / loadOutputWeights (llama/LlamaModel.java:68-156,
+// rows for q/k/v/gate/up, columns for o/down) and MixtralModel.java:88-105 with expert e on rank e % tp
+static std::vector<Registered> expected_registrations(const Blob &b, const jl_model &m, bool moe) {
+    std::vector<Registered> v;
+    const bool sh = m.tp > 1;
+    const int rank = sh ? m.d.attentionSegmentStart / m.d.attentionSegmentLength : 0;
+    const int64_t ar0 = sh ? m.d.attentionSegmentStart : 0, ar = sh ? m.d.attentionSegmentLength : -1;
+    const int64_t kr0 = sh ? m.d.kvSegmentStart : 0, kr = sh ? m.d.kvSegmentLength : -1;
+    const int64_t hr0 = sh ? m.d.hiddenSegmentStart : 0, hr = sh ? m.d.hiddenSegmentLength : -1;
+    v.push_back(expect(b, "model.embed_tokens.weight", 0, -1, 0, -1));
+    v.push_back(expect(b, "model.norm.weight", 0, -1, 0, -1));
+    v.push_back(expect(b, "lm_head.weight", 0, -1, 0, -1));
+    for (int l = 0; l < LAYERS; l++) {
+        const std::string p = "model.layers." + std::to_string(l) + ".";
+        v.push_back(expect(b, p + "input_layernorm.weight", 0, -1, 0, -1));
+        v.push_back(expect(b, p + "self_attn.q_proj.weight", ar0, ar, 0, -1));
+        v.push_back(expect(b, p + "self_attn.k_proj.weight", kr0, kr, 0, -1));
+        v.push_back(expect(b, p + "self_attn.v_proj.weight", kr0, kr, 0, -1));
+        v.push_back(expect(b, p + "self_attn.o_proj.weight", 0, -1, ar0, ar));
+        v.push_back(expect(b, p + "post_attention_layernorm.weight", 0, -1, 0, -1));
+        if (moe) {
+            v.push_back(expect(b, p + "block_sparse_moe.gate.weight", 0, -1, 0, -1));
+            for (int e = 0; e < 4; e++) {
+                if (e % m.tp != rank) continue;
+                const std::string q = p + "block_sparse_moe.experts." + std::to_string(e) + ".";
+                for (const char *w : {"w1.weight", "w2.weight", "w3.weight"}) v.push_back(expect(b, q + w, 0, -1, 0, -1));
+            }
+        } else {
+            v.push_back(expect(b, p + "mlp.gate_proj.weight", hr0, hr, 0, -1));
+            v.push_back(expect(b, p + "mlp.down_proj.weight", 0, -1, hr0, hr));
+            v.push_back(expect(b, p + "mlp.up_proj.weight", hr0, hr, 0, -1));
+        }
+    }
+    return v;
+}
+
 static jl_model shard(int rank, int tp, bool moe) {
     jl_model m = {};
     m.tp = tp, m.experts = moe ? 4 : 0, m.layers = LAYERS;
@@ -160,8 +236,17 @@ int main(int argc, char **argv) {
                 jl_model m = shard(rank, tp, moe != 0);
                 int64_t ids[256];
                 int n = 0;
+                g_registered.clear();
                 REQUIRE(jl_model_load_safetensors(&m, &ctx, st, ids, 256, &n) == JL_OK);
                 REQUIRE(n == m.sets && n > 0);
+                // the bytes each rank received are exactly its rows / columns of the stored tensors
+                const std::vector<Registered> want = expected_registrations(b, m, moe != 0);
+                REQUIRE(want.size() == g_registered.size());
+                for (size_t i = 0; i < want.size(); i++) {
+                    const Registered &g = g_registered[i], &w = want[i];
+                    REQUIRE(g.dtype == w.dtype && g.rows == w.rows && g.cols == w.cols);
+                    REQUIRE(g.data_sum == w.data_sum && g.scale_sum == w.scale_sum);
+                }
                 slices += n;
             }
         REQUIRE(jl_st_close(st) == JL_OK);
