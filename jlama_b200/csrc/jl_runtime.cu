@@ -645,7 +645,8 @@ extern "C" int jl_dctx_build(int E, int attention_length, int H, int head_size, 
 // KvBufferCache.computePageSize (core/tensor/KvBufferCache.java:224-280)
 extern "C" int jl_kv_page_geometry(int num_layers, int context_length, int kv_segment_length, int dtype_size,
                                    int64_t max_page_bytes, int *layers_per_page, int *ctx_per_page) {
-    if (!layers_per_page || !ctx_per_page || num_layers <= 0 || context_length <= 0 || kv_segment_length <= 0) return JL_ERR_INVALID;
+    if (!layers_per_page || !ctx_per_page || num_layers <= 0 || context_length <= 0 || kv_segment_length <= 0 || dtype_size <= 0)
+        return JL_ERR_INVALID; // a zero element size would divide by zero below
     const int64_t s = 2LL * dtype_size * kv_segment_length;
     if (max_page_bytes <= s) return JL_ERR_INVALID; // Preconditions.checkArgument(:229)
     int optL = 1, optC = 1;

@@ -200,3 +200,37 @@ def test_model_config_mirror_matches_the_c_struct(lib):
     from jlama_b200 import native
     assert lib.jl_model_config_size() == C.sizeof(native.ModelConfig) == 104
     assert native.ModelConfig.arch.offset == 100 and native.ModelConfig.rope_theta.offset == 40
+
+
+def test_pure_host_functions_reject_degenerate_arguments_instead_of_faulting(lib, oracle):
+    """The library never aborts the host process (the reference's natives call exit(), vector_gpu.c:96,116): zero / negative sizes in the
+    pure host functions are status codes, not divisions by zero; valid random arguments agree with the oracle."""
+    from jlama_b200 import native
+    a, b = C.c_int(), C.c_int()
+    for args in [(32, 8192, 1024, 0), (32, 8192, 1024, -4), (0, 8192, 1024, 4), (32, 0, 1024, 4), (32, 8192, 0, 4)]:
+        assert lib.jl_kv_page_geometry(*args, 1 << 23, C.byref(a), C.byref(b)) == native.JL_ERR_INVALID
+    assert lib.jl_kv_page_geometry(32, 8192, 1024, 4, 16, C.byref(a), C.byref(b)) == native.JL_ERR_INVALID  # page smaller than one position
+    assert lib.jl_kv_page_geometry(32, 8192, 1024, 4, 1 << 23, None, C.byref(b)) == native.JL_ERR_INVALID
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        layers, ctx_len = int(rng.integers(1, 129)), int(2 ** rng.integers(4, 18))
+        kvl, esz = int(rng.integers(1, 65)) * 32, int(rng.choice([2, 4]))
+        assert lib.jl_kv_page_geometry(layers, ctx_len, kvl, esz, 1 << 23, C.byref(a), C.byref(b)) == 0
+        assert (a.value, b.value) == oracle.kv_page_solver(layers, ctx_len, kvl, esz)
+        assert 1 <= a.value <= layers and 1 <= b.value <= ctx_len and 2 * esz * kvl * a.value * b.value <= (1 << 23)
+    d = native.Dctx()
+    for bad in [(4096, 4096, 14336, 0, 4, 32, 0, 8, 0, 1), (4096, 4096, 14336, 128, 0, 32, 0, 8, 0, 1), (4096, 4096, 14336, 128, 4, 32, 0, 0, 0, 1),
+                (4096, 4096, 14336, 128, 4, 32, -1, 8, 0, 1), (4096, 4096, 14336, 128, 4, 32, 0, 8, 0, 0), (4096, 4096, 14336, 128, 4, 32, 0, 8, 2, 2)]:
+        assert lib.jl_dctx_build(*bad, C.byref(d)) == native.JL_ERR_INVALID
+    assert lib.jl_dctx_build(4096, 4096, 14336, 128, 4, 32, 0, 8, 0, 1, None) == native.JL_ERR_INVALID
+    t = np.empty((4, 2), dtype=np.float32)
+    for bad in [(0, 4), (3, 4), (4, 0), (-2, 4)]:
+        assert lib.jl_precompute_freqs_cis(bad[0], bad[1], 10000.0, 1.0, native.ptr(t)) == native.JL_ERR_INVALID
+    assert lib.jl_precompute_freqs_cis(4, 2, 10000.0, 1.0, None) == native.JL_ERR_INVALID
+    assert lib.jl_model_config_size() == C.sizeof(native.ModelConfig)
+    # handles that are NULL: status codes, never a fault
+    assert lib.jl_sched_step(None, None) == native.JL_ERR_INVALID and lib.jl_sched_free(None) == native.JL_ERR_INVALID
+    assert lib.jl_sched_submit(None, None, 0, 0, None, 0, 0, -1, C.c_float(0), 0) == -1
+    assert lib.jl_st_close(None) == native.JL_ERR_INVALID and lib.jl_st_count(None) == native.JL_ERR_INVALID
+    assert lib.jl_model_free(None) == native.JL_ERR_INVALID and lib.jl_model_kv_pages(None, 0) == native.JL_ERR_INVALID
+    assert lib.jl_shutdown(None) == native.JL_ERR_INVALID and lib.jl_kernel_launches(None) == -1
