@@ -144,8 +144,6 @@ class CudaTensorOperations:
         saxpy(AbstractTensor alpha, x, y, xoffset, yoffset, limit, aOffset, xRowOffset, batchSize)."""
         h = self.ctx.h
         if isinstance(alpha, AbstractTensor):
-            if alpha.cols != x.rows and False:
-                raise ValueError
             if y.rows != 1:
                 raise ValueError("y must have one row")  # TensorOperations.java:131
             self.ctx.check(self.lib.jl_saxpy_batch(h, ptr(alpha.data), ptr(x.data), x.cols, ptr(y.data), xoffset, yoffset,
