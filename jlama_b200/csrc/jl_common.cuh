@@ -28,7 +28,8 @@ struct jl_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr; // op-level API stream
     std::mutex mu;
-    std::string last_error;
+    std::mutex err_mu;      // guards last_error only: model entry points report errors without holding `mu`
+    std::string last_error; // the most recent error of any thread; jl_last_error prefers the calling thread's own (jl_runtime.cu)
     std::unordered_map<int64_t, DevTensor> tensors;
     std::vector<struct jl_model *> models; // live models (freed by jl_shutdown before the tensors they point at)
     int64_t next_id = 1;

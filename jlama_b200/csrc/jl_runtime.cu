@@ -7,7 +7,11 @@
 #include <stdio.h>
 #include <string.h>
 
-static thread_local std::string g_init_error = "";
+// Error text is kept per calling thread (errno style): op-level calls fail under ctx->mu, model-level calls under their model's lock,
+// request threads and a scheduler thread may fail at the same time -- one shared std::string would be written concurrently and the
+// pointer jl_last_error hands out could be freed under its reader.  The context also keeps the latest message of any thread for a
+// caller that asks from a thread which has not failed itself.
+static thread_local std::string g_thread_error = "";
 
 int jl_set_error(jl_ctx *ctx, int code, const char *fmt, ...) {
     char buf[1024];
@@ -15,14 +19,23 @@ int jl_set_error(jl_ctx *ctx, int code, const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
-    if (ctx) ctx->last_error = buf;
-    else g_init_error = buf;
+    g_thread_error = buf;
+    if (ctx) {
+        std::lock_guard<std::mutex> lk(ctx->err_mu);
+        ctx->last_error = buf;
+    }
     return code;
 }
 
 extern "C" const char *jl_version(void) { return "jlama_b200 0.1 (sm_100a)"; }
 
-extern "C" const char *jl_last_error(jl_ctx *ctx) { return ctx ? ctx->last_error.c_str() : g_init_error.c_str(); }
+extern "C" const char *jl_last_error(jl_ctx *ctx) {
+    if (g_thread_error.empty() && ctx) {
+        std::lock_guard<std::mutex> lk(ctx->err_mu);
+        g_thread_error = ctx->last_error; // a copy this thread owns: valid until its next failing call
+    }
+    return g_thread_error.c_str();
+}
 
 extern "C" int jl_init(int device, jl_ctx **out, int64_t *info) {
     if (!out) return JL_ERR_INVALID;
