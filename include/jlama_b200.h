@@ -50,7 +50,9 @@ typedef struct jl_model jl_model;
 /* info[0]=free bytes, [1]=total bytes, [2]=SM count, [3]=compute capability*10 (100 for B200). */
 int jl_init(int device, jl_ctx **out, int64_t *info /* nullable, int64[4] */);
 int jl_shutdown(jl_ctx *ctx);
-const char *jl_last_error(jl_ctx *ctx); /* never NULL */
+/* never NULL.  errno style: the text of the calling thread's most recent failing call (any entry point of this library), or, if this
+ * thread has not failed yet, the most recent failure of any thread on `ctx`.  Valid until the calling thread's next failing call. */
+const char *jl_last_error(jl_ctx *ctx);
 const char *jl_version(void);
 int jl_sync(jl_ctx *ctx);
 /* number of kernels this library launched since jl_init (bench.py's gpu_launches claim) */
