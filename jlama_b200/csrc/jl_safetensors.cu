@@ -433,6 +433,15 @@ static std::string json_escape(const std::string &s) {
 extern "C" int jl_st_write(const char *path, int n, const char *const *names, const int *dtypes, const int *ndims, const int64_t *shapes4,
                            const void *const *data, const int64_t *nbytes, int n_meta, const char *const *meta_kv) {
     if (!path || n < 0 || (n && (!names || !dtypes || !ndims || !shapes4 || !data || !nbytes))) return JL_ERR_INVALID;
+    for (int i = 0; i < n; i++) {
+        if (!names[i] || ndims[i] < 0 || ndims[i] > 4 || nbytes[i] < 0 || (nbytes[i] > 0 && !data[i]))
+            return st_fail("st_write: tensor " + std::to_string(i) + " has a null name / data pointer, more than 4 dims or a negative size");
+        for (int k = 0; k < ndims[i]; k++)
+            if (shapes4[(size_t)i * 4 + k] < 0) return st_fail(std::string("st_write: negative dimension in ") + names[i]);
+    }
+    if (n_meta < 0 || (n_meta > 0 && !meta_kv)) return st_fail("st_write: metadata count without metadata");
+    for (int i = 0; i < 2 * n_meta; i++)
+        if (!meta_kv[i]) return st_fail("st_write: null metadata string");
     std::string h = "{";
     uint64_t off = 0;
     for (int i = 0; i < n; i++) {

@@ -197,3 +197,25 @@ def test_config_json_mixtral_fields(tmp_path):
     (tmp_path / "broken.json").write_text("{\"hidden_size\": 12")
     with pytest.raises(sio.SafeTensorsError):
         sio.config_from_json(str(tmp_path / "broken.json"))
+
+
+def test_writer_rejects_descriptions_it_cannot_write(tmp_path):
+    import ctypes as C
+    lib = native.load()
+    a = np.zeros(4, np.float32)
+
+    def write(ndim=1, nbytes=16, shape=(4, 0, 0, 0), name=b"t", data=a.ctypes.data):
+        names = (C.c_char_p * 1)(name)
+        return lib.jl_st_write(os.fsencode(str(tmp_path / "w.safetensors")), 1, names, (C.c_int * 1)(native.F32), (C.c_int * 1)(ndim),
+                               (C.c_int64 * 4)(*shape), (C.c_void_p * 1)(data), (C.c_int64 * 1)(nbytes), 0, None)
+
+    assert write() == 0
+    with sio.SafeTensors(str(tmp_path / "w.safetensors")) as st:
+        assert st.info("t")["shape"] == (4,)
+    for kw in (dict(ndim=5), dict(ndim=-1), dict(nbytes=-16), dict(shape=(-4, 0, 0, 0)), dict(name=None), dict(data=None)):
+        assert write(**kw) == native.JL_ERR_INVALID, kw
+        assert b"st_write" in lib.jl_st_last_error()
+    # a file this writer produced with a shape that does not match its bytes is refused by the reader, not by luck of the writer
+    assert write(nbytes=8) == 0
+    with pytest.raises(sio.SafeTensorsError, match="does not match"):
+        sio.SafeTensors(str(tmp_path / "w.safetensors"))
