@@ -219,3 +219,21 @@ def test_writer_rejects_descriptions_it_cannot_write(tmp_path):
     assert write(nbytes=8) == 0
     with pytest.raises(sio.SafeTensorsError, match="does not match"):
         sio.SafeTensors(str(tmp_path / "w.safetensors"))
+
+
+def test_config_json_head_dim_and_linear_rope_scaling(tmp_path):
+    """MistralConfig / LlamaConfig: `head_dim` overrides hidden_size / heads (Config.java:254); only rope_type "linear" scales the table
+    (LlamaConfig.java:55-56).  MistralModel extends LlamaModel without overriding anything, so a Mistral checkpoint is this path."""
+    base = {"hidden_size": 4096, "intermediate_size": 14336, "num_attention_heads": 32, "num_key_value_heads": 8, "num_hidden_layers": 32,
+            "vocab_size": 32000, "max_position_embeddings": 32768, "rms_norm_eps": 1e-5, "rope_theta": 1000000.0}
+    p = tmp_path / "config.json"
+    p.write_text(json.dumps(dict(base, head_dim=96)))
+    mc = sio.config_from_json(str(p))
+    assert mc.head_size == 96 and mc.num_kv_heads == 8 and mc.rope_theta == 1000000.0 and mc.rope_scaling == 1.0
+    p.write_text(json.dumps(dict(base, rope_scaling={"rope_type": "linear", "factor": 4.0})))
+    assert sio.config_from_json(str(p)).rope_scaling == 4.0 and sio.config_from_json(str(p)).head_size == 128
+    p.write_text(json.dumps(dict(base, rope_scaling={"rope_type": "llama3", "factor": 8.0})))
+    assert sio.config_from_json(str(p)).rope_scaling == 1.0  # ignored by the reference, ignored here (SURVEY appendix C.4)
+    del base["num_key_value_heads"]
+    p.write_text(json.dumps(base))
+    assert sio.config_from_json(str(p)).num_kv_heads == 32  # multi-head attention when the key is absent
