@@ -170,7 +170,14 @@ extern "C" int jl_sched_free(jl_sched *s) {
     return JL_OK;
 }
 
-extern "C" const char *jl_sched_last_error(jl_sched *s) { return s ? s->last_error.c_str() : "null scheduler"; }
+// a copy the calling thread owns (the shared string is rewritten under `mu` by whichever thread fails next)
+extern "C" const char *jl_sched_last_error(jl_sched *s) {
+    static thread_local std::string mine;
+    if (!s) return "null scheduler";
+    std::lock_guard<std::mutex> lk(s->mu);
+    mine = s->last_error;
+    return mine.c_str();
+}
 
 extern "C" int64_t jl_sched_submit(jl_sched *s, const int32_t *prompt, int n_prompt, int max_new, const int32_t *stop_tokens,
                                    int n_stop, int flags, int64_t continue_request, float temperature, uint64_t seed) {

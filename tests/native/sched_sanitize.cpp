@@ -135,6 +135,7 @@ int main() {
                     kept.erase(kept.begin() + (long)k);
                 }
             }
+            if (it % 11 == 0) jl_sched_submit(s, nullptr, 0, 0, nullptr, 0, 0, -1, 0.0f, 0); // a rejected submit writes the error text
             const int n = 1 + (int)(rng() % 7);
             for (int i = 0; i < n; i++) m.prompt.push_back((int32_t)(rng() % VOCAB));
             m.max_new = 1 + (int)(rng() % 6);
@@ -182,6 +183,7 @@ int main() {
                 if (jl_sched_result(s, id, buf.data(), (int)buf.size(), &n, &state, &reason) != JL_OK) continue;
                 jl_sched_request_info_t info;
                 jl_sched_request_info(s, id, &info);
+                if (jl_sched_last_error(s)[0] == 1) abort(); // reads the error text while other threads may be failing (bad submits)
                 if (state == JL_SCHED_FINISHED && reason != JL_FINISH_CANCELLED && !seen[id]) {
                     seen[id] = 1;
                     std::lock_guard<std::mutex> lk(meta_mu);
