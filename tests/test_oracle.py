@@ -65,6 +65,32 @@ def test_gemm_restatement_matches_reference_c_kernels(oracle, ref_kernels, M, N,
     assert abs(naive.sum() - r_q8.sum()) <= 0.01 * abs(naive.sum())
 
 
+@pytest.mark.parametrize("M,N,K", [(1, 320, 4096), (8, 320, 4096), (1, 320, 14336), (8, 160, 14336)])
+def test_gemm_restatement_matches_reference_c_kernels_at_the_8b_reduction_lengths(oracle, ref_kernels, M, N, K):
+    """The same pinning in the regime the benchmark runs in: K = 4096 (q/k/v/o, gate/up) and K = 14336 (down_proj) of Llama-3-8B, weights
+    N(0, 0.02^2) through the reference's Q4 quantiser, activations N(0, 1) through its Q8 quantiser.  The two differ by summation order
+    only; the float64 product of the dequantised operands bounds both."""
+    rng = np.random.default_rng(K + M)
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    w = (rng.standard_normal((N, K)) * 0.02).astype(np.float32)
+    bq, bs = oracle.quantize_q4(w)
+    aq, as_ = oracle.quantize_q8_act(a)
+    A8, Af, B = oracle.OTensor(oracle.I8, aq, as_), oracle.f32(a), oracle.OTensor(oracle.Q4, bq, bs)
+    oracle.use_reference_kernels(False)
+    r_q8, r_f32 = oracle.batch_dot(A8, B, 0, 0, K, 0, 0, N), oracle.batch_dot(Af, B, 0, 0, K, 0, 0, N)
+    oracle.use_reference_kernels(True)
+    q_q8, q_f32 = oracle.batch_dot(A8, B, 0, 0, K, 0, 0, N), oracle.batch_dot(Af, B, 0, 0, K, 0, 0, N)
+    oracle.use_reference_kernels(False)
+    assert not np.array_equal(r_f32, q_f32)  # two implementations really ran
+    assert np.abs(r_q8 - q_q8).max() <= 3e-6 * np.abs(q_q8).max()
+    assert np.abs(r_f32 - q_f32).max() <= 1e-5 * np.abs(q_f32).max()
+    wd = oracle.dequantize_q4(bq, bs).astype(np.float64)
+    exact_f32 = a.astype(np.float64) @ wd.T
+    exact_q8 = (aq.astype(np.float64).reshape(M, K // 32, 32) * as_.astype(np.float64)[:, :, None]).reshape(M, K) @ wd.T
+    for got, exact in ((r_f32, exact_f32), (q_f32, exact_f32), (r_q8, exact_q8), (q_q8, exact_q8)):
+        assert np.abs(got - exact).max() <= 1e-5 * np.abs(exact).max()
+
+
 def test_dense_f32_matches_reference_c_kernel(oracle, ref_kernels):
     rng = np.random.default_rng(5)
     a = rng.uniform(-1, 100, (5, 512)).astype(np.float32)
