@@ -122,15 +122,16 @@ def cpu_isa_flags():
     return set()
 
 
-def load_reference_kernels():
-    """dlopen the reference's own C kernels (oracle/_ref).  Returns a label or None."""
+def load_reference_kernels(build=None):
+    """dlopen the reference's own C kernels (oracle/_ref).  Returns a label or None.  build: None = the widest this CPU runs,
+    "avx512" / "avx2" = that build only (the reference ships both code paths; their summation orders differ)."""
     fl = cpu_isa_flags()
     need512 = {"avx512f", "avx512bw", "avx512vl", "avx512dq", "avx512_vnni"}
     cands = []
-    if need512 <= fl:
+    if need512 <= fl and build in (None, "avx512"):
         # HAS_AVX2 selects the *_512 bodies (vector_simd.c:465-468)
         cands.append(("libjlama.so", HAS_F16C | HAS_AVX2, "jlama-native C kernels (AVX-512 VNNI build)"))
-    if "avx2" in fl and "fma" in fl:
+    if "avx2" in fl and "fma" in fl and build in (None, "avx2"):
         cands.append(("libjlama_avx2.so", HAS_F16C, "jlama-native C kernels (AVX2 build)"))
     for name, flags, label in cands:
         path = os.path.join(HERE, "_ref", name)

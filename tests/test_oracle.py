@@ -91,6 +91,39 @@ def test_gemm_restatement_matches_reference_c_kernels_at_the_8b_reduction_length
         assert np.abs(got - exact).max() <= 1e-5 * np.abs(exact).max()
 
 
+def test_both_reference_builds_bracket_the_restatement(oracle, ref_kernels):
+    """The reference ships 256-bit and 512-bit bodies of every kernel (vector_simd.c:465-468); they sum in different orders, so they
+    differ from each other by as much as either differs from the restatement -- the yardstick for every "matches the reference" bar."""
+    labels = {}
+    for build in ("avx512", "avx2"):
+        lab = oracle.load_reference_kernels(build)
+        if lab is not None:
+            labels[build] = lab
+    if len(labels) < 2:
+        oracle.load_reference_kernels()
+        pytest.skip("this CPU runs only one of the reference's builds")
+    M, N, K = 4, 320, 4096
+    rng = np.random.default_rng(77)
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    bq, bs = oracle.quantize_q4((rng.standard_normal((N, K)) * 0.02).astype(np.float32))
+    aq, as_ = oracle.quantize_q8_act(a)
+    A8, B = oracle.OTensor(oracle.I8, aq, as_), oracle.OTensor(oracle.Q4, bq, bs)
+    out = {}
+    for build in ("avx512", "avx2"):
+        oracle.load_reference_kernels(build)
+        oracle.use_reference_kernels(True)
+        out[build] = (oracle.batch_dot(A8, B, 0, 0, K, 0, 0, N), oracle.batch_dot(oracle.f32(a), B, 0, 0, K, 0, 0, N))
+    oracle.use_reference_kernels(False)
+    port = (oracle.batch_dot(A8, B, 0, 0, K, 0, 0, N), oracle.batch_dot(oracle.f32(a), B, 0, 0, K, 0, 0, N))
+    oracle.load_reference_kernels()  # back to the default build for the tests that follow
+    for i, bar in ((0, 3e-6), (1, 1e-5)):
+        scale = np.abs(port[i]).max()
+        d_builds = np.abs(out["avx512"][i] - out["avx2"][i]).max() / scale
+        d_port = max(np.abs(out[b][i] - port[i]).max() / scale for b in out)
+        assert d_builds <= bar and d_port <= bar
+        assert d_builds > 0  # the two builds are not bit-identical: bit-exactness against "the reference" is not defined for these sums
+
+
 def test_dense_f32_matches_reference_c_kernel(oracle, ref_kernels):
     rng = np.random.default_rng(5)
     a = rng.uniform(-1, 100, (5, 512)).astype(np.float32)
